@@ -1,0 +1,240 @@
+#!/usr/bin/env python
+"""Generate tests/golden/* by running the UNMODIFIED reference (test infrastructure).
+
+Run in the build container only (needs /root/reference):
+
+    python oracle/gen_golden.py
+
+For every case it stores the INPUT (upper-triangle stored cells, as .npz -- parsed
+data, not reference source) and the reference's OUTPUTS (bads dicts, biases, printed
+ICE trace, normalised sum, expected dict) as .json.  Cases:
+
+* the reference's own 12 fixtures test/{20,40,80}Kb/chrT/chrT_{A,B,C,D}.tsv
+  (the inputs behind the pinned values at test/test_all.py:332,400-402);
+* seeded synthetic matrices that exercise the parity traps of SURVEY.md 8(a'):
+  several chromosomes, low-coverage and empty bins, stored zeros, rows that touch
+  only bad bins, min_count mode on a symmetricized matrix, all-bad failure.
+"""
+import contextlib
+import io
+import json
+import os
+import sys
+from collections import OrderedDict
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shim  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+ICE_CONFIGS = [
+    # (iterations, max_dev, sqrt, factor)
+    (0, 0.1, False, 1),          # method defaults: "Vanilla" single pass
+    (100, 1e-5, False, 1),       # SURVEY golden setting
+    (3, 1e-9, False, 1),         # iteration-capped
+    (100, 1e-6, False, None),    # CLI setting, no rescale
+    (10, 1e-3, True, 2),         # sqrt before factor
+]
+
+
+def synth_dense(rng, sizes, a=4000.0, trans=0.6, low_frac=0.06, empty_frac=0.02,
+                alpha=1.08):
+    """Poisson counts with per-bin visibility, power-law cis decay, flat trans."""
+    n = int(sum(sizes))
+    vis = rng.lognormal(0.0, 0.35, n)
+    low = rng.random(n) < low_frac
+    vis[low] *= 0.02
+    empty = rng.random(n) < empty_frac
+    vis[empty] = 0.0
+    chrom = np.repeat(np.arange(len(sizes)), sizes)
+    i, j = np.triu_indices(n)
+    lam = np.where(chrom[i] == chrom[j],
+                   a * (np.abs(i - j) + 1.0) ** -alpha, trans) * vis[i] * vis[j]
+    v = rng.poisson(lam)
+    keep = v > 0
+    return n, i[keep], j[keep], v[keep].astype(np.int64)
+
+
+def synth_sparse(rng, n, per_row=12):
+    """Few contacts per row so that the zero-count filter flags many bins."""
+    rows, cols = [], []
+    for i in range(n):
+        k = rng.integers(0, 2 * per_row) if i % 7 else rng.integers(0, 3)
+        off = np.unique(np.minimum(rng.geometric(0.02, k) - 1, n - 1 - i))
+        rows.append(np.full(off.size, i))
+        cols.append(i + off)
+    r = np.concatenate(rows)
+    c = np.concatenate(cols)
+    v = 1 + rng.geometric(0.4, r.size)
+    return n, r, c, v.astype(np.int64)
+
+
+def build_reference(ns, n, r, c, v, chrom_sizes=None, names=None, symmetricized=False):
+    dico = {}
+    for a, b, x in zip(r.tolist(), c.tolist(), v.tolist()):
+        dico[a * n + b] = x
+        dico[b * n + a] = x
+    chromosomes = sections = None
+    if chrom_sizes is not None:
+        chromosomes = OrderedDict(zip(names, [int(s) for s in chrom_sizes]))
+        sections, idx = {}, 0
+        for name in chromosomes:
+            for p in range(chromosomes[name]):
+                sections[(name, p)] = idx
+                idx += 1
+    else:
+        sections = {}
+    return ns.HiC_data(dico, n, chromosomes=chromosomes, dict_sec=sections,
+                       symmetricized=symmetricized)
+
+
+def upper_store(hic):
+    n = len(hic)
+    keys = np.fromiter(dict.keys(hic), dtype=np.int64, count=dict.__len__(hic))
+    vals = np.array([dict.__getitem__(hic, int(k)) for k in keys])
+    i, j = np.divmod(keys, n)
+    keep = i <= j
+    order = np.argsort(keys[keep])
+    return i[keep][order], j[keep][order], vals[keep][order]
+
+
+def jsonable_bads(bads):
+    return OrderedDict((str(k), (True if bads[k] is True else int(bads[k])))
+                       for k in sorted(bads))
+
+
+def run_case(ns, name, hic, ice_configs=ICE_CONFIGS, filter_kw=None, extra=None):
+    print("case", name, file=sys.stderr)
+    n = len(hic)
+    r, c, v = upper_store(hic)
+    chroms = list(hic.chromosomes.items()) if hic.chromosomes else None
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), size=n, rows=r.astype(np.int32),
+                        cols=c.astype(np.int32), vals=v)
+    out = OrderedDict(name=name, size=n, nnz_upper=int(r.size), chromosomes=chroms,
+                      symmetricized=bool(hic.symmetricized))
+    # --- filters --------------------------------------------------------
+    out["zero_count_99"] = jsonable_bads(ns.filter_by_zero_count(hic, 99))
+    out["zero_count_75"] = jsonable_bads(ns.filter_by_zero_count(hic, 75))
+    mc = int(np.percentile(np.bincount(np.concatenate([r, c[r != c]]),
+                                       weights=np.concatenate([v, v[r != c]]),
+                                       minlength=n), 20)) + 1
+    with contextlib.redirect_stderr(io.StringIO()):
+        out["min_count"] = dict(min_count=mc,
+                                bads=jsonable_bads(ns.filter_by_zero_count(hic, 99, min_count=mc)))
+    hic.bads = {}
+    hic.filter_columns(silent=True, **(filter_kw or {}))
+    out["filter_kw"] = filter_kw or {}
+    out["filter_columns"] = jsonable_bads(hic.bads)
+    bads = dict(hic.bads)
+    # --- ICE ------------------------------------------------------------
+    out["ice"] = []
+    for iterations, max_dev, sqrt, factor in ice_configs:
+        hic.bads = dict(bads)
+        buf = io.StringIO()
+        rec = OrderedDict(iterations=iterations, max_dev=max_dev, sqrt=sqrt, factor=factor)
+        try:
+            with contextlib.redirect_stdout(buf):
+                hic.normalize_hic(iterations=iterations, max_dev=max_dev, silent=False,
+                                  sqrt=sqrt, factor=factor)
+            rec["bias"] = [float(hic.bias[i]) for i in range(n)]
+            rec["stdout"] = buf.getvalue()
+        except ZeroDivisionError as e:
+            rec["raises"] = "ZeroDivisionError"
+            rec["message"] = str(e)
+        out["ice"].append(rec)
+    # raw sum and normalised sum with the last successful bias
+    hic.bads = dict(bads)
+    out["raw_sum"] = int(hic.sum())
+    # --- expected -------------------------------------------------------
+    out["expected"] = []
+    for kw in ({}, {"inter_chrom": True}, {"signal_to_noise": 0.02}):
+        hic.bads = dict(bads)
+        hic.normalize_expected(**kw)
+        out["expected"].append(OrderedDict(
+            kw=kw, keys=len(hic.expected),
+            values=[[int(d), float(hic.expected[d])] for d in sorted(hic.expected)]))
+    if extra:
+        out.update(extra)
+    with open(os.path.join(OUT, name + ".json"), "w") as fh:
+        json.dump(out, fh)
+    return out
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ns = ref_shim.load()
+    index = []
+    # 1. the reference's own fixtures
+    for reso in ("20Kb", "40Kb", "80Kb"):
+        for rep in "ABCD":
+            path = os.path.join(ns.root, "test", reso, "chrT", "chrT_%s.tsv" % rep)
+            with contextlib.redirect_stderr(io.StringIO()):
+                hic = ns.read_matrix(path)
+            hic = hic[0] if isinstance(hic, list) else hic
+            name = "chrT_%s_%s" % (reso, rep)
+            run_case(ns, name, hic)
+            index.append(name)
+    # 2. synthetic, seeded
+    rng = np.random.default_rng(20261019)
+    sizes = [120, 80, 50]
+    n, r, c, v = synth_dense(rng, sizes)
+    run_case(ns, "synth_3chrom", build_reference(ns, n, r, c, v, sizes, ["c1", "c2", "c3"]))
+    index.append("synth_3chrom")
+
+    n, r, c, v = synth_dense(rng, [400], a=900.0, low_frac=0.1, empty_frac=0.03)
+    run_case(ns, "synth_1chrom_400", build_reference(ns, n, r, c, v))
+    index.append("synth_1chrom_400")
+
+    n, r, c, v = synth_sparse(rng, 600)
+    run_case(ns, "synth_sparse_600", build_reference(ns, n, r, c, v, [350, 250], ["a", "b"]),
+             filter_kw={"perc_zero": 97})
+    index.append("synth_sparse_600")
+
+    # a low-coverage tail that only the polynomial-fit filter can see
+    n = 500
+    vis = rng.lognormal(0.0, 0.25, n)
+    tail = rng.random(n) < 0.08
+    vis[tail] *= rng.uniform(0.05, 0.35, int(tail.sum()))
+    i, j = np.triu_indices(n)
+    v = rng.poisson(600.0 * (np.abs(i - j) + 1.0) ** -0.9 * vis[i] * vis[j])
+    keep = v > 0
+    run_case(ns, "synth_lowtail_500",
+             build_reference(ns, n, i[keep], j[keep], v[keep].astype(np.int64)),
+             ice_configs=[(0, 0.1, False, 1), (100, 1e-5, False, 1), (100, 1e-6, False, None)])
+    index.append("synth_lowtail_500")
+
+    # stored zeros: row 5 holds only explicit zero cells; row 9 only touches row 5
+    n, r, c, v = synth_dense(rng, [60], a=300.0, low_frac=0.0, empty_frac=0.0)
+    keep = (r != 5) & (c != 5)
+    r, c, v = r[keep], c[keep], v[keep]
+    r = np.concatenate([r, [5, 5, 3]])
+    c = np.concatenate([c, [5, 11, 5]])
+    v = np.concatenate([v, [0, 0, 0]])
+    hic = build_reference(ns, n, r, c, v)
+    run_case(ns, "stored_zero_60", hic, filter_kw={"by_mean": False},
+             ice_configs=[(0, 0.1, False, 1), (6, 1e-5, False, 1), (4, 1e-5, True, None)])
+    index.append("stored_zero_60")
+
+    # symmetricized flag (min_count doubling) + rows touching only bad bins
+    n, r, c, v = synth_dense(rng, [90, 40], a=500.0, low_frac=0.15, empty_frac=0.05)
+    hic = build_reference(ns, n, r, c, v, [90, 40], ["x", "y"], symmetricized=True)
+    run_case(ns, "synth_symmetricized", hic)
+    index.append("synth_symmetricized")
+
+    # all-bad failure: every bin flagged by a harsh zero-count filter
+    n, r, c, v = synth_sparse(rng, 80, per_row=2)
+    hic = build_reference(ns, n, r, c, v)
+    run_case(ns, "all_bad_80", hic, filter_kw={"perc_zero": 1, "by_mean": False},
+             ice_configs=[(0, 0.1, False, 1), (10, 1e-5, False, 1)])
+    index.append("all_bad_80")
+
+    with open(os.path.join(OUT, "INDEX.json"), "w") as fh:
+        json.dump(dict(cases=index, numpy=np.__version__,
+                       generator="oracle/gen_golden.py", reference="TADbit v1.1 (unmodified, via oracle/ref_shim.py)"), fh, indent=1)
+
+
+if __name__ == "__main__":
+    main()

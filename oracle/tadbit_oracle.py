@@ -1,0 +1,382 @@
+"""CPU ORACLE -- test infrastructure, NOT product code.
+
+A numpy/scipy restatement of the TADbit Hi-C balancing hot path, written from the
+behaviour of the reference (citations are ``path:line`` under the reference root):
+
+* ``filter_by_zero_count``  <- _pytadbit/utils/hic_filtering.py:173-222
+* ``filter_by_mean``        <- _pytadbit/utils/hic_filtering.py:19-170
+* ``iterative`` (ICE)       <- _pytadbit/utils/normalize_hic.py:136-231
+* ``expected``/``_meandiag``<- _pytadbit/utils/normalize_hic.py:234-291
+* ``matrix_sum``            <- _pytadbit/hic_data.py:350-375
+* ``filter_columns``        <- _pytadbit/hic_data.py:318-348
+* ``normalize_hic``         <- _pytadbit/hic_data.py:380-413
+
+Parity is PINNED: ``oracle/gen_golden.py`` runs the unmodified reference (through
+``oracle/ref_shim.py``) on the reference's own 12 chrT fixtures and on seeded
+synthetic matrices, and ``tests/test_oracle_golden.py`` checks this module against
+those committed vectors (``tests/golden/*.json``), including the values pinned by
+the reference's own tests (test/test_all.py:332,400-402 feed from mask {22: 48}).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` legs may import this module.  The product package
+``tadbit_b200`` never does.
+
+Storage model: the reference keeps BOTH triangles in a dict keyed ``row*N+col``
+(hic_data.py:54-118).  Here a matrix is the set of stored upper-triangle cells
+(i <= j) as three arrays; every reference sum is re-expressed over that store
+(SURVEY.md section 8 a', trap 1).
+"""
+from collections import OrderedDict
+from sys import stderr
+
+import numpy as np
+from scipy import sparse
+
+
+class OracleMatrix(object):
+    """Upper-triangle store of a symmetric Hi-C matrix (stored cells only).
+
+    ``chromosomes``: OrderedDict name -> number of bins, or None.  When None the
+    matrix behaves as one section spanning [0, N) (hic_data.py:70-78 with
+    ``sections == {}``, and the no-section branch normalize_hic.py:279-283).
+    """
+
+    def __init__(self, size, rows, cols, vals, chromosomes=None,
+                 symmetricized=False):
+        rows = np.asarray(rows, dtype=np.int64)
+        cols = np.asarray(cols, dtype=np.int64)
+        vals = np.asarray(vals)
+        if np.any(rows > cols):
+            raise ValueError("upper-triangle store needs row <= col")
+        key = rows * size + cols
+        order = np.argsort(key, kind="stable")
+        key = key[order]
+        if key.size and np.any(key[1:] == key[:-1]):
+            raise ValueError("duplicate cells")
+        self.size = int(size)
+        self.rows = rows[order]
+        self.cols = cols[order]
+        self.vals = vals[order]
+        self.chromosomes = chromosomes
+        self.symmetricized = symmetricized
+        if chromosomes:
+            pos, total = OrderedDict(), 0
+            for crm in chromosomes:
+                pos[crm] = (total, total + chromosomes[crm])
+                total += chromosomes[crm]
+            self.section_pos = pos
+        else:
+            self.section_pos = OrderedDict([(None, (0, self.size))])
+
+    # -- constructors -----------------------------------------------------
+    @classmethod
+    def from_full_dict(cls, dico, size, **kw):
+        """From a reference-style dict ``{row*N+col: v}`` holding both triangles."""
+        keys = np.fromiter(dico.keys(), dtype=np.int64, count=len(dico))
+        vals = np.array([dico[k] for k in keys.tolist()])
+        i, j = np.divmod(keys, size)
+        keep = i <= j
+        return cls(size, i[keep], j[keep], vals[keep], **kw)
+
+    @classmethod
+    def from_dense(cls, mat, **kw):
+        mat = np.asarray(mat)
+        iu = np.triu_indices(mat.shape[0])
+        v = mat[iu]
+        keep = v != 0
+        return cls(mat.shape[0], iu[0][keep], iu[1][keep], v[keep], **kw)
+
+    # -- helpers ----------------------------------------------------------
+    def offdiag(self):
+        return self.rows != self.cols
+
+    def full_csr(self, keep=None, dtype=np.float64):
+        """Both triangles (diagonal once) as scipy CSR, optionally masked."""
+        r, c, v = self.rows, self.cols, self.vals.astype(dtype)
+        if keep is not None:
+            r, c, v = r[keep], c[keep], v[keep]
+        od = r != c
+        rr = np.concatenate([r, c[od]])
+        cc = np.concatenate([c, r[od]])
+        vv = np.concatenate([v, v[od]])
+        return sparse.csr_matrix((vv, (rr, cc)), shape=(self.size, self.size))
+
+
+def _bad_mask(size, bads):
+    mask = np.zeros(size, dtype=bool)
+    if bads:
+        idx = np.fromiter((int(b) for b in bads), dtype=np.int64, count=len(bads))
+        idx = idx[(idx >= 0) & (idx < size)]
+        mask[idx] = True
+    return mask
+
+
+def row_stats(m):
+    """(stored cells per full row, full row sums) -- exact integers.
+
+    hic_filtering.py:187-190 (``cols[k // size] -= 1`` for every stored key) and
+    :198-200 (``cols[k // size] += v``) over the both-triangle dict."""
+    od = m.offdiag()
+    nnz = np.bincount(m.rows, minlength=m.size).astype(np.int64)
+    nnz += np.bincount(m.cols[od], minlength=m.size)
+    if np.issubdtype(m.vals.dtype, np.integer):
+        v = m.vals.astype(np.int64)
+        rsum = np.zeros(m.size, dtype=np.int64)
+        np.add.at(rsum, m.rows, v)
+        np.add.at(rsum, m.cols[od], v[od])
+    else:
+        rsum = np.bincount(m.rows, weights=m.vals, minlength=m.size)
+        rsum += np.bincount(m.cols[od], weights=m.vals[od], minlength=m.size)
+    return nnz, rsum
+
+
+def masked_col_sums(m, bad):
+    """Column sums over rows NOT in ``bad`` (exact int64), for every column."""
+    od = m.offdiag()
+    v = m.vals.astype(np.int64)
+    out = np.zeros(m.size, dtype=np.int64)
+    k1 = ~bad[m.rows]                      # cell (i,j) adds to column j if row i good
+    np.add.at(out, m.cols[k1], v[k1])
+    k2 = od & ~bad[m.cols]                 # mirror cell (j,i) adds to column i if row j good
+    np.add.at(out, m.rows[k2], v[k2])
+    return out
+
+
+# --------------------------------------------------------------------------
+# filters
+# --------------------------------------------------------------------------
+def filter_by_zero_count(m, perc_zero, min_count=None, silent=True):
+    """hic_filtering.py:173-222."""
+    size = m.size
+    nnz, rsum = row_stats(m)
+    if min_count is None:
+        min_val = int(size * float(perc_zero) / 100)
+        flagged = (size - nnz) > min_val                       # :189-191,203
+    else:
+        if m.symmetricized:                                    # :193-197
+            if not silent:
+                stderr.write('\nWARNING: Using twice min_count as the matrix was '
+                             'symmetricized and contains twice as many '
+                             'interactions as the original\n')
+            min_count *= 2
+        flagged = rsum < min_count                             # :205
+    return dict((int(i), True) for i in np.nonzero(flagged)[0])
+
+
+def _r2_swapped(poly, counts, edges):
+    # get_r2(p, x, y) is called with the counts as X and the bin edges as Y
+    # (hic_filtering.py:19-22 vs :94).  Sequential python sums, as there.
+    mean_y = np.mean(edges)
+    sstot = sum([(edges[i] - mean_y) ** 2 for i in range(len(edges))])
+    sserr = sum([(edges[i] - poly(counts[i])) ** 2 for i in range(len(edges))])
+    return 1 - sserr / sstot
+
+
+def _hundred_bins(cols, nbins):
+    edges = np.linspace(min(cols), max(cols), nbins)
+    which = np.digitize(cols, edges)
+    counts = [sum(which == i) for i in range(1, nbins + 1)]
+    return edges, counts
+
+
+def mean_filter_cutoff(cols, nbins=100):
+    """The <=100-point numpy tail of filter_by_mean (hic_filtering.py:43-99).
+
+    ``cols``: ascending column sums of the good sub-matrix.  Returns the chosen
+    root, or raises ValueError("few") / LookupError("none") for the two failure
+    exits (:164-167 and :153-156)."""
+    percentile = np.percentile(cols, 5)
+    edges, counts = _hundred_bins(cols, nbins)
+    dropped = 0
+    while list(counts).count(0) > len(counts) / 2:
+        dropped += 1
+        cols = cols[:-1]
+        edges, counts = _hundred_bins(cols, nbins)
+        if dropped > 10000:
+            raise ValueError("few")
+    best_r2, best_root = float('-inf'), None
+    for order in range(6, 18):
+        z = np.polyfit(edges, counts, order)
+        dz = np.polyder(z, m=1)
+        roots = np.roots(np.polyder(z))
+        slope = np.polyval(dz, abs(roots[-2] - roots[-1]) / 2 + roots[-1])
+        root = roots[-1] if slope > 0 else roots[-2]
+        if root <= 0:
+            continue
+        if root >= percentile:
+            continue
+        r2 = _r2_swapped(np.poly1d(z), counts, edges)
+        if order > 13:
+            r2 -= float(order) / 30
+        if best_r2 < r2:
+            best_r2, best_root = r2, root
+    if best_root is None:
+        raise LookupError("none")
+    return best_root
+
+
+def filter_by_mean(m, bads=None, silent=True):
+    """hic_filtering.py:25-170 (draw_hist=False path)."""
+    if not bads:
+        bads = {}
+    bad = _bad_mask(m.size, bads)
+    good_sums = masked_col_sums(m, bad)[~bad]                  # :36-39
+    cols = np.sort(good_sums)
+    try:
+        try:
+            root = mean_filter_cutoff(cols)
+        except IndexError:
+            if cols.size:
+                raise
+            return bads                                        # :45-47
+        except LookupError:
+            if not silent:
+                stderr.write('WARNING: Too many zeroes to filter columns.'
+                             ' SKIPPING...\n')
+            return bads
+        all_sums = masked_col_sums(m, np.zeros(m.size, dtype=bool))
+        for i in np.nonzero(all_sums < root)[0]:               # :141-145
+            bads[int(i)] = int(all_sums[i])
+    except ValueError:
+        if not silent:
+            stderr.write('WARNING: Too few data to filter columns based on '
+                         'mean value.\n')
+    return bads
+
+
+def filter_columns(m, perc_zero=99, by_mean=True, min_count=None, silent=True):
+    """hic_data.py:318-348; returns the new ``bads`` dict."""
+    bads = filter_by_zero_count(m, perc_zero, min_count=min_count, silent=silent)
+    if by_mean:
+        bads.update(filter_by_mean(m, bads=bads, silent=silent))
+    return bads
+
+
+# --------------------------------------------------------------------------
+# ICE
+# --------------------------------------------------------------------------
+def iterative(m, bads=None, iterations=0, max_dev=0.00001):
+    """normalize_hic.py:180-231 in the non-mutating form S = x * (W0 x), x = 1/B.
+
+    Returns (bias[N] float64, trace) where trace rows are
+    (Smin, meanS, Smax, it, dev) exactly as printed at :219-220."""
+    size = m.size
+    bad = _bad_mask(size, bads)
+    keep = ~(bad[m.rows] | bad[m.cols])                        # copy_matrix :165-177
+    w0 = m.full_csr(keep)
+    present = np.zeros(size, dtype=bool)
+    present[m.rows[keep]] = True
+    present[m.cols[keep]] = True
+    npresent = int(present.sum())
+    if npresent == 0:
+        raise ZeroDivisionError('ERROR: normalization failed, all bad columns')
+    b = np.ones(size)
+    x = np.where(present, 1.0, 0.0)
+    trace = []
+    mean_s = 0.0
+    for it in range(iterations + 1):
+        s = x * (w0 @ x)                                       # _update_S :136-143
+        mean_s = s[present].sum() / npresent
+        db = s / mean_s                                        # _updateDB :146-151
+        b[present] *= db[present]
+        if iterations == 0:
+            break
+        with np.errstate(divide='ignore'):
+            x = np.where(present & (b != 0), 1.0 / b, 0.0)     # _update_W :154-162
+        smin, smax = s[present].min(), s[present].max()
+        dev = max(abs(smin / mean_s - 1), abs(smax / mean_s - 1))
+        trace.append((smin, mean_s, smax, it, dev))
+        if dev < max_dev:
+            break
+    bias = np.ones(size)                                       # :223-230
+    ok = present & (b != 0)
+    bias[ok] = b[ok] * mean_s ** .5
+    return bias, trace
+
+
+def matrix_sum(m, bias=None, bads=None):
+    """hic_data.py:350-375 -- both triangles, diagonal once."""
+    bad = _bad_mask(m.size, bads)
+    keep = ~(bad[m.rows] | bad[m.cols])
+    r, c, v = m.rows[keep], m.cols[keep], m.vals[keep]
+    w = np.where(r == c, 1, 2)
+    if bias is None:
+        return (v * w).sum()
+    bias = np.asarray(bias, dtype=np.float64)
+    return float(((v / (bias[r] * bias[c])) * w).sum())
+
+
+def normalize_hic(m, bads=None, iterations=0, max_dev=0.1, sqrt=False, factor=1):
+    """hic_data.py:380-413.  Returns (bias[N], trace, norm_sum or None)."""
+    bias, trace = iterative(m, bads=bads, iterations=iterations, max_dev=max_dev)
+    if sqrt:
+        bias = bias ** 0.5
+    norm_sum = None
+    if factor:
+        norm_sum = matrix_sum(m, bias, bads)
+        target = (norm_sum / float(m.size * m.size * factor)) ** 0.5
+        bias = bias * target
+    return bias, trace, norm_sum
+
+
+# --------------------------------------------------------------------------
+# expected
+# --------------------------------------------------------------------------
+def diagonal_sums(m, bads, ndiag):
+    """Per-distance integer sums and valid-cell counts of _meandiag's cells
+    (normalize_hic.py:271-283): cell (i, i+d), i and i+d in the same section, only
+    the row index tested against bads.  Returns (sum_d, cnt_d) for d in [0, ndiag)."""
+    size = m.size
+    bad = _bad_mask(size, bads)
+    chrom_of = np.empty(size, dtype=np.int64)
+    for n, (beg, end) in enumerate(m.section_pos.values()):
+        chrom_of[beg:end] = n
+    d = m.cols - m.rows
+    keep = (~bad[m.rows]) & (chrom_of[m.rows] == chrom_of[m.cols]) & (d < ndiag)
+    if np.issubdtype(m.vals.dtype, np.integer):
+        sum_d = np.zeros(ndiag, dtype=np.int64)
+        np.add.at(sum_d, d[keep], m.vals[keep].astype(np.int64))
+    else:
+        sum_d = np.bincount(d[keep], weights=m.vals[keep], minlength=ndiag)
+    good_before = np.concatenate([[0], np.cumsum(~bad)])       # good rows in [0, k)
+    cnt_d = np.zeros(ndiag, dtype=np.int64)
+    for beg, end in m.section_pos.values():
+        span = min(end - beg, ndiag)
+        dd = np.arange(span)
+        cnt_d[:span] += good_before[end - dd] - good_before[beg]
+    return sum_d, cnt_d
+
+
+def pool_diagonals(sum_d, cnt_d, size, min_n):
+    """The pooling recursion of expected/_meandiag (normalize_hic.py:260-291), run
+    iteratively over precomputed per-distance sums/counts."""
+    expc = {}
+    dist = 0
+    ndiag = len(sum_d)
+    while dist < size:
+        tot, cnt, d = 0, 0, dist
+        while True:
+            if d < ndiag:
+                tot += sum_d[d]
+                cnt += cnt_d[d]
+            if not cnt:
+                new_dist, val = d + 1, 0.
+                break
+            if tot > min_n or d >= size:
+                new_dist, val = d + 1, float(tot) / int(cnt)
+                break
+            d += 1
+        for dist in range(dist, new_dist + 1):
+            expc[dist] = val
+    return expc
+
+
+def expected(m, bads=None, signal_to_noise=0.05, inter_chrom=False):
+    """normalize_hic.py:234-268."""
+    min_n = signal_to_noise ** -2.
+    size = m.size
+    if m.chromosomes and not inter_chrom:
+        size = max(m.chromosomes.values())
+    sum_d, cnt_d = diagonal_sums(m, bads or {}, size)
+    sum_d = [int(s) for s in sum_d] if sum_d.dtype.kind == 'i' else list(sum_d)
+    return pool_diagonals(sum_d, cnt_d, size, min_n)
