@@ -1,0 +1,182 @@
+/*
+ * tadbit_b200 -- C-ABI of the B200-native Hi-C matrix-balancing hot path.
+ *
+ * Drop-in boundary for ONE path of 3DGenomes/TADbit: filter_columns -> ICE
+ * (normalize_hic) -> per-diagonal expected.  The reference has no FFI for this path
+ * (it is pure Python over a dict); each entry point below names the reference
+ * function it replaces (paths relative to the reference root).  The Python host class
+ * tadbit_b200.HiC_data binds these with ctypes (tadbit_b200/_capi.py) and keeps the
+ * reference's method signatures; INTEGRATION.md shows the stub a TADbit maintainer
+ * would add.
+ *
+ * Conventions
+ *   - every function returns a tb_status (0 = ok); tb_last_error() gives the text of
+ *     the last failure on the calling thread;
+ *   - plain pointers and sizes only.  Pointers named h_* are HOST memory, d_* are
+ *     DEVICE memory on the store's device, "mem" arguments say which (TB_MEM_*);
+ *   - the library never frees caller memory; a tb_store owns every device buffer it
+ *     allocates and releases them in tb_store_destroy;
+ *   - a tb_store is not thread-safe; calls block until their result is in the output
+ *     buffers (the store's private CUDA stream is synchronised before returning);
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *     TB_ERR_CUDA.
+ *
+ * Contact store.  A symmetric N x N integer matrix given as its stored upper-triangle
+ * cells (row <= col, each cell once; stored zeros allowed and counted as stored, as the
+ * reference's dict does -- _pytadbit/hic_data.py:54-118).  A store may own only a
+ * contiguous block of matrix rows [row_begin, row_end) (multi-GPU row sharding); it then
+ * keeps every cell of the FULL symmetric matrix whose row lies in the block.
+ */
+#ifndef TADBIT_B200_H
+#define TADBIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tb_store tb_store;
+
+typedef enum {
+  TB_OK = 0,
+  TB_ERR_ARG = 1,      /* bad argument (null pointer, row > col, out of range ...)        */
+  TB_ERR_CUDA = 2,     /* CUDA runtime failure or no device                               */
+  TB_ERR_ALL_BAD = 3,  /* ICE: no row left after masking (reference: ZeroDivisionError
+                          'ERROR: normalization failed, all bad columns',
+                          _pytadbit/utils/normalize_hic.py:207-208)                      */
+  TB_ERR_NCCL = 4,     /* NCCL failure / NCCL not loadable                                */
+  TB_ERR_STATE = 5     /* call not valid in this state (e.g. comm not initialised)        */
+} tb_status;
+
+enum { TB_MEM_HOST = 0, TB_MEM_DEVICE = 1 };
+
+/* ---- library ------------------------------------------------------------------- */
+int tb_version(void);
+const char *tb_last_error(void);
+int tb_device_count(int *count);
+
+/* ---- store construction -------------------------------------------------------- */
+/*
+ * Replaces building the dict (HiC_data.__init__, _pytadbit/hic_data.py:58-81) and the
+ * array export HiC_data.get_hic_data_as_csr (_pytadbit/hic_data.py:166-181).
+ *
+ * nbins        N, the matrix size (len(hic_data), hic_data.py:124)
+ * nnz          number of upper-triangle cells passed
+ * row,col,val  int32[nnz], row[k] <= col[k] < N, cells unique, any order
+ * mem          TB_MEM_HOST or TB_MEM_DEVICE for row/col/val
+ * n_chrom      number of sections (0 = one section [0,N): hic_data.py:76-78)
+ * chrom_offsets int64[n_chrom+1] HOST, bin offsets of the sections (section_pos,
+ *              hic_data.py:70-75); ignored when n_chrom == 0
+ * row_begin,row_end  block of full-matrix rows this store owns (0,N for one GPU)
+ * device       CUDA device ordinal
+ */
+int tb_store_create_coo(int64_t nbins, int64_t nnz, const int32_t *row, const int32_t *col,
+                        const int32_t *val, int mem, int32_t n_chrom,
+                        const int64_t *chrom_offsets, int64_t row_begin, int64_t row_end,
+                        int device, tb_store **out);
+
+/*
+ * Synthetic Hi-C matrix generated on the device (SURVEY.md 8d model): per-bin
+ * visibility b_i, cis mean a*b_i*b_j*(|i-j|+1)^-alpha, trans mean t*b_i*b_j, counts
+ * Poisson(mean) decided per CELL by a counter-based hash of (seed, min(i,j), max(i,j)),
+ * so the matrix does not depend on how rows are sharded.  Not in the reference (its
+ * test/simulate_genomic_matrix.py is unrelated); used by bench.py and the scale tests.
+ */
+typedef struct {
+  uint64_t seed;
+  double cis_scale;      /* a      */
+  double cis_alpha;      /* alpha  */
+  double trans_mean;     /* t      */
+  double vis_sigma;      /* sigma of log-normal visibility          */
+  double low_frac;       /* fraction of bins scaled by low_scale    */
+  double low_scale;
+  double empty_frac;     /* fraction of bins with zero visibility   */
+} tb_synth_params;
+
+int tb_store_create_synthetic(int64_t nbins, int32_t n_chrom, const int64_t *chrom_offsets,
+                              const tb_synth_params *params, int64_t row_begin,
+                              int64_t row_end, int device, tb_store **out);
+/* full-row stored-cell counts of rows [row_begin,row_end) of the synthetic matrix
+ * (int64[row_end-row_begin], HOST) without materialising it -- used to balance shards */
+int tb_synthetic_row_counts(int64_t nbins, int32_t n_chrom, const int64_t *chrom_offsets,
+                            const tb_synth_params *params, int64_t row_begin,
+                            int64_t row_end, int device, int64_t *h_counts);
+
+int tb_store_destroy(tb_store *s);
+
+/* nbins, owned row block, stored upper-triangle cells with row in the block (i<=j),
+ * stored full-matrix cells in the block, device bytes held */
+int tb_store_info(const tb_store *s, int64_t *nbins, int64_t *row_begin, int64_t *row_end,
+                  int64_t *nnz_upper_owned, int64_t *nnz_full_owned, int64_t *device_bytes);
+
+/* Export the owned upper-triangle cells (row in block, row <= col), row-major sorted.
+ * Call with row == NULL to get the count in *nnz first.  Buffers are HOST. */
+int tb_store_export_upper(const tb_store *s, int64_t *nnz, int32_t *h_row, int32_t *h_col,
+                          int32_t *h_val);
+
+/* ---- multi-GPU (one process per GPU) ------------------------------------------- */
+/* 128-byte NCCL unique id made on rank 0 and passed to every rank by the host
+ * (torch.distributed / MPI / files -- plumbing is the caller's). */
+int tb_comm_unique_id(uint8_t id_out[128]);
+int tb_comm_init(tb_store *s, int32_t rank, int32_t world, const uint8_t id[128]);
+
+/* ---- K4: filter statistics ----------------------------------------------------- */
+/*
+ * Replaces the two loops of filter_by_zero_count
+ * (_pytadbit/utils/hic_filtering.py:185-190 stored cells per row, :198-200 row sums).
+ * Outputs int64[N] HOST, exact; rows outside the owned block are all-reduced in when a
+ * communicator is set, otherwise left 0.
+ */
+int tb_row_stats(tb_store *s, int64_t *h_nnz_row, int64_t *h_row_sum);
+/*
+ * Replaces the O(N^2) column-sum list comprehensions of filter_by_mean
+ * (_pytadbit/utils/hic_filtering.py:36-39 with the bad rows excluded; :141-145 with
+ * h_bad == NULL, all rows).  h_bad: uint8[N] HOST (non-zero = bad) or NULL.
+ * h_col_sum: int64[N] HOST, sum over NON-bad rows of every column, exact.
+ */
+int tb_col_sums_masked(tb_store *s, const uint8_t *h_bad, int64_t *h_col_sum);
+
+/* ---- K1 + K2: ICE --------------------------------------------------------------- */
+/*
+ * Replaces iterative() incl. copy_matrix/_update_S/_updateDB/_update_W
+ * (_pytadbit/utils/normalize_hic.py:136-231).
+ *
+ * h_bad       uint8[N] HOST or NULL (bads dict as a mask)
+ * iterations  as the reference: at most iterations+1 passes; 0 = one pass, no test
+ * max_dev     stop when max(|Smin/meanS-1|,|Smax/meanS-1|) < max_dev
+ * h_bias      float64[N] HOST out: B_i*sqrt(meanS); 1.0 for rows not present or B_i==0
+ * h_trace     float64[(iterations+1)*4] HOST out or NULL: per pass Smin, meanS, Smax, dev
+ *             (the verbose line of normalize_hic.py:219-220)
+ * n_passes    passes executed (= trace lines; for iterations==0 it is 1 with no line)
+ * Returns TB_ERR_ALL_BAD when no row is present.
+ */
+int tb_ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev,
+           double *h_bias, double *h_trace, int32_t *n_passes);
+
+/* timing of the last tb_ice call, measured with CUDA events on the store's stream:
+ * total device ms of the pass loop, and the ms spent in the row-sum (K1) launches */
+int tb_ice_last_timing(const tb_store *s, double *loop_ms, double *rowsum_ms,
+                       int32_t *rowsum_launches, int32_t *total_launches);
+
+/* ---- K3: normalised sum ---------------------------------------------------------- */
+/*
+ * Replaces HiC_data.sum(bias, bads) (_pytadbit/hic_data.py:350-375): sum over BOTH
+ * triangles (diagonal once) of v/(bias_i*bias_j) for i,j not bad.  h_bias == NULL gives
+ * the raw sum.  Result is all-reduced when a communicator is set.
+ */
+int tb_norm_sum(tb_store *s, const double *h_bias, const uint8_t *h_bad, double *out);
+
+/* ---- K5: per-diagonal sums -------------------------------------------------------- */
+/*
+ * Replaces the cell loop of _meandiag (_pytadbit/utils/normalize_hic.py:271-283):
+ * h_sum_d[d] = sum of cells (i, i+d), i and i+d in the same section, i not bad, for
+ * d in [0, ndiag).  int64[ndiag] HOST, exact.  (Valid-cell counts are closed-form from
+ * the section lengths and the mask; the host computes them.)
+ */
+int tb_diag_sums(tb_store *s, const uint8_t *h_bad, int64_t ndiag, int64_t *h_sum_d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TADBIT_B200_H */

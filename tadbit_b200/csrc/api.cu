@@ -1,0 +1,289 @@
+// C-ABI of include/tadbit_b200.h: argument checks, exception -> status mapping.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <new>
+
+#include "common.cuh"
+
+namespace tb {
+
+static thread_local char g_error[1024] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+template <typename F>
+int guarded(F &&f) {
+  try {
+    return f();
+  } catch (const Fail &e) {
+    return e.code;
+  } catch (const std::bad_alloc &) {
+    set_error("host allocation failed");
+    return TB_ERR_ARG;
+  } catch (...) {
+    set_error("unexpected C++ exception");
+    return TB_ERR_ARG;
+  }
+}
+
+tb_store *new_store(int64_t nbins, int32_t n_chrom, const int64_t *chrom_offsets,
+                    int64_t row_begin, int64_t row_end, int device) {
+  TB_REQUIRE(nbins > 0 && nbins < 2147483647LL, "nbins must be in [1, 2^31)");
+  TB_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= nbins,
+             "row block [%lld,%lld) not inside [0,%lld)", (long long)row_begin,
+             (long long)row_end, (long long)nbins);
+  TB_REQUIRE(n_chrom >= 0, "n_chrom must be >= 0");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_error("no CUDA device available (%s); tadbit_b200 has no CPU fallback",
+              cudaGetErrorString(e));
+    throw Fail{TB_ERR_CUDA};
+  }
+  TB_REQUIRE(device >= 0 && device < count, "device %d out of range (%d devices)", device, count);
+  TB_CUDA(cudaSetDevice(device));
+  tb_store *s = new tb_store();
+  try {
+    s->device = device;
+    cudaDeviceProp prop;
+    TB_CUDA(cudaGetDeviceProperties(&prop, device));
+    s->sm_count = prop.multiProcessorCount;
+    TB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    s->nbins = nbins;
+    s->row_begin = row_begin;
+    s->row_end = row_end;
+    s->nrows = row_end - row_begin;
+    s->n_chrom = n_chrom;
+    if (n_chrom > 0) {
+      TB_REQUIRE(chrom_offsets, "chrom_offsets is null");
+      s->chrom_offsets.assign(chrom_offsets, chrom_offsets + n_chrom + 1);
+      TB_REQUIRE(s->chrom_offsets.front() == 0 && s->chrom_offsets.back() == nbins,
+                 "chrom_offsets must start at 0 and end at nbins");
+      for (int32_t c = 0; c < n_chrom; ++c)
+        TB_REQUIRE(s->chrom_offsets[c] <= s->chrom_offsets[c + 1], "chrom_offsets not ascending");
+    } else {
+      s->chrom_offsets = {0, nbins};
+    }
+    setup_sections(s);
+  } catch (...) {
+    tb_store_destroy(s);
+    throw;
+  }
+  return s;
+}
+
+struct DeviceGuard {          // every call runs on the store's device, then restores
+  int prev = 0;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    cudaSetDevice(dev);
+  }
+  ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+}  // namespace
+}  // namespace tb
+
+using namespace tb;
+
+extern "C" {
+
+int tb_version(void) { return 100; }
+
+const char *tb_last_error(void) { return g_error; }
+
+int tb_device_count(int *count) {
+  if (!count) return TB_ERR_ARG;
+  cudaError_t e = cudaGetDeviceCount(count);
+  if (e != cudaSuccess) {
+    *count = 0;
+    set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return TB_ERR_CUDA;
+  }
+  return TB_OK;
+}
+
+int tb_store_create_coo(int64_t nbins, int64_t nnz, const int32_t *row, const int32_t *col,
+                        const int32_t *val, int mem, int32_t n_chrom,
+                        const int64_t *chrom_offsets, int64_t row_begin, int64_t row_end,
+                        int device, tb_store **out) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(out, "out is null");
+    *out = nullptr;
+    TB_REQUIRE(nnz >= 0 && (nnz == 0 || (row && col && val)), "null cell arrays");
+    TB_REQUIRE(mem == TB_MEM_HOST || mem == TB_MEM_DEVICE, "mem must be TB_MEM_HOST/TB_MEM_DEVICE");
+    int prev = 0;
+    cudaGetDevice(&prev);
+    tb_store *s = new_store(nbins, n_chrom, chrom_offsets, row_begin, row_end, device);
+    try {
+      build_from_coo(s, nnz, row, col, val, mem);
+    } catch (...) {
+      tb_store_destroy(s);
+      cudaSetDevice(prev);
+      throw;
+    }
+    cudaSetDevice(prev);
+    *out = s;
+    return TB_OK;
+  });
+}
+
+int tb_store_create_synthetic(int64_t nbins, int32_t n_chrom, const int64_t *chrom_offsets,
+                              const tb_synth_params *params, int64_t row_begin,
+                              int64_t row_end, int device, tb_store **out) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(out && params, "null argument");
+    *out = nullptr;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    tb_store *s = new_store(nbins, n_chrom, chrom_offsets, row_begin, row_end, device);
+    try {
+      build_synthetic(s, params);
+    } catch (...) {
+      tb_store_destroy(s);
+      cudaSetDevice(prev);
+      throw;
+    }
+    cudaSetDevice(prev);
+    *out = s;
+    return TB_OK;
+  });
+}
+
+int tb_synthetic_row_counts(int64_t nbins, int32_t n_chrom, const int64_t *chrom_offsets,
+                            const tb_synth_params *params, int64_t row_begin,
+                            int64_t row_end, int device, int64_t *h_counts) {
+  return guarded([&]() -> int {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+      set_error("no CUDA device available; tadbit_b200 has no CPU fallback");
+      return TB_ERR_CUDA;
+    }
+    DeviceGuard g(device);
+    synthetic_row_counts(nbins, n_chrom, chrom_offsets, params, row_begin, row_end, device,
+                         h_counts);
+    return TB_OK;
+  });
+}
+
+int tb_store_destroy(tb_store *s) {
+  if (!s) return TB_OK;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(s->device);
+  try {
+    comm_destroy(s);
+  } catch (...) {
+  }
+  if (s->stream) {
+    cudaStreamSynchronize(s->stream);
+    cudaStreamDestroy(s->stream);
+  }
+  delete s;
+  cudaSetDevice(prev);
+  return TB_OK;
+}
+
+int tb_store_info(const tb_store *s, int64_t *nbins, int64_t *row_begin, int64_t *row_end,
+                  int64_t *nnz_upper_owned, int64_t *nnz_full_owned, int64_t *device_bytes) {
+  if (!s) { set_error("null store"); return TB_ERR_ARG; }
+  if (nbins) *nbins = s->nbins;
+  if (row_begin) *row_begin = s->row_begin;
+  if (row_end) *row_end = s->row_end;
+  if (nnz_upper_owned) *nnz_upper_owned = s->nnz_upper;
+  if (nnz_full_owned) *nnz_full_owned = s->nnz_full;
+  if (device_bytes) *device_bytes = s->device_bytes;
+  return TB_OK;
+}
+
+int tb_store_export_upper(const tb_store *s, int64_t *nnz, int32_t *h_row, int32_t *h_col,
+                          int32_t *h_val) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(s && nnz, "null argument");
+    DeviceGuard g(s->device);
+    export_upper(s, nnz, h_row, h_col, h_val);
+    return TB_OK;
+  });
+}
+
+int tb_comm_unique_id(uint8_t id_out[128]) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(id_out, "null argument");
+    comm_unique_id(id_out);
+    return TB_OK;
+  });
+}
+
+int tb_comm_init(tb_store *s, int32_t rank, int32_t world, const uint8_t id[128]) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(s && (world == 1 || id), "null argument");
+    DeviceGuard g(s->device);
+    comm_init(s, rank, world, id);
+    return TB_OK;
+  });
+}
+
+int tb_row_stats(tb_store *s, int64_t *h_nnz_row, int64_t *h_row_sum) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(s && h_nnz_row && h_row_sum, "null argument");
+    DeviceGuard g(s->device);
+    row_stats(s, h_nnz_row, h_row_sum);
+    return TB_OK;
+  });
+}
+
+int tb_col_sums_masked(tb_store *s, const uint8_t *h_bad, int64_t *h_col_sum) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(s && h_col_sum, "null argument");
+    DeviceGuard g(s->device);
+    col_sums_masked(s, h_bad, h_col_sum);
+    return TB_OK;
+  });
+}
+
+int tb_ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev,
+           double *h_bias, double *h_trace, int32_t *n_passes) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(s && h_bias, "null argument");
+    DeviceGuard g(s->device);
+    return ice(s, h_bad, iterations, max_dev, h_bias, h_trace, n_passes);
+  });
+}
+
+int tb_ice_last_timing(const tb_store *s, double *loop_ms, double *rowsum_ms,
+                       int32_t *rowsum_launches, int32_t *total_launches) {
+  if (!s) { set_error("null store"); return TB_ERR_ARG; }
+  if (loop_ms) *loop_ms = s->loop_ms;
+  if (rowsum_ms) *rowsum_ms = s->rowsum_ms;
+  if (rowsum_launches) *rowsum_launches = s->rowsum_launches;
+  if (total_launches) *total_launches = s->total_launches;
+  return TB_OK;
+}
+
+int tb_norm_sum(tb_store *s, const double *h_bias, const uint8_t *h_bad, double *out) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(s && out, "null argument");
+    DeviceGuard g(s->device);
+    norm_sum(s, h_bias, h_bad, out);
+    return TB_OK;
+  });
+}
+
+int tb_diag_sums(tb_store *s, const uint8_t *h_bad, int64_t ndiag, int64_t *h_sum_d) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(s, "null argument");
+    DeviceGuard g(s->device);
+    diag_sums(s, h_bad, ndiag, h_sum_d);
+    return TB_OK;
+  });
+}
+
+}  // extern "C"

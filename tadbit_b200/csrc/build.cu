@@ -1,0 +1,336 @@
+// Contact-store construction: upper-triangle COO -> device-resident CSR of the owned
+// rows of the FULL symmetric matrix (both triangles, diagonal once), columns ascending.
+//
+// Why both triangles: every reduction of the hot path (ICE row sums, filter statistics,
+// masked column sums) is a sum over a full matrix row (SURVEY.md 8a' trap 1).  Holding the
+// mirrored cells turns all of them into gather-only, atomic-free, deterministic row
+// reductions of one stream; the reference's dict holds both triangles too
+// (_pytadbit/hic_data.py:54-118).
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace tb {
+
+namespace {
+
+__global__ void k_validate_count(const int32_t *__restrict__ row, const int32_t *__restrict__ col,
+                                 int64_t nnz, int64_t nbins, int64_t rb, int64_t re,
+                                 unsigned long long *n_out, int *bad_input) {
+  unsigned long long mine = 0;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nnz;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i = row[k], j = col[k];
+    if (i < 0 || j < i || j >= nbins) {
+      *bad_input = 1;
+      continue;
+    }
+    mine += (i >= rb && i < re);
+    mine += (i != j && j >= rb && j < re);
+  }
+  for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_out, mine);
+}
+
+// Emit the directed cells (row in block) as sortable keys (local_row << 32 | col).
+__global__ void k_emit(const int32_t *__restrict__ row, const int32_t *__restrict__ col,
+                       const int32_t *__restrict__ val, int64_t nnz, int64_t rb, int64_t re,
+                       unsigned long long *cursor, uint64_t *keys, int32_t *vals) {
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nround = (nnz + stride - 1) / stride;
+  for (int64_t r = 0; r < nround; ++r) {
+    int64_t k = r * stride + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t i = 0, j = 0;
+    int32_t v = 0;
+    int c1 = 0, c2 = 0;
+    if (k < nnz) {
+      i = row[k];
+      j = col[k];
+      v = val[k];
+      c1 = (i >= rb && i < re);
+      c2 = (i != j && j >= rb && j < re);
+    }
+    int cnt = c1 + c2, incl = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    int total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 31 && total) base = atomicAdd(cursor, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    unsigned long long pos = base + (incl - cnt);
+    if (c1) {
+      keys[pos] = ((uint64_t)(i - rb) << 32) | (uint32_t)j;
+      vals[pos] = v;
+      ++pos;
+    }
+    if (c2) {
+      keys[pos] = ((uint64_t)(j - rb) << 32) | (uint32_t)i;
+      vals[pos] = v;
+    }
+  }
+}
+
+// keys sorted: split into col[] and rowptr[], flag duplicate cells.
+__global__ void k_split_keys(const uint64_t *__restrict__ keys, int64_t m, int64_t nrows,
+                             int32_t *col, int64_t *rowptr, int *dup) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < m;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t key = keys[k];
+    int64_t r = (int64_t)(key >> 32);
+    col[k] = (int32_t)(key & 0xffffffffu);
+    int64_t rprev = -1;
+    if (k) {
+      uint64_t kp = keys[k - 1];
+      if (kp == key) *dup = 1;
+      rprev = (int64_t)(kp >> 32);
+    }
+    for (int64_t rr = rprev + 1; rr <= r; ++rr) rowptr[rr] = k;
+    if (k == m - 1)
+      for (int64_t rr = r + 1; rr <= nrows; ++rr) rowptr[rr] = m;
+  }
+}
+
+__global__ void k_fill_i64(int64_t *p, int64_t n, int64_t v) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n;
+       k += (int64_t)gridDim.x * blockDim.x)
+    p[k] = v;
+}
+
+__global__ void k_row_chunk_counts(const int64_t *__restrict__ rowptr, int64_t nrows,
+                                   int64_t *nchunk) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    int64_t len = rowptr[r + 1] - rowptr[r];
+    nchunk[r] = (len + kChunk - 1) / kChunk;
+  }
+}
+
+__global__ void k_fill_chunks(const int64_t *__restrict__ rowptr,
+                              const int64_t *__restrict__ row_chunk, int64_t nrows,
+                              int64_t *chunk_beg, int32_t *chunk_row) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    int64_t c0 = row_chunk[r], c1 = row_chunk[r + 1], b = rowptr[r];
+    for (int64_t c = c0; c < c1; ++c) {
+      chunk_beg[c] = b + (c - c0) * kChunk;
+      chunk_row[c] = (int32_t)r;
+    }
+  }
+}
+
+// first stored cell of each owned row with col >= its own (global) row index
+__global__ void k_upper_start(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                              int64_t nrows, int64_t rb, int64_t *ustart, int64_t *ucount) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    int64_t lo = rowptr[r], hi = rowptr[r + 1], end = hi;
+    int32_t g = (int32_t)(rb + r);
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if (col[mid] < g) lo = mid + 1; else hi = mid;
+    }
+    ustart[r] = lo;
+    ucount[r] = end - lo;
+  }
+}
+
+__global__ void k_copy_upper(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
+                             const int64_t *__restrict__ ustart, const int64_t *__restrict__ ucount,
+                             const int64_t *__restrict__ uoff, int64_t nrows, int64_t rb,
+                             int32_t *orow, int32_t *ocol, int32_t *oval) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < nrows; r += nwarp) {
+    int64_t src = ustart[r], n = ucount[r], dst = uoff[r];
+    for (int64_t k = lane; k < n; k += 32) {
+      orow[dst + k] = (int32_t)(rb + r);
+      ocol[dst + k] = col[src + k];
+      oval[dst + k] = val[src + k];
+    }
+  }
+}
+
+inline int grid_for(int64_t n, int threads, int sm_count) {
+  int64_t g = (n + threads - 1) / threads;
+  int64_t cap = (int64_t)sm_count * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+void exclusive_scan_i64(cudaStream_t st, const int64_t *in, int64_t *out, int64_t n) {
+  size_t tmp_bytes = 0;
+  TB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, n, st));
+  DevBuf<uint8_t> tmp;
+  tmp.alloc(tmp_bytes ? tmp_bytes : 1);
+  TB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, in, out, n, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+}
+
+}  // namespace
+
+void build_from_coo(tb_store *s, int64_t nnz, const int32_t *row, const int32_t *col,
+                    const int32_t *val, int mem) {
+  cudaStream_t st = s->stream;
+  DevBuf<int32_t> drow, dcol, dval;
+  const int32_t *r = row, *c = col, *v = val;
+  if (mem == TB_MEM_HOST && nnz) {
+    drow.alloc(nnz); dcol.alloc(nnz); dval.alloc(nnz);
+    TB_CUDA(cudaMemcpyAsync(drow.p, row, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    TB_CUDA(cudaMemcpyAsync(dcol.p, col, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    TB_CUDA(cudaMemcpyAsync(dval.p, val, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    r = drow.p; c = dcol.p; v = dval.p;
+  }
+  DevBuf<unsigned long long> counters;   // [0] directed cells, [1] emit cursor
+  DevBuf<int> flags;                     // [0] bad input, [1] duplicate
+  counters.alloc(2);
+  flags.alloc(2);
+  TB_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), st));
+  TB_CUDA(cudaMemsetAsync(flags.p, 0, flags.bytes(), st));
+  const int threads = 256;
+  if (nnz)
+    k_validate_count<<<grid_for(nnz, threads, s->sm_count), threads, 0, st>>>(
+        r, c, nnz, s->nbins, s->row_begin, s->row_end, counters.p, flags.p);
+  unsigned long long h_cnt[2] = {0, 0};
+  int h_flags[2] = {0, 0};
+  TB_CUDA(cudaMemcpyAsync(h_cnt, counters.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaMemcpyAsync(h_flags, flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  TB_REQUIRE(!h_flags[0], "contact store: a cell has row < 0, row > col or col >= nbins");
+  const int64_t m = (int64_t)h_cnt[0];
+  s->nnz_full = m;
+  s->rowptr.alloc(s->nrows + 1);
+  s->col.alloc(m ? m : 1);
+  s->val.alloc(m ? m : 1);
+  if (m == 0) {
+    k_fill_i64<<<grid_for(s->nrows + 1, threads, s->sm_count), threads, 0, st>>>(
+        s->rowptr.p, s->nrows + 1, 0);
+    TB_CUDA(cudaStreamSynchronize(st));
+    finish_layout(s);
+    return;
+  }
+  {
+    DevBuf<uint64_t> keys_in, keys_out;
+    DevBuf<int32_t> vals_in;
+    keys_in.alloc(m); keys_out.alloc(m); vals_in.alloc(m);
+    k_emit<<<grid_for(nnz, threads, s->sm_count), threads, 0, st>>>(
+        r, c, v, nnz, s->row_begin, s->row_end, counters.p + 1, keys_in.p, vals_in.p);
+    int row_bits = 1;
+    while (((int64_t)1 << row_bits) < s->nrows) ++row_bits;
+    const int end_bit = 32 + row_bits;
+    size_t tmp_bytes = 0;
+    TB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in.p, keys_out.p, vals_in.p,
+                                            s->val.p, m, 0, end_bit, st));
+    DevBuf<uint8_t> tmp;
+    tmp.alloc(tmp_bytes ? tmp_bytes : 1);
+    TB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_in.p, keys_out.p, vals_in.p,
+                                            s->val.p, m, 0, end_bit, st));
+    k_split_keys<<<grid_for(m, threads, s->sm_count), threads, 0, st>>>(
+        keys_out.p, m, s->nrows, s->col.p, s->rowptr.p, flags.p + 1);
+    TB_CUDA(cudaMemcpyAsync(h_flags, flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    TB_REQUIRE(!h_flags[1], "contact store: duplicate cells (each upper-triangle cell must appear once)");
+  }
+  finish_layout(s);
+}
+
+void finish_layout(tb_store *s) {
+  cudaStream_t st = s->stream;
+  const int threads = 256;
+  const int64_t nrows = s->nrows, N = s->nbins;
+  // chunks
+  s->row_chunk.alloc(nrows + 1);
+  {
+    DevBuf<int64_t> cnt;
+    cnt.alloc(nrows + 1);
+    TB_CUDA(cudaMemsetAsync(cnt.p, 0, cnt.bytes(), st));
+    if (nrows)
+      k_row_chunk_counts<<<grid_for(nrows, threads, s->sm_count), threads, 0, st>>>(
+          s->rowptr.p, nrows, cnt.p);
+    exclusive_scan_i64(st, cnt.p, s->row_chunk.p, nrows + 1);
+  }
+  int64_t nchunks = 0;
+  TB_CUDA(cudaMemcpy(&nchunks, s->row_chunk.p + nrows, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  s->nchunks = nchunks;
+  s->chunk_beg.alloc(nchunks + 1);
+  s->chunk_row.alloc(nchunks + 1);
+  if (nrows)
+    k_fill_chunks<<<grid_for(nrows, threads, s->sm_count), threads, 0, st>>>(
+        s->rowptr.p, s->row_chunk.p, nrows, s->chunk_beg.p, s->chunk_row.p);
+  // upper-triangle count of the block
+  {
+    DevBuf<int64_t> us, uc, total;
+    us.alloc(nrows + 1); uc.alloc(nrows + 1); total.alloc(1);
+    TB_CUDA(cudaMemsetAsync(uc.p, 0, uc.bytes(), st));
+    if (nrows)
+      k_upper_start<<<grid_for(nrows, threads, s->sm_count), threads, 0, st>>>(
+          s->rowptr.p, s->col.p, nrows, s->row_begin, us.p, uc.p);
+    size_t tmp_bytes = 0;
+    TB_CUDA(cub::DeviceReduce::Sum(nullptr, tmp_bytes, uc.p, total.p, nrows + 1, st));
+    DevBuf<uint8_t> tmp;
+    tmp.alloc(tmp_bytes ? tmp_bytes : 1);
+    TB_CUDA(cub::DeviceReduce::Sum(tmp.p, tmp_bytes, uc.p, total.p, nrows + 1, st));
+    TB_CUDA(cudaMemcpyAsync(&s->nnz_upper, total.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+  }
+  // scratch
+  const size_t nc = nchunks ? nchunks : 1, nn = N ? N : 1;
+  s->partial_f.alloc(nc);
+  s->partial_i.alloc(nc);
+  s->x.alloc(nn); s->b.alloc(nn);
+  s->s_part.alloc(2 * nn); s->s_full.alloc(2 * nn);
+  s->i_part.alloc(2 * nn); s->i_full.alloc(2 * nn);
+  s->bad.alloc(nn); s->present.alloc(nn);
+  s->block_red.alloc(4 * 1024);
+  s->scal_f.alloc(16);
+  s->scal_i.alloc(16);
+  s->state.alloc(1);
+  s->h_state.alloc(1);
+  TB_CUDA(cudaMemsetAsync(s->s_part.p, 0, s->s_part.bytes(), st));
+  TB_CUDA(cudaMemsetAsync(s->i_part.p, 0, s->i_part.bytes(), st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  s->device_bytes = s->rowptr.bytes() + s->col.bytes() + s->val.bytes() + s->chunk_beg.bytes() +
+                    s->chunk_row.bytes() + s->row_chunk.bytes() + s->partial_f.bytes() +
+                    s->partial_i.bytes() + s->x.bytes() + s->b.bytes() +
+                    s->s_part.bytes() + s->s_full.bytes() + s->i_part.bytes() + s->i_full.bytes() +
+                    s->bad.bytes() + s->present.bytes() + s->chrom_of.bytes();
+}
+
+void setup_sections(tb_store *s) {
+  const int64_t N = s->nbins;
+  std::vector<int32_t> h(N ? N : 1);
+  for (int32_t c = 0; c + 1 < (int32_t)s->chrom_offsets.size(); ++c)
+    for (int64_t i = s->chrom_offsets[c]; i < s->chrom_offsets[c + 1]; ++i) h[i] = c;
+  s->chrom_of.alloc(N ? N : 1);
+  if (N) TB_CUDA(cudaMemcpy(s->chrom_of.p, h.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice));
+}
+
+void export_upper(const tb_store *s, int64_t *nnz, int32_t *h_row, int32_t *h_col, int32_t *h_val) {
+  *nnz = s->nnz_upper;
+  if (!h_row) return;
+  TB_REQUIRE(h_col && h_val, "export: null output buffer");
+  if (s->nnz_upper == 0) return;
+  cudaStream_t st = s->stream;
+  const int threads = 256;
+  const int64_t nrows = s->nrows;
+  DevBuf<int64_t> us, uc, uo;
+  us.alloc(nrows + 1); uc.alloc(nrows + 1); uo.alloc(nrows + 1);
+  TB_CUDA(cudaMemsetAsync(uc.p, 0, uc.bytes(), st));
+  k_upper_start<<<grid_for(nrows, threads, s->sm_count), threads, 0, st>>>(
+      s->rowptr.p, s->col.p, nrows, s->row_begin, us.p, uc.p);
+  exclusive_scan_i64(st, uc.p, uo.p, nrows + 1);
+  DevBuf<int32_t> orow, ocol, oval;
+  orow.alloc(s->nnz_upper); ocol.alloc(s->nnz_upper); oval.alloc(s->nnz_upper);
+  k_copy_upper<<<grid_for(nrows * 32, threads, s->sm_count), threads, 0, st>>>(
+      s->col.p, s->val.p, us.p, uc.p, uo.p, nrows, s->row_begin, orow.p, ocol.p, oval.p);
+  TB_CUDA(cudaMemcpyAsync(h_row, orow.p, orow.bytes(), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaMemcpyAsync(h_col, ocol.p, ocol.bytes(), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaMemcpyAsync(h_val, oval.p, oval.bytes(), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+}
+
+}  // namespace tb

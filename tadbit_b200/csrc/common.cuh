@@ -1,0 +1,155 @@
+// Shared declarations of the tadbit_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/tadbit_b200.h"
+
+namespace tb {
+
+void set_error(const char *fmt, ...);
+struct Fail {           // thrown inside the library, mapped to a tb_status at the C-ABI
+  int code;
+};
+
+#define TB_CUDA(call)                                                                  \
+  do {                                                                                 \
+    cudaError_t e__ = (call);                                                          \
+    if (e__ != cudaSuccess) {                                                          \
+      ::tb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,                     \
+                      cudaGetErrorString(e__));                                        \
+      throw ::tb::Fail{TB_ERR_CUDA};                                                   \
+    }                                                                                  \
+  } while (0)
+
+#define TB_REQUIRE(cond, ...)                                                          \
+  do {                                                                                 \
+    if (!(cond)) {                                                                     \
+      ::tb::set_error(__VA_ARGS__);                                                    \
+      throw ::tb::Fail{TB_ERR_ARG};                                                    \
+    }                                                                                  \
+  } while (0)
+
+// Device allocation owned by a store; freed in its destructor.
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { release(); }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) TB_CUDA(cudaMalloc(&p, count * sizeof(T)));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+template <typename T>
+struct PinnedBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  ~PinnedBuf() { release(); }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) TB_CUDA(cudaMallocHost(&p, count * sizeof(T)));
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+// Device-side state of one ICE call (written by the reduce kernel, polled by the host).
+struct IceState {
+  double mean_s, s_min, s_max, dev;
+  long long n_present;
+  int passes_done;   // passes whose statistics were finalised
+  int stopped;       // 1 once the reference loop would have left (dev < max_dev, or iterations == 0)
+  int all_bad;       // no present row
+  unsigned int blocks_arrived;
+};
+
+constexpr int kWarp = 32;
+constexpr int kChunk = 4096;      // max stored cells one warp reduces before writing a partial
+
+}  // namespace tb
+
+// The opaque handle of include/tadbit_b200.h.
+struct tb_store {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  int64_t nbins = 0, row_begin = 0, row_end = 0, nrows = 0;
+  int64_t nnz_full = 0;     // stored full-matrix cells with row in the block
+  int64_t nnz_upper = 0;    // of those, col >= row
+  // sections
+  int32_t n_chrom = 0;
+  std::vector<int64_t> chrom_offsets;     // n_chrom+1 (always >= 2 entries: one section if none given)
+  tb::DevBuf<int32_t> chrom_of;           // [N] section id of each bin
+  // CSR of the owned rows of the FULL symmetric matrix, columns ascending
+  tb::DevBuf<int64_t> rowptr;             // [nrows+1]
+  tb::DevBuf<int32_t> col, val;           // [nnz_full]
+  // warp work items: <= kChunk consecutive cells of one row
+  int64_t nchunks = 0;
+  tb::DevBuf<int64_t> chunk_beg;          // [nchunks+1] first cell of the chunk
+  tb::DevBuf<int32_t> chunk_row;          // [nchunks] local row
+  tb::DevBuf<int64_t> row_chunk;          // [nrows+1] first chunk of each row
+  // scratch
+  tb::DevBuf<double> partial_f;           // [nchunks]
+  tb::DevBuf<long long> partial_i;        // [nchunks]
+  tb::DevBuf<double> x, b, s_part, s_full, block_red;
+  tb::DevBuf<long long> i_part, i_full;   // [2N] integer reductions
+  tb::DevBuf<double> scal_f;              // [16] scalar results
+  tb::DevBuf<long long> scal_i;           // [16]
+  tb::DevBuf<uint8_t> bad, present;
+  tb::DevBuf<tb::IceState> state;
+  tb::DevBuf<double> trace;               // [(iterations+1)*4]
+  tb::PinnedBuf<tb::IceState> h_state;
+  // multi-GPU
+  void *comm = nullptr;
+  int rank = 0, world = 1;
+  // timing of the last ICE call
+  double loop_ms = 0, rowsum_ms = 0;
+  int rowsum_launches = 0, total_launches = 0;
+  int64_t device_bytes = 0;
+};
+
+namespace tb {
+// build.cu
+void build_from_coo(tb_store *s, int64_t nnz, const int32_t *row, const int32_t *col,
+                    const int32_t *val, int mem);
+void setup_sections(tb_store *s);   // bin -> section id table (before any build)
+void finish_layout(tb_store *s);     // chunks + scratch once rowptr/col/val are in place
+void export_upper(const tb_store *s, int64_t *nnz, int32_t *h_row, int32_t *h_col, int32_t *h_val);
+// synth.cu
+void build_synthetic(tb_store *s, const tb_synth_params *p);
+void synthetic_row_counts(int64_t nbins, int32_t n_chrom, const int64_t *chrom_offsets,
+                          const tb_synth_params *p, int64_t rb, int64_t re, int device,
+                          int64_t *h_counts);
+// kernels.cu
+void row_stats(tb_store *s, int64_t *h_nnz_row, int64_t *h_row_sum);
+void col_sums_masked(tb_store *s, const uint8_t *h_bad, int64_t *h_col_sum);
+int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, double *h_bias,
+        double *h_trace, int32_t *n_passes);
+void norm_sum(tb_store *s, const double *h_bias, const uint8_t *h_bad, double *out);
+void diag_sums(tb_store *s, const uint8_t *h_bad, int64_t ndiag, int64_t *h_sum_d);
+// comm.cu
+void comm_unique_id(uint8_t id[128]);
+void comm_init(tb_store *s, int rank, int world, const uint8_t id[128]);
+void comm_destroy(tb_store *s);
+void allreduce_f64(tb_store *s, const double *send, double *recv, size_t n);
+void allreduce_i64(tb_store *s, const long long *send, long long *recv, size_t n);
+}  // namespace tb

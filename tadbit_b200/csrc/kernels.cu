@@ -1,0 +1,559 @@
+// Hot-path kernels (sm_100a).  Round-1 layout: CSR of the owned full-matrix rows, one
+// warp reduces one chunk (<= kChunk stored cells of one row), a second tiny kernel adds
+// the chunk partials of each row in a fixed order -> deterministic, atomic-free.
+//
+//   K1  k_chunk_reduce<F64>      s_i = sum_j v_ij * x_j          (normalize_hic.py:136-143,154-162)
+//   K2  k_ice_reduce/_update     S = x.s, meanS/min/max/dev, B *= S/meanS, x = 1/B (:146-151,217-222)
+//   K3  K1 + k_dot               sum v/(b_i b_j)                 (hic_data.py:350-375)
+//   K4  k_chunk_reduce<I64*>     row sums / masked column sums   (hic_filtering.py:36-39,141-145,185-200)
+//   K5  k_diag_hist              per-distance sums               (normalize_hic.py:271-283)
+#include <math.h>
+
+#include "common.cuh"
+
+namespace tb {
+
+namespace {
+
+enum { M_F64 = 0, M_F64_COUNT = 1, M_I64 = 2, M_I64_MASKED = 3 };
+
+__device__ __forceinline__ int32_t ld_stream(const int32_t *p) {
+  int32_t r;   // streamed once: keep it out of L1 so the gathered vector stays resident
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_chunk_reduce(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
+               const int64_t *__restrict__ chunk_beg, const int32_t *__restrict__ chunk_row,
+               const int64_t *__restrict__ rowptr, int64_t nchunks,
+               const double *__restrict__ x, const uint8_t *__restrict__ bad,
+               double *__restrict__ pf, long long *__restrict__ pi,
+               const IceState *__restrict__ state) {
+  if (state && state->stopped) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t c = warp; c < nchunks; c += nwarp) {
+    const int64_t beg = chunk_beg[c];
+    int64_t end = rowptr[chunk_row[c] + 1];
+    if (end > beg + kChunk) end = beg + kChunk;
+    double fa = 0.0, fb = 0.0;
+    long long ia = 0, ic = 0;
+    int64_t k = beg + lane;
+    for (; k + 96 < end; k += 128) {
+      int32_t c0 = ld_stream(col + k), c1 = ld_stream(col + k + 32);
+      int32_t c2 = ld_stream(col + k + 64), c3 = ld_stream(col + k + 96);
+      int32_t v0 = ld_stream(val + k), v1 = ld_stream(val + k + 32);
+      int32_t v2 = ld_stream(val + k + 64), v3 = ld_stream(val + k + 96);
+      if (MODE == M_F64 || MODE == M_F64_COUNT) {
+        double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+        fa = fma((double)v0, x0, fa);
+        fb = fma((double)v1, x1, fb);
+        fa = fma((double)v2, x2, fa);
+        fb = fma((double)v3, x3, fb);
+        if (MODE == M_F64_COUNT) ic += (x0 != 0.0) + (x1 != 0.0) + (x2 != 0.0) + (x3 != 0.0);
+      } else if (MODE == M_I64) {
+        ia += (long long)v0 + v1 + v2 + v3;
+      } else {
+        ia += (bad[c0] ? 0 : v0) + (long long)(bad[c1] ? 0 : v1) + (bad[c2] ? 0 : v2) +
+              (long long)(bad[c3] ? 0 : v3);
+      }
+    }
+    for (; k < end; k += 32) {
+      int32_t c0 = ld_stream(col + k), v0 = ld_stream(val + k);
+      if (MODE == M_F64 || MODE == M_F64_COUNT) {
+        double x0 = __ldg(x + c0);
+        fa = fma((double)v0, x0, fa);
+        if (MODE == M_F64_COUNT) ic += (x0 != 0.0);
+      } else if (MODE == M_I64) {
+        ia += v0;
+      } else {
+        ia += bad[c0] ? 0 : v0;
+      }
+    }
+    if (MODE == M_F64 || MODE == M_F64_COUNT) {
+      fa += fb;
+      for (int o = 16; o; o >>= 1) fa += __shfl_xor_sync(0xffffffffu, fa, o);
+      if (MODE == M_F64_COUNT)
+        for (int o = 16; o; o >>= 1) ic += __shfl_xor_sync(0xffffffffu, ic, o);
+      if (lane == 0) {
+        pf[c] = fa;
+        if (MODE == M_F64_COUNT) pi[c] = ic;
+      }
+    } else {
+      for (int o = 16; o; o >>= 1) ia += __shfl_xor_sync(0xffffffffu, ia, o);
+      if (lane == 0) pi[c] = ia;
+    }
+  }
+}
+
+// out[rb + r] = sum of the row's chunk partials, in chunk order.  WITH_COUNT also writes the
+// count partials (as exact doubles) to out[N + rb + r] so one all-reduce carries both.
+template <bool WITH_COUNT>
+__global__ void k_combine_f64(const double *__restrict__ pf, const long long *__restrict__ pc,
+                              const int64_t *__restrict__ row_chunk, int64_t nrows, int64_t rb,
+                              int64_t nbins, double *__restrict__ out,
+                              const IceState *__restrict__ state) {
+  if (state && state->stopped) return;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    double a = 0.0;
+    long long n = 0;
+    for (int64_t c = row_chunk[r]; c < row_chunk[r + 1]; ++c) {
+      a += pf[c];
+      if (WITH_COUNT) n += pc[c];
+    }
+    out[rb + r] = a;
+    if (WITH_COUNT) out[nbins + rb + r] = (double)n;
+  }
+}
+
+__global__ void k_combine_i64(const long long *__restrict__ pi, const int64_t *__restrict__ row_chunk,
+                              int64_t nrows, int64_t rb, long long *__restrict__ out) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    long long a = 0;
+    for (int64_t c = row_chunk[r]; c < row_chunk[r + 1]; ++c) a += pi[c];
+    out[rb + r] = a;
+  }
+}
+
+__global__ void k_row_nnz(const int64_t *__restrict__ rowptr, int64_t nrows, int64_t rb,
+                          long long *__restrict__ out) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
+       r += (int64_t)gridDim.x * blockDim.x)
+    out[rb + r] = rowptr[r + 1] - rowptr[r];
+}
+
+// ---------------------------------------------------------------------------------
+// ICE vector kernels
+// ---------------------------------------------------------------------------------
+__global__ void k_ice_init(const uint8_t *__restrict__ bad, int64_t n, double *x, double *b,
+                           IceState *state) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] = bad[i] ? 0.0 : 1.0;
+    b[i] = 1.0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    state->mean_s = state->s_min = state->s_max = state->dev = 0.0;
+    state->n_present = 0;
+    state->passes_done = 0;
+    state->stopped = 0;
+    state->all_bad = 0;
+    state->blocks_arrived = 0;
+  }
+}
+
+constexpr int kRedThreads = 256;
+
+// S_i = x_i * s_i over present rows -> sum / min / max; the last block to arrive folds the
+// per-block partials in block order and takes the reference's loop decision.
+__global__ void __launch_bounds__(kRedThreads)
+k_ice_reduce(const double *__restrict__ s_full, const double *__restrict__ x,
+             const uint8_t *__restrict__ bad, uint8_t *__restrict__ present, int64_t n,
+             int pass, int iterations, double max_dev, double *__restrict__ block_red,
+             double *__restrict__ trace, IceState *state) {
+  if (state->stopped) return;
+  __shared__ double sh_sum[kRedThreads / 32], sh_min[kRedThreads / 32], sh_max[kRedThreads / 32];
+  __shared__ long long sh_cnt[kRedThreads / 32];
+  __shared__ bool is_last;
+  double sum = 0.0, mn = INFINITY, mx = -INFINITY;
+  long long cnt = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    bool p;
+    if (pass == 0) {
+      p = !bad[i] && s_full[n + i] > 0.0;      // row kept by copy_matrix (normalize_hic.py:165-177)
+      present[i] = p;
+    } else {
+      p = present[i];
+    }
+    if (p) {
+      double S = x[i] * s_full[i];
+      sum += S;
+      mn = fmin(mn, S);
+      mx = fmax(mx, S);
+      ++cnt;
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh_sum[w] = sum; sh_min[w] = mn; sh_max[w] = mx; sh_cnt[w] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < kRedThreads / 32; ++k) {
+      sum += sh_sum[k]; mn = fmin(mn, sh_min[k]); mx = fmax(mx, sh_max[k]); cnt += sh_cnt[k];
+    }
+    block_red[4 * blockIdx.x + 0] = sum;
+    block_red[4 * blockIdx.x + 1] = mn;
+    block_red[4 * blockIdx.x + 2] = mx;
+    block_red[4 * blockIdx.x + 3] = (double)cnt;
+    __threadfence();
+    unsigned int t = atomicAdd(&state->blocks_arrived, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last || threadIdx.x != 0) return;
+  __threadfence();
+  sum = 0.0; mn = INFINITY; mx = -INFINITY;
+  double dcnt = 0.0;
+  for (unsigned int bl = 0; bl < gridDim.x; ++bl) {
+    const volatile double *br = block_red + 4 * bl;
+    sum += br[0]; mn = fmin(mn, br[1]); mx = fmax(mx, br[2]); dcnt += br[3];
+  }
+  state->blocks_arrived = 0;
+  if (pass == 0) state->n_present = (long long)dcnt;
+  const long long np = state->n_present;
+  if (np == 0) {
+    state->all_bad = 1;
+    state->stopped = 1;
+    return;
+  }
+  const double mean = sum / (double)np;
+  state->mean_s = mean;
+  state->s_min = mn;
+  state->s_max = mx;
+  if (iterations == 0) {            // single pass, no deviation test (normalize_hic.py:214-215)
+    state->passes_done = pass + 1;
+    state->stopped = 1;
+    return;
+  }
+  const double dev = fmax(fabs(mn / mean - 1.0), fabs(mx / mean - 1.0));
+  state->dev = dev;
+  trace[4 * pass + 0] = mn;
+  trace[4 * pass + 1] = mean;
+  trace[4 * pass + 2] = mx;
+  trace[4 * pass + 3] = dev;
+  state->passes_done = pass + 1;
+  if (dev < max_dev) state->stopped = 1;
+}
+
+// B_i *= S_i / meanS ; x_i = 1 / B_i.  Runs for every pass whose statistics were finalised,
+// including the one that stops the loop (the reference updates B before it tests dev).
+__global__ void k_ice_update(const double *__restrict__ s_full, double *__restrict__ x,
+                             double *__restrict__ b, const uint8_t *__restrict__ present,
+                             int64_t n, int pass, const IceState *__restrict__ state) {
+  if (state->passes_done != pass + 1 || state->all_bad) return;
+  const double mean = state->mean_s;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (!present[i]) {
+      x[i] = 0.0;
+      continue;
+    }
+    const double S = x[i] * s_full[i];
+    const double bi = b[i] * (S / mean);
+    b[i] = bi;
+    x[i] = (bi != 0.0) ? 1.0 / bi : 0.0;     // B == 0: row frozen by the ZeroDivisionError skip
+  }
+}
+
+__global__ void k_ice_finalize(const double *__restrict__ b, const uint8_t *__restrict__ present,
+                               int64_t n, const IceState *__restrict__ state,
+                               double *__restrict__ bias) {
+  const double f = sqrt(state->mean_s);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double bi = b[i];
+    bias[i] = (present[i] && bi != 0.0) ? bi * f : 1.0;   // normalize_hic.py:223-230
+  }
+}
+
+__global__ void k_inverse_bias(const double *__restrict__ bias, const uint8_t *__restrict__ bad,
+                               int64_t n, double *__restrict__ y) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = bad[i] ? 0.0 : 1.0 / bias[i];
+}
+
+// sum over owned rows of y_i * s_i, single block (N fits: one pass, fixed order)
+__global__ void __launch_bounds__(1024)
+k_dot_rows(const double *__restrict__ y, const double *__restrict__ s, int64_t rb, int64_t re,
+           double *__restrict__ out) {
+  __shared__ double sh[32];
+  double a = 0.0;
+  for (int64_t i = rb + threadIdx.x; i < re; i += blockDim.x) a += y[i] * s[i];
+  for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) a += sh[k];
+    out[0] = a;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+k_sum_good_rows(const long long *__restrict__ v, const uint8_t *__restrict__ bad, int64_t rb,
+                int64_t re, long long *__restrict__ out) {
+  __shared__ long long sh[32];
+  long long a = 0;
+  for (int64_t i = rb + threadIdx.x; i < re; i += blockDim.x) a += bad[i] ? 0 : v[i];
+  for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) a += sh[k];
+    out[0] = a;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// K5: per-distance sums.  Cells of one row have distinct distances, and a warp walks
+// consecutive cells of one row, so the shared-memory histogram sees no intra-warp
+// collisions; distances beyond the shared window go straight to L2 atomics.
+// ---------------------------------------------------------------------------------
+constexpr int kDiagShared = 4096;
+
+__global__ void __launch_bounds__(256)
+k_diag_hist(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
+            const int64_t *__restrict__ chunk_beg, const int32_t *__restrict__ chunk_row,
+            const int64_t *__restrict__ rowptr, int64_t nchunks, int64_t rb,
+            const uint8_t *__restrict__ bad, const int32_t *__restrict__ chrom_of, int64_t ndiag,
+            unsigned long long *__restrict__ hist) {
+  __shared__ unsigned long long sh[kDiagShared];
+  for (int k = threadIdx.x; k < kDiagShared; k += blockDim.x) sh[k] = 0ull;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t c = warp; c < nchunks; c += nwarp) {
+    const int64_t r = chunk_row[c];
+    const int64_t g = rb + r;
+    if (bad[g]) continue;
+    const int64_t beg = chunk_beg[c];
+    int64_t end = rowptr[r + 1];
+    if (end > beg + kChunk) end = beg + kChunk;
+    if (col[end - 1] < g) continue;            // chunk entirely below the diagonal
+    const int32_t cg = chrom_of[g];
+    for (int64_t k = beg + lane; k < end; k += 32) {
+      const int64_t j = ld_stream(col + k);
+      const int64_t d = j - g;
+      if (d < 0 || d >= ndiag || chrom_of[j] != cg) continue;
+      const unsigned long long v = (unsigned long long)(long long)ld_stream(val + k);
+      if (d < kDiagShared) atomicAdd(&sh[d], v);
+      else atomicAdd(&hist[d], v);
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < kDiagShared && k < ndiag; k += blockDim.x)
+    if (sh[k]) atomicAdd(&hist[k], sh[k]);
+}
+
+inline int grid_1d(int64_t n, int threads, int sm_count, int per_sm = 8) {
+  int64_t g = (n + threads - 1) / threads;
+  int64_t cap = (int64_t)sm_count * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+inline int chunk_grid(const tb_store *s) {
+  // 8 warps per CTA, 8 CTAs per SM resident; grid = multiple of the SM count
+  int64_t need = (s->nchunks + 7) / 8;
+  int64_t cap = (int64_t)s->sm_count * 8;
+  int64_t g = need < cap ? need : cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+void upload_bad(tb_store *s, const uint8_t *h_bad) {
+  if (h_bad)
+    TB_CUDA(cudaMemcpyAsync(s->bad.p, h_bad, s->nbins, cudaMemcpyHostToDevice, s->stream));
+  else
+    TB_CUDA(cudaMemsetAsync(s->bad.p, 0, s->nbins, s->stream));
+}
+
+template <int MODE>
+void launch_chunks(tb_store *s, const double *x, const uint8_t *bad, const IceState *state) {
+  if (s->nchunks == 0) return;
+  k_chunk_reduce<MODE><<<chunk_grid(s), 256, 0, s->stream>>>(
+      s->col.p, s->val.p, s->chunk_beg.p, s->chunk_row.p, s->rowptr.p, s->nchunks, x, bad,
+      s->partial_f.p, s->partial_i.p, state);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------
+void row_stats(tb_store *s, int64_t *h_nnz_row, int64_t *h_row_sum) {
+  cudaStream_t st = s->stream;
+  const int64_t N = s->nbins;
+  long long *dst = s->world > 1 ? s->i_part.p : s->i_full.p;
+  if (s->world == 1) TB_CUDA(cudaMemsetAsync(dst, 0, 2 * N * sizeof(long long), st));
+  launch_chunks<M_I64>(s, nullptr, nullptr, nullptr);
+  if (s->nrows) {
+    k_row_nnz<<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(s->rowptr.p, s->nrows,
+                                                                   s->row_begin, dst);
+    k_combine_i64<<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
+        s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, dst + N);
+  }
+  if (s->world > 1) allreduce_i64(s, s->i_part.p, s->i_full.p, 2 * N);
+  TB_CUDA(cudaMemcpyAsync(h_nnz_row, s->i_full.p, N * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaMemcpyAsync(h_row_sum, s->i_full.p + N, N * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+}
+
+void col_sums_masked(tb_store *s, const uint8_t *h_bad, int64_t *h_col_sum) {
+  cudaStream_t st = s->stream;
+  const int64_t N = s->nbins;
+  upload_bad(s, h_bad);
+  long long *dst = s->world > 1 ? s->i_part.p : s->i_full.p;
+  if (s->world == 1) TB_CUDA(cudaMemsetAsync(dst, 0, N * sizeof(long long), st));
+  launch_chunks<M_I64_MASKED>(s, nullptr, s->bad.p, nullptr);
+  if (s->nrows)
+    k_combine_i64<<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
+        s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, dst);
+  if (s->world > 1) allreduce_i64(s, s->i_part.p, s->i_full.p, N);
+  TB_CUDA(cudaMemcpyAsync(h_col_sum, s->i_full.p, N * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+}
+
+int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, double *h_bias,
+        double *h_trace, int32_t *n_passes) {
+  cudaStream_t st = s->stream;
+  const int64_t N = s->nbins;
+  TB_REQUIRE(iterations >= 0, "ice: iterations must be >= 0");
+  TB_REQUIRE(N > 0, "ice: empty matrix");
+  const int npass_max = iterations + 1;
+  if (s->trace.n < (size_t)npass_max * 4) s->trace.alloc((size_t)npass_max * 4);
+  upload_bad(s, h_bad);
+  const int vg = grid_1d(N, 256, s->sm_count);
+  int rg = grid_1d(N, kRedThreads, s->sm_count, 4);
+  if (rg > 768) rg = 768;
+  k_ice_init<<<vg, 256, 0, st>>>(s->bad.p, N, s->x.p, s->b.p, s->state.p);
+
+  std::vector<cudaEvent_t> ev(2 * (size_t)npass_max + 2);
+  for (auto &e : ev) TB_CUDA(cudaEventCreate(&e));
+  double *dst = s->world > 1 ? s->s_part.p : s->s_full.p;
+  const int poll = iterations == 0 ? 1 : 4;
+  int launched = 0;
+  bool stopped = false;
+  TB_CUDA(cudaEventRecord(ev[2 * npass_max], st));
+  for (int p = 0; p < npass_max && !stopped; ++p) {
+    TB_CUDA(cudaEventRecord(ev[2 * p], st));
+    if (p == 0) launch_chunks<M_F64_COUNT>(s, s->x.p, nullptr, s->state.p);
+    else launch_chunks<M_F64>(s, s->x.p, nullptr, s->state.p);
+    TB_CUDA(cudaEventRecord(ev[2 * p + 1], st));
+    if (s->nrows) {
+      if (p == 0)
+        k_combine_f64<true><<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
+            s->partial_f.p, s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, N, dst, s->state.p);
+      else
+        k_combine_f64<false><<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
+            s->partial_f.p, s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, N, dst, s->state.p);
+    }
+    if (s->world > 1) allreduce_f64(s, s->s_part.p, s->s_full.p, p == 0 ? 2 * N : N);
+    k_ice_reduce<<<rg, kRedThreads, 0, st>>>(s->s_full.p, s->x.p, s->bad.p, s->present.p, N, p,
+                                             iterations, max_dev, s->block_red.p, s->trace.p,
+                                             s->state.p);
+    k_ice_update<<<vg, 256, 0, st>>>(s->s_full.p, s->x.p, s->b.p, s->present.p, N, p, s->state.p);
+    ++launched;
+    if ((p + 1) % poll == 0 || p == npass_max - 1) {
+      TB_CUDA(cudaMemcpyAsync(s->h_state.p, s->state.p, sizeof(IceState), cudaMemcpyDeviceToHost, st));
+      TB_CUDA(cudaStreamSynchronize(st));
+      stopped = s->h_state.p->stopped != 0;
+    }
+  }
+  TB_CUDA(cudaEventRecord(ev[2 * npass_max + 1], st));
+  TB_CUDA(cudaMemcpyAsync(s->h_state.p, s->state.p, sizeof(IceState), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  const IceState hs = *s->h_state.p;
+  int rc = TB_OK;
+  if (hs.all_bad) {
+    set_error("ERROR: normalization failed, all bad columns");
+    rc = TB_ERR_ALL_BAD;
+  } else {
+    // bias into s_part's tail is avoided: reuse partial-free buffer b -> finalize into x
+    k_ice_finalize<<<vg, 256, 0, st>>>(s->b.p, s->present.p, N, s->state.p, s->x.p);
+    TB_CUDA(cudaMemcpyAsync(h_bias, s->x.p, N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    const int done = hs.passes_done;
+    if (h_trace && iterations > 0 && done > 0)
+      TB_CUDA(cudaMemcpyAsync(h_trace, s->trace.p, (size_t)done * 4 * sizeof(double),
+                              cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    if (n_passes) *n_passes = done;
+  }
+  // timing (only passes that did work)
+  float ms = 0.f;
+  TB_CUDA(cudaEventElapsedTime(&ms, ev[2 * npass_max], ev[2 * npass_max + 1]));
+  s->loop_ms = ms;
+  s->rowsum_ms = 0;
+  s->rowsum_launches = 0;
+  const int real = hs.all_bad ? 0 : hs.passes_done;
+  for (int p = 0; p < real && p < launched; ++p) {
+    TB_CUDA(cudaEventElapsedTime(&ms, ev[2 * p], ev[2 * p + 1]));
+    s->rowsum_ms += ms;
+    ++s->rowsum_launches;
+  }
+  s->total_launches = launched * (3 + (s->nrows ? 1 : 0)) + 2;
+  for (auto &e : ev) cudaEventDestroy(e);
+  return rc;
+}
+
+void norm_sum(tb_store *s, const double *h_bias, const uint8_t *h_bad, double *out) {
+  cudaStream_t st = s->stream;
+  const int64_t N = s->nbins;
+  TB_REQUIRE(out, "norm_sum: null output");
+  upload_bad(s, h_bad);
+  if (!h_bias) {        // raw sum: exact integers
+    launch_chunks<M_I64_MASKED>(s, nullptr, s->bad.p, nullptr);
+    if (s->nrows)
+      k_combine_i64<<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
+          s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, s->i_full.p);
+    k_sum_good_rows<<<1, 1024, 0, st>>>(s->i_full.p, s->bad.p, s->row_begin, s->row_end,
+                                        s->scal_i.p);
+    if (s->world > 1) allreduce_i64(s, s->scal_i.p, s->scal_i.p + 8, 1);
+    long long v = 0;
+    TB_CUDA(cudaMemcpyAsync(&v, s->world > 1 ? s->scal_i.p + 8 : s->scal_i.p, sizeof(long long),
+                            cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    *out = (double)v;
+    return;
+  }
+  // y = 1/bias on good bins, 0 on bad ones; sum = y . (W y)
+  TB_CUDA(cudaMemcpyAsync(s->b.p, h_bias, N * sizeof(double), cudaMemcpyHostToDevice, st));
+  k_inverse_bias<<<grid_1d(N, 256, s->sm_count), 256, 0, st>>>(s->b.p, s->bad.p, N, s->x.p);
+  launch_chunks<M_F64>(s, s->x.p, nullptr, nullptr);
+  if (s->nrows)
+    k_combine_f64<false><<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
+        s->partial_f.p, s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, N, s->s_full.p,
+        nullptr);
+  k_dot_rows<<<1, 1024, 0, st>>>(s->x.p, s->s_full.p, s->row_begin, s->row_end, s->scal_f.p);
+  if (s->world > 1) allreduce_f64(s, s->scal_f.p, s->scal_f.p + 8, 1);
+  TB_CUDA(cudaMemcpyAsync(out, s->world > 1 ? s->scal_f.p + 8 : s->scal_f.p, sizeof(double),
+                          cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+}
+
+void diag_sums(tb_store *s, const uint8_t *h_bad, int64_t ndiag, int64_t *h_sum_d) {
+  cudaStream_t st = s->stream;
+  TB_REQUIRE(ndiag >= 0 && h_sum_d, "diag_sums: bad arguments");
+  if (ndiag == 0) return;
+  upload_bad(s, h_bad);
+  DevBuf<unsigned long long> hist, red;
+  hist.alloc(ndiag);
+  TB_CUDA(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
+  if (s->nchunks) {
+    int64_t need = (s->nchunks + 7) / 8, cap = (int64_t)s->sm_count * 4;
+    int g = (int)(need < cap ? need : cap);
+    k_diag_hist<<<g, 256, 0, st>>>(s->col.p, s->val.p, s->chunk_beg.p, s->chunk_row.p, s->rowptr.p,
+                                   s->nchunks, s->row_begin, s->bad.p, s->chrom_of.p, ndiag, hist.p);
+  }
+  unsigned long long *src = hist.p;
+  if (s->world > 1) {
+    red.alloc(ndiag);
+    allreduce_i64(s, (const long long *)hist.p, (long long *)red.p, ndiag);
+    src = red.p;
+  }
+  TB_CUDA(cudaMemcpyAsync(h_sum_d, src, ndiag * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+}
+
+}  // namespace tb

@@ -1,0 +1,342 @@
+"""``HiC_data``: the reference's container surface over a GPU-resident contact store.
+
+Mirrors ``pytadbit.HiC_data`` (reference: _pytadbit/hic_data.py:54-181, 318-444) for the
+matrix-balancing path: same constructor arguments, ``len()``, ``hic[i, j]``,
+``filter_columns``, ``sum``, ``normalize_expected``, ``normalize_hic``, ``save_biases`` /
+``load_biases``, ``get_hic_data_as_csr`` and the attributes ``bias``, ``bads``,
+``expected``, ``chromosomes``, ``sections``, ``section_pos``, ``resolution``,
+``symmetricized``.  The cells live in HBM as a ``ContactStore``; all reductions are
+CUDA kernels behind the C-ABI.  Everything else of the reference class (compartments,
+writers, ...) is out of scope.
+"""
+from collections import OrderedDict
+from pickle import HIGHEST_PROTOCOL, dump, load
+
+import numpy as np
+
+from .hic_filtering import filter_by_mean, filter_by_zero_count
+from .normalize_hic import expected, iterative
+from .store import ContactStore
+from .vectors import BinVector
+
+_INT32_MAX = 2147483647
+
+
+def isclose(a, b, rel_tol=1e-09, abs_tol=0.0):
+    return abs(a - b) <= max(rel_tol * max(abs(a), abs(b)), abs_tol)
+
+
+def _as_key_value_arrays(items):
+    """dict or iterable of (key, value) -> (keys int64, values) in insertion order,
+    later duplicates overriding earlier ones as a dict would."""
+    if not isinstance(items, dict):
+        items = dict(items)
+    n = len(items)
+    keys = np.fromiter(items.keys(), dtype=np.int64, count=n)
+    vals = np.array(list(items.values())) if n else np.zeros(0, dtype=np.int64)
+    return keys, vals
+
+
+def _symmetric_upper(keys, vals, size):
+    """Upper-triangle cells of the matrix the reference would hold after
+    ``_symmetricize`` (hic_data.py:83-118).
+
+    The reference inspects the first non-zero off-diagonal cells (in dict order): if one
+    differs from its mirror the matrix is completed -- mirrors copied when one side is
+    empty, both sides summed when both hold counts -- otherwise it is taken as is.
+    """
+    order = np.argsort(keys, kind="stable")
+    skeys, svals = keys[order], vals[order]
+
+    def lookup(k):
+        pos = np.searchsorted(skeys, k)
+        pos = np.minimum(pos, max(skeys.size - 1, 0))
+        found = (skeys[pos] == k) if skeys.size else np.zeros(np.shape(k), dtype=bool)
+        return found, pos
+
+    rows, cols = np.divmod(keys, size)
+    mirror_found, mirror_pos = lookup(cols * size + rows)
+    mirror_val = np.where(mirror_found, svals[mirror_pos] if skeys.size else 0, 0)
+
+    # --- detection on the first cells, as the reference does -------------------------
+    symmetric, to_sum, seen = True, False, 0
+    for n in np.flatnonzero((rows != cols) & (vals != 0)):
+        if not isclose(vals[n], mirror_val[n]):
+            to_sum = bool(mirror_val[n] != 0)
+            symmetric = False
+            break
+        if seen > 10:
+            break
+        seen += 1
+
+    upper = rows <= cols
+    lower = ~upper
+    if symmetric:
+        # cells only present below the diagonal would be invisible to an upper store
+        if np.any(lower & ~mirror_found) or np.any(
+                upper & mirror_found & ~np.isclose(vals, mirror_val, rtol=1e-9, atol=0)):
+            raise ValueError('matrix is neither symmetric nor consistently half-filled')
+        return rows[upper], cols[upper], vals[upper]
+    if to_sum:
+        # both mirrors summed; a pair present on both sides is visited twice (hic_data.py:106-111)
+        tot = np.where(rows == cols, vals, np.where(mirror_found, 2 * (vals + mirror_val), vals))
+    else:
+        # mirrors copied: the cell visited first fixes the pair (hic_data.py:112-116)
+        visit = np.arange(keys.size)
+        mirror_visit = np.where(mirror_found, order[mirror_pos] if skeys.size else 0, keys.size)
+        tot = np.where(visit <= mirror_visit, vals, mirror_val)
+    keep = upper | (lower & ~mirror_found)
+    r = np.where(upper, rows, cols)[keep]
+    c = np.where(upper, cols, rows)[keep]
+    return r, c, tot[keep]
+
+
+class HiC_data(object):
+    """Hi-C matrix whose cells are resident on a B200; see the module docstring.
+
+    :param items: dict (or iterable of pairs) ``{row * size + col: count}`` as the
+       reference takes it, either triangle or both
+    :param size: number of bins
+    :param None chromosomes: OrderedDict ``name -> number of bins``
+    :param None dict_sec: ``{(chromosome, position): bin}``
+    :param 0 device: CUDA device ordinal
+    """
+
+    def __init__(self, items, size, chromosomes=None, dict_sec=None,
+                 resolution=1, masked=None, symmetricized=False, device=0):
+        keys, vals = _as_key_value_arrays(items)
+        if keys.size and (keys.min() < 0 or keys.max() >= size * size):
+            raise IndexError('ERROR: position larger than %s^2' % size)
+        rows, cols, vals = _symmetric_upper(keys, vals, size)
+        self._init_common(size, chromosomes, dict_sec, resolution, masked, symmetricized)
+        self._set_cells(rows, cols, vals, device)
+
+    # -- alternative constructors ------------------------------------------------------
+    @classmethod
+    def from_coo(cls, size, rows, cols, vals, chromosomes=None, dict_sec=None, resolution=1,
+                 masked=None, symmetricized=False, device=0):
+        """From upper-triangle cells (``rows[k] <= cols[k]``, each cell once)."""
+        self = cls.__new__(cls)
+        self._init_common(size, chromosomes, dict_sec, resolution, masked, symmetricized)
+        self._set_cells(np.asarray(rows), np.asarray(cols), np.asarray(vals), device)
+        return self
+
+    @classmethod
+    def from_store(cls, store, chromosomes=None, dict_sec=None, resolution=1, masked=None,
+                   symmetricized=False):
+        """Around a store that is already resident (synthetic generator, device data)."""
+        self = cls.__new__(cls)
+        self._init_common(store.size, chromosomes, dict_sec, resolution, masked, symmetricized)
+        self.store = store
+        self._keys = self._vals = None
+        return self
+
+    def _init_common(self, size, chromosomes, dict_sec, resolution, masked, symmetricized):
+        self.__size = int(size)
+        self._size2 = self.__size ** 2
+        self.bias = None
+        self.bads = masked or {}
+        self.chromosomes = chromosomes
+        self.sections = dict_sec
+        self.section_pos = {}
+        self.resolution = resolution
+        self.expected = None
+        self.symmetricized = symmetricized
+        self.compartments = {}
+        self.last_trace = None
+        if self.chromosomes:                                   # hic_data.py:70-75
+            total = 0
+            for crm in self.chromosomes:
+                self.section_pos[crm] = (total, total + self.chromosomes[crm])
+                total += self.chromosomes[crm]
+        if self.sections == {}:                                # hic_data.py:76-79
+            self.section_pos = {None: (0, self.__size)}
+            self.sections = dict([((None, i), i) for i in range(0, self.__size)])
+
+    def _set_cells(self, rows, cols, vals, device):
+        vals = np.asarray(vals)
+        if vals.size:
+            if vals.dtype.kind == 'f':
+                if not np.all(vals == np.rint(vals)):
+                    raise NotImplementedError(
+                        'tadbit_b200 balances raw integer counts; normalised (float) '
+                        'matrices are outside the accelerated path')
+                vals = vals.astype(np.int64)
+            if np.abs(vals).max() > _INT32_MAX:
+                raise OverflowError('cell count does not fit int32')
+        rows = np.asarray(rows, dtype=np.int64)
+        cols = np.asarray(cols, dtype=np.int64)
+        if rows.size and (rows.min() < 0 or cols.max() >= self.__size):
+            raise IndexError('ERROR: row or column larger than %s' % self.__size)
+        keys = rows * self.__size + cols
+        order = np.argsort(keys, kind="stable")
+        self._keys = keys[order]
+        self._vals = vals[order].astype(np.int64)
+        chrom = self.chromosomes if self.chromosomes else None
+        self.store = ContactStore.from_coo(self.__size, rows[order], cols[order],
+                                           self._vals, chromosomes=chrom, device=device)
+
+    # -- dict-like surface --------------------------------------------------------------
+    def __len__(self):
+        return self.__size
+
+    def _host_cells(self):
+        if self._keys is None:
+            r, c, v = self.store.export_upper()
+            self._keys = r.astype(np.int64) * self.__size + c
+            self._vals = v.astype(np.int64)
+        return self._keys, self._vals
+
+    def get(self, pos, default=0):
+        row, col = divmod(int(pos), self.__size)
+        if row > col:
+            row, col = col, row
+        keys, vals = self._host_cells()
+        k = row * self.__size + col
+        p = int(np.searchsorted(keys, k))
+        if p < keys.size and keys[p] == k:
+            return int(vals[p])
+        return default
+
+    def __getitem__(self, row_col):
+        try:
+            row, col = row_col
+            pos = row * self.__size + col
+            if pos > self._size2:
+                raise IndexError('ERROR: row or column larger than %s' % self.__size)
+            return self.get(pos, 0)
+        except TypeError:
+            if row_col > self._size2:
+                raise IndexError('ERROR: position %d larger than %s^2' % (row_col, self.__size))
+            return self.get(row_col, 0)
+
+    def __setitem__(self, row_col, val):
+        raise NotImplementedError('the GPU-resident contact store is immutable; build a new '
+                                  'HiC_data to change cells')
+
+    def items(self):
+        """(key, value) over BOTH triangles, as the reference's dict holds them."""
+        keys, vals = self._host_cells()
+        n = self.__size
+        for k, v in zip(keys.tolist(), vals.tolist()):
+            yield k, v
+            i, j = divmod(k, n)
+            if i != j:
+                yield j * n + i, v
+
+    def keys(self):
+        return (k for k, _ in self.items())
+
+    def values(self):
+        return (v for _, v in self.items())
+
+    def __iter__(self):
+        return self.keys()
+
+    def get_hic_data_as_csr(self):
+        """scipy CSR of the full symmetric matrix (hic_data.py:166-181)."""
+        from scipy.sparse import csr_matrix
+        keys, vals = self._host_cells()
+        i, j = np.divmod(keys, self.__size)
+        od = i != j
+        rows = np.concatenate([i, j[od]])
+        cols = np.concatenate([j, i[od]])
+        data = np.concatenate([vals, vals[od]]).astype(float)
+        return csr_matrix((data, (rows, cols)), shape=(self.__size, self.__size))
+
+    # -- the accelerated path -------------------------------------------------------------
+    def filter_columns(self, draw_hist=False, savefig=None, perc_zero=99,
+                       by_mean=True, min_count=None, silent=False):
+        """Flag artifactual columns (hic_data.py:318-348); result in ``self.bads``."""
+        self.bads = filter_by_zero_count(self, perc_zero, min_count=min_count,
+                                         silent=silent)
+        if by_mean:
+            self.bads.update(filter_by_mean(
+                self, draw_hist=draw_hist, silent=silent,
+                savefig=savefig, bads=self.bads))
+        if not silent:
+            print('Found %d of %d columns with poor signal' % (len(self.bads),
+                                                               len(self)))
+
+    def sum(self, bias=None, bads=None):
+        """Sum of the matrix skipping bad columns, optionally divided by the biases
+        (hic_data.py:350-375).  K3 on the device."""
+        from ._capi import bad_mask
+        bads = bads or self.bads
+        mask = bad_mask(self.__size, bads)
+        if bias:
+            arr = bias.to_array() if isinstance(bias, BinVector) else np.array(
+                [bias[i] for i in range(self.__size)], dtype=np.float64)
+            return self.store.norm_sum(arr, mask)
+        return int(self.store.norm_sum(None, mask))
+
+    def normalize_expected(self, **kwargs):
+        self.expected = expected(self, bads=self.bads, **kwargs)
+
+    def normalize_hic(self, iterations=0, max_dev=0.1, silent=False,
+                      sqrt=False, factor=1):
+        """Compute the ICE biases (hic_data.py:380-413); result in ``self.bias``.
+
+        :param 0 iterations: number of iterations
+        :param 0.1 max_dev: stop when the maximum deviation between row sums drops below
+        :param False sqrt: use the square root of the biases
+        :param 1 factor: final mean number of normalised interactions per cell
+        """
+        bias = iterative(self, iterations=iterations,
+                         max_dev=max_dev, bads=self.bads,
+                         verbose=not silent)
+        values = bias.to_array()
+        if sqrt:
+            values = values ** 0.5
+            bias = BinVector(values)
+        if factor:
+            if not silent:
+                print('rescaling to factor %d' % factor)
+                print('  - getting the sum of the matrix')
+            norm_sum = self.sum(bias)
+            if not silent:
+                print('    => %.3f' % norm_sum)
+                print('  - rescaling biases')
+            target = (norm_sum / float(len(self) * len(self) * factor)) ** 0.5
+            bias = BinVector(values * target)
+        self.bias = bias
+
+    def save_biases(self, fnam, protocol=None):
+        """Pickle biases, decay and bad columns in the reference's format
+        (hic_data.py:415-429): plain dicts, readable by TADbit's loaders."""
+        bias = self.bias.to_dict() if isinstance(self.bias, BinVector) else self.bias
+        with open(fnam, 'wb') as out:
+            dump({'biases': bias,
+                  'decay': self.expected,
+                  'badcol': self.bads,
+                  'resolution': self.resolution}, out,
+                 protocol if protocol else HIGHEST_PROTOCOL)
+
+    def load_biases(self, fnam, protocol=None):
+        """hic_data.py:431-444."""
+        with open(fnam, 'rb') as fh:
+            biases = load(fh)
+        if biases['resolution'] != self.resolution:
+            raise Exception(('Error: resolution in Pickle (%d) does not match '
+                             'the one of this HiC_data object (%d)') % (
+                                 biases['resolution'], self.resolution))
+        self.bias = biases['biases']
+        self.expected = biases['decay']
+        self.bads = biases['badcol']
+
+
+def from_reference(hic_data, device=0):
+    """Build a :class:`HiC_data` from a TADbit ``pytadbit.HiC_data`` (a dict subclass) or
+    any ``{row * N + col: count}`` mapping that has ``len() == N`` semantics."""
+    size = len(hic_data)
+    items = dict.items(hic_data) if isinstance(hic_data, dict) else hic_data.items()
+    new = HiC_data(items, size,
+                   chromosomes=getattr(hic_data, 'chromosomes', None),
+                   dict_sec=getattr(hic_data, 'sections', None),
+                   resolution=getattr(hic_data, 'resolution', 1),
+                   masked=getattr(hic_data, 'bads', None),
+                   symmetricized=getattr(hic_data, 'symmetricized', False), device=device)
+    return new
+
+
+__all__ = ["HiC_data", "from_reference", "OrderedDict"]

@@ -1,0 +1,180 @@
+"""Device-resident contact store: thin object wrapper over the C-ABI handle.
+
+One ``ContactStore`` = one ``tb_store`` = the rows of the full symmetric matrix that one
+GPU owns.  All numerics run in libtadbit_b200 (CUDA); this module only moves numpy
+buffers across the boundary.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import SynthParams, check, lib, ptr
+
+
+def _offsets(size, chromosomes):
+    """chromosomes (OrderedDict name -> nbins) -> (n_chrom, int64 offsets or None)."""
+    if not chromosomes:
+        return 0, None
+    sizes = np.array([int(v) for v in chromosomes.values()], dtype=np.int64)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    if offs[-1] != size:
+        raise ValueError("chromosome sizes sum to %d, matrix has %d bins" % (offs[-1], size))
+    return len(sizes), offs
+
+
+class ContactStore(object):
+    def __init__(self, handle, size):
+        self._h = handle
+        self.size = int(size)
+
+    # -- construction ---------------------------------------------------------
+    @classmethod
+    def from_coo(cls, size, rows, cols, vals, chromosomes=None, row_block=None, device=0):
+        """Upper-triangle cells (row <= col, unique) as host arrays."""
+        rows, cols, vals = _capi.as_i32(rows), _capi.as_i32(cols), _capi.as_i32(vals)
+        if not (rows.shape == cols.shape == vals.shape and rows.ndim == 1):
+            raise ValueError("rows, cols, vals must be 1-D arrays of equal length")
+        n_chrom, offs = _offsets(size, chromosomes)
+        rb, re = row_block if row_block is not None else (0, size)
+        out = C.c_void_p()
+        check(lib().tb_store_create_coo(
+            size, rows.size, rows.ctypes.data, cols.ctypes.data, vals.ctypes.data,
+            _capi.TB_MEM_HOST, n_chrom, ptr(offs, C.c_int64) if offs is not None else None,
+            rb, re, device, C.byref(out)))
+        return cls(out, size)
+
+    @classmethod
+    def from_device_pointers(cls, size, nnz, d_rows, d_cols, d_vals, chromosomes=None,
+                             row_block=None, device=0):
+        """Cells already resident on the device (int32 arrays, e.g. torch tensors'
+        ``data_ptr()``); the caller keeps ownership of those buffers."""
+        n_chrom, offs = _offsets(size, chromosomes)
+        rb, re = row_block if row_block is not None else (0, size)
+        out = C.c_void_p()
+        check(lib().tb_store_create_coo(
+            size, nnz, d_rows, d_cols, d_vals, _capi.TB_MEM_DEVICE, n_chrom,
+            ptr(offs, C.c_int64) if offs is not None else None, rb, re, device, C.byref(out)))
+        return cls(out, size)
+
+    @classmethod
+    def synthetic(cls, size, params, chromosomes=None, row_block=None, device=0):
+        n_chrom, offs = _offsets(size, chromosomes)
+        rb, re = row_block if row_block is not None else (0, size)
+        out = C.c_void_p()
+        check(lib().tb_store_create_synthetic(
+            size, n_chrom, ptr(offs, C.c_int64) if offs is not None else None,
+            C.byref(params), rb, re, device, C.byref(out)))
+        return cls(out, size)
+
+    @staticmethod
+    def synthetic_row_counts(size, params, chromosomes=None, row_block=None, device=0):
+        n_chrom, offs = _offsets(size, chromosomes)
+        rb, re = row_block if row_block is not None else (0, size)
+        counts = np.zeros(re - rb, dtype=np.int64)
+        check(lib().tb_synthetic_row_counts(
+            size, n_chrom, ptr(offs, C.c_int64) if offs is not None else None,
+            C.byref(params), rb, re, device, ptr(counts, C.c_int64)))
+        return counts
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            lib().tb_store_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- info -----------------------------------------------------------------
+    def info(self):
+        v = [C.c_int64() for _ in range(6)]
+        check(lib().tb_store_info(self._h, *[C.byref(x) for x in v]))
+        keys = ("nbins", "row_begin", "row_end", "nnz_upper", "nnz_full", "device_bytes")
+        return dict(zip(keys, [x.value for x in v]))
+
+    def export_upper(self):
+        """Owned upper-triangle cells, row-major sorted: (rows, cols, vals) int32."""
+        n = C.c_int64()
+        check(lib().tb_store_export_upper(self._h, C.byref(n), None, None, None))
+        r = np.empty(n.value, dtype=np.int32)
+        c = np.empty(n.value, dtype=np.int32)
+        v = np.empty(n.value, dtype=np.int32)
+        if n.value:
+            check(lib().tb_store_export_upper(self._h, C.byref(n), ptr(r, C.c_int32),
+                                              ptr(c, C.c_int32), ptr(v, C.c_int32)))
+        return r, c, v
+
+    # -- multi-GPU ------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        buf = np.zeros(128, dtype=np.uint8)
+        check(lib().tb_comm_unique_id(ptr(buf, C.c_uint8)))
+        return buf
+
+    def comm_init(self, rank, world, unique_id):
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        check(lib().tb_comm_init(self._h, rank, world, ptr(uid, C.c_uint8)))
+
+    # -- kernels ----------------------------------------------------------------
+    def _mask(self, bad):
+        if bad is None:
+            return None, None
+        m = np.ascontiguousarray(bad, dtype=np.uint8)
+        if m.shape != (self.size,):
+            raise ValueError("bad mask must have %d entries" % self.size)
+        return m, ptr(m, C.c_uint8)
+
+    def row_stats(self):
+        nnz = np.zeros(self.size, dtype=np.int64)
+        rsum = np.zeros(self.size, dtype=np.int64)
+        check(lib().tb_row_stats(self._h, ptr(nnz, C.c_int64), ptr(rsum, C.c_int64)))
+        return nnz, rsum
+
+    def col_sums_masked(self, bad=None):
+        m, mp = self._mask(bad)
+        out = np.zeros(self.size, dtype=np.int64)
+        check(lib().tb_col_sums_masked(self._h, mp, ptr(out, C.c_int64)))
+        return out
+
+    def ice(self, bad=None, iterations=0, max_dev=1e-5):
+        """-> (bias float64[N], trace float64[passes,4] = Smin, meanS, Smax, dev)."""
+        m, mp = self._mask(bad)
+        bias = np.empty(self.size, dtype=np.float64)
+        trace = np.zeros((iterations + 1, 4), dtype=np.float64)
+        npass = C.c_int32(0)
+        check(lib().tb_ice(self._h, mp, int(iterations), float(max_dev), ptr(bias, C.c_double),
+                           ptr(trace, C.c_double), C.byref(npass)))
+        ntrace = npass.value if iterations > 0 else 0
+        return bias, trace[:ntrace]
+
+    def ice_timing(self):
+        a, b = C.c_double(), C.c_double()
+        n, t = C.c_int32(), C.c_int32()
+        check(lib().tb_ice_last_timing(self._h, C.byref(a), C.byref(b), C.byref(n), C.byref(t)))
+        return dict(loop_ms=a.value, rowsum_ms=b.value, rowsum_launches=n.value,
+                    total_launches=t.value)
+
+    def norm_sum(self, bias=None, bad=None):
+        m, mp = self._mask(bad)
+        bp = None
+        if bias is not None:
+            bias = np.ascontiguousarray(bias, dtype=np.float64)
+            if bias.shape != (self.size,):
+                raise ValueError("bias must have %d entries" % self.size)
+            bp = ptr(bias, C.c_double)
+        out = C.c_double()
+        check(lib().tb_norm_sum(self._h, bp, mp, C.byref(out)))
+        return out.value
+
+    def diag_sums(self, bad, ndiag):
+        m, mp = self._mask(bad)
+        out = np.zeros(max(int(ndiag), 0), dtype=np.int64)
+        if ndiag > 0:
+            check(lib().tb_diag_sums(self._h, mp, int(ndiag), ptr(out, C.c_int64)))
+        return out
+
+
+__all__ = ["ContactStore", "SynthParams"]

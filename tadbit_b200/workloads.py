@@ -1,0 +1,80 @@
+"""Synthetic workloads of BASELINE.json (shapes and generator parameters) and the
+nnz-balanced row sharding used when one matrix is spread over several GPUs."""
+from collections import OrderedDict
+
+import numpy as np
+
+from ._capi import SynthParams
+from .store import ContactStore
+
+# hg38 primary assembly, chr1..22, X, Y
+HG38 = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973,
+        145138636, 138394717, 133797422, 135086622, 133275309, 114364328, 107043718,
+        101991189, 90338345, 83257441, 80373285, 58617616, 64444167, 46709983, 50818468,
+        156040895, 57227415]
+HG38_NAMES = ["chr%d" % i for i in range(1, 23)] + ["chrX", "chrY"]
+SEED = 20261019
+
+
+def genome_bins(resolution, chroms=None):
+    """bins per chromosome = len_bp // resolution + 1 (reference: parsers/hic_parser.py:578)."""
+    idx = range(len(HG38)) if chroms is None else chroms
+    return OrderedDict((HG38_NAMES[i], HG38[i] // resolution + 1) for i in idx)
+
+
+def workload(name):
+    """-> dict(name, chromosomes, size, params, description)."""
+    if name == "c2":        # chr1 at 10 kb, dense
+        chroms = genome_bins(10000, [0])
+        params = SynthParams(seed=SEED, cis_scale=2.8e5, cis_alpha=1.08, trans_mean=0.0,
+                             vis_sigma=0.35, low_frac=0.02, low_scale=0.02, empty_frac=0.005)
+        desc = "synthetic human chr1 @10kb, dense Poisson x power-law (BASELINE configs[1])"
+    elif name == "c3":      # genome-wide 5 kb, sparse
+        chroms = genome_bins(5000)
+        params = SynthParams(seed=SEED, cis_scale=1300.0, cis_alpha=1.08, trans_mean=1.1e-3,
+                             vis_sigma=0.35, low_frac=0.02, low_scale=0.02, empty_frac=0.005)
+        desc = "synthetic genome-wide human @5kb (BASELINE configs[2])"
+    elif name == "c3s":     # 1/8 genome (chr1-3) at 5 kb: sparse profile at a size quick to build
+        chroms = genome_bins(5000, [0, 1, 2])
+        params = SynthParams(seed=SEED, cis_scale=1300.0, cis_alpha=1.08, trans_mean=1.1e-3,
+                             vis_sigma=0.35, low_frac=0.02, low_scale=0.02, empty_frac=0.005)
+        desc = "synthetic human chr1-3 @5kb (sparse profile of configs[2], reduced)"
+    elif name == "small":   # parity-sized
+        chroms = OrderedDict([("chrA", 1400), ("chrB", 900), ("chrC", 500)])
+        params = SynthParams(seed=SEED, cis_scale=600.0, cis_alpha=1.08, trans_mean=0.02,
+                             vis_sigma=0.35, low_frac=0.03, low_scale=0.02, empty_frac=0.01)
+        desc = "small 3-chromosome synthetic"
+    else:
+        raise ValueError("unknown workload %r" % name)
+    return dict(name=name, chromosomes=chroms, size=int(sum(chroms.values())), params=params,
+                description=desc)
+
+
+def balanced_row_blocks(row_counts, world):
+    """Contiguous row blocks with (nearly) equal numbers of stored cells."""
+    csum = np.concatenate([[0], np.cumsum(row_counts, dtype=np.int64)])
+    total = csum[-1]
+    bounds = [0]
+    for r in range(1, world):
+        bounds.append(int(np.searchsorted(csum, total * r / world)))
+    bounds.append(len(row_counts))
+    for r in range(1, world + 1):
+        bounds[r] = max(bounds[r], bounds[r - 1])
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
+def build_sharded(wl, rank, world, device, gather=None):
+    """Generate this rank's block of the synthetic matrix.  ``gather`` is a callable that
+    all-gathers a numpy int64 array over ranks (host plumbing, e.g. torch.distributed)."""
+    n = wl["size"]
+    if world == 1:
+        return ContactStore.synthetic(n, wl["params"], chromosomes=wl["chromosomes"],
+                                      device=device), (0, n)
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    mine = ContactStore.synthetic_row_counts(n, wl["params"], chromosomes=wl["chromosomes"],
+                                             row_block=(lo, hi), device=device)
+    counts = np.concatenate(gather(mine))
+    blocks = balanced_row_blocks(counts, world)
+    store = ContactStore.synthetic(n, wl["params"], chromosomes=wl["chromosomes"],
+                                   row_block=blocks[rank], device=device)
+    return store, blocks[rank]
