@@ -1,0 +1,93 @@
+"""Run under torchrun (one rank per GPU): row-sharded path vs the single-GPU path.
+
+Each rank builds its nnz-balanced row block of the same synthetic matrix, joins the NCCL
+communicator of the library, and runs filter statistics, ICE, normalised sum and diagonal
+sums.  Rank 0 also builds the whole matrix on its GPU and compares: integers bit-exact,
+biases bit-identical (same chunk partials, same reduction order; the all-reduce only adds
+zeros)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import tadbit_b200
+    from tadbit_b200 import workloads
+    from tadbit_b200._capi import bad_mask
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    dist.init_process_group("gloo")
+    torch.cuda.set_device(local)
+    wl = workloads.workload(sys.argv[1] if len(sys.argv) > 1 else "small")
+
+    def gather(arr):
+        out = [None] * world
+        dist.all_gather_object(out, arr)
+        return out
+
+    store, block = workloads.build_sharded(wl, rank, world, local, gather)
+    uid = [tadbit_b200.ContactStore.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    store.comm_init(rank, world, uid[0])
+    hic = tadbit_b200.HiC_data.from_store(store, chromosomes=wl["chromosomes"])
+    hic.filter_columns(silent=True)
+    hic.normalize_hic(iterations=100, max_dev=1e-5, silent=True, factor=None)
+    raw_bias = hic.bias.to_array().copy()
+    hic.normalize_hic(iterations=100, max_dev=1e-5, silent=True)
+    hic.normalize_expected()
+    nnz, rsum = store.row_stats()
+    raw = hic.sum()
+    result = dict(bads=hic.bads, bias=hic.bias.to_array(), raw_bias=raw_bias, expected=hic.expected, nnz=nnz,
+                  rsum=rsum, raw=raw, passes=len(hic.last_trace), block=block,
+                  nnz_upper=store.info()["nnz_upper"])
+    allres = gather(result)
+    ok = True
+    if rank == 0:
+        # every rank must hold the same answer
+        for r in range(1, world):
+            ok &= allres[r]["bads"] == allres[0]["bads"]
+            ok &= np.array_equal(allres[r]["bias"], allres[0]["bias"])
+            ok &= allres[r]["expected"] == allres[0]["expected"]
+        one = tadbit_b200.ContactStore.synthetic(wl["size"], wl["params"],
+                                                 chromosomes=wl["chromosomes"], device=local)
+        ref = tadbit_b200.HiC_data.from_store(one, chromosomes=wl["chromosomes"])
+        ref.filter_columns(silent=True)
+        ref.normalize_hic(iterations=100, max_dev=1e-5, silent=True, factor=None)
+        ref_raw = ref.bias.to_array().copy()
+        ref.normalize_hic(iterations=100, max_dev=1e-5, silent=True)
+        ref.normalize_expected()
+        n1, s1 = one.row_stats()
+        checks = {
+            "blocks cover rows": [b["block"] for b in allres][0][0] == 0 and
+                                 allres[-1]["block"][1] == wl["size"],
+            "nnz_upper adds up": sum(b["nnz_upper"] for b in allres) == one.info()["nnz_upper"],
+            "row nnz": np.array_equal(n1, nnz), "row sums": np.array_equal(s1, rsum),
+            "bads": ref.bads == hic.bads, "raw sum": ref.sum() == raw,
+            "passes": len(ref.last_trace) == len(hic.last_trace),
+            # ICE itself: same chunk partials, same order, all-reduce adds zeros -> same bits
+            "ICE bias bit-identical": np.array_equal(ref_raw, raw_bias),
+            # factor step sums per-rank partial dot products: 1e-13 relative
+            "rescaled bias 1e-13": np.allclose(ref.bias.to_array(), hic.bias.to_array(),
+                                               rtol=1e-13, atol=0),
+            "expected": ref.expected == hic.expected,
+        }
+        for k, v in checks.items():
+            print("%-22s %s" % (k, "ok" if v else "FAIL"))
+            ok &= bool(v)
+        print("MULTIGPU_RESULT", "PASS" if ok else "FAIL", "world", world,
+              "blocks", [b["block"] for b in allres])
+    dist.barrier()
+    store.close()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
