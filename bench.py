@@ -241,10 +241,13 @@ def main():
     alg_bytes = 12.0 * info["nnz_upper"] + 24.0 * (block[1] - block[0])
     k1_ms = rowsum_ms / max(rowsum_n, 1)
     achieved = alg_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0
-    layout_bytes = 8.0 * info["nnz_full"]
+    lay = store.layout()
+    csr_walk = os.environ.get("TB_ROWSUM") == "csr"
+    layout_bytes = 8.0 * info["nnz_full"] if csr_walk else float(lay["stream_bytes"])
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "kernel": "k_chunk_reduce<F64> (K1 row sum)", "kernel_ms": k1_ms,
+                "kernel": "k_chunk_reduce<F64> (CSR walk)" if csr_walk else "k_rowsum (K1, compact stream)",
+                "kernel_ms": k1_ms, "stream_encodings": lay["encodings"],
                 "kernel_share_of_step": rowsum_ms / dev_ms if dev_ms else None,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "layout_bytes_per_launch": layout_bytes,

@@ -110,6 +110,10 @@ int tb_store_destroy(tb_store *s);
 int tb_store_info(const tb_store *s, int64_t *nbins, int64_t *row_begin, int64_t *row_end,
                   int64_t *nnz_upper_owned, int64_t *nnz_full_owned, int64_t *device_bytes);
 
+/* Layout of the compact row-sum stream: out[0] payload bytes, out[1..5] chunks encoded as
+ * S32, S16, D32, D16, D8 (tadbit_b200/csrc/encode.cu), out[6] chunks, out[7] CSR bytes. */
+int tb_store_layout(const tb_store *s, int64_t out[8]);
+
 /* Export the owned upper-triangle cells (row in block, row <= col), row-major sorted.
  * Call with row == NULL to get the count in *nnz first.  Buffers are HOST. */
 int tb_store_export_upper(const tb_store *s, int64_t *nnz, int32_t *h_row, int32_t *h_col,

@@ -46,6 +46,7 @@ PROTOTYPES = {
                                  C.c_int64, C.c_int, _i64p], C.c_int),
     "tb_store_destroy": ([_store], C.c_int),
     "tb_store_info": ([_store, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p], C.c_int),
+    "tb_store_layout": ([_store, _i64p], C.c_int),
     "tb_store_export_upper": ([_store, _i64p, _i32p, _i32p, _i32p], C.c_int),
     "tb_comm_unique_id": ([_u8p], C.c_int),
     "tb_comm_init": ([_store, C.c_int32, C.c_int32, _u8p], C.c_int),

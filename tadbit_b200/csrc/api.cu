@@ -204,6 +204,15 @@ int tb_store_info(const tb_store *s, int64_t *nbins, int64_t *row_begin, int64_t
   return TB_OK;
 }
 
+int tb_store_layout(const tb_store *s, int64_t out[8]) {
+  if (!s || !out) { set_error("null argument"); return TB_ERR_ARG; }
+  out[0] = s->enc_bytes;
+  for (int k = 0; k < 5; ++k) out[1 + k] = s->enc_chunks[k];
+  out[6] = s->nchunks;
+  out[7] = (int64_t)(s->col.bytes() + s->val.bytes() + s->rowptr.bytes());
+  return TB_OK;
+}
+
 int tb_store_export_upper(const tb_store *s, int64_t *nnz, int32_t *h_row, int32_t *h_col,
                           int32_t *h_val) {
   return guarded([&]() -> int {

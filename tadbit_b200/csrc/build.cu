@@ -99,25 +99,55 @@ __global__ void k_fill_i64(int64_t *p, int64_t n, int64_t v) {
     p[k] = v;
 }
 
-__global__ void k_row_chunk_counts(const int64_t *__restrict__ rowptr, int64_t nrows,
-                                   int64_t *nchunk) {
-  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
-       r += (int64_t)gridDim.x * blockDim.x) {
-    int64_t len = rowptr[r + 1] - rowptr[r];
-    nchunk[r] = (len + kChunk - 1) / kChunk;
+__device__ __forceinline__ int64_t lower_bound_col(const int32_t *__restrict__ col, int64_t lo,
+                                                   int64_t hi, int64_t key) {
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (col[mid] < key) lo = mid + 1; else hi = mid;
   }
+  return lo;
 }
 
-__global__ void k_fill_chunks(const int64_t *__restrict__ rowptr,
-                              const int64_t *__restrict__ row_chunk, int64_t nrows,
-                              int64_t *chunk_beg, int32_t *chunk_row) {
+// Split every row into chunks (the warp work items).  Columns are cut at multiples of kPanel:
+// a panel holding >= 1/4 of its columns becomes one chunk on its own (a candidate for the
+// dense encodings, and aligned with the same panel of every other row so that several rows
+// can share one pass over x); runs of emptier panels are merged up to kChunk cells.
+// FILL == false counts the chunks of each row, FILL == true writes them.
+template <bool FILL>
+__global__ void k_plan_chunks(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                              int64_t nrows, int64_t nbins, int64_t *__restrict__ nchunk,
+                              const int64_t *__restrict__ row_chunk, int64_t *__restrict__ chunk_beg,
+                              int32_t *__restrict__ chunk_row) {
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
        r += (int64_t)gridDim.x * blockDim.x) {
-    int64_t c0 = row_chunk[r], c1 = row_chunk[r + 1], b = rowptr[r];
-    for (int64_t c = c0; c < c1; ++c) {
-      chunk_beg[c] = b + (c - c0) * kChunk;
-      chunk_row[c] = (int32_t)r;
+    const int64_t b = rowptr[r], e = rowptr[r + 1];
+    int64_t n = 0, c = FILL ? row_chunk[r] : 0;
+    int64_t pos = b;
+    while (pos < e) {
+      const int64_t p = col[pos] / kPanel;
+      const int64_t pend = lower_bound_col(col, pos, e, (p + 1) * kPanel);
+      int64_t width = nbins - p * kPanel;
+      if (width > kPanel) width = kPanel;
+      int64_t stop = pend;
+      if ((pend - pos) * 4 < width) {           // sparse: absorb the following sparse panels
+        while (stop < e) {
+          const int64_t p2 = col[stop] / kPanel;
+          const int64_t q2 = lower_bound_col(col, stop, e, (p2 + 1) * kPanel);
+          int64_t w2 = nbins - p2 * kPanel;
+          if (w2 > kPanel) w2 = kPanel;
+          if ((q2 - stop) * 4 >= w2 || q2 - pos > kChunk) break;
+          stop = q2;
+        }
+      }
+      if (FILL) {
+        chunk_beg[c] = pos;
+        chunk_row[c] = (int32_t)r;
+        ++c;
+      }
+      ++n;
+      pos = stop;
     }
+    if (!FILL) nchunk[r] = n;
   }
 }
 
@@ -249,8 +279,8 @@ void finish_layout(tb_store *s) {
     cnt.alloc(nrows + 1);
     TB_CUDA(cudaMemsetAsync(cnt.p, 0, cnt.bytes(), st));
     if (nrows)
-      k_row_chunk_counts<<<grid_for(nrows, threads, s->sm_count), threads, 0, st>>>(
-          s->rowptr.p, nrows, cnt.p);
+      k_plan_chunks<false><<<grid_for(nrows, threads, s->sm_count), threads, 0, st>>>(
+          s->rowptr.p, s->col.p, nrows, N, cnt.p, nullptr, nullptr, nullptr);
     exclusive_scan_i64(st, cnt.p, s->row_chunk.p, nrows + 1);
   }
   int64_t nchunks = 0;
@@ -259,8 +289,11 @@ void finish_layout(tb_store *s) {
   s->chunk_beg.alloc(nchunks + 1);
   s->chunk_row.alloc(nchunks + 1);
   if (nrows)
-    k_fill_chunks<<<grid_for(nrows, threads, s->sm_count), threads, 0, st>>>(
-        s->rowptr.p, s->row_chunk.p, nrows, s->chunk_beg.p, s->chunk_row.p);
+    k_plan_chunks<true><<<grid_for(nrows, threads, s->sm_count), threads, 0, st>>>(
+        s->rowptr.p, s->col.p, nrows, N, nullptr, s->row_chunk.p, s->chunk_beg.p, s->chunk_row.p);
+  // chunk c covers cells [chunk_beg[c], chunk_beg[c+1]): close the last one
+  TB_CUDA(cudaMemcpyAsync(s->chunk_beg.p + nchunks, &s->nnz_full, sizeof(int64_t),
+                          cudaMemcpyHostToDevice, st));
   // upper-triangle count of the block
   {
     DevBuf<int64_t> us, uc, total;
@@ -281,7 +314,8 @@ void finish_layout(tb_store *s) {
   const size_t nc = nchunks ? nchunks : 1, nn = N ? N : 1;
   s->partial_f.alloc(nc);
   s->partial_i.alloc(nc);
-  s->x.alloc(nn); s->b.alloc(nn);
+  s->x.alloc(nn + kXPad); s->b.alloc(nn);
+  TB_CUDA(cudaMemsetAsync(s->x.p, 0, s->x.bytes(), st));
   s->s_part.alloc(2 * nn); s->s_full.alloc(2 * nn);
   s->i_part.alloc(2 * nn); s->i_full.alloc(2 * nn);
   s->bad.alloc(nn); s->present.alloc(nn);
@@ -293,7 +327,8 @@ void finish_layout(tb_store *s) {
   TB_CUDA(cudaMemsetAsync(s->s_part.p, 0, s->s_part.bytes(), st));
   TB_CUDA(cudaMemsetAsync(s->i_part.p, 0, s->i_part.bytes(), st));
   TB_CUDA(cudaStreamSynchronize(st));
-  s->device_bytes = s->rowptr.bytes() + s->col.bytes() + s->val.bytes() + s->chunk_beg.bytes() +
+  build_encoded(s);
+  s->device_bytes = s->enc_data.bytes() + s->enc_off.bytes() + s->enc_desc.bytes() + s->rowptr.bytes() + s->col.bytes() + s->val.bytes() + s->chunk_beg.bytes() +
                     s->chunk_row.bytes() + s->row_chunk.bytes() + s->partial_f.bytes() +
                     s->partial_i.bytes() + s->x.bytes() + s->b.bytes() +
                     s->s_part.bytes() + s->s_full.bytes() + s->i_part.bytes() + s->i_full.bytes() +

@@ -84,6 +84,12 @@ struct IceState {
 
 constexpr int kWarp = 32;
 constexpr int kChunk = 4096;      // max stored cells one warp reduces before writing a partial
+constexpr int kPanel = 4096;      // column panel of the chunk planner / dense encodings
+constexpr int kRows = 4;          // dense chunks (rows) one warp walks together
+constexpr int kXPad = 1024;       // zero tail of the gathered vector (dense chunks read past N)
+
+// chunk encodings of the compact row-sum stream
+enum { ENC_S32 = 0, ENC_S16 = 1, ENC_D32 = 2, ENC_D16 = 3, ENC_D8 = 4 };
 
 }  // namespace tb
 
@@ -104,9 +110,19 @@ struct tb_store {
   tb::DevBuf<int32_t> col, val;           // [nnz_full]
   // warp work items: <= kChunk consecutive cells of one row
   int64_t nchunks = 0;
-  tb::DevBuf<int64_t> chunk_beg;          // [nchunks+1] first cell of the chunk
+  tb::DevBuf<int64_t> chunk_beg;          // [nchunks+1] chunk c = cells [chunk_beg[c], chunk_beg[c+1])
   tb::DevBuf<int32_t> chunk_row;          // [nchunks] local row
   tb::DevBuf<int64_t> row_chunk;          // [nrows+1] first chunk of each row
+  // compact row-sum stream (encode.cu): one record per chunk, same chunk order as above
+  tb::DevBuf<uint8_t> enc_data;           // packed chunk payloads, each 16-byte aligned
+  tb::DevBuf<int64_t> enc_off;            // [nchunks] payload offset
+  tb::DevBuf<int4> enc_desc;              // [nchunks] (first column, slots or cells, encoding, 0)
+  tb::DevBuf<int32_t> work_ids;           // [nchunks] chunk ids in work order: sparse, then dense
+  int64_t n_sparse = 0, n_dense = 0;
+  tb::DevBuf<int32_t> dense_gids;         // [n_groups * kRows] dense chunk ids, same panel and
+  int64_t n_groups = 0;                   //   encoding within a group, -1 = empty seat
+  int64_t enc_bytes = 0;
+  int64_t enc_chunks[5] = {0, 0, 0, 0, 0};  // chunks per encoding
   // scratch
   tb::DevBuf<double> partial_f;           // [nchunks]
   tb::DevBuf<long long> partial_i;        // [nchunks]
@@ -134,6 +150,10 @@ void build_from_coo(tb_store *s, int64_t nnz, const int32_t *row, const int32_t 
 void setup_sections(tb_store *s);   // bin -> section id table (before any build)
 void finish_layout(tb_store *s);     // chunks + scratch once rowptr/col/val are in place
 void export_upper(const tb_store *s, int64_t *nnz, int32_t *h_row, int32_t *h_col, int32_t *h_val);
+// encode.cu
+void build_encoded(tb_store *s);     // compact row-sum stream from the CSR
+// rowsum.cu
+void launch_rowsum(tb_store *s, const double *x, const IceState *state);   // K1 over the compact stream
 // synth.cu
 void build_synthetic(tb_store *s, const tb_synth_params *p);
 void synthetic_row_counts(int64_t nbins, int32_t n_chrom, const int64_t *chrom_offsets,

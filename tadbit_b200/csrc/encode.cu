@@ -1,0 +1,227 @@
+// Compact row-sum stream.
+//
+// The ICE pass is bound by the bytes of the stored cells, so every chunk (build.cu:
+// k_plan_chunks) is re-encoded into the smallest of five layouts:
+//
+//   S32  (col:int32, val:int32) per cell                      8 B / cell
+//   S16  (col - c0 : u16, val : u16) per cell                 4 B / cell   span, values < 65536
+//   D32  one int32 per COLUMN of the chunk's panel             4 B / slot   zeros explicit
+//   D16  one u16 per column                                    2 B / slot   values < 65536
+//   D8   one u8 per column                                     1 B / slot   values < 256
+//
+// Dense chunks cover their whole kPanel-aligned column panel (a multiple of 128 slots), so
+// (padded to 512 slots) the same panel of different rows has the same shape: the row-sum kernel walks kRows such
+// chunks at once and reads x a single time for all of them.  Inside a 128-slot group the
+// slots are permuted so that lane l owns {2l, 2l+1, 64+2l, 64+2l+1}: its four values are
+// one 4/8/16-byte word and the matching x entries are two aligned 16-byte loads, contiguous
+// across the warp.
+//
+// Work order = payload order: sparse chunks first (row order), then dense chunks sorted by
+// (encoding, panel) with rows ascending inside -- each kernel streams its payload front to
+// back.  The CSR stays resident for the one-pass kernels (filter statistics, diagonal sums,
+// export).
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace tb {
+
+namespace {
+
+__device__ __forceinline__ int64_t align16(int64_t b) { return (b + 15) & ~(int64_t)15; }
+
+// position (in elements) of slot s inside the permuted dense layout
+__device__ __forceinline__ int64_t dense_pos(int64_t s) {
+  const int64_t g = s >> 7;
+  const int r = (int)(s & 127);
+  const int half = r >> 6, rr = r & 63;
+  return g * 128 + (rr >> 1) * 4 + half * 2 + (rr & 1);
+}
+
+// one warp per chunk: choose the encoding, report payload size and the work-order key
+__global__ void __launch_bounds__(256)
+k_plan(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
+       const int64_t *__restrict__ chunk_beg, int64_t nchunks, int64_t nbins,
+       int4 *__restrict__ desc, uint64_t *__restrict__ key, int32_t *__restrict__ ids) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t c = warp; c < nchunks; c += nwarp) {
+    const int64_t beg = chunk_beg[c], end = chunk_beg[c + 1];
+    int32_t vmin = 2147483647, vmax = -2147483647 - 1;
+    for (int64_t k = beg + lane; k < end; k += 32) {
+      const int32_t v = val[k];
+      vmin = min(vmin, v);
+      vmax = max(vmax, v);
+    }
+    for (int o = 16; o; o >>= 1) {
+      vmin = min(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+      vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    }
+    if (lane == 0) {
+      const int64_t count = end - beg;
+      const int32_t cfirst = col[beg], clast = col[end - 1];
+      const bool nonneg = vmin >= 0;
+      int enc = ENC_S32;
+      int64_t best = 8 * count;
+      if (nonneg && vmax < 65536 && (int64_t)clast - cfirst < 65536 && 4 * count < best) {
+        enc = ENC_S16; best = 4 * count;
+      }
+      int32_t c0 = cfirst;
+      int64_t n = count;
+      if (cfirst / kPanel == clast / kPanel) {          // inside one panel: dense is possible
+        const int32_t p0 = (cfirst / kPanel) * kPanel;
+        int64_t width = nbins - p0;
+        if (width > kPanel) width = kPanel;
+        const int64_t nslots = (width + 511) & ~(int64_t)511;   // whole 512-byte sub-blocks (rowsum.cu)
+        int denc = -1;
+        int64_t dbest = best + 1;
+        if (4 * nslots <= best) { denc = ENC_D32; dbest = 4 * nslots; }
+        if (nonneg && vmax < 65536 && 2 * nslots <= best) { denc = ENC_D16; dbest = 2 * nslots; }
+        if (nonneg && vmax < 256 && nslots <= best) { denc = ENC_D8; dbest = nslots; }
+        if (denc >= 0) { enc = denc; best = dbest; c0 = p0; n = nslots; }
+      }
+      desc[c] = make_int4(c0, (int)n, enc, (int)align16(best));
+      // sparse chunks keep row order (key 0); dense chunks sort by (encoding, panel)
+      key[c] = enc >= ENC_D32 ? (((uint64_t)1 << 40) | ((uint64_t)enc << 32) | (uint32_t)c0) : 0;
+      ids[c] = (int32_t)c;
+    }
+  }
+}
+
+__global__ void k_sorted_bytes(const int32_t *__restrict__ ids, const int4 *__restrict__ desc,
+                               int64_t nchunks, int64_t *__restrict__ bytes) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nchunks;
+       k += (int64_t)gridDim.x * blockDim.x)
+    bytes[k] = desc[ids[k]].w;
+}
+
+__global__ void k_scatter_off(const int32_t *__restrict__ ids, const int64_t *__restrict__ off_sorted,
+                              int64_t nchunks, int64_t *__restrict__ off) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nchunks;
+       k += (int64_t)gridDim.x * blockDim.x)
+    off[ids[k]] = off_sorted[k];
+}
+
+__global__ void __launch_bounds__(256)
+k_encode(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
+         const int64_t *__restrict__ chunk_beg, int64_t nchunks, const int4 *__restrict__ desc,
+         const int64_t *__restrict__ off, uint8_t *__restrict__ data) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t c = warp; c < nchunks; c += nwarp) {
+    const int64_t beg = chunk_beg[c], end = chunk_beg[c + 1];
+    const int4 d = desc[c];
+    uint8_t *out = data + off[c];
+    const int c0 = d.x, enc = d.z;
+    if (enc == ENC_S32) {
+      int2 *o = reinterpret_cast<int2 *>(out);
+      for (int64_t k = beg + lane; k < end; k += 32) o[k - beg] = make_int2(col[k], val[k]);
+    } else if (enc == ENC_S16) {
+      uint32_t *o = reinterpret_cast<uint32_t *>(out);
+      for (int64_t k = beg + lane; k < end; k += 32)
+        o[k - beg] = (uint32_t)(col[k] - c0) | ((uint32_t)val[k] << 16);
+    } else {
+      const int width = enc == ENC_D32 ? 4 : (enc == ENC_D16 ? 2 : 1);
+      const int64_t nbytes = (int64_t)d.y * width;           // multiple of 128
+      uint4 *z = reinterpret_cast<uint4 *>(out);
+      for (int64_t k = lane; k < nbytes / 16; k += 32) z[k] = make_uint4(0, 0, 0, 0);
+      __syncwarp();
+      for (int64_t k = beg + lane; k < end; k += 32) {
+        const int64_t p = dense_pos(col[k] - c0);
+        const int32_t v = val[k];
+        if (enc == ENC_D32) reinterpret_cast<int32_t *>(out)[p] = v;
+        else if (enc == ENC_D16) reinterpret_cast<uint16_t *>(out)[p] = (uint16_t)v;
+        else out[p] = (uint8_t)v;
+      }
+    }
+  }
+}
+
+__global__ void k_count_enc(const int4 *__restrict__ desc, int64_t nchunks,
+                            unsigned long long *counts) {
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nchunks;
+       c += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(&counts[desc[c].z], 1ull);
+}
+
+}  // namespace
+
+void build_encoded(tb_store *s) {
+  cudaStream_t st = s->stream;
+  const int64_t nc = s->nchunks;
+  s->enc_bytes = 0;
+  s->n_sparse = s->n_dense = s->n_groups = 0;
+  for (auto &c : s->enc_chunks) c = 0;
+  s->enc_off.alloc(nc + 1);
+  s->enc_desc.alloc(nc + 1);
+  s->work_ids.alloc(nc + 1);
+  if (nc == 0) {
+    s->enc_data.alloc(16);
+    return;
+  }
+  int64_t need = (nc + 7) / 8, cap = (int64_t)s->sm_count * 8;
+  const int grid = (int)(need < cap ? need : cap);
+  int64_t need1 = (nc + 255) / 256, cap1 = (int64_t)s->sm_count * 16;
+  const int grid1 = (int)(need1 < cap1 ? need1 : cap1);
+  {
+    DevBuf<uint64_t> key_in, key_out;
+    DevBuf<int32_t> ids_in;
+    DevBuf<int64_t> bytes, off_sorted;
+    key_in.alloc(nc); key_out.alloc(nc); ids_in.alloc(nc);
+    bytes.alloc(nc + 1); off_sorted.alloc(nc + 1);
+    k_plan<<<grid, 256, 0, st>>>(s->col.p, s->val.p, s->chunk_beg.p, nc, s->nbins, s->enc_desc.p,
+                                 key_in.p, ids_in.p);
+    size_t tmp_bytes = 0, tmp2 = 0;
+    TB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_in.p, key_out.p, ids_in.p,
+                                            s->work_ids.p, nc, 0, 41, st));
+    TB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, bytes.p, off_sorted.p, nc + 1, st));
+    DevBuf<uint8_t> tmp;
+    tmp.alloc((tmp_bytes > tmp2 ? tmp_bytes : tmp2) + 16);
+    TB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key_in.p, key_out.p, ids_in.p,
+                                            s->work_ids.p, nc, 0, 41, st));
+    TB_CUDA(cudaMemsetAsync(bytes.p + nc, 0, sizeof(int64_t), st));
+    k_sorted_bytes<<<grid1, 256, 0, st>>>(s->work_ids.p, s->enc_desc.p, nc, bytes.p);
+    TB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp2, bytes.p, off_sorted.p, nc + 1, st));
+    k_scatter_off<<<grid1, 256, 0, st>>>(s->work_ids.p, off_sorted.p, nc, s->enc_off.p);
+    TB_CUDA(cudaMemcpyAsync(&s->enc_bytes, off_sorted.p + nc, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    // Groups of kRows dense chunks with identical (encoding, panel): runs of equal sort keys,
+    // each padded with empty seats (-1) to a multiple of kRows.  The key list is short
+    // (one entry per chunk), so the run split is done on the host.
+    std::vector<uint64_t> hk(nc);
+    std::vector<int32_t> hid(nc), seats;
+    TB_CUDA(cudaMemcpy(hk.data(), key_out.p, nc * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    TB_CUDA(cudaMemcpy(hid.data(), s->work_ids.p, nc * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    int64_t first_dense = 0;
+    while (first_dense < nc && hk[first_dense] == 0) ++first_dense;
+    seats.reserve((size_t)(nc - first_dense) + 64);
+    for (int64_t i = first_dense; i < nc;) {
+      int64_t j = i;
+      while (j < nc && hk[j] == hk[i]) seats.push_back(hid[j++]);
+      while (seats.size() % kRows) seats.push_back(-1);
+      i = j;
+    }
+    s->n_groups = (int64_t)seats.size() / kRows;
+    s->dense_gids.alloc(seats.size() ? seats.size() : 1);
+    if (!seats.empty())
+      TB_CUDA(cudaMemcpy(s->dense_gids.p, seats.data(), seats.size() * sizeof(int32_t),
+                         cudaMemcpyHostToDevice));
+  }
+  s->enc_data.alloc(s->enc_bytes + 16);
+  k_encode<<<grid, 256, 0, st>>>(s->col.p, s->val.p, s->chunk_beg.p, nc, s->enc_desc.p, s->enc_off.p,
+                                 s->enc_data.p);
+  DevBuf<unsigned long long> counts;
+  counts.alloc(5);
+  TB_CUDA(cudaMemsetAsync(counts.p, 0, counts.bytes(), st));
+  k_count_enc<<<grid1, 256, 0, st>>>(s->enc_desc.p, nc, counts.p);
+  unsigned long long h[5];
+  TB_CUDA(cudaMemcpyAsync(h, counts.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  for (int k = 0; k < 5; ++k) s->enc_chunks[k] = (int64_t)h[k];
+  s->n_sparse = s->enc_chunks[ENC_S32] + s->enc_chunks[ENC_S16];
+  s->n_dense = nc - s->n_sparse;
+}
+
+}  // namespace tb

@@ -8,6 +8,8 @@
 //   K4  k_chunk_reduce<I64*>     row sums / masked column sums   (hic_filtering.py:36-39,141-145,185-200)
 //   K5  k_diag_hist              per-distance sums               (normalize_hic.py:271-283)
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -36,9 +38,7 @@ k_chunk_reduce(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t c = warp; c < nchunks; c += nwarp) {
-    const int64_t beg = chunk_beg[c];
-    int64_t end = rowptr[chunk_row[c] + 1];
-    if (end > beg + kChunk) end = beg + kChunk;
+    const int64_t beg = chunk_beg[c], end = chunk_beg[c + 1];
     double fa = 0.0, fb = 0.0;
     long long ia = 0, ic = 0;
     int64_t k = beg + lane;
@@ -328,9 +328,7 @@ k_diag_hist(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
     const int64_t r = chunk_row[c];
     const int64_t g = rb + r;
     if (bad[g]) continue;
-    const int64_t beg = chunk_beg[c];
-    int64_t end = rowptr[r + 1];
-    if (end > beg + kChunk) end = beg + kChunk;
+    const int64_t beg = chunk_beg[c], end = chunk_beg[c + 1];
     if (col[end - 1] < g) continue;            // chunk entirely below the diagonal
     const int32_t cg = chrom_of[g];
     for (int64_t k = beg + lane; k < end; k += 32) {
@@ -377,6 +375,15 @@ void launch_chunks(tb_store *s, const double *x, const uint8_t *bad, const IceSt
   k_chunk_reduce<MODE><<<chunk_grid(s), 256, 0, s->stream>>>(
       s->col.p, s->val.p, s->chunk_beg.p, s->chunk_row.p, s->rowptr.p, s->nchunks, x, bad,
       s->partial_f.p, s->partial_i.p, state);
+}
+
+bool use_csr_rowsum() {       // TB_ROWSUM=csr: A/B switch back to the uncompressed CSR walk
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("TB_ROWSUM");
+    v = (e && !strcmp(e, "csr")) ? 1 : 0;
+  }
+  return v == 1;
 }
 
 }  // namespace
@@ -438,8 +445,11 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
   TB_CUDA(cudaEventRecord(ev[2 * npass_max], st));
   for (int p = 0; p < npass_max && !stopped; ++p) {
     TB_CUDA(cudaEventRecord(ev[2 * p], st));
+    // pass 0 also counts the cells that survive the mask (which rows are "present"), so it
+    // walks the CSR; every later pass streams the compact encoding
     if (p == 0) launch_chunks<M_F64_COUNT>(s, s->x.p, nullptr, s->state.p);
-    else launch_chunks<M_F64>(s, s->x.p, nullptr, s->state.p);
+    else if (use_csr_rowsum()) launch_chunks<M_F64>(s, s->x.p, nullptr, s->state.p);
+    else launch_rowsum(s, s->x.p, s->state.p);
     TB_CUDA(cudaEventRecord(ev[2 * p + 1], st));
     if (s->nrows) {
       if (p == 0)
@@ -487,7 +497,7 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
   s->rowsum_ms = 0;
   s->rowsum_launches = 0;
   const int real = hs.all_bad ? 0 : hs.passes_done;
-  for (int p = 0; p < real && p < launched; ++p) {
+  for (int p = (real > 1 ? 1 : 0); p < real && p < launched; ++p) {   // pass 0 walks the CSR
     TB_CUDA(cudaEventElapsedTime(&ms, ev[2 * p], ev[2 * p + 1]));
     s->rowsum_ms += ms;
     ++s->rowsum_launches;
@@ -520,7 +530,8 @@ void norm_sum(tb_store *s, const double *h_bias, const uint8_t *h_bad, double *o
   // y = 1/bias on good bins, 0 on bad ones; sum = y . (W y)
   TB_CUDA(cudaMemcpyAsync(s->b.p, h_bias, N * sizeof(double), cudaMemcpyHostToDevice, st));
   k_inverse_bias<<<grid_1d(N, 256, s->sm_count), 256, 0, st>>>(s->b.p, s->bad.p, N, s->x.p);
-  launch_chunks<M_F64>(s, s->x.p, nullptr, nullptr);
+  if (use_csr_rowsum()) launch_chunks<M_F64>(s, s->x.p, nullptr, nullptr);
+  else launch_rowsum(s, s->x.p, nullptr);
   if (s->nrows)
     k_combine_f64<false><<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
         s->partial_f.p, s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, N, s->s_full.p,

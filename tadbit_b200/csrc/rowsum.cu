@@ -1,0 +1,304 @@
+// K1 -- the ICE row sum s_i = sum_j v_ij * x_j over the compact stream (encode.cu).
+// Replaces _update_S + _update_W of the reference (_pytadbit/utils/normalize_hic.py:136-162)
+// in the non-mutating form S = x * (W0 x).
+//
+// Two kernels per pass, no atomics, fixed summation order:
+//
+//   k_rowsum_dense   A warp owns a group of kRows dense chunks that cover the SAME column
+//                    panel of different rows.  The payloads are pulled into shared memory by
+//                    the bulk-copy engine (cp.async.bulk -> mbarrier complete_tx, SASS UBLKCP):
+//                    every warp keeps a private ring of kStages stages, each kRows x kSub
+//                    bytes, and runs its producer cursor kStages sub-blocks ahead of its
+//                    consumer cursor, across group boundaries.  HBM latency is therefore
+//                    covered by bytes in flight in the copy engine (up to 128 KB per SM),
+//                    not by resident warps or registers.  Per 128 columns a lane reads one
+//                    word per row from shared memory (conflict-free) and two 16-byte x loads
+//                    shared by the kRows rows, then 4 x kRows DFMA.
+//   k_rowsum_sparse  one sparse chunk per warp, x gathered through L1/L2.
+//
+// Integer -> double by exponent splice (one DADD) instead of I2F.F64.
+#include "common.cuh"
+
+namespace tb {
+
+namespace {
+
+constexpr int kStages = 4;          // sub-blocks in flight per warp
+constexpr int kSub = 512;           // bytes per row per stage
+constexpr int kDenseWarps = 16;     // warps per CTA, one CTA per SM
+constexpr int kWarpRing = kStages * kRows * kSub;                 // 8 KB per warp
+constexpr int kDenseSmem = kDenseWarps * kWarpRing + kDenseWarps * kStages * 8;
+
+__device__ __forceinline__ double u2d(uint32_t v) {      // exact for v < 2^32
+  return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
+}
+__device__ __forceinline__ double i2d(int32_t v) {       // exact for any int32
+  return __hiloint2double(0x43300000, (int)((uint32_t)v ^ 0x80000000u)) - 4503601774854144.0;
+}
+
+__device__ __forceinline__ uint32_t ldg_stream_u32(const void *p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint2 ldg_stream_u64(const void *p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double2 ldg_x2(const double *p) {      // cached: x is reused
+  return __ldg(reinterpret_cast<const double2 *>(p));
+}
+__device__ __forceinline__ double warp_sum(double a) {
+  for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  return a;
+}
+
+// ---- mbarrier / bulk copy (PTX) -----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+// One group of kRows same-shaped dense chunks, as a cursor over its kSub-byte sub-blocks.
+struct Group {
+  int32_t id[kRows];
+  int64_t off[kRows];
+  int c0, enc, row_bytes, nsub;
+};
+
+__device__ __forceinline__ void load_group(Group &g, int64_t gi, const int32_t *__restrict__ gids,
+                                           const int4 *__restrict__ desc,
+                                           const int64_t *__restrict__ off) {
+  const int4 seats = __ldg(reinterpret_cast<const int4 *>(gids) + gi);
+  g.id[0] = seats.x; g.id[1] = seats.y; g.id[2] = seats.z; g.id[3] = seats.w;
+  const int4 d = __ldg(desc + g.id[0]);          // seat 0 is always occupied
+  g.c0 = d.x;
+  g.enc = d.z;
+  g.row_bytes = d.y * (d.z == ENC_D32 ? 4 : (d.z == ENC_D16 ? 2 : 1));
+  g.nsub = (g.row_bytes + kSub - 1) / kSub;
+#pragma unroll
+  for (int r = 0; r < kRows; ++r) g.off[r] = g.id[r] >= 0 ? __ldg(off + g.id[r]) : 0;
+}
+
+// One full stage: kRows rows x kSub bytes = 512/256/128 columns for D8/D16/D32.  Everything is
+// compile-time shaped (dense chunks are padded to 512 columns), so the body is straight-line:
+// per column and row one byte-extract (PRMT), one DADD (exponent splice) and one DFMA.
+template <int ENC>
+__device__ __forceinline__ void consume(const uint8_t *stage, const double *xb, int lane,
+                                        double lo[kRows], double hi[kRows]) {
+  constexpr int W = ENC == ENC_D32 ? 4 : (ENC == ENC_D16 ? 2 : 1);
+  constexpr int G = kSub / (128 * W);            // 128-column groups per stage
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const double2 xa = ldg_x2(xb + g * 128), xc = ldg_x2(xb + g * 128 + 64);
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const uint8_t *p = stage + r * kSub + g * 128 * W;
+      double v0, v1, v2, v3;
+      if (ENC == ENC_D8) {
+        const uint32_t w = reinterpret_cast<const uint32_t *>(p)[lane];
+        v0 = u2d(__byte_perm(w, 0, 0x4440)); v1 = u2d(__byte_perm(w, 0, 0x4441));
+        v2 = u2d(__byte_perm(w, 0, 0x4442)); v3 = u2d(__byte_perm(w, 0, 0x4443));
+      } else if (ENC == ENC_D16) {
+        const uint2 w = reinterpret_cast<const uint2 *>(p)[lane];
+        v0 = u2d(w.x & 0xffff); v1 = u2d(w.x >> 16); v2 = u2d(w.y & 0xffff); v3 = u2d(w.y >> 16);
+      } else {
+        const uint4 w = reinterpret_cast<const uint4 *>(p)[lane];
+        v0 = i2d((int32_t)w.x); v1 = i2d((int32_t)w.y); v2 = i2d((int32_t)w.z); v3 = i2d((int32_t)w.w);
+      }
+      lo[r] = fma(v0, xa.x, lo[r]);
+      hi[r] = fma(v1, xa.y, hi[r]);
+      lo[r] = fma(v2, xc.x, lo[r]);
+      hi[r] = fma(v3, xc.y, hi[r]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kDenseWarps * 32, 1)
+k_rowsum_dense(const uint8_t *__restrict__ data, const int64_t *__restrict__ off,
+               const int4 *__restrict__ desc, const int32_t *__restrict__ gids, int64_t ngroups,
+               const double *__restrict__ x, double *__restrict__ partial,
+               const IceState *__restrict__ state) {
+  if (state && state->stopped) return;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  uint8_t *ring = smem + wic * kWarpRing;
+  const uint32_t ring_u32 = smem_u32(ring);
+  const uint32_t bars = smem_u32(smem + kDenseWarps * kWarpRing) + wic * kStages * 8;
+  if (lane == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(bars + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  const int64_t warp = (int64_t)blockIdx.x * kDenseWarps + wic;
+  const int64_t nwarp = (int64_t)gridDim.x * kDenseWarps;
+
+  // producer cursor (runs ahead) and consumer cursor over the same (group, sub-block) sequence
+  Group pg, cg;
+  int64_t pgi = warp, cgi = warp;
+  int psub = 0, csub = 0;
+  if (pgi < ngroups) {
+    load_group(pg, pgi, gids, desc, off);
+    cg = pg;
+  }
+  auto issue = [&](int stage) {             // all lanes advance the cursor, lane 0 issues
+    if (pgi >= ngroups) return;
+    constexpr int bytes = kSub;              // chunks are padded to whole sub-blocks
+    if (lane == 0) {
+      int nvalid = 0;
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) nvalid += pg.id[r] >= 0;
+      const uint32_t bar = bars + 8 * stage;
+      mbar_expect_tx(bar, (uint32_t)(nvalid * bytes));
+#pragma unroll
+      for (int r = 0; r < kRows; ++r)
+        if (pg.id[r] >= 0)
+          bulk_g2s(ring_u32 + (stage * kRows + r) * kSub, data + pg.off[r] + (int64_t)psub * kSub,
+                   (uint32_t)bytes, bar);
+    }
+    if (++psub == pg.nsub) {
+      psub = 0;
+      pgi += nwarp;
+      if (pgi < ngroups) load_group(pg, pgi, gids, desc, off);
+    }
+  };
+  for (int s = 0; s < kStages; ++s) issue(s);
+
+  double lo[kRows], hi[kRows];
+#pragma unroll
+  for (int r = 0; r < kRows; ++r) lo[r] = hi[r] = 0.0;
+  uint32_t phase = 0;                      // bit s = parity to wait for on stage s
+  int stage = 0;
+  while (cgi < ngroups) {
+    mbar_wait(bars + 8 * stage, (phase >> stage) & 1u);
+    phase ^= 1u << stage;
+    const uint8_t *sp = ring + stage * kRows * kSub;
+    const int W = cg.enc == ENC_D32 ? 4 : (cg.enc == ENC_D16 ? 2 : 1);
+    const double *xb = x + cg.c0 + (int64_t)csub * (kSub / W) + 2 * lane;
+    if (cg.enc == ENC_D8) consume<ENC_D8>(sp, xb, lane, lo, hi);
+    else if (cg.enc == ENC_D16) consume<ENC_D16>(sp, xb, lane, lo, hi);
+    else consume<ENC_D32>(sp, xb, lane, lo, hi);
+    __syncwarp();                          // every lane is done with this stage's bytes
+    issue(stage);
+    stage = (stage + 1 == kStages) ? 0 : stage + 1;
+    if (++csub == cg.nsub) {               // group finished: reduce and publish
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        const double a = warp_sum(lo[r] + hi[r]);
+        if (lane == 0 && cg.id[r] >= 0) partial[cg.id[r]] = a;
+        lo[r] = hi[r] = 0.0;
+      }
+      csub = 0;
+      cgi += nwarp;
+      if (cgi < ngroups) load_group(cg, cgi, gids, desc, off);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_rowsum_sparse(const uint8_t *__restrict__ data, const int64_t *__restrict__ off,
+                const int4 *__restrict__ desc, const int32_t *__restrict__ ids, int64_t ns,
+                const double *__restrict__ x, double *__restrict__ partial,
+                const IceState *__restrict__ state) {
+  if (state && state->stopped) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < ns; i += nwarp) {
+    const int32_t c = ids[i];
+    const int4 d = desc[c];
+    const uint8_t *p = data + off[c];
+    const int n = d.y;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (d.z == ENC_S16) {
+      const double *xb = x + d.x;
+      const uint32_t *w = reinterpret_cast<const uint32_t *>(p);
+      int k = lane;
+      for (; k + 96 < n; k += 128) {
+        const uint32_t e0 = ldg_stream_u32(w + k), e1 = ldg_stream_u32(w + k + 32);
+        const uint32_t e2 = ldg_stream_u32(w + k + 64), e3 = ldg_stream_u32(w + k + 96);
+        const double x0 = __ldg(xb + (e0 & 0xffff)), x1 = __ldg(xb + (e1 & 0xffff));
+        const double x2 = __ldg(xb + (e2 & 0xffff)), x3 = __ldg(xb + (e3 & 0xffff));
+        a0 = fma(u2d(e0 >> 16), x0, a0);
+        a1 = fma(u2d(e1 >> 16), x1, a1);
+        a2 = fma(u2d(e2 >> 16), x2, a2);
+        a3 = fma(u2d(e3 >> 16), x3, a3);
+      }
+      for (; k < n; k += 32) {
+        const uint32_t e0 = ldg_stream_u32(w + k);
+        a0 = fma(u2d(e0 >> 16), __ldg(xb + (e0 & 0xffff)), a0);
+      }
+    } else {                                     // ENC_S32
+      const uint2 *w = reinterpret_cast<const uint2 *>(p);
+      int k = lane;
+      for (; k + 96 < n; k += 128) {
+        const uint2 e0 = ldg_stream_u64(w + k), e1 = ldg_stream_u64(w + k + 32);
+        const uint2 e2 = ldg_stream_u64(w + k + 64), e3 = ldg_stream_u64(w + k + 96);
+        const double x0 = __ldg(x + e0.x), x1 = __ldg(x + e1.x);
+        const double x2 = __ldg(x + e2.x), x3 = __ldg(x + e3.x);
+        a0 = fma(i2d((int32_t)e0.y), x0, a0);
+        a1 = fma(i2d((int32_t)e1.y), x1, a1);
+        a2 = fma(i2d((int32_t)e2.y), x2, a2);
+        a3 = fma(i2d((int32_t)e3.y), x3, a3);
+      }
+      for (; k < n; k += 32) {
+        const uint2 e0 = ldg_stream_u64(w + k);
+        a0 = fma(i2d((int32_t)e0.y), __ldg(x + e0.x), a0);
+      }
+    }
+    const double a = warp_sum((a0 + a1) + (a2 + a3));
+    if (lane == 0) partial[c] = a;
+  }
+}
+
+}  // namespace
+
+void launch_rowsum(tb_store *s, const double *x, const IceState *state) {
+  if (s->n_groups) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      TB_CUDA(cudaFuncSetAttribute(k_rowsum_dense, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kDenseSmem));
+      attr_set = true;
+    }
+    int64_t need = (s->n_groups + kDenseWarps - 1) / kDenseWarps;
+    const int grid = (int)(need < s->sm_count ? need : s->sm_count);
+    k_rowsum_dense<<<grid, kDenseWarps * 32, kDenseSmem, s->stream>>>(
+        s->enc_data.p, s->enc_off.p, s->enc_desc.p, s->dense_gids.p, s->n_groups, x, s->partial_f.p,
+        state);
+  }
+  if (s->n_sparse) {
+    int64_t need = (s->n_sparse + 7) / 8, cap = (int64_t)s->sm_count * 8;
+    const int grid = (int)(need < cap ? need : cap);
+    k_rowsum_sparse<<<grid, 256, 0, s->stream>>>(s->enc_data.p, s->enc_off.p, s->enc_desc.p,
+                                                 s->work_ids.p, s->n_sparse, x, s->partial_f.p, state);
+  }
+}
+
+}  // namespace tb

@@ -95,6 +95,13 @@ class ContactStore(object):
         keys = ("nbins", "row_begin", "row_end", "nnz_upper", "nnz_full", "device_bytes")
         return dict(zip(keys, [x.value for x in v]))
 
+    def layout(self):
+        """Compact row-sum stream: payload bytes and chunks per encoding."""
+        out = np.zeros(8, dtype=np.int64)
+        check(lib().tb_store_layout(self._h, ptr(out, C.c_int64)))
+        return dict(stream_bytes=int(out[0]), chunks=int(out[6]), csr_bytes=int(out[7]),
+                    encodings=dict(zip(("S32", "S16", "D32", "D16", "D8"), out[1:6].tolist())))
+
     def export_upper(self):
         """Owned upper-triangle cells, row-major sorted: (rows, cols, vals) int32."""
         n = C.c_int64()
