@@ -196,11 +196,11 @@ def main():
         store.comm_init(rank, world, uid[0])
     info = store.info()
     t_build = time.perf_counter() - t_build
-    nnz_upper = info["nnz_upper"]
+    nnz_upper, nnz_full = info["nnz_upper"], info["nnz_full"]
     if world > 1:
-        t = torch.tensor([nnz_upper], dtype=torch.int64)
+        t = torch.tensor([nnz_upper, nnz_full], dtype=torch.int64)
         dist.all_reduce(t)
-        nnz_upper = int(t.item())
+        nnz_upper, nnz_full = int(t[0].item()), int(t[1].item())
 
     def barrier():
         if world > 1:
@@ -238,7 +238,9 @@ def main():
     # roofline of the dominant kernel (K1 row sum), this rank's launches
     peak, peak_src = measured_peaks()
     n = wl["size"]
-    alg_bytes = 12.0 * info["nnz_upper"] + 24.0 * (block[1] - block[0])
+    # algorithmic bytes of THIS rank's launch (12 B per contact + 24 B per bin): the
+    # rank walks info["nnz_full"] of the nnz_full directed cells, i.e. that share of the contacts
+    alg_bytes = 12.0 * nnz_upper * info["nnz_full"] / max(nnz_full, 1) + 24.0 * (block[1] - block[0])
     k1_ms = rowsum_ms / max(rowsum_n, 1)
     achieved = alg_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0
     lay = store.layout()
@@ -246,7 +248,8 @@ def main():
     layout_bytes = 8.0 * info["nnz_full"] if csr_walk else float(lay["stream_bytes"])
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "kernel": "k_chunk_reduce<F64> (CSR walk)" if csr_walk else "k_rowsum (K1, compact stream)",
+                "kernel": "k_chunk_reduce<F64> (CSR walk)" if csr_walk else
+                          "k_rowsum_dense + k_rowsum_sparse (K1 over the compact stream)",
                 "kernel_ms": k1_ms, "stream_encodings": lay["encodings"],
                 "kernel_share_of_step": rowsum_ms / dev_ms if dev_ms else None,
                 "algorithmic_bytes_per_launch": alg_bytes,

@@ -86,7 +86,7 @@ constexpr int kWarp = 32;
 constexpr int kChunk = 4096;      // max stored cells one warp reduces before writing a partial
 constexpr int kPanel = 4096;      // column panel of the chunk planner / dense encodings
 constexpr int kRows = 4;          // dense chunks (rows) one warp walks together
-constexpr int kXPad = 1024;       // zero tail of the gathered vector (dense chunks read past N)
+constexpr int kXPad = 2048;       // zero tail of the gathered vector (dense chunks read past N)
 
 // chunk encodings of the compact row-sum stream
 enum { ENC_S32 = 0, ENC_S16 = 1, ENC_D32 = 2, ENC_D16 = 3, ENC_D8 = 4 };

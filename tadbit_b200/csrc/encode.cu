@@ -73,7 +73,7 @@ k_plan(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
         const int32_t p0 = (cfirst / kPanel) * kPanel;
         int64_t width = nbins - p0;
         if (width > kPanel) width = kPanel;
-        const int64_t nslots = (width + 511) & ~(int64_t)511;   // whole 512-byte sub-blocks (rowsum.cu)
+        const int64_t nslots = (width + 1023) & ~(int64_t)1023;   // whole 512-byte sub-blocks (rowsum.cu)
         int denc = -1;
         int64_t dbest = best + 1;
         if (4 * nslots <= best) { denc = ENC_D32; dbest = 4 * nslots; }

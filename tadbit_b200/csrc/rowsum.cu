@@ -23,9 +23,9 @@ namespace tb {
 
 namespace {
 
-constexpr int kStages = 4;          // sub-blocks in flight per warp
-constexpr int kSub = 512;           // bytes per row per stage
-constexpr int kDenseWarps = 16;     // warps per CTA, one CTA per SM
+constexpr int kStages = 2;          // sub-blocks in flight per warp
+constexpr int kSub = 1024;          // bytes per row per stage
+constexpr int kDenseWarps = 24;     // warps per CTA, one CTA per SM
 constexpr int kWarpRing = kStages * kRows * kSub;                 // 8 KB per warp
 constexpr int kDenseSmem = kDenseWarps * kWarpRing + kDenseWarps * kStages * 8;
 
@@ -112,7 +112,7 @@ template <int ENC>
 __device__ __forceinline__ void consume(const uint8_t *stage, const double *xb, int lane,
                                         double lo[kRows], double hi[kRows]) {
   constexpr int W = ENC == ENC_D32 ? 4 : (ENC == ENC_D16 ? 2 : 1);
-  constexpr int G = kSub / (128 * W);            // 128-column groups per stage
+  constexpr int G = 512 / (128 * W);             // 128-column groups per 512-byte piece
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     const double2 xa = ldg_x2(xb + g * 128), xc = ldg_x2(xb + g * 128 + 64);
@@ -201,9 +201,12 @@ k_rowsum_dense(const uint8_t *__restrict__ data, const int64_t *__restrict__ off
     const uint8_t *sp = ring + stage * kRows * kSub;
     const int W = cg.enc == ENC_D32 ? 4 : (cg.enc == ENC_D16 ? 2 : 1);
     const double *xb = x + cg.c0 + (int64_t)csub * (kSub / W) + 2 * lane;
-    if (cg.enc == ENC_D8) consume<ENC_D8>(sp, xb, lane, lo, hi);
-    else if (cg.enc == ENC_D16) consume<ENC_D16>(sp, xb, lane, lo, hi);
-    else consume<ENC_D32>(sp, xb, lane, lo, hi);
+#pragma unroll 1
+    for (int h = 0; h < kSub / 512; ++h) {
+      if (cg.enc == ENC_D8) consume<ENC_D8>(sp + h * 512, xb + h * 512, lane, lo, hi);
+      else if (cg.enc == ENC_D16) consume<ENC_D16>(sp + h * 512, xb + h * 256, lane, lo, hi);
+      else consume<ENC_D32>(sp + h * 512, xb + h * 128, lane, lo, hi);
+    }
     __syncwarp();                          // every lane is done with this stage's bytes
     issue(stage);
     stage = (stage + 1 == kStages) ? 0 : stage + 1;
