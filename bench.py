@@ -124,17 +124,11 @@ def cpu_baseline(wl, nbins, device, threads=None):
     r, c, v = store.export_upper()
     store.close()
     m = orc.OracleMatrix(nbins, r, c, v)
-    fast = getattr(orc, "iterative_fast", None)
-    t0 = time.perf_counter()
-    if fast is not None:
-        bias, trace, cores, kind = fast(m, {}, ITERATIONS, MAX_DEV, threads)
-    else:
-        bias, trace = orc.iterative(m, bads={}, iterations=ITERATIONS, max_dev=MAX_DEV)
-        cores, kind = 1, "port"
-    dt = time.perf_counter() - t0
-    return {"value": r.size * len(trace) / dt, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": "leading %d x %d block of the %s model (%d contacts, %d passes, %.1f s)"
-                      % (nbins, nbins, wl["name"], r.size, len(trace), dt)}
+    # pass loop in C + OpenMP (oracle/ice_port.c); only the loop is timed, the CSR build is not
+    bias, trace, cores, dt = orc.iterative_fast(m, {}, ITERATIONS, MAX_DEV, threads)
+    return {"value": r.size * len(trace) / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "leading %d x %d block of the %s model (%d contacts, %d passes, %.2f s "
+                      "in the pass loop)" % (nbins, nbins, wl["name"], r.size, len(trace), dt)}
 
 
 def run_reference(args, rank, world):

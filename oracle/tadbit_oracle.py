@@ -294,6 +294,71 @@ def iterative(m, bads=None, iterations=0, max_dev=0.00001):
     return bias, trace
 
 
+_PORT = None
+
+
+def _load_port():
+    """ctypes handle of oracle/_build/libice_port.so (built by oracle/Makefile), or None."""
+    global _PORT
+    if _PORT is None:
+        import ctypes
+        import os
+        import subprocess
+        here = os.path.dirname(os.path.abspath(__file__))
+        path = os.path.join(here, "_build", "libice_port.so")
+        if not os.path.exists(path):
+            try:
+                subprocess.check_call(["make", "-s", "-C", here])
+            except Exception:
+                _PORT = False
+                return None
+        try:
+            lib = ctypes.CDLL(path)
+        except OSError:
+            _PORT = False
+            return None
+        lib.ice_port.restype = ctypes.c_int
+        lib.ice_port.argtypes = [ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                 ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
+                                 ctypes.c_int]
+        lib.ice_port_threads.restype = ctypes.c_int
+        _PORT = lib
+    return _PORT or None
+
+
+def iterative_fast(m, bads=None, iterations=0, max_dev=0.00001, threads=None):
+    """Same as :func:`iterative` with the pass loop in C + OpenMP (oracle/ice_port.c).
+
+    Returns (bias, trace, cores, seconds spent in the loop).  Falls back to the numpy loop
+    (cores = 1) when the C library cannot be built."""
+    import time
+    lib = _load_port()
+    if lib is None:
+        t0 = time.perf_counter()
+        bias, trace = iterative(m, bads, iterations, max_dev)
+        return bias, trace, 1, time.perf_counter() - t0
+    size = m.size
+    bad = _bad_mask(size, bads)
+    keep = ~(bad[m.rows] | bad[m.cols])
+    w0 = m.full_csr(keep)
+    w0.sort_indices()
+    indptr = np.ascontiguousarray(w0.indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(w0.indices, dtype=np.int32)
+    data = np.ascontiguousarray(w0.data, dtype=np.float64)
+    bias = np.empty(size)
+    trace = np.zeros((iterations + 1, 4))
+    cores = int(threads) if threads else lib.ice_port_threads()
+    t0 = time.perf_counter()
+    passes = lib.ice_port(size, indptr.ctypes.data, indices.ctypes.data, data.ctypes.data,
+                          int(iterations), float(max_dev), bias.ctypes.data, trace.ctypes.data,
+                          cores)
+    dt = time.perf_counter() - t0
+    if passes < 0:
+        raise ZeroDivisionError('ERROR: normalization failed, all bad columns')
+    ntrace = passes if iterations > 0 else 0
+    return bias, [(t[0], t[1], t[2], it, t[3]) for it, t in enumerate(trace[:ntrace])], cores, dt
+
+
 def matrix_sum(m, bias=None, bads=None):
     """hic_data.py:350-375 -- both triangles, diagonal once."""
     bad = _bad_mask(m.size, bads)
