@@ -85,11 +85,23 @@ struct IceState {
 constexpr int kWarp = 32;
 constexpr int kChunk = 4096;      // max stored cells one warp reduces before writing a partial
 constexpr int kPanel = 4096;      // column panel of the chunk planner / dense encodings
+constexpr int kSub = 1024;        // bytes per row per pipeline stage of k_rowsum_dense
 constexpr int kRows = 4;          // dense chunks (rows) one warp walks together
 constexpr int kXPad = 2048;       // zero tail of the gathered vector (dense chunks read past N)
 
 // chunk encodings of the compact row-sum stream
 enum { ENC_S32 = 0, ENC_S16 = 1, ENC_D32 = 2, ENC_D16 = 3, ENC_D8 = 4 };
+
+// A group of kRows dense chunks that share (encoding, column panel): the unit of work of a
+// warp of k_rowsum_dense.  Built on the host in encode.cu.
+struct GroupRec {
+  uint32_t off16[kRows];   // payload offset / 16 of each seat
+  int32_t id[kRows];       // chunk id (index of its partial), -1 = empty seat
+  int32_t c0;              // first column of the panel
+  int32_t nsub;            // kSub-byte sub-blocks per row
+  int32_t enc;             // ENC_D32 / ENC_D16 / ENC_D8
+  int32_t ovf;             // some seat carries overflow cells
+};
 
 }  // namespace tb
 
@@ -119,8 +131,9 @@ struct tb_store {
   tb::DevBuf<int4> enc_desc;              // [nchunks] (first column, slots or cells, encoding, 0)
   tb::DevBuf<int32_t> work_ids;           // [nchunks] chunk ids in work order: sparse, then dense
   int64_t n_sparse = 0, n_dense = 0;
-  tb::DevBuf<int32_t> dense_gids;         // [n_groups * kRows] dense chunk ids, same panel and
-  int64_t n_groups = 0;                   //   encoding within a group, -1 = empty seat
+  tb::DevBuf<tb::GroupRec> groups;        // [n_groups] kRows dense chunks of one panel each
+  int64_t n_groups = 0;
+  int64_t n_overflow = 0;                 // cells kept outside their dense chunk's value width
   int64_t enc_bytes = 0;
   int64_t enc_chunks[5] = {0, 0, 0, 0, 0};  // chunks per encoding
   // scratch

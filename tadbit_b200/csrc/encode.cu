@@ -1,20 +1,22 @@
 // Compact row-sum stream.
 //
-// The ICE pass is bound by the bytes of the stored cells, so every chunk (build.cu:
-// k_plan_chunks) is re-encoded into the smallest of five layouts:
+// The ICE pass re-reads the matrix every iteration, so every chunk (build.cu:
+// k_plan_chunks) is re-encoded into the smallest of these layouts:
 //
 //   S32  (col:int32, val:int32) per cell                      8 B / cell
 //   S16  (col - c0 : u16, val : u16) per cell                 4 B / cell   span, values < 65536
 //   D32  one int32 per COLUMN of the chunk's panel             4 B / slot   zeros explicit
-//   D16  one u16 per column                                    2 B / slot   values < 65536
-//   D8   one u8 per column                                     1 B / slot   values < 256
+//   D16  one u16 per column  + overflow cells                  2 B / slot   (+ 8 B per cell >= 65536)
+//   D8   one u8 per column   + overflow cells                  1 B / slot   (+ 8 B per cell >= 256)
 //
-// Dense chunks cover their whole kPanel-aligned column panel (a multiple of 128 slots), so
-// (padded to 512 slots) the same panel of different rows has the same shape: the row-sum kernel walks kRows such
-// chunks at once and reads x a single time for all of them.  Inside a 128-slot group the
-// slots are permuted so that lane l owns {2l, 2l+1, 64+2l, 64+2l+1}: its four values are
-// one 4/8/16-byte word and the matching x entries are two aligned 16-byte loads, contiguous
-// across the warp.
+// Dense chunks cover their whole kPanel-aligned column panel (padded to 1024 slots), so the
+// same panel of different rows has the same shape: the row-sum kernel walks kRows such chunks
+// at once and reads x a single time for all of them.  A cell too large for the chunk's width
+// is written as 0 in the dense part and appended to the chunk's overflow list (col, val); a
+// handful of huge cells next to the diagonal then no longer force a whole panel to 32 bits.
+// Inside a 128-slot group the slots are permuted so that lane l owns {2l, 2l+1, 64+2l,
+// 64+2l+1}: its four values are one 4/8/16-byte word and the matching x entries are two
+// aligned 16-byte loads, contiguous across the warp.
 //
 // Work order = payload order: sparse chunks first (row order), then dense chunks sorted by
 // (encoding, panel) with rows ascending inside -- each kernel streams its payload front to
@@ -39,6 +41,7 @@ __device__ __forceinline__ int64_t dense_pos(int64_t s) {
 }
 
 // one warp per chunk: choose the encoding, report payload size and the work-order key
+// desc = (first column, slots or cells, encoding | overflow cells << 8, payload bytes)
 __global__ void __launch_bounds__(256)
 k_plan(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
        const int64_t *__restrict__ chunk_beg, int64_t nchunks, int64_t nbins,
@@ -49,22 +52,26 @@ k_plan(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
   for (int64_t c = warp; c < nchunks; c += nwarp) {
     const int64_t beg = chunk_beg[c], end = chunk_beg[c + 1];
     int32_t vmin = 2147483647, vmax = -2147483647 - 1;
+    int n8 = 0, n16 = 0;                       // cells that do not fit u8 / u16
     for (int64_t k = beg + lane; k < end; k += 32) {
       const int32_t v = val[k];
       vmin = min(vmin, v);
       vmax = max(vmax, v);
+      n8 += (v < 0 || v > 255);
+      n16 += (v < 0 || v > 65535);
     }
     for (int o = 16; o; o >>= 1) {
       vmin = min(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
       vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+      n8 += __shfl_xor_sync(0xffffffffu, n8, o);
+      n16 += __shfl_xor_sync(0xffffffffu, n16, o);
     }
     if (lane == 0) {
       const int64_t count = end - beg;
       const int32_t cfirst = col[beg], clast = col[end - 1];
-      const bool nonneg = vmin >= 0;
-      int enc = ENC_S32;
+      int enc = ENC_S32, novf = 0;
       int64_t best = 8 * count;
-      if (nonneg && vmax < 65536 && (int64_t)clast - cfirst < 65536 && 4 * count < best) {
+      if (n16 == 0 && (int64_t)clast - cfirst < 65536 && 4 * count < best) {
         enc = ENC_S16; best = 4 * count;
       }
       int32_t c0 = cfirst;
@@ -73,15 +80,19 @@ k_plan(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
         const int32_t p0 = (cfirst / kPanel) * kPanel;
         int64_t width = nbins - p0;
         if (width > kPanel) width = kPanel;
-        const int64_t nslots = (width + 1023) & ~(int64_t)1023;   // whole 512-byte sub-blocks (rowsum.cu)
-        int denc = -1;
+        const int64_t nslots = (width + kSub - 1) / kSub * kSub;     // whole sub-blocks (rowsum.cu)
+        int denc = -1, dovf = 0;
         int64_t dbest = best + 1;
-        if (4 * nslots <= best) { denc = ENC_D32; dbest = 4 * nslots; }
-        if (nonneg && vmax < 65536 && 2 * nslots <= best) { denc = ENC_D16; dbest = 2 * nslots; }
-        if (nonneg && vmax < 256 && nslots <= best) { denc = ENC_D8; dbest = nslots; }
-        if (denc >= 0) { enc = denc; best = dbest; c0 = p0; n = nslots; }
+        if (4 * nslots <= best) { denc = ENC_D32; dbest = 4 * nslots; dovf = 0; }
+        if (2 * nslots + 8 * (int64_t)n16 <= (denc >= 0 ? dbest : best)) {
+          denc = ENC_D16; dbest = 2 * nslots + 8 * (int64_t)n16; dovf = n16;
+        }
+        if (nslots + 8 * (int64_t)n8 <= (denc >= 0 ? dbest : best)) {
+          denc = ENC_D8; dbest = nslots + 8 * (int64_t)n8; dovf = n8;
+        }
+        if (denc >= 0) { enc = denc; best = dbest; c0 = p0; n = nslots; novf = dovf; }
       }
-      desc[c] = make_int4(c0, (int)n, enc, (int)align16(best));
+      desc[c] = make_int4(c0, (int)n, enc | (novf << 8), (int)align16(best));
       // sparse chunks keep row order (key 0); dense chunks sort by (encoding, panel)
       key[c] = enc >= ENC_D32 ? (((uint64_t)1 << 40) | ((uint64_t)enc << 32) | (uint32_t)c0) : 0;
       ids[c] = (int32_t)c;
@@ -114,7 +125,7 @@ k_encode(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
     const int64_t beg = chunk_beg[c], end = chunk_beg[c + 1];
     const int4 d = desc[c];
     uint8_t *out = data + off[c];
-    const int c0 = d.x, enc = d.z;
+    const int c0 = d.x, enc = d.z & 0xff;
     if (enc == ENC_S32) {
       int2 *o = reinterpret_cast<int2 *>(out);
       for (int64_t k = beg + lane; k < end; k += 32) o[k - beg] = make_int2(col[k], val[k]);
@@ -124,16 +135,31 @@ k_encode(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
         o[k - beg] = (uint32_t)(col[k] - c0) | ((uint32_t)val[k] << 16);
     } else {
       const int width = enc == ENC_D32 ? 4 : (enc == ENC_D16 ? 2 : 1);
-      const int64_t nbytes = (int64_t)d.y * width;           // multiple of 128
+      const int32_t vcap = enc == ENC_D32 ? 2147483647 : (enc == ENC_D16 ? 65535 : 255);
+      const int64_t nbytes = (int64_t)d.y * width;           // multiple of kSub
       uint4 *z = reinterpret_cast<uint4 *>(out);
       for (int64_t k = lane; k < nbytes / 16; k += 32) z[k] = make_uint4(0, 0, 0, 0);
       __syncwarp();
-      for (int64_t k = beg + lane; k < end; k += 32) {
-        const int64_t p = dense_pos(col[k] - c0);
-        const int32_t v = val[k];
-        if (enc == ENC_D32) reinterpret_cast<int32_t *>(out)[p] = v;
-        else if (enc == ENC_D16) reinterpret_cast<uint16_t *>(out)[p] = (uint16_t)v;
-        else out[p] = (uint8_t)v;
+      int2 *ovf = reinterpret_cast<int2 *>(out + nbytes);
+      int novf = 0;
+      for (int64_t k0 = beg; k0 < end; k0 += 32) {
+        const int64_t k = k0 + lane;
+        int32_t v = 0, cc = 0;
+        bool fits = true;
+        if (k < end) {
+          v = val[k];
+          cc = col[k];
+          fits = enc == ENC_D32 || (v >= 0 && v <= vcap);
+          if (fits) {
+            const int64_t p = dense_pos(cc - c0);
+            if (enc == ENC_D32) reinterpret_cast<int32_t *>(out)[p] = v;
+            else if (enc == ENC_D16) reinterpret_cast<uint16_t *>(out)[p] = (uint16_t)v;
+            else out[p] = (uint8_t)v;
+          }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, !fits);
+        if (!fits) ovf[novf + __popc(m & ((1u << lane) - 1u))] = make_int2(cc, v);
+        novf += __popc(m);
       }
     }
   }
@@ -142,8 +168,10 @@ k_encode(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
 __global__ void k_count_enc(const int4 *__restrict__ desc, int64_t nchunks,
                             unsigned long long *counts) {
   for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nchunks;
-       c += (int64_t)gridDim.x * blockDim.x)
-    atomicAdd(&counts[desc[c].z], 1ull);
+       c += (int64_t)gridDim.x * blockDim.x) {
+    atomicAdd(&counts[desc[c].z & 0xff], 1ull);
+    if (desc[c].z >> 8) atomicAdd(&counts[5], (unsigned long long)(desc[c].z >> 8));
+  }
 }
 
 }  // namespace
@@ -153,12 +181,14 @@ void build_encoded(tb_store *s) {
   const int64_t nc = s->nchunks;
   s->enc_bytes = 0;
   s->n_sparse = s->n_dense = s->n_groups = 0;
+  s->n_overflow = 0;
   for (auto &c : s->enc_chunks) c = 0;
   s->enc_off.alloc(nc + 1);
   s->enc_desc.alloc(nc + 1);
   s->work_ids.alloc(nc + 1);
   if (nc == 0) {
     s->enc_data.alloc(16);
+    s->groups.alloc(1);
     return;
   }
   int64_t need = (nc + 7) / 8, cap = (int64_t)s->sm_count * 8;
@@ -187,39 +217,67 @@ void build_encoded(tb_store *s) {
     k_scatter_off<<<grid1, 256, 0, st>>>(s->work_ids.p, off_sorted.p, nc, s->enc_off.p);
     TB_CUDA(cudaMemcpyAsync(&s->enc_bytes, off_sorted.p + nc, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     TB_CUDA(cudaStreamSynchronize(st));
-    // Groups of kRows dense chunks with identical (encoding, panel): runs of equal sort keys,
-    // each padded with empty seats (-1) to a multiple of kRows.  The key list is short
-    // (one entry per chunk), so the run split is done on the host.
+    // Group records: runs of equal sort keys = dense chunks of one (encoding, panel), rows
+    // ascending; each run is cut into groups of kRows seats, the last one padded with empty
+    // seats.  One entry per chunk, so this runs on the host.
     std::vector<uint64_t> hk(nc);
-    std::vector<int32_t> hid(nc), seats;
+    std::vector<int32_t> hid(nc);
+    std::vector<int4> hdesc(nc);
+    std::vector<int64_t> hoff(nc);
     TB_CUDA(cudaMemcpy(hk.data(), key_out.p, nc * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     TB_CUDA(cudaMemcpy(hid.data(), s->work_ids.p, nc * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    TB_CUDA(cudaMemcpy(hdesc.data(), s->enc_desc.p, nc * sizeof(int4), cudaMemcpyDeviceToHost));
+    TB_CUDA(cudaMemcpy(hoff.data(), s->enc_off.p, nc * sizeof(int64_t), cudaMemcpyDeviceToHost));
     int64_t first_dense = 0;
     while (first_dense < nc && hk[first_dense] == 0) ++first_dense;
-    seats.reserve((size_t)(nc - first_dense) + 64);
+    std::vector<GroupRec> recs;
+    recs.reserve((size_t)(nc - first_dense) / kRows + 64);
     for (int64_t i = first_dense; i < nc;) {
       int64_t j = i;
-      while (j < nc && hk[j] == hk[i]) seats.push_back(hid[j++]);
-      while (seats.size() % kRows) seats.push_back(-1);
+      while (j < nc && hk[j] == hk[i]) ++j;
+      for (int64_t k = i; k < j; k += kRows) {
+        GroupRec g;
+        const int4 d0 = hdesc[hid[k]];
+        const int enc = d0.z & 0xff;
+        const int width = enc == ENC_D32 ? 4 : (enc == ENC_D16 ? 2 : 1);
+        g.c0 = d0.x;
+        g.nsub = d0.y * width / kSub;
+        g.enc = enc;
+        g.ovf = 0;
+        for (int r = 0; r < kRows; ++r) {
+          if (k + r < j) {
+            const int32_t id = hid[k + r];
+            g.id[r] = id;
+            g.off16[r] = (uint32_t)(hoff[id] >> 4);
+            g.ovf |= (hdesc[id].z >> 8) != 0;
+          } else {
+            g.id[r] = -1;
+            g.off16[r] = 0;
+          }
+        }
+        recs.push_back(g);
+      }
       i = j;
     }
-    s->n_groups = (int64_t)seats.size() / kRows;
-    s->dense_gids.alloc(seats.size() ? seats.size() : 1);
-    if (!seats.empty())
-      TB_CUDA(cudaMemcpy(s->dense_gids.p, seats.data(), seats.size() * sizeof(int32_t),
+    TB_REQUIRE(s->enc_bytes < ((int64_t)1 << 36), "compact stream larger than 64 GB per GPU");
+    s->n_groups = (int64_t)recs.size();
+    s->groups.alloc(recs.size() ? recs.size() : 1);
+    if (!recs.empty())
+      TB_CUDA(cudaMemcpy(s->groups.p, recs.data(), recs.size() * sizeof(GroupRec),
                          cudaMemcpyHostToDevice));
   }
   s->enc_data.alloc(s->enc_bytes + 16);
   k_encode<<<grid, 256, 0, st>>>(s->col.p, s->val.p, s->chunk_beg.p, nc, s->enc_desc.p, s->enc_off.p,
                                  s->enc_data.p);
   DevBuf<unsigned long long> counts;
-  counts.alloc(5);
+  counts.alloc(6);
   TB_CUDA(cudaMemsetAsync(counts.p, 0, counts.bytes(), st));
   k_count_enc<<<grid1, 256, 0, st>>>(s->enc_desc.p, nc, counts.p);
-  unsigned long long h[5];
+  unsigned long long h[6];
   TB_CUDA(cudaMemcpyAsync(h, counts.p, sizeof(h), cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaStreamSynchronize(st));
   for (int k = 0; k < 5; ++k) s->enc_chunks[k] = (int64_t)h[k];
+  s->n_overflow = (int64_t)h[5];
   s->n_sparse = s->enc_chunks[ENC_S32] + s->enc_chunks[ENC_S16];
   s->n_dense = nc - s->n_sparse;
 }

@@ -151,11 +151,15 @@ constexpr int kRedThreads = 256;
 
 // S_i = x_i * s_i over present rows -> sum / min / max; the last block to arrive folds the
 // per-block partials in block order and takes the reference's loop decision.
+// FUSED (single GPU): the row's chunk partials are added here instead of in k_combine_f64
+// (one kernel and one pass over s less); s_full is still written for k_ice_update.
+template <bool FUSED>
 __global__ void __launch_bounds__(kRedThreads)
-k_ice_reduce(const double *__restrict__ s_full, const double *__restrict__ x,
+k_ice_reduce(double *__restrict__ s_full, const double *__restrict__ x,
              const uint8_t *__restrict__ bad, uint8_t *__restrict__ present, int64_t n,
              int pass, int iterations, double max_dev, double *__restrict__ block_red,
-             double *__restrict__ trace, IceState *state) {
+             double *__restrict__ trace, IceState *state, const double *__restrict__ pf,
+             const long long *__restrict__ pc, const int64_t *__restrict__ row_chunk) {
   if (state->stopped) return;
   __shared__ double sh_sum[kRedThreads / 32], sh_min[kRedThreads / 32], sh_max[kRedThreads / 32];
   __shared__ long long sh_cnt[kRedThreads / 32];
@@ -165,14 +169,28 @@ k_ice_reduce(const double *__restrict__ s_full, const double *__restrict__ x,
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     bool p;
-    if (pass == 0) {
-      p = !bad[i] && s_full[n + i] > 0.0;      // row kept by copy_matrix (normalize_hic.py:165-177)
-      present[i] = p;
+    double si;
+    if (FUSED) {
+      double a = 0.0;
+      long long nc = 0;
+      for (int64_t c = row_chunk[i]; c < row_chunk[i + 1]; ++c) {
+        a += pf[c];
+        if (pass == 0) nc += pc[c];
+      }
+      s_full[i] = si = a;
+      if (pass == 0) present[i] = p = !bad[i] && nc > 0;
+      else p = present[i];
     } else {
-      p = present[i];
+      si = s_full[i];
+      if (pass == 0) {
+        p = !bad[i] && s_full[n + i] > 0.0;    // row kept by copy_matrix (normalize_hic.py:165-177)
+        present[i] = p;
+      } else {
+        p = present[i];
+      }
     }
     if (p) {
-      double S = x[i] * s_full[i];
+      double S = x[i] * si;
       sum += S;
       mn = fmin(mn, S);
       mx = fmax(mx, S);
@@ -201,14 +219,23 @@ k_ice_reduce(const double *__restrict__ s_full, const double *__restrict__ x,
     is_last = (t == gridDim.x - 1);
   }
   __syncthreads();
-  if (!is_last || threadIdx.x != 0) return;
+  if (!is_last || threadIdx.x >= 32) return;
   __threadfence();
+  // last block: one warp folds the per-block partials, lane l takes blocks l, l+32, ... and the
+  // lanes are then combined by a fixed butterfly -> same bits every run
   sum = 0.0; mn = INFINITY; mx = -INFINITY;
   double dcnt = 0.0;
-  for (unsigned int bl = 0; bl < gridDim.x; ++bl) {
+  for (unsigned int bl = threadIdx.x; bl < gridDim.x; bl += 32) {
     const volatile double *br = block_red + 4 * bl;
     sum += br[0]; mn = fmin(mn, br[1]); mx = fmax(mx, br[2]); dcnt += br[3];
   }
+  for (int o = 16; o; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    dcnt += __shfl_xor_sync(0xffffffffu, dcnt, o);
+  }
+  if (threadIdx.x != 0) return;
   state->blocks_arrived = 0;
   if (pass == 0) state->n_present = (long long)dcnt;
   const long long np = state->n_present;
@@ -439,7 +466,12 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
   std::vector<cudaEvent_t> ev(2 * (size_t)npass_max + 2);
   for (auto &e : ev) TB_CUDA(cudaEventCreate(&e));
   double *dst = s->world > 1 ? s->s_part.p : s->s_full.p;
-  const int poll = iterations == 0 ? 1 : 4;
+  // The host only needs to know WHEN the loop stopped: passes queued after the stop are no-ops
+  // on the device.  ICE converges geometrically, so the next look is scheduled where the
+  // deviation is predicted to cross max_dev (at most 16 passes ahead).
+  int next_poll = iterations == 0 ? 1 : 4;
+  double prev_dev = -1.0;
+  int prev_done = 0;
   int launched = 0;
   bool stopped = false;
   TB_CUDA(cudaEventRecord(ev[2 * npass_max], st));
@@ -451,24 +483,40 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
     else if (use_csr_rowsum()) launch_chunks<M_F64>(s, s->x.p, nullptr, s->state.p);
     else launch_rowsum(s, s->x.p, s->state.p);
     TB_CUDA(cudaEventRecord(ev[2 * p + 1], st));
-    if (s->nrows) {
-      if (p == 0)
-        k_combine_f64<true><<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
-            s->partial_f.p, s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, N, dst, s->state.p);
-      else
-        k_combine_f64<false><<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
-            s->partial_f.p, s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, N, dst, s->state.p);
+    if (s->world > 1) {
+      if (s->nrows) {
+        if (p == 0)
+          k_combine_f64<true><<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
+              s->partial_f.p, s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, N, dst, s->state.p);
+        else
+          k_combine_f64<false><<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
+              s->partial_f.p, s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, N, dst, s->state.p);
+      }
+      allreduce_f64(s, s->s_part.p, s->s_full.p, p == 0 ? 2 * N : N);
+      k_ice_reduce<false><<<rg, kRedThreads, 0, st>>>(
+          s->s_full.p, s->x.p, s->bad.p, s->present.p, N, p, iterations, max_dev, s->block_red.p,
+          s->trace.p, s->state.p, nullptr, nullptr, nullptr);
+    } else {
+      k_ice_reduce<true><<<rg, kRedThreads, 0, st>>>(
+          s->s_full.p, s->x.p, s->bad.p, s->present.p, N, p, iterations, max_dev, s->block_red.p,
+          s->trace.p, s->state.p, s->partial_f.p, s->partial_i.p, s->row_chunk.p);
     }
-    if (s->world > 1) allreduce_f64(s, s->s_part.p, s->s_full.p, p == 0 ? 2 * N : N);
-    k_ice_reduce<<<rg, kRedThreads, 0, st>>>(s->s_full.p, s->x.p, s->bad.p, s->present.p, N, p,
-                                             iterations, max_dev, s->block_red.p, s->trace.p,
-                                             s->state.p);
     k_ice_update<<<vg, 256, 0, st>>>(s->s_full.p, s->x.p, s->b.p, s->present.p, N, p, s->state.p);
     ++launched;
-    if ((p + 1) % poll == 0 || p == npass_max - 1) {
+    if (p + 1 >= next_poll || p == npass_max - 1) {
       TB_CUDA(cudaMemcpyAsync(s->h_state.p, s->state.p, sizeof(IceState), cudaMemcpyDeviceToHost, st));
       TB_CUDA(cudaStreamSynchronize(st));
-      stopped = s->h_state.p->stopped != 0;
+      const IceState &h = *s->h_state.p;
+      stopped = h.stopped != 0;
+      int step = 4;
+      if (!stopped && prev_dev > 0.0 && h.dev > 0.0 && h.dev < prev_dev && h.passes_done > prev_done) {
+        const double rate = log(prev_dev / h.dev) / (double)(h.passes_done - prev_done);
+        const double remain = log(h.dev / max_dev) / rate;
+        step = remain < 1.0 ? 1 : (remain > 16.0 ? 16 : (int)ceil(remain));
+      }
+      prev_dev = h.dev;
+      prev_done = h.passes_done;
+      next_poll = p + 1 + step;
     }
   }
   TB_CUDA(cudaEventRecord(ev[2 * npass_max + 1], st));
@@ -502,7 +550,7 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
     s->rowsum_ms += ms;
     ++s->rowsum_launches;
   }
-  s->total_launches = launched * (3 + (s->nrows ? 1 : 0)) + 2;
+  s->total_launches = launched * (s->world > 1 ? 5 : 4) + 2;
   for (auto &e : ev) cudaEventDestroy(e);
   return rc;
 }

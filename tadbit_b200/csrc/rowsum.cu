@@ -24,7 +24,6 @@ namespace tb {
 namespace {
 
 constexpr int kStages = 2;          // sub-blocks in flight per warp
-constexpr int kSub = 1024;          // bytes per row per stage
 constexpr int kDenseWarps = 24;     // warps per CTA, one CTA per SM
 constexpr int kWarpRing = kStages * kRows * kSub;                 // 8 KB per warp
 constexpr int kDenseSmem = kDenseWarps * kWarpRing + kDenseWarps * kStages * 8;
@@ -84,30 +83,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
       : "memory");
 }
 
-// One group of kRows same-shaped dense chunks, as a cursor over its kSub-byte sub-blocks.
-struct Group {
-  int32_t id[kRows];
-  int64_t off[kRows];
-  int c0, enc, row_bytes, nsub;
-};
-
-__device__ __forceinline__ void load_group(Group &g, int64_t gi, const int32_t *__restrict__ gids,
-                                           const int4 *__restrict__ desc,
-                                           const int64_t *__restrict__ off) {
-  const int4 seats = __ldg(reinterpret_cast<const int4 *>(gids) + gi);
-  g.id[0] = seats.x; g.id[1] = seats.y; g.id[2] = seats.z; g.id[3] = seats.w;
-  const int4 d = __ldg(desc + g.id[0]);          // seat 0 is always occupied
-  g.c0 = d.x;
-  g.enc = d.z;
-  g.row_bytes = d.y * (d.z == ENC_D32 ? 4 : (d.z == ENC_D16 ? 2 : 1));
-  g.nsub = (g.row_bytes + kSub - 1) / kSub;
-#pragma unroll
-  for (int r = 0; r < kRows; ++r) g.off[r] = g.id[r] >= 0 ? __ldg(off + g.id[r]) : 0;
-}
-
-// One full stage: kRows rows x kSub bytes = 512/256/128 columns for D8/D16/D32.  Everything is
-// compile-time shaped (dense chunks are padded to 512 columns), so the body is straight-line:
-// per column and row one byte-extract (PRMT), one DADD (exponent splice) and one DFMA.
+// One 512-byte piece of a stage for every row: 512/256/128 columns for D8/D16/D32.
+// Straight-line: per column and row one byte-extract (PRMT), one DADD (exponent splice) and
+// one DFMA; x is loaded once for the kRows rows.
 template <int ENC>
 __device__ __forceinline__ void consume(const uint8_t *stage, const double *xb, int lane,
                                         double lo[kRows], double hi[kRows]) {
@@ -139,11 +117,28 @@ __device__ __forceinline__ void consume(const uint8_t *stage, const double *xb, 
   }
 }
 
+template <int ENC>
+__device__ __forceinline__ void consume_stage(const uint8_t *sp, const double *xb, int lane,
+                                              double lo[kRows], double hi[kRows]) {
+  constexpr int W = ENC == ENC_D32 ? 4 : (ENC == ENC_D16 ? 2 : 1);
+#pragma unroll 1
+  for (int h = 0; h < kSub / 512; ++h) consume<ENC>(sp + h * 512, xb + h * (512 / W), lane, lo, hi);
+}
+
+__device__ __forceinline__ GroupRec load_rec(const GroupRec *__restrict__ recs, int64_t gi) {
+  const int4 *p = reinterpret_cast<const int4 *>(recs + gi);
+  const int4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+  GroupRec g;
+  g.off16[0] = a.x; g.off16[1] = a.y; g.off16[2] = a.z; g.off16[3] = a.w;
+  g.id[0] = b.x; g.id[1] = b.y; g.id[2] = b.z; g.id[3] = b.w;
+  g.c0 = c.x; g.nsub = c.y; g.enc = c.z; g.ovf = c.w;
+  return g;
+}
+
 __global__ void __launch_bounds__(kDenseWarps * 32, 1)
-k_rowsum_dense(const uint8_t *__restrict__ data, const int64_t *__restrict__ off,
-               const int4 *__restrict__ desc, const int32_t *__restrict__ gids, int64_t ngroups,
-               const double *__restrict__ x, double *__restrict__ partial,
-               const IceState *__restrict__ state) {
+k_rowsum_dense(const uint8_t *__restrict__ data, const GroupRec *__restrict__ recs, int64_t ngroups,
+               const int4 *__restrict__ desc, const double *__restrict__ x,
+               double *__restrict__ partial, const IceState *__restrict__ state) {
   if (state && state->stopped) return;
   extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
@@ -159,68 +154,92 @@ k_rowsum_dense(const uint8_t *__restrict__ data, const int64_t *__restrict__ off
   const int64_t warp = (int64_t)blockIdx.x * kDenseWarps + wic;
   const int64_t nwarp = (int64_t)gridDim.x * kDenseWarps;
 
-  // producer cursor (runs ahead) and consumer cursor over the same (group, sub-block) sequence
-  Group pg, cg;
+  // Producer cursor (pg, psub) runs kStages sub-blocks ahead of the consumer cursor (cg, csub)
+  // over the same sequence of (group, sub-block) pairs, across group boundaries.
   int64_t pgi = warp, cgi = warp;
   int psub = 0, csub = 0;
+  // producer keeps only what the copies need: payload offsets (0xffffffff = empty seat)
+  uint32_t poff[kRows];
+  int pnsub = 0;
+  GroupRec cg;
+  auto load_producer = [&](const GroupRec &g) {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) poff[r] = g.id[r] >= 0 ? g.off16[r] : 0xffffffffu;
+    pnsub = g.nsub;
+  };
   if (pgi < ngroups) {
-    load_group(pg, pgi, gids, desc, off);
-    cg = pg;
+    cg = load_rec(recs, pgi);
+    load_producer(cg);
   }
   auto issue = [&](int stage) {             // all lanes advance the cursor, lane 0 issues
     if (pgi >= ngroups) return;
-    constexpr int bytes = kSub;              // chunks are padded to whole sub-blocks
     if (lane == 0) {
       int nvalid = 0;
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) nvalid += pg.id[r] >= 0;
+      for (int r = 0; r < kRows; ++r) nvalid += poff[r] != 0xffffffffu;
       const uint32_t bar = bars + 8 * stage;
-      mbar_expect_tx(bar, (uint32_t)(nvalid * bytes));
+      mbar_expect_tx(bar, (uint32_t)(nvalid * kSub));
 #pragma unroll
       for (int r = 0; r < kRows; ++r)
-        if (pg.id[r] >= 0)
-          bulk_g2s(ring_u32 + (stage * kRows + r) * kSub, data + pg.off[r] + (int64_t)psub * kSub,
-                   (uint32_t)bytes, bar);
+        if (poff[r] != 0xffffffffu)
+          bulk_g2s(ring_u32 + (stage * kRows + r) * kSub,
+                   data + ((int64_t)poff[r] << 4) + (int64_t)psub * kSub, kSub, bar);
     }
-    if (++psub == pg.nsub) {
+    if (++psub == pnsub) {
       psub = 0;
       pgi += nwarp;
-      if (pgi < ngroups) load_group(pg, pgi, gids, desc, off);
+      if (pgi < ngroups) load_producer(load_rec(recs, pgi));
     }
   };
+#pragma unroll
   for (int s = 0; s < kStages; ++s) issue(s);
 
   double lo[kRows], hi[kRows];
 #pragma unroll
   for (int r = 0; r < kRows; ++r) lo[r] = hi[r] = 0.0;
-  uint32_t phase = 0;                      // bit s = parity to wait for on stage s
-  int stage = 0;
+  uint32_t parity = 0;
   while (cgi < ngroups) {
-    mbar_wait(bars + 8 * stage, (phase >> stage) & 1u);
-    phase ^= 1u << stage;
-    const uint8_t *sp = ring + stage * kRows * kSub;
-    const int W = cg.enc == ENC_D32 ? 4 : (cg.enc == ENC_D16 ? 2 : 1);
-    const double *xb = x + cg.c0 + (int64_t)csub * (kSub / W) + 2 * lane;
-#pragma unroll 1
-    for (int h = 0; h < kSub / 512; ++h) {
-      if (cg.enc == ENC_D8) consume<ENC_D8>(sp + h * 512, xb + h * 512, lane, lo, hi);
-      else if (cg.enc == ENC_D16) consume<ENC_D16>(sp + h * 512, xb + h * 256, lane, lo, hi);
-      else consume<ENC_D32>(sp + h * 512, xb + h * 128, lane, lo, hi);
-    }
-    __syncwarp();                          // every lane is done with this stage's bytes
-    issue(stage);
-    stage = (stage + 1 == kStages) ? 0 : stage + 1;
-    if (++csub == cg.nsub) {               // group finished: reduce and publish
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) {
-        const double a = warp_sum(lo[r] + hi[r]);
-        if (lane == 0 && cg.id[r] >= 0) partial[cg.id[r]] = a;
-        lo[r] = hi[r] = 0.0;
+    for (int stage = 0; stage < kStages; ++stage) {       // compile-time stage -> fixed addresses
+      if (cgi >= ngroups) break;
+      mbar_wait(bars + 8 * stage, parity);
+      const uint8_t *sp = ring + stage * kRows * kSub;
+      if (cg.enc == ENC_D8)
+        consume_stage<ENC_D8>(sp, x + cg.c0 + csub * kSub + 2 * lane, lane, lo, hi);
+      else if (cg.enc == ENC_D16)
+        consume_stage<ENC_D16>(sp, x + cg.c0 + csub * (kSub / 2) + 2 * lane, lane, lo, hi);
+      else
+        consume_stage<ENC_D32>(sp, x + cg.c0 + csub * (kSub / 4) + 2 * lane, lane, lo, hi);
+      __syncwarp();                          // every lane is done with this stage's bytes
+      issue(stage);
+      if (++csub == cg.nsub) {               // group finished: overflow cells, reduce, publish
+        if (cg.ovf) {
+          const int width = cg.enc == ENC_D16 ? 2 : 1;
+#pragma unroll
+          for (int r = 0; r < kRows; ++r) {
+            if (cg.id[r] < 0) continue;
+            const int novf = __ldg(desc + cg.id[r]).z >> 8;
+            const int2 *cells = reinterpret_cast<const int2 *>(
+                data + ((int64_t)cg.off16[r] << 4) + (int64_t)cg.nsub * kSub);
+            for (int k = lane; k < novf; k += 32) {
+              const int2 e = __ldg(cells + k);
+              lo[r] = fma(i2d(e.y), __ldg(x + e.x), lo[r]);
+            }
+          }
+          (void)width;
+        }
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          const double a = warp_sum(lo[r] + hi[r]);
+          if (lane == 0 && cg.id[r] >= 0) partial[cg.id[r]] = a;
+          lo[r] = hi[r] = 0.0;
+        }
+        csub = 0;
+        cgi += nwarp;
+        if (cgi < ngroups) cg = load_rec(recs, cgi);
       }
-      csub = 0;
-      cgi += nwarp;
-      if (cgi < ngroups) load_group(cg, cgi, gids, desc, off);
     }
+    parity ^= 1u;
   }
 }
 
@@ -239,7 +258,7 @@ k_rowsum_sparse(const uint8_t *__restrict__ data, const int64_t *__restrict__ of
     const uint8_t *p = data + off[c];
     const int n = d.y;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    if (d.z == ENC_S16) {
+    if ((d.z & 0xff) == ENC_S16) {
       const double *xb = x + d.x;
       const uint32_t *w = reinterpret_cast<const uint32_t *>(p);
       int k = lane;
@@ -293,8 +312,7 @@ void launch_rowsum(tb_store *s, const double *x, const IceState *state) {
     int64_t need = (s->n_groups + kDenseWarps - 1) / kDenseWarps;
     const int grid = (int)(need < s->sm_count ? need : s->sm_count);
     k_rowsum_dense<<<grid, kDenseWarps * 32, kDenseSmem, s->stream>>>(
-        s->enc_data.p, s->enc_off.p, s->enc_desc.p, s->dense_gids.p, s->n_groups, x, s->partial_f.p,
-        state);
+        s->enc_data.p, s->groups.p, s->n_groups, s->enc_desc.p, x, s->partial_f.p, state);
   }
   if (s->n_sparse) {
     int64_t need = (s->n_sparse + 7) / 8, cap = (int64_t)s->sm_count * 8;

@@ -31,7 +31,7 @@ def workload(name):
         desc = "synthetic human chr1 @10kb, dense Poisson x power-law (BASELINE configs[1])"
     elif name == "c3":      # genome-wide 5 kb, sparse
         chroms = genome_bins(5000)
-        params = SynthParams(seed=SEED, cis_scale=1300.0, cis_alpha=1.08, trans_mean=1.1e-3,
+        params = SynthParams(seed=SEED, cis_scale=1900.0, cis_alpha=1.08, trans_mean=1.2e-3,
                              vis_sigma=0.35, low_frac=0.02, low_scale=0.02, empty_frac=0.005)
         desc = "synthetic genome-wide human @5kb (BASELINE configs[2])"
     elif name == "c3s":     # 1/8 genome (chr1-3) at 5 kb: sparse profile at a size quick to build
