@@ -246,8 +246,9 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "kernel": "k_chunk_reduce<F64> (CSR walk)" if csr_walk else
-                          "k_rowsum_dense + k_rowsum_sparse (K1 over the compact stream)",
+                          "k_rowsum_tiles + k_rowsum_dense (+ k_rowsum_sparse) = K1 over the compact stream",
                 "kernel_ms": k1_ms, "stream_encodings": lay["encodings"],
+                "tile_cells": lay["tile_cells"], "tile_cells_padded": lay["tile_cells_padded"],
                 "kernel_share_of_step": rowsum_ms / dev_ms if dev_ms else None,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "layout_bytes_per_launch": layout_bytes,

@@ -110,9 +110,12 @@ int tb_store_destroy(tb_store *s);
 int tb_store_info(const tb_store *s, int64_t *nbins, int64_t *row_begin, int64_t *row_end,
                   int64_t *nnz_upper_owned, int64_t *nnz_full_owned, int64_t *device_bytes);
 
-/* Layout of the compact row-sum stream: out[0] payload bytes, out[1..5] chunks encoded as
- * S32, S16, D32, D16, D8 (tadbit_b200/csrc/encode.cu), out[6] chunks, out[7] CSR bytes. */
-int tb_store_layout(const tb_store *s, int64_t out[8]);
+/* Layout of the compact row-sum stream (tadbit_b200/csrc/encode.cu, tiles.cu):
+ * out[0] chunk payload bytes, out[1..6] chunks encoded as S32, S16, D32, D16, D8, T (cells in
+ * the sparse tiles), out[7] chunks, out[8] CSR bytes, out[9] cells in sparse tiles, out[10]
+ * the same with padding, out[11] tile work units, out[12] overflow cells of dense chunks,
+ * out[13] bytes of the sparse tiles. */
+int tb_store_layout(const tb_store *s, int64_t out[16]);
 
 /* Export the owned upper-triangle cells (row in block, row <= col), row-major sorted.
  * Call with row == NULL to get the count in *nnz first.  Buffers are HOST. */

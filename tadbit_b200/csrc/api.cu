@@ -204,12 +204,18 @@ int tb_store_info(const tb_store *s, int64_t *nbins, int64_t *row_begin, int64_t
   return TB_OK;
 }
 
-int tb_store_layout(const tb_store *s, int64_t out[8]) {
+int tb_store_layout(const tb_store *s, int64_t out[16]) {
   if (!s || !out) { set_error("null argument"); return TB_ERR_ARG; }
+  for (int k = 0; k < 16; ++k) out[k] = 0;
   out[0] = s->enc_bytes;
-  for (int k = 0; k < 5; ++k) out[1 + k] = s->enc_chunks[k];
-  out[6] = s->nchunks;
-  out[7] = (int64_t)(s->col.bytes() + s->val.bytes() + s->rowptr.bytes());
+  for (int k = 0; k < 6; ++k) out[1 + k] = s->enc_chunks[k];
+  out[7] = s->nchunks;
+  out[8] = (int64_t)(s->col.bytes() + s->val.bytes() + s->rowptr.bytes());
+  out[9] = s->t_ncells;
+  out[10] = s->t_npadded;
+  out[11] = s->t_nunits;
+  out[12] = s->n_overflow;
+  out[13] = s->t_nunits ? (int64_t)(s->t_npadded * 4 + s->t_perm.bytes() + s->t_slice.bytes()) : 0;
   return TB_OK;
 }
 

@@ -313,6 +313,7 @@ void finish_layout(tb_store *s) {
   // scratch
   const size_t nc = nchunks ? nchunks : 1, nn = N ? N : 1;
   s->partial_f.alloc(nc);
+  TB_CUDA(cudaMemsetAsync(s->partial_f.p, 0, s->partial_f.bytes(), st));   // tile chunks never write theirs
   s->partial_i.alloc(nc);
   s->x.alloc(nn + kXPad); s->b.alloc(nn);
   TB_CUDA(cudaMemsetAsync(s->x.p, 0, s->x.bytes(), st));
@@ -328,7 +329,9 @@ void finish_layout(tb_store *s) {
   TB_CUDA(cudaMemsetAsync(s->i_part.p, 0, s->i_part.bytes(), st));
   TB_CUDA(cudaStreamSynchronize(st));
   build_encoded(s);
-  s->device_bytes = s->enc_data.bytes() + s->enc_off.bytes() + s->enc_desc.bytes() + s->rowptr.bytes() + s->col.bytes() + s->val.bytes() + s->chunk_beg.bytes() +
+  build_tiles(s);
+  s->device_bytes = s->t_cells.bytes() + s->t_perm.bytes() + s->t_slice.bytes() + s->t_off.bytes() +
+                    s->t_partial.bytes() + s->enc_data.bytes() + s->enc_off.bytes() + s->enc_desc.bytes() + s->rowptr.bytes() + s->col.bytes() + s->val.bytes() + s->chunk_beg.bytes() +
                     s->chunk_row.bytes() + s->row_chunk.bytes() + s->partial_f.bytes() +
                     s->partial_i.bytes() + s->x.bytes() + s->b.bytes() +
                     s->s_part.bytes() + s->s_full.bytes() + s->i_part.bytes() + s->i_full.bytes() +

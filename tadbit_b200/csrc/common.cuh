@@ -87,10 +87,14 @@ constexpr int kChunk = 4096;      // max stored cells one warp reduces before wr
 constexpr int kPanel = 4096;      // column panel of the chunk planner / dense encodings
 constexpr int kSub = 1024;        // bytes per row per pipeline stage of k_rowsum_dense
 constexpr int kRows = 4;          // dense chunks (rows) one warp walks together
-constexpr int kXPad = 2048;       // zero tail of the gathered vector (dense chunks read past N)
+constexpr int kXPad = 16384;      // zero tail of the gathered vector (panels / windows read past N)
+constexpr int kTileRows = 2048;   // rows of a sparse tile (two per thread of a k_rowsum_tiles CTA)
+constexpr int kTileCols = 4 * kPanel;  // columns of a sparse tile = x window in shared memory (128 KB)
+constexpr int kTileColBits = 14;  // packed tile cell: column offset (14 bits) | value (18 bits)
+constexpr int kTileValBits = 32 - kTileColBits;
 
-// chunk encodings of the compact row-sum stream
-enum { ENC_S32 = 0, ENC_S16 = 1, ENC_D32 = 2, ENC_D16 = 3, ENC_D8 = 4 };
+// chunk encodings of the compact row-sum stream; ENC_T = the cells live in the sparse tiles
+enum { ENC_S32 = 0, ENC_S16 = 1, ENC_D32 = 2, ENC_D16 = 3, ENC_D8 = 4, ENC_T = 5 };
 
 // A group of kRows dense chunks that share (encoding, column panel): the unit of work of a
 // warp of k_rowsum_dense.  Built on the host in encode.cu.
@@ -135,7 +139,20 @@ struct tb_store {
   int64_t n_groups = 0;
   int64_t n_overflow = 0;                 // cells kept outside their dense chunk's value width
   int64_t enc_bytes = 0;
-  int64_t enc_chunks[5] = {0, 0, 0, 0, 0};  // chunks per encoding
+  int64_t enc_chunks[6] = {0, 0, 0, 0, 0, 0};  // chunks per encoding
+  // sparse tiles (tiles.cu): cells of ENC_T chunks, kTileRows x kTileCols tiles, rows of a tile
+  // sorted by length and stored lane-interleaved in slices of 32 rows (sliced ELL)
+  int64_t t_nrb = 0, t_nwin = 0;          // row blocks, column windows
+  int64_t t_ncells = 0, t_npadded = 0;    // real cells / stored cells incl. padding
+  tb::DevBuf<uint32_t> t_cells;           // packed cells, tile after tile
+  tb::DevBuf<int64_t> t_off;              // [t_nrb*t_nwin + 1] first cell of each tile
+  tb::DevBuf<uint16_t> t_perm;            // [tiles * kTileRows] local row handled by thread t
+  tb::DevBuf<uint32_t> t_slice;           // [tiles * 33] first cell of each 32-row slice in the tile
+  tb::DevBuf<int32_t> t_list;             // non-empty tile ids, grouped by work unit
+  tb::DevBuf<int32_t> t_unit;             // [t_nunits * 4] (row block, list begin, list end, 0)
+  tb::DevBuf<int32_t> t_unit_of_rb;       // [t_nrb + 1] units of a row block are contiguous
+  int64_t t_nunits = 0;
+  tb::DevBuf<double> t_partial;           // [t_nunits * kTileRows] per-unit row sums
   // scratch
   tb::DevBuf<double> partial_f;           // [nchunks]
   tb::DevBuf<long long> partial_i;        // [nchunks]
@@ -167,6 +184,9 @@ void export_upper(const tb_store *s, int64_t *nnz, int32_t *h_row, int32_t *h_co
 void build_encoded(tb_store *s);     // compact row-sum stream from the CSR
 // rowsum.cu
 void launch_rowsum(tb_store *s, const double *x, const IceState *state);   // K1 over the compact stream
+// tiles.cu
+void build_tiles(tb_store *s);       // sparse tiles from the ENC_T chunks (after build_encoded)
+void launch_rowsum_tiles(tb_store *s, const double *x, const IceState *state);
 // synth.cu
 void build_synthetic(tb_store *s, const tb_synth_params *p);
 void synthetic_row_counts(int64_t nbins, int32_t n_chrom, const int64_t *chrom_offsets,

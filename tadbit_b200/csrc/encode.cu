@@ -22,6 +22,8 @@
 // (encoding, panel) with rows ascending inside -- each kernel streams its payload front to
 // back.  The CSR stays resident for the one-pass kernels (filter statistics, diagonal sums,
 // export).
+#include <stdlib.h>
+
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -44,7 +46,7 @@ __device__ __forceinline__ int64_t dense_pos(int64_t s) {
 // desc = (first column, slots or cells, encoding | overflow cells << 8, payload bytes)
 __global__ void __launch_bounds__(256)
 k_plan(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
-       const int64_t *__restrict__ chunk_beg, int64_t nchunks, int64_t nbins,
+       const int64_t *__restrict__ chunk_beg, int64_t nchunks, int64_t nbins, bool use_tiles,
        int4 *__restrict__ desc, uint64_t *__restrict__ key, int32_t *__restrict__ ids) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -74,6 +76,8 @@ k_plan(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
       if (n16 == 0 && (int64_t)clast - cfirst < 65536 && 4 * count < best) {
         enc = ENC_S16; best = 4 * count;
       }
+      // small non-negative counts: the cells go to the sparse tiles (tiles.cu), 4 B each there
+      if (use_tiles && vmin >= 0 && vmax < (1 << kTileValBits)) { enc = ENC_T; best = 4 * count; }
       int32_t c0 = cfirst;
       int64_t n = count;
       if (cfirst / kPanel == clast / kPanel) {          // inside one panel: dense is possible
@@ -92,9 +96,12 @@ k_plan(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
         }
         if (denc >= 0) { enc = denc; best = dbest; c0 = p0; n = nslots; novf = dovf; }
       }
+      if (enc == ENC_T) best = 0;                       // no payload in the chunk stream
       desc[c] = make_int4(c0, (int)n, enc | (novf << 8), (int)align16(best));
-      // sparse chunks keep row order (key 0); dense chunks sort by (encoding, panel)
-      key[c] = enc >= ENC_D32 ? (((uint64_t)1 << 40) | ((uint64_t)enc << 32) | (uint32_t)c0) : 0;
+      // work order: sparse chunks in row order (key 0), dense chunks by (encoding, panel),
+      // tile chunks last (they are not walked chunk by chunk)
+      key[c] = enc == ENC_T ? ((uint64_t)1 << 41)
+               : (enc >= ENC_D32 ? (((uint64_t)1 << 40) | ((uint64_t)enc << 32) | (uint32_t)c0) : 0);
       ids[c] = (int32_t)c;
     }
   }
@@ -129,6 +136,8 @@ k_encode(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
     if (enc == ENC_S32) {
       int2 *o = reinterpret_cast<int2 *>(out);
       for (int64_t k = beg + lane; k < end; k += 32) o[k - beg] = make_int2(col[k], val[k]);
+    } else if (enc == ENC_T) {
+      // cells are written by build_tiles
     } else if (enc == ENC_S16) {
       uint32_t *o = reinterpret_cast<uint32_t *>(out);
       for (int64_t k = beg + lane; k < end; k += 32)
@@ -170,7 +179,7 @@ __global__ void k_count_enc(const int4 *__restrict__ desc, int64_t nchunks,
   for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nchunks;
        c += (int64_t)gridDim.x * blockDim.x) {
     atomicAdd(&counts[desc[c].z & 0xff], 1ull);
-    if (desc[c].z >> 8) atomicAdd(&counts[5], (unsigned long long)(desc[c].z >> 8));
+    if (desc[c].z >> 8) atomicAdd(&counts[6], (unsigned long long)(desc[c].z >> 8));
   }
 }
 
@@ -201,16 +210,18 @@ void build_encoded(tb_store *s) {
     DevBuf<int64_t> bytes, off_sorted;
     key_in.alloc(nc); key_out.alloc(nc); ids_in.alloc(nc);
     bytes.alloc(nc + 1); off_sorted.alloc(nc + 1);
-    k_plan<<<grid, 256, 0, st>>>(s->col.p, s->val.p, s->chunk_beg.p, nc, s->nbins, s->enc_desc.p,
-                                 key_in.p, ids_in.p);
+    const char *env = getenv("TB_TILES");
+    const bool use_tiles = !(env && env[0] == '0');      // TB_TILES=0: A/B switch, L2-gather path only
+    k_plan<<<grid, 256, 0, st>>>(s->col.p, s->val.p, s->chunk_beg.p, nc, s->nbins, use_tiles,
+                                 s->enc_desc.p, key_in.p, ids_in.p);
     size_t tmp_bytes = 0, tmp2 = 0;
     TB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_in.p, key_out.p, ids_in.p,
-                                            s->work_ids.p, nc, 0, 41, st));
+                                            s->work_ids.p, nc, 0, 42, st));
     TB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, bytes.p, off_sorted.p, nc + 1, st));
     DevBuf<uint8_t> tmp;
     tmp.alloc((tmp_bytes > tmp2 ? tmp_bytes : tmp2) + 16);
     TB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key_in.p, key_out.p, ids_in.p,
-                                            s->work_ids.p, nc, 0, 41, st));
+                                            s->work_ids.p, nc, 0, 42, st));
     TB_CUDA(cudaMemsetAsync(bytes.p + nc, 0, sizeof(int64_t), st));
     k_sorted_bytes<<<grid1, 256, 0, st>>>(s->work_ids.p, s->enc_desc.p, nc, bytes.p);
     TB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp2, bytes.p, off_sorted.p, nc + 1, st));
@@ -232,7 +243,7 @@ void build_encoded(tb_store *s) {
     while (first_dense < nc && hk[first_dense] == 0) ++first_dense;
     std::vector<GroupRec> recs;
     recs.reserve((size_t)(nc - first_dense) / kRows + 64);
-    for (int64_t i = first_dense; i < nc;) {
+    for (int64_t i = first_dense; i < nc && hk[i] < ((uint64_t)1 << 41);) {
       int64_t j = i;
       while (j < nc && hk[j] == hk[i]) ++j;
       for (int64_t k = i; k < j; k += kRows) {
@@ -270,16 +281,16 @@ void build_encoded(tb_store *s) {
   k_encode<<<grid, 256, 0, st>>>(s->col.p, s->val.p, s->chunk_beg.p, nc, s->enc_desc.p, s->enc_off.p,
                                  s->enc_data.p);
   DevBuf<unsigned long long> counts;
-  counts.alloc(6);
+  counts.alloc(7);
   TB_CUDA(cudaMemsetAsync(counts.p, 0, counts.bytes(), st));
   k_count_enc<<<grid1, 256, 0, st>>>(s->enc_desc.p, nc, counts.p);
-  unsigned long long h[6];
+  unsigned long long h[7];
   TB_CUDA(cudaMemcpyAsync(h, counts.p, sizeof(h), cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaStreamSynchronize(st));
-  for (int k = 0; k < 5; ++k) s->enc_chunks[k] = (int64_t)h[k];
-  s->n_overflow = (int64_t)h[5];
+  for (int k = 0; k < 6; ++k) s->enc_chunks[k] = (int64_t)h[k];
+  s->n_overflow = (int64_t)h[6];
   s->n_sparse = s->enc_chunks[ENC_S32] + s->enc_chunks[ENC_S16];
-  s->n_dense = nc - s->n_sparse;
+  s->n_dense = s->enc_chunks[ENC_D32] + s->enc_chunks[ENC_D16] + s->enc_chunks[ENC_D8];
 }
 
 }  // namespace tb

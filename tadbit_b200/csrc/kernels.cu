@@ -91,11 +91,25 @@ k_chunk_reduce(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
 
 // out[rb + r] = sum of the row's chunk partials, in chunk order.  WITH_COUNT also writes the
 // count partials (as exact doubles) to out[N + rb + r] so one all-reduce carries both.
+// sum over the work units of the row's block of the sparse-tile partials (tiles.cu), unit order
+struct TileSums {
+  const double *partial;        // null when the store has no sparse tiles
+  const int32_t *unit_of_rb;
+};
+__device__ __forceinline__ double tile_sum(const TileSums &ts, int64_t r) {
+  if (!ts.partial) return 0.0;
+  const int64_t rb = r / kTileRows;
+  double a = 0.0;
+  for (int32_t u = ts.unit_of_rb[rb]; u < ts.unit_of_rb[rb + 1]; ++u)
+    a += ts.partial[(int64_t)u * kTileRows + (r % kTileRows)];
+  return a;
+}
+
 template <bool WITH_COUNT>
 __global__ void k_combine_f64(const double *__restrict__ pf, const long long *__restrict__ pc,
                               const int64_t *__restrict__ row_chunk, int64_t nrows, int64_t rb,
                               int64_t nbins, double *__restrict__ out,
-                              const IceState *__restrict__ state) {
+                              const IceState *__restrict__ state, TileSums ts) {
   if (state && state->stopped) return;
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
        r += (int64_t)gridDim.x * blockDim.x) {
@@ -105,6 +119,7 @@ __global__ void k_combine_f64(const double *__restrict__ pf, const long long *__
       a += pf[c];
       if (WITH_COUNT) n += pc[c];
     }
+    if (!WITH_COUNT) a += tile_sum(ts, r);        // pass 0 (WITH_COUNT) walks the CSR, all cells
     out[rb + r] = a;
     if (WITH_COUNT) out[nbins + rb + r] = (double)n;
   }
@@ -159,7 +174,7 @@ k_ice_reduce(double *__restrict__ s_full, const double *__restrict__ x,
              const uint8_t *__restrict__ bad, uint8_t *__restrict__ present, int64_t n,
              int pass, int iterations, double max_dev, double *__restrict__ block_red,
              double *__restrict__ trace, IceState *state, const double *__restrict__ pf,
-             const long long *__restrict__ pc, const int64_t *__restrict__ row_chunk) {
+             const long long *__restrict__ pc, const int64_t *__restrict__ row_chunk, TileSums ts) {
   if (state->stopped) return;
   __shared__ double sh_sum[kRedThreads / 32], sh_min[kRedThreads / 32], sh_max[kRedThreads / 32];
   __shared__ long long sh_cnt[kRedThreads / 32];
@@ -177,6 +192,7 @@ k_ice_reduce(double *__restrict__ s_full, const double *__restrict__ x,
         a += pf[c];
         if (pass == 0) nc += pc[c];
       }
+      if (pass != 0) a += tile_sum(ts, i);        // pass 0 walks the CSR, all cells
       s_full[i] = si = a;
       if (pass == 0) present[i] = p = !bad[i] && nc > 0;
       else p = present[i];
@@ -466,6 +482,8 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
   std::vector<cudaEvent_t> ev(2 * (size_t)npass_max + 2);
   for (auto &e : ev) TB_CUDA(cudaEventCreate(&e));
   double *dst = s->world > 1 ? s->s_part.p : s->s_full.p;
+  const bool csr_walk = use_csr_rowsum();
+  const TileSums ts = {(!csr_walk && s->t_nunits) ? s->t_partial.p : nullptr, s->t_unit_of_rb.p};
   // The host only needs to know WHEN the loop stopped: passes queued after the stop are no-ops
   // on the device.  ICE converges geometrically, so the next look is scheduled where the
   // deviation is predicted to cross max_dev (at most 16 passes ahead).
@@ -487,21 +505,25 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
       if (s->nrows) {
         if (p == 0)
           k_combine_f64<true><<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
-              s->partial_f.p, s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, N, dst, s->state.p);
+              s->partial_f.p, s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, N, dst, s->state.p, ts);
         else
           k_combine_f64<false><<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
-              s->partial_f.p, s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, N, dst, s->state.p);
+              s->partial_f.p, s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, N, dst, s->state.p, ts);
       }
       allreduce_f64(s, s->s_part.p, s->s_full.p, p == 0 ? 2 * N : N);
       k_ice_reduce<false><<<rg, kRedThreads, 0, st>>>(
           s->s_full.p, s->x.p, s->bad.p, s->present.p, N, p, iterations, max_dev, s->block_red.p,
-          s->trace.p, s->state.p, nullptr, nullptr, nullptr);
+          s->trace.p, s->state.p, nullptr, nullptr, nullptr, ts);
     } else {
       k_ice_reduce<true><<<rg, kRedThreads, 0, st>>>(
           s->s_full.p, s->x.p, s->bad.p, s->present.p, N, p, iterations, max_dev, s->block_red.p,
-          s->trace.p, s->state.p, s->partial_f.p, s->partial_i.p, s->row_chunk.p);
+          s->trace.p, s->state.p, s->partial_f.p, s->partial_i.p, s->row_chunk.p, ts);
     }
     k_ice_update<<<vg, 256, 0, st>>>(s->s_full.p, s->x.p, s->b.p, s->present.p, N, p, s->state.p);
+    // pass 0 walked the CSR and left a partial in EVERY chunk; chunks whose cells live in the
+    // sparse tiles are never written again, so clear the partials before the compact passes
+    if (p == 0 && ts.partial)
+      TB_CUDA(cudaMemsetAsync(s->partial_f.p, 0, s->partial_f.bytes(), st));
     ++launched;
     if (p + 1 >= next_poll || p == npass_max - 1) {
       TB_CUDA(cudaMemcpyAsync(s->h_state.p, s->state.p, sizeof(IceState), cudaMemcpyDeviceToHost, st));
@@ -583,7 +605,8 @@ void norm_sum(tb_store *s, const double *h_bias, const uint8_t *h_bad, double *o
   if (s->nrows)
     k_combine_f64<false><<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
         s->partial_f.p, s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, N, s->s_full.p,
-        nullptr);
+        nullptr, TileSums{(!use_csr_rowsum() && s->t_nunits) ? s->t_partial.p : nullptr,
+                          s->t_unit_of_rb.p});
   k_dot_rows<<<1, 1024, 0, st>>>(s->x.p, s->s_full.p, s->row_begin, s->row_end, s->scal_f.p);
   if (s->world > 1) allreduce_f64(s, s->scal_f.p, s->scal_f.p + 8, 1);
   TB_CUDA(cudaMemcpyAsync(out, s->world > 1 ? s->scal_f.p + 8 : s->scal_f.p, sizeof(double),

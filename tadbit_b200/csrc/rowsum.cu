@@ -302,6 +302,7 @@ k_rowsum_sparse(const uint8_t *__restrict__ data, const int64_t *__restrict__ of
 }  // namespace
 
 void launch_rowsum(tb_store *s, const double *x, const IceState *state) {
+  launch_rowsum_tiles(s, x, state);
   if (s->n_groups) {
     static bool attr_set = false;
     if (!attr_set) {

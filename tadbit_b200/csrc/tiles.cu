@@ -1,0 +1,403 @@
+// Sparse tiles: the part of K1 (s_i = sum_j v_ij x_j) for cells outside the dense panels.
+//
+// Gathering x_j straight from L2 costs a 32-byte sector per 8-byte value and saturates the L2
+// (measured on the genome-wide 5 kb matrix: 13 TB/s of sector traffic, 11 % L1 hit rate).
+// Here the sparse cells are tiled kTileRows x kTileCols: a CTA owns a row block, walks its
+// non-empty tiles and keeps the tile's x window (kTileCols = 16384 doubles, 128 KB) in shared
+// memory -- fetched by cp.async.bulk while the threads already load their tile metadata and
+// first cells -- so every gather is a shared-memory read.  (A wide single buffer beats two
+// narrow ones here: far from the diagonal a tile holds only a few cells per row, and the fixed
+// cost per tile is what matters.)
+//
+// Inside a tile the rows are sorted by their number of cells (per-tile permutation) and stored
+// as sliced ELL: 32 consecutive sorted rows form a slice, cell k of lane l sits at
+// slice_base + 32 k + l (one coalesced 128-byte load per warp and k), padded to the slice's
+// longest row; sorting keeps the padding small even where a row has 0-10 cells per tile.
+// A tile has 64 slices for 32 warps: warp w takes slice w and slice 63-w (longest with
+// shortest), which evens out the work between the warps that meet at the tile's barrier.
+// A cell is 32 bits: column offset in the window (14) | count (18).  A thread accumulates its
+// row of the tile in a register and adds it to the row block's accumulators in shared memory
+// (conflict-free: the permutation maps threads to distinct rows).  Row blocks are cut into work
+// units of roughly equal cell count; a unit writes kTileRows partial sums, added per row in
+// unit order by the combine step -> deterministic, no atomics in the pass loop.
+#include <algorithm>
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace tb {
+
+namespace {
+
+constexpr int kTileThreads = kTileRows / 2;
+constexpr int kSlices = kTileRows / 32;
+constexpr int kSliceTab = kSlices + 1;
+constexpr int kRowBits = 11;                               // kTileRows = 2048
+constexpr int kWinBytes = kTileCols * 8;
+constexpr int kTileSmem = kWinBytes + kTileRows * 8 + 64;
+constexpr uint32_t kColMask = (1u << kTileColBits) - 1u;
+static_assert(kTileRows == 1 << kRowBits, "kRowBits");
+
+__device__ __forceinline__ double u2d(uint32_t v) {
+  return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
+}
+__device__ __forceinline__ uint32_t ldg_stream_u32(const void *p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+// ---- build ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_tile_count(const int32_t *__restrict__ col, const int64_t *__restrict__ chunk_beg,
+             const int32_t *__restrict__ chunk_row, const int4 *__restrict__ desc, int64_t nchunks,
+             int64_t nwin, int32_t *__restrict__ cnt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t c = warp; c < nchunks; c += nwarp) {
+    if ((desc[c].z & 0xff) != ENC_T) continue;
+    const int64_t beg = chunk_beg[c], end = chunk_beg[c + 1], row = chunk_row[c];
+    for (int64_t k = beg + lane; k < end; k += 32)
+      atomicAdd(&cnt[row * nwin + col[k] / kTileCols], 1);
+  }
+}
+
+// one CTA per tile: sort the tile's rows by cell count (descending, ties by row), write the
+// permutation, its inverse, the slice offsets and the padded size of the tile
+__global__ void __launch_bounds__(kTileThreads)
+k_tile_sort(const int32_t *__restrict__ cnt, int64_t nwin, uint16_t *__restrict__ perm,
+            uint16_t *__restrict__ inv, uint32_t *__restrict__ slice, int64_t *__restrict__ tile_size,
+            unsigned long long *__restrict__ totals) {
+  __shared__ uint32_t key[kTileRows];
+  const int t = threadIdx.x;
+  const int64_t tile = blockIdx.x, rb = tile / nwin, w = tile % nwin;
+  unsigned long long real = 0;
+  for (int e = t; e < kTileRows; e += kTileThreads) {
+    const uint32_t mine = (uint32_t)cnt[(rb * kTileRows + e) * nwin + w];
+    key[e] = (mine << kRowBits) | (uint32_t)(kTileRows - 1 - e);
+    real += mine;
+  }
+  __syncthreads();
+  for (int k = 2; k <= kTileRows; k <<= 1)            // bitonic sort, descending
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int e = t; e < kTileRows; e += kTileThreads) {
+        const int o = e ^ j;
+        if (o > e) {
+          const uint32_t a = key[e], b = key[o];
+          const bool desc_dir = (e & k) == 0;
+          if (desc_dir ? a < b : a > b) { key[e] = b; key[o] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int e = t; e < kTileRows; e += kTileThreads) {
+    const int row = kTileRows - 1 - (int)(key[e] & (uint32_t)(kTileRows - 1));
+    perm[tile * kTileRows + e] = (uint16_t)row;
+    inv[(rb * kTileRows + row) * nwin + w] = (uint16_t)e;
+  }
+  if (t == 0) {                                        // slice s is as long as its first row
+    uint32_t run = 0;
+    for (int s = 0; s < kSlices; ++s) {
+      slice[tile * kSliceTab + s] = run;
+      run += (key[s * 32] >> kRowBits) * 32u;
+    }
+    slice[tile * kSliceTab + kSlices] = run;
+    tile_size[tile] = run;
+  }
+  for (int o = 16; o; o >>= 1) real += __shfl_xor_sync(0xffffffffu, real, o);
+  if ((t & 31) == 0 && real) atomicAdd(totals, real);  // unpadded cells, for the layout report
+}
+
+// one thread per row: for every tile chunk, the number of tile cells of the same row that sit
+// in the chunk's FIRST window but in earlier chunks (a window spans several panels, so dense
+// chunks can split a row's sparse cells of one window over several chunks)
+__global__ void k_tile_rank_base(const int32_t *__restrict__ col, const int64_t *__restrict__ chunk_beg,
+                                 const int64_t *__restrict__ row_chunk, const int4 *__restrict__ desc,
+                                 int64_t nrows, int32_t *__restrict__ base) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    int64_t cur_w = -1, cur_n = 0;
+    for (int64_t c = row_chunk[r]; c < row_chunk[r + 1]; ++c) {
+      if ((desc[c].z & 0xff) != ENC_T) continue;
+      const int64_t beg = chunk_beg[c], end = chunk_beg[c + 1];
+      const int64_t wf = col[beg] / kTileCols, wl = col[end - 1] / kTileCols;
+      base[c] = wf == cur_w ? (int32_t)cur_n : 0;
+      int64_t lo = beg, hi = end;                      // first cell of the chunk in window wl
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (col[mid] < wl * kTileCols) lo = mid + 1; else hi = mid;
+      }
+      cur_n = (wl == cur_w ? cur_n : 0) + (end - lo);
+      cur_w = wl;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_tile_fill(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
+            const int64_t *__restrict__ chunk_beg, const int32_t *__restrict__ chunk_row,
+            const int4 *__restrict__ desc, const int32_t *__restrict__ rank_base, int64_t nchunks,
+            int64_t nwin, const uint16_t *__restrict__ inv, const uint32_t *__restrict__ slice,
+            const int64_t *__restrict__ t_off, uint32_t *__restrict__ cells) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t c = warp; c < nchunks; c += nwarp) {
+    if ((desc[c].z & 0xff) != ENC_T) continue;
+    const int64_t beg = chunk_beg[c], end = chunk_beg[c + 1], row = chunk_row[c];
+    const int64_t rb = row / kTileRows;
+    const int64_t wfirst = col[beg] / kTileCols;
+    const int32_t base = rank_base[c];
+    for (int64_t k = beg + lane; k < end; k += 32) {
+      const int32_t cc = col[k];
+      const int64_t w = cc / kTileCols;
+      int64_t lo = beg, hi = k;                        // first cell of this chunk in window w
+      const int32_t wstart = (int32_t)(w * kTileCols);
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (col[mid] < wstart) lo = mid + 1; else hi = mid;
+      }
+      const int64_t rank = k - lo + (w == wfirst ? base : 0), tile = rb * nwin + w;
+      const int t = inv[row * nwin + w];
+      cells[t_off[tile] + slice[tile * kSliceTab + (t >> 5)] + rank * 32 + (t & 31)] =
+          (uint32_t)(cc - wstart) | ((uint32_t)val[k] << kTileColBits);
+    }
+  }
+}
+
+// ---- the pass kernel --------------------------------------------------------------------------
+__device__ __forceinline__ double cell_term(uint32_t c, const double *xw) {
+  return u2d(c >> kTileColBits) * xw[c & kColMask];
+}
+
+// one slice of `len` cells per lane, 16 independent 128-byte warp loads kept in flight;
+// c[] holds the first 16 cells when len >= 16 (loaded before the window was waited for)
+__device__ __forceinline__ double slice_sum(const uint32_t *__restrict__ p, int len, uint32_t c[16],
+                                            const double *xw) {
+  double a0 = 0.0, a1 = 0.0;
+  int k = 0;
+  for (; k + 16 <= len; k += 16) {
+    uint32_t d[16];
+    const bool more = k + 32 <= len;
+    if (more) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) d[q] = ldg_stream_u32(p + (k + 16 + q) * 32);
+    }
+#pragma unroll
+    for (int q = 0; q < 16; q += 2) {
+      a0 += cell_term(c[q], xw);
+      a1 += cell_term(c[q + 1], xw);
+    }
+    if (more) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) c[q] = d[q];
+    }
+  }
+  for (; k < len; ++k) a0 += cell_term(ldg_stream_u32(p + k * 32), xw);
+  return a0 + a1;
+}
+
+__global__ void __launch_bounds__(kTileThreads, 1)
+k_rowsum_tiles(const uint32_t *__restrict__ cells, const int64_t *__restrict__ t_off,
+               const uint16_t *__restrict__ perm, const uint32_t *__restrict__ slice,
+               const int32_t *__restrict__ list, const int4 *__restrict__ unit, int64_t nunits,
+               int64_t nwin, const double *__restrict__ x, double *__restrict__ partial,
+               const IceState *__restrict__ state) {
+  if (state && state->stopped) return;
+  extern __shared__ __align__(128) uint8_t smem[];
+  double *xw = reinterpret_cast<double *>(smem);                       // [kTileCols]
+  double *acc = reinterpret_cast<double *>(smem + kWinBytes);          // [kTileRows]
+  const uint32_t bar = smem_u32(smem + kWinBytes + kTileRows * 8);
+  const int t = threadIdx.x, lane = t & 31, wic = t >> 5;
+  const int sa = wic, sb = kSlices - 1 - wic;          // longest slices paired with shortest
+  if (t == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t parity = 0;
+  for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+    const int4 un = unit[u];
+    const int i0 = un.y, n = un.z - un.y;
+    acc[t] = 0.0;
+    acc[t + kTileThreads] = 0.0;
+    for (int j = 0; j < n; ++j) {
+      const int64_t tile = list[i0 + j];
+      __syncthreads();                       // the window of the previous tile is consumed
+      if (t == 0) {                          // 128 KB window, four 32 KB bulk copies
+        const double *src = x + (tile % nwin) * kTileCols;
+        mbar_expect_tx(bar, kWinBytes);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          bulk_g2s(smem_u32(xw) + q * (kWinBytes / 4), src + q * (kTileCols / 4), kWinBytes / 4, bar);
+      }
+      // metadata and the first cells do not depend on the window: fetch them while it lands
+      const uint32_t *st = slice + tile * kSliceTab;
+      const uint32_t a0 = st[sa], a1 = st[sa + 1], b0 = st[sb], b1 = st[sb + 1];
+      const int len_a = (int)((a1 - a0) >> 5), len_b = (int)((b1 - b0) >> 5);
+      const int row_a = perm[tile * kTileRows + sa * 32 + lane];
+      const int row_b = perm[tile * kTileRows + sb * 32 + lane];
+      const uint32_t *pa = cells + t_off[tile] + a0 + lane, *pb = cells + t_off[tile] + b0 + lane;
+      uint32_t c[16];
+      if (len_a >= 16) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) c[q] = ldg_stream_u32(pa + q * 32);
+      }
+      mbar_wait(bar, parity);
+      parity ^= 1u;
+      if (len_a) acc[row_a] += slice_sum(pa, len_a, c, xw);    // distinct rows: no conflict
+      if (len_b >= 16) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) c[q] = ldg_stream_u32(pb + q * 32);
+      }
+      if (len_b) acc[row_b] += slice_sum(pb, len_b, c, xw);
+    }
+    __syncthreads();
+    partial[u * kTileRows + t] = acc[t];
+    partial[u * kTileRows + t + kTileThreads] = acc[t + kTileThreads];
+    __syncthreads();                          // acc is re-zeroed at the top of the next unit
+  }
+}
+
+inline int grid_1d(int64_t n, int threads, int sm_count, int per_sm) {
+  int64_t g = (n + threads - 1) / threads, cap = (int64_t)sm_count * per_sm;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+}  // namespace
+
+void build_tiles(tb_store *s) {
+  cudaStream_t st = s->stream;
+  s->t_nrb = s->t_nwin = s->t_ncells = s->t_npadded = s->t_nunits = 0;
+  if (s->enc_chunks[ENC_T] == 0) return;
+  const int64_t nrb = (s->nrows + kTileRows - 1) / kTileRows;
+  const int64_t nwin = (s->nbins + kTileCols - 1) / kTileCols;
+  const int64_t ntiles = nrb * nwin;
+  TB_REQUIRE(ntiles < 2147483647LL, "too many sparse tiles");
+  s->t_nrb = nrb;
+  s->t_nwin = nwin;
+  DevBuf<int32_t> cnt;
+  DevBuf<uint16_t> inv;
+  DevBuf<int64_t> tile_size;
+  DevBuf<unsigned long long> totals;
+  cnt.alloc(nrb * kTileRows * nwin);
+  inv.alloc(nrb * kTileRows * nwin);
+  tile_size.alloc(ntiles + 1);
+  totals.alloc(1);
+  TB_CUDA(cudaMemsetAsync(cnt.p, 0, cnt.bytes(), st));
+  TB_CUDA(cudaMemsetAsync(tile_size.p, 0, tile_size.bytes(), st));
+  TB_CUDA(cudaMemsetAsync(totals.p, 0, totals.bytes(), st));
+  const int cg = grid_1d(s->nchunks * 32, 256, s->sm_count, 8);
+  k_tile_count<<<cg, 256, 0, st>>>(s->col.p, s->chunk_beg.p, s->chunk_row.p, s->enc_desc.p,
+                                   s->nchunks, nwin, cnt.p);
+  s->t_perm.alloc(ntiles * kTileRows);
+  s->t_slice.alloc(ntiles * kSliceTab);
+  s->t_off.alloc(ntiles + 1);
+  k_tile_sort<<<(unsigned)ntiles, kTileThreads, 0, st>>>(cnt.p, nwin, s->t_perm.p, inv.p,
+                                                        s->t_slice.p, tile_size.p, totals.p);
+  {
+    size_t tmp_bytes = 0;
+    TB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, tile_size.p, s->t_off.p, ntiles + 1, st));
+    DevBuf<uint8_t> tmp;
+    tmp.alloc(tmp_bytes ? tmp_bytes : 1);
+    TB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, tile_size.p, s->t_off.p, ntiles + 1, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+  }
+  std::vector<int64_t> h_size(ntiles);
+  unsigned long long h_total = 0;
+  TB_CUDA(cudaMemcpy(h_size.data(), tile_size.p, ntiles * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  TB_CUDA(cudaMemcpy(&h_total, totals.p, sizeof(h_total), cudaMemcpyDeviceToHost));
+  TB_CUDA(cudaMemcpy(&s->t_npadded, s->t_off.p + ntiles, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  s->t_ncells = (int64_t)h_total;
+  cnt.release();
+  s->t_cells.alloc(s->t_npadded ? s->t_npadded : 1);
+  TB_CUDA(cudaMemsetAsync(s->t_cells.p, 0, s->t_cells.bytes(), st));       // padding = (col 0, count 0)
+  DevBuf<int32_t> rank_base;
+  rank_base.alloc(s->nchunks + 1);
+  TB_CUDA(cudaMemsetAsync(rank_base.p, 0, rank_base.bytes(), st));
+  k_tile_rank_base<<<grid_1d(s->nrows, 256, s->sm_count, 16), 256, 0, st>>>(
+      s->col.p, s->chunk_beg.p, s->row_chunk.p, s->enc_desc.p, s->nrows, rank_base.p);
+  k_tile_fill<<<cg, 256, 0, st>>>(s->col.p, s->val.p, s->chunk_beg.p, s->chunk_row.p, s->enc_desc.p,
+                                  rank_base.p, s->nchunks, nwin, inv.p, s->t_slice.p, s->t_off.p,
+                                  s->t_cells.p);
+  // Work units: each row block's non-empty tiles, cut into runs of about equal stored cells so
+  // that there are ~16 units per SM whatever the number of row blocks (1 GPU or a 1/8 shard).
+  const double target = (double)s->t_npadded / (16.0 * s->sm_count) + 1.0;
+  std::vector<int32_t> list, units, unit_of_rb(nrb + 1, 0);
+  for (int64_t rb = 0; rb < nrb; ++rb) {
+    unit_of_rb[rb] = (int32_t)(units.size() / 4);
+    int64_t run = 0;
+    int32_t begin = (int32_t)list.size();
+    for (int64_t w = 0; w < nwin; ++w) {
+      const int64_t sz = h_size[rb * nwin + w];
+      if (!sz) continue;
+      list.push_back((int32_t)(rb * nwin + w));
+      run += sz;
+      if ((double)run >= target) {
+        units.insert(units.end(), {(int32_t)rb, begin, (int32_t)list.size(), 0});
+        begin = (int32_t)list.size();
+        run = 0;
+      }
+    }
+    if ((int32_t)list.size() > begin)
+      units.insert(units.end(), {(int32_t)rb, begin, (int32_t)list.size(), 0});
+  }
+  unit_of_rb[nrb] = (int32_t)(units.size() / 4);
+  s->t_nunits = (int64_t)units.size() / 4;
+  s->t_list.alloc(list.size() ? list.size() : 1);
+  s->t_unit.alloc(units.size() ? units.size() : 4);
+  s->t_unit_of_rb.alloc(nrb + 1);
+  s->t_partial.alloc(s->t_nunits ? s->t_nunits * kTileRows : 1);
+  if (!list.empty())
+    TB_CUDA(cudaMemcpy(s->t_list.p, list.data(), list.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  if (!units.empty())
+    TB_CUDA(cudaMemcpy(s->t_unit.p, units.data(), units.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  TB_CUDA(cudaMemcpy(s->t_unit_of_rb.p, unit_of_rb.data(), (nrb + 1) * sizeof(int32_t),
+                     cudaMemcpyHostToDevice));
+  TB_CUDA(cudaMemsetAsync(s->t_partial.p, 0, s->t_partial.bytes(), st));
+  TB_CUDA(cudaStreamSynchronize(st));
+}
+
+void launch_rowsum_tiles(tb_store *s, const double *x, const IceState *state) {
+  if (s->t_nunits == 0) return;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TB_CUDA(cudaFuncSetAttribute(k_rowsum_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
+    attr_set = true;
+  }
+  const int grid = (int)(s->t_nunits < s->sm_count ? s->t_nunits : s->sm_count);
+  k_rowsum_tiles<<<grid, kTileThreads, kTileSmem, s->stream>>>(
+      s->t_cells.p, s->t_off.p, s->t_perm.p, s->t_slice.p, s->t_list.p,
+      reinterpret_cast<const int4 *>(s->t_unit.p), s->t_nunits, s->t_nwin, x, s->t_partial.p, state);
+}
+
+}  // namespace tb

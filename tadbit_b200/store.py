@@ -97,10 +97,14 @@ class ContactStore(object):
 
     def layout(self):
         """Compact row-sum stream: payload bytes and chunks per encoding."""
-        out = np.zeros(8, dtype=np.int64)
+        out = np.zeros(16, dtype=np.int64)
         check(lib().tb_store_layout(self._h, ptr(out, C.c_int64)))
-        return dict(stream_bytes=int(out[0]), chunks=int(out[6]), csr_bytes=int(out[7]),
-                    encodings=dict(zip(("S32", "S16", "D32", "D16", "D8"), out[1:6].tolist())))
+        return dict(stream_bytes=int(out[0] + out[13]), chunk_bytes=int(out[0]),
+                    tile_bytes=int(out[13]), chunks=int(out[7]), csr_bytes=int(out[8]),
+                    tile_cells=int(out[9]), tile_cells_padded=int(out[10]),
+                    tile_units=int(out[11]), overflow_cells=int(out[12]),
+                    encodings=dict(zip(("S32", "S16", "D32", "D16", "D8", "T"),
+                                       out[1:7].tolist())))
 
     def export_upper(self):
         """Owned upper-triangle cells, row-major sorted: (rows, cols, vals) int32."""
