@@ -239,6 +239,10 @@ def main():
     # rank walks info["nnz_full"] of the nnz_full directed cells, i.e. that share of the contacts
     alg_bytes = 12.0 * nnz_upper * info["nnz_full"] / max(nnz_full, 1) + 24.0 * (block[1] - block[0])
     k1_ms = rowsum_ms / max(rowsum_n, 1)
+    rank_k1 = [k1_ms]
+    if world > 1:                          # every rank's mean K1 time: shows the shard balance
+        rank_k1 = [None] * world
+        dist.all_gather_object(rank_k1, k1_ms)
     achieved = alg_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0
     lay = store.layout()
     csr_walk = os.environ.get("TB_ROWSUM") == "csr"
@@ -264,7 +268,8 @@ def main():
                        "sharding": "rows, nnz-balanced, 1 NCCL all-reduce/pass" if world > 1 else "single GPU",
                        "build_s": t_build},
             "wall_ms_per_step": wall_ms / args.steps,
-            "roofline": roofline, "gpu_launches": launches, "clocks": clocks}
+            "roofline": roofline, "rank_kernel_ms": rank_k1, "gpu_launches": launches,
+            "clocks": clocks}
 
     if rank == 0 and world == 1 and not args.no_e2e:
         cells = [torch.from_numpy(a).pin_memory() for a in store.export_upper()]

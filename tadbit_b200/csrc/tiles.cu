@@ -247,6 +247,7 @@ k_rowsum_tiles(const uint32_t *__restrict__ cells, const int64_t *__restrict__ t
   for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
     const int4 un = unit[u];
     const int i0 = un.y, n = un.z - un.y;
+    const int part = un.w >> 8, parts = un.w & 0xff;   // a heavy tile is split over several units
     acc[t] = 0.0;
     acc[t + kTileThreads] = 0.0;
     for (int j = 0; j < n; ++j) {
@@ -262,10 +263,14 @@ k_rowsum_tiles(const uint32_t *__restrict__ cells, const int64_t *__restrict__ t
       // metadata and the first cells do not depend on the window: fetch them while it lands
       const uint32_t *st = slice + tile * kSliceTab;
       const uint32_t a0 = st[sa], a1 = st[sa + 1], b0 = st[sb], b1 = st[sb + 1];
-      const int len_a = (int)((a1 - a0) >> 5), len_b = (int)((b1 - b0) >> 5);
+      const int full_a = (int)((a1 - a0) >> 5), full_b = (int)((b1 - b0) >> 5);
+      // this unit's share of every slice: cells [len*part/parts, len*(part+1)/parts)
+      const int ka = full_a * part / parts, kb = full_b * part / parts;
+      const int len_a = full_a * (part + 1) / parts - ka, len_b = full_b * (part + 1) / parts - kb;
       const int row_a = perm[tile * kTileRows + sa * 32 + lane];
       const int row_b = perm[tile * kTileRows + sb * 32 + lane];
-      const uint32_t *pa = cells + t_off[tile] + a0 + lane, *pb = cells + t_off[tile] + b0 + lane;
+      const uint32_t *pa = cells + t_off[tile] + a0 + ka * 32 + lane;
+      const uint32_t *pb = cells + t_off[tile] + b0 + kb * 32 + lane;
       uint32_t c[16];
       if (len_a >= 16) {
 #pragma unroll
@@ -351,25 +356,38 @@ void build_tiles(tb_store *s) {
                                   s->t_cells.p);
   // Work units: each row block's non-empty tiles, cut into runs of about equal stored cells so
   // that there are ~16 units per SM whatever the number of row blocks (1 GPU or a 1/8 shard).
+  // A tile heavier than that (the ones on the diagonal) is split: `parts` units each take a
+  // share of every slice of the tile.  unit = (row block, list begin, list end, part<<8|parts).
   const double target = (double)s->t_npadded / (16.0 * s->sm_count) + 1.0;
   std::vector<int32_t> list, units, unit_of_rb(nrb + 1, 0);
   for (int64_t rb = 0; rb < nrb; ++rb) {
     unit_of_rb[rb] = (int32_t)(units.size() / 4);
     int64_t run = 0;
     int32_t begin = (int32_t)list.size();
+    auto flush = [&]() {
+      if ((int32_t)list.size() > begin)
+        units.insert(units.end(), {(int32_t)rb, begin, (int32_t)list.size(), 1});
+      begin = (int32_t)list.size();
+      run = 0;
+    };
     for (int64_t w = 0; w < nwin; ++w) {
       const int64_t sz = h_size[rb * nwin + w];
       if (!sz) continue;
+      if ((double)sz > 1.5 * target) {
+        flush();
+        int parts = (int)((double)sz / target + 0.999);
+        if (parts > 64) parts = 64;
+        list.push_back((int32_t)(rb * nwin + w));
+        for (int p = 0; p < parts; ++p)
+          units.insert(units.end(), {(int32_t)rb, begin, begin + 1, (p << 8) | parts});
+        begin = (int32_t)list.size();
+        continue;
+      }
       list.push_back((int32_t)(rb * nwin + w));
       run += sz;
-      if ((double)run >= target) {
-        units.insert(units.end(), {(int32_t)rb, begin, (int32_t)list.size(), 0});
-        begin = (int32_t)list.size();
-        run = 0;
-      }
+      if ((double)run >= target) flush();
     }
-    if ((int32_t)list.size() > begin)
-      units.insert(units.end(), {(int32_t)rb, begin, (int32_t)list.size(), 0});
+    flush();
   }
   unit_of_rb[nrb] = (int32_t)(units.size() / 4);
   s->t_nunits = (int64_t)units.size() / 4;

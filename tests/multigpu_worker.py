@@ -71,8 +71,9 @@ def main():
             "row nnz": np.array_equal(n1, nnz), "row sums": np.array_equal(s1, rsum),
             "bads": ref.bads == hic.bads, "raw sum": ref.sum() == raw,
             "passes": len(ref.last_trace) == len(hic.last_trace),
-            # ICE itself: same chunk partials, same order, all-reduce adds zeros -> same bits
-            "ICE bias bit-identical": np.array_equal(ref_raw, raw_bias),
+            # ICE itself: every rank holds identical bits (checked above); against ONE GPU the
+            # sparse tiles of a shard are cut differently, so the summation order differs
+            "ICE bias 1e-13": np.allclose(ref_raw, raw_bias, rtol=1e-13, atol=0),
             # factor step sums per-rank partial dot products: 1e-13 relative
             "rescaled bias 1e-13": np.allclose(ref.bias.to_array(), hic.bias.to_array(),
                                                rtol=1e-13, atol=0),
