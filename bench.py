@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--workload", default="auto")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-bins", type=int, default=6144,
+    ap.add_argument("--cpu-bins", type=int, default=32768,
                     help="bins of the leading sub-matrix used for the CPU baseline sample")
     return ap.parse_args()
 
@@ -247,10 +247,20 @@ def main():
     lay = store.layout()
     csr_walk = os.environ.get("TB_ROWSUM") == "csr"
     layout_bytes = 8.0 * info["nnz_full"] if csr_walk else float(lay["stream_bytes"])
+    traffic = None                       # ncu dram bytes of one K1 evaluation (1 GPU capture)
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(wl["name"])
+        if rec and world == 1 and not csr_walk:
+            traffic = rec["k1_dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "note": "achieved = SURVEY 8d algorithmic bytes (12 B/contact + 24 B/bin) / K1 time; "
+                        "the compact stream moves layout_bytes_per_launch (< algorithmic), so frac "
+                        "can exceed the fraction of HBM peak actually drawn (layout_gbs / peak)",
                 "kernel": "k_chunk_reduce<F64> (CSR walk)" if csr_walk else
-                          "k_rowsum_tiles + k_rowsum_dense (+ k_rowsum_sparse) = K1 over the compact stream",
+                          "K1 row sum = k_rowsum_tiles + k_rowsum_dense (2 launches per pass, timed together)",
                 "kernel_ms": k1_ms, "stream_encodings": lay["encodings"],
                 "tile_cells": lay["tile_cells"], "tile_cells_padded": lay["tile_cells_padded"],
                 "kernel_share_of_step": rowsum_ms / dev_ms if dev_ms else None,

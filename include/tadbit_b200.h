@@ -161,6 +161,23 @@ int tb_col_sums_masked(tb_store *s, const uint8_t *h_bad, int64_t *h_col_sum);
 int tb_ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev,
            double *h_bias, double *h_trace, int32_t *n_passes);
 
+/*
+ * Batch mode (BASELINE configs[4]: many experiments normalised at once on one GPU).
+ * tb_store_create_batch concatenates n whole stores of one device into a block-diagonal store
+ * whose section k is member k (device-to-device; the members stay valid and independent).
+ * tb_ice_batch runs iterative() on every SECTION independently -- own present rows, meanS,
+ * deviation test and stop pass; a converged section is frozen while the others continue.
+ * In the reference this is a Python loop over experiments (Experiment.normalize_hic,
+ * _pytadbit/experiment.py:704-748 -> _pytadbit/utils/normalize_hic.py:180-231).
+ *   h_bias   float64[N] of the batch store (sections concatenated)
+ *   h_trace  float64[n_sections][iterations+1][4] or NULL
+ *   n_passes int32[n_sections]; -1 where no row is present (the reference raises
+ *            ZeroDivisionError for that experiment; its biases are left at 1.0)
+ */
+int tb_store_create_batch(int32_t n, tb_store *const *members, int device, tb_store **out);
+int tb_ice_batch(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev,
+                 double *h_bias, double *h_trace, int32_t *n_passes);
+
 /* timing of the last tb_ice call, measured with CUDA events on the store's stream:
  * total device ms of the pass loop, and the ms spent in the row-sum (K1) launches */
 int tb_ice_last_timing(const tb_store *s, double *loop_ms, double *rowsum_ms,

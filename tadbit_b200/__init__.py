@@ -6,6 +6,7 @@ sums) is a hand-written sm_100a CUDA kernel behind the C-ABI of include/tadbit_b
 There is no CPU fallback.
 """
 from ._capi import B200Error, SynthParams, device_count
+from .batch import batch_store, ice_batch, normalize_hic_batch
 from .hic_data import HiC_data, from_reference
 from .hic_filtering import filter_by_mean, filter_by_zero_count
 from .normalize_hic import expected, iterative
@@ -15,4 +16,4 @@ from .vectors import BinVector
 __version__ = "0.1.0"
 __all__ = ["HiC_data", "from_reference", "ContactStore", "SynthParams", "BinVector",
            "iterative", "expected", "filter_by_mean", "filter_by_zero_count",
-           "device_count", "B200Error"]
+           "device_count", "B200Error", "normalize_hic_batch", "batch_store", "ice_batch"]

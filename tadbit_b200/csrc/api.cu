@@ -174,6 +174,45 @@ int tb_synthetic_row_counts(int64_t nbins, int32_t n_chrom, const int64_t *chrom
   });
 }
 
+int tb_store_create_batch(int32_t n, tb_store *const *members, int device, tb_store **out) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(out && members && n > 0, "bad arguments");
+    *out = nullptr;
+    std::vector<int64_t> offs(1, 0);
+    for (int32_t k = 0; k < n; ++k) {
+      const tb_store *m = members[k];
+      TB_REQUIRE(m, "null member store");
+      TB_REQUIRE(m->device == device, "batch members must live on the batch's device");
+      TB_REQUIRE(m->row_begin == 0 && m->row_end == m->nbins && m->world == 1,
+                 "batch members must be whole (unsharded) matrices");
+      offs.push_back(offs.back() + m->nbins);
+    }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    tb_store *s = new_store(offs.back(), n, offs.data(), 0, offs.back(), device);
+    try {
+      build_batch(s, n, members);
+    } catch (...) {
+      tb_store_destroy(s);
+      cudaSetDevice(prev);
+      throw;
+    }
+    cudaSetDevice(prev);
+    *out = s;
+    return TB_OK;
+  });
+}
+
+int tb_ice_batch(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev,
+                 double *h_bias, double *h_trace, int32_t *n_passes) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(s && h_bias && n_passes, "null argument");
+    DeviceGuard g(s->device);
+    ice_batch(s, h_bad, iterations, max_dev, h_bias, h_trace, n_passes);
+    return TB_OK;
+  });
+}
+
 int tb_store_destroy(tb_store *s) {
   if (!s) return TB_OK;
   int prev = 0;

@@ -338,6 +338,53 @@ void finish_layout(tb_store *s) {
                     s->bad.bytes() + s->present.bytes() + s->chrom_of.bytes();
 }
 
+namespace {
+__global__ void k_copy_rowptr(const int64_t *__restrict__ src, int64_t nrows, int64_t cell_off,
+                              int64_t *__restrict__ dst) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
+       r += (int64_t)gridDim.x * blockDim.x)
+    dst[r] = src[r] + cell_off;
+}
+__global__ void k_copy_cells(const int32_t *__restrict__ scol, const int32_t *__restrict__ sval,
+                             int64_t n, int32_t col_off, int32_t *__restrict__ dcol,
+                             int32_t *__restrict__ dval) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    dcol[k] = scol[k] + col_off;
+    dval[k] = sval[k];
+  }
+}
+}  // namespace
+
+// Block-diagonal concatenation of whole (unsharded) stores on the same device: member k
+// becomes section k.  Device-to-device, no host traffic.
+void build_batch(tb_store *s, int32_t n, tb_store *const *members) {
+  cudaStream_t st = s->stream;
+  const int threads = 256;
+  int64_t cells = 0;
+  for (int32_t k = 0; k < n; ++k) cells += members[k]->nnz_full;
+  s->nnz_full = cells;
+  s->rowptr.alloc(s->nrows + 1);
+  s->col.alloc(cells ? cells : 1);
+  s->val.alloc(cells ? cells : 1);
+  int64_t row_off = 0, cell_off = 0;
+  for (int32_t k = 0; k < n; ++k) {
+    const tb_store *m = members[k];
+    TB_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->nrows)
+      k_copy_rowptr<<<grid_for(m->nrows, threads, s->sm_count), threads, 0, st>>>(
+          m->rowptr.p, m->nrows, cell_off, s->rowptr.p + row_off);
+    if (m->nnz_full)
+      k_copy_cells<<<grid_for(m->nnz_full, threads, s->sm_count), threads, 0, st>>>(
+          m->col.p, m->val.p, m->nnz_full, (int32_t)row_off, s->col.p + cell_off, s->val.p + cell_off);
+    row_off += m->nrows;
+    cell_off += m->nnz_full;
+  }
+  TB_CUDA(cudaMemcpyAsync(s->rowptr.p + s->nrows, &s->nnz_full, sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  finish_layout(s);
+}
+
 void setup_sections(tb_store *s) {
   const int64_t N = s->nbins;
   std::vector<int32_t> h(N ? N : 1);

@@ -180,6 +180,7 @@ void build_from_coo(tb_store *s, int64_t nnz, const int32_t *row, const int32_t 
 void setup_sections(tb_store *s);   // bin -> section id table (before any build)
 void finish_layout(tb_store *s);     // chunks + scratch once rowptr/col/val are in place
 void export_upper(const tb_store *s, int64_t *nnz, int32_t *h_row, int32_t *h_col, int32_t *h_val);
+void build_batch(tb_store *s, int32_t n, tb_store *const *members);   // block-diagonal concatenation
 // encode.cu
 void build_encoded(tb_store *s);     // compact row-sum stream from the CSR
 // rowsum.cu
@@ -198,6 +199,8 @@ void col_sums_masked(tb_store *s, const uint8_t *h_bad, int64_t *h_col_sum);
 int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, double *h_bias,
         double *h_trace, int32_t *n_passes);
 void norm_sum(tb_store *s, const double *h_bias, const uint8_t *h_bad, double *out);
+void ice_batch(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, double *h_bias,
+               double *h_trace, int32_t *n_passes);
 void diag_sums(tb_store *s, const uint8_t *h_bad, int64_t ndiag, int64_t *h_sum_d);
 // comm.cu
 void comm_unique_id(uint8_t id[128]);

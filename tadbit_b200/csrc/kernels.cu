@@ -420,6 +420,124 @@ void launch_chunks(tb_store *s, const double *x, const uint8_t *bad, const IceSt
       s->partial_f.p, s->partial_i.p, state);
 }
 
+// ---------------------------------------------------------------------------------
+// Batch ICE: every section of the store is an independent matrix (block-diagonal store made
+// by tb_store_create_batch).  K1 is unchanged -- rows are rows -- but the statistics, the
+// stop decision and the bias update are per section, and a section that has converged is
+// frozen while the others go on (BASELINE configs[4]: many experiments normalised at once).
+// ---------------------------------------------------------------------------------
+struct SegState {
+  double mean_s, dev;
+  long long n_present;
+  int passes_done;      // passes whose statistics were finalised for this section
+  int stopped, all_bad, pad;
+};
+
+__global__ void k_seg_init(SegState *seg, int nseg, unsigned int *n_stopped) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nseg; k += gridDim.x * blockDim.x) {
+    seg[k].mean_s = seg[k].dev = 0.0;
+    seg[k].n_present = 0;
+    seg[k].passes_done = seg[k].stopped = seg[k].all_bad = 0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *n_stopped = 0;
+}
+
+// one CTA per section: combine the chunk partials of its rows, S = x*s, sum/min/max, decision
+__global__ void __launch_bounds__(1024)
+k_seg_reduce(double *__restrict__ s_full, const double *__restrict__ x,
+             const uint8_t *__restrict__ bad, uint8_t *__restrict__ present,
+             const int64_t *__restrict__ seg_off, int nseg, int pass, int iterations, double max_dev,
+             double *__restrict__ trace, int npass_max, SegState *seg, unsigned int *n_stopped,
+             IceState *state, const double *__restrict__ pf, const long long *__restrict__ pc,
+             const int64_t *__restrict__ row_chunk, TileSums ts) {
+  const int k = blockIdx.x;
+  if (seg[k].stopped) return;
+  __shared__ double sh_sum[32], sh_min[32], sh_max[32];
+  __shared__ long long sh_cnt[32];
+  double sum = 0.0, mn = INFINITY, mx = -INFINITY;
+  long long cnt = 0;
+  for (int64_t i = seg_off[k] + threadIdx.x; i < seg_off[k + 1]; i += blockDim.x) {
+    double a = 0.0;
+    long long nc = 0;
+    for (int64_t c = row_chunk[i]; c < row_chunk[i + 1]; ++c) {
+      a += pf[c];
+      if (pass == 0) nc += pc[c];
+    }
+    if (pass != 0) a += tile_sum(ts, i);
+    s_full[i] = a;
+    bool p;
+    if (pass == 0) present[i] = p = !bad[i] && nc > 0;
+    else p = present[i];
+    if (p) {
+      const double S = x[i] * a;
+      sum += S; mn = fmin(mn, S); mx = fmax(mx, S); ++cnt;
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh_sum[w] = sum; sh_min[w] = mn; sh_max[w] = mx; sh_cnt[w] = cnt; }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  for (int q = 1; q < (int)(blockDim.x >> 5); ++q) {
+    sum += sh_sum[q]; mn = fmin(mn, sh_min[q]); mx = fmax(mx, sh_max[q]); cnt += sh_cnt[q];
+  }
+  SegState &g = seg[k];
+  if (pass == 0) g.n_present = cnt;
+  bool stop = false;
+  if (g.n_present == 0) {
+    g.all_bad = 1;
+    stop = true;
+  } else {
+    const double mean = sum / (double)g.n_present;
+    g.mean_s = mean;
+    g.passes_done = pass + 1;
+    if (iterations == 0) {
+      stop = true;
+    } else {
+      const double dev = fmax(fabs(mn / mean - 1.0), fabs(mx / mean - 1.0));
+      g.dev = dev;
+      double *t = trace + ((int64_t)k * npass_max + pass) * 4;
+      t[0] = mn; t[1] = mean; t[2] = mx; t[3] = dev;
+      stop = dev < max_dev;
+    }
+  }
+  if (stop) {
+    g.stopped = 1;
+    if (atomicAdd(n_stopped, 1u) + 1u == (unsigned)nseg) state->stopped = 1;
+  }
+}
+
+__global__ void k_seg_update(const double *__restrict__ s_full, double *__restrict__ x,
+                             double *__restrict__ b, const uint8_t *__restrict__ present,
+                             const int32_t *__restrict__ seg_of, int64_t n, int pass,
+                             const SegState *__restrict__ seg) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const SegState g = seg[seg_of[i]];
+    if (g.passes_done != pass + 1 || g.all_bad) continue;     // frozen or failed section
+    if (!present[i]) { x[i] = 0.0; continue; }
+    const double bi = b[i] * ((x[i] * s_full[i]) / g.mean_s);
+    b[i] = bi;
+    x[i] = (bi != 0.0) ? 1.0 / bi : 0.0;
+  }
+}
+
+__global__ void k_seg_finalize(const double *__restrict__ b, const uint8_t *__restrict__ present,
+                               const int32_t *__restrict__ seg_of, int64_t n,
+                               const SegState *__restrict__ seg, double *__restrict__ bias) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const SegState g = seg[seg_of[i]];
+    const double bi = b[i];
+    bias[i] = (!g.all_bad && present[i] && bi != 0.0) ? bi * sqrt(g.mean_s) : 1.0;
+  }
+}
+
 bool use_csr_rowsum() {       // TB_ROWSUM=csr: A/B switch back to the uncompressed CSR walk
   static int v = -1;
   if (v < 0) {
@@ -636,6 +754,74 @@ void diag_sums(tb_store *s, const uint8_t *h_bad, int64_t ndiag, int64_t *h_sum_
   }
   TB_CUDA(cudaMemcpyAsync(h_sum_d, src, ndiag * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaStreamSynchronize(st));
+}
+
+void ice_batch(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, double *h_bias,
+               double *h_trace, int32_t *n_passes) {
+  cudaStream_t st = s->stream;
+  const int64_t N = s->nbins;
+  TB_REQUIRE(iterations >= 0, "ice_batch: iterations must be >= 0");
+  TB_REQUIRE(s->world == 1, "ice_batch: batches are not sharded (one replica per GPU)");
+  const int nseg = (int)s->chrom_offsets.size() - 1;
+  const int npass_max = iterations + 1;
+  DevBuf<SegState> seg;
+  DevBuf<unsigned int> n_stopped;
+  DevBuf<int64_t> seg_off;
+  DevBuf<double> trace;
+  seg.alloc(nseg);
+  n_stopped.alloc(1);
+  seg_off.alloc(nseg + 1);
+  trace.alloc((size_t)nseg * npass_max * 4);
+  TB_CUDA(cudaMemcpyAsync(seg_off.p, s->chrom_offsets.data(), (nseg + 1) * sizeof(int64_t),
+                          cudaMemcpyHostToDevice, st));
+  TB_CUDA(cudaMemsetAsync(trace.p, 0, trace.bytes(), st));
+  upload_bad(s, h_bad);
+  const int vg = grid_1d(N, 256, s->sm_count);
+  k_ice_init<<<vg, 256, 0, st>>>(s->bad.p, N, s->x.p, s->b.p, s->state.p);
+  k_seg_init<<<(nseg + 255) / 256, 256, 0, st>>>(seg.p, nseg, n_stopped.p);
+  const bool csr_walk = use_csr_rowsum();
+  const TileSums ts = {(!csr_walk && s->t_nunits) ? s->t_partial.p : nullptr, s->t_unit_of_rb.p};
+  cudaEvent_t e0, e1;
+  TB_CUDA(cudaEventCreate(&e0));
+  TB_CUDA(cudaEventCreate(&e1));
+  TB_CUDA(cudaEventRecord(e0, st));
+  bool stopped = false;
+  int launched = 0;
+  for (int p = 0; p < npass_max && !stopped; ++p) {
+    if (p == 0) launch_chunks<M_F64_COUNT>(s, s->x.p, nullptr, s->state.p);
+    else if (csr_walk) launch_chunks<M_F64>(s, s->x.p, nullptr, s->state.p);
+    else launch_rowsum(s, s->x.p, s->state.p);
+    k_seg_reduce<<<nseg, 1024, 0, st>>>(s->s_full.p, s->x.p, s->bad.p, s->present.p, seg_off.p, nseg,
+                                        p, iterations, max_dev, trace.p, npass_max, seg.p,
+                                        n_stopped.p, s->state.p, s->partial_f.p, s->partial_i.p,
+                                        s->row_chunk.p, ts);
+    k_seg_update<<<vg, 256, 0, st>>>(s->s_full.p, s->x.p, s->b.p, s->present.p, s->chrom_of.p, N, p,
+                                     seg.p);
+    if (p == 0 && ts.partial) TB_CUDA(cudaMemsetAsync(s->partial_f.p, 0, s->partial_f.bytes(), st));
+    ++launched;
+    if ((p + 1) % 4 == 0 || p == npass_max - 1 || iterations == 0) {
+      TB_CUDA(cudaMemcpyAsync(s->h_state.p, s->state.p, sizeof(IceState), cudaMemcpyDeviceToHost, st));
+      TB_CUDA(cudaStreamSynchronize(st));
+      stopped = s->h_state.p->stopped != 0;
+    }
+  }
+  TB_CUDA(cudaEventRecord(e1, st));
+  k_seg_finalize<<<vg, 256, 0, st>>>(s->b.p, s->present.p, s->chrom_of.p, N, seg.p, s->x.p);
+  std::vector<SegState> hseg(nseg);
+  TB_CUDA(cudaMemcpyAsync(h_bias, s->x.p, N * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaMemcpyAsync(hseg.data(), seg.p, nseg * sizeof(SegState), cudaMemcpyDeviceToHost, st));
+  if (h_trace && iterations > 0)
+    TB_CUDA(cudaMemcpyAsync(h_trace, trace.p, trace.bytes(), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  for (int k = 0; k < nseg; ++k) n_passes[k] = hseg[k].all_bad ? -1 : hseg[k].passes_done;
+  float ms = 0.f;
+  TB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  s->loop_ms = ms;
+  s->rowsum_ms = 0;
+  s->rowsum_launches = 0;
+  s->total_launches = launched * 4 + 3;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
 }
 
 }  // namespace tb
