@@ -55,6 +55,9 @@ enum { TB_MEM_HOST = 0, TB_MEM_DEVICE = 1 };
 int tb_version(void);
 const char *tb_last_error(void);
 int tb_device_count(int *count);
+/* Device memory is cached in the device's stream-ordered pool between stores (building a
+ * store needs tens of GB of scratch); this returns the cached memory to the driver. */
+int tb_trim_memory(int device);
 
 /* ---- store construction -------------------------------------------------------- */
 /*

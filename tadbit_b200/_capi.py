@@ -37,6 +37,7 @@ PROTOTYPES = {
     "tb_version": ([], C.c_int),
     "tb_last_error": ([], C.c_char_p),
     "tb_device_count": ([C.POINTER(C.c_int)], C.c_int),
+    "tb_trim_memory": ([C.c_int], C.c_int),
     "tb_store_create_coo": ([C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                              C.c_int32, _i64p, C.c_int64, C.c_int64, C.c_int,
                              C.POINTER(_store)], C.c_int),
@@ -97,6 +98,11 @@ def device_count():
     n = C.c_int(0)
     st = lib().tb_device_count(C.byref(n))
     return n.value if st == TB_OK else 0
+
+
+def trim_memory(device=0):
+    """Return the device memory cached by the library's allocation pool to the driver."""
+    check(lib().tb_trim_memory(device))
 
 
 def ptr(arr, ctype):

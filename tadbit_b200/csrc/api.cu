@@ -1,6 +1,7 @@
 // C-ABI of include/tadbit_b200.h: argument checks, exception -> status mapping.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <new>
 
@@ -15,6 +16,58 @@ void set_error(const char *fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_error, sizeof(g_error), fmt, ap);
   va_end(ap);
+}
+
+namespace {
+struct PoolState {
+  bool ready = false, enabled = true;
+  cudaStream_t stream = nullptr;
+};
+PoolState g_pool[64];
+
+PoolState &pool_for_current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  PoolState &ps = g_pool[dev & 63];
+  if (!ps.ready) {
+    const char *e = getenv("TB_POOL");
+    ps.enabled = !(e && e[0] == '0');
+    if (ps.enabled) {
+      cudaMemPool_t pool;
+      uint64_t keep = UINT64_MAX;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess ||
+          cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess ||
+          cudaStreamCreateWithFlags(&ps.stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        ps.enabled = false;
+      }
+    }
+    ps.ready = true;
+  }
+  return ps;
+}
+}  // namespace
+
+void *dev_malloc(size_t bytes) {
+  PoolState &ps = pool_for_current_device();
+  void *p = nullptr;
+  if (ps.enabled) {
+    TB_CUDA(cudaMallocAsync(&p, bytes, ps.stream));
+    TB_CUDA(cudaStreamSynchronize(ps.stream));       // usable from any stream afterwards
+  } else {
+    TB_CUDA(cudaMalloc(&p, bytes));
+  }
+  return p;
+}
+
+void dev_free(void *p) {
+  PoolState &ps = pool_for_current_device();
+  if (ps.enabled) {
+    cudaDeviceSynchronize();                         // same guarantee as cudaFree: no user left
+    cudaFreeAsync(p, ps.stream);
+  } else {
+    cudaFree(p);
+  }
 }
 
 namespace {
@@ -53,9 +106,7 @@ tb_store *new_store(int64_t nbins, int32_t n_chrom, const int64_t *chrom_offsets
   tb_store *s = new tb_store();
   try {
     s->device = device;
-    cudaDeviceProp prop;
-    TB_CUDA(cudaGetDeviceProperties(&prop, device));
-    s->sm_count = prop.multiProcessorCount;
+    TB_CUDA(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device));
     TB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     s->nbins = nbins;
     s->row_begin = row_begin;
@@ -99,6 +150,17 @@ extern "C" {
 int tb_version(void) { return 100; }
 
 const char *tb_last_error(void) { return g_error; }
+
+int tb_trim_memory(int device) {
+  int prev = 0;
+  cudaGetDevice(&prev);
+  if (cudaSetDevice(device) != cudaSuccess) { set_error("bad device"); return TB_ERR_ARG; }
+  cudaDeviceSynchronize();
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+  cudaSetDevice(prev);
+  return TB_OK;
+}
 
 int tb_device_count(int *count) {
   if (!count) return TB_ERR_ARG;

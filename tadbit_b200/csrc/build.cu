@@ -6,6 +6,10 @@
 // mirrored cells turns all of them into gather-only, atomic-free, deterministic row
 // reductions of one stream; the reference's dict holds both triangles too
 // (_pytadbit/hic_data.py:54-118).
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <chrono>
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -203,9 +207,31 @@ void exclusive_scan_i64(cudaStream_t st, const int64_t *in, int64_t *out, int64_
 
 }  // namespace
 
+namespace {
+struct StageTimer {            // TB_TIMING=1: wall time of the build stages on stderr
+  bool on;
+  cudaStream_t st;
+  std::chrono::steady_clock::time_point t0;
+  explicit StageTimer(cudaStream_t s) : st(s) {
+    const char *e = getenv("TB_TIMING");
+    on = e && e[0] == '1';
+    t0 = std::chrono::steady_clock::now();
+  }
+  void lap(const char *what) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[tadbit_b200] %-28s %8.1f ms\n", what,
+            std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+}  // namespace
+
 void build_from_coo(tb_store *s, int64_t nnz, const int32_t *row, const int32_t *col,
                     const int32_t *val, int mem) {
   cudaStream_t st = s->stream;
+  StageTimer tm(st);
   DevBuf<int32_t> drow, dcol, dval;
   const int32_t *r = row, *c = col, *v = val;
   if (mem == TB_MEM_HOST && nnz) {
@@ -215,6 +241,7 @@ void build_from_coo(tb_store *s, int64_t nnz, const int32_t *row, const int32_t 
     TB_CUDA(cudaMemcpyAsync(dval.p, val, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     r = drow.p; c = dcol.p; v = dval.p;
   }
+  tm.lap("H2D cells");
   DevBuf<unsigned long long> counters;   // [0] directed cells, [1] emit cursor
   DevBuf<int> flags;                     // [0] bad input, [1] duplicate
   counters.alloc(2);
@@ -265,11 +292,15 @@ void build_from_coo(tb_store *s, int64_t nnz, const int32_t *row, const int32_t 
     TB_CUDA(cudaStreamSynchronize(st));
     TB_REQUIRE(!h_flags[1], "contact store: duplicate cells (each upper-triangle cell must appear once)");
   }
+  tm.lap("mirror + sort + split");
+  drow.release(); dcol.release(); dval.release(); counters.release(); flags.release();
+  tm.lap("free input copies");
   finish_layout(s);
 }
 
 void finish_layout(tb_store *s) {
   cudaStream_t st = s->stream;
+  StageTimer tm(st);
   const int threads = 256;
   const int64_t nrows = s->nrows, N = s->nbins;
   // chunks
@@ -328,8 +359,11 @@ void finish_layout(tb_store *s) {
   TB_CUDA(cudaMemsetAsync(s->s_part.p, 0, s->s_part.bytes(), st));
   TB_CUDA(cudaMemsetAsync(s->i_part.p, 0, s->i_part.bytes(), st));
   TB_CUDA(cudaStreamSynchronize(st));
+  tm.lap("chunks + scratch");
   build_encoded(s);
+  tm.lap("encode dense stream");
   build_tiles(s);
+  tm.lap("sparse tiles");
   s->device_bytes = s->t_cells.bytes() + s->t_perm.bytes() + s->t_slice.bytes() + s->t_off.bytes() +
                     s->t_partial.bytes() + s->enc_data.bytes() + s->enc_off.bytes() + s->enc_desc.bytes() + s->rowptr.bytes() + s->col.bytes() + s->val.bytes() + s->chunk_beg.bytes() +
                     s->chunk_row.bytes() + s->row_chunk.bytes() + s->partial_f.bytes() +

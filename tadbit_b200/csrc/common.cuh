@@ -33,6 +33,13 @@ struct Fail {           // thrown inside the library, mapped to a tb_status at t
     }                                                                                  \
   } while (0)
 
+// Device memory comes from the device's stream-ordered pool with the release threshold
+// lifted (api.cu): building a store needs tens of GB of short-lived scratch, and handing
+// that back to the driver and mapping it again dominated repeated store creation.
+// tb_trim_memory() returns the cached memory.  TB_POOL=0 falls back to cudaMalloc/cudaFree.
+void *dev_malloc(size_t bytes);
+void dev_free(void *p);
+
 // Device allocation owned by a store; freed in its destructor.
 template <typename T>
 struct DevBuf {
@@ -45,10 +52,10 @@ struct DevBuf {
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) TB_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    if (count) p = static_cast<T *>(dev_malloc(count * sizeof(T)));
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) dev_free(p);
     p = nullptr;
     n = 0;
   }

@@ -183,8 +183,8 @@ void synthetic_row_counts(int64_t nbins, int32_t n_chrom, const int64_t *chrom_o
   TB_REQUIRE(nbins > 0 && rb >= 0 && re >= rb && re <= nbins && p && h_counts,
              "synthetic_row_counts: bad arguments");
   TB_CUDA(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  TB_CUDA(cudaGetDeviceProperties(&prop, device));
+  struct { int multiProcessorCount; } prop;
+  TB_CUDA(cudaDeviceGetAttribute(&prop.multiProcessorCount, cudaDevAttrMultiProcessorCount, device));
   std::vector<int64_t> offs;
   if (n_chrom > 0) offs.assign(chrom_offsets, chrom_offsets + n_chrom + 1);
   else offs = {0, nbins};
