@@ -113,6 +113,11 @@ int tb_store_destroy(tb_store *s);
 int tb_store_info(const tb_store *s, int64_t *nbins, int64_t *row_begin, int64_t *row_end,
                   int64_t *nnz_upper_owned, int64_t *nnz_full_owned, int64_t *device_bytes);
 
+/* Options of a store.  "rowsum" = "compact" (default) or "csr": which copy of the matrix the
+ * ICE passes walk -- the compact stream, or the plain CSR (two independent K1 implementations;
+ * the parity tests compare them at full size). */
+int tb_store_set_option(tb_store *s, const char *name, const char *value);
+
 /* Layout of the compact row-sum stream (tadbit_b200/csrc/encode.cu, tiles.cu):
  * out[0] chunk payload bytes, out[1..6] chunks encoded as S32, S16, D32, D16, D8, T (cells in
  * the sparse tiles), out[7] chunks, out[8] CSR bytes, out[9] cells in sparse tiles, out[10]

@@ -47,6 +47,7 @@ PROTOTYPES = {
                                  C.c_int64, C.c_int, _i64p], C.c_int),
     "tb_store_destroy": ([_store], C.c_int),
     "tb_store_info": ([_store, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p], C.c_int),
+    "tb_store_set_option": ([_store, C.c_char_p, C.c_char_p], C.c_int),
     "tb_store_layout": ([_store, _i64p], C.c_int),
     "tb_store_export_upper": ([_store, _i64p, _i32p, _i32p, _i32p], C.c_int),
     "tb_comm_unique_id": ([_u8p], C.c_int),

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <new>
 
@@ -303,6 +304,18 @@ int tb_store_info(const tb_store *s, int64_t *nbins, int64_t *row_begin, int64_t
   if (nnz_full_owned) *nnz_full_owned = s->nnz_full;
   if (device_bytes) *device_bytes = s->device_bytes;
   return TB_OK;
+}
+
+int tb_store_set_option(tb_store *s, const char *name, const char *value) {
+  if (!s || !name || !value) { set_error("null argument"); return TB_ERR_ARG; }
+  if (!strcmp(name, "rowsum")) {
+    if (!strcmp(value, "csr")) s->rowsum_mode = 1;
+    else if (!strcmp(value, "compact")) s->rowsum_mode = 0;
+    else { set_error("rowsum must be 'compact' or 'csr'"); return TB_ERR_ARG; }
+    return TB_OK;
+  }
+  set_error("unknown option %s", name);
+  return TB_ERR_ARG;
 }
 
 int tb_store_layout(const tb_store *s, int64_t out[16]) {

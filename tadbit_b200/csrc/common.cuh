@@ -178,6 +178,7 @@ struct tb_store {
   double loop_ms = 0, rowsum_ms = 0;
   int rowsum_launches = 0, total_launches = 0;
   int64_t device_bytes = 0;
+  int rowsum_mode = -1;     // -1 default (compact stream), 0 compact, 1 CSR walk (tb_store_set_option)
 };
 
 namespace tb {

@@ -538,7 +538,10 @@ __global__ void k_seg_finalize(const double *__restrict__ b, const uint8_t *__re
   }
 }
 
-bool use_csr_rowsum() {       // TB_ROWSUM=csr: A/B switch back to the uncompressed CSR walk
+// A/B switch: walk the uncompressed CSR in every pass instead of the compact stream.  Set per
+// store with tb_store_set_option("rowsum", "csr"); the environment TB_ROWSUM=csr sets the default.
+bool use_csr_rowsum(const tb_store *s) {
+  if (s->rowsum_mode >= 0) return s->rowsum_mode == 1;
   static int v = -1;
   if (v < 0) {
     const char *e = getenv("TB_ROWSUM");
@@ -600,7 +603,7 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
   std::vector<cudaEvent_t> ev(2 * (size_t)npass_max + 2);
   for (auto &e : ev) TB_CUDA(cudaEventCreate(&e));
   double *dst = s->world > 1 ? s->s_part.p : s->s_full.p;
-  const bool csr_walk = use_csr_rowsum();
+  const bool csr_walk = use_csr_rowsum(s);
   const TileSums ts = {(!csr_walk && s->t_nunits) ? s->t_partial.p : nullptr, s->t_unit_of_rb.p};
   // The host only needs to know WHEN the loop stopped: passes queued after the stop are no-ops
   // on the device.  ICE converges geometrically, so the next look is scheduled where the
@@ -616,7 +619,7 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
     // pass 0 also counts the cells that survive the mask (which rows are "present"), so it
     // walks the CSR; every later pass streams the compact encoding
     if (p == 0) launch_chunks<M_F64_COUNT>(s, s->x.p, nullptr, s->state.p);
-    else if (use_csr_rowsum()) launch_chunks<M_F64>(s, s->x.p, nullptr, s->state.p);
+    else if (use_csr_rowsum(s)) launch_chunks<M_F64>(s, s->x.p, nullptr, s->state.p);
     else launch_rowsum(s, s->x.p, s->state.p);
     TB_CUDA(cudaEventRecord(ev[2 * p + 1], st));
     if (s->world > 1) {
@@ -718,12 +721,18 @@ void norm_sum(tb_store *s, const double *h_bias, const uint8_t *h_bad, double *o
   // y = 1/bias on good bins, 0 on bad ones; sum = y . (W y)
   TB_CUDA(cudaMemcpyAsync(s->b.p, h_bias, N * sizeof(double), cudaMemcpyHostToDevice, st));
   k_inverse_bias<<<grid_1d(N, 256, s->sm_count), 256, 0, st>>>(s->b.p, s->bad.p, N, s->x.p);
-  if (use_csr_rowsum()) launch_chunks<M_F64>(s, s->x.p, nullptr, nullptr);
-  else launch_rowsum(s, s->x.p, nullptr);
+  if (use_csr_rowsum(s)) {
+    launch_chunks<M_F64>(s, s->x.p, nullptr, nullptr);
+  } else {
+    // chunks whose cells live in the sparse tiles are not written by the compact kernels: make
+    // sure no partial of an earlier CSR walk (pass 0, or the "csr" option) is left in them
+    if (s->t_nunits) TB_CUDA(cudaMemsetAsync(s->partial_f.p, 0, s->partial_f.bytes(), st));
+    launch_rowsum(s, s->x.p, nullptr);
+  }
   if (s->nrows)
     k_combine_f64<false><<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
         s->partial_f.p, s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, N, s->s_full.p,
-        nullptr, TileSums{(!use_csr_rowsum() && s->t_nunits) ? s->t_partial.p : nullptr,
+        nullptr, TileSums{(!use_csr_rowsum(s) && s->t_nunits) ? s->t_partial.p : nullptr,
                           s->t_unit_of_rb.p});
   k_dot_rows<<<1, 1024, 0, st>>>(s->x.p, s->s_full.p, s->row_begin, s->row_end, s->scal_f.p);
   if (s->world > 1) allreduce_f64(s, s->scal_f.p, s->scal_f.p + 8, 1);
@@ -779,7 +788,7 @@ void ice_batch(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max
   const int vg = grid_1d(N, 256, s->sm_count);
   k_ice_init<<<vg, 256, 0, st>>>(s->bad.p, N, s->x.p, s->b.p, s->state.p);
   k_seg_init<<<(nseg + 255) / 256, 256, 0, st>>>(seg.p, nseg, n_stopped.p);
-  const bool csr_walk = use_csr_rowsum();
+  const bool csr_walk = use_csr_rowsum(s);
   const TileSums ts = {(!csr_walk && s->t_nunits) ? s->t_partial.p : nullptr, s->t_unit_of_rb.p};
   cudaEvent_t e0, e1;
   TB_CUDA(cudaEventCreate(&e0));

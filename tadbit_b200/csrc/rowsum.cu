@@ -304,11 +304,11 @@ k_rowsum_sparse(const uint8_t *__restrict__ data, const int64_t *__restrict__ of
 void launch_rowsum(tb_store *s, const double *x, const IceState *state) {
   launch_rowsum_tiles(s, x, state);
   if (s->n_groups) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};          // per device: the attribute is per context
+    if (!attr_set[s->device & 63]) {
       TB_CUDA(cudaFuncSetAttribute(k_rowsum_dense, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    kDenseSmem));
-      attr_set = true;
+      attr_set[s->device & 63] = true;
     }
     int64_t need = (s->n_groups + kDenseWarps - 1) / kDenseWarps;
     const int grid = (int)(need < s->sm_count ? need : s->sm_count);

@@ -407,10 +407,10 @@ void build_tiles(tb_store *s) {
 
 void launch_rowsum_tiles(tb_store *s, const double *x, const IceState *state) {
   if (s->t_nunits == 0) return;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};            // per device: the attribute is per context
+  if (!attr_set[s->device & 63]) {
     TB_CUDA(cudaFuncSetAttribute(k_rowsum_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
-    attr_set = true;
+    attr_set[s->device & 63] = true;
   }
   const int grid = (int)(s->t_nunits < s->sm_count ? s->t_nunits : s->sm_count);
   k_rowsum_tiles<<<grid, kTileThreads, kTileSmem, s->stream>>>(

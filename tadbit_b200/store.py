@@ -95,6 +95,10 @@ class ContactStore(object):
         keys = ("nbins", "row_begin", "row_end", "nnz_upper", "nnz_full", "device_bytes")
         return dict(zip(keys, [x.value for x in v]))
 
+    def set_option(self, name, value):
+        """e.g. ``set_option("rowsum", "csr")``: ICE passes walk the plain CSR, not the compact stream."""
+        check(lib().tb_store_set_option(self._h, name.encode(), value.encode()))
+
     def layout(self):
         """Compact row-sum stream: payload bytes and chunks per encoding."""
         out = np.zeros(16, dtype=np.int64)
