@@ -113,13 +113,14 @@ __device__ __forceinline__ int64_t lower_bound_col(const int32_t *__restrict__ c
 }
 
 // Split every row into chunks (the warp work items).  Columns are cut at multiples of kPanel:
-// a panel holding >= 1/4 of its columns becomes one chunk on its own (a candidate for the
+// a panel holding >= 1/dense_fill of its columns becomes one chunk on its own (a candidate for the
 // dense encodings, and aligned with the same panel of every other row so that several rows
 // can share one pass over x); runs of emptier panels are merged up to kChunk cells.
 // FILL == false counts the chunks of each row, FILL == true writes them.
 template <bool FILL>
 __global__ void k_plan_chunks(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                              int64_t nrows, int64_t nbins, int64_t *__restrict__ nchunk,
+                              int64_t nrows, int64_t nbins, int dense_fill,
+                              int64_t *__restrict__ nchunk,
                               const int64_t *__restrict__ row_chunk, int64_t *__restrict__ chunk_beg,
                               int32_t *__restrict__ chunk_row) {
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
@@ -133,13 +134,13 @@ __global__ void k_plan_chunks(const int64_t *__restrict__ rowptr, const int32_t 
       int64_t width = nbins - p * kPanel;
       if (width > kPanel) width = kPanel;
       int64_t stop = pend;
-      if ((pend - pos) * 4 < width) {           // sparse: absorb the following sparse panels
+      if ((pend - pos) * dense_fill < width) {  // sparse: absorb the following sparse panels
         while (stop < e) {
           const int64_t p2 = col[stop] / kPanel;
           const int64_t q2 = lower_bound_col(col, stop, e, (p2 + 1) * kPanel);
           int64_t w2 = nbins - p2 * kPanel;
           if (w2 > kPanel) w2 = kPanel;
-          if ((q2 - stop) * 4 >= w2 || q2 - pos > kChunk) break;
+          if ((q2 - stop) * dense_fill >= w2 || q2 - pos > kChunk) break;
           stop = q2;
         }
       }
@@ -298,6 +299,21 @@ void build_from_coo(tb_store *s, int64_t nnz, const int32_t *row, const int32_t 
   finish_layout(s);
 }
 
+// A panel is encoded densely (explicit zeros) when at least 1/F of its columns hold a cell.  By
+// bytes alone the break-even against 4-byte tile cells is F = 4; measured per stored cell the
+// dense kernel is faster than the tile kernel, but explicit zeros at low fill cost more than
+// that buys: F = 8 and 16 were slower than 4 on the genome-wide 5 kb matrix (TB_DENSE_FILL to try).
+int dense_fill_factor() {
+  static int f = 0;
+  if (!f) {
+    const char *e = getenv("TB_DENSE_FILL");
+    f = e ? atoi(e) : 4;
+    if (f < 1) f = 1;
+    if (f > 64) f = 64;
+  }
+  return f;
+}
+
 void finish_layout(tb_store *s) {
   cudaStream_t st = s->stream;
   StageTimer tm(st);
@@ -311,7 +327,7 @@ void finish_layout(tb_store *s) {
     TB_CUDA(cudaMemsetAsync(cnt.p, 0, cnt.bytes(), st));
     if (nrows)
       k_plan_chunks<false><<<grid_for(nrows, threads, s->sm_count), threads, 0, st>>>(
-          s->rowptr.p, s->col.p, nrows, N, cnt.p, nullptr, nullptr, nullptr);
+          s->rowptr.p, s->col.p, nrows, N, dense_fill_factor(), cnt.p, nullptr, nullptr, nullptr);
     exclusive_scan_i64(st, cnt.p, s->row_chunk.p, nrows + 1);
   }
   int64_t nchunks = 0;
@@ -321,7 +337,8 @@ void finish_layout(tb_store *s) {
   s->chunk_row.alloc(nchunks + 1);
   if (nrows)
     k_plan_chunks<true><<<grid_for(nrows, threads, s->sm_count), threads, 0, st>>>(
-        s->rowptr.p, s->col.p, nrows, N, nullptr, s->row_chunk.p, s->chunk_beg.p, s->chunk_row.p);
+        s->rowptr.p, s->col.p, nrows, N, dense_fill_factor(), nullptr, s->row_chunk.p, s->chunk_beg.p,
+        s->chunk_row.p);
   // chunk c covers cells [chunk_beg[c], chunk_beg[c+1]): close the last one
   TB_CUDA(cudaMemcpyAsync(s->chunk_beg.p + nchunks, &s->nnz_full, sizeof(int64_t),
                           cudaMemcpyHostToDevice, st));

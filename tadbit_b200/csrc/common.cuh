@@ -185,6 +185,7 @@ namespace tb {
 // build.cu
 void build_from_coo(tb_store *s, int64_t nnz, const int32_t *row, const int32_t *col,
                     const int32_t *val, int mem);
+int dense_fill_factor();            // see build.cu
 void setup_sections(tb_store *s);   // bin -> section id table (before any build)
 void finish_layout(tb_store *s);     // chunks + scratch once rowptr/col/val are in place
 void export_upper(const tb_store *s, int64_t *nnz, int32_t *h_row, int32_t *h_col, int32_t *h_val);

@@ -46,7 +46,7 @@ __device__ __forceinline__ int64_t dense_pos(int64_t s) {
 // desc = (first column, slots or cells, encoding | overflow cells << 8, payload bytes)
 __global__ void __launch_bounds__(256)
 k_plan(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
-       const int64_t *__restrict__ chunk_beg, int64_t nchunks, int64_t nbins, bool use_tiles,
+       const int64_t *__restrict__ chunk_beg, int64_t nchunks, int64_t nbins, bool use_tiles, int dense_fill,
        int4 *__restrict__ desc, uint64_t *__restrict__ key, int32_t *__restrict__ ids) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -77,7 +77,8 @@ k_plan(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
         enc = ENC_S16; best = 4 * count;
       }
       // small non-negative counts: the cells go to the sparse tiles (tiles.cu), 4 B each there
-      if (use_tiles && vmin >= 0 && vmax < (1 << kTileValBits)) { enc = ENC_T; best = 4 * count; }
+      // (tile cells are weighted dense_fill bytes, not 4: see dense_fill_factor)
+      if (use_tiles && vmin >= 0 && vmax < (1 << kTileValBits)) { enc = ENC_T; best = (int64_t)dense_fill * count; }
       int32_t c0 = cfirst;
       int64_t n = count;
       if (cfirst / kPanel == clast / kPanel) {          // inside one panel: dense is possible
@@ -212,7 +213,7 @@ void build_encoded(tb_store *s) {
     bytes.alloc(nc + 1); off_sorted.alloc(nc + 1);
     const char *env = getenv("TB_TILES");
     const bool use_tiles = !(env && env[0] == '0');      // TB_TILES=0: A/B switch, L2-gather path only
-    k_plan<<<grid, 256, 0, st>>>(s->col.p, s->val.p, s->chunk_beg.p, nc, s->nbins, use_tiles,
+    k_plan<<<grid, 256, 0, st>>>(s->col.p, s->val.p, s->chunk_beg.p, nc, s->nbins, use_tiles, dense_fill_factor(),
                                  s->enc_desc.p, key_in.p, ids_in.p);
     size_t tmp_bytes = 0, tmp2 = 0;
     TB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_in.p, key_out.p, ids_in.p,

@@ -43,7 +43,7 @@ __device__ __forceinline__ double u2d(uint32_t v) {
 }
 __device__ __forceinline__ uint32_t ldg_stream_u32(const void *p) {
   uint32_t r;
-  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::256B.u32 %0, [%1];" : "=r"(r) : "l"(p));
   return r;
 }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
