@@ -186,6 +186,11 @@ int tb_store_create_batch(int32_t n, tb_store *const *members, int device, tb_st
 int tb_ice_batch(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev,
                  double *h_bias, double *h_trace, int32_t *n_passes);
 
+/* Mean device time (ms) of one row-sum evaluation (K1) of this store alone, measured with CUDA
+ * events over `reps` launches.  Works on a shard that is not connected yet: the host uses it to
+ * re-cut row blocks so that every GPU takes the same time per pass. */
+int tb_probe_rowsum(tb_store *s, int32_t reps, double *ms_per_launch);
+
 /* timing of the last tb_ice call, measured with CUDA events on the store's stream:
  * total device ms of the pass loop, and the ms spent in the row-sum (K1) launches */
 int tb_ice_last_timing(const tb_store *s, double *loop_ms, double *rowsum_ms,

@@ -58,6 +58,7 @@ PROTOTYPES = {
     "tb_store_create_batch": ([C.c_int32, C.POINTER(_store), C.c_int, C.POINTER(_store)], C.c_int),
     "tb_ice_batch": ([_store, _u8p, C.c_int32, C.c_double, _f64p, _f64p, C.POINTER(C.c_int32)],
                      C.c_int),
+    "tb_probe_rowsum": ([_store, C.c_int32, _f64p], C.c_int),
     "tb_ice_last_timing": ([_store, _f64p, _f64p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
                            C.c_int),
     "tb_norm_sum": ([_store, _f64p, _u8p, _f64p], C.c_int),

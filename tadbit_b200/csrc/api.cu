@@ -387,6 +387,15 @@ int tb_ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev
   });
 }
 
+int tb_probe_rowsum(tb_store *s, int32_t reps, double *ms_per_launch) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(s, "null argument");
+    DeviceGuard g(s->device);
+    probe_rowsum(s, reps, ms_per_launch);
+    return TB_OK;
+  });
+}
+
 int tb_ice_last_timing(const tb_store *s, double *loop_ms, double *rowsum_ms,
                        int32_t *rowsum_launches, int32_t *total_launches) {
   if (!s) { set_error("null store"); return TB_ERR_ARG; }

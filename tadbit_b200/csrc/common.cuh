@@ -208,6 +208,7 @@ void col_sums_masked(tb_store *s, const uint8_t *h_bad, int64_t *h_col_sum);
 int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, double *h_bias,
         double *h_trace, int32_t *n_passes);
 void norm_sum(tb_store *s, const double *h_bias, const uint8_t *h_bad, double *out);
+void probe_rowsum(tb_store *s, int32_t reps, double *ms_per_launch);
 void ice_batch(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, double *h_bias,
                double *h_trace, int32_t *n_passes);
 void diag_sums(tb_store *s, const uint8_t *h_bad, int64_t ndiag, int64_t *h_sum_d);

@@ -592,6 +592,8 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
   const int64_t N = s->nbins;
   TB_REQUIRE(iterations >= 0, "ice: iterations must be >= 0");
   TB_REQUIRE(N > 0, "ice: empty matrix");
+  TB_REQUIRE(s->world > 1 || s->nrows == N,
+             "ice: the store owns a row block only; connect the shards first (tb_comm_init)");
   const int npass_max = iterations + 1;
   if (s->trace.n < (size_t)npass_max * 4) s->trace.alloc((size_t)npass_max * 4);
   upload_bad(s, h_bad);
@@ -831,6 +833,28 @@ void ice_batch(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max
   s->total_launches = launched * 4 + 3;
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+}
+
+// Mean device time of one K1 evaluation (x = 1), for balancing shards before they are connected.
+void probe_rowsum(tb_store *s, int32_t reps, double *ms_per_launch) {
+  cudaStream_t st = s->stream;
+  TB_REQUIRE(reps > 0 && ms_per_launch, "probe_rowsum: bad arguments");
+  TB_CUDA(cudaMemsetAsync(s->bad.p, 0, s->nbins, st));
+  k_ice_init<<<grid_1d(s->nbins, 256, s->sm_count), 256, 0, st>>>(s->bad.p, s->nbins, s->x.p, s->b.p,
+                                                                  s->state.p);
+  launch_rowsum(s, s->x.p, nullptr);                 // warm-up
+  cudaEvent_t e0, e1;
+  TB_CUDA(cudaEventCreate(&e0));
+  TB_CUDA(cudaEventCreate(&e1));
+  TB_CUDA(cudaEventRecord(e0, st));
+  for (int r = 0; r < reps; ++r) launch_rowsum(s, s->x.p, nullptr);
+  TB_CUDA(cudaEventRecord(e1, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  TB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_launch = ms / reps;
 }
 
 }  // namespace tb

@@ -199,31 +199,52 @@ __device__ __forceinline__ double cell_term(uint32_t c, const double *xw) {
   return u2d(c >> kTileColBits) * xw[c & kColMask];
 }
 
-// one slice of `len` cells per lane, 16 independent 128-byte warp loads kept in flight;
-// c[] holds the first 16 cells when len >= 16 (loaded before the window was waited for)
-__device__ __forceinline__ double slice_sum(const uint32_t *__restrict__ p, int len, uint32_t c[16],
-                                            const double *xw) {
-  double a0 = 0.0, a1 = 0.0;
-  int k = 0;
-  for (; k + 16 <= len; k += 16) {
-    uint32_t d[16];
-    const bool more = k + 32 <= len;
-    if (more) {
-#pragma unroll
-      for (int q = 0; q < 16; ++q) d[q] = ldg_stream_u32(p + (k + 16 + q) * 32);
-    }
-#pragma unroll
-    for (int q = 0; q < 16; q += 2) {
-      a0 += cell_term(c[q], xw);
-      a1 += cell_term(c[q + 1], xw);
-    }
-    if (more) {
-#pragma unroll
-      for (int q = 0; q < 16; ++q) c[q] = d[q];
-    }
+// A warp's cells of one unit form a stream that does not depend on the x windows: slice a of
+// tile 0, slice b of tile 0, slice a of tile 1, ...  The warp pulls that stream through a private
+// ring in shared memory with cp.async.bulk (pieces of up to kPiece k-steps = 1 KB), the producer
+// cursor running kRing pieces ahead of the consumer cursor across slice and tile boundaries, so
+// HBM latency is covered by bytes in flight in the copy engine instead of registers.
+constexpr int kPiece = 8;                                  // k-steps (128 B each) per ring stage
+constexpr int kRing = 2;                                   // stages per warp
+constexpr int kRingBytes = kRing * kPiece * 128;           // 2 KB per warp
+constexpr int kTileWarps = kTileThreads / 32;
+constexpr int kTileSmemRing = kWinBytes + kTileRows * 8 + kTileWarps * kRingBytes + kTileWarps * kRing * 8 + 64;
+
+struct SliceCur {            // a warp's position in its cell stream
+  int j, which, k, len;
+  const uint32_t *p;
+};
+
+__device__ __forceinline__ void cur_load(SliceCur &c, const int32_t *__restrict__ list, int i0, int n,
+                                         const uint32_t *__restrict__ slice,
+                                         const int64_t *__restrict__ t_off,
+                                         const uint32_t *__restrict__ cells, int sa, int sb, int part,
+                                         int parts) {
+  // move to the next non-empty slice at or after (j, which); len = 0 and j = n when exhausted
+  while (c.j < n) {
+    const int64_t tile = list[i0 + c.j];
+    const int s = c.which ? sb : sa;
+    const uint32_t s0 = slice[tile * kSliceTab + s], s1 = slice[tile * kSliceTab + s + 1];
+    const int full = (int)((s1 - s0) >> 5);
+    const int kb = full * part / parts;
+    c.len = full * (part + 1) / parts - kb;
+    c.k = 0;
+    c.p = cells + t_off[tile] + s0 + kb * 32;
+    if (c.len > 0) return;
+    if (c.which) { c.which = 0; ++c.j; } else c.which = 1;
   }
-  for (; k < len; ++k) a0 += cell_term(ldg_stream_u32(p + k * 32), xw);
-  return a0 + a1;
+  c.len = 0;
+}
+
+__device__ __forceinline__ void cur_advance(SliceCur &c, int steps, const int32_t *__restrict__ list,
+                                            int i0, int n, const uint32_t *__restrict__ slice,
+                                            const int64_t *__restrict__ t_off,
+                                            const uint32_t *__restrict__ cells, int sa, int sb, int part,
+                                            int parts) {
+  c.k += steps;
+  if (c.k < c.len) return;
+  if (c.which) { c.which = 0; ++c.j; } else c.which = 1;
+  cur_load(c, list, i0, n, slice, t_off, cells, sa, sb, part, parts);
 }
 
 __global__ void __launch_bounds__(kTileThreads, 1)
@@ -236,54 +257,86 @@ k_rowsum_tiles(const uint32_t *__restrict__ cells, const int64_t *__restrict__ t
   extern __shared__ __align__(128) uint8_t smem[];
   double *xw = reinterpret_cast<double *>(smem);                       // [kTileCols]
   double *acc = reinterpret_cast<double *>(smem + kWinBytes);          // [kTileRows]
-  const uint32_t bar = smem_u32(smem + kWinBytes + kTileRows * 8);
   const int t = threadIdx.x, lane = t & 31, wic = t >> 5;
+  uint8_t *ring = smem + kWinBytes + kTileRows * 8 + wic * kRingBytes;
+  const uint32_t ring_u32 = smem_u32(ring);
+  const uint32_t bars = smem_u32(smem + kWinBytes + kTileRows * 8 + kTileWarps * kRingBytes);
+  const uint32_t wbar = bars + kTileWarps * kRing * 8;                 // window barrier
+  const uint32_t rbar = bars + wic * kRing * 8;                        // this warp's ring barriers
   const int sa = wic, sb = kSlices - 1 - wic;          // longest slices paired with shortest
-  if (t == 0) {
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  if (t == 0) mbar_init(wbar, 1);
+  if (lane == 0) {
+    for (int q = 0; q < kRing; ++q) mbar_init(rbar + 8 * q, 1);
   }
-  uint32_t parity = 0;
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  uint32_t wparity = 0, rparity = 0;                    // rparity bit q = parity of ring stage q
   for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
     const int4 un = unit[u];
     const int i0 = un.y, n = un.z - un.y;
     const int part = un.w >> 8, parts = un.w & 0xff;   // a heavy tile is split over several units
     acc[t] = 0.0;
     acc[t + kTileThreads] = 0.0;
+    // producer: runs ahead over this warp's stream of the whole unit
+    SliceCur pc;
+    pc.j = 0; pc.which = 0;
+    cur_load(pc, list, i0, n, slice, t_off, cells, sa, sb, part, parts);
+    auto issue = [&](int stage) {
+      if (pc.len == 0) return;                          // stream exhausted
+      const int steps = min(kPiece, pc.len - pc.k);
+      if (lane == 0) {
+        mbar_expect_tx(rbar + 8 * stage, steps * 128);
+        bulk_g2s(ring_u32 + stage * kPiece * 128, pc.p + pc.k * 32, steps * 128, rbar + 8 * stage);
+      }
+      cur_advance(pc, steps, list, i0, n, slice, t_off, cells, sa, sb, part, parts);
+    };
+#pragma unroll
+    for (int q = 0; q < kRing; ++q) issue(q);
+    int stage = 0;
     for (int j = 0; j < n; ++j) {
       const int64_t tile = list[i0 + j];
       __syncthreads();                       // the window of the previous tile is consumed
       if (t == 0) {                          // 128 KB window, four 32 KB bulk copies
         const double *src = x + (tile % nwin) * kTileCols;
-        mbar_expect_tx(bar, kWinBytes);
+        mbar_expect_tx(wbar, kWinBytes);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          bulk_g2s(smem_u32(xw) + q * (kWinBytes / 4), src + q * (kTileCols / 4), kWinBytes / 4, bar);
+          bulk_g2s(smem_u32(xw) + q * (kWinBytes / 4), src + q * (kTileCols / 4), kWinBytes / 4, wbar);
       }
-      // metadata and the first cells do not depend on the window: fetch them while it lands
       const uint32_t *st = slice + tile * kSliceTab;
-      const uint32_t a0 = st[sa], a1 = st[sa + 1], b0 = st[sb], b1 = st[sb + 1];
-      const int full_a = (int)((a1 - a0) >> 5), full_b = (int)((b1 - b0) >> 5);
-      // this unit's share of every slice: cells [len*part/parts, len*(part+1)/parts)
-      const int ka = full_a * part / parts, kb = full_b * part / parts;
-      const int len_a = full_a * (part + 1) / parts - ka, len_b = full_b * (part + 1) / parts - kb;
-      const int row_a = perm[tile * kTileRows + sa * 32 + lane];
-      const int row_b = perm[tile * kTileRows + sb * 32 + lane];
-      const uint32_t *pa = cells + t_off[tile] + a0 + ka * 32 + lane;
-      const uint32_t *pb = cells + t_off[tile] + b0 + kb * 32 + lane;
-      uint32_t c[16];
-      if (len_a >= 16) {
+      int len[2], row[2];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) c[q] = ldg_stream_u32(pa + q * 32);
+      for (int h = 0; h < 2; ++h) {
+        const int s = h ? sb : sa;
+        const int full = (int)((st[s + 1] - st[s]) >> 5);
+        len[h] = full * (part + 1) / parts - full * part / parts;
+        row[h] = perm[tile * kTileRows + s * 32 + lane];
       }
-      mbar_wait(bar, parity);
-      parity ^= 1u;
-      if (len_a) acc[row_a] += slice_sum(pa, len_a, c, xw);    // distinct rows: no conflict
-      if (len_b >= 16) {
+      mbar_wait(wbar, wparity);
+      wparity ^= 1u;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) c[q] = ldg_stream_u32(pb + q * 32);
+      for (int h = 0; h < 2; ++h) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int k = 0; k < len[h]; k += kPiece) {
+          const int steps = min(kPiece, len[h] - k);
+          mbar_wait(rbar + 8 * stage, (rparity >> stage) & 1u);
+          rparity ^= 1u << stage;
+          const uint32_t *rp = reinterpret_cast<const uint32_t *>(ring + stage * kPiece * 128) + lane;
+          if (steps == kPiece) {
+#pragma unroll
+            for (int q = 0; q < kPiece; q += 2) {
+              a0 += cell_term(rp[q * 32], xw);
+              a1 += cell_term(rp[(q + 1) * 32], xw);
+            }
+          } else {
+            for (int q = 0; q < steps; ++q) a0 += cell_term(rp[q * 32], xw);
+          }
+          __syncwarp();                      // every lane has read this stage
+          issue(stage);
+          stage = (stage + 1 == kRing) ? 0 : stage + 1;
+        }
+        if (len[h]) acc[row[h]] += a0 + a1;  // distinct rows per thread: no conflict
       }
-      if (len_b) acc[row_b] += slice_sum(pb, len_b, c, xw);
     }
     __syncthreads();
     partial[u * kTileRows + t] = acc[t];
@@ -409,11 +462,11 @@ void launch_rowsum_tiles(tb_store *s, const double *x, const IceState *state) {
   if (s->t_nunits == 0) return;
   static bool attr_set[64] = {false};            // per device: the attribute is per context
   if (!attr_set[s->device & 63]) {
-    TB_CUDA(cudaFuncSetAttribute(k_rowsum_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
+    TB_CUDA(cudaFuncSetAttribute(k_rowsum_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemRing));
     attr_set[s->device & 63] = true;
   }
   const int grid = (int)(s->t_nunits < s->sm_count ? s->t_nunits : s->sm_count);
-  k_rowsum_tiles<<<grid, kTileThreads, kTileSmem, s->stream>>>(
+  k_rowsum_tiles<<<grid, kTileThreads, kTileSmemRing, s->stream>>>(
       s->t_cells.p, s->t_off.p, s->t_perm.p, s->t_slice.p, s->t_list.p,
       reinterpret_cast<const int4 *>(s->t_unit.p), s->t_nunits, s->t_nwin, x, s->t_partial.p, state);
 }

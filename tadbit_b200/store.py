@@ -165,6 +165,12 @@ class ContactStore(object):
         ntrace = npass.value if iterations > 0 else 0
         return bias, trace[:ntrace]
 
+    def probe_rowsum(self, reps=4):
+        """Mean device ms of one K1 evaluation of this store (also on an unconnected shard)."""
+        ms = C.c_double()
+        check(lib().tb_probe_rowsum(self._h, int(reps), C.byref(ms)))
+        return ms.value
+
     def ice_timing(self):
         a, b = C.c_double(), C.c_double()
         n, t = C.c_int32(), C.c_int32()

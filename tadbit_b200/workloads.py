@@ -52,7 +52,9 @@ def workload(name):
 
 def balanced_row_blocks(row_counts, world):
     """Contiguous row blocks with (nearly) equal numbers of stored cells."""
-    csum = np.concatenate([[0], np.cumsum(row_counts, dtype=np.int64)])
+    row_counts = np.asarray(row_counts)
+    acc = np.float64 if row_counts.dtype.kind == 'f' else np.int64
+    csum = np.concatenate([[0], np.cumsum(row_counts, dtype=acc)])
     total = csum[-1]
     bounds = [0]
     for r in range(1, world):
@@ -63,9 +65,23 @@ def balanced_row_blocks(row_counts, world):
     return [(bounds[r], bounds[r + 1]) for r in range(world)]
 
 
-def build_sharded(wl, rank, world, device, gather=None):
+def rebalance_by_time(blocks, times, size):
+    """New contiguous row blocks of equal estimated time, from the measured row-sum time of
+    each current block (cost taken as uniform inside a block)."""
+    cost = np.zeros(size)
+    for (a, b), t in zip(blocks, times):
+        if b > a:
+            cost[a:b] = float(t) / (b - a)
+    return balanced_row_blocks(cost, len(blocks))
+
+
+def build_sharded(wl, rank, world, device, gather=None, refine=2):
     """Generate this rank's block of the synthetic matrix.  ``gather`` is a callable that
-    all-gathers a numpy int64 array over ranks (host plumbing, e.g. torch.distributed)."""
+    all-gathers a python object over ranks (host plumbing, e.g. torch.distributed).
+
+    Blocks are first balanced by stored cells; a cell does not cost the same in the dense and
+    in the sparse part of the row-sum, so the blocks are then re-cut ``refine`` times from the
+    measured K1 time of every shard (``tb_probe_rowsum`` on the not yet connected shard)."""
     n = wl["size"]
     if world == 1:
         return ContactStore.synthetic(n, wl["params"], chromosomes=wl["chromosomes"],
@@ -77,4 +93,15 @@ def build_sharded(wl, rank, world, device, gather=None):
     blocks = balanced_row_blocks(counts, world)
     store = ContactStore.synthetic(n, wl["params"], chromosomes=wl["chromosomes"],
                                    row_block=blocks[rank], device=device)
+    for _ in range(refine):
+        times = [float(t) for t in gather(store.probe_rowsum(4))]   # shard alone, timing only
+        if max(times) <= 1.03 * (sum(times) / world):
+            break
+        new = rebalance_by_time(blocks, times, n)
+        if new == blocks:
+            break
+        blocks = new
+        store.close()
+        store = ContactStore.synthetic(n, wl["params"], chromosomes=wl["chromosomes"],
+                                       row_block=blocks[rank], device=device)
     return store, blocks[rank]
