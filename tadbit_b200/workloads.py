@@ -34,6 +34,11 @@ def workload(name):
         params = SynthParams(seed=SEED, cis_scale=1900.0, cis_alpha=1.08, trans_mean=1.2e-3,
                              vis_sigma=0.35, low_frac=0.02, low_scale=0.02, empty_frac=0.005)
         desc = "synthetic genome-wide human @5kb (BASELINE configs[2])"
+    elif name == "c4":      # genome-wide 1 kb, 8 GPUs
+        chroms = genome_bins(1000)
+        params = SynthParams(seed=SEED, cis_scale=2600.0, cis_alpha=1.08, trans_mean=2.4e-4,
+                             vis_sigma=0.35, low_frac=0.02, low_scale=0.02, empty_frac=0.005)
+        desc = "synthetic genome-wide human @1kb (BASELINE configs[3])"
     elif name == "c3s":     # 1/8 genome (chr1-3) at 5 kb: sparse profile at a size quick to build
         chroms = genome_bins(5000, [0, 1, 2])
         params = SynthParams(seed=SEED, cis_scale=1300.0, cis_alpha=1.08, trans_mean=1.1e-3,
