@@ -187,9 +187,13 @@ int tb_ice_batch(tb_store *s, const uint8_t *h_bad, int32_t iterations, double m
                  double *h_bias, double *h_trace, int32_t *n_passes);
 
 /* Mean device time (ms) of one row-sum evaluation (K1) of this store alone, measured with CUDA
- * events over `reps` launches.  Works on a shard that is not connected yet: the host uses it to
- * re-cut row blocks so that every GPU takes the same time per pass. */
-int tb_probe_rowsum(tb_store *s, int32_t reps, double *ms_per_launch);
+ * events over `reps` launches: ms[0] total, ms[1] sparse-tile kernel, ms[2] dense (+ per-cell)
+ * kernels.  Works on a shard that is not connected yet.  tb_row_work gives, for every owned row,
+ * the payload bytes of its dense chunks and its cells in sparse tiles (int64[row_end-row_begin],
+ * HOST).  The host combines both to re-cut row blocks so that every GPU takes the same time per
+ * pass (tadbit_b200/workloads.py:build_sharded). */
+int tb_probe_rowsum(tb_store *s, int32_t reps, double ms[3]);
+int tb_row_work(tb_store *s, int64_t *h_dense_bytes, int64_t *h_tile_cells);
 
 /* timing of the last tb_ice call, measured with CUDA events on the store's stream:
  * total device ms of the pass loop, and the ms spent in the row-sum (K1) launches */

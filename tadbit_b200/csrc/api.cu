@@ -387,11 +387,20 @@ int tb_ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev
   });
 }
 
-int tb_probe_rowsum(tb_store *s, int32_t reps, double *ms_per_launch) {
+int tb_probe_rowsum(tb_store *s, int32_t reps, double ms[3]) {
   return guarded([&]() -> int {
     TB_REQUIRE(s, "null argument");
     DeviceGuard g(s->device);
-    probe_rowsum(s, reps, ms_per_launch);
+    probe_rowsum(s, reps, ms);
+    return TB_OK;
+  });
+}
+
+int tb_row_work(tb_store *s, int64_t *h_dense_bytes, int64_t *h_tile_cells) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(s && h_dense_bytes && h_tile_cells, "null argument");
+    DeviceGuard g(s->device);
+    row_work(s, h_dense_bytes, h_tile_cells);
     return TB_OK;
   });
 }

@@ -194,6 +194,7 @@ void build_batch(tb_store *s, int32_t n, tb_store *const *members);   // block-d
 void build_encoded(tb_store *s);     // compact row-sum stream from the CSR
 // rowsum.cu
 void launch_rowsum(tb_store *s, const double *x, const IceState *state);   // K1 over the compact stream
+void launch_rowsum_chunks(tb_store *s, const double *x, const IceState *state);   // dense + per-cell part
 // tiles.cu
 void build_tiles(tb_store *s);       // sparse tiles from the ENC_T chunks (after build_encoded)
 void launch_rowsum_tiles(tb_store *s, const double *x, const IceState *state);
@@ -208,7 +209,8 @@ void col_sums_masked(tb_store *s, const uint8_t *h_bad, int64_t *h_col_sum);
 int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, double *h_bias,
         double *h_trace, int32_t *n_passes);
 void norm_sum(tb_store *s, const double *h_bias, const uint8_t *h_bad, double *out);
-void probe_rowsum(tb_store *s, int32_t reps, double *ms_per_launch);
+void probe_rowsum(tb_store *s, int32_t reps, double ms[3]);
+void row_work(tb_store *s, int64_t *h_dense, int64_t *h_tile);
 void ice_batch(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, double *h_bias,
                double *h_trace, int32_t *n_passes);
 void diag_sums(tb_store *s, const uint8_t *h_bad, int64_t ndiag, int64_t *h_sum_d);

@@ -695,7 +695,12 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
     s->rowsum_ms += ms;
     ++s->rowsum_launches;
   }
-  s->total_launches = launched * (s->world > 1 ? 5 : 4) + 2;
+  {   // kernels of this library launched by the call (NCCL's own kernels are not counted)
+    const int k1 = csr_walk ? 1 : (s->t_nunits > 0) + (s->n_groups > 0) + (s->n_sparse > 0);
+    const int k2 = 2 + (s->world > 1 && s->nrows ? 1 : 0);       // (combine) + reduce + update
+    s->total_launches = 2 /* init, finalize */ + (launched ? 1 + k2 : 0) +
+                        (launched > 1 ? (launched - 1) * (k1 + k2) : 0);
+  }
   for (auto &e : ev) cudaEventDestroy(e);
   return rc;
 }
@@ -830,31 +835,75 @@ void ice_batch(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max
   s->loop_ms = ms;
   s->rowsum_ms = 0;
   s->rowsum_launches = 0;
-  s->total_launches = launched * 4 + 3;
+  {
+    const int k1 = csr_walk ? 1 : (s->t_nunits > 0) + (s->n_groups > 0) + (s->n_sparse > 0);
+    s->total_launches = 3 + (launched ? 3 : 0) + (launched > 1 ? (launched - 1) * (k1 + 2) : 0);
+  }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
 }
 
-// Mean device time of one K1 evaluation (x = 1), for balancing shards before they are connected.
-void probe_rowsum(tb_store *s, int32_t reps, double *ms_per_launch) {
+// Work of every owned row in the two K1 kernels: slots of its dense chunks, cells in sparse tiles.
+namespace {
+__global__ void k_row_work(const int4 *__restrict__ desc, const int64_t *__restrict__ row_chunk,
+                           int64_t nrows, long long *__restrict__ dense_slots,
+                           long long *__restrict__ tile_cells) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    long long d = 0, t = 0;
+    for (int64_t c = row_chunk[r]; c < row_chunk[r + 1]; ++c) {
+      const int4 e = desc[c];
+      const int enc = e.z & 0xff;
+      if (enc >= ENC_D32 && enc <= ENC_D8) d += e.y * (enc == ENC_D32 ? 4 : (enc == ENC_D16 ? 2 : 1));
+      else t += e.y;
+    }
+    dense_slots[r] = d;      // weighted by bytes per slot
+    tile_cells[r] = t;
+  }
+}
+}  // namespace
+
+void row_work(tb_store *s, int64_t *h_dense, int64_t *h_tile) {
   cudaStream_t st = s->stream;
-  TB_REQUIRE(reps > 0 && ms_per_launch, "probe_rowsum: bad arguments");
+  if (!s->nrows) return;
+  DevBuf<long long> d, t;
+  d.alloc(s->nrows);
+  t.alloc(s->nrows);
+  k_row_work<<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(s->enc_desc.p, s->row_chunk.p,
+                                                                  s->nrows, d.p, t.p);
+  TB_CUDA(cudaMemcpyAsync(h_dense, d.p, s->nrows * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaMemcpyAsync(h_tile, t.p, s->nrows * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+}
+
+// Mean device time of one K1 evaluation (x = 1) of this store alone -- total, sparse-tile kernel,
+// dense (+ per-cell sparse) kernels -- for balancing shards before they are connected.
+void probe_rowsum(tb_store *s, int32_t reps, double ms[3]) {
+  cudaStream_t st = s->stream;
+  TB_REQUIRE(reps > 0 && ms, "probe_rowsum: bad arguments");
   TB_CUDA(cudaMemsetAsync(s->bad.p, 0, s->nbins, st));
   k_ice_init<<<grid_1d(s->nbins, 256, s->sm_count), 256, 0, st>>>(s->bad.p, s->nbins, s->x.p, s->b.p,
                                                                   s->state.p);
   launch_rowsum(s, s->x.p, nullptr);                 // warm-up
-  cudaEvent_t e0, e1;
-  TB_CUDA(cudaEventCreate(&e0));
-  TB_CUDA(cudaEventCreate(&e1));
-  TB_CUDA(cudaEventRecord(e0, st));
-  for (int r = 0; r < reps; ++r) launch_rowsum(s, s->x.p, nullptr);
-  TB_CUDA(cudaEventRecord(e1, st));
-  TB_CUDA(cudaStreamSynchronize(st));
-  float ms = 0.f;
-  TB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  *ms_per_launch = ms / reps;
+  cudaEvent_t e[3];
+  for (auto &x : e) TB_CUDA(cudaEventCreate(&x));
+  float tiles = 0.f, rest = 0.f, f = 0.f;
+  for (int r = 0; r < reps; ++r) {
+    TB_CUDA(cudaEventRecord(e[0], st));
+    launch_rowsum_tiles(s, s->x.p, nullptr);
+    TB_CUDA(cudaEventRecord(e[1], st));
+    launch_rowsum_chunks(s, s->x.p, nullptr);
+    TB_CUDA(cudaEventRecord(e[2], st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    TB_CUDA(cudaEventElapsedTime(&f, e[0], e[1]));
+    tiles += f;
+    TB_CUDA(cudaEventElapsedTime(&f, e[1], e[2]));
+    rest += f;
+  }
+  for (auto &x : e) cudaEventDestroy(x);
+  ms[1] = tiles / reps;
+  ms[2] = rest / reps;
+  ms[0] = ms[1] + ms[2];
 }
 
 }  // namespace tb

@@ -303,6 +303,10 @@ k_rowsum_sparse(const uint8_t *__restrict__ data, const int64_t *__restrict__ of
 
 void launch_rowsum(tb_store *s, const double *x, const IceState *state) {
   launch_rowsum_tiles(s, x, state);
+  launch_rowsum_chunks(s, x, state);
+}
+
+void launch_rowsum_chunks(tb_store *s, const double *x, const IceState *state) {
   if (s->n_groups) {
     static bool attr_set[64] = {false};          // per device: the attribute is per context
     if (!attr_set[s->device & 63]) {

@@ -166,10 +166,21 @@ class ContactStore(object):
         return bias, trace[:ntrace]
 
     def probe_rowsum(self, reps=4):
-        """Mean device ms of one K1 evaluation of this store (also on an unconnected shard)."""
-        ms = C.c_double()
-        check(lib().tb_probe_rowsum(self._h, int(reps), C.byref(ms)))
-        return ms.value
+        """Mean device ms of one K1 evaluation of this store (also on an unconnected shard):
+        (total, sparse-tile kernel, dense kernels)."""
+        ms = np.zeros(3, dtype=np.float64)
+        check(lib().tb_probe_rowsum(self._h, int(reps), ptr(ms, C.c_double)))
+        return tuple(ms.tolist())
+
+    def row_work(self):
+        """Per owned row: payload bytes of its dense chunks, cells in sparse tiles."""
+        i = self.info()
+        n = i["row_end"] - i["row_begin"]
+        dense = np.zeros(n, dtype=np.int64)
+        tiles = np.zeros(n, dtype=np.int64)
+        if n:
+            check(lib().tb_row_work(self._h, ptr(dense, C.c_int64), ptr(tiles, C.c_int64)))
+        return dense, tiles
 
     def ice_timing(self):
         a, b = C.c_double(), C.c_double()

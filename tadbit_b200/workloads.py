@@ -70,13 +70,22 @@ def balanced_row_blocks(row_counts, world):
     return [(bounds[r], bounds[r + 1]) for r in range(world)]
 
 
-def rebalance_by_time(blocks, times, size):
-    """New contiguous row blocks of equal estimated time, from the measured row-sum time of
-    each current block (cost taken as uniform inside a block)."""
+def rebalance_by_time(blocks, probes, size):
+    """New contiguous row blocks of equal estimated K1 time.
+
+    ``probes[r]`` = (ms_tiles, ms_dense, dense_bytes_per_row, tile_cells_per_row) of the shard
+    that currently owns ``blocks[r]``.  Each kernel's measured time is spread over the shard's
+    rows in proportion to the row's share of that kernel's work, which gives a cost per row
+    that follows the structure of the matrix inside a block."""
     cost = np.zeros(size)
-    for (a, b), t in zip(blocks, times):
-        if b > a:
-            cost[a:b] = float(t) / (b - a)
+    for (a, b), (ms_t, ms_d, dense, tiles) in zip(blocks, probes):
+        if b <= a:
+            continue
+        row = np.zeros(b - a)
+        dt, tt = float(np.sum(dense)), float(np.sum(tiles))
+        row += ms_d * (dense / dt) if dt > 0 else ms_d / (b - a)
+        row += ms_t * (tiles / tt) if tt > 0 else ms_t / (b - a)
+        cost[a:b] = row
     return balanced_row_blocks(cost, len(blocks))
 
 
@@ -99,10 +108,13 @@ def build_sharded(wl, rank, world, device, gather=None, refine=2):
     store = ContactStore.synthetic(n, wl["params"], chromosomes=wl["chromosomes"],
                                    row_block=blocks[rank], device=device)
     for _ in range(refine):
-        times = [float(t) for t in gather(store.probe_rowsum(4))]   # shard alone, timing only
+        total, ms_t, ms_d = store.probe_rowsum(4)                    # shard alone, timing only
+        dense, tiles = store.row_work()
+        probes = gather((ms_t, ms_d, dense, tiles))
+        times = [p[0] + p[1] for p in probes]
         if max(times) <= 1.03 * (sum(times) / world):
             break
-        new = rebalance_by_time(blocks, times, n)
+        new = rebalance_by_time(blocks, probes, n)
         if new == blocks:
             break
         blocks = new
