@@ -21,6 +21,7 @@ namespace {
 __global__ void k_validate_count(const int32_t *__restrict__ row, const int32_t *__restrict__ col,
                                  int64_t nnz, int64_t nbins, int64_t rb, int64_t re,
                                  unsigned long long *n_out, int *bad_input) {
+  // bad_input[0] invalid cell, [1] duplicate (set later), [2] cells not in strict row-major order
   unsigned long long mine = 0;
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nnz;
        k += (int64_t)gridDim.x * blockDim.x) {
@@ -28,6 +29,10 @@ __global__ void k_validate_count(const int32_t *__restrict__ row, const int32_t 
     if (i < 0 || j < i || j >= nbins) {
       *bad_input = 1;
       continue;
+    }
+    if (k + 1 < nnz) {
+      const int64_t i2 = row[k + 1], j2 = col[k + 1];
+      if (i2 < i || (i2 == i && j2 <= j)) bad_input[2] = 1;
     }
     mine += (i >= rb && i < re);
     mine += (i != j && j >= rb && j < re);
@@ -95,6 +100,71 @@ __global__ void k_split_keys(const uint64_t *__restrict__ keys, int64_t m, int64
     if (k == m - 1)
       for (int64_t rr = r + 1; rr <= nrows; ++rr) rowptr[rr] = m;
   }
+}
+
+// ---- fast path for row-major sorted input (whole matrix) ------------------------------------
+// rows sorted: upper row pointers from the row boundaries; column counts by atomics
+__global__ void k_sorted_counts(const int32_t *__restrict__ row, const int32_t *__restrict__ col,
+                                int64_t nnz, int64_t nbins, int64_t *__restrict__ up_ptr,
+                                unsigned int *__restrict__ col_cnt) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nnz;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = row[k], rprev = k ? row[k - 1] : -1;
+    for (int64_t rr = rprev + 1; rr <= r; ++rr) up_ptr[rr] = k;
+    if (k == nnz - 1)
+      for (int64_t rr = r + 1; rr <= nbins; ++rr) up_ptr[rr] = nnz;
+    atomicAdd(&col_cnt[col[k]], 1u);
+  }
+}
+
+// full-row length = cells above the diagonal in this column + cells of the upper row
+__global__ void k_full_counts(const int64_t *__restrict__ up_ptr, const unsigned int *__restrict__ col_cnt,
+                              const int32_t *__restrict__ col, int64_t nbins, int64_t *__restrict__ full_cnt,
+                              int64_t *__restrict__ col_cnt64) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nbins;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t up = up_ptr[r + 1] - up_ptr[r];
+    const int has_diag = up > 0 && col[up_ptr[r]] == r;      // first cell of the upper row
+    col_cnt64[r] = col_cnt[r];
+    full_cnt[r] = (int64_t)col_cnt[r] - has_diag + up;
+  }
+}
+
+__global__ void k_fill_upper(const int32_t *__restrict__ row, const int32_t *__restrict__ col,
+                             const int32_t *__restrict__ val, int64_t nnz,
+                             const int64_t *__restrict__ up_ptr, const int64_t *__restrict__ rowptr,
+                             int32_t *__restrict__ ocol, int32_t *__restrict__ oval) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nnz;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = row[k];
+    const int64_t up = up_ptr[r + 1] - up_ptr[r];
+    const int64_t dest = rowptr[r + 1] - up + (k - up_ptr[r]);   // upper cells close the row
+    ocol[dest] = col[k];
+    oval[dest] = val[k];
+  }
+}
+
+// cells stably sorted by column: position p of column j's run is the p-th smallest row
+__global__ void k_fill_lower(const uint32_t *__restrict__ sorted_col, const uint32_t *__restrict__ idx,
+                             const int32_t *__restrict__ row, const int32_t *__restrict__ val, int64_t nnz,
+                             const int64_t *__restrict__ cptr, const int64_t *__restrict__ rowptr,
+                             int32_t *__restrict__ ocol, int32_t *__restrict__ oval) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nnz;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = sorted_col[p];
+    const uint32_t k = idx[p];
+    const int32_t i = row[k];
+    if (i == j) continue;                                       // the diagonal is stored once
+    const int64_t dest = rowptr[j] + (p - cptr[j]);
+    ocol[dest] = i;
+    oval[dest] = val[k];
+  }
+}
+
+__global__ void k_iota_u32(uint32_t *p, int64_t n) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n;
+       k += (int64_t)gridDim.x * blockDim.x)
+    p[k] = (uint32_t)k;
 }
 
 __global__ void k_fill_i64(int64_t *p, int64_t n, int64_t v) {
@@ -244,9 +314,9 @@ void build_from_coo(tb_store *s, int64_t nnz, const int32_t *row, const int32_t 
   }
   tm.lap("H2D cells");
   DevBuf<unsigned long long> counters;   // [0] directed cells, [1] emit cursor
-  DevBuf<int> flags;                     // [0] bad input, [1] duplicate
+  DevBuf<int> flags;                     // [0] bad input, [1] duplicate, [2] not row-major sorted
   counters.alloc(2);
-  flags.alloc(2);
+  flags.alloc(4);
   TB_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), st));
   TB_CUDA(cudaMemsetAsync(flags.p, 0, flags.bytes(), st));
   const int threads = 256;
@@ -254,7 +324,7 @@ void build_from_coo(tb_store *s, int64_t nnz, const int32_t *row, const int32_t 
     k_validate_count<<<grid_for(nnz, threads, s->sm_count), threads, 0, st>>>(
         r, c, nnz, s->nbins, s->row_begin, s->row_end, counters.p, flags.p);
   unsigned long long h_cnt[2] = {0, 0};
-  int h_flags[2] = {0, 0};
+  int h_flags[4] = {0, 0, 0, 0};
   TB_CUDA(cudaMemcpyAsync(h_cnt, counters.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaMemcpyAsync(h_flags, flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaStreamSynchronize(st));
@@ -268,6 +338,53 @@ void build_from_coo(tb_store *s, int64_t nnz, const int32_t *row, const int32_t 
     k_fill_i64<<<grid_for(s->nrows + 1, threads, s->sm_count), threads, 0, st>>>(
         s->rowptr.p, s->nrows + 1, 0);
     TB_CUDA(cudaStreamSynchronize(st));
+    finish_layout(s);
+    return;
+  }
+  const char *no_fast = getenv("TB_NO_SORTED_PATH");
+  if (!h_flags[2] && s->row_begin == 0 && s->row_end == s->nbins && nnz < 4294967295LL &&
+      !(no_fast && no_fast[0] == '1')) {
+    // Row-major sorted cells of the whole matrix (what HiC_data and tb_store_export_upper
+    // produce): the upper rows are already in place, and the mirrored half only needs the cells
+    // stably sorted by COLUMN -- a 32-bit key sort of nnz items instead of a 64-bit key sort of
+    // 2 nnz.  Strictly increasing (row, col) also rules out duplicates.
+    const int64_t N = s->nbins;
+    DevBuf<int64_t> up_ptr, full_cnt, col_cnt64, cptr;
+    DevBuf<unsigned int> col_cnt;
+    up_ptr.alloc(N + 1); full_cnt.alloc(N + 1); col_cnt64.alloc(N + 1); cptr.alloc(N + 1);
+    col_cnt.alloc(N + 1);
+    TB_CUDA(cudaMemsetAsync(col_cnt.p, 0, col_cnt.bytes(), st));
+    TB_CUDA(cudaMemsetAsync(full_cnt.p, 0, full_cnt.bytes(), st));
+    TB_CUDA(cudaMemsetAsync(col_cnt64.p, 0, col_cnt64.bytes(), st));
+    k_sorted_counts<<<grid_for(nnz, threads, s->sm_count), threads, 0, st>>>(r, c, nnz, N, up_ptr.p,
+                                                                             col_cnt.p);
+    k_full_counts<<<grid_for(N, threads, s->sm_count), threads, 0, st>>>(up_ptr.p, col_cnt.p, c, N,
+                                                                         full_cnt.p, col_cnt64.p);
+    exclusive_scan_i64(st, full_cnt.p, s->rowptr.p, N + 1);
+    exclusive_scan_i64(st, col_cnt64.p, cptr.p, N + 1);
+    k_fill_upper<<<grid_for(nnz, threads, s->sm_count), threads, 0, st>>>(r, c, v, nnz, up_ptr.p,
+                                                                          s->rowptr.p, s->col.p, s->val.p);
+    {
+      DevBuf<uint32_t> key_out, idx_in, idx_out;
+      key_out.alloc(nnz); idx_in.alloc(nnz); idx_out.alloc(nnz);
+      k_iota_u32<<<grid_for(nnz, threads, s->sm_count), threads, 0, st>>>(idx_in.p, nnz);
+      int bits = 1;
+      while (((int64_t)1 << bits) < N) ++bits;
+      size_t tmp_bytes = 0;
+      const uint32_t *key_in = reinterpret_cast<const uint32_t *>(c);
+      TB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_in, key_out.p, idx_in.p,
+                                              idx_out.p, nnz, 0, bits, st));
+      DevBuf<uint8_t> tmp;
+      tmp.alloc(tmp_bytes ? tmp_bytes : 1);
+      TB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key_in, key_out.p, idx_in.p,
+                                              idx_out.p, nnz, 0, bits, st));
+      k_fill_lower<<<grid_for(nnz, threads, s->sm_count), threads, 0, st>>>(
+          key_out.p, idx_out.p, r, v, nnz, cptr.p, s->rowptr.p, s->col.p, s->val.p);
+      TB_CUDA(cudaStreamSynchronize(st));
+    }
+    tm.lap("mirror by column sort");
+    drow.release(); dcol.release(); dval.release(); counters.release(); flags.release();
+    tm.lap("free input copies");
     finish_layout(s);
     return;
   }
