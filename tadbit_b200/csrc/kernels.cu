@@ -119,7 +119,7 @@ __global__ void k_combine_f64(const double *__restrict__ pf, const long long *__
       a += pf[c];
       if (WITH_COUNT) n += pc[c];
     }
-    if (!WITH_COUNT) a += tile_sum(ts, r);        // pass 0 (WITH_COUNT) walks the CSR, all cells
+    a += tile_sum(ts, r);
     out[rb + r] = a;
     if (WITH_COUNT) out[nbins + rb + r] = (double)n;
   }
@@ -145,6 +145,32 @@ __global__ void k_row_nnz(const int64_t *__restrict__ rowptr, int64_t nrows, int
 // ---------------------------------------------------------------------------------
 // ICE vector kernels
 // ---------------------------------------------------------------------------------
+// "Present" rows (copy_matrix, normalize_hic.py:165-177): non-bad rows that keep at least one
+// stored cell whose partner is not bad.  live_i = stored cells of row i - cells of row i whose
+// partner is bad; by symmetry the second term is collected by walking only the BAD rows (a few
+// per cent of the matrix).  Counts are exact small integers carried as doubles so that they can
+// ride in the same all-reduce as the row sums.
+__global__ void k_live_init(const int64_t *__restrict__ rowptr, int64_t nrows, int64_t rb,
+                            double *__restrict__ live) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
+       r += (int64_t)gridDim.x * blockDim.x)
+    live[rb + r] = (double)(rowptr[r + 1] - rowptr[r]);
+}
+
+__global__ void __launch_bounds__(256)
+k_bad_partners(const int32_t *__restrict__ col, const int64_t *__restrict__ chunk_beg,
+               const int32_t *__restrict__ chunk_row, int64_t nchunks, int64_t rb,
+               const uint8_t *__restrict__ bad, double *__restrict__ live) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t c = warp; c < nchunks; c += nwarp) {
+    if (!bad[rb + chunk_row[c]]) continue;
+    for (int64_t k = chunk_beg[c] + lane; k < chunk_beg[c + 1]; k += 32)
+      atomicAdd(&live[col[k]], -1.0);       // integers: the order of the additions is irrelevant
+  }
+}
+
 __global__ void k_ice_init(const uint8_t *__restrict__ bad, int64_t n, double *x, double *b,
                            IceState *state) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
@@ -187,14 +213,10 @@ k_ice_reduce(double *__restrict__ s_full, const double *__restrict__ x,
     double si;
     if (FUSED) {
       double a = 0.0;
-      long long nc = 0;
-      for (int64_t c = row_chunk[i]; c < row_chunk[i + 1]; ++c) {
-        a += pf[c];
-        if (pass == 0) nc += pc[c];
-      }
-      if (pass != 0) a += tile_sum(ts, i);        // pass 0 walks the CSR, all cells
+      for (int64_t c = row_chunk[i]; c < row_chunk[i + 1]; ++c) a += pf[c];
+      a += tile_sum(ts, i);
       s_full[i] = si = a;
-      if (pass == 0) present[i] = p = !bad[i] && nc > 0;
+      if (pass == 0) present[i] = p = !bad[i] && s_full[n + i] > 0.0;
       else p = present[i];
     } else {
       si = s_full[i];
@@ -446,7 +468,8 @@ __global__ void k_seg_init(SegState *seg, int nseg, unsigned int *n_stopped) {
 __global__ void __launch_bounds__(1024)
 k_seg_reduce(double *__restrict__ s_full, const double *__restrict__ x,
              const uint8_t *__restrict__ bad, uint8_t *__restrict__ present,
-             const int64_t *__restrict__ seg_off, int nseg, int pass, int iterations, double max_dev,
+             const int64_t *__restrict__ seg_off, int nseg, int64_t nbins, int pass, int iterations,
+             double max_dev,
              double *__restrict__ trace, int npass_max, SegState *seg, unsigned int *n_stopped,
              IceState *state, const double *__restrict__ pf, const long long *__restrict__ pc,
              const int64_t *__restrict__ row_chunk, TileSums ts) {
@@ -458,15 +481,11 @@ k_seg_reduce(double *__restrict__ s_full, const double *__restrict__ x,
   long long cnt = 0;
   for (int64_t i = seg_off[k] + threadIdx.x; i < seg_off[k + 1]; i += blockDim.x) {
     double a = 0.0;
-    long long nc = 0;
-    for (int64_t c = row_chunk[i]; c < row_chunk[i + 1]; ++c) {
-      a += pf[c];
-      if (pass == 0) nc += pc[c];
-    }
-    if (pass != 0) a += tile_sum(ts, i);
+    for (int64_t c = row_chunk[i]; c < row_chunk[i + 1]; ++c) a += pf[c];
+    a += tile_sum(ts, i);
     s_full[i] = a;
     bool p;
-    if (pass == 0) present[i] = p = !bad[i] && nc > 0;
+    if (pass == 0) present[i] = p = !bad[i] && s_full[nbins + i] > 0.0;
     else p = present[i];
     if (p) {
       const double S = x[i] * a;
@@ -586,6 +605,18 @@ void col_sums_masked(tb_store *s, const uint8_t *h_bad, int64_t *h_col_sum) {
   TB_CUDA(cudaStreamSynchronize(st));
 }
 
+// live[i] for the owned rows (+ the bad-partner corrections of any row), zeros elsewhere
+void prepare_live(tb_store *s, double *live) {
+  cudaStream_t st = s->stream;
+  TB_CUDA(cudaMemsetAsync(live, 0, s->nbins * sizeof(double), st));
+  if (!s->nrows) return;
+  k_live_init<<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(s->rowptr.p, s->nrows,
+                                                                   s->row_begin, live);
+  if (s->nchunks)
+    k_bad_partners<<<chunk_grid(s), 256, 0, st>>>(s->col.p, s->chunk_beg.p, s->chunk_row.p, s->nchunks,
+                                                  s->row_begin, s->bad.p, live);
+}
+
 int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, double *h_bias,
         double *h_trace, int32_t *n_passes) {
   cudaStream_t st = s->stream;
@@ -607,6 +638,8 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
   double *dst = s->world > 1 ? s->s_part.p : s->s_full.p;
   const bool csr_walk = use_csr_rowsum(s);
   const TileSums ts = {(!csr_walk && s->t_nunits) ? s->t_partial.p : nullptr, s->t_unit_of_rb.p};
+  prepare_live(s, dst + N);
+  if (ts.partial) TB_CUDA(cudaMemsetAsync(s->partial_f.p, 0, s->partial_f.bytes(), st));
   // The host only needs to know WHEN the loop stopped: passes queued after the stop are no-ops
   // on the device.  ICE converges geometrically, so the next look is scheduled where the
   // deviation is predicted to cross max_dev (at most 16 passes ahead).
@@ -618,21 +651,13 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
   TB_CUDA(cudaEventRecord(ev[2 * npass_max], st));
   for (int p = 0; p < npass_max && !stopped; ++p) {
     TB_CUDA(cudaEventRecord(ev[2 * p], st));
-    // pass 0 also counts the cells that survive the mask (which rows are "present"), so it
-    // walks the CSR; every later pass streams the compact encoding
-    if (p == 0) launch_chunks<M_F64_COUNT>(s, s->x.p, nullptr, s->state.p);
-    else if (use_csr_rowsum(s)) launch_chunks<M_F64>(s, s->x.p, nullptr, s->state.p);
+    if (csr_walk) launch_chunks<M_F64>(s, s->x.p, nullptr, s->state.p);
     else launch_rowsum(s, s->x.p, s->state.p);
     TB_CUDA(cudaEventRecord(ev[2 * p + 1], st));
     if (s->world > 1) {
-      if (s->nrows) {
-        if (p == 0)
-          k_combine_f64<true><<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
-              s->partial_f.p, s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, N, dst, s->state.p, ts);
-        else
-          k_combine_f64<false><<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
-              s->partial_f.p, s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, N, dst, s->state.p, ts);
-      }
+      if (s->nrows)
+        k_combine_f64<false><<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
+            s->partial_f.p, s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, N, dst, s->state.p, ts);
       allreduce_f64(s, s->s_part.p, s->s_full.p, p == 0 ? 2 * N : N);
       k_ice_reduce<false><<<rg, kRedThreads, 0, st>>>(
           s->s_full.p, s->x.p, s->bad.p, s->present.p, N, p, iterations, max_dev, s->block_red.p,
@@ -643,10 +668,6 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
           s->trace.p, s->state.p, s->partial_f.p, s->partial_i.p, s->row_chunk.p, ts);
     }
     k_ice_update<<<vg, 256, 0, st>>>(s->s_full.p, s->x.p, s->b.p, s->present.p, N, p, s->state.p);
-    // pass 0 walked the CSR and left a partial in EVERY chunk; chunks whose cells live in the
-    // sparse tiles are never written again, so clear the partials before the compact passes
-    if (p == 0 && ts.partial)
-      TB_CUDA(cudaMemsetAsync(s->partial_f.p, 0, s->partial_f.bytes(), st));
     ++launched;
     if (p + 1 >= next_poll || p == npass_max - 1) {
       TB_CUDA(cudaMemcpyAsync(s->h_state.p, s->state.p, sizeof(IceState), cudaMemcpyDeviceToHost, st));
@@ -690,7 +711,7 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
   s->rowsum_ms = 0;
   s->rowsum_launches = 0;
   const int real = hs.all_bad ? 0 : hs.passes_done;
-  for (int p = (real > 1 ? 1 : 0); p < real && p < launched; ++p) {   // pass 0 walks the CSR
+  for (int p = 0; p < real && p < launched; ++p) {
     TB_CUDA(cudaEventElapsedTime(&ms, ev[2 * p], ev[2 * p + 1]));
     s->rowsum_ms += ms;
     ++s->rowsum_launches;
@@ -698,8 +719,7 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
   {   // kernels of this library launched by the call (NCCL's own kernels are not counted)
     const int k1 = csr_walk ? 1 : (s->t_nunits > 0) + (s->n_groups > 0) + (s->n_sparse > 0);
     const int k2 = 2 + (s->world > 1 && s->nrows ? 1 : 0);       // (combine) + reduce + update
-    s->total_launches = 2 /* init, finalize */ + (launched ? 1 + k2 : 0) +
-                        (launched > 1 ? (launched - 1) * (k1 + k2) : 0);
+    s->total_launches = 4 /* init, live, bad partners, finalize */ + launched * (k1 + k2);
   }
   for (auto &e : ev) cudaEventDestroy(e);
   return rc;
@@ -797,6 +817,8 @@ void ice_batch(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max
   k_seg_init<<<(nseg + 255) / 256, 256, 0, st>>>(seg.p, nseg, n_stopped.p);
   const bool csr_walk = use_csr_rowsum(s);
   const TileSums ts = {(!csr_walk && s->t_nunits) ? s->t_partial.p : nullptr, s->t_unit_of_rb.p};
+  prepare_live(s, s->s_full.p + N);
+  if (ts.partial) TB_CUDA(cudaMemsetAsync(s->partial_f.p, 0, s->partial_f.bytes(), st));
   cudaEvent_t e0, e1;
   TB_CUDA(cudaEventCreate(&e0));
   TB_CUDA(cudaEventCreate(&e1));
@@ -804,16 +826,14 @@ void ice_batch(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max
   bool stopped = false;
   int launched = 0;
   for (int p = 0; p < npass_max && !stopped; ++p) {
-    if (p == 0) launch_chunks<M_F64_COUNT>(s, s->x.p, nullptr, s->state.p);
-    else if (csr_walk) launch_chunks<M_F64>(s, s->x.p, nullptr, s->state.p);
+    if (csr_walk) launch_chunks<M_F64>(s, s->x.p, nullptr, s->state.p);
     else launch_rowsum(s, s->x.p, s->state.p);
     k_seg_reduce<<<nseg, 1024, 0, st>>>(s->s_full.p, s->x.p, s->bad.p, s->present.p, seg_off.p, nseg,
-                                        p, iterations, max_dev, trace.p, npass_max, seg.p,
+                                        N, p, iterations, max_dev, trace.p, npass_max, seg.p,
                                         n_stopped.p, s->state.p, s->partial_f.p, s->partial_i.p,
                                         s->row_chunk.p, ts);
     k_seg_update<<<vg, 256, 0, st>>>(s->s_full.p, s->x.p, s->b.p, s->present.p, s->chrom_of.p, N, p,
                                      seg.p);
-    if (p == 0 && ts.partial) TB_CUDA(cudaMemsetAsync(s->partial_f.p, 0, s->partial_f.bytes(), st));
     ++launched;
     if ((p + 1) % 4 == 0 || p == npass_max - 1 || iterations == 0) {
       TB_CUDA(cudaMemcpyAsync(s->h_state.p, s->state.p, sizeof(IceState), cudaMemcpyDeviceToHost, st));
