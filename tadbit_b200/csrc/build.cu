@@ -499,6 +499,7 @@ void finish_layout(tb_store *s) {
   build_tiles(s);
   tm.lap("sparse tiles");
   s->device_bytes = s->t_cells.bytes() + s->t_perm.bytes() + s->t_slice.bytes() + s->t_off.bytes() +
+                    s->t_desc.bytes() + s->t_desc_off.bytes() +
                     s->t_partial.bytes() + s->enc_data.bytes() + s->enc_off.bytes() + s->enc_desc.bytes() + s->rowptr.bytes() + s->col.bytes() + s->val.bytes() + s->chunk_beg.bytes() +
                     s->chunk_row.bytes() + s->row_chunk.bytes() + s->partial_f.bytes() +
                     s->partial_i.bytes() + s->x.bytes() + s->b.bytes() +

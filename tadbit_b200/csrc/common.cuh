@@ -97,8 +97,7 @@ constexpr int kRows = 4;          // dense chunks (rows) one warp walks together
 constexpr int kXPad = 16384;      // zero tail of the gathered vector (panels / windows read past N)
 constexpr int kTileRows = 2048;   // rows of a sparse tile (two per thread of a k_rowsum_tiles CTA)
 constexpr int kTileCols = 4 * kPanel;  // columns of a sparse tile = x window in shared memory (128 KB)
-constexpr int kTileColBits = 14;  // packed tile cell: column offset (14 bits) | value (18 bits)
-constexpr int kTileValBits = 32 - kTileColBits;
+constexpr int kTileValBits = 15;  // packed tile cell: (column offset * 4) << 16 | value, value < 2^15
 
 // chunk encodings of the compact row-sum stream; ENC_T = the cells live in the sparse tiles
 enum { ENC_S32 = 0, ENC_S16 = 1, ENC_D32 = 2, ENC_D16 = 3, ENC_D8 = 4, ENC_T = 5 };
@@ -154,10 +153,15 @@ struct tb_store {
   tb::DevBuf<uint32_t> t_cells;           // packed cells, tile after tile
   tb::DevBuf<int64_t> t_off;              // [t_nrb*t_nwin + 1] first cell of each tile
   tb::DevBuf<uint16_t> t_perm;            // [tiles * kTileRows] local row handled by thread t
-  tb::DevBuf<uint32_t> t_slice;           // [tiles * 33] first cell of each 32-row slice in the tile
+  tb::DevBuf<uint32_t> t_slice;           // [tiles * 65] first cell of each 32-row slice in the tile
   tb::DevBuf<int32_t> t_list;             // non-empty tile ids, grouped by work unit
-  tb::DevBuf<int32_t> t_unit;             // [t_nunits * 4] (row block, list begin, list end, 0)
+  tb::DevBuf<int32_t> t_unit;             // [t_nunits * 4] (row block, list begin, list end, part<<8|parts)
   tb::DevBuf<int32_t> t_unit_of_rb;       // [t_nrb + 1] units of a row block are contiguous
+  tb::DevBuf<int32_t> t_order;            // [t_nunits] unit ids, most expensive first (fetch order)
+  tb::DevBuf<uint2> t_desc;               // copy descriptors: per (unit, warp) the pieces of its cell stream
+  tb::DevBuf<int64_t> t_desc_off;         // [t_nunits * 32 + 1]
+  tb::DevBuf<unsigned int> t_counter;     // [2] unit fetch counters, used alternately by successive launches
+  int t_launches = 0;
   int64_t t_nunits = 0;
   tb::DevBuf<double> t_partial;           // [t_nunits * kTileRows] per-unit row sums
   // scratch

@@ -4,23 +4,36 @@
 // (measured on the genome-wide 5 kb matrix: 13 TB/s of sector traffic, 11 % L1 hit rate).
 // Here the sparse cells are tiled kTileRows x kTileCols: a CTA owns a row block, walks its
 // non-empty tiles and keeps the tile's x window (kTileCols = 16384 doubles, 128 KB) in shared
-// memory -- fetched by cp.async.bulk while the threads already load their tile metadata and
-// first cells -- so every gather is a shared-memory read.  (A wide single buffer beats two
-// narrow ones here: far from the diagonal a tile holds only a few cells per row, and the fixed
-// cost per tile is what matters.)
+// memory, fetched by cp.async.bulk, so every gather is a shared-memory read.
 //
-// Inside a tile the rows are sorted by their number of cells (per-tile permutation) and stored
-// as sliced ELL: 32 consecutive sorted rows form a slice, cell k of lane l sits at
-// slice_base + 32 k + l (one coalesced 128-byte load per warp and k), padded to the slice's
-// longest row; sorting keeps the padding small even where a row has 0-10 cells per tile.
-// A tile has 64 slices for 32 warps: warp w takes slice w and slice 63-w (longest with
-// shortest), which evens out the work between the warps that meet at the tile's barrier.
-// A cell is 32 bits: column offset in the window (14) | count (18).  A thread accumulates its
-// row of the tile in a register and adds it to the row block's accumulators in shared memory
-// (conflict-free: the permutation maps threads to distinct rows).  Row blocks are cut into work
-// units of roughly equal cell count; a unit writes kTileRows partial sums, added per row in
-// unit order by the combine step -> deterministic, no atomics in the pass loop.
+// Layout.  Inside a tile the rows are sorted by their number of cells (per-tile permutation)
+// and stored as sliced ELL: 32 consecutive sorted rows form a slice, padded to the slice's
+// longest row rounded up to 4 cells; cell k of lane l sits at slice_base + 128 (k / 4) + 4 l +
+// k % 4, so a lane reads four of its cells with one 16-byte shared-memory load.  A cell is 32
+// bits, (column offset * 4) << 16 | count with count < 2^15: `cell >> 15` is the byte offset of
+// x_j in the window and `cell & 0xffff` the count.
+//
+// Bank conflicts.  ncu showed the first version of this kernel waiting on the shared-memory
+// pipe (mio_throttle): a random 8-byte gather by 32 lanes costs ~6 wavefronts instead of 2.
+// The order of a row's cells inside a tile is free, so the fill kernel deals them out by bank:
+// at step k lane l prefers a cell whose column is congruent to l + k mod 16 (the 16 lanes of a
+// half-warp then hit 16 different 8-byte bank pairs); cells that find no such step take the
+// steps left over, padding gets the preferred residue with count 0.
+//
+// Streaming.  A warp's cells of one work unit form a stream that does not depend on the x
+// windows.  It is cut at build time into pieces of 8 (or 4) steps, one 8-byte copy descriptor
+// each (where the piece starts, which rows it belongs to, end-of-slice / end-of-tile marks); the
+// warp pulls the pieces through a private two-stage ring in shared memory with cp.async.bulk,
+// two pieces ahead of what it consumes, across slice and tile boundaries.  Warp w takes slices
+// w and 63 - w of every tile (longest with shortest).
+//
+// Scheduling.  Row blocks are cut into work units of roughly equal cost; CTAs (one per SM)
+// fetch them from an atomic counter, most expensive first.  A unit writes kTileRows partial
+// sums, added per row in unit order by the combine step, so results do not depend on which CTA
+// ran which unit: deterministic, no atomics on the data path.
 #include <algorithm>
+#include <numeric>
+#include <type_traits>
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -30,21 +43,31 @@ namespace tb {
 namespace {
 
 constexpr int kTileThreads = kTileRows / 2;
+constexpr int kTileWarps = kTileThreads / 32;
 constexpr int kSlices = kTileRows / 32;
 constexpr int kSliceTab = kSlices + 1;
 constexpr int kRowBits = 11;                               // kTileRows = 2048
 constexpr int kWinBytes = kTileCols * 8;
-constexpr int kTileSmem = kWinBytes + kTileRows * 8 + 64;
-constexpr uint32_t kColMask = (1u << kTileColBits) - 1u;
 static_assert(kTileRows == 1 << kRowBits, "kRowBits");
+static_assert(kSlices == 2 * kTileWarps, "two slices per warp");
+static_assert(kTileCols * 4 <= 65536 && kTileValBits == 15, "cell packing");
+
+// copy descriptor: x = first step of the piece in the cell array (cell index / 32),
+// y = row group (tile * 64 + slice) | steps / 4 << 26 | end-of-slice << 28 | end-of-tile << 29
+constexpr uint32_t kDescGroupMask = (1u << 26) - 1u;
+constexpr uint32_t kDescEndSlice = 1u << 28, kDescEndTile = 1u << 29;
+constexpr int kPieceBytes = 1024;                          // 8 steps x 128 B
+constexpr int kRing = 2;
+constexpr int kTileSmem = kWinBytes + kTileRows * 8 + kTileWarps * kRing * kPieceBytes +
+                          (kTileWarps * kRing + 1) * 8 + 64;
+// fixed cost of a tile in a unit (window load + barrier), in cells of stream
+constexpr int64_t kTileFixedCost = 12000;
 
 __device__ __forceinline__ double u2d(uint32_t v) {
   return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
 }
-__device__ __forceinline__ uint32_t ldg_stream_u32(const void *p) {
-  uint32_t r;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::256B.u32 %0, [%1];" : "=r"(r) : "l"(p));
-  return r;
+__device__ __forceinline__ uint32_t pack_cell(int col_off, int v) {
+  return ((uint32_t)col_off << 18) | (uint32_t)v;
 }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -124,11 +147,11 @@ k_tile_sort(const int32_t *__restrict__ cnt, int64_t nwin, uint16_t *__restrict_
     perm[tile * kTileRows + e] = (uint16_t)row;
     inv[(rb * kTileRows + row) * nwin + w] = (uint16_t)e;
   }
-  if (t == 0) {                                        // slice s is as long as its first row
+  if (t == 0) {               // slice s is as long as its first row, rounded up to 4 steps
     uint32_t run = 0;
     for (int s = 0; s < kSlices; ++s) {
       slice[tile * kSliceTab + s] = run;
-      run += (key[s * 32] >> kRowBits) * 32u;
+      run += (((key[s * 32] >> kRowBits) + 3u) & ~3u) * 32u;
     }
     slice[tile * kSliceTab + kSlices] = run;
     tile_size[tile] = run;
@@ -137,211 +160,321 @@ k_tile_sort(const int32_t *__restrict__ cnt, int64_t nwin, uint16_t *__restrict_
   if ((t & 31) == 0 && real) atomicAdd(totals, real);  // unpadded cells, for the layout report
 }
 
-// one thread per row: for every tile chunk, the number of tile cells of the same row that sit
-// in the chunk's FIRST window but in earlier chunks (a window spans several panels, so dense
-// chunks can split a row's sparse cells of one window over several chunks)
-__global__ void k_tile_rank_base(const int32_t *__restrict__ col, const int64_t *__restrict__ chunk_beg,
-                                 const int64_t *__restrict__ row_chunk, const int4 *__restrict__ desc,
-                                 int64_t nrows, int32_t *__restrict__ base) {
-  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
-       r += (int64_t)gridDim.x * blockDim.x) {
-    int64_t cur_w = -1, cur_n = 0;
-    for (int64_t c = row_chunk[r]; c < row_chunk[r + 1]; ++c) {
-      if ((desc[c].z & 0xff) != ENC_T) continue;
-      const int64_t beg = chunk_beg[c], end = chunk_beg[c + 1];
-      const int64_t wf = col[beg] / kTileCols, wl = col[end - 1] / kTileCols;
-      base[c] = wf == cur_w ? (int32_t)cur_n : 0;
-      int64_t lo = beg, hi = end;                      // first cell of the chunk in window wl
-      while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (col[mid] < wl * kTileCols) lo = mid + 1; else hi = mid;
+// A warp's position in the tile cells of one row: the row's ENC_T chunks in column order.
+struct RowCursor {
+  int64_t c, cend, k, kend;
+  const int64_t *chunk_beg;
+  const int4 *desc;
+  __device__ __forceinline__ void seek() {       // to the next ENC_T chunk at or after c
+    while (c < cend && (desc[c].z & 0xff) != ENC_T) ++c;
+    if (c < cend) { k = chunk_beg[c]; kend = chunk_beg[c + 1]; }
+  }
+  // after a block of `na` (<= 32) cells of the current window was taken: true = the window goes on
+  __device__ __forceinline__ bool advance(int na, const int32_t *__restrict__ col, int32_t whi) {
+    k += na;
+    if (k < kend) return na == 32;               // fewer than 32: the next cell is in a later window
+    ++c;
+    seek();
+    return c < cend && col[k] < whi;
+  }
+};
+
+// per-residue slot tables of one (row, tile) segment, lane r < 16 holds residue r
+struct SlotTables {
+  int served, freebase, fre;
+};
+// slot of the t-th cell (or padding) that found no step of its own residue
+__device__ __forceinline__ void leftover_slot(const SlotTables &tb_, int t, bool want, int &r2, int &m2) {
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int fb = __shfl_sync(0xffffffffu, tb_.freebase, q);
+    const int fr = __shfl_sync(0xffffffffu, tb_.fre, q);
+    const int sv = __shfl_sync(0xffffffffu, tb_.served, q);
+    if (want && t >= fb && t < fb + fr) { r2 = q; m2 = sv + t - fb; }
+  }
+}
+
+// one warp per row: deal the row's cells of every tile out over the steps of its lane
+__global__ void __launch_bounds__(256)
+k_tile_fill(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
+            const int64_t *__restrict__ chunk_beg, const int64_t *__restrict__ row_chunk,
+            const int4 *__restrict__ desc, int64_t nrows, int64_t nwin,
+            const uint16_t *__restrict__ inv, const uint32_t *__restrict__ slice,
+            const int64_t *__restrict__ t_off, uint32_t *__restrict__ cells) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < nrows; r += nwarp) {
+    const int64_t rb = r / kTileRows;
+    RowCursor cur;
+    cur.c = row_chunk[r]; cur.cend = row_chunk[r + 1]; cur.k = cur.kend = 0;
+    cur.chunk_beg = chunk_beg; cur.desc = desc;
+    cur.seek();
+    while (cur.c < cur.cend) {
+      const int32_t w = col[cur.k] / kTileCols, wlo = w * kTileCols, whi = wlo + kTileCols;
+      const int64_t tile = rb * nwin + w;
+      const int p = inv[r * nwin + w], l = p & 31;
+      const uint32_t s0 = slice[tile * kSliceTab + (p >> 5)];
+      const int L = (int)((slice[tile * kSliceTab + (p >> 5) + 1] - s0) >> 5);
+      uint32_t *out = cells + t_off[tile] + s0 + l * 4;
+      const RowCursor start = cur;
+      // sweep 1: cells per residue (lane r < 16 counts residue r)
+      int b = 0;
+      for (;;) {
+        const int64_t idx = cur.k + lane;
+        int32_t cc = idx < cur.kend ? col[idx] : 0x7fffffff;
+        const bool act = cc < whi;
+        const int res = cc & 15;
+        const int na = __popc(__ballot_sync(0xffffffffu, act));
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const unsigned m = __ballot_sync(0xffffffffu, act && res == q);
+          if (lane == q) b += __popc(m);
+        }
+        if (!cur.advance(na, col, whi)) break;
       }
-      cur_n = (wl == cur_w ? cur_n : 0) + (end - lo);
-      cur_w = wl;
+      // steps of residue q for this lane: k = ((q - l) & 15) + 16 m, m < req
+      const int d = (lane - l) & 15;
+      const int req = (lane < 16 && d < L) ? (L - 1 - d) / 16 + 1 : 0;
+      const int bb = lane < 16 ? b : 0;
+      SlotTables tabs;
+      tabs.served = min(bb, req);
+      const int left = bb - tabs.served;
+      tabs.fre = req - tabs.served;
+      int li = left, fi = tabs.fre;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, li, o), f = __shfl_up_sync(0xffffffffu, fi, o);
+        if (lane >= o) { li += a; fi += f; }
+      }
+      const int leftbase = li - left;
+      tabs.freebase = fi - tabs.fre;
+      const int total_left = __shfl_sync(0xffffffffu, li, 31);
+      const int total_free = __shfl_sync(0xffffffffu, fi, 31);
+      // sweep 2: place the cells
+      cur = start;
+      int run = 0;
+      for (;;) {
+        const int64_t idx = cur.k + lane;
+        int32_t cc = idx < cur.kend ? col[idx] : 0x7fffffff;
+        const bool act = cc < whi;
+        const int res = cc & 15;
+        const int na = __popc(__ballot_sync(0xffffffffu, act));
+        const unsigned same = __match_any_sync(0xffffffffu, act ? res : 16 + lane);
+        const int m = __shfl_sync(0xffffffffu, run, res) + __popc(same & lt);
+        const int sv = __shfl_sync(0xffffffffu, tabs.served, res);
+        const int lb = __shfl_sync(0xffffffffu, leftbase, res);
+        int r2 = res, m2 = m;
+        leftover_slot(tabs, lb + m - sv, act && m >= sv, r2, m2);
+        if (act) {
+          const int ks = ((r2 - l) & 15) + 16 * m2;
+          out[(ks >> 2) * 128 + (ks & 3)] = pack_cell(cc - wlo, val[idx]);
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const unsigned mq = __ballot_sync(0xffffffffu, act && res == q);
+          if (lane == q) run += __popc(mq);
+        }
+        if (!cur.advance(na, col, whi)) break;
+      }
+      // padding: the remaining free steps read x at their preferred residue, count 0
+      for (int t0 = total_left; t0 < total_free; t0 += 32) {
+        const int t = t0 + lane;
+        int r2 = 0, m2 = 0;
+        leftover_slot(tabs, t, t < total_free, r2, m2);
+        if (t < total_free) {
+          const int ks = ((r2 - l) & 15) + 16 * m2;
+          out[(ks >> 2) * 128 + (ks & 3)] = pack_cell(r2, 0);
+        }
+      }
     }
   }
 }
 
+// steps [kb, kb + len) of a slice that belong to part `part` of `parts` (multiples of 4)
+__device__ __forceinline__ int part_range(uint32_t s0, uint32_t s1, int part, int parts, int &kb) {
+  const int64_t quads = (s1 - s0) >> 7;                    // steps / 4
+  kb = (int)(quads * part / parts) * 4;
+  return (int)(quads * (part + 1) / parts) * 4 - kb;
+}
+
+// one thread per (unit, warp): count / write the copy descriptors of the warp's cell stream
+template <bool FILL>
 __global__ void __launch_bounds__(256)
-k_tile_fill(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
-            const int64_t *__restrict__ chunk_beg, const int32_t *__restrict__ chunk_row,
-            const int4 *__restrict__ desc, const int32_t *__restrict__ rank_base, int64_t nchunks,
-            int64_t nwin, const uint16_t *__restrict__ inv, const uint32_t *__restrict__ slice,
-            const int64_t *__restrict__ t_off, uint32_t *__restrict__ cells) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t c = warp; c < nchunks; c += nwarp) {
-    if ((desc[c].z & 0xff) != ENC_T) continue;
-    const int64_t beg = chunk_beg[c], end = chunk_beg[c + 1], row = chunk_row[c];
-    const int64_t rb = row / kTileRows;
-    const int64_t wfirst = col[beg] / kTileCols;
-    const int32_t base = rank_base[c];
-    for (int64_t k = beg + lane; k < end; k += 32) {
-      const int32_t cc = col[k];
-      const int64_t w = cc / kTileCols;
-      int64_t lo = beg, hi = k;                        // first cell of this chunk in window w
-      const int32_t wstart = (int32_t)(w * kTileCols);
-      while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (col[mid] < wstart) lo = mid + 1; else hi = mid;
+k_tile_desc(const int4 *__restrict__ unit, const int32_t *__restrict__ list,
+            const uint32_t *__restrict__ slice, const int64_t *__restrict__ t_off, int64_t nunits,
+            int64_t *__restrict__ count, const int64_t *__restrict__ desc_off, uint2 *__restrict__ desc) {
+  const int64_t id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (id >= nunits * kTileWarps) return;
+  const int w = (int)(id % kTileWarps);
+  const int4 un = unit[id / kTileWarps];
+  const int part = un.w >> 8, parts = un.w & 0xff;
+  uint2 *o = FILL ? desc + desc_off[id] : nullptr;
+  int64_t n_out = 0;
+  for (int j = un.y; j < un.z; ++j) {
+    const int64_t tile = list[j];
+    const uint32_t *st = slice + tile * kSliceTab;
+    int kb[2], len[2];
+    const int sl[2] = {w, kSlices - 1 - w};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) len[h] = part_range(st[sl[h]], st[sl[h] + 1], part, parts, kb[h]);
+    if (len[0] + len[1] == 0) {
+      if (FILL) o[n_out] = make_uint2(0u, (uint32_t)(tile * kSlices + w) | kDescEndTile);
+      ++n_out;
+      continue;
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int pieces = (len[h] + 7) / 8;
+      if (FILL) {
+        const int64_t first = (t_off[tile] + st[sl[h]]) / 32 + kb[h];
+        for (int i = 0; i < pieces; ++i) {
+          const int steps = min(8, len[h] - 8 * i);
+          uint32_t y = (uint32_t)(tile * kSlices + sl[h]) | ((uint32_t)(steps / 4) << 26);
+          if (i == pieces - 1) {
+            y |= kDescEndSlice;
+            if (h == 1 || len[1] == 0) y |= kDescEndTile;
+          }
+          o[n_out + i] = make_uint2((uint32_t)(first + 8 * i), y);
+        }
       }
-      const int64_t rank = k - lo + (w == wfirst ? base : 0), tile = rb * nwin + w;
-      const int t = inv[row * nwin + w];
-      cells[t_off[tile] + slice[tile * kSliceTab + (t >> 5)] + rank * 32 + (t & 31)] =
-          (uint32_t)(cc - wstart) | ((uint32_t)val[k] << kTileColBits);
+      n_out += pieces;
     }
   }
+  if (!FILL) count[id] = n_out;
 }
 
 // ---- the pass kernel --------------------------------------------------------------------------
-__device__ __forceinline__ double cell_term(uint32_t c, const double *xw) {
-  return u2d(c >> kTileColBits) * xw[c & kColMask];
+__device__ __forceinline__ double cell_term(uint32_t c, const uint8_t *xw) {
+  return u2d(c & 0xffffu) * *reinterpret_cast<const double *>(xw + (c >> 15));
 }
 
-// A warp's cells of one unit form a stream that does not depend on the x windows: slice a of
-// tile 0, slice b of tile 0, slice a of tile 1, ...  The warp pulls that stream through a private
-// ring in shared memory with cp.async.bulk (pieces of up to kPiece k-steps = 1 KB), the producer
-// cursor running kRing pieces ahead of the consumer cursor across slice and tile boundaries, so
-// HBM latency is covered by bytes in flight in the copy engine instead of registers.
-constexpr int kPiece = 8;                                  // k-steps (128 B each) per ring stage
-constexpr int kRing = 2;                                   // stages per warp
-constexpr int kRingBytes = kRing * kPiece * 128;           // 2 KB per warp
-constexpr int kTileWarps = kTileThreads / 32;
-constexpr int kTileSmemRing = kWinBytes + kTileRows * 8 + kTileWarps * kRingBytes + kTileWarps * kRing * 8 + 64;
-
-struct SliceCur {            // a warp's position in its cell stream
-  int j, which, k, len;
-  const uint32_t *p;
-};
-
-__device__ __forceinline__ void cur_load(SliceCur &c, const int32_t *__restrict__ list, int i0, int n,
-                                         const uint32_t *__restrict__ slice,
-                                         const int64_t *__restrict__ t_off,
-                                         const uint32_t *__restrict__ cells, int sa, int sb, int part,
-                                         int parts) {
-  // move to the next non-empty slice at or after (j, which); len = 0 and j = n when exhausted
-  while (c.j < n) {
-    const int64_t tile = list[i0 + c.j];
-    const int s = c.which ? sb : sa;
-    const uint32_t s0 = slice[tile * kSliceTab + s], s1 = slice[tile * kSliceTab + s + 1];
-    const int full = (int)((s1 - s0) >> 5);
-    const int kb = full * part / parts;
-    c.len = full * (part + 1) / parts - kb;
-    c.k = 0;
-    c.p = cells + t_off[tile] + s0 + kb * 32;
-    if (c.len > 0) return;
-    if (c.which) { c.which = 0; ++c.j; } else c.which = 1;
+template <int QUADS>
+__device__ __forceinline__ void consume(const uint8_t *stage, int lane, const uint8_t *xw, double &a0,
+                                        double &a1) {
+  const uint4 *rp = reinterpret_cast<const uint4 *>(stage) + lane;
+  uint4 q[QUADS];
+#pragma unroll
+  for (int g = 0; g < QUADS; ++g) q[g] = rp[g * 32];
+#pragma unroll
+  for (int g = 0; g < QUADS; ++g) {
+    a0 += cell_term(q[g].x, xw);
+    a1 += cell_term(q[g].y, xw);
+    a0 += cell_term(q[g].z, xw);
+    a1 += cell_term(q[g].w, xw);
   }
-  c.len = 0;
-}
-
-__device__ __forceinline__ void cur_advance(SliceCur &c, int steps, const int32_t *__restrict__ list,
-                                            int i0, int n, const uint32_t *__restrict__ slice,
-                                            const int64_t *__restrict__ t_off,
-                                            const uint32_t *__restrict__ cells, int sa, int sb, int part,
-                                            int parts) {
-  c.k += steps;
-  if (c.k < c.len) return;
-  if (c.which) { c.which = 0; ++c.j; } else c.which = 1;
-  cur_load(c, list, i0, n, slice, t_off, cells, sa, sb, part, parts);
 }
 
 __global__ void __launch_bounds__(kTileThreads, 1)
-k_rowsum_tiles(const uint32_t *__restrict__ cells, const int64_t *__restrict__ t_off,
-               const uint16_t *__restrict__ perm, const uint32_t *__restrict__ slice,
-               const int32_t *__restrict__ list, const int4 *__restrict__ unit, int64_t nunits,
-               int64_t nwin, const double *__restrict__ x, double *__restrict__ partial,
-               const IceState *__restrict__ state) {
+k_rowsum_tiles(const uint32_t *__restrict__ cells, const uint2 *__restrict__ desc,
+               const int64_t *__restrict__ desc_off, const uint16_t *__restrict__ perm,
+               const int32_t *__restrict__ list, const int4 *__restrict__ unit,
+               const int32_t *__restrict__ order, unsigned int nunits, int64_t nwin,
+               const double *__restrict__ x, double *__restrict__ partial,
+               unsigned int *__restrict__ counter, int cur, const IceState *__restrict__ state) {
+  // the next launch fetches from the other counter
+  if (blockIdx.x == 0 && threadIdx.x == 0) counter[cur ^ 1] = 0u;
   if (state && state->stopped) return;
   extern __shared__ __align__(128) uint8_t smem[];
-  double *xw = reinterpret_cast<double *>(smem);                       // [kTileCols]
+  uint8_t *xw = smem;                                                   // [kTileCols] doubles
   double *acc = reinterpret_cast<double *>(smem + kWinBytes);          // [kTileRows]
   const int t = threadIdx.x, lane = t & 31, wic = t >> 5;
-  uint8_t *ring = smem + kWinBytes + kTileRows * 8 + wic * kRingBytes;
+  uint8_t *ring = smem + kWinBytes + kTileRows * 8 + wic * (kRing * kPieceBytes);
   const uint32_t ring_u32 = smem_u32(ring);
-  const uint32_t bars = smem_u32(smem + kWinBytes + kTileRows * 8 + kTileWarps * kRingBytes);
+  uint8_t *tail = smem + kWinBytes + kTileRows * 8 + kTileWarps * kRing * kPieceBytes;
+  const uint32_t bars = smem_u32(tail);
   const uint32_t wbar = bars + kTileWarps * kRing * 8;                 // window barrier
   const uint32_t rbar = bars + wic * kRing * 8;                        // this warp's ring barriers
-  const int sa = wic, sb = kSlices - 1 - wic;          // longest slices paired with shortest
+  volatile unsigned int *s_next = reinterpret_cast<volatile unsigned int *>(tail + (kTileWarps * kRing + 1) * 8);
   if (t == 0) mbar_init(wbar, 1);
   if (lane == 0) {
+#pragma unroll
     for (int q = 0; q < kRing; ++q) mbar_init(rbar + 8 * q, 1);
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncthreads();
   uint32_t wparity = 0, rparity = 0;                    // rparity bit q = parity of ring stage q
-  for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+  for (;;) {
+    if (t == 0) *s_next = atomicAdd(&counter[cur], 1u);
+    __syncthreads();
+    const unsigned int ui = *s_next;
+    if (ui >= nunits) break;
+    const int u = order[ui];
     const int4 un = unit[u];
     const int i0 = un.y, n = un.z - un.y;
-    const int part = un.w >> 8, parts = un.w & 0xff;   // a heavy tile is split over several units
     acc[t] = 0.0;
     acc[t + kTileThreads] = 0.0;
-    // producer: runs ahead over this warp's stream of the whole unit
-    SliceCur pc;
-    pc.j = 0; pc.which = 0;
-    cur_load(pc, list, i0, n, slice, t_off, cells, sa, sb, part, parts);
-    auto issue = [&](int stage) {
-      if (pc.len == 0) return;                          // stream exhausted
-      const int steps = min(kPiece, pc.len - pc.k);
-      if (lane == 0) {
-        mbar_expect_tx(rbar + 8 * stage, steps * 128);
-        bulk_g2s(ring_u32 + stage * kPiece * 128, pc.p + pc.k * 32, steps * 128, rbar + 8 * stage);
+    const int64_t dbeg = desc_off[(int64_t)u * kTileWarps + wic];
+    const int nd = (int)(desc_off[(int64_t)u * kTileWarps + wic + 1] - dbeg);
+    const uint2 *dp = desc + dbeg;
+    // start the copy of piece `e` into `stage`; fetch the rows of its slice if it ends one
+    auto issue = [&](int stage, const uint2 &e, uint32_t &row) {
+      const uint32_t quads = (e.y >> 26) & 3u;
+      if (quads && lane == 0) {
+        mbar_expect_tx(rbar + 8 * stage, quads * 512u);
+        bulk_g2s(ring_u32 + stage * kPieceBytes, cells + (size_t)e.x * 32, quads * 512u, rbar + 8 * stage);
       }
-      cur_advance(pc, steps, list, i0, n, slice, t_off, cells, sa, sb, part, parts);
+      if (e.y & kDescEndSlice) row = perm[(size_t)(e.y & kDescGroupMask) * 32 + lane];
     };
-#pragma unroll
-    for (int q = 0; q < kRing; ++q) issue(q);
-    int stage = 0;
+    uint2 e0 = dp[0], e1 = make_uint2(0u, 0u);
+    uint32_t row0 = 0, row1 = 0;
+    issue(0, e0, row0);
+    if (nd > 1) { e1 = dp[1]; issue(1, e1, row1); }
+    uint2 pf = nd > 2 ? dp[2] : make_uint2(0u, 0u);     // descriptor two ahead of the consumer
+    int ci = 0, stage = 0;
     for (int j = 0; j < n; ++j) {
-      const int64_t tile = list[i0 + j];
       __syncthreads();                       // the window of the previous tile is consumed
       if (t == 0) {                          // 128 KB window, four 32 KB bulk copies
-        const double *src = x + (tile % nwin) * kTileCols;
+        const double *src = x + (list[i0 + j] % nwin) * kTileCols;
         mbar_expect_tx(wbar, kWinBytes);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           bulk_g2s(smem_u32(xw) + q * (kWinBytes / 4), src + q * (kTileCols / 4), kWinBytes / 4, wbar);
       }
-      const uint32_t *st = slice + tile * kSliceTab;
-      int len[2], row[2];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int s = h ? sb : sa;
-        const int full = (int)((st[s + 1] - st[s]) >> 5);
-        len[h] = full * (part + 1) / parts - full * part / parts;
-        row[h] = perm[tile * kTileRows + s * 32 + lane];
-      }
       mbar_wait(wbar, wparity);
       wparity ^= 1u;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        double a0 = 0.0, a1 = 0.0;
-        for (int k = 0; k < len[h]; k += kPiece) {
-          const int steps = min(kPiece, len[h] - k);
-          mbar_wait(rbar + 8 * stage, (rparity >> stage) & 1u);
-          rparity ^= 1u << stage;
-          const uint32_t *rp = reinterpret_cast<const uint32_t *>(ring + stage * kPiece * 128) + lane;
-          if (steps == kPiece) {
-#pragma unroll
-            for (int q = 0; q < kPiece; q += 2) {
-              a0 += cell_term(rp[q * 32], xw);
-              a1 += cell_term(rp[(q + 1) * 32], xw);
-            }
-          } else {
-            for (int q = 0; q < steps; ++q) a0 += cell_term(rp[q * 32], xw);
-          }
-          __syncwarp();                      // every lane has read this stage
-          issue(stage);
-          stage = (stage + 1 == kRing) ? 0 : stage + 1;
+      double a0 = 0.0, a1 = 0.0;
+      // one piece of the stream; the ring stage is a compile-time constant (two copies of the code)
+      auto step = [&](auto stage_c) -> bool {
+        constexpr int ST = decltype(stage_c)::value;
+        uint2 &e = ST ? e1 : e0;
+        uint32_t &erow = ST ? row1 : row0;
+        const uint32_t meta = e.y, row = erow;
+        const uint32_t quads = (meta >> 26) & 3u;
+        if (quads) {
+          mbar_wait(rbar + 8 * ST, (rparity >> ST) & 1u);
+          rparity ^= 1u << ST;
+          const uint8_t *rs = ring + ST * kPieceBytes;
+          if (quads == 2) consume<2>(rs, lane, xw, a0, a1);
+          else consume<1>(rs, lane, xw, a0, a1);
         }
-        if (len[h]) acc[row[h]] += a0 + a1;  // distinct rows per thread: no conflict
+        __syncwarp();                        // every lane has read this stage
+        if (meta & kDescEndSlice) {          // distinct rows per thread of a tile: no conflict
+          acc[row] += a0 + a1;
+          a0 = a1 = 0.0;
+        }
+        if (ci + 2 < nd) {
+          e = pf;
+          issue(ST, e, erow);
+          if (ci + 3 < nd) pf = dp[ci + 3];
+        }
+        ++ci;
+        return (meta & kDescEndTile) != 0u;
+      };
+      bool done = false;
+      if (stage) { done = step(std::integral_constant<int, 1>()); stage = 0; }
+      while (!done) {
+        done = step(std::integral_constant<int, 0>());
+        stage = 1;
+        if (done) break;
+        done = step(std::integral_constant<int, 1>());
+        stage = 0;
       }
     }
     __syncthreads();
-    partial[u * kTileRows + t] = acc[t];
-    partial[u * kTileRows + t + kTileThreads] = acc[t + kTileThreads];
-    __syncthreads();                          // acc is re-zeroed at the top of the next unit
+    partial[(int64_t)u * kTileRows + t] = acc[t];
+    partial[(int64_t)u * kTileRows + t + kTileThreads] = acc[t + kTileThreads];
+    __syncthreads();                          // acc is re-zeroed, s_next rewritten for the next unit
   }
 }
 
@@ -356,11 +489,12 @@ inline int grid_1d(int64_t n, int threads, int sm_count, int per_sm) {
 void build_tiles(tb_store *s) {
   cudaStream_t st = s->stream;
   s->t_nrb = s->t_nwin = s->t_ncells = s->t_npadded = s->t_nunits = 0;
+  s->t_launches = 0;
   if (s->enc_chunks[ENC_T] == 0) return;
   const int64_t nrb = (s->nrows + kTileRows - 1) / kTileRows;
   const int64_t nwin = (s->nbins + kTileCols - 1) / kTileCols;
   const int64_t ntiles = nrb * nwin;
-  TB_REQUIRE(ntiles < 2147483647LL, "too many sparse tiles");
+  TB_REQUIRE(ntiles < (1LL << 20), "too many sparse tiles");
   s->t_nrb = nrb;
   s->t_nwin = nwin;
   DevBuf<int32_t> cnt;
@@ -399,27 +533,28 @@ void build_tiles(tb_store *s) {
   cnt.release();
   s->t_cells.alloc(s->t_npadded ? s->t_npadded : 1);
   TB_CUDA(cudaMemsetAsync(s->t_cells.p, 0, s->t_cells.bytes(), st));       // padding = (col 0, count 0)
-  DevBuf<int32_t> rank_base;
-  rank_base.alloc(s->nchunks + 1);
-  TB_CUDA(cudaMemsetAsync(rank_base.p, 0, rank_base.bytes(), st));
-  k_tile_rank_base<<<grid_1d(s->nrows, 256, s->sm_count, 16), 256, 0, st>>>(
-      s->col.p, s->chunk_beg.p, s->row_chunk.p, s->enc_desc.p, s->nrows, rank_base.p);
-  k_tile_fill<<<cg, 256, 0, st>>>(s->col.p, s->val.p, s->chunk_beg.p, s->chunk_row.p, s->enc_desc.p,
-                                  rank_base.p, s->nchunks, nwin, inv.p, s->t_slice.p, s->t_off.p,
-                                  s->t_cells.p);
-  // Work units: each row block's non-empty tiles, cut into runs of about equal stored cells so
-  // that there are ~16 units per SM whatever the number of row blocks (1 GPU or a 1/8 shard).
-  // A tile heavier than that (the ones on the diagonal) is split: `parts` units each take a
-  // share of every slice of the tile.  unit = (row block, list begin, list end, part<<8|parts).
-  const double target = (double)s->t_npadded / (16.0 * s->sm_count) + 1.0;
+  k_tile_fill<<<grid_1d(s->nrows * 32, 256, s->sm_count, 8), 256, 0, st>>>(
+      s->col.p, s->val.p, s->chunk_beg.p, s->row_chunk.p, s->enc_desc.p, s->nrows, nwin, inv.p,
+      s->t_slice.p, s->t_off.p, s->t_cells.p);
+  // Work units: each row block's non-empty tiles, cut into runs of about equal cost so that there
+  // are ~16 units per SM whatever the number of row blocks (1 GPU or a 1/8 shard).  A tile heavier
+  // than that (the ones on the diagonal) is split: `parts` units each take a share of every
+  // slice of the tile.  unit = (row block, list begin, list end, part<<8|parts).
+  int64_t nonempty = 0;
+  for (int64_t q = 0; q < ntiles; ++q) nonempty += h_size[q] != 0;
+  const double total_cost = (double)s->t_npadded + (double)kTileFixedCost * (double)nonempty;
+  const double target = total_cost / (16.0 * s->sm_count) + 1.0;
   std::vector<int32_t> list, units, unit_of_rb(nrb + 1, 0);
+  std::vector<double> cost;
   for (int64_t rb = 0; rb < nrb; ++rb) {
     unit_of_rb[rb] = (int32_t)(units.size() / 4);
-    int64_t run = 0;
+    double run = 0;
     int32_t begin = (int32_t)list.size();
     auto flush = [&]() {
-      if ((int32_t)list.size() > begin)
+      if ((int32_t)list.size() > begin) {
         units.insert(units.end(), {(int32_t)rb, begin, (int32_t)list.size(), 1});
+        cost.push_back(run);
+      }
       begin = (int32_t)list.size();
       run = 0;
     };
@@ -431,30 +566,63 @@ void build_tiles(tb_store *s) {
         int parts = (int)((double)sz / target + 0.999);
         if (parts > 64) parts = 64;
         list.push_back((int32_t)(rb * nwin + w));
-        for (int p = 0; p < parts; ++p)
+        for (int p = 0; p < parts; ++p) {
           units.insert(units.end(), {(int32_t)rb, begin, begin + 1, (p << 8) | parts});
+          cost.push_back((double)sz / parts + (double)kTileFixedCost);
+        }
         begin = (int32_t)list.size();
         continue;
       }
       list.push_back((int32_t)(rb * nwin + w));
-      run += sz;
-      if ((double)run >= target) flush();
+      run += (double)(sz + kTileFixedCost);
+      if (run >= target) flush();
     }
     flush();
   }
   unit_of_rb[nrb] = (int32_t)(units.size() / 4);
   s->t_nunits = (int64_t)units.size() / 4;
+  std::vector<int32_t> order(s->t_nunits);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return cost[a] > cost[b]; });
   s->t_list.alloc(list.size() ? list.size() : 1);
   s->t_unit.alloc(units.size() ? units.size() : 4);
+  s->t_order.alloc(s->t_nunits ? s->t_nunits : 1);
   s->t_unit_of_rb.alloc(nrb + 1);
   s->t_partial.alloc(s->t_nunits ? s->t_nunits * kTileRows : 1);
+  s->t_counter.alloc(2);
   if (!list.empty())
     TB_CUDA(cudaMemcpy(s->t_list.p, list.data(), list.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-  if (!units.empty())
+  if (!units.empty()) {
     TB_CUDA(cudaMemcpy(s->t_unit.p, units.data(), units.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    TB_CUDA(cudaMemcpy(s->t_order.p, order.data(), order.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
   TB_CUDA(cudaMemcpy(s->t_unit_of_rb.p, unit_of_rb.data(), (nrb + 1) * sizeof(int32_t),
                      cudaMemcpyHostToDevice));
   TB_CUDA(cudaMemsetAsync(s->t_partial.p, 0, s->t_partial.bytes(), st));
+  TB_CUDA(cudaMemsetAsync(s->t_counter.p, 0, s->t_counter.bytes(), st));
+  // copy descriptors of every (unit, warp) stream
+  const int64_t nstreams = s->t_nunits * kTileWarps;
+  s->t_desc_off.alloc(nstreams + 1);
+  if (nstreams) {
+    DevBuf<int64_t> dcount;
+    dcount.alloc(nstreams + 1);
+    TB_CUDA(cudaMemsetAsync(dcount.p, 0, dcount.bytes(), st));
+    const unsigned dg = (unsigned)((nstreams + 255) / 256);
+    const int4 *d_unit = reinterpret_cast<const int4 *>(s->t_unit.p);
+    k_tile_desc<false><<<dg, 256, 0, st>>>(d_unit, s->t_list.p, s->t_slice.p, s->t_off.p, s->t_nunits,
+                                           dcount.p, nullptr, nullptr);
+    size_t tmp_bytes = 0;
+    TB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, dcount.p, s->t_desc_off.p, nstreams + 1, st));
+    DevBuf<uint8_t> tmp;
+    tmp.alloc(tmp_bytes ? tmp_bytes : 1);
+    TB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, dcount.p, s->t_desc_off.p, nstreams + 1, st));
+    int64_t ndesc = 0;
+    TB_CUDA(cudaMemcpyAsync(&ndesc, s->t_desc_off.p + nstreams, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    s->t_desc.alloc(ndesc ? ndesc : 1);
+    k_tile_desc<true><<<dg, 256, 0, st>>>(d_unit, s->t_list.p, s->t_slice.p, s->t_off.p, s->t_nunits,
+                                          nullptr, s->t_desc_off.p, s->t_desc.p);
+  }
   TB_CUDA(cudaStreamSynchronize(st));
 }
 
@@ -462,13 +630,16 @@ void launch_rowsum_tiles(tb_store *s, const double *x, const IceState *state) {
   if (s->t_nunits == 0) return;
   static bool attr_set[64] = {false};            // per device: the attribute is per context
   if (!attr_set[s->device & 63]) {
-    TB_CUDA(cudaFuncSetAttribute(k_rowsum_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemRing));
+    TB_CUDA(cudaFuncSetAttribute(k_rowsum_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
     attr_set[s->device & 63] = true;
   }
   const int grid = (int)(s->t_nunits < s->sm_count ? s->t_nunits : s->sm_count);
-  k_rowsum_tiles<<<grid, kTileThreads, kTileSmemRing, s->stream>>>(
-      s->t_cells.p, s->t_off.p, s->t_perm.p, s->t_slice.p, s->t_list.p,
-      reinterpret_cast<const int4 *>(s->t_unit.p), s->t_nunits, s->t_nwin, x, s->t_partial.p, state);
+  const int cur = s->t_launches & 1;
+  ++s->t_launches;
+  k_rowsum_tiles<<<grid, kTileThreads, kTileSmem, s->stream>>>(
+      s->t_cells.p, s->t_desc.p, s->t_desc_off.p, s->t_perm.p, s->t_list.p,
+      reinterpret_cast<const int4 *>(s->t_unit.p), s->t_order.p, (unsigned int)s->t_nunits, s->t_nwin, x,
+      s->t_partial.p, s->t_counter.p, cur, state);
 }
 
 }  // namespace tb

@@ -52,7 +52,7 @@ def main():
     run_path(syn, chroms, "synthetic")
 
     # the same cells through the COO constructor: sorted input, then shuffled input with a few
-    # huge values (D32 / S32 / overflow cells) and a negative one (no tiles for that chunk)
+    # huge values (S32 / S16 chunks, overflow cells of dense panels) and negative ones
     rows, cols, vals = syn.export_upper()
     coo = ContactStore.from_coo(n, rows, cols, vals, chromosomes=chroms)
     a = run_path(coo, chroms, "coo-sorted")
@@ -63,7 +63,8 @@ def main():
     v2[big[:100]] = 70000 + rng.randint(0, 1000, 100)
     v2[big[100:150]] = 300000 + rng.randint(0, 1000, 50)
     v2[big[150:190]] = 1 << 20
-    v2[big[190:]] = -3
+    v2[big[190:195]] = -3
+    v2[big[195:]] = 40000 + rng.randint(0, 1000, 5)
     shuf = ContactStore.from_coo(n, rows[perm], cols[perm], v2[perm], chromosomes=chroms)
     run_path(shuf, chroms, "coo-shuf")
     r2, c2, w2 = shuf.export_upper()

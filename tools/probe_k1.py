@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""Build one synthetic workload on cuda:0 and print the K1 split (total, sparse tiles, dense
+kernels) from tb_probe_rowsum, the stream layout and the TB_TIMING build stages.
+
+    python tools/probe_k1.py c3 [reps]
+"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from tadbit_b200 import ContactStore, HiC_data, workloads  # noqa: E402
+
+
+def main():
+    name = sys.argv[1] if len(sys.argv) > 1 else "c3"
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+    wl = workloads.workload(name)
+    t0 = time.time()
+    store = ContactStore.synthetic(wl["size"], wl["params"], chromosomes=wl["chromosomes"])
+    t1 = time.time()
+    lay = store.layout()
+    print("workload %s: N=%d nnz_upper=%d build %.2f s" % (name, wl["size"], store.info()["nnz_upper"], t1 - t0))
+    print("layout", lay)
+    store.probe_rowsum(2)
+    total, tiles, dense = store.probe_rowsum(reps)
+    print("K1 ms: total %.3f  tiles %.3f  dense %.3f" % (total, tiles, dense))
+    hic = HiC_data.from_store(store, chromosomes=wl["chromosomes"])
+    hic.filter_columns(silent=True)
+    t0 = time.time()
+    hic.normalize_hic(iterations=100, max_dev=1e-5, silent=True)
+    t1 = time.time()
+    tm = store.ice_timing()
+    print("normalize_hic %.1f ms wall; loop %.1f ms, %d passes, K1 %.3f ms/pass"
+          % ((t1 - t0) * 1e3, tm["loop_ms"], len(hic.last_trace),
+             tm["rowsum_ms"] / max(tm["rowsum_launches"], 1)))
+    bias = hic.bias.to_array().copy()
+    store.set_option("rowsum", "csr")
+    hic.normalize_hic(iterations=100, max_dev=1e-5, silent=True)
+    import numpy as np
+    print("compact vs csr bias max rel diff %.2e" % float(np.max(np.abs(hic.bias.to_array() - bias) / np.abs(bias))))
+
+
+if __name__ == "__main__":
+    main()
