@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtadbit_b200.so")
+# TADBIT_B200_LIB: explicit path of the library (a build variant under test)
+LIB_PATH = os.environ.get("TADBIT_B200_LIB") or os.path.join(_HERE, "libtadbit_b200.so")
 
 TB_OK, TB_ERR_ARG, TB_ERR_CUDA, TB_ERR_ALL_BAD, TB_ERR_NCCL, TB_ERR_STATE = range(6)
 TB_MEM_HOST, TB_MEM_DEVICE = 0, 1

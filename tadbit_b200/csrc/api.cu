@@ -329,6 +329,7 @@ int tb_store_layout(const tb_store *s, int64_t out[16]) {
   out[10] = s->t_npadded;
   out[11] = s->t_nunits;
   out[12] = s->n_overflow;
+  out[14] = s->n_overflow_tiled;
   out[13] = s->t_nunits ? (int64_t)(s->t_npadded * 4 + s->t_perm.bytes() + s->t_desc.bytes() + s->t_desc_off.bytes()) : 0;
   return TB_OK;
 }

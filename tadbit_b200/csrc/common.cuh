@@ -109,9 +109,15 @@ struct GroupRec {
   int32_t id[kRows];       // chunk id (index of its partial), -1 = empty seat
   int32_t c0;              // first column of the panel
   int32_t nsub;            // kSub-byte sub-blocks per row
-  int32_t enc;             // ENC_D32 / ENC_D16 / ENC_D8
-  int32_t ovf;             // some seat carries overflow cells
+  int32_t enc;             // ENC_D32 / ENC_D16 / ENC_D8 | (some seat carries overflow cells) << 8
+  int32_t seg_end;         // first group after this one that sits in another panel
+  int32_t novf[kRows];     // overflow cells of each seat
 };
+static_assert(sizeof(GroupRec) == 64, "GroupRec is read as four int4");
+#ifndef TB_DENSE_WARPS
+#define TB_DENSE_WARPS 24
+#endif
+constexpr int kDenseWarps = TB_DENSE_WARPS;   // warps per CTA of k_rowsum_dense (one CTA per SM)
 
 }  // namespace tb
 
@@ -143,7 +149,11 @@ struct tb_store {
   int64_t n_sparse = 0, n_dense = 0;
   tb::DevBuf<tb::GroupRec> groups;        // [n_groups] kRows dense chunks of one panel each
   int64_t n_groups = 0;
-  int64_t n_overflow = 0;                 // cells kept outside their dense chunk's value width
+  tb::DevBuf<int32_t> group_range;        // [n_dense_ctas + 1] contiguous groups of each k_rowsum_dense CTA
+  int n_dense_ctas = 0;
+  int64_t n_overflow = 0;                 // cells kept in a list behind their dense chunk (value out of range)
+  tb::DevBuf<uint16_t> enc_tovf;          // [nchunks] cells of a D8 chunk (255 < v < 2^15) moved to the tiles
+  int64_t n_overflow_tiled = 0;
   int64_t enc_bytes = 0;
   int64_t enc_chunks[6] = {0, 0, 0, 0, 0, 0};  // chunks per encoding
   // sparse tiles (tiles.cu): cells of ENC_T chunks, kTileRows x kTileCols tiles, rows of a tile

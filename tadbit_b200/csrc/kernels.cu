@@ -865,7 +865,8 @@ void ice_batch(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max
 
 // Work of every owned row in the two K1 kernels: slots of its dense chunks, cells in sparse tiles.
 namespace {
-__global__ void k_row_work(const int4 *__restrict__ desc, const int64_t *__restrict__ row_chunk,
+__global__ void k_row_work(const int4 *__restrict__ desc, const uint16_t *__restrict__ tovf,
+                           const int64_t *__restrict__ row_chunk,
                            int64_t nrows, long long *__restrict__ dense_slots,
                            long long *__restrict__ tile_cells) {
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
@@ -876,6 +877,7 @@ __global__ void k_row_work(const int4 *__restrict__ desc, const int64_t *__restr
       const int enc = e.z & 0xff;
       if (enc >= ENC_D32 && enc <= ENC_D8) d += e.y * (enc == ENC_D32 ? 4 : (enc == ENC_D16 ? 2 : 1));
       else t += e.y;
+      t += tovf[c];
     }
     dense_slots[r] = d;      // weighted by bytes per slot
     tile_cells[r] = t;
@@ -889,7 +891,7 @@ void row_work(tb_store *s, int64_t *h_dense, int64_t *h_tile) {
   DevBuf<long long> d, t;
   d.alloc(s->nrows);
   t.alloc(s->nrows);
-  k_row_work<<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(s->enc_desc.p, s->row_chunk.p,
+  k_row_work<<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(s->enc_desc.p, s->enc_tovf.p, s->row_chunk.p,
                                                                   s->nrows, d.p, t.p);
   TB_CUDA(cudaMemcpyAsync(h_dense, d.p, s->nrows * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaMemcpyAsync(h_tile, t.p, s->nrows * sizeof(int64_t), cudaMemcpyDeviceToHost, st));

@@ -11,12 +11,17 @@
 //                    bytes, and runs its producer cursor kStages sub-blocks ahead of its
 //                    consumer cursor, across group boundaries.  HBM latency is therefore
 //                    covered by bytes in flight in the copy engine (up to 128 KB per SM),
-//                    not by resident warps or registers.  Per 128 columns a lane reads one
-//                    word per row from shared memory (conflict-free) and two 16-byte x loads
-//                    shared by the kRows rows, then 4 x kRows DFMA.
+//                    not by resident warps or registers.  The groups are sorted by panel and
+//                    a CTA owns a contiguous range of them, so the 32 KB of x of the current
+//                    panel sit in shared memory too (one bulk copy per panel change, 1-3 per
+//                    CTA and pass) instead of being re-read from L2 by every warp.  Per 128
+//                    columns a lane reads one word per row and two 16-byte x values shared by
+//                    the kRows rows (all conflict-free shared-memory loads), then 4 x kRows DFMA.
 //   k_rowsum_sparse  one sparse chunk per warp, x gathered through L1/L2.
 //
 // Integer -> double by exponent splice (one DADD) instead of I2F.F64.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace tb {
@@ -24,9 +29,9 @@ namespace tb {
 namespace {
 
 constexpr int kStages = 2;          // sub-blocks in flight per warp
-constexpr int kDenseWarps = 24;     // warps per CTA, one CTA per SM
 constexpr int kWarpRing = kStages * kRows * kSub;                 // 8 KB per warp
-constexpr int kDenseSmem = kDenseWarps * kWarpRing + kDenseWarps * kStages * 8;
+constexpr int kPanelBytes = kPanel * 8;                           // x of one column panel, 32 KB
+constexpr int kDenseSmem = kPanelBytes + kDenseWarps * kWarpRing + (kDenseWarps * kStages + 1) * 8;
 
 __device__ __forceinline__ double u2d(uint32_t v) {      // exact for v < 2^32
   return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
@@ -44,9 +49,6 @@ __device__ __forceinline__ uint2 ldg_stream_u64(const void *p) {
   uint2 r;
   asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
   return r;
-}
-__device__ __forceinline__ double2 ldg_x2(const double *p) {      // cached: x is reused
-  return __ldg(reinterpret_cast<const double2 *>(p));
 }
 __device__ __forceinline__ double warp_sum(double a) {
   for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
@@ -83,6 +85,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
       : "memory");
 }
 
+__device__ __forceinline__ double2 lds_x2(const double *p) {      // x panel in shared memory
+  double2 r;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(smem_u32(p)));
+  return r;
+}
+
 // One 512-byte piece of a stage for every row: 512/256/128 columns for D8/D16/D32.
 // Straight-line: per column and row one byte-extract (PRMT), one DADD (exponent splice) and
 // one DFMA; x is loaded once for the kRows rows.
@@ -93,7 +101,7 @@ __device__ __forceinline__ void consume(const uint8_t *stage, const double *xb, 
   constexpr int G = 512 / (128 * W);             // 128-column groups per 512-byte piece
 #pragma unroll
   for (int g = 0; g < G; ++g) {
-    const double2 xa = ldg_x2(xb + g * 128), xc = ldg_x2(xb + g * 128 + 64);
+    const double2 xa = lds_x2(xb + g * 128), xc = lds_x2(xb + g * 128 + 64);
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
       const uint8_t *p = stage + r * kSub + g * 128 * W;
@@ -128,35 +136,40 @@ __device__ __forceinline__ void consume_stage(const uint8_t *sp, const double *x
 __device__ __forceinline__ GroupRec load_rec(const GroupRec *__restrict__ recs, int64_t gi) {
   const int4 *p = reinterpret_cast<const int4 *>(recs + gi);
   const int4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-  GroupRec g;
+  GroupRec g;                            // novf[] is read where it is needed (load_novf)
   g.off16[0] = a.x; g.off16[1] = a.y; g.off16[2] = a.z; g.off16[3] = a.w;
   g.id[0] = b.x; g.id[1] = b.y; g.id[2] = b.z; g.id[3] = b.w;
-  g.c0 = c.x; g.nsub = c.y; g.enc = c.z; g.ovf = c.w;
+  g.c0 = c.x; g.nsub = c.y; g.enc = c.z; g.seg_end = c.w;
   return g;
 }
 
 __global__ void __launch_bounds__(kDenseWarps * 32, 1)
-k_rowsum_dense(const uint8_t *__restrict__ data, const GroupRec *__restrict__ recs, int64_t ngroups,
-               const int4 *__restrict__ desc, const double *__restrict__ x,
-               double *__restrict__ partial, const IceState *__restrict__ state) {
+k_rowsum_dense(const uint8_t *__restrict__ data, const GroupRec *__restrict__ recs,
+               const int32_t *__restrict__ cta_range, const int4 *__restrict__ desc,
+               const double *__restrict__ x, double *__restrict__ partial,
+               const IceState *__restrict__ state) {
   if (state && state->stopped) return;
   extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
-  uint8_t *ring = smem + wic * kWarpRing;
+  const double *xs = reinterpret_cast<const double *>(smem);           // x of the current panel
+  uint8_t *ring = smem + kPanelBytes + wic * kWarpRing;
   const uint32_t ring_u32 = smem_u32(ring);
-  const uint32_t bars = smem_u32(smem + kDenseWarps * kWarpRing) + wic * kStages * 8;
+  const uint32_t bar0 = smem_u32(smem + kPanelBytes + kDenseWarps * kWarpRing);
+  const uint32_t bars = bar0 + wic * kStages * 8;
+  const uint32_t xbar = bar0 + kDenseWarps * kStages * 8;
   if (lane == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(bars + 8 * s, 1);
+    if (wic == 0) mbar_init(xbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncwarp();
+  __syncthreads();
 
-  const int64_t warp = (int64_t)blockIdx.x * kDenseWarps + wic;
-  const int64_t nwarp = (int64_t)gridDim.x * kDenseWarps;
+  // this CTA's contiguous range of groups; its warps take them round robin
+  const int64_t g0 = cta_range[blockIdx.x], g1 = cta_range[blockIdx.x + 1];
 
   // Producer cursor (pg, psub) runs kStages sub-blocks ahead of the consumer cursor (cg, csub)
-  // over the same sequence of (group, sub-block) pairs, across group boundaries.
-  int64_t pgi = warp, cgi = warp;
+  // over the same sequence of (group, sub-block) pairs, across group and panel boundaries.
+  int64_t pgi = g0 + wic, cgi = g0 + wic;
   int psub = 0, csub = 0;
   // producer keeps only what the copies need: payload offsets (0xffffffff = empty seat)
   uint32_t poff[kRows];
@@ -167,12 +180,12 @@ k_rowsum_dense(const uint8_t *__restrict__ data, const GroupRec *__restrict__ re
     for (int r = 0; r < kRows; ++r) poff[r] = g.id[r] >= 0 ? g.off16[r] : 0xffffffffu;
     pnsub = g.nsub;
   };
-  if (pgi < ngroups) {
+  if (pgi < g1) {
     cg = load_rec(recs, pgi);
     load_producer(cg);
   }
   auto issue = [&](int stage) {             // all lanes advance the cursor, lane 0 issues
-    if (pgi >= ngroups) return;
+    if (pgi >= g1) return;
     if (lane == 0) {
       int nvalid = 0;
 #pragma unroll
@@ -187,8 +200,8 @@ k_rowsum_dense(const uint8_t *__restrict__ data, const GroupRec *__restrict__ re
     }
     if (++psub == pnsub) {
       psub = 0;
-      pgi += nwarp;
-      if (pgi < ngroups) load_producer(load_rec(recs, pgi));
+      pgi += kDenseWarps;
+      if (pgi < g1) load_producer(load_rec(recs, pgi));
     }
   };
 #pragma unroll
@@ -197,49 +210,68 @@ k_rowsum_dense(const uint8_t *__restrict__ data, const GroupRec *__restrict__ re
   double lo[kRows], hi[kRows];
 #pragma unroll
   for (int r = 0; r < kRows; ++r) lo[r] = hi[r] = 0.0;
-  uint32_t parity = 0;
-  while (cgi < ngroups) {
-#pragma unroll
-    for (int stage = 0; stage < kStages; ++stage) {       // compile-time stage -> fixed addresses
-      if (cgi >= ngroups) break;
-      mbar_wait(bars + 8 * stage, parity);
-      const uint8_t *sp = ring + stage * kRows * kSub;
-      if (cg.enc == ENC_D8)
-        consume_stage<ENC_D8>(sp, x + cg.c0 + csub * kSub + 2 * lane, lane, lo, hi);
-      else if (cg.enc == ENC_D16)
-        consume_stage<ENC_D16>(sp, x + cg.c0 + csub * (kSub / 2) + 2 * lane, lane, lo, hi);
-      else
-        consume_stage<ENC_D32>(sp, x + cg.c0 + csub * (kSub / 4) + 2 * lane, lane, lo, hi);
-      __syncwarp();                          // every lane is done with this stage's bytes
-      issue(stage);
-      if (++csub == cg.nsub) {               // group finished: overflow cells, reduce, publish
-        if (cg.ovf) {
-          const int width = cg.enc == ENC_D16 ? 2 : 1;
-#pragma unroll
-          for (int r = 0; r < kRows; ++r) {
-            if (cg.id[r] < 0) continue;
-            const int novf = __ldg(desc + cg.id[r]).z >> 8;
-            const int2 *cells = reinterpret_cast<const int2 *>(
-                data + ((int64_t)cg.off16[r] << 4) + (int64_t)cg.nsub * kSub);
-            for (int k = lane; k < novf; k += 32) {
-              const int2 e = __ldg(cells + k);
-              lo[r] = fma(i2d(e.y), __ldg(x + e.x), lo[r]);
-            }
-          }
-          (void)width;
-        }
+  uint32_t rparity = 0, xparity = 0;        // rparity bit q = parity of ring stage q
+  int stage = 0;
+  // one sub-block of group cgi; the ring stage is a compile-time constant (fixed addresses)
+  auto step = [&](auto stage_c) {
+    constexpr int ST = decltype(stage_c)::value;
+    mbar_wait(bars + 8 * ST, (rparity >> ST) & 1u);
+    rparity ^= 1u << ST;
+    const uint8_t *sp = ring + ST * kRows * kSub;
+    const int enc = cg.enc & 0xff;
+    if (enc == ENC_D8)
+      consume_stage<ENC_D8>(sp, xs + csub * kSub + 2 * lane, lane, lo, hi);
+    else if (enc == ENC_D16)
+      consume_stage<ENC_D16>(sp, xs + csub * (kSub / 2) + 2 * lane, lane, lo, hi);
+    else
+      consume_stage<ENC_D32>(sp, xs + csub * (kSub / 4) + 2 * lane, lane, lo, hi);
+    __syncwarp();                          // every lane is done with this stage's bytes
+    issue(ST);
+    if (++csub == cg.nsub) {               // group finished: overflow cells, reduce, publish
+      if (cg.enc >> 8) {                     // cells outside [0, 2^15): a list behind the seat (rare)
+        const int4 nv = __ldg(reinterpret_cast<const int4 *>(recs + cgi) + 3);
+        const int novf[kRows] = {nv.x, nv.y, nv.z, nv.w};
 #pragma unroll
         for (int r = 0; r < kRows; ++r) {
-          const double a = warp_sum(lo[r] + hi[r]);
-          if (lane == 0 && cg.id[r] >= 0) partial[cg.id[r]] = a;
-          lo[r] = hi[r] = 0.0;
+          const int2 *cells = reinterpret_cast<const int2 *>(
+              data + ((int64_t)cg.off16[r] << 4) + (int64_t)cg.nsub * kSub);
+          for (int k = lane; k < novf[r]; k += 32) {
+            const int2 e = __ldg(cells + k);
+            lo[r] = fma(i2d(e.y), xs[e.x - cg.c0], lo[r]);
+          }
         }
-        csub = 0;
-        cgi += nwarp;
-        if (cgi < ngroups) cg = load_rec(recs, cgi);
       }
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        const double a = warp_sum(lo[r] + hi[r]);
+        if (lane == 0 && cg.id[r] >= 0) partial[cg.id[r]] = a;
+        lo[r] = hi[r] = 0.0;
+      }
+      csub = 0;
+      cgi += kDenseWarps;
+      if (cgi < g1) cg = load_rec(recs, cgi);
     }
-    parity ^= 1u;
+  };
+  for (int64_t g = g0; g < g1;) {            // panel segments of the range
+    const int4 head = __ldg(reinterpret_cast<const int4 *>(recs + g) + 2);   // c0, nsub, enc, seg_end
+    const int64_t ge = head.w < g1 ? head.w : g1;
+    __syncthreads();                         // every warp is done with the previous panel
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(xbar, kPanelBytes);
+      bulk_g2s(smem_u32(smem), x + head.x, kPanelBytes, xbar);
+    }
+    mbar_wait(xbar, xparity);
+    xparity ^= 1u;
+    while (cgi < ge) {
+      if (stage == 0) {
+        step(std::integral_constant<int, 0>());
+        stage = 1;
+        if (cgi >= ge) break;
+      }
+      step(std::integral_constant<int, 1>());
+      stage = 0;
+    }
+    g = ge;
   }
 }
 
@@ -314,10 +346,8 @@ void launch_rowsum_chunks(tb_store *s, const double *x, const IceState *state) {
                                    kDenseSmem));
       attr_set[s->device & 63] = true;
     }
-    int64_t need = (s->n_groups + kDenseWarps - 1) / kDenseWarps;
-    const int grid = (int)(need < s->sm_count ? need : s->sm_count);
-    k_rowsum_dense<<<grid, kDenseWarps * 32, kDenseSmem, s->stream>>>(
-        s->enc_data.p, s->groups.p, s->n_groups, s->enc_desc.p, x, s->partial_f.p, state);
+    k_rowsum_dense<<<s->n_dense_ctas, kDenseWarps * 32, kDenseSmem, s->stream>>>(
+        s->enc_data.p, s->groups.p, s->group_range.p, s->enc_desc.p, x, s->partial_f.p, state);
   }
   if (s->n_sparse) {
     int64_t need = (s->n_sparse + 7) / 8, cap = (int64_t)s->sm_count * 8;

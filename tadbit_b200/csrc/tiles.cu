@@ -60,8 +60,8 @@ constexpr int kPieceBytes = 1024;                          // 8 steps x 128 B
 constexpr int kRing = 2;
 constexpr int kTileSmem = kWinBytes + kTileRows * 8 + kTileWarps * kRing * kPieceBytes +
                           (kTileWarps * kRing + 1) * 8 + 64;
-// fixed cost of a tile in a unit (window load + barrier), in cells of stream
-constexpr int64_t kTileFixedCost = 12000;
+// fixed cost of a tile in a unit (window load, barrier, descriptor chain), in cells of stream
+constexpr int64_t kTileFixedCost = 24000;
 
 __device__ __forceinline__ double u2d(uint32_t v) {
   return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
@@ -99,18 +99,24 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 }
 
 // ---- build ---------------------------------------------------------------------------------
+// The tiles hold every cell of the ENC_T chunks, plus the cells of D8 chunks that are too large
+// for a byte but fit a tile cell (encode.cu counts them per chunk in tovf).
+__device__ __forceinline__ bool tile_overflow(int32_t v) { return v > 255 && v < (1 << kTileValBits); }
+
 __global__ void __launch_bounds__(256)
-k_tile_count(const int32_t *__restrict__ col, const int64_t *__restrict__ chunk_beg,
-             const int32_t *__restrict__ chunk_row, const int4 *__restrict__ desc, int64_t nchunks,
+k_tile_count(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
+             const int64_t *__restrict__ chunk_beg, const int32_t *__restrict__ chunk_row,
+             const int4 *__restrict__ desc, const uint16_t *__restrict__ tovf, int64_t nchunks,
              int64_t nwin, int32_t *__restrict__ cnt) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t c = warp; c < nchunks; c += nwarp) {
-    if ((desc[c].z & 0xff) != ENC_T) continue;
+    const bool all = (desc[c].z & 0xff) == ENC_T;
+    if (!all && tovf[c] == 0) continue;
     const int64_t beg = chunk_beg[c], end = chunk_beg[c + 1], row = chunk_row[c];
     for (int64_t k = beg + lane; k < end; k += 32)
-      atomicAdd(&cnt[row * nwin + col[k] / kTileCols], 1);
+      if (all || tile_overflow(val[k])) atomicAdd(&cnt[row * nwin + col[k] / kTileCols], 1);
   }
 }
 
@@ -119,7 +125,7 @@ k_tile_count(const int32_t *__restrict__ col, const int64_t *__restrict__ chunk_
 __global__ void __launch_bounds__(kTileThreads)
 k_tile_sort(const int32_t *__restrict__ cnt, int64_t nwin, uint16_t *__restrict__ perm,
             uint16_t *__restrict__ inv, uint32_t *__restrict__ slice, int64_t *__restrict__ tile_size,
-            unsigned long long *__restrict__ totals) {
+            int32_t *__restrict__ tile_crit, unsigned long long *__restrict__ totals) {
   __shared__ uint32_t key[kTileRows];
   const int t = threadIdx.x;
   const int64_t tile = blockIdx.x, rb = tile / nwin, w = tile % nwin;
@@ -155,19 +161,30 @@ k_tile_sort(const int32_t *__restrict__ cnt, int64_t nwin, uint16_t *__restrict_
     }
     slice[tile * kSliceTab + kSlices] = run;
     tile_size[tile] = run;
+    // steps of the busiest warp (warp w streams slices w and 63 - w one after the other)
+    uint32_t crit = 0;
+    for (int w = 0; w < kTileWarps; ++w) {
+      const uint32_t a = ((key[w * 32] >> kRowBits) + 3u) & ~3u;
+      const uint32_t b = ((key[(kSlices - 1 - w) * 32] >> kRowBits) + 3u) & ~3u;
+      crit = max(crit, a + b);
+    }
+    tile_crit[tile] = (int32_t)crit;
   }
   for (int o = 16; o; o >>= 1) real += __shfl_xor_sync(0xffffffffu, real, o);
   if ((t & 31) == 0 && real) atomicAdd(totals, real);  // unpadded cells, for the layout report
 }
 
-// A warp's position in the tile cells of one row: the row's ENC_T chunks in column order.
+// A warp's position in the tile cells of one row: the row's chunks that hold tile cells, in
+// column order.  `filter`: the current chunk is a D8 chunk, only its tile_overflow cells count.
 struct RowCursor {
   int64_t c, cend, k, kend;
+  bool filter;
   const int64_t *chunk_beg;
   const int4 *desc;
-  __device__ __forceinline__ void seek() {       // to the next ENC_T chunk at or after c
-    while (c < cend && (desc[c].z & 0xff) != ENC_T) ++c;
-    if (c < cend) { k = chunk_beg[c]; kend = chunk_beg[c + 1]; }
+  const uint16_t *tovf;
+  __device__ __forceinline__ void seek() {       // to the next chunk with tile cells at or after c
+    while (c < cend && (desc[c].z & 0xff) != ENC_T && tovf[c] == 0) ++c;
+    if (c < cend) { k = chunk_beg[c]; kend = chunk_beg[c + 1]; filter = (desc[c].z & 0xff) != ENC_T; }
   }
   // after a block of `na` (<= 32) cells of the current window was taken: true = the window goes on
   __device__ __forceinline__ bool advance(int na, const int32_t *__restrict__ col, int32_t whi) {
@@ -198,8 +215,8 @@ __device__ __forceinline__ void leftover_slot(const SlotTables &tb_, int t, bool
 __global__ void __launch_bounds__(256)
 k_tile_fill(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
             const int64_t *__restrict__ chunk_beg, const int64_t *__restrict__ row_chunk,
-            const int4 *__restrict__ desc, int64_t nrows, int64_t nwin,
-            const uint16_t *__restrict__ inv, const uint32_t *__restrict__ slice,
+            const int4 *__restrict__ desc, const uint16_t *__restrict__ tovf, int64_t nrows,
+            int64_t nwin, const uint16_t *__restrict__ inv, const uint32_t *__restrict__ slice,
             const int64_t *__restrict__ t_off, uint32_t *__restrict__ cells) {
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
@@ -209,7 +226,8 @@ k_tile_fill(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
     const int64_t rb = r / kTileRows;
     RowCursor cur;
     cur.c = row_chunk[r]; cur.cend = row_chunk[r + 1]; cur.k = cur.kend = 0;
-    cur.chunk_beg = chunk_beg; cur.desc = desc;
+    cur.filter = false;
+    cur.chunk_beg = chunk_beg; cur.desc = desc; cur.tovf = tovf;
     cur.seek();
     while (cur.c < cur.cend) {
       const int32_t w = col[cur.k] / kTileCols, wlo = w * kTileCols, whi = wlo + kTileCols;
@@ -223,10 +241,11 @@ k_tile_fill(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
       int b = 0;
       for (;;) {
         const int64_t idx = cur.k + lane;
-        int32_t cc = idx < cur.kend ? col[idx] : 0x7fffffff;
-        const bool act = cc < whi;
+        const int32_t cc = idx < cur.kend ? col[idx] : 0x7fffffff;
+        const bool inwin = cc < whi;
+        const bool act = inwin && (!cur.filter || tile_overflow(val[idx]));
         const int res = cc & 15;
-        const int na = __popc(__ballot_sync(0xffffffffu, act));
+        const int na = __popc(__ballot_sync(0xffffffffu, inwin));
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
           const unsigned m = __ballot_sync(0xffffffffu, act && res == q);
@@ -257,10 +276,12 @@ k_tile_fill(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
       int run = 0;
       for (;;) {
         const int64_t idx = cur.k + lane;
-        int32_t cc = idx < cur.kend ? col[idx] : 0x7fffffff;
-        const bool act = cc < whi;
+        const int32_t cc = idx < cur.kend ? col[idx] : 0x7fffffff;
+        const bool inwin = cc < whi;
+        const int32_t vv = inwin ? val[idx] : 0;
+        const bool act = inwin && (!cur.filter || tile_overflow(vv));
         const int res = cc & 15;
-        const int na = __popc(__ballot_sync(0xffffffffu, act));
+        const int na = __popc(__ballot_sync(0xffffffffu, inwin));
         const unsigned same = __match_any_sync(0xffffffffu, act ? res : 16 + lane);
         const int m = __shfl_sync(0xffffffffu, run, res) + __popc(same & lt);
         const int sv = __shfl_sync(0xffffffffu, tabs.served, res);
@@ -269,7 +290,7 @@ k_tile_fill(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
         leftover_slot(tabs, lb + m - sv, act && m >= sv, r2, m2);
         if (act) {
           const int ks = ((r2 - l) & 15) + 16 * m2;
-          out[(ks >> 2) * 128 + (ks & 3)] = pack_cell(cc - wlo, val[idx]);
+          out[(ks >> 2) * 128 + (ks & 3)] = pack_cell(cc - wlo, vv);
         }
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
@@ -490,7 +511,7 @@ void build_tiles(tb_store *s) {
   cudaStream_t st = s->stream;
   s->t_nrb = s->t_nwin = s->t_ncells = s->t_npadded = s->t_nunits = 0;
   s->t_launches = 0;
-  if (s->enc_chunks[ENC_T] == 0) return;
+  if (s->enc_chunks[ENC_T] == 0 && s->n_overflow_tiled == 0) return;
   const int64_t nrb = (s->nrows + kTileRows - 1) / kTileRows;
   const int64_t nwin = (s->nbins + kTileCols - 1) / kTileCols;
   const int64_t ntiles = nrb * nwin;
@@ -500,22 +521,24 @@ void build_tiles(tb_store *s) {
   DevBuf<int32_t> cnt;
   DevBuf<uint16_t> inv;
   DevBuf<int64_t> tile_size;
+  DevBuf<int32_t> tile_crit;
   DevBuf<unsigned long long> totals;
   cnt.alloc(nrb * kTileRows * nwin);
   inv.alloc(nrb * kTileRows * nwin);
   tile_size.alloc(ntiles + 1);
+  tile_crit.alloc(ntiles + 1);
   totals.alloc(1);
   TB_CUDA(cudaMemsetAsync(cnt.p, 0, cnt.bytes(), st));
   TB_CUDA(cudaMemsetAsync(tile_size.p, 0, tile_size.bytes(), st));
   TB_CUDA(cudaMemsetAsync(totals.p, 0, totals.bytes(), st));
   const int cg = grid_1d(s->nchunks * 32, 256, s->sm_count, 8);
-  k_tile_count<<<cg, 256, 0, st>>>(s->col.p, s->chunk_beg.p, s->chunk_row.p, s->enc_desc.p,
-                                   s->nchunks, nwin, cnt.p);
+  k_tile_count<<<cg, 256, 0, st>>>(s->col.p, s->val.p, s->chunk_beg.p, s->chunk_row.p, s->enc_desc.p,
+                                   s->enc_tovf.p, s->nchunks, nwin, cnt.p);
   s->t_perm.alloc(ntiles * kTileRows);
   s->t_slice.alloc(ntiles * kSliceTab);
   s->t_off.alloc(ntiles + 1);
   k_tile_sort<<<(unsigned)ntiles, kTileThreads, 0, st>>>(cnt.p, nwin, s->t_perm.p, inv.p,
-                                                        s->t_slice.p, tile_size.p, totals.p);
+                                                        s->t_slice.p, tile_size.p, tile_crit.p, totals.p);
   {
     size_t tmp_bytes = 0;
     TB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, tile_size.p, s->t_off.p, ntiles + 1, st));
@@ -525,8 +548,10 @@ void build_tiles(tb_store *s) {
     TB_CUDA(cudaStreamSynchronize(st));
   }
   std::vector<int64_t> h_size(ntiles);
+  std::vector<int32_t> h_crit(ntiles);
   unsigned long long h_total = 0;
   TB_CUDA(cudaMemcpy(h_size.data(), tile_size.p, ntiles * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  TB_CUDA(cudaMemcpy(h_crit.data(), tile_crit.p, ntiles * sizeof(int32_t), cudaMemcpyDeviceToHost));
   TB_CUDA(cudaMemcpy(&h_total, totals.p, sizeof(h_total), cudaMemcpyDeviceToHost));
   TB_CUDA(cudaMemcpy(&s->t_npadded, s->t_off.p + ntiles, sizeof(int64_t), cudaMemcpyDeviceToHost));
   s->t_ncells = (int64_t)h_total;
@@ -534,16 +559,26 @@ void build_tiles(tb_store *s) {
   s->t_cells.alloc(s->t_npadded ? s->t_npadded : 1);
   TB_CUDA(cudaMemsetAsync(s->t_cells.p, 0, s->t_cells.bytes(), st));       // padding = (col 0, count 0)
   k_tile_fill<<<grid_1d(s->nrows * 32, 256, s->sm_count, 8), 256, 0, st>>>(
-      s->col.p, s->val.p, s->chunk_beg.p, s->row_chunk.p, s->enc_desc.p, s->nrows, nwin, inv.p,
+      s->col.p, s->val.p, s->chunk_beg.p, s->row_chunk.p, s->enc_desc.p, s->enc_tovf.p, s->nrows, nwin, inv.p,
       s->t_slice.p, s->t_off.p, s->t_cells.p);
   // Work units: each row block's non-empty tiles, cut into runs of about equal cost so that there
   // are ~16 units per SM whatever the number of row blocks (1 GPU or a 1/8 shard).  A tile heavier
   // than that (the ones on the diagonal) is split: `parts` units each take a share of every
   // slice of the tile.  unit = (row block, list begin, list end, part<<8|parts).
+  // The cost of a tile is its cell count, or what its busiest warp streams if the rows are so
+  // uneven that this warp, not the SM, sets the time: a lone warp moves about 1/(0.7 * 32) of
+  // what the SM does (two 1 KB pieces in flight).
+  std::vector<double> h_eff(ntiles);
   int64_t nonempty = 0;
-  for (int64_t q = 0; q < ntiles; ++q) nonempty += h_size[q] != 0;
-  const double total_cost = (double)s->t_npadded + (double)kTileFixedCost * (double)nonempty;
-  const double target = total_cost / (16.0 * s->sm_count) + 1.0;
+  double total_cost = 0.0;
+  for (int64_t q = 0; q < ntiles; ++q) {
+    h_eff[q] = std::max((double)h_size[q], 0.7 * 1024.0 * (double)h_crit[q]);
+    if (h_size[q]) { ++nonempty; total_cost += h_eff[q] + (double)kTileFixedCost; }
+  }
+  // ... but no smaller than a few times the fixed cost of a unit, unless that would leave SMs
+  // without work (small or mostly dense matrices: one unit per SM then)
+  const double target = std::max(total_cost / (16.0 * s->sm_count),
+                                 std::min(3.0 * (double)kTileFixedCost, total_cost / s->sm_count)) + 1.0;
   std::vector<int32_t> list, units, unit_of_rb(nrb + 1, 0);
   std::vector<double> cost;
   for (int64_t rb = 0; rb < nrb; ++rb) {
@@ -559,22 +594,22 @@ void build_tiles(tb_store *s) {
       run = 0;
     };
     for (int64_t w = 0; w < nwin; ++w) {
-      const int64_t sz = h_size[rb * nwin + w];
-      if (!sz) continue;
-      if ((double)sz > 1.5 * target) {
+      if (!h_size[rb * nwin + w]) continue;
+      const double sz = h_eff[rb * nwin + w];
+      if (sz > 1.5 * target) {
         flush();
-        int parts = (int)((double)sz / target + 0.999);
-        if (parts > 64) parts = 64;
+        int parts = (int)(sz / target + 0.999);
+        if (parts > 128) parts = 128;
         list.push_back((int32_t)(rb * nwin + w));
         for (int p = 0; p < parts; ++p) {
           units.insert(units.end(), {(int32_t)rb, begin, begin + 1, (p << 8) | parts});
-          cost.push_back((double)sz / parts + (double)kTileFixedCost);
+          cost.push_back(sz / parts + (double)kTileFixedCost);
         }
         begin = (int32_t)list.size();
         continue;
       }
       list.push_back((int32_t)(rb * nwin + w));
-      run += (double)(sz + kTileFixedCost);
+      run += sz + (double)kTileFixedCost;
       if (run >= target) flush();
     }
     flush();

@@ -107,6 +107,7 @@ class ContactStore(object):
                     tile_bytes=int(out[13]), chunks=int(out[7]), csr_bytes=int(out[8]),
                     tile_cells=int(out[9]), tile_cells_padded=int(out[10]),
                     tile_units=int(out[11]), overflow_cells=int(out[12]),
+                    overflow_cells_in_tiles=int(out[14]),
                     encodings=dict(zip(("S32", "S16", "D32", "D16", "D8", "T"),
                                        out[1:7].tolist())))
 

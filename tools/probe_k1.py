@@ -18,6 +18,9 @@ def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "c3"
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
     wl = workloads.workload(name)
+    if os.environ.get("PROBE_WARM"):          # a first build warms the memory pool
+        ContactStore.synthetic(wl["size"], wl["params"], chromosomes=wl["chromosomes"]).close()
+        print("---- second (warm) build ----", file=sys.stderr)
     t0 = time.time()
     store = ContactStore.synthetic(wl["size"], wl["params"], chromosomes=wl["chromosomes"])
     t1 = time.time()
@@ -27,6 +30,8 @@ def main():
     store.probe_rowsum(2)
     total, tiles, dense = store.probe_rowsum(reps)
     print("K1 ms: total %.3f  tiles %.3f  dense %.3f" % (total, tiles, dense))
+    if os.environ.get("PROBE_ONLY"):
+        return
     hic = HiC_data.from_store(store, chromosomes=wl["chromosomes"])
     hic.filter_columns(silent=True)
     t0 = time.time()
