@@ -21,11 +21,14 @@
 // steps left over, padding gets the preferred residue with count 0.
 //
 // Streaming.  A warp's cells of one work unit form a stream that does not depend on the x
-// windows.  It is cut at build time into pieces of 8 (or 4) steps, one 8-byte copy descriptor
-// each (where the piece starts, which rows it belongs to, end-of-slice / end-of-tile marks); the
-// warp pulls the pieces through a private two-stage ring in shared memory with cp.async.bulk,
-// two pieces ahead of what it consumes, across slice and tile boundaries.  Warp w takes slices
-// w and 63 - w of every tile (longest with shortest).
+// windows.  It is cut at build time into pieces of up to 16 steps (2 KB), one 8-byte copy
+// descriptor each (where the piece starts, which rows it belongs to, end-of-slice / end-of-tile
+// marks); the warp pulls the pieces through a private two-stage ring in shared memory with
+// cp.async.bulk, two pieces ahead of what it consumes, across slice and tile boundaries.  A CTA
+// has 16 warps; warp w takes slices w, 31 - w, 32 + w and 63 - w of every tile (long with
+// short).  Measured on the genome-wide 5 kb matrix: 32 warps x 1 KB pieces 1.54 ms, 16 x 2 KB
+// 1.36 ms, 8 x 4 KB 1.40 ms -- the fixed work per piece (barrier wait, copy issue) is what the
+// larger pieces save.
 //
 // Scheduling.  Row blocks are cut into work units of roughly equal cost; CTAs (one per SM)
 // fetch them from an atomic counter, most expensive first.  A unit writes kTileRows partial
@@ -42,21 +45,30 @@ namespace tb {
 
 namespace {
 
-constexpr int kTileThreads = kTileRows / 2;
-constexpr int kTileWarps = kTileThreads / 32;
+#ifndef TB_TILE_WARPS
+#define TB_TILE_WARPS 16
+#endif
+#ifndef TB_PIECE_QUADS
+#define TB_PIECE_QUADS 4
+#endif
+constexpr int kSortThreads = kTileRows / 2;                // k_tile_sort
+constexpr int kTileWarps = TB_TILE_WARPS;                  // warps of a k_rowsum_tiles CTA
+constexpr int kTileThreads = kTileWarps * 32;
+constexpr int kPieceQuads = TB_PIECE_QUADS;                // steps / 4 per ring stage
 constexpr int kSlices = kTileRows / 32;
 constexpr int kSliceTab = kSlices + 1;
 constexpr int kRowBits = 11;                               // kTileRows = 2048
 constexpr int kWinBytes = kTileCols * 8;
 static_assert(kTileRows == 1 << kRowBits, "kRowBits");
-static_assert(kSlices == 2 * kTileWarps, "two slices per warp");
+constexpr int kWarpSlices = kSlices / kTileWarps;          // slices of a tile one warp streams
+static_assert(kSlices % kTileWarps == 0 && kPieceQuads >= 1 && kPieceQuads <= 15, "tile kernel shape");
 static_assert(kTileCols * 4 <= 65536 && kTileValBits == 15, "cell packing");
 
 // copy descriptor: x = first step of the piece in the cell array (cell index / 32),
-// y = row group (tile * 64 + slice) | steps / 4 << 26 | end-of-slice << 28 | end-of-tile << 29
+// y = row group (tile * 64 + slice) | steps / 4 << 26 | end-of-slice << 30 | end-of-tile << 31
 constexpr uint32_t kDescGroupMask = (1u << 26) - 1u;
-constexpr uint32_t kDescEndSlice = 1u << 28, kDescEndTile = 1u << 29;
-constexpr int kPieceBytes = 1024;                          // 8 steps x 128 B
+constexpr uint32_t kDescEndSlice = 1u << 30, kDescEndTile = 1u << 31;
+constexpr int kPieceBytes = kPieceQuads * 512;             // steps x 128 B
 constexpr int kRing = 2;
 constexpr int kTileSmem = kWinBytes + kTileRows * 8 + kTileWarps * kRing * kPieceBytes +
                           (kTileWarps * kRing + 1) * 8 + 64;
@@ -99,6 +111,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 }
 
 // ---- build ---------------------------------------------------------------------------------
+// h-th slice of warp w: blocks of kTileWarps slices, walked back and forth (long with short)
+__host__ __device__ __forceinline__ int warp_slice(int w, int h) {
+  return h * kTileWarps + ((h & 1) ? kTileWarps - 1 - w : w);
+}
+
 // The tiles hold every cell of the ENC_T chunks, plus the cells of D8 chunks that are too large
 // for a byte but fit a tile cell (encode.cu counts them per chunk in tovf).
 __device__ __forceinline__ bool tile_overflow(int32_t v) { return v > 255 && v < (1 << kTileValBits); }
@@ -122,7 +139,7 @@ k_tile_count(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
 
 // one CTA per tile: sort the tile's rows by cell count (descending, ties by row), write the
 // permutation, its inverse, the slice offsets and the padded size of the tile
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kSortThreads)
 k_tile_sort(const int32_t *__restrict__ cnt, int64_t nwin, uint16_t *__restrict__ perm,
             uint16_t *__restrict__ inv, uint32_t *__restrict__ slice, int64_t *__restrict__ tile_size,
             int32_t *__restrict__ tile_crit, unsigned long long *__restrict__ totals) {
@@ -130,7 +147,7 @@ k_tile_sort(const int32_t *__restrict__ cnt, int64_t nwin, uint16_t *__restrict_
   const int t = threadIdx.x;
   const int64_t tile = blockIdx.x, rb = tile / nwin, w = tile % nwin;
   unsigned long long real = 0;
-  for (int e = t; e < kTileRows; e += kTileThreads) {
+  for (int e = t; e < kTileRows; e += kSortThreads) {
     const uint32_t mine = (uint32_t)cnt[(rb * kTileRows + e) * nwin + w];
     key[e] = (mine << kRowBits) | (uint32_t)(kTileRows - 1 - e);
     real += mine;
@@ -138,7 +155,7 @@ k_tile_sort(const int32_t *__restrict__ cnt, int64_t nwin, uint16_t *__restrict_
   __syncthreads();
   for (int k = 2; k <= kTileRows; k <<= 1)            // bitonic sort, descending
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int e = t; e < kTileRows; e += kTileThreads) {
+      for (int e = t; e < kTileRows; e += kSortThreads) {
         const int o = e ^ j;
         if (o > e) {
           const uint32_t a = key[e], b = key[o];
@@ -148,7 +165,7 @@ k_tile_sort(const int32_t *__restrict__ cnt, int64_t nwin, uint16_t *__restrict_
       }
       __syncthreads();
     }
-  for (int e = t; e < kTileRows; e += kTileThreads) {
+  for (int e = t; e < kTileRows; e += kSortThreads) {
     const int row = kTileRows - 1 - (int)(key[e] & (uint32_t)(kTileRows - 1));
     perm[tile * kTileRows + e] = (uint16_t)row;
     inv[(rb * kTileRows + row) * nwin + w] = (uint16_t)e;
@@ -164,9 +181,9 @@ k_tile_sort(const int32_t *__restrict__ cnt, int64_t nwin, uint16_t *__restrict_
     // steps of the busiest warp (warp w streams slices w and 63 - w one after the other)
     uint32_t crit = 0;
     for (int w = 0; w < kTileWarps; ++w) {
-      const uint32_t a = ((key[w * 32] >> kRowBits) + 3u) & ~3u;
-      const uint32_t b = ((key[(kSlices - 1 - w) * 32] >> kRowBits) + 3u) & ~3u;
-      crit = max(crit, a + b);
+      uint32_t mine = 0;
+      for (int h = 0; h < kWarpSlices; ++h) mine += ((key[warp_slice(w, h) * 32] >> kRowBits) + 3u) & ~3u;
+      crit = max(crit, mine);
     }
     tile_crit[tile] = (int32_t)crit;
   }
@@ -336,28 +353,33 @@ k_tile_desc(const int4 *__restrict__ unit, const int32_t *__restrict__ list,
   for (int j = un.y; j < un.z; ++j) {
     const int64_t tile = list[j];
     const uint32_t *st = slice + tile * kSliceTab;
-    int kb[2], len[2];
-    const int sl[2] = {w, kSlices - 1 - w};
+    int kb[kWarpSlices], len[kWarpSlices], total = 0, last = 0;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) len[h] = part_range(st[sl[h]], st[sl[h] + 1], part, parts, kb[h]);
-    if (len[0] + len[1] == 0) {
+    for (int h = 0; h < kWarpSlices; ++h) {
+      const int sl = warp_slice(w, h);
+      len[h] = part_range(st[sl], st[sl + 1], part, parts, kb[h]);
+      total += len[h];
+      if (len[h]) last = h;
+    }
+    if (total == 0) {
       if (FILL) o[n_out] = make_uint2(0u, (uint32_t)(tile * kSlices + w) | kDescEndTile);
       ++n_out;
       continue;
     }
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int pieces = (len[h] + 7) / 8;
+    for (int h = 0; h < kWarpSlices; ++h) {
+      const int sl = warp_slice(w, h);
+      const int pieces = (len[h] + 4 * kPieceQuads - 1) / (4 * kPieceQuads);
       if (FILL) {
-        const int64_t first = (t_off[tile] + st[sl[h]]) / 32 + kb[h];
+        const int64_t first = (t_off[tile] + st[sl]) / 32 + kb[h];
         for (int i = 0; i < pieces; ++i) {
-          const int steps = min(8, len[h] - 8 * i);
-          uint32_t y = (uint32_t)(tile * kSlices + sl[h]) | ((uint32_t)(steps / 4) << 26);
+          const int steps = min(4 * kPieceQuads, len[h] - 4 * kPieceQuads * i);
+          uint32_t y = (uint32_t)(tile * kSlices + sl) | ((uint32_t)(steps / 4) << 26);
           if (i == pieces - 1) {
             y |= kDescEndSlice;
-            if (h == 1 || len[1] == 0) y |= kDescEndTile;
+            if (h == last) y |= kDescEndTile;
           }
-          o[n_out + i] = make_uint2((uint32_t)(first + 8 * i), y);
+          o[n_out + i] = make_uint2((uint32_t)(first + 4 * kPieceQuads * i), y);
         }
       }
       n_out += pieces;
@@ -423,14 +445,14 @@ k_rowsum_tiles(const uint32_t *__restrict__ cells, const uint2 *__restrict__ des
     const int u = order[ui];
     const int4 un = unit[u];
     const int i0 = un.y, n = un.z - un.y;
-    acc[t] = 0.0;
-    acc[t + kTileThreads] = 0.0;
+#pragma unroll
+    for (int e = t; e < kTileRows; e += kTileThreads) acc[e] = 0.0;
     const int64_t dbeg = desc_off[(int64_t)u * kTileWarps + wic];
     const int nd = (int)(desc_off[(int64_t)u * kTileWarps + wic + 1] - dbeg);
     const uint2 *dp = desc + dbeg;
     // start the copy of piece `e` into `stage`; fetch the rows of its slice if it ends one
     auto issue = [&](int stage, const uint2 &e, uint32_t &row) {
-      const uint32_t quads = (e.y >> 26) & 3u;
+      const uint32_t quads = (e.y >> 26) & 15u;
       if (quads && lane == 0) {
         mbar_expect_tx(rbar + 8 * stage, quads * 512u);
         bulk_g2s(ring_u32 + stage * kPieceBytes, cells + (size_t)e.x * 32, quads * 512u, rbar + 8 * stage);
@@ -461,13 +483,17 @@ k_rowsum_tiles(const uint32_t *__restrict__ cells, const uint2 *__restrict__ des
         uint2 &e = ST ? e1 : e0;
         uint32_t &erow = ST ? row1 : row0;
         const uint32_t meta = e.y, row = erow;
-        const uint32_t quads = (meta >> 26) & 3u;
+        const uint32_t quads = (meta >> 26) & 15u;
         if (quads) {
           mbar_wait(rbar + 8 * ST, (rparity >> ST) & 1u);
           rparity ^= 1u << ST;
           const uint8_t *rs = ring + ST * kPieceBytes;
-          if (quads == 2) consume<2>(rs, lane, xw, a0, a1);
-          else consume<1>(rs, lane, xw, a0, a1);
+          if (quads == kPieceQuads) consume<kPieceQuads>(rs, lane, xw, a0, a1);
+          else {                                           // a short last piece: pairs, then one
+            uint32_t g = 0;
+            for (; g + 2 <= quads; g += 2) consume<2>(rs + g * 512, lane, xw, a0, a1);
+            if (g < quads) consume<1>(rs + g * 512, lane, xw, a0, a1);
+          }
         }
         __syncwarp();                        // every lane has read this stage
         if (meta & kDescEndSlice) {          // distinct rows per thread of a tile: no conflict
@@ -493,8 +519,8 @@ k_rowsum_tiles(const uint32_t *__restrict__ cells, const uint2 *__restrict__ des
       }
     }
     __syncthreads();
-    partial[(int64_t)u * kTileRows + t] = acc[t];
-    partial[(int64_t)u * kTileRows + t + kTileThreads] = acc[t + kTileThreads];
+#pragma unroll
+    for (int e = t; e < kTileRows; e += kTileThreads) partial[(int64_t)u * kTileRows + e] = acc[e];
     __syncthreads();                          // acc is re-zeroed, s_next rewritten for the next unit
   }
 }
@@ -537,7 +563,7 @@ void build_tiles(tb_store *s) {
   s->t_perm.alloc(ntiles * kTileRows);
   s->t_slice.alloc(ntiles * kSliceTab);
   s->t_off.alloc(ntiles + 1);
-  k_tile_sort<<<(unsigned)ntiles, kTileThreads, 0, st>>>(cnt.p, nwin, s->t_perm.p, inv.p,
+  k_tile_sort<<<(unsigned)ntiles, kSortThreads, 0, st>>>(cnt.p, nwin, s->t_perm.p, inv.p,
                                                         s->t_slice.p, tile_size.p, tile_crit.p, totals.p);
   {
     size_t tmp_bytes = 0;
@@ -567,7 +593,7 @@ void build_tiles(tb_store *s) {
   // slice of the tile.  unit = (row block, list begin, list end, part<<8|parts).
   // The cost of a tile is its cell count, or what its busiest warp streams if the rows are so
   // uneven that this warp, not the SM, sets the time: a lone warp moves about 1/(0.7 * 32) of
-  // what the SM does (two 1 KB pieces in flight).
+  // what the SM does (two pieces in flight).
   std::vector<double> h_eff(ntiles);
   int64_t nonempty = 0;
   double total_cost = 0.0;
