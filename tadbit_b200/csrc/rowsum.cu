@@ -17,7 +17,8 @@
 //                    CTA and pass) instead of being re-read from L2 by every warp.  Per 128
 //                    columns a lane reads one word per row and two 16-byte x values shared by
 //                    the kRows rows (all conflict-free shared-memory loads), then 4 x kRows DFMA.
-//   k_rowsum_sparse  one sparse chunk per warp, x gathered through L1/L2.
+//   k_rowsum_sparse  one per-cell chunk (negative or very large values) per CTA, x gathered
+//                    through L1/L2.
 //
 // Integer -> double by exponent splice (one DADD) instead of I2F.F64.
 #include <type_traits>
@@ -281,10 +282,11 @@ k_rowsum_sparse(const uint8_t *__restrict__ data, const int64_t *__restrict__ of
                 const double *__restrict__ x, double *__restrict__ partial,
                 const IceState *__restrict__ state) {
   if (state && state->stopped) return;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t i = warp; i < ns; i += nwarp) {
+  // one CTA per chunk (these chunks are few: cells with negative or very large values): the
+  // gathers of a chunk are spread over 8 warps, warp sums are added in warp order
+  __shared__ double wsum[8];
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5, tid = threadIdx.x;
+  for (int64_t i = blockIdx.x; i < ns; i += gridDim.x) {
     const int32_t c = ids[i];
     const int4 d = desc[c];
     const uint8_t *p = data + off[c];
@@ -293,10 +295,10 @@ k_rowsum_sparse(const uint8_t *__restrict__ data, const int64_t *__restrict__ of
     if ((d.z & 0xff) == ENC_S16) {
       const double *xb = x + d.x;
       const uint32_t *w = reinterpret_cast<const uint32_t *>(p);
-      int k = lane;
-      for (; k + 96 < n; k += 128) {
-        const uint32_t e0 = ldg_stream_u32(w + k), e1 = ldg_stream_u32(w + k + 32);
-        const uint32_t e2 = ldg_stream_u32(w + k + 64), e3 = ldg_stream_u32(w + k + 96);
+      int k = tid;
+      for (; k + 768 < n; k += 1024) {
+        const uint32_t e0 = ldg_stream_u32(w + k), e1 = ldg_stream_u32(w + k + 256);
+        const uint32_t e2 = ldg_stream_u32(w + k + 512), e3 = ldg_stream_u32(w + k + 768);
         const double x0 = __ldg(xb + (e0 & 0xffff)), x1 = __ldg(xb + (e1 & 0xffff));
         const double x2 = __ldg(xb + (e2 & 0xffff)), x3 = __ldg(xb + (e3 & 0xffff));
         a0 = fma(u2d(e0 >> 16), x0, a0);
@@ -304,16 +306,16 @@ k_rowsum_sparse(const uint8_t *__restrict__ data, const int64_t *__restrict__ of
         a2 = fma(u2d(e2 >> 16), x2, a2);
         a3 = fma(u2d(e3 >> 16), x3, a3);
       }
-      for (; k < n; k += 32) {
+      for (; k < n; k += 256) {
         const uint32_t e0 = ldg_stream_u32(w + k);
         a0 = fma(u2d(e0 >> 16), __ldg(xb + (e0 & 0xffff)), a0);
       }
     } else {                                     // ENC_S32
       const uint2 *w = reinterpret_cast<const uint2 *>(p);
-      int k = lane;
-      for (; k + 96 < n; k += 128) {
-        const uint2 e0 = ldg_stream_u64(w + k), e1 = ldg_stream_u64(w + k + 32);
-        const uint2 e2 = ldg_stream_u64(w + k + 64), e3 = ldg_stream_u64(w + k + 96);
+      int k = tid;
+      for (; k + 768 < n; k += 1024) {
+        const uint2 e0 = ldg_stream_u64(w + k), e1 = ldg_stream_u64(w + k + 256);
+        const uint2 e2 = ldg_stream_u64(w + k + 512), e3 = ldg_stream_u64(w + k + 768);
         const double x0 = __ldg(x + e0.x), x1 = __ldg(x + e1.x);
         const double x2 = __ldg(x + e2.x), x3 = __ldg(x + e3.x);
         a0 = fma(i2d((int32_t)e0.y), x0, a0);
@@ -321,13 +323,21 @@ k_rowsum_sparse(const uint8_t *__restrict__ data, const int64_t *__restrict__ of
         a2 = fma(i2d((int32_t)e2.y), x2, a2);
         a3 = fma(i2d((int32_t)e3.y), x3, a3);
       }
-      for (; k < n; k += 32) {
+      for (; k < n; k += 256) {
         const uint2 e0 = ldg_stream_u64(w + k);
         a0 = fma(i2d((int32_t)e0.y), __ldg(x + e0.x), a0);
       }
     }
     const double a = warp_sum((a0 + a1) + (a2 + a3));
-    if (lane == 0) partial[c] = a;
+    if (lane == 0) wsum[wic] = a;
+    __syncthreads();
+    if (tid == 0) {
+      double t = wsum[0];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) t += wsum[q];
+      partial[c] = t;
+    }
+    __syncthreads();
   }
 }
 
@@ -350,8 +360,8 @@ void launch_rowsum_chunks(tb_store *s, const double *x, const IceState *state) {
         s->enc_data.p, s->groups.p, s->group_range.p, s->enc_desc.p, x, s->partial_f.p, state);
   }
   if (s->n_sparse) {
-    int64_t need = (s->n_sparse + 7) / 8, cap = (int64_t)s->sm_count * 8;
-    const int grid = (int)(need < cap ? need : cap);
+    const int64_t cap = (int64_t)s->sm_count * 8;
+    const int grid = (int)(s->n_sparse < cap ? s->n_sparse : cap);
     k_rowsum_sparse<<<grid, 256, 0, s->stream>>>(s->enc_data.p, s->enc_off.p, s->enc_desc.p,
                                                  s->work_ids.p, s->n_sparse, x, s->partial_f.p, state);
   }
