@@ -70,6 +70,31 @@ def main():
     r2, c2, w2 = shuf.export_upper()
     assert np.array_equal(r2, rows) and np.array_equal(c2, cols) and np.array_equal(w2, v2)
 
+    # value boundaries of the encodings (D8 byte, tile cell 2^15, D16, int32) placed on dense rows,
+    # and a few very long sparse rows among short ones (tiles split by their busiest warp)
+    edge = np.array([255, 256, 32767, 32768, 65535, 65536, 2147483647, -1, -3, 0], dtype=np.int64)
+    v3 = vals.copy()
+    pick = rng.choice(rows.size, 50 * edge.size, replace=False)
+    v3[pick] = np.tile(edge, 50).astype(np.int32)
+    long_rows = np.array([7, 1033, 2050, 4100, 5999])
+    extra_r, extra_c = [], []
+    have = set(zip(rows.tolist(), cols.tolist()))
+    for r in long_rows:
+        for c in range(0, n, 2):
+            i, j = (r, c) if r <= c else (c, r)
+            if (i, j) not in have:
+                have.add((i, j))
+                extra_r.append(i)
+                extra_c.append(j)
+    r3 = np.concatenate([rows, np.array(extra_r, dtype=np.int32)])
+    c3 = np.concatenate([cols, np.array(extra_c, dtype=np.int32)])
+    w3 = np.concatenate([v3, np.ones(len(extra_r), dtype=np.int32)])
+    skew = ContactStore.from_coo(n, r3, c3, w3, chromosomes=chroms)
+    run_path(skew, chroms, "edges+skew")
+    r4, c4, w4 = skew.export_upper()
+    order = np.lexsort((c3, r3))
+    assert np.array_equal(r4, r3[order]) and np.array_equal(c4, c3[order]) and np.array_equal(w4, w3[order])
+
     # dense single chromosome (D8 / D16 panels)
     chrom1 = OrderedDict([("chr1", 5000)])
     pd = SynthParams(seed=3, cis_scale=3.0e4, cis_alpha=1.08, trans_mean=0.0, vis_sigma=0.35,
@@ -93,7 +118,7 @@ def main():
         h.normalize_hic(iterations=20, max_dev=1e-5, silent=True)
         assert np.allclose(b, h.bias.to_array(), rtol=1e-12, atol=0)
     print("batch ok; raw sum %d, normalised sum %.6f" % (a.sum(), a.sum(a.bias)))
-    for s in (syn, coo, shuf, dense):
+    for s in (syn, coo, shuf, skew, dense):
         s.close()
     from tadbit_b200._capi import trim_memory
     trim_memory()
