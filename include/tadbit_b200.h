@@ -121,8 +121,9 @@ int tb_store_set_option(tb_store *s, const char *name, const char *value);
 /* Layout of the compact row-sum stream (tadbit_b200/csrc/encode.cu, tiles.cu):
  * out[0] chunk payload bytes, out[1..6] chunks encoded as S32, S16, D32, D16, D8, T (cells in
  * the sparse tiles), out[7] chunks, out[8] CSR bytes, out[9] cells in sparse tiles, out[10]
- * the same with padding, out[11] tile work units, out[12] overflow cells of dense chunks,
- * out[13] bytes of the sparse tiles. */
+ * the same with padding, out[11] tile work units, out[12] cells kept in overflow lists behind
+ * dense chunks (value fits neither the slot nor a tile cell), out[13] bytes of the sparse tiles,
+ * out[14] cells of D8 chunks stored in the sparse tiles (255 < count < 2^15). */
 int tb_store_layout(const tb_store *s, int64_t out[16]);
 
 /* Export the owned upper-triangle cells (row in block, row <= col), row-major sorted.

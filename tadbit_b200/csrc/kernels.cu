@@ -17,7 +17,7 @@ namespace tb {
 
 namespace {
 
-enum { M_F64 = 0, M_F64_COUNT = 1, M_I64 = 2, M_I64_MASKED = 3 };
+enum { M_F64 = 0, M_I64 = 1, M_I64_MASKED = 2 };
 
 __device__ __forceinline__ int32_t ld_stream(const int32_t *p) {
   int32_t r;   // streamed once: keep it out of L1 so the gathered vector stays resident
@@ -40,20 +40,19 @@ k_chunk_reduce(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
   for (int64_t c = warp; c < nchunks; c += nwarp) {
     const int64_t beg = chunk_beg[c], end = chunk_beg[c + 1];
     double fa = 0.0, fb = 0.0;
-    long long ia = 0, ic = 0;
+    long long ia = 0;
     int64_t k = beg + lane;
     for (; k + 96 < end; k += 128) {
       int32_t c0 = ld_stream(col + k), c1 = ld_stream(col + k + 32);
       int32_t c2 = ld_stream(col + k + 64), c3 = ld_stream(col + k + 96);
       int32_t v0 = ld_stream(val + k), v1 = ld_stream(val + k + 32);
       int32_t v2 = ld_stream(val + k + 64), v3 = ld_stream(val + k + 96);
-      if (MODE == M_F64 || MODE == M_F64_COUNT) {
+      if (MODE == M_F64) {
         double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
         fa = fma((double)v0, x0, fa);
         fb = fma((double)v1, x1, fb);
         fa = fma((double)v2, x2, fa);
         fb = fma((double)v3, x3, fb);
-        if (MODE == M_F64_COUNT) ic += (x0 != 0.0) + (x1 != 0.0) + (x2 != 0.0) + (x3 != 0.0);
       } else if (MODE == M_I64) {
         ia += (long long)v0 + v1 + v2 + v3;
       } else {
@@ -63,25 +62,19 @@ k_chunk_reduce(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
     }
     for (; k < end; k += 32) {
       int32_t c0 = ld_stream(col + k), v0 = ld_stream(val + k);
-      if (MODE == M_F64 || MODE == M_F64_COUNT) {
+      if (MODE == M_F64) {
         double x0 = __ldg(x + c0);
         fa = fma((double)v0, x0, fa);
-        if (MODE == M_F64_COUNT) ic += (x0 != 0.0);
       } else if (MODE == M_I64) {
         ia += v0;
       } else {
         ia += bad[c0] ? 0 : v0;
       }
     }
-    if (MODE == M_F64 || MODE == M_F64_COUNT) {
+    if (MODE == M_F64) {
       fa += fb;
       for (int o = 16; o; o >>= 1) fa += __shfl_xor_sync(0xffffffffu, fa, o);
-      if (MODE == M_F64_COUNT)
-        for (int o = 16; o; o >>= 1) ic += __shfl_xor_sync(0xffffffffu, ic, o);
-      if (lane == 0) {
-        pf[c] = fa;
-        if (MODE == M_F64_COUNT) pi[c] = ic;
-      }
+      if (lane == 0) pf[c] = fa;
     } else {
       for (int o = 16; o; o >>= 1) ia += __shfl_xor_sync(0xffffffffu, ia, o);
       if (lane == 0) pi[c] = ia;
@@ -89,8 +82,6 @@ k_chunk_reduce(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
   }
 }
 
-// out[rb + r] = sum of the row's chunk partials, in chunk order.  WITH_COUNT also writes the
-// count partials (as exact doubles) to out[N + rb + r] so one all-reduce carries both.
 // sum over the work units of the row's block of the sparse-tile partials (tiles.cu), unit order
 struct TileSums {
   const double *partial;        // null when the store has no sparse tiles
@@ -105,23 +96,17 @@ __device__ __forceinline__ double tile_sum(const TileSums &ts, int64_t r) {
   return a;
 }
 
-template <bool WITH_COUNT>
-__global__ void k_combine_f64(const double *__restrict__ pf, const long long *__restrict__ pc,
-                              const int64_t *__restrict__ row_chunk, int64_t nrows, int64_t rb,
-                              int64_t nbins, double *__restrict__ out,
+// out[rb + r] = sum of the row's chunk partials in chunk order + its sparse-tile sums
+__global__ void k_combine_f64(const double *__restrict__ pf, const int64_t *__restrict__ row_chunk,
+                              int64_t nrows, int64_t rb, double *__restrict__ out,
                               const IceState *__restrict__ state, TileSums ts) {
   if (state && state->stopped) return;
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
        r += (int64_t)gridDim.x * blockDim.x) {
     double a = 0.0;
-    long long n = 0;
-    for (int64_t c = row_chunk[r]; c < row_chunk[r + 1]; ++c) {
-      a += pf[c];
-      if (WITH_COUNT) n += pc[c];
-    }
+    for (int64_t c = row_chunk[r]; c < row_chunk[r + 1]; ++c) a += pf[c];
     a += tile_sum(ts, r);
     out[rb + r] = a;
-    if (WITH_COUNT) out[nbins + rb + r] = (double)n;
   }
 }
 
@@ -200,7 +185,7 @@ k_ice_reduce(double *__restrict__ s_full, const double *__restrict__ x,
              const uint8_t *__restrict__ bad, uint8_t *__restrict__ present, int64_t n,
              int pass, int iterations, double max_dev, double *__restrict__ block_red,
              double *__restrict__ trace, IceState *state, const double *__restrict__ pf,
-             const long long *__restrict__ pc, const int64_t *__restrict__ row_chunk, TileSums ts) {
+             const int64_t *__restrict__ row_chunk, TileSums ts) {
   if (state->stopped) return;
   __shared__ double sh_sum[kRedThreads / 32], sh_min[kRedThreads / 32], sh_max[kRedThreads / 32];
   __shared__ long long sh_cnt[kRedThreads / 32];
@@ -471,7 +456,7 @@ k_seg_reduce(double *__restrict__ s_full, const double *__restrict__ x,
              const int64_t *__restrict__ seg_off, int nseg, int64_t nbins, int pass, int iterations,
              double max_dev,
              double *__restrict__ trace, int npass_max, SegState *seg, unsigned int *n_stopped,
-             IceState *state, const double *__restrict__ pf, const long long *__restrict__ pc,
+             IceState *state, const double *__restrict__ pf,
              const int64_t *__restrict__ row_chunk, TileSums ts) {
   const int k = blockIdx.x;
   if (seg[k].stopped) return;
@@ -656,16 +641,16 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
     TB_CUDA(cudaEventRecord(ev[2 * p + 1], st));
     if (s->world > 1) {
       if (s->nrows)
-        k_combine_f64<false><<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
-            s->partial_f.p, s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, N, dst, s->state.p, ts);
+        k_combine_f64<<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
+            s->partial_f.p, s->row_chunk.p, s->nrows, s->row_begin, dst, s->state.p, ts);
       allreduce_f64(s, s->s_part.p, s->s_full.p, p == 0 ? 2 * N : N);
       k_ice_reduce<false><<<rg, kRedThreads, 0, st>>>(
           s->s_full.p, s->x.p, s->bad.p, s->present.p, N, p, iterations, max_dev, s->block_red.p,
-          s->trace.p, s->state.p, nullptr, nullptr, nullptr, ts);
+          s->trace.p, s->state.p, nullptr, nullptr, ts);
     } else {
       k_ice_reduce<true><<<rg, kRedThreads, 0, st>>>(
           s->s_full.p, s->x.p, s->bad.p, s->present.p, N, p, iterations, max_dev, s->block_red.p,
-          s->trace.p, s->state.p, s->partial_f.p, s->partial_i.p, s->row_chunk.p, ts);
+          s->trace.p, s->state.p, s->partial_f.p, s->row_chunk.p, ts);
     }
     k_ice_update<<<vg, 256, 0, st>>>(s->s_full.p, s->x.p, s->b.p, s->present.p, N, p, s->state.p);
     ++launched;
@@ -757,8 +742,8 @@ void norm_sum(tb_store *s, const double *h_bias, const uint8_t *h_bad, double *o
     launch_rowsum(s, s->x.p, nullptr);
   }
   if (s->nrows)
-    k_combine_f64<false><<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
-        s->partial_f.p, s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, N, s->s_full.p,
+    k_combine_f64<<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
+        s->partial_f.p, s->row_chunk.p, s->nrows, s->row_begin, s->s_full.p,
         nullptr, TileSums{(!use_csr_rowsum(s) && s->t_nunits) ? s->t_partial.p : nullptr,
                           s->t_unit_of_rb.p});
   k_dot_rows<<<1, 1024, 0, st>>>(s->x.p, s->s_full.p, s->row_begin, s->row_end, s->scal_f.p);
@@ -830,8 +815,7 @@ void ice_batch(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max
     else launch_rowsum(s, s->x.p, s->state.p);
     k_seg_reduce<<<nseg, 1024, 0, st>>>(s->s_full.p, s->x.p, s->bad.p, s->present.p, seg_off.p, nseg,
                                         N, p, iterations, max_dev, trace.p, npass_max, seg.p,
-                                        n_stopped.p, s->state.p, s->partial_f.p, s->partial_i.p,
-                                        s->row_chunk.p, ts);
+                                        n_stopped.p, s->state.p, s->partial_f.p, s->row_chunk.p, ts);
     k_seg_update<<<vg, 256, 0, st>>>(s->s_full.p, s->x.p, s->b.p, s->present.p, s->chrom_of.p, N, p,
                                      seg.p);
     ++launched;
