@@ -111,18 +111,12 @@ def dist_setup(args):
 
 def cpu_baseline(wl, nbins, device, threads=None):
     """The oracle port on a bounded sample: the leading nbins x nbins block of the same
-    synthetic model (generated on the device, exported, then balanced on the host)."""
+    synthetic model, generated on the host (oracle/synth_port.c) and balanced on the host --
+    no GPU and no product code on this leg."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import tadbit_oracle as orc
-    import tadbit_b200
-    from collections import OrderedDict
     nbins = min(nbins, wl["size"])
-    first = next(iter(wl["chromosomes"]))
-    chroms = OrderedDict([(first, nbins)]) if wl["chromosomes"][first] >= nbins else None
-    store = tadbit_b200.ContactStore.synthetic(nbins, wl["params"], chromosomes=chroms,
-                                               device=device)
-    r, c, v = store.export_upper()
-    store.close()
+    r, c, v = orc.synthetic_block(nbins, wl["params"], wl["chromosomes"])
     m = orc.OracleMatrix(nbins, r, c, v)
     # pass loop in C + OpenMP (oracle/ice_port.c); only the loop is timed, the CSR build is not
     bias, trace, cores, dt = orc.iterative_fast(m, {}, ITERATIONS, MAX_DEV, threads)
@@ -136,8 +130,7 @@ def run_reference(args, rank, world):
     the oracle port (validated against the unmodified reference's golden vectors)."""
     if rank != 0:
         return
-    import tadbit_b200
-    from tadbit_b200 import workloads
+    from tadbit_b200 import workloads                    # workload definitions only (no library call)
     name = args.workload if args.workload != "auto" else "c3"
     wl = workloads.workload(name)
     vals = []

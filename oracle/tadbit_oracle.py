@@ -326,6 +326,41 @@ def _load_port():
     return _PORT or None
 
 
+def synthetic_block(nbins, params, chromosomes=None):
+    """Upper-triangle cells (rows, cols, vals; int32, row-major sorted) of the leading
+    ``nbins`` x ``nbins`` block of the synthetic Hi-C model of SURVEY.md 8d, generated on the
+    CPU by oracle/synth_port.c.  ``params`` is any object with the fields seed, cis_scale,
+    cis_alpha, trans_mean, vis_sigma, low_frac, low_scale, empty_frac; ``chromosomes`` an
+    ordered mapping name -> bins (the block is cut out of their concatenation).  Used by
+    bench.py's CPU legs so that they need neither a GPU nor any product code."""
+    import ctypes
+
+    class _Params(ctypes.Structure):
+        _fields_ = [("seed", ctypes.c_uint64)] + [(k, ctypes.c_double) for k in (
+            "cis_scale", "cis_alpha", "trans_mean", "vis_sigma", "low_frac", "low_scale", "empty_frac")]
+
+    lib = _load_port()
+    if lib is None or not hasattr(lib, "synth_block"):
+        raise RuntimeError("oracle/_build/libice_port.so is missing or stale: run `make -C oracle`")
+    cp = _Params(int(params.seed), *[float(getattr(params, k[0])) for k in _Params._fields_[1:]])
+    sizes = [int(v) for v in chromosomes.values()] if chromosomes else [int(nbins)]
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    fn = lib.synth_block
+    fn.restype = ctypes.c_int64
+    fn.argtypes = [ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    n = fn(int(nbins), len(sizes), offs.ctypes.data, ctypes.addressof(cp), None, None, None)
+    if n < 0:
+        raise MemoryError("synth_block")
+    rows = np.empty(n, dtype=np.int32)
+    cols = np.empty(n, dtype=np.int32)
+    vals = np.empty(n, dtype=np.int32)
+    got = fn(int(nbins), len(sizes), offs.ctypes.data, ctypes.addressof(cp), rows.ctypes.data,
+             cols.ctypes.data, vals.ctypes.data)
+    assert got == n
+    return rows, cols, vals
+
+
 def iterative_fast(m, bads=None, iterations=0, max_dev=0.00001, threads=None):
     """Same as :func:`iterative` with the pass loop in C + OpenMP (oracle/ice_port.c).
 

@@ -52,3 +52,26 @@ def test_large_roundtrip_export_rebuild():
     b1, t1 = s.ice(None, 100, 1e-5)
     b2, t2 = t.ice(None, 100, 1e-5)
     assert np.array_equal(b1, b2) and len(t1) == len(t2)
+
+
+@pytest.mark.gpu
+def test_device_generator_agrees_with_cpu_generator():
+    """Two independent implementations of the synthetic model (synth.cu on the device,
+    oracle/synth_port.c on the host, the input of bench.py's CPU legs): same cells except where
+    single-precision libm and the device round a Poisson threshold differently."""
+    from collections import OrderedDict
+    import tadbit_oracle as orc
+    import tadbit_b200
+    chroms = OrderedDict([("chrA", 1400), ("chrB", 900), ("chrC", 500)])
+    n = 2800
+    p = tadbit_b200.SynthParams(seed=20261019, cis_scale=600.0, cis_alpha=1.08, trans_mean=0.02,
+                                vis_sigma=0.35, low_frac=0.03, low_scale=0.02, empty_frac=0.01)
+    store = tadbit_b200.ContactStore.synthetic(n, p, chromosomes=chroms)
+    r, c, v = store.export_upper()
+    store.close()
+    r2, c2, v2 = orc.synthetic_block(n, p, chroms)
+    a = dict(zip((r.astype(np.int64) * n + c).tolist(), v.tolist()))
+    b = dict(zip((r2.astype(np.int64) * n + c2).tolist(), v2.tolist()))
+    differing = sum(1 for k in a.keys() | b.keys() if a.get(k, 0) != b.get(k, 0))
+    assert differing <= 1e-4 * len(a), (differing, len(a))
+    assert abs(int(v.sum()) - int(v2.sum())) <= 1e-4 * int(v.sum())
