@@ -9,15 +9,29 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.gpu
-def test_kernel_coverage_script():
+def _run(extra_env):
+    env = dict(os.environ, **extra_env)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "kernel_coverage.py")],
-                         capture_output=True, text=True, timeout=600)
+                         capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "KERNEL_COVERAGE_OK" in out.stdout
+    return [l for l in out.stdout.splitlines() if "enc=" in l]
+
+
+@pytest.mark.gpu
+def test_kernel_coverage_script():
+    lines = _run({})
     # the inputs are built to reach the dense, per-cell and tile encodings
-    lines = [l for l in out.stdout.splitlines() if "enc=" in l]
     assert any("'D16': 0" not in l for l in lines)
     assert any("'S32': 0" not in l for l in lines)
     assert any("'S16': 0" not in l for l in lines)
     assert all("'T': 0" not in l for l in lines)
+
+
+@pytest.mark.gpu
+def test_kernel_coverage_without_tiles():
+    """TB_TILES=0 (A/B switch): sparse cells stay per-cell chunks, large cells of dense chunks
+    stay in their overflow lists -- the list walk at the end of a dense group gets real work."""
+    lines = _run({"TB_TILES": "0"})
+    assert all("'T': 0" in l and "tile_cells=0" in l for l in lines)
+    assert any("overflow=0" not in l for l in lines)
