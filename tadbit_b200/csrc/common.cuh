@@ -92,7 +92,10 @@ struct IceState {
 constexpr int kWarp = 32;
 constexpr int kChunk = 4096;      // max stored cells one warp reduces before writing a partial
 constexpr int kPanel = 4096;      // column panel of the chunk planner / dense encodings
-constexpr int kSub = 1024;        // bytes per row per pipeline stage of k_rowsum_dense
+#ifndef TB_KSUB
+#define TB_KSUB 1024
+#endif
+constexpr int kSub = TB_KSUB;     // bytes per row per pipeline stage of k_rowsum_dense
 constexpr int kRows = 4;          // dense chunks (rows) one warp walks together
 constexpr int kXPad = 16384;      // zero tail of the gathered vector (panels / windows read past N)
 constexpr int kTileRows = 2048;   // rows of a sparse tile (two per thread of a k_rowsum_tiles CTA)
