@@ -100,6 +100,9 @@ constexpr int kRows = 4;          // dense chunks (rows) one warp walks together
 constexpr int kXPad = 16384;      // zero tail of the gathered vector (panels / windows read past N)
 constexpr int kTileRows = 2048;   // rows of a sparse tile (two per thread of a k_rowsum_tiles CTA)
 constexpr int kTileCols = 4 * kPanel;  // columns of a sparse tile = x window in shared memory (128 KB)
+#ifndef TB_TILES16
+#define TB_TILES16 1     // sparse tiles: 1 = two-section layout (tiles16.cu), 0 = 32-bit cells only (tiles.cu)
+#endif
 constexpr int kTileValBits = 15;  // packed tile cell: (column offset * 4) << 16 | value, value < 2^15
 
 // chunk encodings of the compact row-sum stream; ENC_T = the cells live in the sparse tiles
