@@ -33,6 +33,10 @@ namespace {
 #ifndef TB_TILE_WARPS
 #define TB_TILE_WARPS 16
 #endif
+#ifndef TB_FILL_HIST
+#define TB_FILL_HIST 0      // 1: k_tile_fill counts residues in a shared-memory histogram per warp
+#endif                      //    (match_any + one add per group) instead of 32 ballots per 32 cells;
+                            //    written at the end of round 1, not yet run on a GPU
 constexpr int kSortThreads = kTileRows / 2;                // k_tile_sort
 constexpr int kTileWarps = TB_TILE_WARPS;                  // warps of a k_rowsum_tiles CTA
 constexpr int kTileThreads = kTileWarps * 32;
@@ -257,6 +261,9 @@ struct SlotTables {
 // slot of the t-th cell of a section (base lane 0 or 16) that found no step of its own residue
 __device__ __forceinline__ void leftover_slot(const SlotTables &tb_, int base, int t, bool want, int &r2,
                                               int &m2) {
+#if TB_FILL_HIST
+  if (!__any_sync(0xffffffffu, want)) return;          // every cell of the block found its own bank
+#endif
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
     const int fb = __shfl_sync(0xffffffffu, tb_.freebase, base + q);
@@ -277,6 +284,10 @@ k_tile_fill(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
   const unsigned lt = (1u << lane) - 1u;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+#if TB_FILL_HIST
+  __shared__ int s_hist[8][32];                        // per warp: cells per key / cells placed per key
+  int *hist = s_hist[threadIdx.x >> 5];
+#endif
   for (int64_t r = warp; r < nrows; r += nwarp) {
     const int64_t rb = r / kTileRows;
     RowCursor cur;
@@ -297,6 +308,10 @@ k_tile_fill(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
       const RowCursor start = cur;
       // sweep 1: cells per (section, residue): lane q counts key q = 16 * general + residue
       int b = 0;
+#if TB_FILL_HIST
+      hist[lane] = 0;
+      __syncwarp();
+#endif
       for (;;) {
         const int64_t idx = cur.k + lane;
         const int32_t cc = idx < cur.kend ? col[idx] : 0x7fffffff;
@@ -305,13 +320,26 @@ k_tile_fill(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
         const bool act = inwin && (!cur.filter || tile_overflow(vv));
         const int key = (cc & 15) + ((cur.filter || vv != 1) ? 16 : 0);
         const int na = __popc(__ballot_sync(0xffffffffu, inwin));
+#if TB_FILL_HIST
+        // lanes with the same key form a group; its first lane adds the group to the histogram
+        const unsigned grp = __match_any_sync(0xffffffffu, act ? key : 32 + lane);
+        if (act && (grp & lt) == 0u) hist[key] += __popc(grp);
+        __syncwarp();
+#else
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
           const unsigned m = __ballot_sync(0xffffffffu, act && key == q);
           if (lane == q) b += __popc(m);
         }
+#endif
         if (!cur.advance(na, col, whi)) break;
       }
+#if TB_FILL_HIST
+      b = hist[lane];
+      __syncwarp();
+      hist[lane] = 0;                        // reused as the cells placed per key in sweep 2
+      __syncwarp();
+#endif
       // steps of residue q for this lane: k = ((q - l) & 15) + 16 m, m < req
       const int L = lane < 16 ? L1 : L2;
       const int d = ((lane & 15) - l) & 15;
@@ -333,7 +361,9 @@ k_tile_fill(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
       tabs.freebase = fi - tabs.fre;
       // sweep 2: place the cells
       cur = start;
+#if !TB_FILL_HIST
       int run = 0;
+#endif
       for (;;) {
         const int64_t idx = cur.k + lane;
         const int32_t cc = idx < cur.kend ? col[idx] : 0x7fffffff;
@@ -344,7 +374,14 @@ k_tile_fill(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
         const int key = (cc & 15) + general;
         const int na = __popc(__ballot_sync(0xffffffffu, inwin));
         const unsigned same = __match_any_sync(0xffffffffu, act ? key : 32 + lane);
+#if TB_FILL_HIST
+        const int m = hist[key] + __popc(same & lt);
+        __syncwarp();                        // every lane has read the counts of this block
+        if (act && (same & lt) == 0u) hist[key] += __popc(same);
+        __syncwarp();
+#else
         const int m = __shfl_sync(0xffffffffu, run, key) + __popc(same & lt);
+#endif
         const int sv = __shfl_sync(0xffffffffu, tabs.served, key);
         const int lb = __shfl_sync(0xffffffffu, leftbase, key);
         int r2 = key & 15, m2 = m;
@@ -354,11 +391,13 @@ k_tile_fill(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
           if (general) out2[(ks >> 2) * 128 + (ks & 3)] = pack_cell(cc - wlo, vv);
           else out1[(ks >> 3) * 256 + (ks & 7)] = (uint16_t)(cc - wlo);
         }
+#if !TB_FILL_HIST
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
           const unsigned mq = __ballot_sync(0xffffffffu, act && key == q);
           if (lane == q) run += __popc(mq);
         }
+#endif
         if (!cur.advance(na, col, whi)) break;
       }
     }
