@@ -1,3 +1,5 @@
+"""Wall time of `tb_store_create_coo` (stage by stage, TB_TIMING=1), `tb_ice` and destruction
+for one synthetic workload whose cells sit in pinned host memory: python tools/e2e_breakdown.py c3"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, tadbit_b200
