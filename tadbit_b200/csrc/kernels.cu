@@ -11,6 +11,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace tb {
@@ -620,6 +623,14 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
 
   std::vector<cudaEvent_t> ev(2 * (size_t)npass_max + 2);
   for (auto &e : ev) TB_CUDA(cudaEventCreate(&e));
+  // TB_TIMING=1 on several GPUs: where the time between two row sums goes (combine, all-reduce,
+  // statistics + update), printed per rank after the call
+  const char *tenv = getenv("TB_TIMING");
+  std::vector<cudaEvent_t> evx;
+  if (s->world > 1 && tenv && tenv[0] == '1') {
+    evx.resize(3 * (size_t)npass_max);
+    for (auto &e : evx) TB_CUDA(cudaEventCreate(&e));
+  }
   double *dst = s->world > 1 ? s->s_part.p : s->s_full.p;
   const bool csr_walk = use_csr_rowsum(s);
   const TileSums ts = {(!csr_walk && s->t_nunits) ? s->t_partial.p : nullptr, s->t_unit_of_rb.p};
@@ -643,7 +654,9 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
       if (s->nrows)
         k_combine_f64<<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
             s->partial_f.p, s->row_chunk.p, s->nrows, s->row_begin, dst, s->state.p, ts);
+      if (!evx.empty()) TB_CUDA(cudaEventRecord(evx[3 * p], st));
       allreduce_f64(s, s->s_part.p, s->s_full.p, p == 0 ? 2 * N : N);
+      if (!evx.empty()) TB_CUDA(cudaEventRecord(evx[3 * p + 1], st));
       k_ice_reduce<false><<<rg, kRedThreads, 0, st>>>(
           s->s_full.p, s->x.p, s->bad.p, s->present.p, N, p, iterations, max_dev, s->block_red.p,
           s->trace.p, s->state.p, nullptr, nullptr, ts);
@@ -653,6 +666,7 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
           s->trace.p, s->state.p, s->partial_f.p, s->row_chunk.p, ts);
     }
     k_ice_update<<<vg, 256, 0, st>>>(s->s_full.p, s->x.p, s->b.p, s->present.p, N, p, s->state.p);
+    if (!evx.empty()) TB_CUDA(cudaEventRecord(evx[3 * p + 2], st));
     ++launched;
     if (p + 1 >= next_poll || p == npass_max - 1) {
       TB_CUDA(cudaMemcpyAsync(s->h_state.p, s->state.p, sizeof(IceState), cudaMemcpyDeviceToHost, st));
@@ -705,6 +719,24 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
     const int k1 = csr_walk ? 1 : (s->t_nunits > 0) + (s->n_groups > 0) + (s->n_sparse > 0);
     const int k2 = 2 + (s->world > 1 && s->nrows ? 1 : 0);       // (combine) + reduce + update
     s->total_launches = 4 /* init, live, bad partners, finalize */ + launched * (k1 + k2);
+  }
+  if (!evx.empty()) {
+    double t_comb = 0, t_red = 0, t_upd = 0;
+    int cnt = 0;
+    for (int p = 1; p < real && p < launched; ++p) {       // pass 0 carries 2N in the all-reduce
+      float a = 0.f, b = 0.f, c = 0.f;
+      cudaEventElapsedTime(&a, ev[2 * p + 1], evx[3 * p]);
+      cudaEventElapsedTime(&b, evx[3 * p], evx[3 * p + 1]);
+      cudaEventElapsedTime(&c, evx[3 * p + 1], evx[3 * p + 2]);
+      t_comb += a; t_red += b; t_upd += c;
+      ++cnt;
+    }
+    if (cnt)
+      fprintf(stderr, "[tadbit_b200] rank %d: per pass row sum %.1f us, combine %.1f us, all-reduce %.1f us, "
+                      "statistics + update %.1f us (%d passes)\n", s->rank,
+              1e3 * s->rowsum_ms / (s->rowsum_launches ? s->rowsum_launches : 1), 1e3 * t_comb / cnt,
+              1e3 * t_red / cnt, 1e3 * t_upd / cnt, cnt);
+    for (auto &e : evx) cudaEventDestroy(e);
   }
   for (auto &e : ev) cudaEventDestroy(e);
   return rc;
