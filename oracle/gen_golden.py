@@ -163,6 +163,59 @@ def run_case(ns, name, hic, ice_configs=ICE_CONFIGS, filter_kw=None, extra=None)
     return out
 
 
+def reference_known_answers(ns):
+    """The two known-answer tests of the reference that run through the balancing path
+    (test/test_all.py:312-334 test_09_hic_normalization, :380-405 test_11_write_interaction_pairs),
+    replayed with the UNMODIFIED reference classes: Experiment.load_hic_data, filter_columns,
+    normalize_hic, get_hic_zscores, write_interaction_pairs.  The asserted literals of those
+    tests (4059.2877; 4674 lines, 0.5852295196345679, 0.07060448846960976) are reproduced here and
+    stored next to the intermediate biases, so that the oracle and the CUDA path can be pinned to
+    the reference's own expectations."""
+    import tempfile
+    ref_shim._stub("pytadbit.modelling.structuralmodels", StructuralModels=object)
+    from pytadbit.experiment import Experiment
+    base = os.path.join(ns.root, "test", "20Kb", "chrT")
+    out = {"source": "reference test/test_all.py:312-334 and :380-405, replayed by oracle/gen_golden.py",
+           "fixture": "chrT_20Kb_A"}
+    with contextlib.redirect_stderr(io.StringIO()), contextlib.redirect_stdout(io.StringIO()):
+        # test_09: no column filter, normalize_hic() defaults (one pass, factor=1)
+        exp = Experiment("exp1", 20000, hic_data=os.path.join(base, "chrT_D.tsv"))
+        exp.load_hic_data(os.path.join(base, "chrT_A.tsv"), silent=True)
+        exp.normalize_hic(silent=True)
+        exp.get_hic_zscores()
+        exp.get_hic_zscores(zscored=False)
+        sumz = sum(exp._zscores[k1][k2] for k1 in exp._zscores for k2 in exp._zscores[k1])
+        bias = exp.hic_data[0].bias
+        out["test_09"] = {"zeros": sorted(int(k) for k in exp._zeros),
+                          "bias": [float(bias[i]) for i in range(exp.size)],
+                          "sum_normalised": float(sumz), "asserted_rounded_4": 4059.2877,
+                          "pairs": sum(len(v) for v in exp._zscores.values())}
+        # test_11: filter_columns, normalize_hic(factor=1), normalised values written pair by pair
+        exp = Experiment("exp1", 20000, hic_data=os.path.join(base, "chrT_D.tsv"))
+        exp.load_hic_data(os.path.join(base, "chrT_A.tsv"), silent=True)
+        exp.filter_columns(silent=True)
+        exp.normalize_hic(factor=1, silent=True)
+        exp.get_hic_zscores(zscored=False)
+        with tempfile.TemporaryDirectory() as tmp:
+            fname = os.path.join(tmp, "pairs.tsv")
+            exp.write_interaction_pairs(fname)
+            lines = open(fname).read().splitlines()
+        bias = exp.hic_data[0].bias
+        out["test_11"] = {"zeros": sorted(int(k) for k in exp._zeros),
+                          "bias": [float(bias[i]) for i in range(exp.size)],
+                          "lines": len(lines), "asserted_lines": 4674,
+                          "line_25": lines[25].split("\t"), "asserted_line_25_value": 0.5852295196345679,
+                          "line_2000": lines[2000].split("\t"),
+                          "asserted_line_2000_value": 0.07060448846960976}
+    assert round(out["test_09"]["sum_normalised"], 4) == 4059.2877
+    assert out["test_11"]["lines"] == 4674
+    assert abs(float(out["test_11"]["line_25"][2]) - 0.5852295196345679) < 1e-7
+    assert abs(float(out["test_11"]["line_2000"][2]) - 0.07060448846960976) < 1e-7
+    with open(os.path.join(OUT, "reference_known_answers.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_shim.load()
@@ -230,6 +283,8 @@ def main():
     run_case(ns, "all_bad_80", hic, filter_kw={"perc_zero": 1, "by_mean": False},
              ice_configs=[(0, 0.1, False, 1), (10, 1e-5, False, 1)])
     index.append("all_bad_80")
+
+    reference_known_answers(ns)
 
     with open(os.path.join(OUT, "INDEX.json"), "w") as fh:
         json.dump(dict(cases=index, numpy=np.__version__,

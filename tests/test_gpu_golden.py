@@ -102,3 +102,38 @@ def test_reference_test_values(hics):
     assert hic.expected[0] == 378.2323232323232
     assert hic.expected[1] == 120.42857142857143
     assert len(hic.expected) == 102
+
+
+# ---- the reference's own known-answer tests (test/test_all.py test_09, test_11) through the product
+def test_reference_test_09_hic_normalization(hics):
+    import _known_answers as ka
+    case, hic = load(ka.KNOWN["fixture"]), hics(ka.KNOWN["fixture"])
+    want = ka.KNOWN["test_09"]
+    hic.bads = {}
+    hic.normalize_hic(silent=True)                                 # defaults, as Experiment.normalize_hic
+    bias = hic.bias.to_array()
+    np.testing.assert_allclose(bias, np.array(want["bias"]), rtol=1e-12, atol=0)
+    lines = ka.pair_lines(case, bias, {})
+    assert len(lines) == want["pairs"]
+    total = sum(v for _, _, v in lines)
+    assert abs(total - want["sum_normalised"]) < 1e-8
+    assert round(total, 4) == round(ka.TEST_09_SUM, 4)            # reference test/test_all.py:332
+
+
+def test_reference_test_11_write_interaction_pairs(hics):
+    import _known_answers as ka
+    case, hic = load(ka.KNOWN["fixture"]), hics(ka.KNOWN["fixture"])
+    want = ka.KNOWN["test_11"]
+    hic.bads = {}
+    hic.filter_columns(silent=True)
+    assert sorted(hic.bads) == want["zeros"]
+    hic.normalize_hic(factor=1, silent=True)
+    bias = hic.bias.to_array()
+    np.testing.assert_allclose(bias, np.array(want["bias"]), rtol=1e-12, atol=0)
+    lines = ka.pair_lines(case, bias, hic.bads)
+    assert len(lines) == ka.TEST_11_LINES                         # reference test/test_all.py:400
+    assert tuple(k + 1 for k in lines[25][:2]) == tuple(int(x) for x in want["line_25"][:2])
+    assert abs(lines[25][2] - ka.TEST_11_LINE_25) < 1e-7          # assertAlmostEqual, :401
+    assert abs(lines[2000][2] - ka.TEST_11_LINE_2000) < 1e-7      # :402
+    assert abs(lines[25][2] - float(want["line_25"][2])) < 1e-12
+    assert abs(lines[2000][2] - float(want["line_2000"][2])) < 1e-12

@@ -81,3 +81,39 @@ def test_survey_pinned_values():
     exp = dict(case.out["expected"][0]["values"])
     assert exp[0] == 378.2323232323232 and exp[1] == 120.42857142857143
     assert case.out["expected"][0]["keys"] == 102
+
+
+# ---- the reference's own known-answer tests (test/test_all.py test_09, test_11) ---------------
+def test_reference_test_09_hic_normalization():
+    import _known_answers as ka
+    case = load(ka.KNOWN["fixture"])
+    m = orc.OracleMatrix(case.size, case.rows, case.cols, case.vals, chromosomes=case.chromosomes)
+    want = ka.KNOWN["test_09"]
+    assert want["zeros"] == []
+    bias, _, _ = orc.normalize_hic(m, bads={}, iterations=0, max_dev=0.1, factor=1)
+    np.testing.assert_allclose(bias, np.array(want["bias"]), rtol=1e-12, atol=0)
+    lines = ka.pair_lines(case, bias, {})
+    assert len(lines) == want["pairs"]
+    total = sum(v for _, _, v in lines)
+    assert abs(total - want["sum_normalised"]) < 1e-8
+    assert round(total, 4) == round(ka.TEST_09_SUM, 4)            # reference test/test_all.py:332
+
+
+def test_reference_test_11_write_interaction_pairs():
+    import _known_answers as ka
+    case = load(ka.KNOWN["fixture"])
+    m = orc.OracleMatrix(case.size, case.rows, case.cols, case.vals, chromosomes=case.chromosomes)
+    want = ka.KNOWN["test_11"]
+    bads = orc.filter_columns(m, silent=True)
+    assert sorted(bads) == want["zeros"]
+    bias, _, _ = orc.normalize_hic(m, bads=bads, iterations=0, max_dev=0.1, factor=1)
+    np.testing.assert_allclose(bias, np.array(want["bias"]), rtol=1e-12, atol=0)
+    lines = ka.pair_lines(case, bias, bads)
+    assert len(lines) == ka.TEST_11_LINES                         # reference test/test_all.py:400
+    # the pair file numbers bins from 1 (experiment.py write_interaction_pairs)
+    assert tuple(k + 1 for k in lines[25][:2]) == tuple(int(x) for x in want["line_25"][:2])
+    assert tuple(k + 1 for k in lines[2000][:2]) == tuple(int(x) for x in want["line_2000"][:2])
+    assert abs(lines[25][2] - ka.TEST_11_LINE_25) < 1e-7          # assertAlmostEqual, :401
+    assert abs(lines[2000][2] - ka.TEST_11_LINE_2000) < 1e-7      # :402
+    assert abs(lines[25][2] - float(want["line_25"][2])) < 1e-12
+    assert abs(lines[2000][2] - float(want["line_2000"][2])) < 1e-12
