@@ -2,8 +2,8 @@
 
 * a 20k-bin multi-chromosome synthetic matrix against the oracle (numpy restatement + C port)
   on the exported cells: mask bit-exact, biases 1e-10, expected bit-exact;
-* the dense chr1 @10 kb workload (BASELINE configs[1], 3e8 contacts) through size-independent
-  properties: the two independent K1 implementations (compact stream vs CSR walk) agree, integer
+* the dense chr1 @10 kb workload (BASELINE configs[1], 3e8 contacts) and the genome-wide 5 kb
+  workload of the bench (configs[2], 1.97e9 contacts) through size-independent properties: the two independent K1 implementations (compact stream vs CSR walk) agree, integer
   reductions are consistent with each other, the rescaled matrix sums to N^2."""
 from collections import OrderedDict
 
@@ -73,3 +73,41 @@ def test_full_size_properties_c2():
     store.set_option("rowsum", "compact")
     # factor=1 rescales so that the normalised matrix sums to N^2 (hic_data.py:406-412)
     assert abs(hic.sum(hic.bias) / float(n * n) - 1.0) < 1e-9
+
+
+def test_full_size_properties_c3():
+    """The bench workload (BASELINE configs[2], genome-wide 5 kb, 1.97e9 contacts) at full size:
+    exact integer identities, and the ICE loop over the compact stream (dense panels + two-section
+    sparse tiles) against the same loop over the plain CSR."""
+    import torch
+    import tadbit_b200
+    from tadbit_b200 import workloads
+    from tadbit_b200._capi import trim_memory
+    trim_memory()                                   # hand cached blocks of earlier tests back first
+    if torch.cuda.mem_get_info(0)[0] < 90 * (1 << 30):
+        pytest.skip("needs ~90 GB of free device memory")
+    wl = workloads.workload("c3")
+    n = wl["size"]
+    store = tadbit_b200.ContactStore.synthetic(n, wl["params"], chromosomes=wl["chromosomes"])
+    try:
+        hic = tadbit_b200.HiC_data.from_store(store, chromosomes=wl["chromosomes"])
+        info = store.info()
+        assert info["nnz_upper"] > 1.9e9
+        lay = store.layout()
+        assert lay["tile_cells"] > 1e9 and lay["encodings"]["D8"] > 1e6
+        hic.filter_columns(silent=True, by_mean=False)
+        nnz, rsum = store.row_stats()
+        assert int(nnz.sum()) == info["nnz_full"]
+        assert hic.bads == dict((int(i), True) for i in np.flatnonzero(n - nnz > int(n * 99.0 / 100)))
+        assert hic.sum(bads={-1: True}) == int(rsum.sum())
+        hic.normalize_hic(iterations=100, max_dev=1e-5, silent=True)
+        compact, passes = hic.bias.to_array().copy(), len(hic.last_trace)
+        assert np.isfinite(compact).all() and passes > 10
+        store.set_option("rowsum", "csr")
+        hic.normalize_hic(iterations=100, max_dev=1e-5, silent=True)
+        assert len(hic.last_trace) == passes
+        np.testing.assert_allclose(hic.bias.to_array(), compact, rtol=1e-11, atol=0)
+        store.set_option("rowsum", "compact")
+        assert abs(hic.sum(hic.bias) / float(n * n) - 1.0) < 1e-9
+    finally:
+        store.close()
