@@ -117,6 +117,11 @@ def test_random_matrix(seed):
                 np.allclose([float(x) for x in line.split()], [float(x) for x in (TRACE_FMT % tuple(t)).split()],
                             rtol=0, atol=2e-3)
         assert orc.matrix_sum(m, None, bads) == hic.sum()
+        # the C + OpenMP port of the pass loop (bench.py's CPU baseline) against iterative() itself
+        raw = ns.iterative(hic, bads=hic.bads, iterations=k["iterations"], max_dev=k["max_dev"])
+        fast, ftrace, _, _ = orc.iterative_fast(m, bads, k["iterations"], k["max_dev"], 2)
+        np.testing.assert_allclose(fast, np.array([raw[i] for i in range(n)]), rtol=1e-12, atol=0)
+        assert len(ftrace) == len(trace)
     # expected
     hic.normalize_expected(signal_to_noise=k["s2n"], inter_chrom=k["inter_chrom"])
     got = orc.expected(m, bads=bads, signal_to_noise=k["s2n"], inter_chrom=k["inter_chrom"])
