@@ -140,8 +140,15 @@ def filter_by_mean(matrx, draw_hist=False, silent=False, bads=None, savefig=None
         for i in np.flatnonzero(totals < root):
             bads[int(i)] = int(totals[i])
         if bads and not silent:
-            stderr.write(('\nWARNING: removing columns having less than %s '
-                          'counts:\n %s\n') % (round(root, 3), _listing(bads.keys())))
+            try:
+                message = ('\nWARNING: removing columns having less than %s '
+                           'counts:\n %s\n') % (round(root, 3), _listing(bads.keys()))
+            except TypeError:
+                # numpy's roots may be complex and a complex number cannot be rounded: in the
+                # reference the columns are already flagged by then and its bare except
+                # prints this instead (hic_filtering.py:141-156)
+                message = 'WARNING: Too many zeroes to filter columns. SKIPPING...\n'
+            stderr.write(message)
     except ValueError:
         if not silent:
             stderr.write('WARNING: Too few data to filter columns based on '

@@ -1,0 +1,47 @@
+"""Test double for ``tadbit_b200.ContactStore`` (TESTS ONLY): the same methods the host classes
+call on a store, answered on the CPU by the oracle.  It lets ``-m "not gpu"`` tests drive the
+product's host layer (tadbit_b200/hic_data.py, hic_filtering.py, normalize_hic.py: thresholds,
+numpy tail of filter_by_mean, pooling of expected, rescaling, printed lines, exceptions) next to
+the unmodified reference.  The product itself never falls back to this: without the CUDA library
+``ContactStore`` raises."""
+import numpy as np
+
+import tadbit_oracle as orc
+
+
+class NumpyStore(object):
+    def __init__(self, size, rows, cols, vals, chromosomes=None, symmetricized=False):
+        self.size = int(size)
+        self.m = orc.OracleMatrix(size, rows, cols, vals, chromosomes=chromosomes,
+                                  symmetricized=symmetricized)
+
+    @staticmethod
+    def _bads(mask):
+        if mask is None:
+            return {}
+        return dict((int(i), True) for i in np.flatnonzero(np.asarray(mask)))
+
+    def row_stats(self):                                   # tb_row_stats
+        return orc.row_stats(self.m)
+
+    def col_sums_masked(self, bad=None):                   # tb_col_sums_masked
+        mask = np.zeros(self.size, dtype=bool) if bad is None else np.asarray(bad).astype(bool)
+        return orc.masked_col_sums(self.m, mask)
+
+    def ice(self, bad=None, iterations=0, max_dev=1e-5):   # tb_ice
+        bias, trace = orc.iterative(self.m, bads=self._bads(bad), iterations=iterations,
+                                    max_dev=max_dev)
+        arr = np.array([(t[0], t[1], t[2], t[4]) for t in trace], dtype=np.float64).reshape(-1, 4)
+        return np.asarray(bias, dtype=np.float64), arr
+
+    def norm_sum(self, bias=None, bad=None):               # tb_norm_sum
+        return orc.matrix_sum(self.m, bias, self._bads(bad))
+
+    def diag_sums(self, bad, ndiag):                       # tb_diag_sums
+        return np.asarray(orc.diagonal_sums(self.m, self._bads(bad), ndiag)[0], dtype=np.int64)
+
+    def export_upper(self):                                # tb_store_export_upper
+        return (self.m.rows.astype(np.int32), self.m.cols.astype(np.int32), self.m.vals)
+
+    def close(self):
+        pass

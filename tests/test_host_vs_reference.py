@@ -1,0 +1,142 @@
+"""The product's HOST layer next to the unmodified reference, on the CPU.
+
+``tadbit_b200.HiC_data`` is built around a test double of the contact store (tests/_numpy_store.py:
+the store's reductions answered by the oracle), so everything above the C-ABI runs as shipped --
+filter thresholds and warnings, the numpy tail of filter_by_mean, the pooling loop of expected,
+sqrt / factor rescaling, printed progress and trace lines, exception types -- and must reproduce
+what the reference's own ``HiC_data`` prints and returns on the same seeded random matrices.
+Skipped where the reference tree is absent."""
+import contextlib
+import io
+import os
+import sys
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+import ref_shim  # noqa: E402
+from _numpy_store import NumpyStore  # noqa: E402
+from test_oracle_vs_reference import _random_case, _reference  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+
+
+def _product(k):
+    import tadbit_b200
+    chroms = OrderedDict(zip(k["names"], k["sizes"])) if k["sizes"] else None
+    store = NumpyStore(k["n"], k["rows"], k["cols"], k["vals"], chromosomes=chroms,
+                       symmetricized=k["symmetricized"])
+    sections = None if chroms else {}
+    if chroms:
+        sections, idx = {}, 0
+        for name in chroms:
+            for p in range(chroms[name]):
+                sections[(name, p)] = idx
+                idx += 1
+    return tadbit_b200.HiC_data.from_store(store, chromosomes=chroms, dict_sec=sections,
+                                           symmetricized=k["symmetricized"])
+
+
+def _run(hic, k, factor):
+    """filter_columns -> normalize_hic -> normalize_expected with everything printed."""
+    out, err = io.StringIO(), io.StringIO()
+    raised = None
+    with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err):
+        hic.filter_columns(silent=False, perc_zero=k["perc_zero"], by_mean=k["by_mean"])
+        try:
+            hic.normalize_hic(iterations=k["iterations"], max_dev=k["max_dev"], silent=False,
+                              sqrt=k["sqrt"], factor=factor)
+        except ZeroDivisionError as e:
+            raised = str(e)
+        hic.normalize_expected(signal_to_noise=k["s2n"], inter_chrom=k["inter_chrom"])
+    return out.getvalue(), err.getvalue(), raised
+
+
+@pytest.mark.parametrize("seed", range(80))
+def test_host_layer_prints_and_returns_what_the_reference_does(seed):
+    ns = ref_shim.load()
+    k = _random_case(5000 + seed)
+    n = k["n"]
+    factor = None if k["factor"] is None else int(k["factor"])
+    ref = _reference(ns, k)
+    ours = _product(k)
+    ref_out, ref_err, ref_raised = _run(ref, k, factor)
+    our_out, our_err, our_raised = _run(ours, k, factor)
+    assert ours.bads == ref.bads
+    for key in ref.bads:
+        assert (ours.bads[key] is True) == (ref.bads[key] is True)
+    assert our_raised == ref_raised
+    if ref_raised is None:
+        got = ours.bias.to_array()
+        want = np.array([ref.bias[i] for i in range(n)])
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
+        assert len(ours.bias) == len(ref.bias) == n
+    assert dict(ours.expected) == dict(ref.expected)
+    # printed lines: same text, numbers equal to what 3 / 5 printed decimals can show
+    ref_lines, our_lines = ref_out.splitlines(), our_out.splitlines()
+    assert len(our_lines) == len(ref_lines)
+    for a, b in zip(our_lines, ref_lines):
+        if a == b:
+            continue
+        ta, tb = a.split(), b.split()
+        assert len(ta) == len(tb)
+        for x, y in zip(ta, tb):
+            if x != y:
+                assert abs(float(x) - float(y)) <= 2e-3 * max(1.0, abs(float(y)) * 1e-9 + 1.0)
+    # warnings on stderr (columns removed, thresholds): identical text
+    assert our_err == ref_err
+
+
+@pytest.mark.parametrize("seed", range(20))
+def test_dict_surface_min_count_and_pickles(seed, tmp_path):
+    """The rest of the reference-facing surface: min_count filtering (with the symmetricized
+    doubling and its warning), cell access, items(), CSR export, sum(), and biases pickles that
+    the reference's own loader reads (and the other way round)."""
+    ns = ref_shim.load()
+    k = _random_case(9000 + seed)
+    n = k["n"]
+    ref, ours = _reference(ns, k), _product(k)
+    rng = np.random.RandomState(seed)
+    # cell access and iteration over BOTH triangles
+    assert len(ours) == len(ref) == n
+    for _ in range(50):
+        i, j = int(rng.randint(n)), int(rng.randint(n))
+        assert ours[i, j] == ref[i, j]
+        assert ours[i * n + j] == ref[i * n + j]
+    assert sorted(ours.items()) == sorted(dict.items(ref))
+    assert np.array_equal(ours.get_hic_data_as_csr().toarray(), ref.get_hic_data_as_csr().toarray())
+    # min_count mode
+    row_sums = np.asarray(ref.get_hic_data_as_csr().sum(axis=1)).ravel()
+    mc = int(np.percentile(row_sums, 25)) + 1
+    outs = []
+    for hic in (ref, ours):
+        err = io.StringIO()
+        with contextlib.redirect_stderr(err), contextlib.redirect_stdout(io.StringIO()):
+            hic.filter_columns(silent=False, min_count=mc, by_mean=k["by_mean"])
+        outs.append(err.getvalue())
+    assert ours.bads == ref.bads
+    assert outs[1] == outs[0]
+    # sums and pickles
+    assert ours.sum() == ref.sum()
+    for hic in (ref, ours):
+        with contextlib.redirect_stdout(io.StringIO()):
+            try:
+                hic.normalize_hic(iterations=10, max_dev=1e-4, silent=True)
+            except ZeroDivisionError:
+                return
+        hic.normalize_expected()
+    assert abs(ours.sum(ours.bias) - ref.sum(ref.bias)) <= 1e-9 * abs(ref.sum(ref.bias))
+    a, b = str(tmp_path / "ours.pickle"), str(tmp_path / "ref.pickle")
+    ours.save_biases(a)
+    ref.save_biases(b)
+    ref2, ours2 = _reference(ns, k), _product(k)
+    ref2.load_biases(a)                      # the reference reads our file
+    ours2.load_biases(b)                     # and we read the reference's
+    assert ref2.bads == ours.bads and ours2.bads == ref.bads
+    assert ref2.expected == ours.expected and ours2.expected == ref.expected
+    np.testing.assert_allclose([ref2.bias[i] for i in range(n)], [ref.bias[i] for i in range(n)],
+                               rtol=1e-12, atol=0)
+    np.testing.assert_allclose([ours2.bias[i] for i in range(n)], [ref.bias[i] for i in range(n)],
+                               rtol=0, atol=0)
