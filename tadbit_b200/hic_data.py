@@ -336,6 +336,9 @@ def from_reference(hic_data, device=0):
                    resolution=getattr(hic_data, 'resolution', 1),
                    masked=getattr(hic_data, 'bads', None),
                    symmetricized=getattr(hic_data, 'symmetricized', False), device=device)
+    # an object built with dict_sec={} carries the filled-in sections; keep its section bounds
+    if getattr(hic_data, 'section_pos', None):
+        new.section_pos = dict(hic_data.section_pos)
     return new
 
 

@@ -140,3 +140,54 @@ def test_dict_surface_min_count_and_pickles(seed, tmp_path):
                                rtol=1e-12, atol=0)
     np.testing.assert_allclose([ours2.bias[i] for i in range(n)], [ref.bias[i] for i in range(n)],
                                rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("seed", range(20))
+def test_module_level_functions_and_constructor(seed, monkeypatch):
+    """Seam 2 of INTEGRATION.md -- the four module-level callables the reference binds at import
+    time -- and the dict constructor (from_reference), with the store replaced by the double."""
+    import tadbit_b200
+    import tadbit_b200.hic_data as hd
+    ns = ref_shim.load()
+    k = _random_case(13000 + seed)
+    n = k["n"]
+    ref = _reference(ns, k)
+
+    def fake_from_coo(size, rows, cols, vals, chromosomes=None, row_block=None, device=0):
+        return NumpyStore(size, rows, cols, vals, chromosomes=chromosomes)
+    monkeypatch.setattr(hd.ContactStore, "from_coo", staticmethod(fake_from_coo))
+    # the reference object itself (a dict subclass, both triangles) goes through the constructor
+    ours = tadbit_b200.from_reference(ref)
+    assert len(ours) == n and ours.symmetricized == ref.symmetricized
+    assert sorted(ours.items()) == sorted(dict.items(ref))
+    assert ours.section_pos == ref.section_pos and ours.chromosomes == ref.chromosomes
+    # filter_by_zero_count / filter_by_mean as functions; the passed dict is extended in place
+    b_ref = ns.filter_by_zero_count(ref, k["perc_zero"])
+    b_our = tadbit_b200.filter_by_zero_count(ours, k["perc_zero"])
+    assert b_our == b_ref
+    with contextlib.redirect_stderr(io.StringIO()):
+        r_ref = ns.filter_by_mean(ref, silent=True, bads=b_ref)
+        r_our = tadbit_b200.filter_by_mean(ours, silent=True, bads=b_our)
+    assert r_our == r_ref
+    assert (r_our is b_our) == (r_ref is b_ref)            # same aliasing rule (empty dict -> new one)
+    # iterative / expected as functions, verbose output included
+    outs, results = [], []
+    for mod, hic, bads in ((ns, ref, r_ref), (tadbit_b200, ours, r_our)):
+        buf = io.StringIO()
+        try:
+            with contextlib.redirect_stdout(buf):
+                bias = mod.iterative(hic, bads=bads, iterations=k["iterations"], max_dev=k["max_dev"],
+                                     verbose=True)
+            results.append(np.array([bias[i] for i in range(n)]))
+        except ZeroDivisionError as e:
+            results.append(str(e))
+        outs.append(buf.getvalue().splitlines())
+    if isinstance(results[0], str):
+        assert results[1] == results[0]
+    else:
+        np.testing.assert_allclose(results[1], results[0], rtol=1e-12, atol=0)
+        assert len(outs[1]) == len(outs[0])
+        assert outs[1][:3] == outs[0][:3]                  # 'iterative correction', '  - copying matrix', ...
+    e_ref = ns.expected(ref, bads=r_ref, signal_to_noise=k["s2n"], inter_chrom=k["inter_chrom"])
+    e_our = tadbit_b200.expected(ours, bads=r_our, signal_to_noise=k["s2n"], inter_chrom=k["inter_chrom"])
+    assert dict(e_our) == dict(e_ref)
