@@ -156,3 +156,31 @@ def test_sharded_protocol_gloo_world2():
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
                          timeout=300, env=env)
     assert "GLOO_PROTOCOL PASS" in out.stdout, out.stdout[-3000:]
+
+
+def test_rebalance_by_time_equalises_estimated_time():
+    """Shards re-cut from per-kernel probe times spread over per-row work (workloads.py): with
+    a matrix whose rows cost more in one region, the new blocks have (nearly) equal estimated
+    time and still tile [0, N) contiguously."""
+    from tadbit_b200.workloads import balanced_row_blocks, rebalance_by_time
+    rng = np.random.RandomState(3)
+    n, world = 4000, 4
+    dense = rng.randint(1000, 5000, n).astype(np.int64)
+    tiles = rng.randint(10, 400, n).astype(np.int64)
+    tiles[:700] *= 20                                        # an expensive sparse region
+    per_row_ms = 2e-6 * dense + 9e-6 * tiles                 # the "true" cost model
+    blocks = balanced_row_blocks(dense + tiles, world)
+    probes = []
+    for a, b in blocks:
+        probes.append((float(9e-6 * tiles[a:b].sum()), float(2e-6 * dense[a:b].sum()),
+                       dense[a:b], tiles[a:b]))
+    before = [per_row_ms[a:b].sum() for a, b in blocks]
+    new = rebalance_by_time(blocks, probes, n)
+    assert new[0][0] == 0 and new[-1][1] == n
+    assert all(new[r][1] == new[r + 1][0] for r in range(world - 1))
+    after = [per_row_ms[a:b].sum() for a, b in new]
+    assert max(after) / (sum(after) / world) < 1.02 < max(before) / (sum(before) / world)
+    # an empty shard or a kernel without work does not break the apportioning
+    probes[1] = (0.0, probes[1][1], probes[1][2], np.zeros_like(probes[1][3]))
+    again = rebalance_by_time(blocks, probes, n)
+    assert again[0][0] == 0 and again[-1][1] == n
