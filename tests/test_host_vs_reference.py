@@ -191,3 +191,78 @@ def test_module_level_functions_and_constructor(seed, monkeypatch):
     e_ref = ns.expected(ref, bads=r_ref, signal_to_noise=k["s2n"], inter_chrom=k["inter_chrom"])
     e_our = tadbit_b200.expected(ours, bads=r_our, signal_to_noise=k["s2n"], inter_chrom=k["inter_chrom"])
     assert dict(e_our) == dict(e_ref)
+
+
+def test_batch_host_logic_matches_the_reference_loop(monkeypatch):
+    """normalize_hic_batch (tadbit_b200/batch.py) against `for h in hics: h.normalize_hic(...)`
+    of the reference: biases, printed lines.  The two C-ABI calls of the batch path are replaced
+    by doubles (per-matrix oracle ICE), everything else runs as shipped."""
+    import tadbit_b200.batch as batch
+    ns = ref_shim.load()
+    cases = [_random_case(17000 + s) for s in range(6)]
+    for k in cases:                                        # one common set of settings
+        k.update(perc_zero=99, by_mean=False)
+    refs = [_reference(ns, k) for k in cases]
+    ours = [_product(k) for k in cases]
+    for r, o in zip(refs, ours):
+        with contextlib.redirect_stderr(io.StringIO()), contextlib.redirect_stdout(io.StringIO()):
+            r.filter_columns(silent=True, by_mean=False)
+            o.filter_columns(silent=True, by_mean=False)
+        assert o.bads == r.bads
+
+    class _Batch(object):
+        def __init__(self, stores):
+            self.stores = stores
+
+        def close(self):
+            pass
+
+    def fake_batch_store(stores, device=0):
+        return _Batch(stores)
+
+    def fake_ice_batch(store, sizes, bad=None, iterations=0, max_dev=1e-5):
+        bias, traces, passes, off = [], [], [], 0
+        for st, n in zip(store.stores, sizes):
+            mask = None if bad is None else bad[off:off + n]
+            off += n
+            try:
+                b, t = st.ice(mask, iterations=iterations, max_dev=max_dev)
+                passes.append(len(t) if iterations > 0 else 1)
+            except ZeroDivisionError:
+                b, t = np.ones(n), np.zeros((0, 4))
+                passes.append(-1)
+            bias.append(b)
+            traces.append(t)
+        return np.concatenate(bias), traces, np.array(passes, dtype=np.int32)
+
+    monkeypatch.setattr(batch, "batch_store", fake_batch_store)
+    monkeypatch.setattr(batch, "ice_batch", fake_ice_batch)
+    for kw in (dict(iterations=0, max_dev=0.1), dict(iterations=30, max_dev=1e-4, factor=2),
+               dict(iterations=5, max_dev=1e-9, sqrt=True, factor=None)):
+        ref_out = io.StringIO()
+        ok = True
+        with contextlib.redirect_stdout(ref_out):
+            try:
+                for r in refs:
+                    r.normalize_hic(silent=False, **kw)
+            except ZeroDivisionError:
+                ok = False
+        our_out = io.StringIO()
+        with contextlib.redirect_stdout(our_out):
+            if ok:
+                batch.normalize_hic_batch(ours, silent=False, **kw)
+            else:
+                with pytest.raises(ZeroDivisionError):
+                    batch.normalize_hic_batch(ours, silent=False, **kw)
+        if not ok:
+            continue
+        for r, o in zip(refs, ours):
+            n = len(r)
+            np.testing.assert_allclose(o.bias.to_array(), [r.bias[i] for i in range(n)], rtol=1e-12, atol=0)
+        a, b = our_out.getvalue().splitlines(), ref_out.getvalue().splitlines()
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            if x != y:
+                words = lambda line: [t for t in line.split()
+                                      if not t.replace('.', '').replace('-', '').isdigit()]
+                assert words(x) == words(y)
