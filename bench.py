@@ -262,13 +262,18 @@ def main():
                         "the compact stream moves layout_bytes_per_launch (< algorithmic), so frac "
                         "can exceed the fraction of HBM peak actually drawn (layout_gbs / peak)",
                 "kernel": "k_chunk_reduce<F64> (CSR walk)" if csr_walk else
-                          "K1 row sum = k_rowsum_tiles + k_rowsum_dense (2 launches per pass, timed together)",
+                          "K1 row sum = k_rowsum_tiles + k_rowsum_dense (+ k_rowsum_sparse for the few "
+                          "per-cell chunks), timed together per pass",
                 "kernel_ms": k1_ms, "stream_encodings": lay["encodings"],
                 "tile_cells": lay["tile_cells"], "tile_cells_padded": lay["tile_cells_padded"],
                 "kernel_share_of_step": rowsum_ms / dev_ms if dev_ms else None,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "layout_bytes_per_launch": layout_bytes,
-                "layout_gbs": layout_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0}
+                "layout_gbs": layout_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0,
+                # the same two rates against the B200 spec sheet (SURVEY 8d asks for both peaks)
+                "peak_spec": 8000.0, "frac_spec": achieved / 8000.0}
+    roofline["layout_frac"] = roofline["layout_gbs"] / peak if peak else None
+    roofline["traffic_gbs"] = traffic / (k1_ms * 1e-3) / 1e9 if traffic and k1_ms > 0 else None
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
