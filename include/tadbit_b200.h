@@ -46,7 +46,11 @@ typedef enum {
                           'ERROR: normalization failed, all bad columns',
                           _pytadbit/utils/normalize_hic.py:207-208)                      */
   TB_ERR_NCCL = 4,     /* NCCL failure / NCCL not loadable                                */
-  TB_ERR_STATE = 5     /* call not valid in this state (e.g. comm not initialised)        */
+  TB_ERR_STATE = 5,    /* call not valid in this state (e.g. comm not initialised), or a
+                          GPU of the group never reached the row-sum exchange             */
+  TB_ERR_ZERO_DIV = 6  /* the reference would divide by zero: mean row sum 0 in ICE
+                          (_pytadbit/utils/normalize_hic.py:148), a bias of 0 in the
+                          normalised sum (_pytadbit/hic_data.py:371-374)                 */
 } tb_status;
 
 enum { TB_MEM_HOST = 0, TB_MEM_DEVICE = 1 };
@@ -200,6 +204,12 @@ int tb_row_work(tb_store *s, int64_t *h_dense_bytes, int64_t *h_tile_cells);
  * total device ms of the pass loop, and the ms spent in the row-sum (K1) launches */
 int tb_ice_last_timing(const tb_store *s, double *loop_ms, double *rowsum_ms,
                        int32_t *rowsum_launches, int32_t *total_launches);
+/* Device times of the last calls on this store, in ms: out[0] ICE loop, [1] its K1 row-sum
+ * launches, [2] everything between them (exchange + statistics + update), [3] the last one-pass
+ * reduction (tb_col_sums_masked / tb_diag_sums), [4] row-sum launches, [5] kernels launched,
+ * [6] row-sum exchange in use: 2 = peer-mapped NVLink stores, 1 = local / NCCL all-reduce,
+ * [7] 1 if the store kept its CSR (matrices with zeros or negative values). */
+int tb_last_timing(const tb_store *s, double out[8]);
 
 /* ---- K3: normalised sum ---------------------------------------------------------- */
 /*

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # TADBIT_B200_LIB: explicit path of the library (a build variant under test)
 LIB_PATH = os.environ.get("TADBIT_B200_LIB") or os.path.join(_HERE, "libtadbit_b200.so")
 
-TB_OK, TB_ERR_ARG, TB_ERR_CUDA, TB_ERR_ALL_BAD, TB_ERR_NCCL, TB_ERR_STATE = range(6)
+TB_OK, TB_ERR_ARG, TB_ERR_CUDA, TB_ERR_ALL_BAD, TB_ERR_NCCL, TB_ERR_STATE, TB_ERR_ZERO_DIV = range(7)
 TB_MEM_HOST, TB_MEM_DEVICE = 0, 1
 
 
@@ -63,6 +63,7 @@ PROTOTYPES = {
     "tb_row_work": ([_store, _i64p, _i64p], C.c_int),
     "tb_ice_last_timing": ([_store, _f64p, _f64p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
                            C.c_int),
+    "tb_last_timing": ([_store, _f64p], C.c_int),
     "tb_norm_sum": ([_store, _f64p, _u8p, _f64p], C.c_int),
     "tb_diag_sums": ([_store, _u8p, C.c_int64, _i64p], C.c_int),
 }
@@ -93,6 +94,8 @@ def check(status):
     msg = lib().tb_last_error().decode("utf-8", "replace")
     if status == TB_ERR_ALL_BAD:
         raise ZeroDivisionError(msg)         # normalize_hic.py:207-208
+    if status == TB_ERR_ZERO_DIV:
+        raise ZeroDivisionError(msg)         # normalize_hic.py:148 / hic_data.py:371-374
     if status == TB_ERR_ARG:
         raise ValueError(msg)
     raise B200Error("tadbit_b200 status %d: %s" % (status, msg))
@@ -113,7 +116,15 @@ def ptr(arr, ctype):
     return arr.ctypes.data_as(C.POINTER(ctype))
 
 
-def as_i32(a):
+def as_i32(a, what="array"):
+    """Contiguous int32 view/copy; refuses values that int32 cannot hold (no silent wrap)."""
+    a = np.asarray(a)
+    if a.dtype != np.int32 and a.size:
+        if a.dtype.kind == 'f':
+            if not np.all(a == np.rint(a)):
+                raise ValueError("%s must hold integers" % what)
+        if a.min() < -2147483648 or a.max() > 2147483647:
+            raise OverflowError("%s does not fit int32" % what)
     return np.ascontiguousarray(a, dtype=np.int32)
 
 

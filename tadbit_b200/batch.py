@@ -41,7 +41,11 @@ def ice_batch(store, sizes, bad=None, iterations=0, max_dev=1e-5):
 def normalize_hic_batch(hics, iterations=0, max_dev=0.1, silent=False, sqrt=False, factor=1,
                         device=0):
     """Same result as ``for h in hics: h.normalize_hic(iterations, max_dev, silent, sqrt,
-    factor)`` (each ``h.bias`` is set), with all ICE loops run as one batch on the GPU."""
+    factor)`` (each ``h.bias`` is set), with all ICE loops run as one batch on the GPU.
+
+    As in the loop, a matrix that cannot be normalised raises ``ZeroDivisionError`` when its
+    turn comes: the matrices before it have their ``bias`` set, the ones after it are left
+    untouched (their loops did run on the device; the results are dropped)."""
     sizes = [len(h) for h in hics]
     store = batch_store([h.store for h in hics], device=device)
     try:
@@ -54,11 +58,15 @@ def normalize_hic_batch(hics, iterations=0, max_dev=0.1, silent=False, sqrt=Fals
         if not silent:
             print('iterative correction')
             print('  - copying matrix')
+        if passes[k] == -1:                      # normalize_hic.py:207-208, before the third line
+            raise ZeroDivisionError('ERROR: normalization failed, all bad columns')
+        if not silent:
             print('  - computing biases')
+        if passes[k] == -2:                      # _updateDB with meanS == 0 (normalize_hic.py:148)
+            raise ZeroDivisionError('float division by zero')
+        if not silent:
             for it, (smin, mean_s, smax, dev) in enumerate(traces[k]):
                 print(TRACE_FORMAT % (smin, mean_s, smax, it, dev))
-        if passes[k] < 0:
-            raise ZeroDivisionError('ERROR: normalization failed, all bad columns')
         values = bias[off:off + sizes[k]].copy()
         off += sizes[k]
         h.last_trace = traces[k]

@@ -148,7 +148,7 @@ using namespace tb;
 
 extern "C" {
 
-int tb_version(void) { return 100; }
+int tb_version(void) { return 200; }
 
 const char *tb_last_error(void) { return g_error; }
 
@@ -289,6 +289,7 @@ int tb_store_destroy(tb_store *s) {
     cudaStreamSynchronize(s->stream);
     cudaStreamDestroy(s->stream);
   }
+  for (cudaEvent_t e : s->events) cudaEventDestroy(e);
   delete s;
   cudaSetDevice(prev);
   return TB_OK;
@@ -413,6 +414,19 @@ int tb_ice_last_timing(const tb_store *s, double *loop_ms, double *rowsum_ms,
   if (rowsum_ms) *rowsum_ms = s->rowsum_ms;
   if (rowsum_launches) *rowsum_launches = s->rowsum_launches;
   if (total_launches) *total_launches = s->total_launches;
+  return TB_OK;
+}
+
+int tb_last_timing(const tb_store *s, double out[8]) {
+  if (!s || !out) { set_error("null argument"); return TB_ERR_ARG; }
+  out[0] = s->loop_ms;
+  out[1] = s->rowsum_ms;
+  out[2] = s->exchange_ms;
+  out[3] = s->last_kernel_ms;
+  out[4] = (double)s->rowsum_launches;
+  out[5] = (double)s->total_launches;
+  out[6] = s->px.mapped ? 2.0 : (s->px.ready ? 1.0 : 0.0);
+  out[7] = s->csr_resident ? 1.0 : 0.0;
   return TB_OK;
 }
 

@@ -6,6 +6,12 @@
 // mirrored cells turns all of them into gather-only, atomic-free, deterministic row
 // reductions of one stream; the reference's dict holds both triangles too
 // (_pytadbit/hic_data.py:54-118).
+//
+// The CSR is scaffolding: finish_layout derives the compact row-sum stream (encode.cu, tiles.cu)
+// and the per-row statistics from it and then RELEASES it when every stored value is > 0 (what
+// the parsers produce); every later kernel walks the compact stream (visit.cuh for the ones that
+// need the cells).  A matrix with stored zeros or negative values keeps its CSR: an explicit zero
+// cannot be told from an absent cell in a dense panel.  TB_KEEP_CSR=1 keeps it always (tests).
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -13,6 +19,7 @@
 #include <cub/cub.cuh>
 
 #include "common.cuh"
+#include "visit.cuh"
 
 namespace tb {
 
@@ -226,6 +233,75 @@ __global__ void k_plan_chunks(const int64_t *__restrict__ rowptr, const int32_t 
   }
 }
 
+// per owned row: stored cells and their sum; over the block: zeros, negative values, sum of |v|
+__global__ void __launch_bounds__(256)
+k_build_row_stats(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ val, int64_t nrows,
+                  long long *__restrict__ row_nnz, long long *__restrict__ row_sum,
+                  unsigned long long *__restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  unsigned long long zeros = 0, negs = 0, mag = 0;
+  for (int64_t r = warp; r < nrows; r += nwarp) {
+    const int64_t b = rowptr[r], e = rowptr[r + 1];
+    long long a = 0;
+    for (int64_t k = b + lane; k < e; k += 32) {
+      const int32_t v = val[k];
+      a += v;
+      zeros += v == 0;
+      negs += v < 0;
+      mag += (unsigned long long)(v < 0 ? -(long long)v : (long long)v);
+    }
+    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) { row_nnz[r] = e - b; row_sum[r] = a; }
+  }
+  for (int o = 16; o; o >>= 1) {
+    zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
+    negs += __shfl_xor_sync(0xffffffffu, negs, o);
+    mag += __shfl_xor_sync(0xffffffffu, mag, o);
+  }
+  if (lane == 0) {
+    if (zeros) atomicAdd(stats, zeros);
+    if (negs) atomicAdd(stats + 1, negs);
+    if (mag) atomicAdd(stats + 2, mag);
+  }
+}
+
+// ---- export of the stored upper-triangle cells from the compact stream (visit.cuh) ----------
+struct CountUpperVisitor {
+  static constexpr int kShared = 0;
+  int64_t rb;
+  unsigned long long *cnt;            // [nrows]
+  __device__ void begin(uint8_t *) {}
+  __device__ void cell(int64_t i, int64_t, int32_t) { atomicAdd(&cnt[i - rb], 1ull); }
+  __device__ void end(uint8_t *) {}
+};
+struct PlaceUpperVisitor {
+  static constexpr int kShared = 0;
+  int64_t rb;
+  const int64_t *off;                 // [nrows] first output slot of each row
+  unsigned long long *cursor;         // [nrows]
+  uint64_t *key;                      // (local row << 32) | column
+  int32_t *val;
+  __device__ void begin(uint8_t *) {}
+  __device__ void cell(int64_t i, int64_t j, int32_t v) {
+    const int64_t r = i - rb;
+    const int64_t pos = off[r] + (int64_t)atomicAdd(&cursor[r], 1ull);
+    key[pos] = ((uint64_t)r << 32) | (uint32_t)j;
+    val[pos] = v;
+  }
+  __device__ void end(uint8_t *) {}
+};
+__global__ void k_unpack_keys(const uint64_t *__restrict__ key, int64_t n, int64_t rb, int32_t row_off,
+                              int32_t col_off, int32_t *__restrict__ orow, int32_t *__restrict__ ocol) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t e = key[k];
+    orow[k] = (int32_t)(rb + (int64_t)(e >> 32)) + row_off;
+    ocol[k] = (int32_t)(e & 0xffffffffu) + col_off;
+  }
+}
+
 // first stored cell of each owned row with col >= its own (global) row index
 __global__ void k_upper_start(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                               int64_t nrows, int64_t rb, int64_t *ustart, int64_t *ucount) {
@@ -244,7 +320,7 @@ __global__ void k_upper_start(const int64_t *__restrict__ rowptr, const int32_t 
 
 __global__ void k_copy_upper(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
                              const int64_t *__restrict__ ustart, const int64_t *__restrict__ ucount,
-                             const int64_t *__restrict__ uoff, int64_t nrows, int64_t rb,
+                             const int64_t *__restrict__ uoff, int64_t nrows, int64_t rb, int32_t bin_off,
                              int32_t *orow, int32_t *ocol, int32_t *oval) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -252,8 +328,8 @@ __global__ void k_copy_upper(const int32_t *__restrict__ col, const int32_t *__r
   for (int64_t r = warp; r < nrows; r += nwarp) {
     int64_t src = ustart[r], n = ucount[r], dst = uoff[r];
     for (int64_t k = lane; k < n; k += 32) {
-      orow[dst + k] = (int32_t)(rb + r);
-      ocol[dst + k] = col[src + k];
+      orow[dst + k] = (int32_t)(rb + r) + bin_off;
+      ocol[dst + k] = col[src + k] + bin_off;
       oval[dst + k] = val[src + k];
     }
   }
@@ -436,6 +512,23 @@ void finish_layout(tb_store *s) {
   StageTimer tm(st);
   const int threads = 256;
   const int64_t nrows = s->nrows, N = s->nbins;
+  // per-row statistics that outlive the CSR, and what kind of values the block holds
+  s->row_nnz.alloc(nrows + 1);
+  s->row_sum.alloc(nrows + 1);
+  {
+    DevBuf<unsigned long long> stats;
+    stats.alloc(4);
+    TB_CUDA(cudaMemsetAsync(stats.p, 0, stats.bytes(), st));
+    if (nrows)
+      k_build_row_stats<<<grid_for(nrows * 32, threads, s->sm_count), threads, 0, st>>>(
+          s->rowptr.p, s->val.p, nrows, s->row_nnz.p, s->row_sum.p, stats.p);
+    unsigned long long h[4] = {0, 0, 0, 0};
+    TB_CUDA(cudaMemcpyAsync(h, stats.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    s->n_zero_cells = (int64_t)h[0];
+    // exact integer sums in fp64 need every partial sum below 2^53
+    s->positive = h[0] == 0 && h[1] == 0 && h[2] < (1ull << 53);
+  }
   // chunks
   s->row_chunk.alloc(nrows + 1);
   {
@@ -498,60 +591,50 @@ void finish_layout(tb_store *s) {
   tm.lap("encode dense stream");
   build_tiles(s);
   tm.lap("sparse tiles");
+  {
+    const char *keep = getenv("TB_KEEP_CSR");
+    s->csr_resident = true;
+    if (s->positive && !(keep && keep[0] == '1')) {
+      TB_CUDA(cudaStreamSynchronize(st));
+      s->rowptr.release();
+      s->col.release();
+      s->val.release();
+      s->chunk_beg.release();
+      s->partial_i.release();
+      s->csr_resident = false;
+    }
+  }
   s->device_bytes = s->t_cells.bytes() + s->t_perm.bytes() + s->t_slice.bytes() + s->t_off.bytes() +
                     s->t_desc.bytes() + s->t_desc_off.bytes() +
                     s->t_partial.bytes() + s->enc_data.bytes() + s->enc_off.bytes() + s->enc_desc.bytes() + s->rowptr.bytes() + s->col.bytes() + s->val.bytes() + s->chunk_beg.bytes() +
                     s->chunk_row.bytes() + s->row_chunk.bytes() + s->partial_f.bytes() +
                     s->partial_i.bytes() + s->x.bytes() + s->b.bytes() +
                     s->s_part.bytes() + s->s_full.bytes() + s->i_part.bytes() + s->i_full.bytes() +
-                    s->bad.bytes() + s->present.bytes() + s->chrom_of.bytes();
+                    s->bad.bytes() + s->present.bytes() + s->chrom_of.bytes() + s->row_nnz.bytes() +
+                    s->row_sum.bytes() + s->t_list.bytes() + s->t_unit.bytes() + s->groups.bytes() +
+                    s->work_ids.bytes() + s->enc_tovf.bytes();
 }
-
-namespace {
-__global__ void k_copy_rowptr(const int64_t *__restrict__ src, int64_t nrows, int64_t cell_off,
-                              int64_t *__restrict__ dst) {
-  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
-       r += (int64_t)gridDim.x * blockDim.x)
-    dst[r] = src[r] + cell_off;
-}
-__global__ void k_copy_cells(const int32_t *__restrict__ scol, const int32_t *__restrict__ sval,
-                             int64_t n, int32_t col_off, int32_t *__restrict__ dcol,
-                             int32_t *__restrict__ dval) {
-  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n;
-       k += (int64_t)gridDim.x * blockDim.x) {
-    dcol[k] = scol[k] + col_off;
-    dval[k] = sval[k];
-  }
-}
-}  // namespace
 
 // Block-diagonal concatenation of whole (unsharded) stores on the same device: member k
-// becomes section k.  Device-to-device, no host traffic.
+// becomes section k.  The members' upper-triangle cells are decoded on the device (row-major
+// sorted, bins shifted by the member's offset) and the batch store is built from them like any
+// other matrix.  No host traffic.
 void build_batch(tb_store *s, int32_t n, tb_store *const *members) {
-  cudaStream_t st = s->stream;
-  const int threads = 256;
   int64_t cells = 0;
-  for (int32_t k = 0; k < n; ++k) cells += members[k]->nnz_full;
-  s->nnz_full = cells;
-  s->rowptr.alloc(s->nrows + 1);
-  s->col.alloc(cells ? cells : 1);
-  s->val.alloc(cells ? cells : 1);
-  int64_t row_off = 0, cell_off = 0;
+  for (int32_t k = 0; k < n; ++k) cells += members[k]->nnz_upper;
+  TB_REQUIRE(cells < 4294967295LL, "batch too large");
+  DevBuf<int32_t> row, col, val;
+  row.alloc(cells ? cells : 1);
+  col.alloc(cells ? cells : 1);
+  val.alloc(cells ? cells : 1);
+  int64_t bin_off = 0, cell_off = 0;
   for (int32_t k = 0; k < n; ++k) {
     const tb_store *m = members[k];
-    TB_CUDA(cudaStreamSynchronize(m->stream));
-    if (m->nrows)
-      k_copy_rowptr<<<grid_for(m->nrows, threads, s->sm_count), threads, 0, st>>>(
-          m->rowptr.p, m->nrows, cell_off, s->rowptr.p + row_off);
-    if (m->nnz_full)
-      k_copy_cells<<<grid_for(m->nnz_full, threads, s->sm_count), threads, 0, st>>>(
-          m->col.p, m->val.p, m->nnz_full, (int32_t)row_off, s->col.p + cell_off, s->val.p + cell_off);
-    row_off += m->nrows;
-    cell_off += m->nnz_full;
+    export_upper_device(m, row.p + cell_off, col.p + cell_off, val.p + cell_off, (int32_t)bin_off);
+    bin_off += m->nbins;
+    cell_off += m->nnz_upper;
   }
-  TB_CUDA(cudaMemcpyAsync(s->rowptr.p + s->nrows, &s->nnz_full, sizeof(int64_t), cudaMemcpyHostToDevice, st));
-  TB_CUDA(cudaStreamSynchronize(st));
-  finish_layout(s);
+  build_from_coo(s, cells, row.p, col.p, val.p, TB_MEM_DEVICE);
 }
 
 void setup_sections(tb_store *s) {
@@ -563,24 +646,74 @@ void setup_sections(tb_store *s) {
   if (N) TB_CUDA(cudaMemcpy(s->chrom_of.p, h.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice));
 }
 
+// The owned upper-triangle cells, row-major sorted, into device arrays of nnz_upper entries;
+// bin_off is added to rows and columns.  Runs on the store's stream and waits for it.
+void export_upper_device(const tb_store *s, int32_t *d_row, int32_t *d_col, int32_t *d_val, int32_t bin_off) {
+  if (s->nnz_upper == 0) return;
+  cudaStream_t st = s->stream;
+  const int threads = 256;
+  const int64_t nrows = s->nrows, m = s->nnz_upper;
+  if (s->csr_resident) {
+    DevBuf<int64_t> us, uc, uo;
+    us.alloc(nrows + 1); uc.alloc(nrows + 1); uo.alloc(nrows + 1);
+    TB_CUDA(cudaMemsetAsync(uc.p, 0, uc.bytes(), st));
+    k_upper_start<<<grid_for(nrows, threads, s->sm_count), threads, 0, st>>>(
+        s->rowptr.p, s->col.p, nrows, s->row_begin, us.p, uc.p);
+    exclusive_scan_i64(st, uc.p, uo.p, nrows + 1);
+    k_copy_upper<<<grid_for(nrows * 32, threads, s->sm_count), threads, 0, st>>>(
+        s->col.p, s->val.p, us.p, uc.p, uo.p, nrows, s->row_begin, bin_off, d_row, d_col, d_val);
+    TB_CUDA(cudaStreamSynchronize(st));
+    return;
+  }
+  // decode the compact stream: count per row, place (any order inside a row), sort by (row, column)
+  DevBuf<unsigned long long> cnt;
+  DevBuf<int64_t> off;
+  cnt.alloc(nrows + 1);
+  off.alloc(nrows + 1);
+  TB_CUDA(cudaMemsetAsync(cnt.p, 0, cnt.bytes(), st));
+  CountUpperVisitor cv;
+  cv.rb = s->row_begin;
+  cv.cnt = cnt.p;
+  visit_upper(s, cv);
+  exclusive_scan_i64(st, reinterpret_cast<const int64_t *>(cnt.p), off.p, nrows + 1);
+  int64_t total = 0;
+  TB_CUDA(cudaMemcpy(&total, off.p + nrows, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  TB_REQUIRE(total == m, "internal: compact stream holds %lld upper cells, expected %lld",
+             (long long)total, (long long)m);
+  DevBuf<uint64_t> key_in, key_out;
+  DevBuf<int32_t> val_in;
+  key_in.alloc(m); key_out.alloc(m); val_in.alloc(m);
+  TB_CUDA(cudaMemsetAsync(cnt.p, 0, cnt.bytes(), st));
+  PlaceUpperVisitor pv;
+  pv.rb = s->row_begin;
+  pv.off = off.p;
+  pv.cursor = cnt.p;
+  pv.key = key_in.p;
+  pv.val = val_in.p;
+  visit_upper(s, pv);
+  int row_bits = 1;
+  while (((int64_t)1 << row_bits) < nrows) ++row_bits;
+  size_t tmp_bytes = 0;
+  TB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_in.p, key_out.p, val_in.p, d_val, m, 0,
+                                          32 + row_bits, st));
+  DevBuf<uint8_t> tmp;
+  tmp.alloc(tmp_bytes ? tmp_bytes : 1);
+  TB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key_in.p, key_out.p, val_in.p, d_val, m, 0,
+                                          32 + row_bits, st));
+  k_unpack_keys<<<grid_for(m, threads, s->sm_count), threads, 0, st>>>(key_out.p, m, s->row_begin, bin_off,
+                                                                       bin_off, d_row, d_col);
+  TB_CUDA(cudaStreamSynchronize(st));
+}
+
 void export_upper(const tb_store *s, int64_t *nnz, int32_t *h_row, int32_t *h_col, int32_t *h_val) {
   *nnz = s->nnz_upper;
   if (!h_row) return;
   TB_REQUIRE(h_col && h_val, "export: null output buffer");
   if (s->nnz_upper == 0) return;
   cudaStream_t st = s->stream;
-  const int threads = 256;
-  const int64_t nrows = s->nrows;
-  DevBuf<int64_t> us, uc, uo;
-  us.alloc(nrows + 1); uc.alloc(nrows + 1); uo.alloc(nrows + 1);
-  TB_CUDA(cudaMemsetAsync(uc.p, 0, uc.bytes(), st));
-  k_upper_start<<<grid_for(nrows, threads, s->sm_count), threads, 0, st>>>(
-      s->rowptr.p, s->col.p, nrows, s->row_begin, us.p, uc.p);
-  exclusive_scan_i64(st, uc.p, uo.p, nrows + 1);
   DevBuf<int32_t> orow, ocol, oval;
   orow.alloc(s->nnz_upper); ocol.alloc(s->nnz_upper); oval.alloc(s->nnz_upper);
-  k_copy_upper<<<grid_for(nrows * 32, threads, s->sm_count), threads, 0, st>>>(
-      s->col.p, s->val.p, us.p, uc.p, uo.p, nrows, s->row_begin, orow.p, ocol.p, oval.p);
+  export_upper_device(s, orow.p, ocol.p, oval.p, 0);
   TB_CUDA(cudaMemcpyAsync(h_row, orow.p, orow.bytes(), cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaMemcpyAsync(h_col, ocol.p, ocol.bytes(), cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaMemcpyAsync(h_val, oval.p, oval.bytes(), cudaMemcpyDeviceToHost, st));

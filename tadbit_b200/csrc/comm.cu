@@ -2,10 +2,17 @@
 // NCCL is resolved at run time (dlopen) so single-GPU use never needs it and the library
 // shares the libnccl.so.2 that the host process (e.g. PyTorch) has already loaded.
 //
-// The path has ONE exchange per ICE pass: the row-sum vector s (each rank fills the rows
-// it owns, zeros elsewhere; x + 0 is exact, so every rank ends with identical bits and
-// takes the same loop decision without a second collective).
+// The path has ONE exchange per ICE pass: the row-sum vector s.  By default it does not go
+// through a collective at all: every rank maps the row-sum buffers of its peers (CUDA IPC,
+// exchange_setup below) and k_ice_exchange (kernels.cu) stores each rank's rows straight into
+// every peer's buffer over NVLink, followed by a flag barrier.  NCCL carries the set-up (IPC
+// handles), the integer reductions of the filters / distance sums, and -- TB_EXCHANGE=nccl, or
+// when the peers cannot be mapped -- the row sums as an all-reduce (each rank fills the rows it
+// owns, zeros elsewhere; x + 0 is exact, so every rank ends with identical bits either way and
+// takes the same loop decision without a second exchange).
 #include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -16,7 +23,7 @@ namespace {
 
 typedef struct { char internal[128]; } NcclUniqueId;
 typedef void *NcclComm;
-enum { kNcclInt64 = 4, kNcclFloat64 = 8, kNcclSum = 0 };
+enum { kNcclInt8 = 0, kNcclInt64 = 4, kNcclFloat64 = 8, kNcclSum = 0 };
 
 struct NcclApi {
   void *lib = nullptr;
@@ -24,6 +31,8 @@ struct NcclApi {
   int (*CommInitRank)(NcclComm *, int, NcclUniqueId, int) = nullptr;
   int (*CommDestroy)(NcclComm) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, NcclComm, cudaStream_t) = nullptr;
+  int (*CommAbort)(NcclComm) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
 };
 
@@ -43,6 +52,8 @@ NcclApi &api() {
   a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.lib, "ncclCommInitRank");
   a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.lib, "ncclCommDestroy");
   a.AllReduce = (decltype(a.AllReduce))dlsym(a.lib, "ncclAllReduce");
+  a.AllGather = (decltype(a.AllGather))dlsym(a.lib, "ncclAllGather");
+  a.CommAbort = (decltype(a.CommAbort))dlsym(a.lib, "ncclCommAbort");
   a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.lib, "ncclGetErrorString");
   if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce) {
     set_error("NCCL symbols missing");
@@ -56,6 +67,18 @@ void check(int rc, const char *what) {
   NcclApi &a = api();
   set_error("NCCL %s failed: %s", what, a.GetErrorString ? a.GetErrorString(rc) : "?");
   throw Fail{TB_ERR_NCCL};
+}
+
+// a failed collective leaves the peers blocked inside it: abort the communicator so that they
+// fail too instead of hanging (the group has to be torn down and rebuilt by the caller)
+void check_abort(tb_store *s, int rc, const char *what) {
+  if (rc == 0) return;
+  NcclApi &a = api();
+  if (a.CommAbort && s->comm) {
+    a.CommAbort((NcclComm)s->comm);
+    s->comm = nullptr;
+  }
+  check(rc, what);
 }
 
 }  // namespace
@@ -77,9 +100,104 @@ void comm_init(tb_store *s, int rank, int world, const uint8_t id[128]) {
   NcclComm c = nullptr;
   check(api().CommInitRank(&c, world, u, rank), "CommInitRank");
   s->comm = c;
+  exchange_setup(s);
+}
+
+// Row-sum exchange buffers (common.cuh:PeerExchange).  Plain cudaMalloc memory (the stream-ordered
+// pool cannot be exported); with several ranks every rank's block is opened by all the others
+// through CUDA IPC.  Whether that worked is agreed on by all ranks (an all-reduce of the failure
+// count): either every rank uses the peer-mapped exchange or every rank uses the all-reduce.
+void exchange_setup(tb_store *s) {
+  exchange_release(s);
+  PeerExchange &px = s->px;
+  TB_REQUIRE(s->world <= kMaxPeers, "at most %d GPUs per group", kMaxPeers);
+  px.stride = (((size_t)s->nbins + 63) / 64) * 64;
+  const size_t flag_off = 2 * px.stride * sizeof(double);
+  const size_t bytes = flag_off + kMaxPeers * sizeof(unsigned long long);
+  TB_CUDA(cudaMalloc(&px.base, bytes));
+  TB_CUDA(cudaMemset(px.base, 0, bytes));
+  px.epoch = 0;
+  PeerView &v = px.view;
+  v = PeerView{};
+  v.rank = s->rank;
+  v.world = 1;                                   // until the peers are mapped
+  auto place = [&](int q, void *base) {
+    v.s[q][0] = reinterpret_cast<double *>(base);
+    v.s[q][1] = reinterpret_cast<double *>(base) + px.stride;
+    v.flag[q] = reinterpret_cast<unsigned long long *>(reinterpret_cast<uint8_t *>(base) + flag_off);
+  };
+  // one GPU: the only "peer" is the rank itself, slot 0
+  v.rank = s->world == 1 ? 0 : s->rank;
+  place(v.rank, px.base);
+  v.my_flags = v.flag[v.rank];
+  px.ready = true;
+  if (s->world == 1) return;
+  const char *e = getenv("TB_EXCHANGE");
+  const bool want = !(e && !strcmp(e, "nccl"));
+  // every rank takes part in the two collectives below whatever it wants, so nobody waits alone
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  long long failed = 0;
+  if (want && cudaIpcGetMemHandle(&mine, px.base) != cudaSuccess) { cudaGetLastError(); failed = 1; }
+  if (!want) failed = 1;
+  DevBuf<uint8_t> d_handles;
+  DevBuf<long long> d_fail;
+  const size_t hb = sizeof(cudaIpcMemHandle_t);
+  d_handles.alloc(hb * (s->world + 1));
+  d_fail.alloc(2);
+  TB_CUDA(cudaMemcpyAsync(d_handles.p + hb * s->world, &mine, hb, cudaMemcpyHostToDevice, s->stream));
+  check_abort(s, api().AllGather ? api().AllGather(d_handles.p + hb * s->world, d_handles.p, hb, kNcclInt8,
+                                                    (NcclComm)s->comm, s->stream) : 0, "AllGather(ipc handles)");
+  std::vector<cudaIpcMemHandle_t> all(s->world);
+  TB_CUDA(cudaMemcpyAsync(all.data(), d_handles.p, hb * s->world, cudaMemcpyDeviceToHost, s->stream));
+  TB_CUDA(cudaStreamSynchronize(s->stream));
+  if (!api().AllGather) failed = 1;
+  if (!failed) {
+    for (int q = 0; q < s->world && !failed; ++q) {
+      if (q == s->rank) continue;
+      void *pb = nullptr;
+      if (cudaIpcOpenMemHandle(&pb, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        failed = 1;
+        break;
+      }
+      px.peer_base[q] = pb;
+    }
+  }
+  TB_CUDA(cudaMemcpyAsync(d_fail.p, &failed, sizeof(long long), cudaMemcpyHostToDevice, s->stream));
+  allreduce_i64(s, d_fail.p, d_fail.p + 1, 1);
+  long long any_failed = 0;
+  TB_CUDA(cudaMemcpyAsync(&any_failed, d_fail.p + 1, sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
+  TB_CUDA(cudaStreamSynchronize(s->stream));
+  if (any_failed) {
+    for (int q = 0; q < kMaxPeers; ++q)
+      if (px.peer_base[q]) { cudaIpcCloseMemHandle(px.peer_base[q]); px.peer_base[q] = nullptr; }
+    if (want && s->rank == 0)
+      fprintf(stderr, "[tadbit_b200] peer-mapped row-sum exchange not available on this box "
+                      "(CUDA IPC failed on %lld rank(s)); using the NCCL all-reduce\n", any_failed);
+    return;
+  }
+  for (int q = 0; q < s->world; ++q)
+    if (q != s->rank) place(q, px.peer_base[q]);
+  v.world = s->world;
+  px.mapped = true;
+}
+
+void exchange_release(tb_store *s) {
+  PeerExchange &px = s->px;
+  for (int q = 0; q < kMaxPeers; ++q)
+    if (px.peer_base[q]) { cudaIpcCloseMemHandle(px.peer_base[q]); px.peer_base[q] = nullptr; }
+  if (px.base) cudaFree(px.base);
+  px = PeerExchange{};
 }
 
 void comm_destroy(tb_store *s) {
+  if (s->px.mapped) {
+    // peers may still be reading this rank's flags / writing nothing: all exchanges of a call are
+    // complete on every rank before the call returns, so only the mappings are left to drop
+    cudaStreamSynchronize(s->stream);
+  }
+  exchange_release(s);
   if (s->comm) api().CommDestroy((NcclComm)s->comm);
   s->comm = nullptr;
   s->world = 1;
@@ -88,14 +206,14 @@ void comm_destroy(tb_store *s) {
 
 void allreduce_f64(tb_store *s, const double *send, double *recv, size_t n) {
   if (!s->comm) { set_error("communicator not initialised"); throw Fail{TB_ERR_STATE}; }
-  check(api().AllReduce(send, recv, n, kNcclFloat64, kNcclSum, (NcclComm)s->comm, s->stream),
-        "AllReduce(f64)");
+  check_abort(s, api().AllReduce(send, recv, n, kNcclFloat64, kNcclSum, (NcclComm)s->comm, s->stream),
+              "AllReduce(f64)");
 }
 
 void allreduce_i64(tb_store *s, const long long *send, long long *recv, size_t n) {
   if (!s->comm) { set_error("communicator not initialised"); throw Fail{TB_ERR_STATE}; }
-  check(api().AllReduce(send, recv, n, kNcclInt64, kNcclSum, (NcclComm)s->comm, s->stream),
-        "AllReduce(i64)");
+  check_abort(s, api().AllReduce(send, recv, n, kNcclInt64, kNcclSum, (NcclComm)s->comm, s->stream),
+              "AllReduce(i64)");
 }
 
 }  // namespace tb

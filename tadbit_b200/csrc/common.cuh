@@ -87,6 +87,32 @@ struct IceState {
   int stopped;       // 1 once the reference loop would have left (dev < max_dev, or iterations == 0)
   int all_bad;       // no present row
   unsigned int blocks_arrived;
+  int zero_div;      // meanS == 0: the reference raises ZeroDivisionError in _updateDB (normalize_hic.py:148)
+  int fault;         // 1 = a peer did not arrive at the exchange in time (k_ice_exchange)
+  unsigned int arrive1, arrive2;          // grid barriers of k_ice_exchange (reset by their last arriver)
+  unsigned long long fold_epoch;          // last exchange whose statistics are final
+  unsigned long long epoch_base;          // exchange number of pass 0 of the current call, minus 1
+};
+
+// Row-sum exchange between the GPUs of one box without a collective: every rank holds two
+// full-length buffers (alternating by pass) that every peer maps through CUDA IPC and writes
+// its own rows into, plus one arrival flag per peer (comm.cu sets this up, k_ice_exchange in
+// kernels.cu uses it).  With one GPU the "peers" are the rank itself and nothing is mapped.
+constexpr int kMaxPeers = 16;
+struct PeerView {                  // passed to the kernel by value
+  double *s[kMaxPeers][2];         // peer q's buffers (s[rank] = local)
+  unsigned long long *flag[kMaxPeers];   // peer q's flag array; this rank writes flag[q][rank]
+  unsigned long long *my_flags;    // local flag array, entry q written by peer q
+  int rank, world;
+};
+struct PeerExchange {
+  bool ready = false;              // buffers allocated (world == 1: local only)
+  bool mapped = false;             // peers' buffers opened (world > 1)
+  void *base = nullptr;            // local allocation: 2 x stride doubles, then kMaxPeers flags
+  size_t stride = 0;               // doubles per buffer
+  void *peer_base[kMaxPeers] = {};
+  unsigned long long epoch = 0;    // exchanges issued so far (same on every rank)
+  PeerView view = {};
 };
 
 constexpr int kWarp = 32;
@@ -100,9 +126,6 @@ constexpr int kRows = 4;          // dense chunks (rows) one warp walks together
 constexpr int kXPad = 16384;      // zero tail of the gathered vector (panels / windows read past N)
 constexpr int kTileRows = 2048;   // rows of a sparse tile (two per thread of a k_rowsum_tiles CTA)
 constexpr int kTileCols = 4 * kPanel;  // columns of a sparse tile = x window in shared memory (128 KB)
-#ifndef TB_TILES16
-#define TB_TILES16 1     // sparse tiles: 1 = two-section layout (tiles16.cu), 0 = 32-bit cells only (tiles.cu)
-#endif
 constexpr int kTileValBits = 15;  // packed tile cell: (column offset * 4) << 16 | value, value < 2^15
 
 // chunk encodings of the compact row-sum stream; ENC_T = the cells live in the sparse tiles
@@ -191,11 +214,20 @@ struct tb_store {
   tb::DevBuf<tb::IceState> state;
   tb::DevBuf<double> trace;               // [(iterations+1)*4]
   tb::PinnedBuf<tb::IceState> h_state;
+  // what survives of the CSR when it is released after the build (positive matrices)
+  bool csr_resident = true;               // rowptr/col/val/chunk_beg still hold the cells
+  bool positive = false;                  // every stored value > 0 and the total < 2^53
+  int64_t n_zero_cells = 0;               // stored cells with value 0
+  tb::DevBuf<long long> row_nnz, row_sum; // [nrows] stored cells / sum of each owned full row (exact)
+  tb::DevBuf<double> live;                // [nrows] cells with a good partner (stores that kept the CSR)
   // multi-GPU
   void *comm = nullptr;
   int rank = 0, world = 1;
+  tb::PeerExchange px;                    // peer-mapped row-sum buffers (comm.cu)
+  std::vector<cudaEvent_t> events;        // reused by every ICE call (kernels.cu)
   // timing of the last ICE call
-  double loop_ms = 0, rowsum_ms = 0;
+  double loop_ms = 0, rowsum_ms = 0, exchange_ms = 0;
+  double last_kernel_ms = 0;              // device time of the last one-pass reduction (K4 / K5)
   int rowsum_launches = 0, total_launches = 0;
   int64_t device_bytes = 0;
   int rowsum_mode = -1;     // -1 default (compact stream), 0 compact, 1 CSR walk (tb_store_set_option)
@@ -209,6 +241,7 @@ int dense_fill_factor();            // see build.cu
 void setup_sections(tb_store *s);   // bin -> section id table (before any build)
 void finish_layout(tb_store *s);     // chunks + scratch once rowptr/col/val are in place
 void export_upper(const tb_store *s, int64_t *nnz, int32_t *h_row, int32_t *h_col, int32_t *h_val);
+void export_upper_device(const tb_store *s, int32_t *d_row, int32_t *d_col, int32_t *d_val, int32_t bin_off);
 void build_batch(tb_store *s, int32_t n, tb_store *const *members);   // block-diagonal concatenation
 // encode.cu
 void build_encoded(tb_store *s);     // compact row-sum stream from the CSR
@@ -238,6 +271,8 @@ void diag_sums(tb_store *s, const uint8_t *h_bad, int64_t ndiag, int64_t *h_sum_
 void comm_unique_id(uint8_t id[128]);
 void comm_init(tb_store *s, int rank, int world, const uint8_t id[128]);
 void comm_destroy(tb_store *s);
+void exchange_setup(tb_store *s);          // (re)allocate the row-sum exchange buffers; maps the peers' when world > 1
+void exchange_release(tb_store *s);
 void allreduce_f64(tb_store *s, const double *send, double *recv, size_t n);
 void allreduce_i64(tb_store *s, const long long *send, long long *recv, size_t n);
 }  // namespace tb

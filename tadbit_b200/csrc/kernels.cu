@@ -1,12 +1,16 @@
-// Hot-path kernels (sm_100a).  Round-1 layout: CSR of the owned full-matrix rows, one
-// warp reduces one chunk (<= kChunk stored cells of one row), a second tiny kernel adds
-// the chunk partials of each row in a fixed order -> deterministic, atomic-free.
+// Hot-path kernels (sm_100a) around K1 (rowsum.cu, tiles.cu):
 //
-//   K1  k_chunk_reduce<F64>      s_i = sum_j v_ij * x_j          (normalize_hic.py:136-143,154-162)
-//   K2  k_ice_reduce/_update     S = x.s, meanS/min/max/dev, B *= S/meanS, x = 1/B (:146-151,217-222)
+//   K2  k_ice_exchange           own row sums -> every GPU's buffer over NVLink, flag barrier,
+//                                S = x.s, meanS/min/max/dev, B *= S/meanS, x = 1/B in ONE kernel
+//                                (normalize_hic.py:146-151,217-222); k_ice_reduce/_update + NCCL
+//                                all-reduce = the same pass as separate steps (TB_EXCHANGE=nccl)
 //   K3  K1 + k_dot               sum v/(b_i b_j)                 (hic_data.py:350-375)
-//   K4  k_chunk_reduce<I64*>     row sums / masked column sums   (hic_filtering.py:36-39,141-145,185-200)
-//   K5  k_diag_hist              per-distance sums               (normalize_hic.py:271-283)
+//   K4  K1 with x = good mask    masked column sums, exact       (hic_filtering.py:36-39,141-145);
+//       row_nnz / row_sum        kept from the build             (hic_filtering.py:185-200)
+//   K5  DiagVisitor              per-distance sums               (normalize_hic.py:271-283)
+//
+// Stores that hold zeros or negative values keep their CSR; the k_chunk_reduce kernels walk it
+// (also the "rowsum=csr" test switch: a second, independent K1).
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -15,6 +19,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "visit.cuh"
 
 namespace tb {
 
@@ -99,17 +104,32 @@ __device__ __forceinline__ double tile_sum(const TileSums &ts, int64_t r) {
   return a;
 }
 
-// out[rb + r] = sum of the row's chunk partials in chunk order + its sparse-tile sums
+// Rows kept by copy_matrix (normalize_hic.py:165-177): not bad, and at least one stored cell whose
+// partner is not bad.  The OWNER of a row decides, in pass 0: a store of positive counts has no
+// CSR, the row keeps a cell iff its first row sum (x = the good mask) is > 0; a store that kept
+// its CSR (zeros, negative values) counts the cells with a good partner (`live`, per owned row).
+// The decision travels with the row sum of pass 0: a row that is not present is published as
+// NaN (its sum is never used), so no second exchange is needed and ranks need not agree on
+// which rule they apply.
+__device__ __forceinline__ double mark_present(const uint8_t *bad, const double *live, int64_t g, int64_t r,
+                                               double a) {
+  const bool p = !bad[g] && (live ? live[r] > 0.0 : a > 0.0);
+  return p ? a : __longlong_as_double(0x7ff8000000000000ll);
+}
+
+// out[rb + r] = sum of the row's chunk partials in chunk order + its sparse-tile sums.
+// mark: pass 0 of an ICE call on several GPUs -- rows that are not present are written as NaN.
 __global__ void k_combine_f64(const double *__restrict__ pf, const int64_t *__restrict__ row_chunk,
                               int64_t nrows, int64_t rb, double *__restrict__ out,
-                              const IceState *__restrict__ state, TileSums ts) {
+                              const IceState *__restrict__ state, TileSums ts, bool mark,
+                              const uint8_t *__restrict__ bad, const double *__restrict__ live) {
   if (state && state->stopped) return;
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
        r += (int64_t)gridDim.x * blockDim.x) {
     double a = 0.0;
     for (int64_t c = row_chunk[r]; c < row_chunk[r + 1]; ++c) a += pf[c];
     a += tile_sum(ts, r);
-    out[rb + r] = a;
+    out[rb + r] = mark ? mark_present(bad, live, rb + r, r, a) : a;
   }
 }
 
@@ -123,44 +143,51 @@ __global__ void k_combine_i64(const long long *__restrict__ pi, const int64_t *_
   }
 }
 
-__global__ void k_row_nnz(const int64_t *__restrict__ rowptr, int64_t nrows, int64_t rb,
-                          long long *__restrict__ out) {
+// out[rb + r] = v[r]: the owned rows' entries of a full-length vector (zeros elsewhere)
+__global__ void k_place_i64(const long long *__restrict__ v, int64_t nrows, int64_t rb,
+                            long long *__restrict__ out) {
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
        r += (int64_t)gridDim.x * blockDim.x)
-    out[rb + r] = rowptr[r + 1] - rowptr[r];
+    out[rb + r] = v[r];
+}
+
+// exact integer row sums computed in fp64 (every partial sum is an integer < 2^53) -> int64
+__global__ void k_f64_to_i64(const double *__restrict__ v, int64_t rb, int64_t re,
+                             long long *__restrict__ out) {
+  for (int64_t i = rb + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < re;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (long long)v[i];
+}
+
+__global__ void k_good_mask(const uint8_t *__restrict__ bad, int64_t n, double *__restrict__ x) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = bad[i] ? 0.0 : 1.0;
 }
 
 // ---------------------------------------------------------------------------------
 // ICE vector kernels
 // ---------------------------------------------------------------------------------
-// "Present" rows (copy_matrix, normalize_hic.py:165-177): non-bad rows that keep at least one
-// stored cell whose partner is not bad.  live_i = stored cells of row i - cells of row i whose
-// partner is bad; by symmetry the second term is collected by walking only the BAD rows (a few
-// per cent of the matrix).  Counts are exact small integers carried as doubles so that they can
-// ride in the same all-reduce as the row sums.
-__global__ void k_live_init(const int64_t *__restrict__ rowptr, int64_t nrows, int64_t rb,
-                            double *__restrict__ live) {
-  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
-       r += (int64_t)gridDim.x * blockDim.x)
-    live[rb + r] = (double)(rowptr[r + 1] - rowptr[r]);
-}
-
+// "Present" rows (copy_matrix, normalize_hic.py:165-177) of a store that kept its CSR:
+// live[r] = stored cells of owned row r whose partner is not bad.  Small integers carried as
+// doubles: the order of the additions is irrelevant.
 __global__ void __launch_bounds__(256)
-k_bad_partners(const int32_t *__restrict__ col, const int64_t *__restrict__ chunk_beg,
-               const int32_t *__restrict__ chunk_row, int64_t nchunks, int64_t rb,
-               const uint8_t *__restrict__ bad, double *__restrict__ live) {
+k_live_rows(const int32_t *__restrict__ col, const int64_t *__restrict__ chunk_beg,
+            const int32_t *__restrict__ chunk_row, int64_t nchunks,
+            const uint8_t *__restrict__ bad, double *__restrict__ live) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t c = warp; c < nchunks; c += nwarp) {
-    if (!bad[rb + chunk_row[c]]) continue;
-    for (int64_t k = chunk_beg[c] + lane; k < chunk_beg[c + 1]; k += 32)
-      atomicAdd(&live[col[k]], -1.0);       // integers: the order of the additions is irrelevant
+    int cnt = 0;
+    for (int64_t k = chunk_beg[c] + lane; k < chunk_beg[c + 1]; k += 32) cnt += !bad[col[k]];
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0 && cnt) atomicAdd(&live[chunk_row[c]], (double)cnt);
   }
 }
 
 __global__ void k_ice_init(const uint8_t *__restrict__ bad, int64_t n, double *x, double *b,
-                           IceState *state) {
+                           IceState *state, unsigned long long epoch_base) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     x[i] = bad[i] ? 0.0 : 1.0;
@@ -173,96 +200,20 @@ __global__ void k_ice_init(const uint8_t *__restrict__ bad, int64_t n, double *x
     state->stopped = 0;
     state->all_bad = 0;
     state->blocks_arrived = 0;
+    state->zero_div = 0;
+    state->fault = 0;
+    state->arrive1 = state->arrive2 = 0;
+    state->fold_epoch = epoch_base;
+    state->epoch_base = epoch_base;
   }
 }
 
 constexpr int kRedThreads = 256;
 
-// S_i = x_i * s_i over present rows -> sum / min / max; the last block to arrive folds the
-// per-block partials in block order and takes the reference's loop decision.
-// FUSED (single GPU): the row's chunk partials are added here instead of in k_combine_f64
-// (one kernel and one pass over s less); s_full is still written for k_ice_update.
-template <bool FUSED>
-__global__ void __launch_bounds__(kRedThreads)
-k_ice_reduce(double *__restrict__ s_full, const double *__restrict__ x,
-             const uint8_t *__restrict__ bad, uint8_t *__restrict__ present, int64_t n,
-             int pass, int iterations, double max_dev, double *__restrict__ block_red,
-             double *__restrict__ trace, IceState *state, const double *__restrict__ pf,
-             const int64_t *__restrict__ row_chunk, TileSums ts) {
-  if (state->stopped) return;
-  __shared__ double sh_sum[kRedThreads / 32], sh_min[kRedThreads / 32], sh_max[kRedThreads / 32];
-  __shared__ long long sh_cnt[kRedThreads / 32];
-  __shared__ bool is_last;
-  double sum = 0.0, mn = INFINITY, mx = -INFINITY;
-  long long cnt = 0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    bool p;
-    double si;
-    if (FUSED) {
-      double a = 0.0;
-      for (int64_t c = row_chunk[i]; c < row_chunk[i + 1]; ++c) a += pf[c];
-      a += tile_sum(ts, i);
-      s_full[i] = si = a;
-      if (pass == 0) present[i] = p = !bad[i] && s_full[n + i] > 0.0;
-      else p = present[i];
-    } else {
-      si = s_full[i];
-      if (pass == 0) {
-        p = !bad[i] && s_full[n + i] > 0.0;    // row kept by copy_matrix (normalize_hic.py:165-177)
-        present[i] = p;
-      } else {
-        p = present[i];
-      }
-    }
-    if (p) {
-      double S = x[i] * si;
-      sum += S;
-      mn = fmin(mn, S);
-      mx = fmax(mx, S);
-      ++cnt;
-    }
-  }
-  for (int o = 16; o; o >>= 1) {
-    sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  }
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) { sh_sum[w] = sum; sh_min[w] = mn; sh_max[w] = mx; sh_cnt[w] = cnt; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int k = 1; k < kRedThreads / 32; ++k) {
-      sum += sh_sum[k]; mn = fmin(mn, sh_min[k]); mx = fmax(mx, sh_max[k]); cnt += sh_cnt[k];
-    }
-    block_red[4 * blockIdx.x + 0] = sum;
-    block_red[4 * blockIdx.x + 1] = mn;
-    block_red[4 * blockIdx.x + 2] = mx;
-    block_red[4 * blockIdx.x + 3] = (double)cnt;
-    __threadfence();
-    unsigned int t = atomicAdd(&state->blocks_arrived, 1u);
-    is_last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!is_last || threadIdx.x >= 32) return;
-  __threadfence();
-  // last block: one warp folds the per-block partials, lane l takes blocks l, l+32, ... and the
-  // lanes are then combined by a fixed butterfly -> same bits every run
-  sum = 0.0; mn = INFINITY; mx = -INFINITY;
-  double dcnt = 0.0;
-  for (unsigned int bl = threadIdx.x; bl < gridDim.x; bl += 32) {
-    const volatile double *br = block_red + 4 * bl;
-    sum += br[0]; mn = fmin(mn, br[1]); mx = fmax(mx, br[2]); dcnt += br[3];
-  }
-  for (int o = 16; o; o >>= 1) {
-    sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    dcnt += __shfl_xor_sync(0xffffffffu, dcnt, o);
-  }
-  if (threadIdx.x != 0) return;
-  state->blocks_arrived = 0;
+// The reference's loop decision for one pass, taken by ONE thread once sum / min / max of S over
+// the present rows are known (normalize_hic.py:211-222).
+__device__ void ice_decide(double sum, double mn, double mx, double dcnt, int pass, int iterations,
+                           double max_dev, double *trace, IceState *state) {
   if (pass == 0) state->n_present = (long long)dcnt;
   const long long np = state->n_present;
   if (np == 0) {
@@ -271,6 +222,11 @@ k_ice_reduce(double *__restrict__ s_full, const double *__restrict__ x,
     return;
   }
   const double mean = sum / (double)np;
+  if (mean == 0.0) {                // float(S) / meanS raises in the reference (_updateDB)
+    state->zero_div = 1;
+    state->stopped = 1;
+    return;
+  }
   state->mean_s = mean;
   state->s_min = mn;
   state->s_max = mx;
@@ -287,6 +243,104 @@ k_ice_reduce(double *__restrict__ s_full, const double *__restrict__ x,
   trace[4 * pass + 3] = dev;
   state->passes_done = pass + 1;
   if (dev < max_dev) state->stopped = 1;
+}
+
+// per-thread sum / min / max / count -> per-block entry of block_red (thread 0 writes it)
+__device__ __forceinline__ void block_stats(double &sum, double &mn, double &mx, long long &cnt,
+                                            double *sh, int nwarps) {
+  for (int o = 16; o; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh[4 * w] = sum; sh[4 * w + 1] = mn; sh[4 * w + 2] = mx; sh[4 * w + 3] = (double)cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double c = (double)cnt;
+    for (int k = 1; k < nwarps; ++k) {
+      sum += sh[4 * k]; mn = fmin(mn, sh[4 * k + 1]); mx = fmax(mx, sh[4 * k + 2]); c += sh[4 * k + 3];
+    }
+    sh[3] = c;
+  }
+}
+
+// one warp folds the per-block entries, lane l takes blocks l, l+32, ... and the lanes are then
+// combined by a fixed butterfly -> same bits every run and on every GPU
+__device__ __forceinline__ void fold_blocks(const double *block_red, unsigned int nblocks, double &sum,
+                                            double &mn, double &mx, double &dcnt) {
+  sum = 0.0; mn = INFINITY; mx = -INFINITY; dcnt = 0.0;
+  for (unsigned int bl = threadIdx.x; bl < nblocks; bl += 32) {
+    const volatile double *br = block_red + 4 * bl;
+    sum += br[0]; mn = fmin(mn, br[1]); mx = fmax(mx, br[2]); dcnt += br[3];
+  }
+  for (int o = 16; o; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    dcnt += __shfl_xor_sync(0xffffffffu, dcnt, o);
+  }
+}
+
+// S_i = x_i * s_i over present rows -> sum / min / max; the last block to arrive folds the
+// per-block partials in block order and takes the reference's loop decision.
+// FUSED (single GPU): the row's chunk partials are added here instead of in k_combine_f64
+// (one kernel and one pass over s less); s_full is still written for k_ice_update.
+template <bool FUSED>
+__global__ void __launch_bounds__(kRedThreads)
+k_ice_reduce(double *__restrict__ s_full, const double *__restrict__ x,
+             const uint8_t *__restrict__ bad, uint8_t *__restrict__ present,
+             const double *__restrict__ live, int64_t n,
+             int pass, int iterations, double max_dev, double *__restrict__ block_red,
+             double *__restrict__ trace, IceState *state, const double *__restrict__ pf,
+             const int64_t *__restrict__ row_chunk, TileSums ts) {
+  if (state->stopped) return;
+  __shared__ double sh[4 * (kRedThreads / 32)];
+  __shared__ bool is_last;
+  double sum = 0.0, mn = INFINITY, mx = -INFINITY;
+  long long cnt = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double si;
+    if (FUSED) {                       // one GPU: row i is local row i
+      double a = 0.0;
+      for (int64_t c = row_chunk[i]; c < row_chunk[i + 1]; ++c) a += pf[c];
+      a += tile_sum(ts, i);
+      if (pass == 0) a = mark_present(bad, live, i, i, a);
+      s_full[i] = si = a;
+    } else {
+      si = s_full[i];
+    }
+    bool p;
+    if (pass == 0) present[i] = p = !isnan(si);
+    else p = present[i];
+    if (p) {
+      double S = x[i] * si;
+      sum += S;
+      mn = fmin(mn, S);
+      mx = fmax(mx, S);
+      ++cnt;
+    }
+  }
+  block_stats(sum, mn, mx, cnt, sh, kRedThreads / 32);
+  if (threadIdx.x == 0) {
+    block_red[4 * blockIdx.x + 0] = sum;
+    block_red[4 * blockIdx.x + 1] = mn;
+    block_red[4 * blockIdx.x + 2] = mx;
+    block_red[4 * blockIdx.x + 3] = sh[3];
+    __threadfence();
+    unsigned int t = atomicAdd(&state->blocks_arrived, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last || threadIdx.x >= 32) return;
+  __threadfence();
+  double dcnt;
+  fold_blocks(block_red, gridDim.x, sum, mn, mx, dcnt);
+  if (threadIdx.x != 0) return;
+  state->blocks_arrived = 0;
+  ice_decide(sum, mn, mx, dcnt, pass, iterations, max_dev, trace, state);
 }
 
 // B_i *= S_i / meanS ; x_i = 1 / B_i.  Runs for every pass whose statistics were finalised,
@@ -309,6 +363,159 @@ __global__ void k_ice_update(const double *__restrict__ s_full, double *__restri
   }
 }
 
+// ---------------------------------------------------------------------------------
+// K2 fused with the exchange between GPUs.  One launch per pass does everything that follows
+// the row sums:
+//   1. every rank adds up the partials of the rows it owns and stores the sums straight into
+//      the buffer of EVERY rank (peer-mapped memory, NVLink stores; buffers alternate by pass so
+//      a fast rank never overwrites what a slow one still reads);
+//   2. flag barrier: when all CTAs of a rank have stored, one thread publishes the exchange
+//      number in every peer's flag array (st.release.sys), and every CTA waits until all peers'
+//      numbers have arrived in its own array (ld.acquire.sys);
+//   3. statistics over the full vector (each rank computes them redundantly from the same bits
+//      in the same order, so all ranks take the same stop decision without a second exchange),
+//      grid-wide fold by the last CTA, loop decision;
+//   4. bias update B *= S / meanS, x = 1 / B.
+// The pass number is read from the device state, so the launch arguments never change.
+// The grid must be co-resident (one CTA per SM): CTAs wait for each other.
+// ---------------------------------------------------------------------------------
+constexpr int kXThreads = 512;
+constexpr unsigned long long kPeerTimeoutNs = 4000000000ull;    // 4 s: a peer that never arrives
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void __launch_bounds__(kXThreads, 1)
+k_ice_exchange(PeerView pv, const double *__restrict__ pf, const int64_t *__restrict__ row_chunk,
+               TileSums ts, int64_t nrows, int64_t rb, int64_t n, double *__restrict__ x,
+               double *__restrict__ b, const uint8_t *__restrict__ bad, uint8_t *__restrict__ present,
+               const double *__restrict__ live, int iterations, double max_dev,
+               double *__restrict__ block_red, double *__restrict__ trace, IceState *state) {
+  volatile IceState *vs = state;
+  if (vs->stopped) return;
+  __shared__ double sh[4 * (kXThreads / 32)];
+  __shared__ int s_last, s_fault;
+  const int pass = vs->passes_done;
+  const unsigned long long epoch = vs->epoch_base + (unsigned long long)pass + 1ull;
+  const int buf = pass & 1;
+  if (threadIdx.x == 0) s_fault = 0;
+  // 1. the rows of this rank -> every rank
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    double a = 0.0;
+    for (int64_t c = row_chunk[r]; c < row_chunk[r + 1]; ++c) a += pf[c];
+    a += tile_sum(ts, r);
+    if (pass == 0) a = mark_present(bad, live, rb + r, r, a);
+    for (int q = 0; q < pv.world; ++q) pv.s[q][buf][rb + r] = a;
+  }
+  __threadfence_system();
+  __syncthreads();
+  // 2. publish once every CTA has stored, then wait for every peer
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&state->arrive1, 1u);
+    if (t == gridDim.x - 1) {
+      state->arrive1 = 0;
+      __threadfence_system();
+      for (int q = 0; q < pv.world; ++q) st_release_sys(pv.flag[q] + pv.rank, epoch);
+    }
+  }
+  if (threadIdx.x < pv.world) {
+    const unsigned long long t0 = now_ns();
+    while (ld_acquire_sys(pv.my_flags + threadIdx.x) < epoch) {
+      if (now_ns() - t0 > kPeerTimeoutNs) { s_fault = 1; break; }
+    }
+  }
+  __syncthreads();
+  if (s_fault) {                       // give up: the host reports it, nothing is updated
+    if (threadIdx.x == 0) { vs->fault = 1; vs->stopped = 1; }
+    return;
+  }
+  // 3. statistics of the pass
+  const double *sfull = pv.s[pv.rank][buf];
+  double sum = 0.0, mn = INFINITY, mx = -INFINITY;
+  long long cnt = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double si = __ldcg(sfull + i);
+    bool p;
+    if (pass == 0) present[i] = p = !isnan(si);
+    else p = present[i];
+    if (p) {
+      const double S = x[i] * si;
+      sum += S;
+      mn = fmin(mn, S);
+      mx = fmax(mx, S);
+      ++cnt;
+    }
+  }
+  block_stats(sum, mn, mx, cnt, sh, kXThreads / 32);
+  if (threadIdx.x == 0) {
+    block_red[4 * blockIdx.x + 0] = sum;
+    block_red[4 * blockIdx.x + 1] = mn;
+    block_red[4 * blockIdx.x + 2] = mx;
+    block_red[4 * blockIdx.x + 3] = sh[3];
+    __threadfence();
+    const unsigned int t = atomicAdd(&state->arrive2, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x < 32) {
+    __threadfence();
+    double dcnt;
+    fold_blocks(block_red, gridDim.x, sum, mn, mx, dcnt);
+    if (threadIdx.x == 0) {
+      state->arrive2 = 0;
+      ice_decide(sum, mn, mx, dcnt, pass, iterations, max_dev, trace, state);
+      __threadfence();
+      st_release_gpu(&state->fold_epoch, epoch);
+    }
+  }
+  // 4. every CTA waits for the decision, then updates its part of B and x
+  if (threadIdx.x == 0) {
+    const unsigned long long t0 = now_ns();
+    while (ld_acquire_gpu(&state->fold_epoch) < epoch) {
+      if (now_ns() - t0 > kPeerTimeoutNs) { s_fault = 1; break; }
+    }
+  }
+  __syncthreads();
+  if (s_fault) {
+    if (threadIdx.x == 0) { vs->fault = 1; vs->stopped = 1; }
+    return;
+  }
+  if (vs->passes_done != pass + 1 || vs->all_bad || vs->zero_div) return;
+  const double mean = vs->mean_s;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (!present[i]) {
+      x[i] = 0.0;
+      continue;
+    }
+    const double S = x[i] * __ldcg(sfull + i);
+    const double bi = b[i] * (S / mean);
+    b[i] = bi;
+    x[i] = (bi != 0.0) ? 1.0 / bi : 0.0;     // B == 0: row frozen by the ZeroDivisionError skip
+  }
+}
+
 __global__ void k_ice_finalize(const double *__restrict__ b, const uint8_t *__restrict__ present,
                                int64_t n, const IceState *__restrict__ state,
                                double *__restrict__ bias) {
@@ -321,10 +528,12 @@ __global__ void k_ice_finalize(const double *__restrict__ b, const uint8_t *__re
 }
 
 __global__ void k_inverse_bias(const double *__restrict__ bias, const uint8_t *__restrict__ bad,
-                               int64_t n, double *__restrict__ y) {
+                               int64_t n, double *__restrict__ y, int *__restrict__ zero_bias) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x)
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (!bad[i] && bias[i] == 0.0) *zero_bias = 1;      // the reference divides by it and raises
     y[i] = bad[i] ? 0.0 : 1.0 / bias[i];
+  }
 }
 
 // sum over owned rows of y_i * s_i, single block (N fits: one pass, fixed order)
@@ -359,44 +568,35 @@ k_sum_good_rows(const long long *__restrict__ v, const uint8_t *__restrict__ bad
 }
 
 // ---------------------------------------------------------------------------------
-// K5: per-distance sums.  Cells of one row have distinct distances, and a warp walks
-// consecutive cells of one row, so the shared-memory histogram sees no intra-warp
-// collisions; distances beyond the shared window go straight to L2 atomics.
+// K5: per-distance sums of the cells (i, i + d) inside one section whose ROW is not bad
+// (normalize_hic.py:271-283: only i is tested).  Visitor over the stored upper-triangle cells:
+// shared-memory histogram for d < 4096, L2 atomics beyond.  Integer sums: any order is exact.
 // ---------------------------------------------------------------------------------
 constexpr int kDiagShared = 4096;
 
-__global__ void __launch_bounds__(256)
-k_diag_hist(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
-            const int64_t *__restrict__ chunk_beg, const int32_t *__restrict__ chunk_row,
-            const int64_t *__restrict__ rowptr, int64_t nchunks, int64_t rb,
-            const uint8_t *__restrict__ bad, const int32_t *__restrict__ chrom_of, int64_t ndiag,
-            unsigned long long *__restrict__ hist) {
-  __shared__ unsigned long long sh[kDiagShared];
-  for (int k = threadIdx.x; k < kDiagShared; k += blockDim.x) sh[k] = 0ull;
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t c = warp; c < nchunks; c += nwarp) {
-    const int64_t r = chunk_row[c];
-    const int64_t g = rb + r;
-    if (bad[g]) continue;
-    const int64_t beg = chunk_beg[c], end = chunk_beg[c + 1];
-    if (col[end - 1] < g) continue;            // chunk entirely below the diagonal
-    const int32_t cg = chrom_of[g];
-    for (int64_t k = beg + lane; k < end; k += 32) {
-      const int64_t j = ld_stream(col + k);
-      const int64_t d = j - g;
-      if (d < 0 || d >= ndiag || chrom_of[j] != cg) continue;
-      const unsigned long long v = (unsigned long long)(long long)ld_stream(val + k);
-      if (d < kDiagShared) atomicAdd(&sh[d], v);
-      else atomicAdd(&hist[d], v);
-    }
+struct DiagVisitor {
+  static constexpr int kShared = kDiagShared * 8;
+  const uint8_t *bad;
+  const int32_t *chrom_of;
+  int64_t ndiag;
+  unsigned long long *hist;
+  unsigned long long *sh;
+  __device__ void begin(uint8_t *smem) {
+    sh = reinterpret_cast<unsigned long long *>(smem);
+    for (int k = threadIdx.x; k < kDiagShared; k += blockDim.x) sh[k] = 0ull;
   }
-  __syncthreads();
-  for (int k = threadIdx.x; k < kDiagShared && k < ndiag; k += blockDim.x)
-    if (sh[k]) atomicAdd(&hist[k], sh[k]);
-}
+  __device__ void cell(int64_t i, int64_t j, int32_t v) {
+    const int64_t d = j - i;
+    if (d >= ndiag || bad[i] || chrom_of[j] != chrom_of[i]) return;
+    const unsigned long long u = (unsigned long long)(long long)v;
+    if (d < kDiagShared) atomicAdd(&sh[d], u);
+    else atomicAdd(&hist[d], u);
+  }
+  __device__ void end(uint8_t *smem) {
+    for (int k = threadIdx.x; k < kDiagShared && k < ndiag; k += blockDim.x)
+      if (sh[k]) atomicAdd(&hist[k], sh[k]);
+  }
+};
 
 inline int grid_1d(int64_t n, int threads, int sm_count, int per_sm = 8) {
   int64_t g = (n + threads - 1) / threads;
@@ -460,7 +660,7 @@ k_seg_reduce(double *__restrict__ s_full, const double *__restrict__ x,
              double max_dev,
              double *__restrict__ trace, int npass_max, SegState *seg, unsigned int *n_stopped,
              IceState *state, const double *__restrict__ pf,
-             const int64_t *__restrict__ row_chunk, TileSums ts) {
+             const int64_t *__restrict__ row_chunk, TileSums ts, const double *__restrict__ live) {
   const int k = blockIdx.x;
   if (seg[k].stopped) return;
   __shared__ double sh_sum[32], sh_min[32], sh_max[32];
@@ -473,7 +673,7 @@ k_seg_reduce(double *__restrict__ s_full, const double *__restrict__ x,
     a += tile_sum(ts, i);
     s_full[i] = a;
     bool p;
-    if (pass == 0) present[i] = p = !bad[i] && s_full[nbins + i] > 0.0;
+    if (pass == 0) present[i] = p = !isnan(mark_present(bad, live, i, i, a));
     else p = present[i];
     if (p) {
       const double S = x[i] * a;
@@ -498,6 +698,9 @@ k_seg_reduce(double *__restrict__ s_full, const double *__restrict__ x,
   bool stop = false;
   if (g.n_present == 0) {
     g.all_bad = 1;
+    stop = true;
+  } else if (sum / (double)g.n_present == 0.0) {   // meanS == 0: ZeroDivisionError in the reference
+    g.all_bad = 2;
     stop = true;
   } else {
     const double mean = sum / (double)g.n_present;
@@ -547,7 +750,9 @@ __global__ void k_seg_finalize(const double *__restrict__ b, const uint8_t *__re
 
 // A/B switch: walk the uncompressed CSR in every pass instead of the compact stream.  Set per
 // store with tb_store_set_option("rowsum", "csr"); the environment TB_ROWSUM=csr sets the default.
+// Only stores that kept their CSR can (TB_KEEP_CSR=1, or matrices with zeros / negative values).
 bool use_csr_rowsum(const tb_store *s) {
+  if (!s->csr_resident) return false;
   if (s->rowsum_mode >= 0) return s->rowsum_mode == 1;
   static int v = -1;
   if (v < 0) {
@@ -555,6 +760,68 @@ bool use_csr_rowsum(const tb_store *s) {
     v = (e && !strcmp(e, "csr")) ? 1 : 0;
   }
   return v == 1;
+}
+
+// TB_EXCHANGE=nccl: the pass is combine -> ncclAllReduce -> statistics -> update as separate
+// steps (the parity reference of the fused exchange); also taken when the peers' buffers
+// could not be mapped.
+bool use_fused_exchange(const tb_store *s) {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("TB_EXCHANGE");
+    v = (e && !strcmp(e, "nccl")) ? 0 : 1;
+  }
+  return v == 1 && s->px.ready && (s->world == 1 || s->px.mapped);
+}
+
+TileSums tile_sums(const tb_store *s) {
+  return TileSums{(!use_csr_rowsum(s) && s->t_nunits) ? s->t_partial.p : nullptr, s->t_unit_of_rb.p};
+}
+
+// One K1 evaluation s = W x into partial_f / t_partial (combined by the caller).
+void rowsum_once(tb_store *s, const double *x, const IceState *state) {
+  if (use_csr_rowsum(s)) {
+    launch_chunks<M_F64>(s, x, nullptr, state);
+  } else {
+    launch_rowsum(s, x, state);
+  }
+}
+
+// Chunks whose cells live in the sparse tiles are not written by the compact kernels: after a
+// CSR walk (which writes every chunk's partial) they must be cleared again.
+void clear_tile_chunk_partials(tb_store *s) {
+  if (s->csr_resident && s->t_nunits)
+    TB_CUDA(cudaMemsetAsync(s->partial_f.p, 0, s->partial_f.bytes(), s->stream));
+}
+
+// Integer row sums of the owned rows over the good columns, exact, into dst[row_begin + r].
+void masked_row_sums(tb_store *s, long long *dst) {
+  cudaStream_t st = s->stream;
+  const int64_t N = s->nbins;
+  if (!s->nrows) return;
+  const int rgrid = grid_1d(s->nrows, 256, s->sm_count);
+  if (s->positive && !use_csr_rowsum(s)) {
+    // K1 with x = the good mask: every term and every partial sum is an integer below 2^53
+    k_good_mask<<<grid_1d(N, 256, s->sm_count), 256, 0, st>>>(s->bad.p, N, s->x.p);
+    clear_tile_chunk_partials(s);
+    launch_rowsum(s, s->x.p, nullptr);
+    k_combine_f64<<<rgrid, 256, 0, st>>>(s->partial_f.p, s->row_chunk.p, s->nrows, s->row_begin,
+                                         s->s_full.p, nullptr, tile_sums(s), false, nullptr, nullptr);
+    k_f64_to_i64<<<rgrid, 256, 0, st>>>(s->s_full.p, s->row_begin, s->row_end, dst);
+  } else {
+    TB_REQUIRE(s->csr_resident, "internal: integer row sums need the CSR for this matrix");
+    launch_chunks<M_I64_MASKED>(s, nullptr, s->bad.p, nullptr);
+    k_combine_i64<<<rgrid, 256, 0, st>>>(s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, dst);
+  }
+}
+
+cudaEvent_t ice_event(tb_store *s, size_t k) {
+  while (s->events.size() <= k) {
+    cudaEvent_t e;
+    TB_CUDA(cudaEventCreate(&e));
+    s->events.push_back(e);
+  }
+  return s->events[k];
 }
 
 }  // namespace
@@ -565,12 +832,10 @@ void row_stats(tb_store *s, int64_t *h_nnz_row, int64_t *h_row_sum) {
   const int64_t N = s->nbins;
   long long *dst = s->world > 1 ? s->i_part.p : s->i_full.p;
   if (s->world == 1) TB_CUDA(cudaMemsetAsync(dst, 0, 2 * N * sizeof(long long), st));
-  launch_chunks<M_I64>(s, nullptr, nullptr, nullptr);
-  if (s->nrows) {
-    k_row_nnz<<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(s->rowptr.p, s->nrows,
-                                                                   s->row_begin, dst);
-    k_combine_i64<<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
-        s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, dst + N);
+  if (s->nrows) {      // both vectors are kept from the build (finish_layout)
+    const int g = grid_1d(s->nrows, 256, s->sm_count);
+    k_place_i64<<<g, 256, 0, st>>>(s->row_nnz.p, s->nrows, s->row_begin, dst);
+    k_place_i64<<<g, 256, 0, st>>>(s->row_sum.p, s->nrows, s->row_begin, dst + N);
   }
   if (s->world > 1) allreduce_i64(s, s->i_part.p, s->i_full.p, 2 * N);
   TB_CUDA(cudaMemcpyAsync(h_nnz_row, s->i_full.p, N * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -584,25 +849,30 @@ void col_sums_masked(tb_store *s, const uint8_t *h_bad, int64_t *h_col_sum) {
   upload_bad(s, h_bad);
   long long *dst = s->world > 1 ? s->i_part.p : s->i_full.p;
   if (s->world == 1) TB_CUDA(cudaMemsetAsync(dst, 0, N * sizeof(long long), st));
-  launch_chunks<M_I64_MASKED>(s, nullptr, s->bad.p, nullptr);
-  if (s->nrows)
-    k_combine_i64<<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
-        s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, dst);
+  cudaEvent_t e0 = ice_event(s, 0), e1 = ice_event(s, 1);
+  TB_CUDA(cudaEventRecord(e0, st));
+  masked_row_sums(s, dst);       // column sums over good rows = row sums over good columns
+  TB_CUDA(cudaEventRecord(e1, st));
   if (s->world > 1) allreduce_i64(s, s->i_part.p, s->i_full.p, N);
   TB_CUDA(cudaMemcpyAsync(h_col_sum, s->i_full.p, N * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  TB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  s->last_kernel_ms = ms;
 }
 
-// live[i] for the owned rows (+ the bad-partner corrections of any row), zeros elsewhere
-void prepare_live(tb_store *s, double *live) {
+// Stores that kept their CSR because they hold zeros or negative values: cells with a good
+// partner per owned row (mark_present).  Positive stores need none of this.
+const double *live_counts(tb_store *s) {
+  if (s->positive) return nullptr;          // with or without the CSR: the same rule, the same result
+  TB_REQUIRE(s->csr_resident, "internal: live counts need the CSR");
   cudaStream_t st = s->stream;
-  TB_CUDA(cudaMemsetAsync(live, 0, s->nbins * sizeof(double), st));
-  if (!s->nrows) return;
-  k_live_init<<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(s->rowptr.p, s->nrows,
-                                                                   s->row_begin, live);
+  if (s->live.n < (size_t)s->nrows + 1) s->live.alloc(s->nrows + 1);
+  TB_CUDA(cudaMemsetAsync(s->live.p, 0, s->live.bytes(), st));
   if (s->nchunks)
-    k_bad_partners<<<chunk_grid(s), 256, 0, st>>>(s->col.p, s->chunk_beg.p, s->chunk_row.p, s->nchunks,
-                                                  s->row_begin, s->bad.p, live);
+    k_live_rows<<<chunk_grid(s), 256, 0, st>>>(s->col.p, s->chunk_beg.p, s->chunk_row.p, s->nchunks,
+                                               s->bad.p, s->live.p);
+  return s->live.p;
 }
 
 int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, double *h_bias,
@@ -615,27 +885,27 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
              "ice: the store owns a row block only; connect the shards first (tb_comm_init)");
   const int npass_max = iterations + 1;
   if (s->trace.n < (size_t)npass_max * 4) s->trace.alloc((size_t)npass_max * 4);
+  if (!s->px.ready) exchange_setup(s);
+  const bool fused = use_fused_exchange(s);
   upload_bad(s, h_bad);
   const int vg = grid_1d(N, 256, s->sm_count);
   int rg = grid_1d(N, kRedThreads, s->sm_count, 4);
   if (rg > 768) rg = 768;
-  k_ice_init<<<vg, 256, 0, st>>>(s->bad.p, N, s->x.p, s->b.p, s->state.p);
+  // every call takes npass_max exchange numbers, used or not: all ranks stay in step
+  const unsigned long long epoch_base = s->px.epoch;
+  s->px.epoch += (unsigned long long)npass_max + 1ull;
+  k_ice_init<<<vg, 256, 0, st>>>(s->bad.p, N, s->x.p, s->b.p, s->state.p, epoch_base);
 
-  std::vector<cudaEvent_t> ev(2 * (size_t)npass_max + 2);
-  for (auto &e : ev) TB_CUDA(cudaEventCreate(&e));
-  // TB_TIMING=1 on several GPUs: where the time between two row sums goes (combine, all-reduce,
-  // statistics + update), printed per rank after the call
+  // TB_TIMING=1: where the time between two row sums goes, printed per rank after the call
   const char *tenv = getenv("TB_TIMING");
-  std::vector<cudaEvent_t> evx;
-  if (s->world > 1 && tenv && tenv[0] == '1') {
-    evx.resize(3 * (size_t)npass_max);
-    for (auto &e : evx) TB_CUDA(cudaEventCreate(&e));
-  }
-  double *dst = s->world > 1 ? s->s_part.p : s->s_full.p;
+  const bool split = tenv && tenv[0] == '1';
+  const size_t ev_pass0 = 2, ev_per_pass = split && !fused && s->world > 1 ? 5 : 3;
+  auto ev = [&](int p, int k) { return ice_event(s, ev_pass0 + (size_t)p * ev_per_pass + k); };
   const bool csr_walk = use_csr_rowsum(s);
-  const TileSums ts = {(!csr_walk && s->t_nunits) ? s->t_partial.p : nullptr, s->t_unit_of_rb.p};
-  prepare_live(s, dst + N);
-  if (ts.partial) TB_CUDA(cudaMemsetAsync(s->partial_f.p, 0, s->partial_f.bytes(), st));
+  const TileSums ts = tile_sums(s);
+  const double *live = live_counts(s);
+  if (!csr_walk) clear_tile_chunk_partials(s);
+  double *dst = s->world > 1 ? s->s_part.p : s->s_full.p;      // separate-step path only
   // The host only needs to know WHEN the loop stopped: passes queued after the stop are no-ops
   // on the device.  ICE converges geometrically, so the next look is scheduled where the
   // deviation is predicted to cross max_dev (at most 16 passes ahead).
@@ -644,29 +914,34 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
   int prev_done = 0;
   int launched = 0;
   bool stopped = false;
-  TB_CUDA(cudaEventRecord(ev[2 * npass_max], st));
+  TB_CUDA(cudaEventRecord(ice_event(s, 0), st));
   for (int p = 0; p < npass_max && !stopped; ++p) {
-    TB_CUDA(cudaEventRecord(ev[2 * p], st));
-    if (csr_walk) launch_chunks<M_F64>(s, s->x.p, nullptr, s->state.p);
-    else launch_rowsum(s, s->x.p, s->state.p);
-    TB_CUDA(cudaEventRecord(ev[2 * p + 1], st));
-    if (s->world > 1) {
+    TB_CUDA(cudaEventRecord(ev(p, 0), st));
+    rowsum_once(s, s->x.p, s->state.p);
+    TB_CUDA(cudaEventRecord(ev(p, 1), st));
+    if (fused) {
+      k_ice_exchange<<<s->sm_count, kXThreads, 0, st>>>(
+          s->px.view, s->partial_f.p, s->row_chunk.p, ts, s->nrows, s->row_begin, N, s->x.p, s->b.p,
+          s->bad.p, s->present.p, live, iterations, max_dev, s->block_red.p, s->trace.p, s->state.p);
+    } else if (s->world > 1) {
       if (s->nrows)
         k_combine_f64<<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
-            s->partial_f.p, s->row_chunk.p, s->nrows, s->row_begin, dst, s->state.p, ts);
-      if (!evx.empty()) TB_CUDA(cudaEventRecord(evx[3 * p], st));
-      allreduce_f64(s, s->s_part.p, s->s_full.p, p == 0 ? 2 * N : N);
-      if (!evx.empty()) TB_CUDA(cudaEventRecord(evx[3 * p + 1], st));
+            s->partial_f.p, s->row_chunk.p, s->nrows, s->row_begin, dst, s->state.p, ts, p == 0,
+            s->bad.p, live);
+      if (ev_per_pass == 5) TB_CUDA(cudaEventRecord(ev(p, 3), st));
+      allreduce_f64(s, s->s_part.p, s->s_full.p, N);
+      if (ev_per_pass == 5) TB_CUDA(cudaEventRecord(ev(p, 4), st));
       k_ice_reduce<false><<<rg, kRedThreads, 0, st>>>(
-          s->s_full.p, s->x.p, s->bad.p, s->present.p, N, p, iterations, max_dev, s->block_red.p,
-          s->trace.p, s->state.p, nullptr, nullptr, ts);
+          s->s_full.p, s->x.p, s->bad.p, s->present.p, live, N, p, iterations, max_dev,
+          s->block_red.p, s->trace.p, s->state.p, nullptr, nullptr, ts);
+      k_ice_update<<<vg, 256, 0, st>>>(s->s_full.p, s->x.p, s->b.p, s->present.p, N, p, s->state.p);
     } else {
       k_ice_reduce<true><<<rg, kRedThreads, 0, st>>>(
-          s->s_full.p, s->x.p, s->bad.p, s->present.p, N, p, iterations, max_dev, s->block_red.p,
-          s->trace.p, s->state.p, s->partial_f.p, s->row_chunk.p, ts);
+          s->s_full.p, s->x.p, s->bad.p, s->present.p, live, N, p, iterations, max_dev,
+          s->block_red.p, s->trace.p, s->state.p, s->partial_f.p, s->row_chunk.p, ts);
+      k_ice_update<<<vg, 256, 0, st>>>(s->s_full.p, s->x.p, s->b.p, s->present.p, N, p, s->state.p);
     }
-    k_ice_update<<<vg, 256, 0, st>>>(s->s_full.p, s->x.p, s->b.p, s->present.p, N, p, s->state.p);
-    if (!evx.empty()) TB_CUDA(cudaEventRecord(evx[3 * p + 2], st));
+    TB_CUDA(cudaEventRecord(ev(p, 2), st));
     ++launched;
     if (p + 1 >= next_poll || p == npass_max - 1) {
       TB_CUDA(cudaMemcpyAsync(s->h_state.p, s->state.p, sizeof(IceState), cudaMemcpyDeviceToHost, st));
@@ -684,16 +959,22 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
       next_poll = p + 1 + step;
     }
   }
-  TB_CUDA(cudaEventRecord(ev[2 * npass_max + 1], st));
+  TB_CUDA(cudaEventRecord(ice_event(s, 1), st));
   TB_CUDA(cudaMemcpyAsync(s->h_state.p, s->state.p, sizeof(IceState), cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaStreamSynchronize(st));
   const IceState hs = *s->h_state.p;
   int rc = TB_OK;
-  if (hs.all_bad) {
+  if (hs.fault) {
+    set_error("ice: a GPU of the group did not reach the row-sum exchange within %.0f s",
+              (double)kPeerTimeoutNs * 1e-9);
+    rc = TB_ERR_STATE;
+  } else if (hs.all_bad) {
     set_error("ERROR: normalization failed, all bad columns");
     rc = TB_ERR_ALL_BAD;
+  } else if (hs.zero_div) {
+    set_error("float division by zero");
+    rc = TB_ERR_ZERO_DIV;
   } else {
-    // bias into s_part's tail is avoided: reuse partial-free buffer b -> finalize into x
     k_ice_finalize<<<vg, 256, 0, st>>>(s->b.p, s->present.p, N, s->state.p, s->x.p);
     TB_CUDA(cudaMemcpyAsync(h_bias, s->x.p, N * sizeof(double), cudaMemcpyDeviceToHost, st));
     const int done = hs.passes_done;
@@ -705,40 +986,43 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
   }
   // timing (only passes that did work)
   float ms = 0.f;
-  TB_CUDA(cudaEventElapsedTime(&ms, ev[2 * npass_max], ev[2 * npass_max + 1]));
+  TB_CUDA(cudaEventElapsedTime(&ms, ice_event(s, 0), ice_event(s, 1)));
   s->loop_ms = ms;
   s->rowsum_ms = 0;
+  s->exchange_ms = 0;
   s->rowsum_launches = 0;
-  const int real = hs.all_bad ? 0 : hs.passes_done;
+  const int real = rc == TB_OK ? hs.passes_done : 0;
+  double t_comb = 0, t_red = 0, t_upd = 0;
   for (int p = 0; p < real && p < launched; ++p) {
-    TB_CUDA(cudaEventElapsedTime(&ms, ev[2 * p], ev[2 * p + 1]));
+    TB_CUDA(cudaEventElapsedTime(&ms, ev(p, 0), ev(p, 1)));
     s->rowsum_ms += ms;
+    TB_CUDA(cudaEventElapsedTime(&ms, ev(p, 1), ev(p, 2)));
+    s->exchange_ms += ms;
     ++s->rowsum_launches;
+    if (ev_per_pass == 5) {
+      float a = 0.f, b = 0.f, c = 0.f;
+      cudaEventElapsedTime(&a, ev(p, 1), ev(p, 3));
+      cudaEventElapsedTime(&b, ev(p, 3), ev(p, 4));
+      cudaEventElapsedTime(&c, ev(p, 4), ev(p, 2));
+      t_comb += a; t_red += b; t_upd += c;
+    }
   }
   {   // kernels of this library launched by the call (NCCL's own kernels are not counted)
     const int k1 = csr_walk ? 1 : (s->t_nunits > 0) + (s->n_groups > 0) + (s->n_sparse > 0);
-    const int k2 = 2 + (s->world > 1 && s->nrows ? 1 : 0);       // (combine) + reduce + update
-    s->total_launches = 4 /* init, live, bad partners, finalize */ + launched * (k1 + k2);
+    const int k2 = fused ? 1 : 2 + (s->world > 1 && s->nrows ? 1 : 0);   // exchange | (combine) + reduce + update
+    s->total_launches = 2 /* init, finalize */ + (live ? 1 : 0) + launched * (k1 + k2);
   }
-  if (!evx.empty()) {
-    double t_comb = 0, t_red = 0, t_upd = 0;
-    int cnt = 0;
-    for (int p = 1; p < real && p < launched; ++p) {       // pass 0 carries 2N in the all-reduce
-      float a = 0.f, b = 0.f, c = 0.f;
-      cudaEventElapsedTime(&a, ev[2 * p + 1], evx[3 * p]);
-      cudaEventElapsedTime(&b, evx[3 * p], evx[3 * p + 1]);
-      cudaEventElapsedTime(&c, evx[3 * p + 1], evx[3 * p + 2]);
-      t_comb += a; t_red += b; t_upd += c;
-      ++cnt;
-    }
-    if (cnt)
+  if (split && real > 0) {
+    const int cnt = real < launched ? real : launched;
+    if (ev_per_pass == 5)
       fprintf(stderr, "[tadbit_b200] rank %d: per pass row sum %.1f us, combine %.1f us, all-reduce %.1f us, "
-                      "statistics + update %.1f us (%d passes)\n", s->rank,
-              1e3 * s->rowsum_ms / (s->rowsum_launches ? s->rowsum_launches : 1), 1e3 * t_comb / cnt,
-              1e3 * t_red / cnt, 1e3 * t_upd / cnt, cnt);
-    for (auto &e : evx) cudaEventDestroy(e);
+                      "statistics + update %.1f us (%d passes)\n", s->rank, 1e3 * s->rowsum_ms / cnt,
+              1e3 * t_comb / cnt, 1e3 * t_red / cnt, 1e3 * t_upd / cnt, cnt);
+    else
+      fprintf(stderr, "[tadbit_b200] rank %d: per pass row sum %.1f us, %s %.1f us, whole pass %.1f us (%d passes)\n",
+              s->rank, 1e3 * s->rowsum_ms / cnt, fused ? "fused exchange + statistics + update" : "statistics + update",
+              1e3 * s->exchange_ms / cnt, 1e3 * s->loop_ms / cnt, cnt);
   }
-  for (auto &e : ev) cudaEventDestroy(e);
   return rc;
 }
 
@@ -748,10 +1032,7 @@ void norm_sum(tb_store *s, const double *h_bias, const uint8_t *h_bad, double *o
   TB_REQUIRE(out, "norm_sum: null output");
   upload_bad(s, h_bad);
   if (!h_bias) {        // raw sum: exact integers
-    launch_chunks<M_I64_MASKED>(s, nullptr, s->bad.p, nullptr);
-    if (s->nrows)
-      k_combine_i64<<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
-          s->partial_i.p, s->row_chunk.p, s->nrows, s->row_begin, s->i_full.p);
+    masked_row_sums(s, s->i_full.p);
     k_sum_good_rows<<<1, 1024, 0, st>>>(s->i_full.p, s->bad.p, s->row_begin, s->row_end,
                                         s->scal_i.p);
     if (s->world > 1) allreduce_i64(s, s->scal_i.p, s->scal_i.p + 8, 1);
@@ -764,25 +1045,26 @@ void norm_sum(tb_store *s, const double *h_bias, const uint8_t *h_bad, double *o
   }
   // y = 1/bias on good bins, 0 on bad ones; sum = y . (W y)
   TB_CUDA(cudaMemcpyAsync(s->b.p, h_bias, N * sizeof(double), cudaMemcpyHostToDevice, st));
-  k_inverse_bias<<<grid_1d(N, 256, s->sm_count), 256, 0, st>>>(s->b.p, s->bad.p, N, s->x.p);
-  if (use_csr_rowsum(s)) {
-    launch_chunks<M_F64>(s, s->x.p, nullptr, nullptr);
-  } else {
-    // chunks whose cells live in the sparse tiles are not written by the compact kernels: make
-    // sure no partial of an earlier CSR walk (pass 0, or the "csr" option) is left in them
-    if (s->t_nunits) TB_CUDA(cudaMemsetAsync(s->partial_f.p, 0, s->partial_f.bytes(), st));
-    launch_rowsum(s, s->x.p, nullptr);
-  }
+  TB_CUDA(cudaMemsetAsync(s->scal_i.p, 0, sizeof(long long), st));
+  k_inverse_bias<<<grid_1d(N, 256, s->sm_count), 256, 0, st>>>(s->b.p, s->bad.p, N, s->x.p,
+                                                               reinterpret_cast<int *>(s->scal_i.p));
+  if (!use_csr_rowsum(s)) clear_tile_chunk_partials(s);
+  rowsum_once(s, s->x.p, nullptr);
   if (s->nrows)
     k_combine_f64<<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
-        s->partial_f.p, s->row_chunk.p, s->nrows, s->row_begin, s->s_full.p,
-        nullptr, TileSums{(!use_csr_rowsum(s) && s->t_nunits) ? s->t_partial.p : nullptr,
-                          s->t_unit_of_rb.p});
+        s->partial_f.p, s->row_chunk.p, s->nrows, s->row_begin, s->s_full.p, nullptr, tile_sums(s),
+        false, nullptr, nullptr);
   k_dot_rows<<<1, 1024, 0, st>>>(s->x.p, s->s_full.p, s->row_begin, s->row_end, s->scal_f.p);
   if (s->world > 1) allreduce_f64(s, s->scal_f.p, s->scal_f.p + 8, 1);
+  int zero_bias = 0;
+  TB_CUDA(cudaMemcpyAsync(&zero_bias, s->scal_i.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaMemcpyAsync(out, s->world > 1 ? s->scal_f.p + 8 : s->scal_f.p, sizeof(double),
                           cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaStreamSynchronize(st));
+  if (zero_bias) {      // v / bias[i] / bias[j] raises in the reference (hic_data.py:371-374)
+    set_error("float division by zero");
+    throw Fail{TB_ERR_ZERO_DIV};
+  }
 }
 
 void diag_sums(tb_store *s, const uint8_t *h_bad, int64_t ndiag, int64_t *h_sum_d) {
@@ -793,12 +1075,16 @@ void diag_sums(tb_store *s, const uint8_t *h_bad, int64_t ndiag, int64_t *h_sum_
   DevBuf<unsigned long long> hist, red;
   hist.alloc(ndiag);
   TB_CUDA(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
-  if (s->nchunks) {
-    int64_t need = (s->nchunks + 7) / 8, cap = (int64_t)s->sm_count * 4;
-    int g = (int)(need < cap ? need : cap);
-    k_diag_hist<<<g, 256, 0, st>>>(s->col.p, s->val.p, s->chunk_beg.p, s->chunk_row.p, s->rowptr.p,
-                                   s->nchunks, s->row_begin, s->bad.p, s->chrom_of.p, ndiag, hist.p);
-  }
+  cudaEvent_t e0 = ice_event(s, 0), e1 = ice_event(s, 1);
+  TB_CUDA(cudaEventRecord(e0, st));
+  DiagVisitor vis;
+  vis.bad = s->bad.p;
+  vis.chrom_of = s->chrom_of.p;
+  vis.ndiag = ndiag;
+  vis.hist = hist.p;
+  vis.sh = nullptr;
+  visit_upper(s, vis);
+  TB_CUDA(cudaEventRecord(e1, st));
   unsigned long long *src = hist.p;
   if (s->world > 1) {
     red.alloc(ndiag);
@@ -807,6 +1093,9 @@ void diag_sums(tb_store *s, const uint8_t *h_bad, int64_t ndiag, int64_t *h_sum_
   }
   TB_CUDA(cudaMemcpyAsync(h_sum_d, src, ndiag * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  TB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  s->last_kernel_ms = ms;
 }
 
 void ice_batch(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, double *h_bias,
@@ -830,24 +1119,21 @@ void ice_batch(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max
   TB_CUDA(cudaMemsetAsync(trace.p, 0, trace.bytes(), st));
   upload_bad(s, h_bad);
   const int vg = grid_1d(N, 256, s->sm_count);
-  k_ice_init<<<vg, 256, 0, st>>>(s->bad.p, N, s->x.p, s->b.p, s->state.p);
+  k_ice_init<<<vg, 256, 0, st>>>(s->bad.p, N, s->x.p, s->b.p, s->state.p, 0ull);
   k_seg_init<<<(nseg + 255) / 256, 256, 0, st>>>(seg.p, nseg, n_stopped.p);
   const bool csr_walk = use_csr_rowsum(s);
-  const TileSums ts = {(!csr_walk && s->t_nunits) ? s->t_partial.p : nullptr, s->t_unit_of_rb.p};
-  prepare_live(s, s->s_full.p + N);
-  if (ts.partial) TB_CUDA(cudaMemsetAsync(s->partial_f.p, 0, s->partial_f.bytes(), st));
-  cudaEvent_t e0, e1;
-  TB_CUDA(cudaEventCreate(&e0));
-  TB_CUDA(cudaEventCreate(&e1));
+  const TileSums ts = tile_sums(s);
+  const double *live = live_counts(s);
+  if (!csr_walk) clear_tile_chunk_partials(s);
+  cudaEvent_t e0 = ice_event(s, 0), e1 = ice_event(s, 1);
   TB_CUDA(cudaEventRecord(e0, st));
   bool stopped = false;
   int launched = 0;
   for (int p = 0; p < npass_max && !stopped; ++p) {
-    if (csr_walk) launch_chunks<M_F64>(s, s->x.p, nullptr, s->state.p);
-    else launch_rowsum(s, s->x.p, s->state.p);
+    rowsum_once(s, s->x.p, s->state.p);
     k_seg_reduce<<<nseg, 1024, 0, st>>>(s->s_full.p, s->x.p, s->bad.p, s->present.p, seg_off.p, nseg,
                                         N, p, iterations, max_dev, trace.p, npass_max, seg.p,
-                                        n_stopped.p, s->state.p, s->partial_f.p, s->row_chunk.p, ts);
+                                        n_stopped.p, s->state.p, s->partial_f.p, s->row_chunk.p, ts, live);
     k_seg_update<<<vg, 256, 0, st>>>(s->s_full.p, s->x.p, s->b.p, s->present.p, s->chrom_of.p, N, p,
                                      seg.p);
     ++launched;
@@ -865,18 +1151,18 @@ void ice_batch(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max
   if (h_trace && iterations > 0)
     TB_CUDA(cudaMemcpyAsync(h_trace, trace.p, trace.bytes(), cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaStreamSynchronize(st));
-  for (int k = 0; k < nseg; ++k) n_passes[k] = hseg[k].all_bad ? -1 : hseg[k].passes_done;
+  // -1: no row left in the matrix (all bad columns); -2: its mean row sum is 0 (float division by zero)
+  for (int k = 0; k < nseg; ++k) n_passes[k] = hseg[k].all_bad ? -hseg[k].all_bad : hseg[k].passes_done;
   float ms = 0.f;
   TB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
   s->loop_ms = ms;
   s->rowsum_ms = 0;
+  s->exchange_ms = 0;
   s->rowsum_launches = 0;
   {
     const int k1 = csr_walk ? 1 : (s->t_nunits > 0) + (s->n_groups > 0) + (s->n_sparse > 0);
-    s->total_launches = 3 + (launched ? 3 : 0) + (launched > 1 ? (launched - 1) * (k1 + 2) : 0);
+    s->total_launches = 3 + (live ? 1 : 0) + launched * (k1 + 2);
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
 }
 
 // Work of every owned row in the two K1 kernels: slots of its dense chunks, cells in sparse tiles.
@@ -921,7 +1207,7 @@ void probe_rowsum(tb_store *s, int32_t reps, double ms[3]) {
   TB_REQUIRE(reps > 0 && ms, "probe_rowsum: bad arguments");
   TB_CUDA(cudaMemsetAsync(s->bad.p, 0, s->nbins, st));
   k_ice_init<<<grid_1d(s->nbins, 256, s->sm_count), 256, 0, st>>>(s->bad.p, s->nbins, s->x.p, s->b.p,
-                                                                  s->state.p);
+                                                                  s->state.p, s->px.epoch);
   launch_rowsum(s, s->x.p, nullptr);                 // warm-up
   cudaEvent_t e[3];
   for (auto &x : e) TB_CUDA(cudaEventCreate(&x));

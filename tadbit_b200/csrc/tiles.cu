@@ -6,36 +6,42 @@
 // non-empty tiles and keeps the tile's x window (kTileCols = 16384 doubles, 128 KB) in shared
 // memory, fetched by cp.async.bulk, so every gather is a shared-memory read.
 //
-// Layout.  Inside a tile the rows are sorted by their number of cells (per-tile permutation)
-// and stored as sliced ELL: 32 consecutive sorted rows form a slice, padded to the slice's
-// longest row rounded up to 4 cells; cell k of lane l sits at slice_base + 128 (k / 4) + 4 l +
-// k % 4, so a lane reads four of its cells with one 16-byte shared-memory load.  A cell is 32
-// bits, (column offset * 4) << 16 | count with count < 2^15: `cell >> 15` is the byte offset of
-// x_j in the window and `cell & 0xffff` the count.
+// Layout.  Inside a tile the rows are sorted by length (per-tile permutation) and stored as
+// sliced ELL: 32 consecutive sorted rows form a slice.  At high resolution most cells outside
+// the dense panels hold exactly ONE contact (genome-wide 5 kb model: 96 % of the tile cells),
+// and a cell worth 1 needs no count: every slice therefore has two sections,
+//
+//   ones     16 bits per cell = column offset in the window; the term is x_j itself (one DADD
+//            instead of unpack + convert + DFMA),
+//   general  32 bits per cell = (column offset * 4) << 16 | count, count < 2^15: `cell >> 15`
+//            is the byte offset of x_j in the window and `cell & 0xffff` the count,
+//
+// both stored in 512-byte blocks (one 16-byte shared-memory read per lane: 8 ones or 4 general
+// cells of that lane), each section padded to the longest row of the slice.  Padding slots are
+// written for every lane and step by k_tile_init: a ones slot points at one of 16 zeros kept
+// behind the x window (index 16384 + r), a general slot has count 0; either way at the bank
+// the slot prefers, r = (lane + step) mod 16.  Rows are sorted by their number of ones.
 //
 // Bank conflicts.  ncu showed the first version of this kernel waiting on the shared-memory
 // pipe (mio_throttle): a random 8-byte gather by 32 lanes costs ~6 wavefronts instead of 2.
 // The order of a row's cells inside a tile is free, so the fill kernel deals them out by bank:
 // at step k lane l prefers a cell whose column is congruent to l + k mod 16 (the 16 lanes of a
 // half-warp then hit 16 different 8-byte bank pairs); cells that find no such step take the
-// steps left over, padding gets the preferred residue with count 0.
+// steps left over.
 //
 // Streaming.  A warp's cells of one work unit form a stream that does not depend on the x
-// windows.  It is cut at build time into pieces of up to 16 steps (2 KB), one 8-byte copy
+// windows.  It is cut at build time into pieces of up to 4 blocks (2 KB), one 8-byte copy
 // descriptor each (where the piece starts, which rows it belongs to, end-of-slice / end-of-tile
 // marks); the warp pulls the pieces through a private two-stage ring in shared memory with
 // cp.async.bulk, two pieces ahead of what it consumes, across slice and tile boundaries.  A CTA
 // has 16 warps; warp w takes slices w, 31 - w, 32 + w and 63 - w of every tile (long with
-// short).  Measured on the genome-wide 5 kb matrix: 32 warps x 1 KB pieces 1.54 ms, 16 x 2 KB
-// 1.36 ms, 8 x 4 KB 1.40 ms -- the fixed work per piece (barrier wait, copy issue) is what the
-// larger pieces save.
+// short).
 //
 // Scheduling.  Row blocks are cut into work units of roughly equal cost; CTAs (one per SM)
 // fetch them from an atomic counter, most expensive first.  A unit writes kTileRows partial
 // sums, added per row in unit order by the combine step, so results do not depend on which CTA
 // ran which unit: deterministic, no atomics on the data path.
 #include "common.cuh"
-#if !TB_TILES16   // the default build uses the two-section layout of tiles16.cu instead
 #include <algorithm>
 #include <numeric>
 #include <type_traits>
@@ -50,32 +56,39 @@ namespace {
 #ifndef TB_TILE_WARPS
 #define TB_TILE_WARPS 16
 #endif
-#ifndef TB_PIECE_QUADS
-#define TB_PIECE_QUADS 4
-#endif
+#ifndef TB_FILL_HIST
+#define TB_FILL_HIST 0      // 1: k_tile_fill counts residues in a shared-memory histogram per warp
+#endif                      //    (match_any + one add per group) instead of 32 ballots per 32 cells;
+                            //    written at the end of round 1, not yet run on a GPU
 constexpr int kSortThreads = kTileRows / 2;                // k_tile_sort
 constexpr int kTileWarps = TB_TILE_WARPS;                  // warps of a k_rowsum_tiles CTA
 constexpr int kTileThreads = kTileWarps * 32;
-constexpr int kPieceQuads = TB_PIECE_QUADS;                // steps / 4 per ring stage
+constexpr int kPieceBlocks = 4;                            // 512-byte blocks per ring stage
 constexpr int kSlices = kTileRows / 32;
-constexpr int kSliceTab = kSlices + 1;
+constexpr int kSliceTab = 2 * kSlices + 1;                 // (ones start, general start) per slice + end
 constexpr int kRowBits = 11;                               // kTileRows = 2048
 constexpr int kWinBytes = kTileCols * 8;
-static_assert(kTileRows == 1 << kRowBits, "kRowBits");
+constexpr int kZeroTail = 128;                             // 16 zeros behind the window (ones padding)
 constexpr int kWarpSlices = kSlices / kTileWarps;          // slices of a tile one warp streams
-static_assert(kSlices % kTileWarps == 0 && kPieceQuads >= 1 && kPieceQuads <= 15, "tile kernel shape");
-static_assert(kTileCols * 4 <= 65536 && kTileValBits == 15, "cell packing");
+static_assert(kTileRows == 1 << kRowBits, "kRowBits");
+static_assert(kSlices % kTileWarps == 0, "tile kernel shape");
+static_assert(kTileCols * 4 <= 65536 && kTileValBits == 15 && kTileCols + 16 <= 32768, "cell packing");
 
-// copy descriptor: x = first step of the piece in the cell array (cell index / 32),
-// y = row group (tile * 64 + slice) | steps / 4 << 26 | end-of-slice << 30 | end-of-tile << 31
-constexpr uint32_t kDescGroupMask = (1u << 26) - 1u;
+// copy descriptor: x = first 512-byte block of the piece in the cell array,
+// y = row group (tile * 64 + slice, 25 bits) | general section << 25 | blocks << 26 |
+//     end-of-slice << 30 | end-of-tile << 31
+constexpr uint32_t kDescGroupMask = (1u << 25) - 1u;
+constexpr uint32_t kDescGeneral = 1u << 25;
 constexpr uint32_t kDescEndSlice = 1u << 30, kDescEndTile = 1u << 31;
-constexpr int kPieceBytes = kPieceQuads * 512;             // steps x 128 B
+constexpr int kPieceBytes = kPieceBlocks * 512;
 constexpr int kRing = 2;
-constexpr int kTileSmem = kWinBytes + kTileRows * 8 + kTileWarps * kRing * kPieceBytes +
-                          (kTileWarps * kRing + 1) * 8 + 64;
-// fixed cost of a tile in a unit (window load, barrier, descriptor chain), in cells of stream
+constexpr int kAccOff = kWinBytes + kZeroTail;
+constexpr int kRingOff = kAccOff + kTileRows * 8;
+constexpr int kTailOff = kRingOff + kTileWarps * kRing * kPieceBytes;
+constexpr int kTileSmem = kTailOff + (kTileWarps * kRing + 1) * 8 + 64;
+// fixed cost of a tile in a unit (window load, barrier, descriptor chain), in general cells
 constexpr int64_t kTileFixedCost = 24000;
+constexpr double kBlockCost = 128.0;                       // a block, in general cells
 
 __device__ __forceinline__ double u2d(uint32_t v) {
   return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
@@ -122,6 +135,7 @@ __host__ __device__ __forceinline__ int warp_slice(int w, int h) {
 // for a byte but fit a tile cell (encode.cu counts them per chunk in tovf).
 __device__ __forceinline__ bool tile_overflow(int32_t v) { return v > 255 && v < (1 << kTileValBits); }
 
+// cnt[row][window]: ones in the low half, general cells in the high half
 __global__ void __launch_bounds__(256)
 k_tile_count(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
              const int64_t *__restrict__ chunk_beg, const int32_t *__restrict__ chunk_row,
@@ -134,25 +148,32 @@ k_tile_count(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
     const bool all = (desc[c].z & 0xff) == ENC_T;
     if (!all && tovf[c] == 0) continue;
     const int64_t beg = chunk_beg[c], end = chunk_beg[c + 1], row = chunk_row[c];
-    for (int64_t k = beg + lane; k < end; k += 32)
-      if (all || tile_overflow(val[k])) atomicAdd(&cnt[row * nwin + col[k] / kTileCols], 1);
+    for (int64_t k = beg + lane; k < end; k += 32) {
+      const int32_t v = val[k];
+      if (all || tile_overflow(v))
+        atomicAdd(&cnt[row * nwin + col[k] / kTileCols], (all && v == 1) ? 1 : (1 << 16));
+    }
   }
 }
 
-// one CTA per tile: sort the tile's rows by cell count (descending, ties by row), write the
-// permutation, its inverse, the slice offsets and the padded size of the tile
+// one CTA per tile: sort the tile's rows by their number of ones (descending, ties by row), write
+// the permutation, its inverse, the block offsets of the slice sections and the size of the tile
 __global__ void __launch_bounds__(kSortThreads)
 k_tile_sort(const int32_t *__restrict__ cnt, int64_t nwin, uint16_t *__restrict__ perm,
             uint16_t *__restrict__ inv, uint32_t *__restrict__ slice, int64_t *__restrict__ tile_size,
             int32_t *__restrict__ tile_crit, unsigned long long *__restrict__ totals) {
   __shared__ uint32_t key[kTileRows];
+  __shared__ uint16_t gen[kTileRows];                  // general cells of each row
+  __shared__ uint32_t b1[kSlices], b2[kSlices];        // blocks of the two sections of each slice
   const int t = threadIdx.x;
   const int64_t tile = blockIdx.x, rb = tile / nwin, w = tile % nwin;
   unsigned long long real = 0;
   for (int e = t; e < kTileRows; e += kSortThreads) {
-    const uint32_t mine = (uint32_t)cnt[(rb * kTileRows + e) * nwin + w];
-    key[e] = (mine << kRowBits) | (uint32_t)(kTileRows - 1 - e);
-    real += mine;
+    const uint32_t both = (uint32_t)cnt[(rb * kTileRows + e) * nwin + w];
+    const uint32_t ones = both & 0xffffu;
+    gen[e] = (uint16_t)(both >> 16);
+    key[e] = (ones << kRowBits) | (uint32_t)(kTileRows - 1 - e);
+    real += ones + (both >> 16);
   }
   __syncthreads();
   for (int k = 2; k <= kTileRows; k <<= 1)            // bitonic sort, descending
@@ -172,25 +193,65 @@ k_tile_sort(const int32_t *__restrict__ cnt, int64_t nwin, uint16_t *__restrict_
     perm[tile * kTileRows + e] = (uint16_t)row;
     inv[(rb * kTileRows + row) * nwin + w] = (uint16_t)e;
   }
-  if (t == 0) {               // slice s is as long as its first row, rounded up to 4 steps
-    uint32_t run = 0;
-    for (int s = 0; s < kSlices; ++s) {
-      slice[tile * kSliceTab + s] = run;
-      run += (((key[s * 32] >> kRowBits) + 3u) & ~3u) * 32u;
+  if (t < kSlices) {          // sections are as long as the longest row of the slice
+    uint32_t gmax = 0;
+    for (int i = 0; i < 32; ++i) {
+      const int row = kTileRows - 1 - (int)(key[t * 32 + i] & (uint32_t)(kTileRows - 1));
+      gmax = max(gmax, (uint32_t)gen[row]);
     }
-    slice[tile * kSliceTab + kSlices] = run;
+    b1[t] = ((key[t * 32] >> kRowBits) + 7u) >> 3;     // 8 ones per lane and block
+    b2[t] = (gmax + 3u) >> 2;                          // 4 general cells per lane and block
+  }
+  __syncthreads();
+  if (t == 0) {
+    uint32_t run = 0, n1 = 0, n2 = 0;
+    for (int s = 0; s < kSlices; ++s) {
+      slice[tile * kSliceTab + 2 * s] = run;
+      run += b1[s];
+      slice[tile * kSliceTab + 2 * s + 1] = run;
+      run += b2[s];
+      n1 += b1[s];
+      n2 += b2[s];
+    }
+    slice[tile * kSliceTab + 2 * kSlices] = run;
     tile_size[tile] = run;
-    // steps of the busiest warp (warp w streams slices w and 63 - w one after the other)
-    uint32_t crit = 0;
-    for (int w = 0; w < kTileWarps; ++w) {
+    uint32_t crit = 0;                                 // blocks of the busiest warp
+    for (int wq = 0; wq < kTileWarps; ++wq) {
       uint32_t mine = 0;
-      for (int h = 0; h < kWarpSlices; ++h) mine += ((key[warp_slice(w, h) * 32] >> kRowBits) + 3u) & ~3u;
+      for (int h = 0; h < kWarpSlices; ++h) mine += b1[warp_slice(wq, h)] + b2[warp_slice(wq, h)];
       crit = max(crit, mine);
     }
     tile_crit[tile] = (int32_t)crit;
+    if (n1) atomicAdd(totals + 1, (unsigned long long)n1);
+    if (n2) atomicAdd(totals + 2, (unsigned long long)n2);
   }
   for (int o = 16; o; o >>= 1) real += __shfl_xor_sync(0xffffffffu, real, o);
   if ((t & 31) == 0 && real) atomicAdd(totals, real);  // unpadded cells, for the layout report
+}
+
+// one CTA per tile: every slot starts as padding at its preferred bank, r = (lane + step) mod 16
+__global__ void __launch_bounds__(256)
+k_tile_init(const uint32_t *__restrict__ slice, const int64_t *__restrict__ t_off,
+            uint32_t *__restrict__ cells) {
+  const int64_t tile = blockIdx.x;
+  const uint32_t *st = slice + tile * kSliceTab;
+  uint32_t *base = cells + t_off[tile] * 128;          // 128 words per block
+  const uint32_t nblocks = st[2 * kSlices];
+  for (int s = 0; s < kSlices; ++s) {
+    const uint32_t o1 = st[2 * s], o2 = st[2 * s + 1], o3 = st[2 * s + 2];
+    // ones section: word i of a block holds steps 2 (i & 3), 2 (i & 3) + 1 of lane i >> 2
+    for (uint32_t i = threadIdx.x; i < (o2 - o1) * 128; i += blockDim.x) {
+      const uint32_t blk = i >> 7, wi = i & 127, lane = wi >> 2, k = blk * 8 + (wi & 3) * 2;
+      const uint32_t lo = 16384u + ((lane + k) & 15u), hi = 16384u + ((lane + k + 1) & 15u);
+      base[(size_t)o1 * 128 + i] = lo | (hi << 16);
+    }
+    // general section: word i of a block holds step i & 3 of lane i >> 2
+    for (uint32_t i = threadIdx.x; i < (o3 - o2) * 128; i += blockDim.x) {
+      const uint32_t blk = i >> 7, wi = i & 127, lane = wi >> 2, k = blk * 4 + (wi & 3);
+      base[(size_t)o2 * 128 + i] = pack_cell((int)((lane + k) & 15u), 0);
+    }
+  }
+  (void)nblocks;
 }
 
 // A warp's position in the tile cells of one row: the row's chunks that hold tile cells, in
@@ -215,17 +276,22 @@ struct RowCursor {
   }
 };
 
-// per-residue slot tables of one (row, tile) segment, lane r < 16 holds residue r
+// per-residue slot tables of one (row, tile) segment: lane r holds residue r of the ones
+// section, lane 16 + r residue r of the general section
 struct SlotTables {
   int served, freebase, fre;
 };
-// slot of the t-th cell (or padding) that found no step of its own residue
-__device__ __forceinline__ void leftover_slot(const SlotTables &tb_, int t, bool want, int &r2, int &m2) {
+// slot of the t-th cell of a section (base lane 0 or 16) that found no step of its own residue
+__device__ __forceinline__ void leftover_slot(const SlotTables &tb_, int base, int t, bool want, int &r2,
+                                              int &m2) {
+#if TB_FILL_HIST
+  if (!__any_sync(0xffffffffu, want)) return;          // every cell of the block found its own bank
+#endif
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
-    const int fb = __shfl_sync(0xffffffffu, tb_.freebase, q);
-    const int fr = __shfl_sync(0xffffffffu, tb_.fre, q);
-    const int sv = __shfl_sync(0xffffffffu, tb_.served, q);
+    const int fb = __shfl_sync(0xffffffffu, tb_.freebase, base + q);
+    const int fr = __shfl_sync(0xffffffffu, tb_.fre, base + q);
+    const int sv = __shfl_sync(0xffffffffu, tb_.served, base + q);
     if (want && t >= fb && t < fb + fr) { r2 = q; m2 = sv + t - fb; }
   }
 }
@@ -241,6 +307,10 @@ k_tile_fill(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
   const unsigned lt = (1u << lane) - 1u;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+#if TB_FILL_HIST
+  __shared__ int s_hist[8][32];                        // per warp: cells per key / cells placed per key
+  int *hist = s_hist[threadIdx.x >> 5];
+#endif
   for (int64_t r = warp; r < nrows; r += nwarp) {
     const int64_t rb = r / kTileRows;
     RowCursor cur;
@@ -251,34 +321,55 @@ k_tile_fill(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
     while (cur.c < cur.cend) {
       const int32_t w = col[cur.k] / kTileCols, wlo = w * kTileCols, whi = wlo + kTileCols;
       const int64_t tile = rb * nwin + w;
-      const int p = inv[r * nwin + w], l = p & 31;
-      const uint32_t s0 = slice[tile * kSliceTab + (p >> 5)];
-      const int L = (int)((slice[tile * kSliceTab + (p >> 5) + 1] - s0) >> 5);
-      uint32_t *out = cells + t_off[tile] + s0 + l * 4;
+      const int p = inv[r * nwin + w], l = p & 31, sl = p >> 5;
+      const uint32_t *st = slice + tile * kSliceTab + 2 * sl;
+      const uint32_t o1 = st[0], o2 = st[1], o3 = st[2];
+      const int L1 = (int)(o2 - o1) * 8, L2 = (int)(o3 - o2) * 4;
+      uint32_t *tbase = cells + t_off[tile] * 128;
+      uint16_t *out1 = reinterpret_cast<uint16_t *>(tbase + (size_t)o1 * 128) + l * 8;
+      uint32_t *out2 = tbase + (size_t)o2 * 128 + l * 4;
       const RowCursor start = cur;
-      // sweep 1: cells per residue (lane r < 16 counts residue r)
+      // sweep 1: cells per (section, residue): lane q counts key q = 16 * general + residue
       int b = 0;
+#if TB_FILL_HIST
+      hist[lane] = 0;
+      __syncwarp();
+#endif
       for (;;) {
         const int64_t idx = cur.k + lane;
         const int32_t cc = idx < cur.kend ? col[idx] : 0x7fffffff;
         const bool inwin = cc < whi;
-        const bool act = inwin && (!cur.filter || tile_overflow(val[idx]));
-        const int res = cc & 15;
+        const int32_t vv = inwin ? val[idx] : 0;
+        const bool act = inwin && (!cur.filter || tile_overflow(vv));
+        const int key = (cc & 15) + ((cur.filter || vv != 1) ? 16 : 0);
         const int na = __popc(__ballot_sync(0xffffffffu, inwin));
+#if TB_FILL_HIST
+        // lanes with the same key form a group; its first lane adds the group to the histogram
+        const unsigned grp = __match_any_sync(0xffffffffu, act ? key : 32 + lane);
+        if (act && (grp & lt) == 0u) hist[key] += __popc(grp);
+        __syncwarp();
+#else
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const unsigned m = __ballot_sync(0xffffffffu, act && res == q);
+        for (int q = 0; q < 32; ++q) {
+          const unsigned m = __ballot_sync(0xffffffffu, act && key == q);
           if (lane == q) b += __popc(m);
         }
+#endif
         if (!cur.advance(na, col, whi)) break;
       }
+#if TB_FILL_HIST
+      b = hist[lane];
+      __syncwarp();
+      hist[lane] = 0;                        // reused as the cells placed per key in sweep 2
+      __syncwarp();
+#endif
       // steps of residue q for this lane: k = ((q - l) & 15) + 16 m, m < req
-      const int d = (lane - l) & 15;
-      const int req = (lane < 16 && d < L) ? (L - 1 - d) / 16 + 1 : 0;
-      const int bb = lane < 16 ? b : 0;
+      const int L = lane < 16 ? L1 : L2;
+      const int d = ((lane & 15) - l) & 15;
+      const int req = d < L ? (L - 1 - d) / 16 + 1 : 0;
       SlotTables tabs;
-      tabs.served = min(bb, req);
-      const int left = bb - tabs.served;
+      tabs.served = min(b, req);
+      const int left = b - tabs.served;
       tabs.fre = req - tabs.served;
       int li = left, fi = tabs.fre;
 #pragma unroll
@@ -286,57 +377,60 @@ k_tile_fill(const int32_t *__restrict__ col, const int32_t *__restrict__ val,
         const int a = __shfl_up_sync(0xffffffffu, li, o), f = __shfl_up_sync(0xffffffffu, fi, o);
         if (lane >= o) { li += a; fi += f; }
       }
+      // the scans run over both sections: take the first section's totals off the second
+      const int l15 = __shfl_sync(0xffffffffu, li, 15), f15 = __shfl_sync(0xffffffffu, fi, 15);
+      if (lane >= 16) { li -= l15; fi -= f15; }
       const int leftbase = li - left;
       tabs.freebase = fi - tabs.fre;
-      const int total_left = __shfl_sync(0xffffffffu, li, 31);
-      const int total_free = __shfl_sync(0xffffffffu, fi, 31);
       // sweep 2: place the cells
       cur = start;
+#if !TB_FILL_HIST
       int run = 0;
+#endif
       for (;;) {
         const int64_t idx = cur.k + lane;
         const int32_t cc = idx < cur.kend ? col[idx] : 0x7fffffff;
         const bool inwin = cc < whi;
         const int32_t vv = inwin ? val[idx] : 0;
         const bool act = inwin && (!cur.filter || tile_overflow(vv));
-        const int res = cc & 15;
+        const int general = (cur.filter || vv != 1) ? 16 : 0;
+        const int key = (cc & 15) + general;
         const int na = __popc(__ballot_sync(0xffffffffu, inwin));
-        const unsigned same = __match_any_sync(0xffffffffu, act ? res : 16 + lane);
-        const int m = __shfl_sync(0xffffffffu, run, res) + __popc(same & lt);
-        const int sv = __shfl_sync(0xffffffffu, tabs.served, res);
-        const int lb = __shfl_sync(0xffffffffu, leftbase, res);
-        int r2 = res, m2 = m;
-        leftover_slot(tabs, lb + m - sv, act && m >= sv, r2, m2);
+        const unsigned same = __match_any_sync(0xffffffffu, act ? key : 32 + lane);
+#if TB_FILL_HIST
+        const int m = hist[key] + __popc(same & lt);
+        __syncwarp();                        // every lane has read the counts of this block
+        if (act && (same & lt) == 0u) hist[key] += __popc(same);
+        __syncwarp();
+#else
+        const int m = __shfl_sync(0xffffffffu, run, key) + __popc(same & lt);
+#endif
+        const int sv = __shfl_sync(0xffffffffu, tabs.served, key);
+        const int lb = __shfl_sync(0xffffffffu, leftbase, key);
+        int r2 = key & 15, m2 = m;
+        leftover_slot(tabs, general, lb + m - sv, act && m >= sv, r2, m2);
         if (act) {
           const int ks = ((r2 - l) & 15) + 16 * m2;
-          out[(ks >> 2) * 128 + (ks & 3)] = pack_cell(cc - wlo, vv);
+          if (general) out2[(ks >> 2) * 128 + (ks & 3)] = pack_cell(cc - wlo, vv);
+          else out1[(ks >> 3) * 256 + (ks & 7)] = (uint16_t)(cc - wlo);
         }
+#if !TB_FILL_HIST
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const unsigned mq = __ballot_sync(0xffffffffu, act && res == q);
+        for (int q = 0; q < 32; ++q) {
+          const unsigned mq = __ballot_sync(0xffffffffu, act && key == q);
           if (lane == q) run += __popc(mq);
         }
+#endif
         if (!cur.advance(na, col, whi)) break;
-      }
-      // padding: the remaining free steps read x at their preferred residue, count 0
-      for (int t0 = total_left; t0 < total_free; t0 += 32) {
-        const int t = t0 + lane;
-        int r2 = 0, m2 = 0;
-        leftover_slot(tabs, t, t < total_free, r2, m2);
-        if (t < total_free) {
-          const int ks = ((r2 - l) & 15) + 16 * m2;
-          out[(ks >> 2) * 128 + (ks & 3)] = pack_cell(r2, 0);
-        }
       }
     }
   }
 }
 
-// steps [kb, kb + len) of a slice that belong to part `part` of `parts` (multiples of 4)
-__device__ __forceinline__ int part_range(uint32_t s0, uint32_t s1, int part, int parts, int &kb) {
-  const int64_t quads = (s1 - s0) >> 7;                    // steps / 4
-  kb = (int)(quads * part / parts) * 4;
-  return (int)(quads * (part + 1) / parts) * 4 - kb;
+// blocks [kb, kb + len) of a section that belong to part `part` of `parts`
+__device__ __forceinline__ int part_range(uint32_t nblocks, int part, int parts, int &kb) {
+  kb = (int)((int64_t)nblocks * part / parts);
+  return (int)((int64_t)nblocks * (part + 1) / parts) - kb;
 }
 
 // one thread per (unit, warp): count / write the copy descriptors of the warp's cell stream
@@ -355,33 +449,35 @@ k_tile_desc(const int4 *__restrict__ unit, const int32_t *__restrict__ list,
   for (int j = un.y; j < un.z; ++j) {
     const int64_t tile = list[j];
     const uint32_t *st = slice + tile * kSliceTab;
-    int kb[kWarpSlices], len[kWarpSlices], total = 0, last = 0;
+    // the warp's sections of this tile, in stream order: ones then general of each of its slices
+    int kb[2 * kWarpSlices], len[2 * kWarpSlices], last = -1;
 #pragma unroll
-    for (int h = 0; h < kWarpSlices; ++h) {
-      const int sl = warp_slice(w, h);
-      len[h] = part_range(st[sl], st[sl + 1], part, parts, kb[h]);
-      total += len[h];
+    for (int h = 0; h < 2 * kWarpSlices; ++h) {
+      const int sl = warp_slice(w, h >> 1);
+      len[h] = part_range(st[2 * sl + (h & 1) + 1] - st[2 * sl + (h & 1)], part, parts, kb[h]);
       if (len[h]) last = h;
     }
-    if (total == 0) {
+    if (last < 0) {
       if (FILL) o[n_out] = make_uint2(0u, (uint32_t)(tile * kSlices + w) | kDescEndTile);
       ++n_out;
       continue;
     }
 #pragma unroll
-    for (int h = 0; h < kWarpSlices; ++h) {
-      const int sl = warp_slice(w, h);
-      const int pieces = (len[h] + 4 * kPieceQuads - 1) / (4 * kPieceQuads);
+    for (int h = 0; h < 2 * kWarpSlices; ++h) {
+      const int sl = warp_slice(w, h >> 1);
+      const int pieces = (len[h] + kPieceBlocks - 1) / kPieceBlocks;
       if (FILL) {
-        const int64_t first = (t_off[tile] + st[sl]) / 32 + kb[h];
+        const int64_t first = t_off[tile] + st[2 * sl + (h & 1)] + kb[h];
+        // the slice ends with this section unless its general section (h odd) still has blocks
+        const bool ends_slice = (h & 1) || len[h + 1] == 0;
         for (int i = 0; i < pieces; ++i) {
-          const int steps = min(4 * kPieceQuads, len[h] - 4 * kPieceQuads * i);
-          uint32_t y = (uint32_t)(tile * kSlices + sl) | ((uint32_t)(steps / 4) << 26);
+          const int nb = min(kPieceBlocks, len[h] - kPieceBlocks * i);
+          uint32_t y = (uint32_t)(tile * kSlices + sl) | ((h & 1) ? kDescGeneral : 0u) | ((uint32_t)nb << 26);
           if (i == pieces - 1) {
-            y |= kDescEndSlice;
+            if (ends_slice) y |= kDescEndSlice;
             if (h == last) y |= kDescEndTile;
           }
-          o[n_out + i] = make_uint2((uint32_t)(first + 4 * kPieceQuads * i), y);
+          o[n_out + i] = make_uint2((uint32_t)(first + kPieceBlocks * i), y);
         }
       }
       n_out += pieces;
@@ -394,20 +490,62 @@ k_tile_desc(const int4 *__restrict__ unit, const int32_t *__restrict__ list,
 __device__ __forceinline__ double cell_term(uint32_t c, const uint8_t *xw) {
   return u2d(c & 0xffffu) * *reinterpret_cast<const double *>(xw + (c >> 15));
 }
+__device__ __forceinline__ double x_at(uint32_t byte_off, const uint8_t *xw) {
+  return *reinterpret_cast<const double *>(xw + byte_off);
+}
 
-template <int QUADS>
-__device__ __forceinline__ void consume(const uint8_t *stage, int lane, const uint8_t *xw, double &a0,
-                                        double &a1) {
+// general section: 4 cells per lane and block
+template <int NB>
+__device__ __forceinline__ void consume_general(const uint8_t *stage, int lane, const uint8_t *xw, double &a0,
+                                                double &a1) {
   const uint4 *rp = reinterpret_cast<const uint4 *>(stage) + lane;
-  uint4 q[QUADS];
+  uint4 q[NB];
 #pragma unroll
-  for (int g = 0; g < QUADS; ++g) q[g] = rp[g * 32];
+  for (int g = 0; g < NB; ++g) q[g] = rp[g * 32];
 #pragma unroll
-  for (int g = 0; g < QUADS; ++g) {
+  for (int g = 0; g < NB; ++g) {
     a0 += cell_term(q[g].x, xw);
     a1 += cell_term(q[g].y, xw);
     a0 += cell_term(q[g].z, xw);
     a1 += cell_term(q[g].w, xw);
+  }
+}
+
+// ones section: 8 cells per lane and block, the term is x itself
+template <int NB>
+__device__ __forceinline__ void consume_ones(const uint8_t *stage, int lane, const uint8_t *xw, double &a0,
+                                             double &a1) {
+  const uint4 *rp = reinterpret_cast<const uint4 *>(stage) + lane;
+  uint4 q[NB];
+#pragma unroll
+  for (int g = 0; g < NB; ++g) q[g] = rp[g * 32];
+#pragma unroll
+  for (int g = 0; g < NB; ++g) {
+    const uint32_t wv[4] = {q[g].x, q[g].y, q[g].z, q[g].w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      a0 += x_at((wv[i] << 3) & 0x7fff8u, xw);
+      a1 += x_at((wv[i] >> 13) & 0x7fff8u, xw);
+    }
+  }
+}
+
+template <bool GENERAL>
+__device__ __forceinline__ void consume_piece(uint32_t nb, const uint8_t *rs, int lane, const uint8_t *xw,
+                                              double &a0, double &a1) {
+  if (nb == kPieceBlocks) {
+    if (GENERAL) consume_general<kPieceBlocks>(rs, lane, xw, a0, a1);
+    else consume_ones<kPieceBlocks>(rs, lane, xw, a0, a1);
+  } else {                                             // a short last piece: pairs, then one
+    uint32_t g = 0;
+    for (; g + 2 <= nb; g += 2) {
+      if (GENERAL) consume_general<2>(rs + g * 512, lane, xw, a0, a1);
+      else consume_ones<2>(rs + g * 512, lane, xw, a0, a1);
+    }
+    if (g < nb) {
+      if (GENERAL) consume_general<1>(rs + g * 512, lane, xw, a0, a1);
+      else consume_ones<1>(rs + g * 512, lane, xw, a0, a1);
+    }
   }
 }
 
@@ -422,16 +560,17 @@ k_rowsum_tiles(const uint32_t *__restrict__ cells, const uint2 *__restrict__ des
   if (blockIdx.x == 0 && threadIdx.x == 0) counter[cur ^ 1] = 0u;
   if (state && state->stopped) return;
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t *xw = smem;                                                   // [kTileCols] doubles
-  double *acc = reinterpret_cast<double *>(smem + kWinBytes);          // [kTileRows]
+  uint8_t *xw = smem;                                   // [kTileCols] doubles + 16 zeros
+  double *acc = reinterpret_cast<double *>(smem + kAccOff);            // [kTileRows]
   const int t = threadIdx.x, lane = t & 31, wic = t >> 5;
-  uint8_t *ring = smem + kWinBytes + kTileRows * 8 + wic * (kRing * kPieceBytes);
+  uint8_t *ring = smem + kRingOff + wic * (kRing * kPieceBytes);
   const uint32_t ring_u32 = smem_u32(ring);
-  uint8_t *tail = smem + kWinBytes + kTileRows * 8 + kTileWarps * kRing * kPieceBytes;
+  uint8_t *tail = smem + kTailOff;
   const uint32_t bars = smem_u32(tail);
   const uint32_t wbar = bars + kTileWarps * kRing * 8;                 // window barrier
   const uint32_t rbar = bars + wic * kRing * 8;                        // this warp's ring barriers
   volatile unsigned int *s_next = reinterpret_cast<volatile unsigned int *>(tail + (kTileWarps * kRing + 1) * 8);
+  if (t < kZeroTail / 8) reinterpret_cast<double *>(smem + kWinBytes)[t] = 0.0;
   if (t == 0) mbar_init(wbar, 1);
   if (lane == 0) {
 #pragma unroll
@@ -454,10 +593,10 @@ k_rowsum_tiles(const uint32_t *__restrict__ cells, const uint2 *__restrict__ des
     const uint2 *dp = desc + dbeg;
     // start the copy of piece `e` into `stage`; fetch the rows of its slice if it ends one
     auto issue = [&](int stage, const uint2 &e, uint32_t &row) {
-      const uint32_t quads = (e.y >> 26) & 15u;
-      if (quads && lane == 0) {
-        mbar_expect_tx(rbar + 8 * stage, quads * 512u);
-        bulk_g2s(ring_u32 + stage * kPieceBytes, cells + (size_t)e.x * 32, quads * 512u, rbar + 8 * stage);
+      const uint32_t nb = (e.y >> 26) & 15u;
+      if (nb && lane == 0) {
+        mbar_expect_tx(rbar + 8 * stage, nb * 512u);
+        bulk_g2s(ring_u32 + stage * kPieceBytes, cells + (size_t)e.x * 128, nb * 512u, rbar + 8 * stage);
       }
       if (e.y & kDescEndSlice) row = perm[(size_t)(e.y & kDescGroupMask) * 32 + lane];
     };
@@ -485,20 +624,16 @@ k_rowsum_tiles(const uint32_t *__restrict__ cells, const uint2 *__restrict__ des
         uint2 &e = ST ? e1 : e0;
         uint32_t &erow = ST ? row1 : row0;
         const uint32_t meta = e.y, row = erow;
-        const uint32_t quads = (meta >> 26) & 15u;
-        if (quads) {
+        const uint32_t nb = (meta >> 26) & 15u;
+        if (nb) {
           mbar_wait(rbar + 8 * ST, (rparity >> ST) & 1u);
           rparity ^= 1u << ST;
           const uint8_t *rs = ring + ST * kPieceBytes;
-          if (quads == kPieceQuads) consume<kPieceQuads>(rs, lane, xw, a0, a1);
-          else {                                           // a short last piece: pairs, then one
-            uint32_t g = 0;
-            for (; g + 2 <= quads; g += 2) consume<2>(rs + g * 512, lane, xw, a0, a1);
-            if (g < quads) consume<1>(rs + g * 512, lane, xw, a0, a1);
-          }
+          if (meta & kDescGeneral) consume_piece<true>(nb, rs, lane, xw, a0, a1);
+          else consume_piece<false>(nb, rs, lane, xw, a0, a1);
         }
         __syncwarp();                        // every lane has read this stage
-        if (meta & kDescEndSlice) {          // distinct rows per thread of a tile: no conflict
+        if (meta & kDescEndSlice) {          // a row belongs to one slice: no other warp adds to it
           acc[row] += a0 + a1;
           a0 = a1 = 0.0;
         }
@@ -543,19 +678,19 @@ void build_tiles(tb_store *s) {
   const int64_t nrb = (s->nrows + kTileRows - 1) / kTileRows;
   const int64_t nwin = (s->nbins + kTileCols - 1) / kTileCols;
   const int64_t ntiles = nrb * nwin;
-  TB_REQUIRE(ntiles < (1LL << 20), "too many sparse tiles");
+  TB_REQUIRE(ntiles < (1LL << 19), "too many sparse tiles");
   s->t_nrb = nrb;
   s->t_nwin = nwin;
   DevBuf<int32_t> cnt;
   DevBuf<uint16_t> inv;
   DevBuf<int64_t> tile_size;
   DevBuf<int32_t> tile_crit;
-  DevBuf<unsigned long long> totals;
+  DevBuf<unsigned long long> totals;       // [0] real cells, [1] ones blocks, [2] general blocks
   cnt.alloc(nrb * kTileRows * nwin);
   inv.alloc(nrb * kTileRows * nwin);
   tile_size.alloc(ntiles + 1);
   tile_crit.alloc(ntiles + 1);
-  totals.alloc(1);
+  totals.alloc(4);
   TB_CUDA(cudaMemsetAsync(cnt.p, 0, cnt.bytes(), st));
   TB_CUDA(cudaMemsetAsync(tile_size.p, 0, tile_size.bytes(), st));
   TB_CUDA(cudaMemsetAsync(totals.p, 0, totals.bytes(), st));
@@ -575,32 +710,34 @@ void build_tiles(tb_store *s) {
     TB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, tile_size.p, s->t_off.p, ntiles + 1, st));
     TB_CUDA(cudaStreamSynchronize(st));
   }
-  std::vector<int64_t> h_size(ntiles);
+  std::vector<int64_t> h_size(ntiles);     // blocks per tile
   std::vector<int32_t> h_crit(ntiles);
-  unsigned long long h_total = 0;
+  unsigned long long h_totals[4] = {0, 0, 0, 0};
+  int64_t nblocks = 0;
   TB_CUDA(cudaMemcpy(h_size.data(), tile_size.p, ntiles * sizeof(int64_t), cudaMemcpyDeviceToHost));
   TB_CUDA(cudaMemcpy(h_crit.data(), tile_crit.p, ntiles * sizeof(int32_t), cudaMemcpyDeviceToHost));
-  TB_CUDA(cudaMemcpy(&h_total, totals.p, sizeof(h_total), cudaMemcpyDeviceToHost));
-  TB_CUDA(cudaMemcpy(&s->t_npadded, s->t_off.p + ntiles, sizeof(int64_t), cudaMemcpyDeviceToHost));
-  s->t_ncells = (int64_t)h_total;
+  TB_CUDA(cudaMemcpy(h_totals, totals.p, sizeof(h_totals), cudaMemcpyDeviceToHost));
+  TB_CUDA(cudaMemcpy(&nblocks, s->t_off.p + ntiles, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  s->t_ncells = (int64_t)h_totals[0];
+  s->t_npadded = nblocks * 128;            // stored stream in 4-byte units (bytes / 4)
   cnt.release();
-  s->t_cells.alloc(s->t_npadded ? s->t_npadded : 1);
-  TB_CUDA(cudaMemsetAsync(s->t_cells.p, 0, s->t_cells.bytes(), st));       // padding = (col 0, count 0)
+  s->t_cells.alloc(nblocks ? nblocks * 128 : 1);
+  k_tile_init<<<(unsigned)ntiles, 256, 0, st>>>(s->t_slice.p, s->t_off.p, s->t_cells.p);
   k_tile_fill<<<grid_1d(s->nrows * 32, 256, s->sm_count, 8), 256, 0, st>>>(
       s->col.p, s->val.p, s->chunk_beg.p, s->row_chunk.p, s->enc_desc.p, s->enc_tovf.p, s->nrows, nwin, inv.p,
       s->t_slice.p, s->t_off.p, s->t_cells.p);
   // Work units: each row block's non-empty tiles, cut into runs of about equal cost so that there
   // are ~16 units per SM whatever the number of row blocks (1 GPU or a 1/8 shard).  A tile heavier
   // than that (the ones on the diagonal) is split: `parts` units each take a share of every
-  // slice of the tile.  unit = (row block, list begin, list end, part<<8|parts).
-  // The cost of a tile is its cell count, or what its busiest warp streams if the rows are so
+  // section of the tile.  unit = (row block, list begin, list end, part<<8|parts).
+  // The cost of a tile is its blocks, or what its busiest warp streams if the rows are so
   // uneven that this warp, not the SM, sets the time: a lone warp moves about 1/(0.7 * 32) of
   // what the SM does (two pieces in flight).
   std::vector<double> h_eff(ntiles);
   int64_t nonempty = 0;
   double total_cost = 0.0;
   for (int64_t q = 0; q < ntiles; ++q) {
-    h_eff[q] = std::max((double)h_size[q], 0.7 * 1024.0 * (double)h_crit[q]);
+    h_eff[q] = kBlockCost * std::max((double)h_size[q], 0.7 * kTileWarps * 2.0 * (double)h_crit[q]);
     if (h_size[q]) { ++nonempty; total_cost += h_eff[q] + (double)kTileFixedCost; }
   }
   // ... but no smaller than a few times the fixed cost of a unit, unless that would leave SMs
@@ -706,4 +843,3 @@ void launch_rowsum_tiles(tb_store *s, const double *x, const IceState *state) {
 }
 
 }  // namespace tb
-#endif  // !TB_TILES16

@@ -24,11 +24,18 @@ def iterative(hic_data, bads=None, iterations=0, max_dev=0.00001,
     if verbose:
         print('iterative correction')
         print('  - copying matrix')
-        print('  - computing biases')
     size = len(hic_data)
-    bias, trace = hic_data.store.ice(bad_mask(size, bads), iterations=iterations,
-                                     max_dev=max_dev)                 # K1 + K2 (device)
+    try:
+        bias, trace = hic_data.store.ice(bad_mask(size, bads), iterations=iterations,
+                                         max_dev=max_dev)             # K1 + K2 (device)
+    except ZeroDivisionError as exc:
+        # "all bad columns" is raised before the third line is printed (normalize_hic.py:203-210),
+        # a zero mean row sum after it (_updateDB, :148)
+        if verbose and 'all bad columns' not in str(exc):
+            print('  - computing biases')
+        raise
     if verbose:
+        print('  - computing biases')
         for it, (smin, mean_s, smax, dev) in enumerate(trace):
             print(TRACE_FORMAT % (smin, mean_s, smax, it, dev))
     hic_data.last_trace = trace

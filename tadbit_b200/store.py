@@ -32,7 +32,7 @@ class ContactStore(object):
     @classmethod
     def from_coo(cls, size, rows, cols, vals, chromosomes=None, row_block=None, device=0):
         """Upper-triangle cells (row <= col, unique) as host arrays."""
-        rows, cols, vals = _capi.as_i32(rows), _capi.as_i32(cols), _capi.as_i32(vals)
+        rows, cols, vals = _capi.as_i32(rows, "rows"), _capi.as_i32(cols, "cols"), _capi.as_i32(vals, "vals")
         if not (rows.shape == cols.shape == vals.shape and rows.ndim == 1):
             raise ValueError("rows, cols, vals must be 1-D arrays of equal length")
         n_chrom, offs = _offsets(size, chromosomes)
@@ -189,6 +189,16 @@ class ContactStore(object):
         check(lib().tb_ice_last_timing(self._h, C.byref(a), C.byref(b), C.byref(n), C.byref(t)))
         return dict(loop_ms=a.value, rowsum_ms=b.value, rowsum_launches=n.value,
                     total_launches=t.value)
+
+    def timing(self):
+        """Device times (ms) of the last calls: ICE loop, its K1 launches, the exchange + statistics
+        + update between them, the last one-pass reduction (masked column sums / distance sums)."""
+        out = np.zeros(8, dtype=np.float64)
+        check(lib().tb_last_timing(self._h, ptr(out, C.c_double)))
+        return dict(loop_ms=out[0], rowsum_ms=out[1], exchange_ms=out[2], kernel_ms=out[3],
+                    rowsum_launches=int(out[4]), total_launches=int(out[5]),
+                    exchange={2: "peer-mapped", 1: "local/nccl", 0: "not set up"}[int(out[6])],
+                    csr_resident=bool(out[7]))
 
     def norm_sum(self, bias=None, bad=None):
         m, mp = self._mask(bad)
