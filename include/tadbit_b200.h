@@ -54,6 +54,9 @@ typedef enum {
 } tb_status;
 
 enum { TB_MEM_HOST = 0, TB_MEM_DEVICE = 1 };
+/* which cells a CSR-form argument holds (tb_store_create_csr, tb_store_export_csr) */
+enum { TB_CELLS_UPPER = 0,      /* stored cells with col >= row of the rows concerned             */
+       TB_CELLS_FULL_ROWS = 1   /* every stored cell of the rows concerned (both triangles)       */ };
 
 /* ---- library ------------------------------------------------------------------- */
 int tb_version(void);
@@ -90,6 +93,18 @@ int tb_store_create_coo(int64_t nbins, int64_t nnz, const int32_t *row, const in
  * so the matrix does not depend on how rows are sharded.  Not in the reference (its
  * test/simulate_genomic_matrix.py is unrelated); used by bench.py and the scale tests.
  */
+/* The same matrix in CSR form (what HiC_data.get_hic_data_as_csr holds, _pytadbit/hic_data.py:166-181).
+ * form = TB_CELLS_UPPER: upper-triangle rows of the WHOLE matrix, ptr[nbins + 1]; 8 bytes per cell
+ *   cross PCIe instead of the 12 of the coordinate form.  row_begin/row_end must be 0/nbins.
+ * form = TB_CELLS_FULL_ROWS: every stored cell of the rows [row_begin, row_end) of the full
+ *   symmetric matrix, ptr[row_end - row_begin + 1] (starting at 0), columns strictly ascending in
+ *   each row: the pre-partitioned input of a row-sharded matrix (each GPU receives only its rows,
+ *   nothing has to be mirrored or sorted).
+ * ptr is int64; col/val as in tb_store_create_coo; mem says where all three arrays live. */
+int tb_store_create_csr(int64_t nbins, int form, const int64_t *ptr, const int32_t *col,
+                        const int32_t *val, int mem, int32_t n_chrom, const int64_t *chrom_offsets,
+                        int64_t row_begin, int64_t row_end, int device, tb_store **out);
+
 typedef struct {
   uint64_t seed;
   double cis_scale;      /* a      */
@@ -117,9 +132,15 @@ int tb_store_destroy(tb_store *s);
 int tb_store_info(const tb_store *s, int64_t *nbins, int64_t *row_begin, int64_t *row_end,
                   int64_t *nnz_upper_owned, int64_t *nnz_full_owned, int64_t *device_bytes);
 
-/* Options of a store.  "rowsum" = "compact" (default) or "csr": which copy of the matrix the
- * ICE passes walk -- the compact stream, or the plain CSR (two independent K1 implementations;
- * the parity tests compare them at full size). */
+/* Options of a store.
+ *   "rowsum" = "compact" (default) or "csr": which copy of the matrix the ICE passes walk -- the
+ *     compact stream, or the plain CSR (two independent K1 implementations; the parity tests
+ *     compare them).  A store of positive counts releases its CSR after the build unless the
+ *     environment has TB_KEEP_CSR=1 at creation; "csr" then fails with TB_ERR_STATE.
+ *   "exchange" = "fused" (default) or "nccl": per ICE pass either ONE kernel that stores the owned
+ *     row sums into every GPU's buffer (peer-mapped memory), waits on flags and does the
+ *     statistics and the bias update, or combine -> ncclAllReduce -> statistics -> update as
+ *     separate launches.  All ranks of a group must choose the same. */
 int tb_store_set_option(tb_store *s, const char *name, const char *value);
 
 /* Layout of the compact row-sum stream (tadbit_b200/csrc/encode.cu, tiles.cu):
@@ -134,6 +155,10 @@ int tb_store_layout(const tb_store *s, int64_t out[16]);
  * Call with row == NULL to get the count in *nnz first.  Buffers are HOST. */
 int tb_store_export_upper(const tb_store *s, int64_t *nnz, int32_t *h_row, int32_t *h_col,
                           int32_t *h_val);
+/* The owned rows in CSR form (see tb_store_create_csr): h_ptr[row_end - row_begin + 1], h_col and
+ * h_val [*nnz].  Call with null arrays first to learn *nnz. */
+int tb_store_export_csr(const tb_store *s, int form, int64_t *nnz, int64_t *h_ptr, int32_t *h_col,
+                        int32_t *h_val);
 
 /* ---- multi-GPU (one process per GPU) ------------------------------------------- */
 /* 128-byte NCCL unique id made on rank 0 and passed to every rank by the host

@@ -284,6 +284,16 @@ def main():
              ice_configs=[(0, 0.1, False, 1), (10, 1e-5, False, 1)])
     index.append("all_bad_80")
 
+    # every stored cell is an explicit zero: rows are "present" (copy_matrix keeps the cells) but the
+    # mean row sum is 0 -> ZeroDivisionError('float division by zero') in _updateDB
+    n = 30
+    i, j = np.triu_indices(n, 0)
+    keep = (j - i) < 4
+    hic = build_reference(ns, n, i[keep], j[keep], np.zeros(int(keep.sum()), dtype=np.int64))
+    run_case(ns, "all_zero_30", hic, filter_kw={"perc_zero": 99, "by_mean": False},
+             ice_configs=[(0, 0.1, False, 1), (5, 1e-5, False, None)])
+    index.append("all_zero_30")
+
     reference_known_answers(ns)
 
     with open(os.path.join(OUT, "INDEX.json"), "w") as fh:

@@ -26,7 +26,8 @@ int ice_port_threads(void) {
 #endif
 }
 
-/* returns the number of passes executed, or -1 if no row is present (:207-208).
+/* returns the number of passes executed, -1 if no row is present (:207-208), -2 if the mean row
+ * sum is 0 (ZeroDivisionError in _updateDB, :148).
  * trace: (iterations+1) x 4 doubles = Smin, meanS, Smax, dev per pass (:219-220). */
 int ice_port(int64_t n, const int64_t *indptr, const int32_t *indices, const double *data,
              int iterations, double max_dev, double *bias, double *trace, int threads) {
@@ -61,6 +62,7 @@ int ice_port(int64_t n, const int64_t *indptr, const int32_t *indices, const dou
       if (a > smax) smax = a;
     }
     mean_s = sum / (double)npresent;
+    if (mean_s == 0.0) { passes = -2; goto done; } /* float(S) / meanS raises in _updateDB (:148) */
     for (int64_t i = 0; i < n; ++i)                /* _updateDB */
       if (present[i]) {
         b[i] *= s[i] / mean_s;

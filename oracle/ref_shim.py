@@ -2,11 +2,12 @@
 
 Loads ``/root/reference/_pytadbit`` as package ``pytadbit`` without running its
 ``__init__`` (which needs compiled extensions and missing third-party modules).
-Only usable in the build container, where ``/root/reference`` exists; nothing in
-``tests/ -m gpu``, ``smoke()`` or ``bench.py`` imports this module.  It is used by
-``oracle/gen_golden.py`` to produce the committed fixtures under ``tests/golden/``
-and by the optional ``tests/test_oracle_vs_reference.py`` (skipped when the
-reference tree is absent).
+It is used by ``oracle/gen_golden.py`` to produce the committed fixtures under
+``tests/golden/``, by the optional ``tests/test_oracle_vs_reference.py`` (skipped when
+the reference tree is absent) and by ``bench.py --impl reference`` to time the
+unmodified reference on a small block.  In the build container the tree is
+``/root/reference``; on the GPU box it is the untouched copy that
+``__graft_entry__.build()`` places under ``baseline/_ref`` (git-ignored).
 
 Recipe follows SURVEY.md Appendix A.
 """
@@ -15,7 +16,19 @@ import sys
 import types
 import warnings
 
-REFERENCE_ROOT = os.environ.get("TADBIT_REFERENCE_ROOT", "/root/reference")
+def _root():
+    """/root/reference in the build container; on the GPU box the unmodified copy of the pure-Python
+    package that __graft_entry__.build() leaves under baseline/_ref (git-ignored, it travels with
+    the snapshot like the built libraries)."""
+    env = os.environ.get("TADBIT_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/_pytadbit"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+REFERENCE_ROOT = _root()
 
 
 def available():

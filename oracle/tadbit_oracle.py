@@ -179,12 +179,25 @@ def _hundred_bins(cols, nbins):
     return edges, counts
 
 
-def mean_filter_cutoff(cols, nbins=100):
+def _hundred_bins_sorted(cols, nbins):
+    """_hundred_bins for ASCENDING ``cols`` without the 100 passes: digitize(x) == b iff
+    edges[b-1] <= x < edges[b] (last bin open-ended), so the counts are differences of
+    searchsorted positions.  Checked equal to _hundred_bins in tests/test_oracle_port.py."""
+    if len(cols) == 0:
+        raise ValueError('min() arg is an empty sequence')     # as min(cols) in _hundred_bins
+    edges = np.linspace(cols[0], cols[-1], nbins)
+    first = np.searchsorted(cols, edges, side='left')
+    return edges, list(np.diff(np.append(first, len(cols))))
+
+
+def mean_filter_cutoff(cols, nbins=100, bins=None):
     """The <=100-point numpy tail of filter_by_mean (hic_filtering.py:43-99).
 
     ``cols``: ascending column sums of the good sub-matrix.  Returns the chosen
     root, or raises ValueError("few") / LookupError("none") for the two failure
-    exits (:164-167 and :153-156)."""
+    exits (:164-167 and :153-156).  ``bins``: histogram builder (_hundred_bins, the literal
+    restatement, unless the full-size path passes _hundred_bins_sorted)."""
+    _hundred_bins = bins or globals()['_hundred_bins']
     percentile = np.percentile(cols, 5)
     edges, counts = _hundred_bins(cols, nbins)
     dropped = 0
@@ -277,6 +290,8 @@ def iterative(m, bads=None, iterations=0, max_dev=0.00001):
     for it in range(iterations + 1):
         s = x * (w0 @ x)                                       # _update_S :136-143
         mean_s = s[present].sum() / npresent
+        if mean_s == 0:                                        # float(S) / meanS in _updateDB :148
+            raise ZeroDivisionError('float division by zero')
         db = s / mean_s                                        # _updateDB :146-151
         b[present] *= db[present]
         if iterations == 0:
@@ -388,6 +403,8 @@ def iterative_fast(m, bads=None, iterations=0, max_dev=0.00001, threads=None):
                           int(iterations), float(max_dev), bias.ctypes.data, trace.ctypes.data,
                           cores)
     dt = time.perf_counter() - t0
+    if passes == -2:
+        raise ZeroDivisionError('float division by zero')
     if passes < 0:
         raise ZeroDivisionError('ERROR: normalization failed, all bad columns')
     ntrace = passes if iterations > 0 else 0
@@ -480,3 +497,166 @@ def expected(m, bads=None, signal_to_noise=0.05, inter_chrom=False):
     sum_d, cnt_d = diagonal_sums(m, bads or {}, size)
     sum_d = [int(s) for s in sum_d] if sum_d.dtype.kind == 'i' else list(sum_d)
     return pool_diagonals(sum_d, cnt_d, size, min_n)
+
+
+# --------------------------------------------------------------------------
+# Full-size matrices: the same restatement over raw upper-triangle int32 arrays,
+# loops in C + OpenMP (oracle/upper_port.c).  No sorting, no int64 copies: BASELINE
+# configs[1..3] (3e8 .. 2e9 stored cells) fit the host this way.  Every function is checked
+# against the numpy restatement above in tests/test_oracle_port.py.
+# --------------------------------------------------------------------------
+class UpperCells(object):
+    """Stored upper-triangle cells (row <= col, each once) as contiguous int32 arrays."""
+
+    def __init__(self, size, rows, cols, vals, chromosomes=None, symmetricized=False):
+        self.size = int(size)
+        self.rows = np.ascontiguousarray(rows, dtype=np.int32)
+        self.cols = np.ascontiguousarray(cols, dtype=np.int32)
+        self.vals = np.ascontiguousarray(vals, dtype=np.int32)
+        self.chromosomes = chromosomes
+        self.symmetricized = symmetricized
+        if chromosomes:
+            pos, total = OrderedDict(), 0
+            for crm in chromosomes:
+                pos[crm] = (total, total + chromosomes[crm])
+                total += chromosomes[crm]
+            self.section_pos = pos
+        else:
+            self.section_pos = OrderedDict([(None, (0, self.size))])
+
+    def _args(self):
+        return (self.rows.size, self.rows.ctypes.data, self.cols.ctypes.data, self.vals.ctypes.data)
+
+
+def _upper_lib():
+    import ctypes as C
+    lib = _load_port()
+    if lib is None or not hasattr(lib, "up_ice"):
+        raise RuntimeError("oracle/_build/libice_port.so is missing or stale: run `make -C oracle`")
+    if not getattr(lib, "_upper_ready", False):
+        vp, i64 = C.c_void_p, C.c_int64
+        lib.up_row_stats.argtypes = [i64, i64, vp, vp, vp, vp, vp, C.c_int]
+        lib.up_masked_col_sums.argtypes = [i64, i64, vp, vp, vp, vp, vp, C.c_int]
+        lib.up_diag_sums.argtypes = [i64, i64, vp, vp, vp, vp, vp, i64, vp, C.c_int]
+        lib.up_norm_sum.argtypes = [i64, vp, vp, vp, vp, vp, C.c_int]
+        lib.up_norm_sum.restype = C.c_double
+        lib.up_ice.argtypes = [i64, i64, vp, vp, vp, vp, C.c_int, C.c_double, vp, vp, C.c_int]
+        for f in (lib.up_row_stats, lib.up_masked_col_sums, lib.up_diag_sums, lib.up_ice):
+            f.restype = C.c_int
+        lib._upper_ready = True
+    return lib
+
+
+def _bad_u8(size, bads):
+    return np.ascontiguousarray(_bad_mask(size, bads), dtype=np.uint8)
+
+
+def fast_row_stats(m, threads=0):
+    nnz = np.zeros(m.size, dtype=np.int64)
+    rsum = np.zeros(m.size, dtype=np.int64)
+    if _upper_lib().up_row_stats(m.size, *m._args(), nnz.ctypes.data, rsum.ctypes.data, threads):
+        raise MemoryError("up_row_stats")
+    return nnz, rsum
+
+
+def fast_masked_col_sums(m, bad_u8, threads=0):
+    out = np.zeros(m.size, dtype=np.int64)
+    if _upper_lib().up_masked_col_sums(m.size, *m._args(), bad_u8.ctypes.data, out.ctypes.data, threads):
+        raise MemoryError("up_masked_col_sums")
+    return out
+
+
+def fast_filter_columns(m, perc_zero=99, by_mean=True, min_count=None, silent=True):
+    """hic_data.py:318-348 = filter_by_zero_count (hic_filtering.py:173-222) then filter_by_mean
+    (:25-170); the integer sums come from C, the <=100-point tail is mean_filter_cutoff above."""
+    size = m.size
+    nnz, rsum = fast_row_stats(m)
+    if min_count is None:
+        flagged = (size - nnz) > int(size * float(perc_zero) / 100)
+    else:
+        if m.symmetricized:
+            min_count *= 2
+        flagged = rsum < min_count
+    bads = dict((int(i), True) for i in np.nonzero(flagged)[0])
+    if not by_mean:
+        return bads
+    bad = _bad_u8(size, bads)
+    cols = np.sort(fast_masked_col_sums(m, bad)[bad == 0])
+    try:
+        try:
+            root = mean_filter_cutoff(cols, bins=_hundred_bins_sorted)
+        except IndexError:
+            if cols.size:
+                raise
+            return bads
+        except LookupError:
+            if not silent:
+                stderr.write('WARNING: Too many zeroes to filter columns. SKIPPING...\n')
+            return bads
+        all_sums = fast_masked_col_sums(m, np.zeros(size, dtype=np.uint8))
+        for i in np.nonzero(all_sums < root)[0]:
+            bads[int(i)] = int(all_sums[i])
+    except ValueError:
+        if not silent:
+            stderr.write('WARNING: Too few data to filter columns based on mean value.\n')
+    return bads
+
+
+def fast_iterative(m, bads=None, iterations=0, max_dev=0.00001, threads=0):
+    """normalize_hic.py:180-231 -> (bias, trace rows (Smin, meanS, Smax, it, dev), seconds)."""
+    import time
+    bias = np.empty(m.size)
+    trace = np.zeros((iterations + 1, 4))
+    bad = _bad_u8(m.size, bads)
+    t0 = time.perf_counter()
+    passes = _upper_lib().up_ice(m.size, *m._args(), bad.ctypes.data, int(iterations), float(max_dev),
+                                 bias.ctypes.data, trace.ctypes.data, threads)
+    dt = time.perf_counter() - t0
+    if passes == -1:
+        raise ZeroDivisionError('ERROR: normalization failed, all bad columns')
+    if passes == -2:
+        raise ZeroDivisionError('float division by zero')
+    if passes < 0:
+        raise MemoryError("up_ice")
+    ntrace = passes if iterations > 0 else 0
+    return bias, [(t[0], t[1], t[2], it, t[3]) for it, t in enumerate(trace[:ntrace])], dt
+
+
+def fast_norm_sum(m, bias, bads=None, threads=0):
+    bias = np.ascontiguousarray(bias, dtype=np.float64)
+    bad = _bad_u8(m.size, bads)
+    return _upper_lib().up_norm_sum(*m._args(), bad.ctypes.data, bias.ctypes.data, threads)
+
+
+def fast_normalize_hic(m, bads=None, iterations=0, max_dev=0.1, sqrt=False, factor=1):
+    """hic_data.py:380-413 -> (bias, trace)."""
+    bias, trace, _ = fast_iterative(m, bads, iterations, max_dev)
+    if sqrt:
+        bias = bias ** 0.5
+    if factor:
+        target = (fast_norm_sum(m, bias, bads) / float(m.size * m.size * factor)) ** 0.5
+        bias = bias * target
+    return bias, trace
+
+
+def fast_expected(m, bads=None, signal_to_noise=0.05, inter_chrom=False, threads=0):
+    """normalize_hic.py:234-291: integer per-distance sums in C, counts and pooling as above."""
+    min_n = signal_to_noise ** -2.
+    size = m.size
+    if m.chromosomes and not inter_chrom:
+        size = max(m.chromosomes.values())
+    bad = _bad_u8(m.size, bads or {})
+    chrom_of = np.empty(m.size, dtype=np.int32)
+    for n, (beg, end) in enumerate(m.section_pos.values()):
+        chrom_of[beg:end] = n
+    sum_d = np.zeros(size, dtype=np.int64)
+    if _upper_lib().up_diag_sums(m.size, *m._args(), bad.ctypes.data, chrom_of.ctypes.data, size,
+                                 sum_d.ctypes.data, threads):
+        raise MemoryError("up_diag_sums")
+    good_before = np.concatenate([[0], np.cumsum(bad == 0)])
+    cnt_d = np.zeros(size, dtype=np.int64)
+    for beg, end in m.section_pos.values():
+        span = min(end - beg, size)
+        dd = np.arange(span)
+        cnt_d[:span] += good_before[end - dd] - good_before[beg]
+    return pool_diagonals([int(v) for v in sum_d], cnt_d, size, min_n)

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("TADBIT_B200_LIB") or os.path.join(_HERE, "libtadbit_b
 
 TB_OK, TB_ERR_ARG, TB_ERR_CUDA, TB_ERR_ALL_BAD, TB_ERR_NCCL, TB_ERR_STATE, TB_ERR_ZERO_DIV = range(7)
 TB_MEM_HOST, TB_MEM_DEVICE = 0, 1
+TB_CELLS_UPPER, TB_CELLS_FULL_ROWS = 0, 1
 
 
 class SynthParams(C.Structure):
@@ -42,6 +43,10 @@ PROTOTYPES = {
     "tb_store_create_coo": ([C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                              C.c_int32, _i64p, C.c_int64, C.c_int64, C.c_int,
                              C.POINTER(_store)], C.c_int),
+    "tb_store_create_csr": ([C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                             C.c_int32, _i64p, C.c_int64, C.c_int64, C.c_int,
+                             C.POINTER(_store)], C.c_int),
+    "tb_store_export_csr": ([_store, C.c_int, _i64p, _i64p, _i32p, _i32p], C.c_int),
     "tb_store_create_synthetic": ([C.c_int64, C.c_int32, _i64p, C.POINTER(SynthParams), C.c_int64,
                                    C.c_int64, C.c_int, C.POINTER(_store)], C.c_int),
     "tb_synthetic_row_counts": ([C.c_int64, C.c_int32, _i64p, C.POINTER(SynthParams), C.c_int64,

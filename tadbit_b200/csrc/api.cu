@@ -199,6 +199,30 @@ int tb_store_create_coo(int64_t nbins, int64_t nnz, const int32_t *row, const in
   });
 }
 
+int tb_store_create_csr(int64_t nbins, int form, const int64_t *ptr, const int32_t *col,
+                        const int32_t *val, int mem, int32_t n_chrom, const int64_t *chrom_offsets,
+                        int64_t row_begin, int64_t row_end, int device, tb_store **out) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(out && ptr, "null argument");
+    *out = nullptr;
+    TB_REQUIRE(form == TB_CELLS_UPPER || form == TB_CELLS_FULL_ROWS, "form must be TB_CELLS_UPPER/TB_CELLS_FULL_ROWS");
+    TB_REQUIRE(mem == TB_MEM_HOST || mem == TB_MEM_DEVICE, "mem must be TB_MEM_HOST/TB_MEM_DEVICE");
+    int prev = 0;
+    cudaGetDevice(&prev);
+    tb_store *s = new_store(nbins, n_chrom, chrom_offsets, row_begin, row_end, device);
+    try {
+      build_from_csr(s, form, ptr, col, val, mem);
+    } catch (...) {
+      tb_store_destroy(s);
+      cudaSetDevice(prev);
+      throw;
+    }
+    cudaSetDevice(prev);
+    *out = s;
+    return TB_OK;
+  });
+}
+
 int tb_store_create_synthetic(int64_t nbins, int32_t n_chrom, const int64_t *chrom_offsets,
                               const tb_synth_params *params, int64_t row_begin,
                               int64_t row_end, int device, tb_store **out) {
@@ -313,6 +337,17 @@ int tb_store_set_option(tb_store *s, const char *name, const char *value) {
     if (!strcmp(value, "csr")) s->rowsum_mode = 1;
     else if (!strcmp(value, "compact")) s->rowsum_mode = 0;
     else { set_error("rowsum must be 'compact' or 'csr'"); return TB_ERR_ARG; }
+    if (s->rowsum_mode == 1 && !s->csr_resident) {
+      s->rowsum_mode = -1;
+      set_error("rowsum=csr: this store released its CSR after the build (create it with TB_KEEP_CSR=1)");
+      return TB_ERR_STATE;
+    }
+    return TB_OK;
+  }
+  if (!strcmp(name, "exchange")) {       // every rank of a group must choose the same
+    if (!strcmp(value, "nccl")) s->exchange_mode = 0;
+    else if (!strcmp(value, "fused")) s->exchange_mode = 1;
+    else { set_error("exchange must be 'fused' or 'nccl'"); return TB_ERR_ARG; }
     return TB_OK;
   }
   set_error("unknown option %s", name);
@@ -341,6 +376,17 @@ int tb_store_export_upper(const tb_store *s, int64_t *nnz, int32_t *h_row, int32
     TB_REQUIRE(s && nnz, "null argument");
     DeviceGuard g(s->device);
     export_upper(s, nnz, h_row, h_col, h_val);
+    return TB_OK;
+  });
+}
+
+int tb_store_export_csr(const tb_store *s, int form, int64_t *nnz, int64_t *h_ptr, int32_t *h_col,
+                        int32_t *h_val) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(s && nnz, "null argument");
+    TB_REQUIRE(form == TB_CELLS_UPPER || form == TB_CELLS_FULL_ROWS, "form must be TB_CELLS_UPPER/TB_CELLS_FULL_ROWS");
+    DeviceGuard g(s->device);
+    export_csr(s, form, nnz, h_ptr, h_col, h_val);
     return TB_OK;
   });
 }

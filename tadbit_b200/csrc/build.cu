@@ -297,18 +297,18 @@ __global__ void k_unpack_keys(const uint64_t *__restrict__ key, int64_t n, int64
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n;
        k += (int64_t)gridDim.x * blockDim.x) {
     const uint64_t e = key[k];
-    orow[k] = (int32_t)(rb + (int64_t)(e >> 32)) + row_off;
+    if (orow) orow[k] = (int32_t)(rb + (int64_t)(e >> 32)) + row_off;
     ocol[k] = (int32_t)(e & 0xffffffffu) + col_off;
   }
 }
 
 // first stored cell of each owned row with col >= its own (global) row index
 __global__ void k_upper_start(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                              int64_t nrows, int64_t rb, int64_t *ustart, int64_t *ucount) {
+                              int64_t nrows, int64_t rb, bool whole_row, int64_t *ustart, int64_t *ucount) {
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
        r += (int64_t)gridDim.x * blockDim.x) {
     int64_t lo = rowptr[r], hi = rowptr[r + 1], end = hi;
-    int32_t g = (int32_t)(rb + r);
+    int32_t g = whole_row ? 0 : (int32_t)(rb + r);
     while (lo < hi) {
       int64_t mid = (lo + hi) >> 1;
       if (col[mid] < g) lo = mid + 1; else hi = mid;
@@ -328,7 +328,7 @@ __global__ void k_copy_upper(const int32_t *__restrict__ col, const int32_t *__r
   for (int64_t r = warp; r < nrows; r += nwarp) {
     int64_t src = ustart[r], n = ucount[r], dst = uoff[r];
     for (int64_t k = lane; k < n; k += 32) {
-      orow[dst + k] = (int32_t)(rb + r) + bin_off;
+      if (orow) orow[dst + k] = (int32_t)(rb + r) + bin_off;
       ocol[dst + k] = col[src + k] + bin_off;
       oval[dst + k] = val[src + k];
     }
@@ -492,6 +492,95 @@ void build_from_coo(tb_store *s, int64_t nnz, const int32_t *row, const int32_t 
   finish_layout(s);
 }
 
+namespace {
+__global__ void k_expand_rows(const int64_t *__restrict__ ptr, int64_t nrows, int32_t *__restrict__ row) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < nrows; r += nwarp)
+    for (int64_t k = ptr[r] + lane; k < ptr[r + 1]; k += 32) row[k] = (int32_t)r;
+}
+// whole rows handed over as they are: columns in range and strictly ascending inside each row
+__global__ void k_check_rows(const int64_t *__restrict__ ptr, const int32_t *__restrict__ col, int64_t nrows,
+                             int64_t nbins, int64_t nnz, int *bad_input) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = ptr[r], e = ptr[r + 1];
+    if (b > e || b < 0 || e > nnz || (r == 0 && b != 0) || (r == nrows - 1 && e != nnz)) { *bad_input = 1; continue; }
+    for (int64_t k = b; k < e; ++k)
+      if (col[k] < 0 || col[k] >= nbins || (k > b && col[k] <= col[k - 1])) { *bad_input = 1; break; }
+  }
+}
+}  // namespace
+
+// Cells in CSR form.  TB_CELLS_UPPER: the upper-triangle rows of the WHOLE matrix (ptr has nbins + 1
+// entries) -- 8 bytes per cell over PCIe instead of the 12 of the coordinate form; the row index
+// is expanded on the device and the cells then take the path of build_from_coo.
+// TB_CELLS_FULL_ROWS: every stored cell of the owned rows [row_begin, row_end) (both triangles,
+// ptr has nrows + 1 entries, columns ascending): the pre-partitioned input of a sharded matrix.
+// The arrays ARE the store's CSR, nothing is mirrored or sorted.
+void build_from_csr(tb_store *s, int form, const int64_t *ptr, const int32_t *col, const int32_t *val, int mem) {
+  cudaStream_t st = s->stream;
+  StageTimer tm(st);
+  const int threads = 256;
+  const int64_t nptr = (form == TB_CELLS_UPPER ? s->nbins : s->nrows) + 1;
+  DevBuf<int64_t> dptr;
+  const int64_t *p = ptr;
+  int64_t nnz = 0;
+  if (mem == TB_MEM_HOST) {
+    nnz = ptr[nptr - 1];
+    dptr.alloc(nptr);
+    TB_CUDA(cudaMemcpyAsync(dptr.p, ptr, nptr * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    p = dptr.p;
+  } else {
+    TB_CUDA(cudaMemcpy(&nnz, ptr + nptr - 1, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  }
+  TB_REQUIRE(nnz >= 0 && (nnz == 0 || (col && val)), "contact store: bad row pointers or null cell arrays");
+  if (form == TB_CELLS_UPPER) {
+    TB_REQUIRE(s->row_begin == 0 && s->row_end == s->nbins,
+               "TB_CELLS_UPPER describes the whole matrix; shards take TB_CELLS_FULL_ROWS");
+    DevBuf<int32_t> drow, dcol, dval;
+    drow.alloc(nnz ? nnz : 1);
+    const int32_t *c = col, *v = val;
+    if (mem == TB_MEM_HOST && nnz) {
+      dcol.alloc(nnz); dval.alloc(nnz);
+      TB_CUDA(cudaMemcpyAsync(dcol.p, col, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      TB_CUDA(cudaMemcpyAsync(dval.p, val, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      c = dcol.p; v = dval.p;
+    }
+    if (nnz)
+      k_expand_rows<<<grid_for(s->nbins * 32, threads, s->sm_count), threads, 0, st>>>(p, s->nbins, drow.p);
+    tm.lap("H2D cells (CSR form)");
+    build_from_coo(s, nnz, drow.p, c, v, TB_MEM_DEVICE);
+    return;
+  }
+  s->nnz_full = nnz;
+  s->rowptr.alloc(s->nrows + 1);
+  s->col.alloc(nnz ? nnz : 1);
+  s->val.alloc(nnz ? nnz : 1);
+  TB_CUDA(cudaMemcpyAsync(s->rowptr.p, p, (s->nrows + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  const cudaMemcpyKind kind = mem == TB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  if (nnz) {
+    TB_CUDA(cudaMemcpyAsync(s->col.p, col, nnz * sizeof(int32_t), kind, st));
+    TB_CUDA(cudaMemcpyAsync(s->val.p, val, nnz * sizeof(int32_t), kind, st));
+  }
+  DevBuf<int> flag;
+  flag.alloc(1);
+  TB_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+  if (s->nrows)
+    k_check_rows<<<grid_for(s->nrows, threads, s->sm_count), threads, 0, st>>>(s->rowptr.p, s->col.p, s->nrows,
+                                                                               s->nbins, nnz, flag.p);
+  int h_flag = 0;
+  TB_CUDA(cudaMemcpyAsync(&h_flag, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  TB_REQUIRE(!h_flag, "contact store: row pointers not ascending, or a row's columns out of range / not "
+                      "strictly ascending");
+  tm.lap("H2D rows (CSR form)");
+  dptr.release();
+  flag.release();
+  finish_layout(s);
+}
+
 // A panel is encoded densely (explicit zeros) when at least 1/F of its columns hold a cell.  By
 // bytes alone the break-even against 4-byte tile cells is F = 4; measured per stored cell the
 // dense kernel is faster than the tile kernel, but explicit zeros at low fill cost more than
@@ -559,7 +648,7 @@ void finish_layout(tb_store *s) {
     TB_CUDA(cudaMemsetAsync(uc.p, 0, uc.bytes(), st));
     if (nrows)
       k_upper_start<<<grid_for(nrows, threads, s->sm_count), threads, 0, st>>>(
-          s->rowptr.p, s->col.p, nrows, s->row_begin, us.p, uc.p);
+          s->rowptr.p, s->col.p, nrows, s->row_begin, false, us.p, uc.p);
     size_t tmp_bytes = 0;
     TB_CUDA(cub::DeviceReduce::Sum(nullptr, tmp_bytes, uc.p, total.p, nrows + 1, st));
     DevBuf<uint8_t> tmp;
@@ -646,22 +735,30 @@ void setup_sections(tb_store *s) {
   if (N) TB_CUDA(cudaMemcpy(s->chrom_of.p, h.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice));
 }
 
-// The owned upper-triangle cells, row-major sorted, into device arrays of nnz_upper entries;
-// bin_off is added to rows and columns.  Runs on the store's stream and waits for it.
-void export_upper_device(const tb_store *s, int32_t *d_row, int32_t *d_col, int32_t *d_val, int32_t bin_off) {
-  if (s->nnz_upper == 0) return;
+// Cells of the owned rows, row-major sorted, into device arrays: the upper triangle (col >= row,
+// nnz_upper entries) or, full_rows, every stored cell of the rows (nnz_full entries).  d_row may
+// be null; d_ptr (nrows + 1, may be null) receives the first cell of every row; bin_off is added
+// to rows and columns.  Runs on the store's stream and waits for it.
+void export_cells_device(const tb_store *s, bool full_rows, int32_t *d_row, int32_t *d_col, int32_t *d_val,
+                         int64_t *d_ptr, int32_t bin_off) {
   cudaStream_t st = s->stream;
   const int threads = 256;
-  const int64_t nrows = s->nrows, m = s->nnz_upper;
+  const int64_t nrows = s->nrows, m = full_rows ? s->nnz_full : s->nnz_upper;
+  if (m == 0) {
+    if (d_ptr) TB_CUDA(cudaMemsetAsync(d_ptr, 0, (nrows + 1) * sizeof(int64_t), st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    return;
+  }
   if (s->csr_resident) {
     DevBuf<int64_t> us, uc, uo;
     us.alloc(nrows + 1); uc.alloc(nrows + 1); uo.alloc(nrows + 1);
     TB_CUDA(cudaMemsetAsync(uc.p, 0, uc.bytes(), st));
     k_upper_start<<<grid_for(nrows, threads, s->sm_count), threads, 0, st>>>(
-        s->rowptr.p, s->col.p, nrows, s->row_begin, us.p, uc.p);
+        s->rowptr.p, s->col.p, nrows, s->row_begin, full_rows, us.p, uc.p);
     exclusive_scan_i64(st, uc.p, uo.p, nrows + 1);
     k_copy_upper<<<grid_for(nrows * 32, threads, s->sm_count), threads, 0, st>>>(
         s->col.p, s->val.p, us.p, uc.p, uo.p, nrows, s->row_begin, bin_off, d_row, d_col, d_val);
+    if (d_ptr) TB_CUDA(cudaMemcpyAsync(d_ptr, uo.p, (nrows + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
     TB_CUDA(cudaStreamSynchronize(st));
     return;
   }
@@ -674,11 +771,11 @@ void export_upper_device(const tb_store *s, int32_t *d_row, int32_t *d_col, int3
   CountUpperVisitor cv;
   cv.rb = s->row_begin;
   cv.cnt = cnt.p;
-  visit_upper(s, cv);
+  visit_upper(s, cv, full_rows);
   exclusive_scan_i64(st, reinterpret_cast<const int64_t *>(cnt.p), off.p, nrows + 1);
   int64_t total = 0;
   TB_CUDA(cudaMemcpy(&total, off.p + nrows, sizeof(int64_t), cudaMemcpyDeviceToHost));
-  TB_REQUIRE(total == m, "internal: compact stream holds %lld upper cells, expected %lld",
+  TB_REQUIRE(total == m, "internal: compact stream holds %lld cells, expected %lld",
              (long long)total, (long long)m);
   DevBuf<uint64_t> key_in, key_out;
   DevBuf<int32_t> val_in;
@@ -690,7 +787,7 @@ void export_upper_device(const tb_store *s, int32_t *d_row, int32_t *d_col, int3
   pv.cursor = cnt.p;
   pv.key = key_in.p;
   pv.val = val_in.p;
-  visit_upper(s, pv);
+  visit_upper(s, pv, full_rows);
   int row_bits = 1;
   while (((int64_t)1 << row_bits) < nrows) ++row_bits;
   size_t tmp_bytes = 0;
@@ -702,6 +799,31 @@ void export_upper_device(const tb_store *s, int32_t *d_row, int32_t *d_col, int3
                                           32 + row_bits, st));
   k_unpack_keys<<<grid_for(m, threads, s->sm_count), threads, 0, st>>>(key_out.p, m, s->row_begin, bin_off,
                                                                        bin_off, d_row, d_col);
+  if (d_ptr) TB_CUDA(cudaMemcpyAsync(d_ptr, off.p, (nrows + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+}
+
+void export_upper_device(const tb_store *s, int32_t *d_row, int32_t *d_col, int32_t *d_val, int32_t bin_off) {
+  export_cells_device(s, false, d_row, d_col, d_val, nullptr, bin_off);
+}
+
+// CSR form on the host: h_ptr[nrows + 1], h_col / h_val [*nnz]; pass null arrays to get *nnz only.
+void export_csr(const tb_store *s, int form, int64_t *nnz, int64_t *h_ptr, int32_t *h_col, int32_t *h_val) {
+  const bool full = form == TB_CELLS_FULL_ROWS;
+  const int64_t m = full ? s->nnz_full : s->nnz_upper;
+  *nnz = m;
+  if (!h_ptr) return;
+  TB_REQUIRE(h_col && h_val, "export: null output buffer");
+  cudaStream_t st = s->stream;
+  DevBuf<int32_t> ocol, oval;
+  DevBuf<int64_t> optr;
+  ocol.alloc(m ? m : 1); oval.alloc(m ? m : 1); optr.alloc(s->nrows + 1);
+  export_cells_device(s, full, nullptr, ocol.p, oval.p, optr.p, 0);
+  TB_CUDA(cudaMemcpyAsync(h_ptr, optr.p, (s->nrows + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  if (m) {
+    TB_CUDA(cudaMemcpyAsync(h_col, ocol.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaMemcpyAsync(h_val, oval.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  }
   TB_CUDA(cudaStreamSynchronize(st));
 }
 

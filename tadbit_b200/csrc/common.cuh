@@ -231,6 +231,7 @@ struct tb_store {
   int rowsum_launches = 0, total_launches = 0;
   int64_t device_bytes = 0;
   int rowsum_mode = -1;     // -1 default (compact stream), 0 compact, 1 CSR walk (tb_store_set_option)
+  int exchange_mode = -1;   // -1 default (TB_EXCHANGE), 1 fused exchange kernel, 0 separate steps / NCCL
 };
 
 namespace tb {
@@ -242,6 +243,8 @@ void setup_sections(tb_store *s);   // bin -> section id table (before any build
 void finish_layout(tb_store *s);     // chunks + scratch once rowptr/col/val are in place
 void export_upper(const tb_store *s, int64_t *nnz, int32_t *h_row, int32_t *h_col, int32_t *h_val);
 void export_upper_device(const tb_store *s, int32_t *d_row, int32_t *d_col, int32_t *d_val, int32_t bin_off);
+void export_csr(const tb_store *s, int form, int64_t *nnz, int64_t *h_ptr, int32_t *h_col, int32_t *h_val);
+void build_from_csr(tb_store *s, int form, const int64_t *ptr, const int32_t *col, const int32_t *val, int mem);
 void build_batch(tb_store *s, int32_t n, tb_store *const *members);   // block-diagonal concatenation
 // encode.cu
 void build_encoded(tb_store *s);     // compact row-sum stream from the CSR

@@ -766,12 +766,16 @@ bool use_csr_rowsum(const tb_store *s) {
 // steps (the parity reference of the fused exchange); also taken when the peers' buffers
 // could not be mapped.
 bool use_fused_exchange(const tb_store *s) {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("TB_EXCHANGE");
-    v = (e && !strcmp(e, "nccl")) ? 0 : 1;
+  int want = s->exchange_mode;           // tb_store_set_option("exchange", ...)
+  if (want < 0) {
+    static int v = -1;
+    if (v < 0) {
+      const char *e = getenv("TB_EXCHANGE");
+      v = (e && !strcmp(e, "nccl")) ? 0 : 1;
+    }
+    want = v;
   }
-  return v == 1 && s->px.ready && (s->world == 1 || s->px.mapped);
+  return want == 1 && s->px.ready && (s->world == 1 || s->px.mapped);
 }
 
 TileSums tile_sums(const tb_store *s) {

@@ -43,6 +43,7 @@ struct VisitSrc {
   const int64_t *chunk_beg;
   const int32_t *col, *val;
   int64_t row_begin, nrows, nbins;
+  bool full_rows;                      // also visit the cells left of the diagonal (export of whole rows)
 };
 
 inline VisitSrc visit_src(const tb_store *s) {
@@ -64,6 +65,7 @@ inline VisitSrc visit_src(const tb_store *s) {
   v.row_begin = s->row_begin;
   v.nrows = s->nrows;
   v.nbins = s->nbins;
+  v.full_rows = false;
   return v;
 }
 
@@ -85,20 +87,21 @@ __global__ void __launch_bounds__(256) k_visit_chunks(VisitSrc src, V vis) {
     const int4 d = src.enc_desc[c];
     const int enc = d.z & 0xff;
     if (enc == ENC_T) continue;                         // its cells are in the tiles
-    const int64_t g = src.row_begin + src.chunk_row[c];
+    const int64_t gi = src.row_begin + src.chunk_row[c];
+    const int64_t g = src.full_rows ? -1 : gi;          // cells with column >= g are visited
     const uint8_t *p = src.enc_data + src.enc_off[c];
     if (enc == ENC_S32) {
       const int2 *w = reinterpret_cast<const int2 *>(p);
       for (int k = lane; k < d.y; k += 32) {
         const int2 e = w[k];
-        if (e.x >= g) vis.cell(g, e.x, e.y);
+        if (e.x >= g) vis.cell(gi, e.x, e.y);
       }
     } else if (enc == ENC_S16) {
       const uint32_t *w = reinterpret_cast<const uint32_t *>(p);
       for (int k = lane; k < d.y; k += 32) {
         const uint32_t e = w[k];
         const int64_t j = d.x + (int64_t)(e & 0xffffu);
-        if (j >= g) vis.cell(g, j, (int32_t)(e >> 16));
+        if (j >= g) vis.cell(gi, j, (int32_t)(e >> 16));
       }
     } else {
       const int c0 = d.x, nslots = d.y, novf = d.z >> 8;
@@ -120,13 +123,13 @@ __global__ void __launch_bounds__(256) k_visit_chunks(VisitSrc src, V vis) {
           else v = (int32_t)u[e];
           if (v == 0) continue;
           const int64_t j = (int64_t)c0 + dense_slot(wi * per + e);
-          if (j >= g) vis.cell(g, j, v);
+          if (j >= g) vis.cell(gi, j, v);
         }
       }
       const int2 *ovf = reinterpret_cast<const int2 *>(p + (int64_t)nslots * width);
       for (int k = lane; k < novf; k += 32) {
         const int2 e = ovf[k];
-        if (e.x >= g) vis.cell(g, e.x, e.y);
+        if (e.x >= g) vis.cell(gi, e.x, e.y);
       }
     }
   }
@@ -149,11 +152,12 @@ __global__ void __launch_bounds__(256) k_visit_tiles(VisitSrc src, V vis) {
     const int sl = (int)(it % kVisitSlices);
     const int64_t rb = tile / src.t_nwin, w = tile % src.t_nwin;
     const int64_t wlo = w * kTileCols, g0 = src.row_begin + rb * kTileRows;
-    if (wlo + kTileCols <= g0) continue;                // tile left of the diagonal
+    if (!src.full_rows && wlo + kTileCols <= g0) continue;     // tile left of the diagonal
     const uint32_t *st = src.t_slice + tile * kVisitSliceTab + 2 * sl;
     const uint32_t o1 = st[0], o2 = st[1], o3 = st[2];
     if (o1 == o3) continue;
-    const int64_t g = g0 + src.t_perm[tile * kTileRows + sl * 32 + lane];
+    const int64_t gi = g0 + src.t_perm[tile * kTileRows + sl * 32 + lane];
+    const int64_t g = src.full_rows ? -1 : gi;
     const uint4 *base = reinterpret_cast<const uint4 *>(src.t_cells + src.t_off[tile] * 128);
     for (uint32_t blk = o1; blk < o2; ++blk) {          // ones: 8 column offsets per lane and block
       const uint4 q = base[(size_t)blk * 32 + lane];
@@ -163,7 +167,7 @@ __global__ void __launch_bounds__(256) k_visit_tiles(VisitSrc src, V vis) {
         const uint32_t off = (u[e >> 1] >> (16 * (e & 1))) & 0xffffu;
         if (off >= (uint32_t)kTileCols) continue;       // padding points behind the window
         const int64_t j = wlo + off;
-        if (j >= g) vis.cell(g, j, 1);
+        if (j >= g) vis.cell(gi, j, 1);
       }
     }
     for (uint32_t blk = o2; blk < o3; ++blk) {          // general: 4 cells per lane and block
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__(256) k_visit_tiles(VisitSrc src, V vis) {
         const int32_t v = (int32_t)(u[e] & 0xffffu);
         if (v == 0) continue;                           // padding
         const int64_t j = wlo + (u[e] >> 18);
-        if (j >= g) vis.cell(g, j, v);
+        if (j >= g) vis.cell(gi, j, v);
       }
     }
   }
@@ -191,12 +195,13 @@ __global__ void __launch_bounds__(256) k_visit_csr(VisitSrc src, V vis) {
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t c = warp; c < src.nchunks; c += nwarp) {
-    const int64_t g = src.row_begin + src.chunk_row[c];
+    const int64_t gi = src.row_begin + src.chunk_row[c];
+    const int64_t g = src.full_rows ? -1 : gi;
     const int64_t beg = src.chunk_beg[c], end = src.chunk_beg[c + 1];
     if (src.col[end - 1] < g) continue;                 // chunk entirely left of the diagonal
     for (int64_t k = beg + lane; k < end; k += 32) {
       const int64_t j = src.col[k];
-      if (j >= g) vis.cell(g, j, src.val[k]);
+      if (j >= g) vis.cell(gi, j, src.val[k]);
     }
   }
   __syncthreads();
@@ -205,8 +210,9 @@ __global__ void __launch_bounds__(256) k_visit_csr(VisitSrc src, V vis) {
 
 // Run `vis` over every stored upper-triangle cell of the store's rows (stream s->stream).
 template <typename V>
-void visit_upper(const tb_store *s, const V &vis) {
-  const VisitSrc src = visit_src(s);
+void visit_upper(const tb_store *s, const V &vis, bool full_rows = false) {
+  VisitSrc src = visit_src(s);
+  src.full_rows = full_rows;
   if (s->nchunks == 0) return;
   int64_t need = (s->nchunks + 7) / 8, cap = (int64_t)s->sm_count * 8;
   const int grid = (int)(need < cap ? (need < 1 ? 1 : need) : cap);

@@ -45,6 +45,34 @@ class ContactStore(object):
         return cls(out, size)
 
     @classmethod
+    def from_csr(cls, size, indptr, cols, vals, form="upper", chromosomes=None, row_block=None,
+                 device=0):
+        """Cells in CSR form as host arrays (pinned memory makes the copy faster).
+
+        ``form="upper"``: upper-triangle rows of the whole matrix, ``indptr`` has ``size + 1``
+        entries.  ``form="full_rows"``: every stored cell of the rows ``row_block`` of the full
+        symmetric matrix (both triangles, columns ascending) -- what each GPU of a row-sharded
+        matrix is given."""
+        forms = {"upper": _capi.TB_CELLS_UPPER, "full_rows": _capi.TB_CELLS_FULL_ROWS}
+        if form not in forms:
+            raise ValueError("form must be 'upper' or 'full_rows'")
+        indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        cols, vals = _capi.as_i32(cols, "cols"), _capi.as_i32(vals, "vals")
+        rb, re = row_block if row_block is not None else (0, size)
+        nrows = size if form == "upper" else re - rb
+        if indptr.shape != (nrows + 1,) or cols.shape != vals.shape or cols.ndim != 1:
+            raise ValueError("indptr must have %d entries; cols and vals equal 1-D shapes" % (nrows + 1))
+        if indptr[0] != 0 or indptr[-1] != cols.size:
+            raise ValueError("indptr must run from 0 to the number of cells")
+        n_chrom, offs = _offsets(size, chromosomes)
+        out = C.c_void_p()
+        check(lib().tb_store_create_csr(
+            size, forms[form], indptr.ctypes.data, cols.ctypes.data, vals.ctypes.data,
+            _capi.TB_MEM_HOST, n_chrom, ptr(offs, C.c_int64) if offs is not None else None,
+            rb, re, device, C.byref(out)))
+        return cls(out, size)
+
+    @classmethod
     def from_device_pointers(cls, size, nnz, d_rows, d_cols, d_vals, chromosomes=None,
                              row_block=None, device=0):
         """Cells already resident on the device (int32 arrays, e.g. torch tensors'
@@ -122,6 +150,21 @@ class ContactStore(object):
             check(lib().tb_store_export_upper(self._h, C.byref(n), ptr(r, C.c_int32),
                                               ptr(c, C.c_int32), ptr(v, C.c_int32)))
         return r, c, v
+
+    def export_csr(self, form="upper", pinned=None):
+        """Owned rows in CSR form: (indptr int64[nrows+1], cols int32, vals int32).  ``pinned``: a
+        callable ``(count, dtype) -> array`` that supplies the output buffers (e.g. pinned memory)."""
+        f = {"upper": _capi.TB_CELLS_UPPER, "full_rows": _capi.TB_CELLS_FULL_ROWS}[form]
+        n = C.c_int64()
+        check(lib().tb_store_export_csr(self._h, f, C.byref(n), None, None, None))
+        i = self.info()
+        alloc = pinned or (lambda count, dtype: np.empty(count, dtype=dtype))
+        indptr = alloc(i["row_end"] - i["row_begin"] + 1, np.int64)
+        c = alloc(n.value, np.int32)
+        v = alloc(n.value, np.int32)
+        check(lib().tb_store_export_csr(self._h, f, C.byref(n), ptr(indptr, C.c_int64),
+                                        ptr(c, C.c_int32), ptr(v, C.c_int32)))
+        return indptr, c, v
 
     # -- multi-GPU ------------------------------------------------------------
     @staticmethod

@@ -44,9 +44,25 @@ def main():
     hic.normalize_expected()
     nnz, rsum = store.row_stats()
     raw = hic.sum()
+    exchange = store.timing()["exchange"]
+    # the same ICE with the pass as separate steps around an NCCL all-reduce (the parity reference
+    # of the fused exchange kernel)
+    store.set_option("exchange", "nccl")
+    hic.normalize_hic(iterations=100, max_dev=1e-5, silent=True, factor=None)
+    nccl_bias, nccl_passes = hic.bias.to_array().copy(), len(hic.last_trace)
+    store.set_option("exchange", "fused")
+    hic.normalize_hic(iterations=100, max_dev=1e-5, silent=True)
+    # pre-partitioned input: this rank's rows exported in CSR form and a second store built from them
+    ptr, cc, vv = store.export_csr("full_rows")
+    again = tadbit_b200.ContactStore.from_csr(wl["size"], ptr, cc, vv, form="full_rows",
+                                              chromosomes=wl["chromosomes"], row_block=block, device=local)
+    same_rows = all(np.array_equal(a, b) for a, b in zip(again.export_csr("full_rows"), (ptr, cc, vv)))
+    same_rows &= again.info()["nnz_upper"] == store.info()["nnz_upper"]
+    again.close()
     result = dict(bads=hic.bads, bias=hic.bias.to_array(), raw_bias=raw_bias, expected=hic.expected, nnz=nnz,
                   rsum=rsum, raw=raw, passes=len(hic.last_trace), block=block,
-                  nnz_upper=store.info()["nnz_upper"])
+                  nnz_upper=store.info()["nnz_upper"], exchange=exchange, nccl_bias=nccl_bias,
+                  nccl_passes=nccl_passes, same_rows=bool(same_rows))
     allres = gather(result)
     ok = True
     if rank == 0:
@@ -78,7 +94,14 @@ def main():
             "rescaled bias 1e-13": np.allclose(ref.bias.to_array(), hic.bias.to_array(),
                                                rtol=1e-13, atol=0),
             "expected": ref.expected == hic.expected,
+            # fused exchange kernel vs combine -> ncclAllReduce -> statistics -> update
+            "fused vs nccl passes": all(b["nccl_passes"] == b["passes"] for b in allres),
+            "fused vs nccl 1e-13": np.allclose(allres[0]["nccl_bias"], raw_bias, rtol=1e-13, atol=0),
+            "nccl path ranks identical": all(np.array_equal(b["nccl_bias"], allres[0]["nccl_bias"])
+                                             for b in allres),
+            "rows round trip (CSR form)": all(b["same_rows"] for b in allres),
         }
+        print("exchange in use:", [b["exchange"] for b in allres])
         for k, v in checks.items():
             print("%-22s %s" % (k, "ok" if v else "FAIL"))
             ok &= bool(v)

@@ -6,6 +6,8 @@ Bars (north_star): filter mask / indices / integer sums bit-exact; expected bit-
 import io
 import contextlib
 
+import re
+
 import numpy as np
 import pytest
 
@@ -66,7 +68,7 @@ def test_normalize_hic(name, hics):
         kw = dict(iterations=rec["iterations"], max_dev=rec["max_dev"],
                   sqrt=rec["sqrt"], factor=rec["factor"])
         if "raises" in rec:
-            with pytest.raises(ZeroDivisionError, match="all bad columns"):
+            with pytest.raises(ZeroDivisionError, match=re.escape(rec["message"])):
                 hic.normalize_hic(silent=True, **kw)
             continue
         out = io.StringIO()

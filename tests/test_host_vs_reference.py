@@ -266,3 +266,27 @@ def test_batch_host_logic_matches_the_reference_loop(monkeypatch):
                 words = lambda line: [t for t in line.split()
                                       if not t.replace('.', '').replace('-', '').isdigit()]
                 assert words(x) == words(y)
+
+
+@pytest.mark.parametrize("kind", ["all_bad", "all_zero"])
+def test_failing_normalisation_prints_and_raises_like_the_reference(kind):
+    """Verbose output up to the exception: 'all bad columns' is raised before '  - computing
+    biases' is printed (normalize_hic.py:203-210), a zero mean row sum right after it (:148)."""
+    ns = ref_shim.load()
+    n = 40
+    i, j = np.triu_indices(n)
+    keep = (j - i) < 3
+    rows, cols = i[keep], j[keep]
+    vals = np.zeros(rows.size, dtype=np.int64) if kind == "all_zero" else np.ones(rows.size, dtype=np.int64)
+    k = dict(n=n, rows=rows, cols=cols, vals=vals, sizes=None, names=None, symmetricized=False)
+    ref, ours = _reference(ns, k), _product(k)
+    bads = dict((b, True) for b in range(n)) if kind == "all_bad" else {3: True}
+    outs = []
+    for h in (ref, ours):
+        h.bads = dict(bads)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf), pytest.raises(ZeroDivisionError) as exc:
+            h.normalize_hic(iterations=5, max_dev=1e-5, silent=False)
+        outs.append((buf.getvalue(), str(exc.value)))
+    assert outs[0] == outs[1]
+    assert ("computing biases" in outs[0][0]) == (kind == "all_zero")

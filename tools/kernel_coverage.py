@@ -1,6 +1,7 @@
 """Small end-to-end pass over every kernel of the library on ONE GPU (a few seconds), written
-as the target for ``compute-sanitizer`` (that tool is closed on the round-1 GPU pool, so the
-run is only self-checked: compact stream vs plain CSR, export round trip, batch vs loop).
+as the target for ``compute-sanitizer`` (that tool is closed on the GPU pool, so the run is
+self-checked: every store is built twice -- CSR released / CSR kept -- and the two must agree on
+every result; export round trips, CSR-form constructors, batch vs loop).
 ``tests/test_gpu_coverage.py`` runs it.
 
 Covers: synthetic generator, COO build (sorted fast path and general sort), chunk plan,
@@ -22,22 +23,52 @@ from tadbit_b200 import ContactStore, HiC_data, SynthParams  # noqa: E402
 from tadbit_b200.batch import normalize_hic_batch  # noqa: E402
 
 
-def run_path(store, chroms, tag):
-    hic = HiC_data.from_store(store, chromosomes=chroms)
-    hic.filter_columns(silent=True)
-    hic.normalize_hic(iterations=20, max_dev=1e-5, silent=True)
-    hic.normalize_expected()
-    bias = hic.bias.to_array().copy()
-    store.set_option("rowsum", "csr")
-    hic.normalize_hic(iterations=20, max_dev=1e-5, silent=True)
-    store.set_option("rowsum", "compact")
-    rel = float(np.max(np.abs(hic.bias.to_array() - bias) / np.abs(bias)))
+def keep_csr(make):
+    """Build a store with TB_KEEP_CSR=1 (the CSR is not released after the build)."""
+    old = os.environ.get("TB_KEEP_CSR")
+    os.environ["TB_KEEP_CSR"] = "1"
+    try:
+        return make()
+    finally:
+        if old is None:
+            del os.environ["TB_KEEP_CSR"]
+        else:
+            os.environ["TB_KEEP_CSR"] = old
+
+
+def run_path(make, chroms, tag):
+    """The pipeline on the store `make()` builds (CSR released when every value is positive: every
+    kernel decodes the compact stream) and on its twin that kept the CSR; the two must agree --
+    integers exactly, ICE to 1e-12 (also against the CSR-walk row sum)."""
+    store, twin = make(), keep_csr(make)
+    assert twin.timing()["csr_resident"]
+    res = []
+    for st in (store, twin):
+        hic = HiC_data.from_store(st, chromosomes=chroms)
+        hic.filter_columns(silent=True)
+        hic.normalize_hic(iterations=20, max_dev=1e-5, silent=True)
+        hic.normalize_expected()
+        res.append((hic, hic.bias.to_array().copy()))
+    (hic, bias), (hic2, bias2) = res
+    assert hic.bads == hic2.bads and hic.expected == hic2.expected
+    assert len(hic.last_trace) == len(hic2.last_trace)
+    for x, y in zip(store.export_upper(), twin.export_upper()):
+        assert np.array_equal(x, y)
+    for x, y in zip(store.export_csr("full_rows"), twin.export_csr("full_rows")):
+        assert np.array_equal(x, y)
+    assert hic.sum() == hic2.sum()
+    twin.set_option("rowsum", "csr")
+    hic2.normalize_hic(iterations=20, max_dev=1e-5, silent=True)
+    twin.set_option("rowsum", "compact")
+    rel = max(float(np.max(np.abs(bias2 - bias) / np.abs(bias))),
+              float(np.max(np.abs(hic2.bias.to_array() - bias) / np.abs(bias))))
     lay = store.layout()
-    print("%-10s bads=%d passes=%d compact-vs-csr=%.1e enc=%s overflow=%d tile_cells=%d"
-          % (tag, len(hic.bads), len(hic.last_trace), rel, lay["encodings"],
+    print("%-10s csr_kept=%d bads=%d passes=%d compact-vs-csr=%.1e enc=%s overflow=%d tile_cells=%d"
+          % (tag, store.timing()["csr_resident"], len(hic.bads), len(hic.last_trace), rel, lay["encodings"],
              lay["overflow_cells"], lay["tile_cells"]))
     assert rel < 1e-12, rel
-    return hic
+    twin.close()
+    return hic, store
 
 
 def main():
@@ -48,14 +79,27 @@ def main():
     n = sum(chroms.values())
     p = SynthParams(seed=11, cis_scale=900.0, cis_alpha=1.08, trans_mean=0.03, vis_sigma=0.35,
                     low_frac=0.03, low_scale=0.02, empty_frac=0.01)
-    syn = ContactStore.synthetic(n, p, chromosomes=chroms)
-    run_path(syn, chroms, "synthetic")
+    _, syn = run_path(lambda: ContactStore.synthetic(n, p, chromosomes=chroms), chroms, "synthetic")
+    assert not syn.timing()["csr_resident"]
 
     # the same cells through the COO constructor: sorted input, then shuffled input with a few
     # huge values (S32 / S16 chunks, overflow cells of dense panels) and negative ones
     rows, cols, vals = syn.export_upper()
-    coo = ContactStore.from_coo(n, rows, cols, vals, chromosomes=chroms)
-    a = run_path(coo, chroms, "coo-sorted")
+    a, coo = run_path(lambda: ContactStore.from_coo(n, rows, cols, vals, chromosomes=chroms), chroms,
+                      "coo-sorted")
+    # the same cells in CSR form (upper triangle, 8 bytes per cell) and as whole rows
+    ptr, cc, vv = syn.export_csr("upper")
+    up = ContactStore.from_csr(n, ptr, cc, vv, form="upper", chromosomes=chroms)
+    for x, y in zip(up.export_upper(), (rows, cols, vals)):
+        assert np.array_equal(x, y)
+    fptr, fc, fv = syn.export_csr("full_rows")
+    assert fptr[-1] == syn.info()["nnz_full"]
+    full = ContactStore.from_csr(n, fptr, fc, fv, form="full_rows", chromosomes=chroms)
+    for x, y in zip(full.export_upper(), (rows, cols, vals)):
+        assert np.array_equal(x, y)
+    assert np.array_equal(full.ice(None, 20, 1e-5)[0], coo.ice(None, 20, 1e-5)[0])
+    up.close()
+    full.close()
     rng = np.random.RandomState(5)
     perm = rng.permutation(rows.size)
     v2 = vals.copy()
@@ -65,10 +109,20 @@ def main():
     v2[big[150:190]] = 1 << 20
     v2[big[190:195]] = -3
     v2[big[195:]] = 40000 + rng.randint(0, 1000, 5)
-    shuf = ContactStore.from_coo(n, rows[perm], cols[perm], v2[perm], chromosomes=chroms)
-    run_path(shuf, chroms, "coo-shuf")
+    _, shuf = run_path(lambda: ContactStore.from_coo(n, rows[perm], cols[perm], v2[perm], chromosomes=chroms),
+                       chroms, "coo-shuf")
+    assert shuf.timing()["csr_resident"]                 # negative values: the CSR stays
     r2, c2, w2 = shuf.export_upper()
     assert np.array_equal(r2, rows) and np.array_equal(c2, cols) and np.array_equal(w2, v2)
+    # the same with positive values only: CSR released, the visitors decode S16 / S32 chunks and the
+    # overflow lists of dense panels
+    v2p = np.abs(v2)
+    _, big = run_path(lambda: ContactStore.from_coo(n, rows[perm], cols[perm], v2p[perm], chromosomes=chroms),
+                      chroms, "coo-big")
+    assert not big.timing()["csr_resident"]
+    r2, c2, w2 = big.export_upper()
+    assert np.array_equal(r2, rows) and np.array_equal(c2, cols) and np.array_equal(w2, v2p)
+    big.close()
 
     # value boundaries of the encodings (D8 byte, tile cell 2^15, D16, int32) placed on dense rows,
     # and a few very long sparse rows among short ones (tiles split by their busiest warp)
@@ -89,18 +143,22 @@ def main():
     r3 = np.concatenate([rows, np.array(extra_r, dtype=np.int32)])
     c3 = np.concatenate([cols, np.array(extra_c, dtype=np.int32)])
     w3 = np.concatenate([v3, np.ones(len(extra_r), dtype=np.int32)])
-    skew = ContactStore.from_coo(n, r3, c3, w3, chromosomes=chroms)
-    run_path(skew, chroms, "edges+skew")
+    _, skew = run_path(lambda: ContactStore.from_coo(n, r3, c3, w3, chromosomes=chroms), chroms, "edges+skew")
     r4, c4, w4 = skew.export_upper()
     order = np.lexsort((c3, r3))
     assert np.array_equal(r4, r3[order]) and np.array_equal(c4, c3[order]) and np.array_equal(w4, w3[order])
+    w3p = np.where(w3 <= 0, 1, w3)                        # same boundaries without zeros / negatives
+    _, skewp = run_path(lambda: ContactStore.from_coo(n, r3, c3, w3p, chromosomes=chroms), chroms, "edges-pos")
+    assert not skewp.timing()["csr_resident"]
+    r4, c4, w4 = skewp.export_upper()
+    assert np.array_equal(r4, r3[order]) and np.array_equal(c4, c3[order]) and np.array_equal(w4, w3p[order])
+    skewp.close()
 
     # dense single chromosome (D8 / D16 panels)
     chrom1 = OrderedDict([("chr1", 5000)])
     pd = SynthParams(seed=3, cis_scale=3.0e4, cis_alpha=1.08, trans_mean=0.0, vis_sigma=0.35,
                      low_frac=0.02, low_scale=0.02, empty_frac=0.005)
-    dense = ContactStore.synthetic(5000, pd, chromosomes=chrom1)
-    run_path(dense, chrom1, "dense")
+    _, dense = run_path(lambda: ContactStore.synthetic(5000, pd, chromosomes=chrom1), chrom1, "dense")
 
     # batch of small matrices
     hics = []

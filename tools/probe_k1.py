@@ -37,15 +37,10 @@ def main():
     t0 = time.time()
     hic.normalize_hic(iterations=100, max_dev=1e-5, silent=True)
     t1 = time.time()
-    tm = store.ice_timing()
+    tm = store.timing()
     print("normalize_hic %.1f ms wall; loop %.1f ms, %d passes, K1 %.3f ms/pass"
           % ((t1 - t0) * 1e3, tm["loop_ms"], len(hic.last_trace),
              tm["rowsum_ms"] / max(tm["rowsum_launches"], 1)))
-    bias = hic.bias.to_array().copy()
-    store.set_option("rowsum", "csr")
-    hic.normalize_hic(iterations=100, max_dev=1e-5, silent=True)
-    import numpy as np
-    print("compact vs csr bias max rel diff %.2e" % float(np.max(np.abs(hic.bias.to_array() - bias) / np.abs(bias))))
 
 
 if __name__ == "__main__":
