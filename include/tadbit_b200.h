@@ -165,6 +165,15 @@ int tb_store_export_csr(const tb_store *s, int form, int64_t *nnz, int64_t *h_pt
  * (torch.distributed / MPI / files -- plumbing is the caller's). */
 int tb_comm_unique_id(uint8_t id_out[128]);
 int tb_comm_init(tb_store *s, int32_t rank, int32_t world, const uint8_t id[128]);
+/* A group that outlives the stores: creating the NCCL communicator costs most of a second, so a
+ * long-running process creates it once per GPU and attaches every matrix it normalises.
+ * tb_store_attach replaces tb_comm_init for such a store (the row-sum exchange buffers of the
+ * store are set up and mapped by its peers, a collective call: every rank attaches its shard).
+ * The group must be destroyed after the stores attached to it. */
+typedef struct tb_comm tb_comm;
+int tb_comm_create(int32_t rank, int32_t world, const uint8_t id[128], int device, tb_comm **out);
+int tb_comm_destroy(tb_comm *c);
+int tb_store_attach(tb_store *s, tb_comm *c);
 
 /* ---- K4: filter statistics ----------------------------------------------------- */
 /*

@@ -21,7 +21,8 @@
 
 static int nthreads_for(int threads) {
 #ifdef _OPENMP
-  return threads > 0 ? threads : omp_get_max_threads();
+  /* 0 = every core of the host, whatever OMP_NUM_THREADS says (torchrun sets it to 1) */
+  return threads > 0 ? threads : omp_get_num_procs();
 #else
   (void)threads;
   return 1;

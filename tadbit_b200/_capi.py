@@ -58,6 +58,9 @@ PROTOTYPES = {
     "tb_store_export_upper": ([_store, _i64p, _i32p, _i32p, _i32p], C.c_int),
     "tb_comm_unique_id": ([_u8p], C.c_int),
     "tb_comm_init": ([_store, C.c_int32, C.c_int32, _u8p], C.c_int),
+    "tb_comm_create": ([C.c_int32, C.c_int32, _u8p, C.c_int, C.POINTER(C.c_void_p)], C.c_int),
+    "tb_comm_destroy": ([C.c_void_p], C.c_int),
+    "tb_store_attach": ([_store, C.c_void_p], C.c_int),
     "tb_row_stats": ([_store, _i64p, _i64p], C.c_int),
     "tb_col_sums_masked": ([_store, _u8p, _i64p], C.c_int),
     "tb_ice": ([_store, _u8p, C.c_int32, C.c_double, _f64p, _f64p, C.POINTER(C.c_int32)], C.c_int),

@@ -408,6 +408,32 @@ int tb_comm_init(tb_store *s, int32_t rank, int32_t world, const uint8_t id[128]
   });
 }
 
+int tb_comm_create(int32_t rank, int32_t world, const uint8_t id[128], int device, tb_comm **out) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(out && (world == 1 || id), "null argument");
+    *out = nullptr;
+    DeviceGuard g(device);
+    *out = group_create(rank, world, id, device);
+    return TB_OK;
+  });
+}
+
+int tb_comm_destroy(tb_comm *c) {
+  if (!c) return TB_OK;
+  DeviceGuard g(c->device);
+  group_destroy(c);
+  return TB_OK;
+}
+
+int tb_store_attach(tb_store *s, tb_comm *c) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(s && c, "null argument");
+    DeviceGuard g(s->device);
+    store_attach(s, c, false);
+    return TB_OK;
+  });
+}
+
 int tb_row_stats(tb_store *s, int64_t *h_nnz_row, int64_t *h_row_sum) {
   return guarded([&]() -> int {
     TB_REQUIRE(s && h_nnz_row && h_row_sum, "null argument");

@@ -270,20 +270,26 @@ k_build_row_stats(const int64_t *__restrict__ rowptr, const int32_t *__restrict_
 // ---- export of the stored upper-triangle cells from the compact stream (visit.cuh) ----------
 struct CountUpperVisitor {
   static constexpr int kShared = 0;
+  static constexpr int kThreads = 256;
   int64_t rb;
   unsigned long long *cnt;            // [nrows]
   __device__ void begin(uint8_t *) {}
+  __device__ bool block(int64_t, int64_t, int64_t, int64_t) { return true; }
+  __device__ bool row(int64_t) { return true; }
   __device__ void cell(int64_t i, int64_t, int32_t) { atomicAdd(&cnt[i - rb], 1ull); }
   __device__ void end(uint8_t *) {}
 };
 struct PlaceUpperVisitor {
   static constexpr int kShared = 0;
+  static constexpr int kThreads = 256;
   int64_t rb;
   const int64_t *off;                 // [nrows] first output slot of each row
   unsigned long long *cursor;         // [nrows]
   uint64_t *key;                      // (local row << 32) | column
   int32_t *val;
   __device__ void begin(uint8_t *) {}
+  __device__ bool block(int64_t, int64_t, int64_t, int64_t) { return true; }
+  __device__ bool row(int64_t) { return true; }
   __device__ void cell(int64_t i, int64_t j, int32_t v) {
     const int64_t r = i - rb;
     const int64_t pos = off[r] + (int64_t)atomicAdd(&cursor[r], 1ull);
@@ -733,6 +739,9 @@ void setup_sections(tb_store *s) {
     for (int64_t i = s->chrom_offsets[c]; i < s->chrom_offsets[c + 1]; ++i) h[i] = c;
   s->chrom_of.alloc(N ? N : 1);
   if (N) TB_CUDA(cudaMemcpy(s->chrom_of.p, h.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice));
+  const size_t nsec = s->chrom_offsets.size() - 1;
+  s->chrom_end.alloc(nsec);
+  TB_CUDA(cudaMemcpy(s->chrom_end.p, s->chrom_offsets.data() + 1, nsec * sizeof(int64_t), cudaMemcpyHostToDevice));
 }
 
 // Cells of the owned rows, row-major sorted, into device arrays: the upper triangle (col >= row,

@@ -77,6 +77,7 @@ void check_abort(tb_store *s, int rc, const char *what) {
   if (a.CommAbort && s->comm) {
     a.CommAbort((NcclComm)s->comm);
     s->comm = nullptr;
+    if (s->group) s->group->nccl = nullptr;
   }
   check(rc, what);
 }
@@ -89,18 +90,57 @@ void comm_unique_id(uint8_t id[128]) {
   memcpy(id, u.internal, 128);
 }
 
-void comm_init(tb_store *s, int rank, int world, const uint8_t id[128]) {
-  TB_REQUIRE(world >= 1 && rank >= 0 && rank < world, "comm_init: bad rank/world");
+// A group = one NCCL communicator of this process (one rank per GPU).  Creating it costs most of a
+// second, so it can outlive the stores: a long-running process creates it once and attaches every
+// matrix it normalises (tb_comm_create / tb_store_attach); tb_comm_init is the one-shot form that
+// creates a group owned by the store.
+tb_comm *group_create(int rank, int world, const uint8_t id[128], int device) {
+  TB_REQUIRE(world >= 1 && rank >= 0 && rank < world, "comm: bad rank/world");
+  TB_REQUIRE(world <= kMaxPeers, "at most %d GPUs per group", kMaxPeers);
+  tb_comm *g = new tb_comm();
+  g->rank = rank;
+  g->world = world;
+  g->device = device;
+  if (world > 1) {
+    NcclUniqueId u;
+    memcpy(u.internal, id, 128);
+    NcclComm c = nullptr;
+    int rc = api().CommInitRank(&c, world, u, rank);
+    if (rc != 0) {
+      delete g;
+      check(rc, "CommInitRank");
+    }
+    g->nccl = c;
+  }
+  return g;
+}
+
+void group_destroy(tb_comm *g) {
+  if (!g) return;
+  if (g->nccl) api().CommDestroy((NcclComm)g->nccl);
+  delete g;
+}
+
+void store_attach(tb_store *s, tb_comm *g, bool owned) {
+  TB_REQUIRE(g && g->device == s->device, "attach: the group lives on another device");
   comm_destroy(s);
-  s->rank = rank;
-  s->world = world;
-  if (world == 1) return;
-  NcclUniqueId u;
-  memcpy(u.internal, id, 128);
-  NcclComm c = nullptr;
-  check(api().CommInitRank(&c, world, u, rank), "CommInitRank");
-  s->comm = c;
+  s->group = g;
+  s->owns_group = owned;
+  s->rank = g->rank;
+  s->world = g->world;
+  s->comm = g->nccl;
   exchange_setup(s);
+}
+
+void comm_init(tb_store *s, int rank, int world, const uint8_t id[128]) {
+  comm_destroy(s);
+  tb_comm *g = group_create(rank, world, id, s->device);
+  try {
+    store_attach(s, g, true);
+  } catch (...) {
+    if (s->group != g) group_destroy(g);
+    throw;
+  }
 }
 
 // Row-sum exchange buffers (common.cuh:PeerExchange).  Plain cudaMalloc memory (the stream-ordered
@@ -198,7 +238,9 @@ void comm_destroy(tb_store *s) {
     cudaStreamSynchronize(s->stream);
   }
   exchange_release(s);
-  if (s->comm) api().CommDestroy((NcclComm)s->comm);
+  if (s->group && s->owns_group) group_destroy(s->group);
+  s->group = nullptr;
+  s->owns_group = false;
   s->comm = nullptr;
   s->world = 1;
   s->rank = 0;

@@ -150,7 +150,12 @@ constexpr int kDenseWarps = TB_DENSE_WARPS;   // warps per CTA of k_rowsum_dense
 
 }  // namespace tb
 
-// The opaque handle of include/tadbit_b200.h.
+// The opaque handles of include/tadbit_b200.h.
+struct tb_comm {
+  void *nccl = nullptr;     // ncclComm_t (null when world == 1)
+  int rank = 0, world = 1, device = 0;
+};
+
 struct tb_store {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -162,6 +167,7 @@ struct tb_store {
   int32_t n_chrom = 0;
   std::vector<int64_t> chrom_offsets;     // n_chrom+1 (always >= 2 entries: one section if none given)
   tb::DevBuf<int32_t> chrom_of;           // [N] section id of each bin
+  tb::DevBuf<int64_t> chrom_end;          // [sections] one past the last bin of each section
   // CSR of the owned rows of the FULL symmetric matrix, columns ascending
   tb::DevBuf<int64_t> rowptr;             // [nrows+1]
   tb::DevBuf<int32_t> col, val;           // [nnz_full]
@@ -221,7 +227,9 @@ struct tb_store {
   tb::DevBuf<long long> row_nnz, row_sum; // [nrows] stored cells / sum of each owned full row (exact)
   tb::DevBuf<double> live;                // [nrows] cells with a good partner (stores that kept the CSR)
   // multi-GPU
-  void *comm = nullptr;
+  void *comm = nullptr;                   // the group's ncclComm_t
+  tb_comm *group = nullptr;
+  bool owns_group = false;                // created by tb_comm_init: destroyed with the store
   int rank = 0, world = 1;
   tb::PeerExchange px;                    // peer-mapped row-sum buffers (comm.cu)
   std::vector<cudaEvent_t> events;        // reused by every ICE call (kernels.cu)
@@ -273,6 +281,9 @@ void diag_sums(tb_store *s, const uint8_t *h_bad, int64_t ndiag, int64_t *h_sum_
 // comm.cu
 void comm_unique_id(uint8_t id[128]);
 void comm_init(tb_store *s, int rank, int world, const uint8_t id[128]);
+tb_comm *group_create(int rank, int world, const uint8_t id[128], int device);
+void group_destroy(tb_comm *g);
+void store_attach(tb_store *s, tb_comm *g, bool owned);
 void comm_destroy(tb_store *s);
 void exchange_setup(tb_store *s);          // (re)allocate the row-sum exchange buffers; maps the peers' when world > 1
 void exchange_release(tb_store *s);

@@ -95,13 +95,35 @@ struct TileSums {
   const double *partial;        // null when the store has no sparse tiles
   const int32_t *unit_of_rb;
 };
+// (loads issued four at a time, additions in unit order: the sum does not depend on the unrolling)
 __device__ __forceinline__ double tile_sum(const TileSums &ts, int64_t r) {
   if (!ts.partial) return 0.0;
   const int64_t rb = r / kTileRows;
+  const double *p = ts.partial + (r % kTileRows);
+  int32_t u = ts.unit_of_rb[rb];
+  const int32_t u1 = ts.unit_of_rb[rb + 1];
   double a = 0.0;
-  for (int32_t u = ts.unit_of_rb[rb]; u < ts.unit_of_rb[rb + 1]; ++u)
-    a += ts.partial[(int64_t)u * kTileRows + (r % kTileRows)];
+  for (; u + 4 <= u1; u += 4) {
+    const double v0 = p[(int64_t)u * kTileRows], v1 = p[(int64_t)(u + 1) * kTileRows];
+    const double v2 = p[(int64_t)(u + 2) * kTileRows], v3 = p[(int64_t)(u + 3) * kTileRows];
+    a += v0; a += v1; a += v2; a += v3;
+  }
+  for (; u < u1; ++u) a += p[(int64_t)u * kTileRows];
   return a;
+}
+
+// row sum of owned row r = its chunk partials in chunk order + its sparse-tile sums
+__device__ __forceinline__ double row_total(const double *__restrict__ pf, const int64_t *__restrict__ row_chunk,
+                                            const TileSums &ts, int64_t r) {
+  int64_t c = row_chunk[r];
+  const int64_t c1 = row_chunk[r + 1];
+  double a = 0.0;
+  for (; c + 4 <= c1; c += 4) {
+    const double v0 = pf[c], v1 = pf[c + 1], v2 = pf[c + 2], v3 = pf[c + 3];
+    a += v0; a += v1; a += v2; a += v3;
+  }
+  for (; c < c1; ++c) a += pf[c];
+  return a + tile_sum(ts, r);
 }
 
 // Rows kept by copy_matrix (normalize_hic.py:165-177): not bad, and at least one stored cell whose
@@ -126,9 +148,7 @@ __global__ void k_combine_f64(const double *__restrict__ pf, const int64_t *__re
   if (state && state->stopped) return;
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
        r += (int64_t)gridDim.x * blockDim.x) {
-    double a = 0.0;
-    for (int64_t c = row_chunk[r]; c < row_chunk[r + 1]; ++c) a += pf[c];
-    a += tile_sum(ts, r);
+    double a = row_total(pf, row_chunk, ts, r);
     out[rb + r] = mark ? mark_present(bad, live, rb + r, r, a) : a;
   }
 }
@@ -304,9 +324,7 @@ k_ice_reduce(double *__restrict__ s_full, const double *__restrict__ x,
        i += (int64_t)gridDim.x * blockDim.x) {
     double si;
     if (FUSED) {                       // one GPU: row i is local row i
-      double a = 0.0;
-      for (int64_t c = row_chunk[i]; c < row_chunk[i + 1]; ++c) a += pf[c];
-      a += tile_sum(ts, i);
+      double a = row_total(pf, row_chunk, ts, i);
       if (pass == 0) a = mark_present(bad, live, i, i, a);
       s_full[i] = si = a;
     } else {
@@ -377,7 +395,9 @@ __global__ void k_ice_update(const double *__restrict__ s_full, double *__restri
 //      grid-wide fold by the last CTA, loop decision;
 //   4. bias update B *= S / meanS, x = 1 / B.
 // The pass number is read from the device state, so the launch arguments never change.
-// The grid must be co-resident (one CTA per SM): CTAs wait for each other.
+// The grid must be co-resident: CTAs wait for each other.  It is sized from the occupancy the
+// runtime reports (exchange_grid), three CTAs of 512 threads per SM: the row phase is a chain of
+// dependent loads per row and needs the threads to cover their latency.
 // ---------------------------------------------------------------------------------
 constexpr int kXThreads = 512;
 constexpr unsigned long long kPeerTimeoutNs = 4000000000ull;    // 4 s: a peer that never arrives
@@ -404,7 +424,7 @@ __device__ __forceinline__ unsigned long long now_ns() {
   return t;
 }
 
-__global__ void __launch_bounds__(kXThreads, 1)
+__global__ void __launch_bounds__(kXThreads, 3)
 k_ice_exchange(PeerView pv, const double *__restrict__ pf, const int64_t *__restrict__ row_chunk,
                TileSums ts, int64_t nrows, int64_t rb, int64_t n, double *__restrict__ x,
                double *__restrict__ b, const uint8_t *__restrict__ bad, uint8_t *__restrict__ present,
@@ -421,9 +441,7 @@ k_ice_exchange(PeerView pv, const double *__restrict__ pf, const int64_t *__rest
   // 1. the rows of this rank -> every rank
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
        r += (int64_t)gridDim.x * blockDim.x) {
-    double a = 0.0;
-    for (int64_t c = row_chunk[r]; c < row_chunk[r + 1]; ++c) a += pf[c];
-    a += tile_sum(ts, r);
+    double a = row_total(pf, row_chunk, ts, r);
     if (pass == 0) a = mark_present(bad, live, rb + r, r, a);
     for (int q = 0; q < pv.world; ++q) pv.s[q][buf][rb + r] = a;
   }
@@ -572,22 +590,38 @@ k_sum_good_rows(const long long *__restrict__ v, const uint8_t *__restrict__ bad
 // (normalize_hic.py:271-283: only i is tested).  Visitor over the stored upper-triangle cells:
 // shared-memory histogram for d < 4096, L2 atomics beyond.  Integer sums: any order is exact.
 // ---------------------------------------------------------------------------------
-constexpr int kDiagShared = 4096;
+#ifndef TB_DIAG_SHARED
+#define TB_DIAG_SHARED 24576      // distances kept in shared memory (8 B each: 192 KB, one CTA per SM)
+#endif
+constexpr int kDiagShared = TB_DIAG_SHARED;
 
 struct DiagVisitor {
   static constexpr int kShared = kDiagShared * 8;
+  static constexpr int kThreads = kDiagShared > 4096 ? 1024 : 256;
   const uint8_t *bad;
   const int32_t *chrom_of;
+  const int64_t *chrom_end;       // [sections] one past the last bin of each section
   int64_t ndiag;
   unsigned long long *hist;
   unsigned long long *sh;
+  int64_t jend;                   // per thread: cells of the current row count up to this column
   __device__ void begin(uint8_t *smem) {
     sh = reinterpret_cast<unsigned long long *>(smem);
     for (int k = threadIdx.x; k < kDiagShared; k += blockDim.x) sh[k] = 0ull;
   }
+  // rows [i0, i1) reach at most to the end of the section of row i1 - 1
+  __device__ bool block(int64_t i0, int64_t i1, int64_t j0, int64_t j1) {
+    return j0 < chrom_end[chrom_of[i1 - 1 < ndiag_rows ? i1 - 1 : ndiag_rows - 1]];
+  }
+  __device__ bool row(int64_t i) {
+    if (bad[i]) return false;
+    jend = chrom_end[chrom_of[i]];
+    if (jend > i + ndiag) jend = i + ndiag;
+    return true;
+  }
   __device__ void cell(int64_t i, int64_t j, int32_t v) {
+    if (j >= jend) return;
     const int64_t d = j - i;
-    if (d >= ndiag || bad[i] || chrom_of[j] != chrom_of[i]) return;
     const unsigned long long u = (unsigned long long)(long long)v;
     if (d < kDiagShared) atomicAdd(&sh[d], u);
     else atomicAdd(&hist[d], u);
@@ -596,6 +630,7 @@ struct DiagVisitor {
     for (int k = threadIdx.x; k < kDiagShared && k < ndiag; k += blockDim.x)
       if (sh[k]) atomicAdd(&hist[k], sh[k]);
   }
+  int64_t ndiag_rows;             // number of bins (rows of a partial last tile lie beyond it)
 };
 
 inline int grid_1d(int64_t n, int threads, int sm_count, int per_sm = 8) {
@@ -668,9 +703,7 @@ k_seg_reduce(double *__restrict__ s_full, const double *__restrict__ x,
   double sum = 0.0, mn = INFINITY, mx = -INFINITY;
   long long cnt = 0;
   for (int64_t i = seg_off[k] + threadIdx.x; i < seg_off[k + 1]; i += blockDim.x) {
-    double a = 0.0;
-    for (int64_t c = row_chunk[i]; c < row_chunk[i + 1]; ++c) a += pf[c];
-    a += tile_sum(ts, i);
+    double a = row_total(pf, row_chunk, ts, i);
     s_full[i] = a;
     bool p;
     if (pass == 0) present[i] = p = !isnan(mark_present(bad, live, i, i, a));
@@ -819,6 +852,18 @@ void masked_row_sums(tb_store *s, long long *dst) {
   }
 }
 
+// CTAs of k_ice_exchange that are resident at the same time on this device
+int exchange_grid(const tb_store *s) {
+  static int per_sm[64] = {0};
+  int &v = per_sm[s->device & 63];
+  if (!v) {
+    TB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_ice_exchange, kXThreads, 0));
+    if (v < 1) v = 1;
+    if (v > 3) v = 3;
+  }
+  return v * s->sm_count;
+}
+
 cudaEvent_t ice_event(tb_store *s, size_t k) {
   while (s->events.size() <= k) {
     cudaEvent_t e;
@@ -924,7 +969,7 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
     rowsum_once(s, s->x.p, s->state.p);
     TB_CUDA(cudaEventRecord(ev(p, 1), st));
     if (fused) {
-      k_ice_exchange<<<s->sm_count, kXThreads, 0, st>>>(
+      k_ice_exchange<<<exchange_grid(s), kXThreads, 0, st>>>(
           s->px.view, s->partial_f.p, s->row_chunk.p, ts, s->nrows, s->row_begin, N, s->x.p, s->b.p,
           s->bad.p, s->present.p, live, iterations, max_dev, s->block_red.p, s->trace.p, s->state.p);
     } else if (s->world > 1) {
@@ -1084,6 +1129,9 @@ void diag_sums(tb_store *s, const uint8_t *h_bad, int64_t ndiag, int64_t *h_sum_
   DiagVisitor vis;
   vis.bad = s->bad.p;
   vis.chrom_of = s->chrom_of.p;
+  vis.chrom_end = s->chrom_end.p;
+  vis.ndiag_rows = s->nbins;
+  vis.jend = 0;
   vis.ndiag = ndiag;
   vis.hist = hist.p;
   vis.sh = nullptr;

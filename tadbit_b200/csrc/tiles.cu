@@ -42,6 +42,7 @@
 // sums, added per row in unit order by the combine step, so results do not depend on which CTA
 // ran which unit: deterministic, no atomics on the data path.
 #include "common.cuh"
+#include <stdlib.h>
 #include <algorithm>
 #include <numeric>
 #include <type_traits>
@@ -742,7 +743,9 @@ void build_tiles(tb_store *s) {
   }
   // ... but no smaller than a few times the fixed cost of a unit, unless that would leave SMs
   // without work (small or mostly dense matrices: one unit per SM then)
-  const double target = std::max(total_cost / (16.0 * s->sm_count),
+  double units_per_sm = 16.0;
+  if (const char *e = getenv("TB_TILE_UNITS_PER_SM")) units_per_sm = std::max(1.0, atof(e));
+  const double target = std::max(total_cost / (units_per_sm * s->sm_count),
                                  std::min(3.0 * (double)kTileFixedCost, total_cost / s->sm_count)) + 1.0;
   std::vector<int32_t> list, units, unit_of_rb(nrb + 1, 0);
   std::vector<double> cost;

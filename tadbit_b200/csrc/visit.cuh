@@ -14,8 +14,13 @@
 // and tiles that lie entirely left of it are skipped as a whole.
 //
 // A Visitor is copied to every thread and provides
-//     static constexpr int kShared;                 // bytes of shared memory per CTA
+//     static constexpr int kShared, kThreads;       // shared memory per CTA, threads per CTA
 //     __device__ void begin(uint8_t *smem);         // all threads, before the walk
+//     __device__ bool block(int64_t i0, int64_t i1, int64_t j0, int64_t j1);
+//                                                   // can a cell of rows [i0, i1) x columns [j0, j1)
+//                                                   // matter?  false skips a whole panel / tile
+//     __device__ bool row(int64_t i);               // once per thread and row before its cells:
+//                                                   // per-row state; false skips the row
 //     __device__ void cell(int64_t i, int64_t j, int32_t v);
 //     __device__ void end(uint8_t *smem);           // all threads, after the walk
 #pragma once
@@ -76,7 +81,7 @@ __device__ __forceinline__ int32_t dense_slot(int32_t p) {
 }
 
 template <typename V>
-__global__ void __launch_bounds__(256) k_visit_chunks(VisitSrc src, V vis) {
+__global__ void __launch_bounds__(1024) k_visit_chunks(VisitSrc src, V vis) {
   extern __shared__ __align__(16) uint8_t vsm[];
   vis.begin(vsm);
   __syncthreads();
@@ -90,6 +95,9 @@ __global__ void __launch_bounds__(256) k_visit_chunks(VisitSrc src, V vis) {
     const int64_t gi = src.row_begin + src.chunk_row[c];
     const int64_t g = src.full_rows ? -1 : gi;          // cells with column >= g are visited
     const uint8_t *p = src.enc_data + src.enc_off[c];
+    if (enc >= ENC_D32 && ((int64_t)d.x + d.y <= g || !vis.block(gi, gi + 1, d.x, (int64_t)d.x + d.y)))
+      continue;                                         // panel left of the diagonal, or of no interest
+    if (!vis.row(gi)) continue;
     if (enc == ENC_S32) {
       const int2 *w = reinterpret_cast<const int2 *>(p);
       for (int k = lane; k < d.y; k += 32) {
@@ -105,7 +113,6 @@ __global__ void __launch_bounds__(256) k_visit_chunks(VisitSrc src, V vis) {
       }
     } else {
       const int c0 = d.x, nslots = d.y, novf = d.z >> 8;
-      if ((int64_t)c0 + nslots <= g) continue;          // the whole panel lies left of the diagonal
       const int width = enc == ENC_D32 ? 4 : (enc == ENC_D16 ? 2 : 1);
       const int per = 16 / width;                       // values per 16-byte word
       const int nwords = nslots / per;
@@ -139,7 +146,7 @@ __global__ void __launch_bounds__(256) k_visit_chunks(VisitSrc src, V vis) {
 
 // one warp per (tile, slice): lane l walks the cells of sorted row 32 * slice + l
 template <typename V>
-__global__ void __launch_bounds__(256) k_visit_tiles(VisitSrc src, V vis) {
+__global__ void __launch_bounds__(1024) k_visit_tiles(VisitSrc src, V vis) {
   extern __shared__ __align__(16) uint8_t vsm[];
   vis.begin(vsm);
   __syncthreads();
@@ -153,13 +160,16 @@ __global__ void __launch_bounds__(256) k_visit_tiles(VisitSrc src, V vis) {
     const int64_t rb = tile / src.t_nwin, w = tile % src.t_nwin;
     const int64_t wlo = w * kTileCols, g0 = src.row_begin + rb * kTileRows;
     if (!src.full_rows && wlo + kTileCols <= g0) continue;     // tile left of the diagonal
+    if (!vis.block(g0, g0 + kTileRows, wlo, wlo + kTileCols)) continue;
     const uint32_t *st = src.t_slice + tile * kVisitSliceTab + 2 * sl;
     const uint32_t o1 = st[0], o2 = st[1], o3 = st[2];
     if (o1 == o3) continue;
     const int64_t gi = g0 + src.t_perm[tile * kTileRows + sl * 32 + lane];
     const int64_t g = src.full_rows ? -1 : gi;
+    const bool mine = gi < src.nbins && vis.row(gi);    // (rows of a partial last tile hold no cells)
     const uint4 *base = reinterpret_cast<const uint4 *>(src.t_cells + src.t_off[tile] * 128);
     for (uint32_t blk = o1; blk < o2; ++blk) {          // ones: 8 column offsets per lane and block
+      if (!mine) break;
       const uint4 q = base[(size_t)blk * 32 + lane];
       const uint32_t u[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
@@ -171,6 +181,7 @@ __global__ void __launch_bounds__(256) k_visit_tiles(VisitSrc src, V vis) {
       }
     }
     for (uint32_t blk = o2; blk < o3; ++blk) {          // general: 4 cells per lane and block
+      if (!mine) break;
       const uint4 q = base[(size_t)blk * 32 + lane];
       const uint32_t u[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
@@ -187,7 +198,7 @@ __global__ void __launch_bounds__(256) k_visit_tiles(VisitSrc src, V vis) {
 }
 
 template <typename V>
-__global__ void __launch_bounds__(256) k_visit_csr(VisitSrc src, V vis) {
+__global__ void __launch_bounds__(1024) k_visit_csr(VisitSrc src, V vis) {
   extern __shared__ __align__(16) uint8_t vsm[];
   vis.begin(vsm);
   __syncthreads();
@@ -199,6 +210,7 @@ __global__ void __launch_bounds__(256) k_visit_csr(VisitSrc src, V vis) {
     const int64_t g = src.full_rows ? -1 : gi;
     const int64_t beg = src.chunk_beg[c], end = src.chunk_beg[c + 1];
     if (src.col[end - 1] < g) continue;                 // chunk entirely left of the diagonal
+    if (!vis.row(gi)) continue;
     for (int64_t k = beg + lane; k < end; k += 32) {
       const int64_t j = src.col[k];
       if (j >= g) vis.cell(gi, j, src.val[k]);
@@ -209,23 +221,32 @@ __global__ void __launch_bounds__(256) k_visit_csr(VisitSrc src, V vis) {
 }
 
 // Run `vis` over every stored upper-triangle cell of the store's rows (stream s->stream).
+// V::kThreads threads per CTA; as many CTAs as fit an SM with V::kShared bytes of shared memory.
+template <typename V, typename K>
+int visit_grid(const tb_store *s, K kernel, int64_t warps_wanted) {
+  if (V::kShared > 48 * 1024)
+    TB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V::kShared));
+  int per_sm = 1;
+  TB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, V::kThreads, V::kShared));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t need = (warps_wanted * 32 + V::kThreads - 1) / V::kThreads;
+  const int64_t cap = (int64_t)s->sm_count * per_sm;
+  return (int)(need < cap ? (need < 1 ? 1 : need) : cap);
+}
+
 template <typename V>
 void visit_upper(const tb_store *s, const V &vis, bool full_rows = false) {
   VisitSrc src = visit_src(s);
   src.full_rows = full_rows;
   if (s->nchunks == 0) return;
-  int64_t need = (s->nchunks + 7) / 8, cap = (int64_t)s->sm_count * 8;
-  const int grid = (int)(need < cap ? (need < 1 ? 1 : need) : cap);
   if (s->csr_resident) {
-    k_visit_csr<V><<<grid, 256, V::kShared, s->stream>>>(src, vis);
+    k_visit_csr<V><<<visit_grid<V>(s, k_visit_csr<V>, s->nchunks), V::kThreads, V::kShared, s->stream>>>(src, vis);
     return;
   }
-  k_visit_chunks<V><<<grid, 256, V::kShared, s->stream>>>(src, vis);
+  k_visit_chunks<V><<<visit_grid<V>(s, k_visit_chunks<V>, s->nchunks), V::kThreads, V::kShared, s->stream>>>(src, vis);
   if (src.t_nrb) {
     const int64_t items = src.t_nrb * src.t_nwin * kVisitSlices;
-    need = (items + 7) / 8;
-    const int tg = (int)(need < cap ? (need < 1 ? 1 : need) : cap);
-    k_visit_tiles<V><<<tg, 256, V::kShared, s->stream>>>(src, vis);
+    k_visit_tiles<V><<<visit_grid<V>(s, k_visit_tiles<V>, items), V::kThreads, V::kShared, s->stream>>>(src, vis);
   }
 }
 

@@ -23,6 +23,28 @@ def _offsets(size, chromosomes):
     return len(sizes), offs
 
 
+class CommGroup(object):
+    """The GPUs that hold the row blocks of one matrix (one process per GPU).  Creating the group
+    sets up an NCCL communicator (slow); create it once and ``attach`` every sharded store."""
+
+    def __init__(self, rank, world, unique_id, device=0):
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        self._h = C.c_void_p()
+        self.rank, self.world = int(rank), int(world)
+        check(lib().tb_comm_create(rank, world, ptr(uid, C.c_uint8), device, C.byref(self._h)))
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            lib().tb_comm_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class ContactStore(object):
     def __init__(self, handle, size):
         self._h = handle
@@ -173,6 +195,11 @@ class ContactStore(object):
         check(lib().tb_comm_unique_id(ptr(buf, C.c_uint8)))
         return buf
 
+    def attach(self, group):
+        """Join a :class:`CommGroup` (a collective call: every rank attaches its shard)."""
+        check(lib().tb_store_attach(self._h, group._h))
+        self._group = group                      # keep it alive as long as the store
+
     def comm_init(self, rank, world, unique_id):
         uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
         check(lib().tb_comm_init(self._h, rank, world, ptr(uid, C.c_uint8)))
@@ -263,4 +290,4 @@ class ContactStore(object):
         return out
 
 
-__all__ = ["ContactStore", "SynthParams"]
+__all__ = ["ContactStore", "CommGroup", "SynthParams"]
