@@ -262,6 +262,29 @@ int tb_norm_sum(tb_store *s, const double *h_bias, const uint8_t *h_bad, double 
  */
 int tb_diag_sums(tb_store *s, const uint8_t *h_bad, int64_t ndiag, int64_t *h_sum_d);
 
+/* ---- consumers of the biases (N1, N2) ---------------------------------------- */
+/* N1 -- Experiment.normalize_hic / get_hic_zscores / tadmaths.zscore
+ * (_pytadbit/experiment.py:737-743, :751-799; _pytadbit/utils/tadmaths.py:94-172).
+ * Over the stored pairs i < j between bins that are not bad, value = count (h_bias NULL) or
+ * count / bias[i] / bias[j]: out[0] = number of pairs with a non-zero value, out[1] = the smallest
+ * such value, out[2] = sum of log10(value), out[3] = sum of (log10(value) - center)^2.  Pairs with
+ * no stored contact are not visited (the caller accounts for them in closed form). */
+int tb_pair_stats(tb_store *s, const double *h_bias, const uint8_t *h_bad, double center,
+                  double out[4]);
+/* The same pairs, row-major: h_val = value, or (log10(value) - mean) / std when zscored.  Call with
+ * NULL arrays to learn *n.  A row-sharded store returns the pairs of its own rows. */
+int tb_pair_values(tb_store *s, const double *h_bias, const uint8_t *h_bad, int32_t zscored,
+                   double mean, double std, int64_t *n, int32_t *h_row, int32_t *h_col,
+                   double *h_val);
+/* N2 -- the reductions `tadbit normalize` makes once it has the biases
+ * (_pytadbit/tools/tadbit_normalize.py:963-1107; sum_dec_matrix :1110-1136, get_cis_perc :1139-1152).
+ * h_bias[nbins] (NaN = bad column, as that tool marks them), h_bad optional.
+ * h_nrm / h_raw [nbins]: entry (first bin of section c) + d = sum over the cells (i, i + d) inside
+ * section c, both bins good, of count / bias[i] / bias[j] and of count (diagonal included).
+ * out_cis_total[0..1] = normalised interactions inside sections / in total, off-diagonal pairs. */
+int tb_decay_sums(tb_store *s, const double *h_bias, const uint8_t *h_bad, double *h_nrm,
+                  int64_t *h_raw, double out_cis_total[2]);
+
 #ifdef __cplusplus
 }
 #endif

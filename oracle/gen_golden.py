@@ -216,6 +216,197 @@ def reference_known_answers(ns):
     return out
 
 
+def _zscore_arrays(exp):
+    out = []
+    for k1 in exp._zscores:
+        for k2, v in exp._zscores[k1].items():
+            out.append((int(k1), int(k2), float(v)))
+    out.sort()
+    a = np.array(out, dtype=np.float64).reshape(-1, 3)
+    return a[:, 0].astype(np.int32), a[:, 1].astype(np.int32), a[:, 2]
+
+
+def reference_pair_cases(ns):
+    """N1: interaction pairs and z-scores from the UNMODIFIED ``Experiment`` class
+    (_pytadbit/experiment.py:704-799, utils/tadmaths.py:94-172) on a reference fixture and on a
+    seeded synthetic matrix: filter_columns -> normalize_hic -> get_hic_zscores in its variants."""
+    ref_shim._stub("pytadbit.modelling.structuralmodels", StructuralModels=object)
+    from pytadbit.experiment import Experiment
+    rng = np.random.default_rng(77)
+    cases = {}
+    base = os.path.join(ns.root, "test", "20Kb", "chrT")
+    with contextlib.redirect_stderr(io.StringIO()), contextlib.redirect_stdout(io.StringIO()):
+        exp = Experiment("exp1", 20000, hic_data=os.path.join(base, "chrT_D.tsv"))
+        exp.load_hic_data(os.path.join(base, "chrT_A.tsv"), silent=True)
+        cases["chrT_20Kb_A"] = (exp, dict(iterations=0, max_dev=0.1, factor=1))
+        n, r, c, v = synth_dense(rng, [70], a=500.0, low_frac=0.1, empty_frac=0.04)
+        hic = build_reference(ns, n, r, c, v)
+        exp2 = Experiment("synth", 10000)
+        exp2.hic_data = [hic]
+        exp2.size = n
+        cases["pairs_synth_70"] = (exp2, dict(iterations=20, max_dev=1e-4, factor=1))
+    index = []
+    for name, (exp, kw) in cases.items():
+        print("pairs", name, file=sys.stderr)
+        hic = exp.hic_data[0]
+        r, c, v = upper_store(hic)
+        rec = OrderedDict(name=name, size=len(hic), normalize=kw)
+        with contextlib.redirect_stderr(io.StringIO()), contextlib.redirect_stdout(io.StringIO()), \
+                np.errstate(all="ignore"):
+            exp.filter_columns(silent=True)
+            exp.normalize_hic(silent=True, **kw)
+            rec["zeros"] = sorted(int(k) for k in exp._zeros)
+            rec["bias"] = [float(exp.hic_data[0].bias[i]) for i in range(exp.size)]
+            arrays = {}
+            for tag, opts in (("z", dict()), ("norm", dict(zscored=False)),
+                              ("raw", dict(normalized=False, zscored=False)),
+                              ("rawz", dict(normalized=False)),
+                              ("z_keep0", dict(remove_zeros=False)),
+                              ("norm_keep0", dict(zscored=False, remove_zeros=False))):
+                exp.get_hic_zscores(**opts)
+                arrays[tag] = _zscore_arrays(exp)
+            # written pairs, as test_11 does (normalised values, default arguments of the writer)
+            import tempfile
+            exp.get_hic_zscores(zscored=False)
+            with tempfile.TemporaryDirectory() as tmp:
+                fname = os.path.join(tmp, "pairs.tsv")
+                exp.write_interaction_pairs(fname)
+                rec["pair_lines"] = open(fname).read().splitlines()
+        np.savez_compressed(os.path.join(OUT, "pairs_" + name + ".npz"), size=len(hic),
+                            rows=r.astype(np.int32), cols=c.astype(np.int32), vals=v,
+                            **dict(("%s_%s" % (t, k), a) for t, arr in arrays.items()
+                                   for k, a in zip(("i", "j", "v"), arr)))
+        with open(os.path.join(OUT, "pairs_" + name + ".json"), "w") as fh:
+            json.dump(rec, fh)
+        index.append(name)
+    return index
+
+
+class _NowPool(object):
+    """Stand-in for multiprocessing.Pool: the reference's tail farms its three helper functions out
+    to worker processes; here they run in place (same functions, same arguments)."""
+
+    class _Res(object):
+        def __init__(self, value):
+            self._v = value
+
+        def get(self):
+            return self._v
+
+        def ready(self):
+            return True
+
+    def __init__(self, *a, **k):
+        pass
+
+    def apply_async(self, fn, args=()):
+        return self._Res(fn(*args))
+
+    def close(self):
+        pass
+
+    def join(self):
+        pass
+
+
+def reference_decay_tail(root):
+    """Compile, UNMODIFIED, the lines of _pytadbit/tools/tadbit_normalize.py that follow the
+    computation of the biases inside read_bam (from 'Getting sum of normalized bins' to its return
+    statement) together with sum_dec_matrix / get_cis_perc / sum_nrm_matrix, as a function of the
+    variables those lines read.  The module itself cannot be imported here (pysam, matplotlib,
+    sqlite helpers ...); only the process pool is substituted (_NowPool)."""
+    import pickle
+    import types
+    src = open(os.path.join(root, "_pytadbit", "tools", "tadbit_normalize.py")).read().splitlines()
+    first = next(i for i, l in enumerate(src) if "Getting sum of normalized bins" in l)
+    last = next(i for i, l in enumerate(src) if l.strip() == "return biases, nrmdec, badcol, raw_cisprc, norm_cisprc")
+    h0 = next(i for i, l in enumerate(src) if l.startswith("def sum_dec_matrix"))
+    h1 = next(i for i, l in enumerate(src) if l.startswith("class SmartFormatter"))
+    code = ("def _tail(outdir, regs, begs, ends, extra_out, biases, ncpus, size, factor, normalize_only, "
+            "badcol, bins, section_pos, sections, raw_cisprc):\n" + "\n".join(src[first:last + 1]) +
+            "\n\n" + "\n".join(src[h0:h1]) + "\n")
+    mu = types.SimpleNamespace(Pool=_NowPool)
+    space = dict(path=os.path, load=pickle.load, system=os.system, nansum=np.nansum, mu=mu,
+                 printime=lambda msg: None, print_progress=lambda procs: None, print=lambda *a, **k: None)
+    exec(compile(code, "tadbit_normalize.py[%d:%d]" % (first + 1, last + 1), "exec"), space)
+    return space["_tail"], (first + 1, last + 1)
+
+
+def reference_decay_cases(ns):
+    """N2: the tail of `tadbit normalize` (rescaled biases, cis percentage, per-chromosome decay)
+    from the reference's own lines on seeded multi-chromosome matrices."""
+    import pickle
+    import tempfile
+    tail, lines = reference_decay_tail(ns.root)
+    rng = np.random.default_rng(4242)
+    index = []
+    for name, sizes, kind, factor in (("decay_3chrom_vanilla", [90, 60, 35], "vanilla", 1),
+                                      ("decay_2chrom_ice", [120, 45], "ice", 1),
+                                      ("decay_sparse_factor2", [150, 80], "vanilla_sparse", 2),
+                                      ("decay_tiny", [12, 9], "vanilla", 1)):
+        print("decay", name, file=sys.stderr)
+        if kind == "vanilla_sparse":
+            n, r, c, v = synth_dense(rng, sizes, a=6.0, trans=0.004, low_frac=0.1, empty_frac=0.05)
+        else:
+            n, r, c, v = synth_dense(rng, sizes, a=400.0, trans=0.3, low_frac=0.08, empty_frac=0.04)
+        names = ["chr%d" % (k + 1) for k in range(len(sizes))]
+        hic = build_reference(ns, n, r, c, v, sizes, names)
+        sections = OrderedDict(zip(names, sizes))
+        section_pos, total = {}, 0
+        for crm in sections:
+            section_pos[crm] = (total, total + sections[crm])
+            total += sections[crm]
+        bins = [(crm, i) for crm in sections for i in range(sections[crm])]
+        with contextlib.redirect_stderr(io.StringIO()), contextlib.redirect_stdout(io.StringIO()):
+            hic.filter_columns(silent=True)
+            badcol = dict(hic.bads)
+            # a bad column on a chromosome border exercises the inclusive test of the cell counts
+            badcol[section_pos[names[1]][0]] = True
+            if kind == "ice":
+                hic.bads = dict(badcol)
+                hic.normalize_hic(iterations=100, max_dev=1e-6, silent=True)
+                biases = dict((k, float(hic.bias[k])) for k in range(n))
+            else:                                       # Vanilla, as read_bam computes it (:901-906)
+                tot = np.zeros(n)
+                np.add.at(tot, r, v)
+                np.add.at(tot, c[r != c], v[r != c])
+                col = [float("nan") if k in badcol else float(tot[k]) for k in range(n)]
+                mean_col = np.nanmean(col)
+                biases = dict((k, b / mean_col * mean_col ** 0.5) for k, b in enumerate(col))
+        dico = {}
+        for a, b, x in zip(r.tolist(), c.tolist(), v.tolist()):
+            dico[(a, b)] = x
+            dico[(b, a)] = x
+        with tempfile.TemporaryDirectory() as tmp:
+            # two regions: the cells are split by their first bin, as read_bam's per-region fetches do
+            cut = section_pos[names[1]][0]
+            regs, begs, ends = [names[0], names[1]], [0, 0], [10, 20]
+            parts = [dict((k, x) for k, x in dico.items() if k[0] < cut),
+                     dict((k, x) for k, x in dico.items() if k[0] >= cut)]
+            for reg, b0, e0, part in zip(regs, begs, ends, parts):
+                with open(os.path.join(tmp, "tmp_%s:%d-%d_%s.pickle" % (reg, b0, e0, "x")), "wb") as fh:
+                    pickle.dump(part, fh)
+            with np.errstate(all="ignore"), contextlib.redirect_stdout(io.StringIO()):
+                out_b, nrmdec, out_bad, raw_c, norm_c = tail(
+                    tmp, regs, begs, ends, "x", dict(biases), 1, n, factor, False, dict(badcol), bins,
+                    section_pos, sections, 0.5)
+        rec = OrderedDict(
+            name=name, size=n, chromosomes=list(sections.items()), factor=factor,
+            reference_lines="_pytadbit/tools/tadbit_normalize.py:%d-%d" % lines,
+            badcol=sorted(int(k) for k in badcol),
+            biases_in=[None if np.isnan(biases[k]) else float(biases[k]) for k in range(n)],
+            biases_out=[None if np.isnan(out_b[k]) else float(out_b[k]) for k in range(n)],
+            norm_cisprc=float(norm_c),
+            decay=OrderedDict((crm, [[int(k), float(x)] for k, x in sorted(nrmdec[crm].items())])
+                              for crm in sections))
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), size=n, rows=r.astype(np.int32),
+                            cols=c.astype(np.int32), vals=v)
+        with open(os.path.join(OUT, name + ".json"), "w") as fh:
+            json.dump(rec, fh)
+        index.append(name)
+    return index
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_shim.load()
@@ -295,9 +486,11 @@ def main():
     index.append("all_zero_30")
 
     reference_known_answers(ns)
+    pair_cases = reference_pair_cases(ns)
+    decay_cases = reference_decay_cases(ns)
 
     with open(os.path.join(OUT, "INDEX.json"), "w") as fh:
-        json.dump(dict(cases=index, numpy=np.__version__,
+        json.dump(dict(cases=index, pair_cases=pair_cases, decay_cases=decay_cases, numpy=np.__version__,
                        generator="oracle/gen_golden.py", reference="TADbit v1.1 (unmodified, via oracle/ref_shim.py)"), fh, indent=1)
 
 

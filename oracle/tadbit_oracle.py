@@ -660,3 +660,143 @@ def fast_expected(m, bads=None, signal_to_noise=0.05, inter_chrom=False, threads
         dd = np.arange(span)
         cnt_d[:span] += good_before[end - dd] - good_before[beg]
     return pool_diagonals([int(v) for v in sum_d], cnt_d, size, min_n)
+
+
+# --------------------------------------------------------------------------
+# N1: interaction pairs, normalised values and z-scores
+# (_pytadbit/experiment.py:737-743, :751-799; _pytadbit/utils/tadmaths.py:94-172)
+# --------------------------------------------------------------------------
+def pair_values(m, bias=None, bads=None):
+    """The stored pairs i < j between columns that are not bad, row-major:
+    (rows, cols, values) with values = count, or float(count) / bias[i] / bias[j]
+    (experiment.py:739-741) when ``bias`` is given.  Pairs whose value is 0 are left out
+    (``remove_zeros``, experiment.py:774-777)."""
+    bad = _bad_mask(m.size, bads)
+    keep = (m.rows < m.cols) & ~bad[m.rows] & ~bad[m.cols] & (m.vals != 0)
+    r, c, v = m.rows[keep], m.cols[keep], m.vals[keep]
+    if bias is not None:
+        bias = np.asarray(bias, dtype=np.float64)
+        v = v.astype(np.float64) / bias[r] / bias[c]
+    return r, c, v
+
+
+def pair_zscores(m, bias=None, bads=None):
+    """tadmaths.zscore over those pairs (:142-172): log10, then (x - mean) / std with numpy's
+    population standard deviation.  Returns (rows, cols, z, (n, min, mean, std))."""
+    r, c, v = pair_values(m, bias, bads)
+    if v.size == 0:
+        raise ValueError('min() arg is an empty sequence')            # nozero_log :96
+    logs = np.log10(v.astype(np.float64))
+    mean_v, std_v = np.mean(logs), np.std(logs)
+    return r, c, (logs - mean_v) / std_v, (v.size, float(v.min()), float(mean_v), float(std_v))
+
+
+# --------------------------------------------------------------------------
+# N2: rescaled biases, cis percentage and per-chromosome decay of `tadbit normalize`
+# (_pytadbit/tools/tadbit_normalize.py:963-1107, helpers :1110-1159)
+# --------------------------------------------------------------------------
+def decay_sums(m, bias, bads=None):
+    """sum_dec_matrix (:1110-1136) and get_cis_perc (:1139-1152) over the upper store: per section
+    and distance the sums of count / bias_i / bias_j and of count over cells between good bins
+    (arrays indexed first bin of the section + distance), and (cis, total) normalised sums of the
+    off-diagonal pairs."""
+    size = m.size
+    bias = np.asarray(bias, dtype=np.float64)
+    bad = _bad_mask(size, bads) | np.isnan(bias)
+    chrom_of = np.empty(size, dtype=np.int64)
+    beg_of = np.empty(size, dtype=np.int64)
+    for n, (beg, end) in enumerate(m.section_pos.values()):
+        chrom_of[beg:end] = n
+        beg_of[beg:end] = beg
+    keep = ~bad[m.rows] & ~bad[m.cols]
+    r, c, v = m.rows[keep], m.cols[keep], m.vals[keep]
+    x = v.astype(np.float64) / bias[r] / bias[c]
+    same = chrom_of[r] == chrom_of[c]
+    off = r != c
+    total = float(np.sum(x[off]))
+    cis = float(np.sum(x[off & same]))
+    nrm = np.zeros(size)
+    raw = np.zeros(size, dtype=np.int64)
+    idx = beg_of[r[same]] + (c[same] - r[same])
+    np.add.at(nrm, idx, x[same])
+    np.add.at(raw, idx, v[same].astype(np.int64))
+    return nrm, raw, (cis, total)
+
+
+def decay_cell_counts(section_pos, badcol):
+    """ndiags (:1044-1072), literally: per chromosome and distance the cells of the diagonal minus
+    the ones that touch a bad column."""
+    out = OrderedDict()
+    for crm, (beg_chr, end_chr) in section_pos.items():
+        chr_size = end_chr - beg_chr
+        nd = dict((k, 0) for k in range(chr_size))
+        thesebads = [b for b in badcol if beg_chr <= b <= end_chr]
+        for dist in range(1, chr_size):
+            nd[dist] += chr_size - dist
+            bad_diag = set()
+            maxp = end_chr - dist
+            minp = beg_chr + dist
+            for b in thesebads:
+                if b < maxp:
+                    bad_diag.add(b)
+                if b >= minp:
+                    bad_diag.add(b - dist)
+            nd[dist] -= len(bad_diag)
+        if chr_size:
+            nd[0] += chr_size - sum(beg_chr <= b < end_chr for b in thesebads)
+        out[crm] = nd
+    return out
+
+
+def rescale_and_decay(m, biases, badcol, factor=1, signal_to_noise=0.05):
+    """The tail of read_bam (:963-1107) -> (biases array, decay {crm: {dist: value}}, norm_cisprc)."""
+    size = m.size
+    b = np.asarray(biases, dtype=np.float64)
+    nan = np.isnan(b)
+    w = np.where(m.rows == m.cols, 1.0, 2.0)                           # both triangles, diagonal once
+    with np.errstate(invalid='ignore'):
+        sumnrm = np.nansum(w * (m.vals.astype(np.float64) / b[m.rows] / b[m.cols]))   # sum_nrm_matrix
+    target = (sumnrm / float(size * size * factor)) ** 0.5
+    b = b * target
+    nrm, raw, (cis, total) = decay_sums(m, b, badcol)
+    norm_cisprc = float(cis) / total
+    ndiags = decay_cell_counts(m.section_pos, badcol)
+    min_n = signal_to_noise ** -2.
+    decay = {}
+    for crm, (beg, end) in m.section_pos.items():
+        dec = dict((k, float(nrm[beg + k])) for k in range(end - beg) if raw[beg + k] != 0)
+        rawd = dict((k, int(raw[beg + k])) for k in range(end - beg) if raw[beg + k] != 0)
+        tmpdec = 0
+        tmpsum = 0
+        ndiag = 0
+        val = 0
+        previous = []
+        for k in ndiags[crm]:
+            tmpdec += dec.get(k, 0.)
+            tmpsum += rawd.get(k, 0.)
+            previous.append(k)
+            if tmpsum > min_n:
+                ndiag = sum(ndiags[crm][q] for q in previous)
+                val = tmpdec
+                try:
+                    ratio = val / ndiag
+                    for q in previous:
+                        dec[q] = ratio
+                except ZeroDivisionError:
+                    pass
+                previous = []
+                tmpdec = 0
+                tmpsum = 0
+        if len(previous) == len(ndiags[crm]):
+            dec = {}
+        elif tmpsum < min_n:
+            ndiag += sum(ndiags[crm][q] for q in previous)
+            val += tmpdec
+            try:
+                ratio = val / ndiag
+                for q in previous:
+                    dec[q] = ratio
+            except ZeroDivisionError:
+                pass
+        decay[crm] = dec
+    return b, decay, norm_cisprc

@@ -74,6 +74,10 @@ PROTOTYPES = {
     "tb_last_timing": ([_store, _f64p], C.c_int),
     "tb_norm_sum": ([_store, _f64p, _u8p, _f64p], C.c_int),
     "tb_diag_sums": ([_store, _u8p, C.c_int64, _i64p], C.c_int),
+    "tb_pair_stats": ([_store, _f64p, _u8p, C.c_double, _f64p], C.c_int),
+    "tb_pair_values": ([_store, _f64p, _u8p, C.c_int32, C.c_double, C.c_double, _i64p, _i32p, _i32p,
+                        _f64p], C.c_int),
+    "tb_decay_sums": ([_store, _f64p, _u8p, _f64p, _i64p, _f64p], C.c_int),
 }
 
 _lib = None

@@ -511,6 +511,36 @@ int tb_norm_sum(tb_store *s, const double *h_bias, const uint8_t *h_bad, double 
   });
 }
 
+int tb_pair_stats(tb_store *s, const double *h_bias, const uint8_t *h_bad, double center, double out[4]) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(s && out, "null argument");
+    DeviceGuard g(s->device);
+    pair_stats(s, h_bias, h_bad, center, out);
+    return TB_OK;
+  });
+}
+
+int tb_pair_values(tb_store *s, const double *h_bias, const uint8_t *h_bad, int32_t zscored, double mean,
+                   double std, int64_t *n, int32_t *h_row, int32_t *h_col, double *h_val) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(s && n, "null argument");
+    TB_REQUIRE(!zscored || std > 0.0, "z-scores need a positive standard deviation");
+    DeviceGuard g(s->device);
+    pair_values(s, h_bias, h_bad, zscored, mean, std, n, h_row, h_col, h_val);
+    return TB_OK;
+  });
+}
+
+int tb_decay_sums(tb_store *s, const double *h_bias, const uint8_t *h_bad, double *h_nrm, int64_t *h_raw,
+                  double out_cis_total[2]) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(s, "null argument");
+    DeviceGuard g(s->device);
+    decay_sums(s, h_bias, h_bad, h_nrm, h_raw, out_cis_total);
+    return TB_OK;
+  });
+}
+
 int tb_diag_sums(tb_store *s, const uint8_t *h_bad, int64_t ndiag, int64_t *h_sum_d) {
   return guarded([&]() -> int {
     TB_REQUIRE(s, "null argument");

@@ -278,6 +278,12 @@ void row_work(tb_store *s, int64_t *h_dense, int64_t *h_tile);
 void ice_batch(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, double *h_bias,
                double *h_trace, int32_t *n_passes);
 void diag_sums(tb_store *s, const uint8_t *h_bad, int64_t ndiag, int64_t *h_sum_d);
+// extras.cu
+void pair_stats(tb_store *s, const double *h_bias, const uint8_t *h_bad, double center, double out[4]);
+void pair_values(tb_store *s, const double *h_bias, const uint8_t *h_bad, int zscored, double mean, double std,
+                 int64_t *n, int32_t *h_row, int32_t *h_col, double *h_val);
+void decay_sums(tb_store *s, const double *h_bias, const uint8_t *h_bad, double *h_nrm, int64_t *h_raw,
+                double out[2]);
 // comm.cu
 void comm_unique_id(uint8_t id[128]);
 void comm_init(tb_store *s, int rank, int world, const uint8_t id[128]);

@@ -1,0 +1,413 @@
+// The consumers of the biases that stream the matrix once more, as
+// cell visitors (visit.cuh) over the compact stream:
+//
+//   N1  normalised values and z-scores of the interaction pairs
+//       (_pytadbit/experiment.py:737-743 Experiment.normalize_hic builds hic[i,j] / bias[i] / bias[j]
+//        for all N^2 pairs; :751-799 get_hic_zscores + utils/tadmaths.py:94-172 take the log10 and
+//        the z-score of the pairs i < j between columns that are not filtered out)
+//         pair_stats   count, smallest value, sum of log10 and sum of squared deviations of the
+//                      non-zero pairs (everything the z-score needs; pairs with no contact are
+//                      accounted for in closed form by the host)
+//         pair_values  the pairs themselves (row, column, raw | normalised | z-score), row-major
+//   N2  what `tadbit normalize` derives from the biases (_pytadbit/tools/tadbit_normalize.py:963-1107,
+//       helpers :1110-1159): cis / total normalised interactions (get_cis_perc) and, per chromosome
+//       and genomic distance, the sums of normalised and raw counts (sum_dec_matrix)
+//         decay_sums
+//
+// Reductions of doubles go through per-CTA partials that are added in CTA order on the host side of
+// the call (same grid, same static work split -> same bits every run); the per-distance sums are
+// atomics on doubles (their order is not fixed: last-bit noise, far below the 1e-10 of north_star).
+#include <math.h>
+
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+#include "visit.cuh"
+
+namespace tb {
+
+namespace {
+
+inline int grid_1d(int64_t n, int threads, int sm_count, int per_sm = 8) {
+  int64_t g = (n + threads - 1) / threads, cap = (int64_t)sm_count * per_sm;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+// 1 / bias on good bins (NaN biases count as bad: tadbit normalize marks bad columns that way)
+__global__ void k_pair_weights(const double *__restrict__ bias, const uint8_t *__restrict__ bad, int64_t n,
+                               double *__restrict__ w, uint8_t *__restrict__ skip) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const bool b = bad[i] || (bias && isnan(bias[i]));
+    skip[i] = b;
+    w[i] = bias ? bias[i] : 1.0;
+  }
+}
+
+constexpr int kStatSlots = 4;        // per CTA: count, min, sum log10, sum squared deviation
+
+// value of the pair as the reference computes it: float(hic[i, j]) / bias[i] / bias[j]
+__device__ __forceinline__ double pair_value(int32_t v, const double *w, int64_t i, int64_t j, bool normalised) {
+  return normalised ? (double)v / w[i] / w[j] : (double)v;
+}
+
+struct PairStatsVisitor {
+  static constexpr int kShared = 32 * kStatSlots * 8;
+  static constexpr int kThreads = 256;
+  const uint8_t *skip;
+  const double *w;
+  bool normalised;
+  double center;
+  double *cta_out;                   // [gridDim.x * kStatSlots] of the kernel this visitor runs in
+  double cnt, mn, sum, dev2;
+  __device__ void begin(uint8_t *) { cnt = 0.0; mn = INFINITY; sum = 0.0; dev2 = 0.0; }
+  __device__ bool block(int64_t, int64_t, int64_t, int64_t) { return true; }
+  __device__ bool row(int64_t i) { return !skip[i]; }
+  __device__ void cell(int64_t i, int64_t j, int32_t v) {
+    if (j == i || v == 0 || skip[j]) return;
+    const double x = pair_value(v, w, i, j, normalised);
+    const double l = log10(x);
+    cnt += 1.0;
+    mn = fmin(mn, x);
+    sum += l;
+    dev2 += (l - center) * (l - center);
+  }
+  __device__ void end(uint8_t *smem) {
+    double *sh = reinterpret_cast<double *>(smem);
+    for (int o = 16; o; o >>= 1) {
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      dev2 += __shfl_xor_sync(0xffffffffu, dev2, o);
+    }
+    const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+      sh[wid * kStatSlots] = cnt; sh[wid * kStatSlots + 1] = mn;
+      sh[wid * kStatSlots + 2] = sum; sh[wid * kStatSlots + 3] = dev2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 1; k < nw; ++k) {
+        cnt += sh[k * kStatSlots]; mn = fmin(mn, sh[k * kStatSlots + 1]);
+        sum += sh[k * kStatSlots + 2]; dev2 += sh[k * kStatSlots + 3];
+      }
+      // the chunk and the tile kernel both run this visitor: each adds to its CTA's slots
+      double *o = cta_out + (size_t)blockIdx.x * kStatSlots;
+      o[0] += cnt; o[1] = fmin(o[1], mn); o[2] += sum; o[3] += dev2;
+    }
+  }
+};
+
+__global__ void k_stats_init(double *o, int n) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+    o[k] = (k % kStatSlots) == 1 ? INFINITY : 0.0;
+}
+
+struct PairCountVisitor {
+  static constexpr int kShared = 0;
+  static constexpr int kThreads = 256;
+  const uint8_t *skip;
+  int64_t rb;
+  unsigned long long *cnt;            // [nrows]
+  __device__ void begin(uint8_t *) {}
+  __device__ bool block(int64_t, int64_t, int64_t, int64_t) { return true; }
+  __device__ bool row(int64_t i) { return !skip[i]; }
+  __device__ void cell(int64_t i, int64_t j, int32_t v) {
+    if (j == i || v == 0 || skip[j]) return;
+    atomicAdd(&cnt[i - rb], 1ull);
+  }
+  __device__ void end(uint8_t *) {}
+};
+
+struct PairPlaceVisitor {
+  static constexpr int kShared = 0;
+  static constexpr int kThreads = 256;
+  const uint8_t *skip;
+  const double *w;
+  bool normalised, zscored;
+  double mean, inv_std;
+  int64_t rb;
+  const int64_t *off;
+  unsigned long long *cursor;
+  uint64_t *key;
+  double *val;
+  __device__ void begin(uint8_t *) {}
+  __device__ bool block(int64_t, int64_t, int64_t, int64_t) { return true; }
+  __device__ bool row(int64_t i) { return !skip[i]; }
+  __device__ void cell(int64_t i, int64_t j, int32_t v) {
+    if (j == i || v == 0 || skip[j]) return;
+    double x = pair_value(v, w, i, j, normalised);
+    if (zscored) x = (log10(x) - mean) * inv_std;
+    const int64_t r = i - rb;
+    const int64_t pos = off[r] + (int64_t)atomicAdd(&cursor[r], 1ull);
+    key[pos] = ((uint64_t)r << 32) | (uint32_t)j;
+    val[pos] = x;
+  }
+  __device__ void end(uint8_t *) {}
+};
+
+__global__ void k_unpack_pairs(const uint64_t *__restrict__ key, int64_t n, int64_t rb,
+                               int32_t *__restrict__ orow, int32_t *__restrict__ ocol) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t e = key[k];
+    orow[k] = (int32_t)(rb + (int64_t)(e >> 32));
+    ocol[k] = (int32_t)(e & 0xffffffffu);
+  }
+}
+
+// N2: cells i <= j between good bins.  Off-diagonal: cis / total normalised sums (get_cis_perc takes
+// i > j of a dict that holds both triangles: every pair once, diagonal excluded).  Same section:
+// per-distance sums at index section start + distance, diagonal included (sum_dec_matrix, i >= j).
+struct DecayVisitor {
+  static constexpr int kShared = 32 * 2 * 8;
+  static constexpr int kThreads = 256;
+  const uint8_t *skip;
+  const double *w;
+  const int32_t *chrom_of;
+  const int64_t *chrom_end;
+  const int64_t *chrom_beg;
+  double *nrm;                        // [nbins]
+  unsigned long long *raw;            // [nbins]
+  double *cta_out;                    // [gridDim.x * 2] cis, total
+  double cis, total;
+  int64_t jend, base;
+  __device__ void begin(uint8_t *) { cis = 0.0; total = 0.0; }
+  __device__ bool block(int64_t, int64_t, int64_t, int64_t) { return true; }
+  __device__ bool row(int64_t i) {
+    if (skip[i]) return false;
+    const int32_t c = chrom_of[i];
+    jend = chrom_end[c];
+    base = chrom_beg[c];
+    return true;
+  }
+  __device__ void cell(int64_t i, int64_t j, int32_t v) {
+    if (skip[j]) return;
+    const double x = (double)v / w[i] / w[j];
+    const bool same = j < jend;
+    if (j != i) {
+      total += x;
+      if (same) cis += x;
+    }
+    if (same) {
+      atomicAdd(&nrm[base + (j - i)], x);
+      atomicAdd(&raw[base + (j - i)], (unsigned long long)(long long)v);
+    }
+  }
+  __device__ void end(uint8_t *smem) {
+    double *sh = reinterpret_cast<double *>(smem);
+    for (int o = 16; o; o >>= 1) {
+      cis += __shfl_xor_sync(0xffffffffu, cis, o);
+      total += __shfl_xor_sync(0xffffffffu, total, o);
+    }
+    const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if ((threadIdx.x & 31) == 0) { sh[2 * wid] = cis; sh[2 * wid + 1] = total; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 1; k < nw; ++k) { cis += sh[2 * k]; total += sh[2 * k + 1]; }
+      cta_out[2 * (size_t)blockIdx.x] += cis;
+      cta_out[2 * (size_t)blockIdx.x + 1] += total;
+    }
+  }
+};
+
+struct Weights {
+  DevBuf<double> w;
+  DevBuf<uint8_t> skip;
+};
+
+void make_weights(tb_store *s, const double *h_bias, const uint8_t *h_bad, Weights &wt) {
+  cudaStream_t st = s->stream;
+  const int64_t N = s->nbins;
+  wt.w.alloc(N);
+  wt.skip.alloc(N);
+  if (h_bad) TB_CUDA(cudaMemcpyAsync(s->bad.p, h_bad, N, cudaMemcpyHostToDevice, st));
+  else TB_CUDA(cudaMemsetAsync(s->bad.p, 0, N, st));
+  const double *bias = nullptr;
+  if (h_bias) {
+    TB_CUDA(cudaMemcpyAsync(s->b.p, h_bias, N * sizeof(double), cudaMemcpyHostToDevice, st));
+    bias = s->b.p;
+  }
+  k_pair_weights<<<grid_1d(N, 256, s->sm_count), 256, 0, st>>>(bias, s->bad.p, N, wt.w.p, wt.skip.p);
+}
+
+constexpr int kMaxCtas = 148 * 16 * 4;
+
+}  // namespace
+
+// out[0] pairs with a non-zero value, [1] the smallest such value, [2] sum of log10(value),
+// [3] sum of (log10(value) - center)^2
+void pair_stats(tb_store *s, const double *h_bias, const uint8_t *h_bad, double center, double out[4]) {
+  cudaStream_t st = s->stream;
+  Weights wt;
+  make_weights(s, h_bias, h_bad, wt);
+  DevBuf<double> cta;
+  cta.alloc((size_t)kMaxCtas * kStatSlots);
+  k_stats_init<<<64, 256, 0, st>>>(cta.p, kMaxCtas * kStatSlots);
+  PairStatsVisitor vis;
+  vis.skip = wt.skip.p;
+  vis.w = wt.w.p;
+  vis.normalised = h_bias != nullptr;
+  vis.center = center;
+  vis.cta_out = cta.p;
+  vis.cnt = vis.sum = vis.dev2 = 0.0;
+  vis.mn = 0.0;
+  visit_upper(s, vis);
+  std::vector<double> h((size_t)kMaxCtas * kStatSlots);
+  TB_CUDA(cudaMemcpyAsync(h.data(), cta.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  double cnt = 0.0, mn = INFINITY, sum = 0.0, dev2 = 0.0;
+  for (int k = 0; k < kMaxCtas; ++k) {            // CTA order: the same bits every run
+    cnt += h[(size_t)k * kStatSlots];
+    mn = fmin(mn, h[(size_t)k * kStatSlots + 1]);
+    sum += h[(size_t)k * kStatSlots + 2];
+    dev2 += h[(size_t)k * kStatSlots + 3];
+  }
+  if (s->world > 1) {                             // sums over the shards; min as -max
+    double part[4] = {cnt, sum, dev2, 0.0};
+    TB_CUDA(cudaMemcpyAsync(s->scal_f.p, part, sizeof(part), cudaMemcpyHostToDevice, st));
+    allreduce_f64(s, s->scal_f.p, s->scal_f.p + 8, 4);
+    TB_CUDA(cudaMemcpyAsync(part, s->scal_f.p + 8, sizeof(part), cudaMemcpyDeviceToHost, st));
+    // the minimum: every rank contributes its own in its own slot, the sum carries them all
+    std::vector<double> slots(s->world, 0.0), all(s->world, 0.0);
+    slots[s->rank] = isinf(mn) ? 0.0 : mn;
+    DevBuf<double> dm;
+    dm.alloc(2 * (size_t)s->world);
+    TB_CUDA(cudaMemcpyAsync(dm.p, slots.data(), s->world * sizeof(double), cudaMemcpyHostToDevice, st));
+    allreduce_f64(s, dm.p, dm.p + s->world, s->world);
+    TB_CUDA(cudaMemcpyAsync(all.data(), dm.p + s->world, s->world * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    cnt = part[0]; sum = part[1]; dev2 = part[2];
+    mn = INFINITY;
+    for (double v : all) if (v > 0.0) mn = fmin(mn, v);
+  }
+  out[0] = cnt; out[1] = mn; out[2] = sum; out[3] = dev2;
+}
+
+// The non-zero pairs i < j between good bins of the owned rows, row-major: value = raw count,
+// normalised count (h_bias given) or z-score of its log10 (zscored).  Call with null arrays to get *n.
+void pair_values(tb_store *s, const double *h_bias, const uint8_t *h_bad, int zscored, double mean, double std,
+                 int64_t *n, int32_t *h_row, int32_t *h_col, double *h_val) {
+  cudaStream_t st = s->stream;
+  const int64_t nrows = s->nrows;
+  Weights wt;
+  make_weights(s, h_bias, h_bad, wt);
+  DevBuf<unsigned long long> cnt;
+  DevBuf<int64_t> off;
+  cnt.alloc(nrows + 1);
+  off.alloc(nrows + 1);
+  TB_CUDA(cudaMemsetAsync(cnt.p, 0, cnt.bytes(), st));
+  PairCountVisitor cv;
+  cv.skip = wt.skip.p;
+  cv.rb = s->row_begin;
+  cv.cnt = cnt.p;
+  visit_upper(s, cv);
+  {
+    size_t tmp_bytes = 0;
+    TB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, reinterpret_cast<const int64_t *>(cnt.p), off.p,
+                                          nrows + 1, st));
+    DevBuf<uint8_t> tmp;
+    tmp.alloc(tmp_bytes ? tmp_bytes : 1);
+    TB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, reinterpret_cast<const int64_t *>(cnt.p), off.p,
+                                          nrows + 1, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+  }
+  int64_t m = 0;
+  TB_CUDA(cudaMemcpy(&m, off.p + nrows, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  *n = m;
+  if (!h_row || m == 0) return;
+  TB_REQUIRE(h_col && h_val, "pair_values: null output buffer");
+  DevBuf<uint64_t> key_in, key_out;
+  DevBuf<double> val_in, val_out;
+  DevBuf<int32_t> orow, ocol;
+  key_in.alloc(m); key_out.alloc(m); val_in.alloc(m); val_out.alloc(m); orow.alloc(m); ocol.alloc(m);
+  TB_CUDA(cudaMemsetAsync(cnt.p, 0, cnt.bytes(), st));
+  PairPlaceVisitor pv;
+  pv.skip = wt.skip.p;
+  pv.w = wt.w.p;
+  pv.normalised = h_bias != nullptr;
+  pv.zscored = zscored != 0;
+  pv.mean = mean;
+  pv.inv_std = zscored ? 1.0 / std : 1.0;
+  pv.rb = s->row_begin;
+  pv.off = off.p;
+  pv.cursor = cnt.p;
+  pv.key = key_in.p;
+  pv.val = val_in.p;
+  visit_upper(s, pv);
+  int row_bits = 1;
+  while (((int64_t)1 << row_bits) < nrows) ++row_bits;
+  size_t tmp_bytes = 0;
+  TB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_in.p, key_out.p, val_in.p, val_out.p, m, 0,
+                                          32 + row_bits, st));
+  DevBuf<uint8_t> tmp;
+  tmp.alloc(tmp_bytes ? tmp_bytes : 1);
+  TB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key_in.p, key_out.p, val_in.p, val_out.p, m, 0,
+                                          32 + row_bits, st));
+  k_unpack_pairs<<<grid_1d(m, 256, s->sm_count), 256, 0, st>>>(key_out.p, m, s->row_begin, orow.p, ocol.p);
+  TB_CUDA(cudaMemcpyAsync(h_row, orow.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaMemcpyAsync(h_col, ocol.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaMemcpyAsync(h_val, val_out.p, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+}
+
+// h_nrm / h_raw [nbins]: entry (first bin of section c) + d = sum over the cells (i, i + d) of section c
+// between good bins of count / bias_i / bias_j and of count.  out[0] cis, out[1] total normalised
+// interactions of the off-diagonal pairs between good bins.
+void decay_sums(tb_store *s, const double *h_bias, const uint8_t *h_bad, double *h_nrm, int64_t *h_raw,
+                double out[2]) {
+  cudaStream_t st = s->stream;
+  const int64_t N = s->nbins;
+  TB_REQUIRE(h_bias && h_nrm && h_raw && out, "decay_sums: null argument");
+  Weights wt;
+  make_weights(s, h_bias, h_bad, wt);
+  DevBuf<double> nrm, cta;
+  DevBuf<unsigned long long> raw;
+  DevBuf<int64_t> beg;
+  nrm.alloc(2 * N); raw.alloc(2 * N); cta.alloc((size_t)kMaxCtas * 2);
+  const size_t nsec = s->chrom_offsets.size() - 1;
+  beg.alloc(nsec);
+  TB_CUDA(cudaMemcpyAsync(beg.p, s->chrom_offsets.data(), nsec * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  TB_CUDA(cudaMemsetAsync(nrm.p, 0, nrm.bytes(), st));
+  TB_CUDA(cudaMemsetAsync(raw.p, 0, raw.bytes(), st));
+  TB_CUDA(cudaMemsetAsync(cta.p, 0, cta.bytes(), st));
+  DecayVisitor vis;
+  vis.skip = wt.skip.p;
+  vis.w = wt.w.p;
+  vis.chrom_of = s->chrom_of.p;
+  vis.chrom_end = s->chrom_end.p;
+  vis.chrom_beg = beg.p;
+  vis.nrm = nrm.p;
+  vis.raw = raw.p;
+  vis.cta_out = cta.p;
+  vis.cis = vis.total = 0.0;
+  vis.jend = vis.base = 0;
+  visit_upper(s, vis);
+  std::vector<double> h((size_t)kMaxCtas * 2);
+  TB_CUDA(cudaMemcpyAsync(h.data(), cta.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  double cis = 0.0, total = 0.0;
+  for (int k = 0; k < kMaxCtas; ++k) { cis += h[2 * (size_t)k]; total += h[2 * (size_t)k + 1]; }
+  const double *src_n = nrm.p;
+  const unsigned long long *src_r = raw.p;
+  if (s->world > 1) {
+    double part[2] = {cis, total};
+    TB_CUDA(cudaMemcpyAsync(s->scal_f.p, part, sizeof(part), cudaMemcpyHostToDevice, st));
+    allreduce_f64(s, s->scal_f.p, s->scal_f.p + 8, 2);
+    TB_CUDA(cudaMemcpyAsync(part, s->scal_f.p + 8, sizeof(part), cudaMemcpyDeviceToHost, st));
+    allreduce_f64(s, nrm.p, nrm.p + N, N);
+    allreduce_i64(s, reinterpret_cast<const long long *>(raw.p), reinterpret_cast<long long *>(raw.p + N), N);
+    TB_CUDA(cudaStreamSynchronize(st));
+    cis = part[0]; total = part[1];
+    src_n = nrm.p + N;
+    src_r = raw.p + N;
+  }
+  TB_CUDA(cudaMemcpyAsync(h_nrm, src_n, N * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaMemcpyAsync(h_raw, src_r, N * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  out[0] = cis;
+  out[1] = total;
+}
+
+}  // namespace tb

@@ -282,6 +282,54 @@ class ContactStore(object):
         check(lib().tb_norm_sum(self._h, bp, mp, C.byref(out)))
         return out.value
 
+    def _bias(self, bias):
+        if bias is None:
+            return None, None
+        b = np.ascontiguousarray(bias, dtype=np.float64)
+        if b.shape != (self.size,):
+            raise ValueError("bias must have %d entries" % self.size)
+        return b, ptr(b, C.c_double)
+
+    def pair_stats(self, bias=None, bad=None, center=0.0):
+        """Over the stored pairs i < j between good bins: (pairs with a non-zero value, smallest
+        value, sum of log10(value), sum of (log10(value) - center)^2); value = count, or
+        count / bias[i] / bias[j] when ``bias`` is given."""
+        m, mp = self._mask(bad)
+        b, bp = self._bias(bias)
+        out = np.zeros(4, dtype=np.float64)
+        check(lib().tb_pair_stats(self._h, bp, mp, float(center), ptr(out, C.c_double)))
+        return int(out[0]), float(out[1]), float(out[2]), float(out[3])
+
+    def pair_values(self, bias=None, bad=None, zscore=None):
+        """The same pairs, row-major: (rows, cols, values).  ``zscore=(mean, std)`` turns the values
+        into (log10(value) - mean) / std."""
+        m, mp = self._mask(bad)
+        b, bp = self._bias(bias)
+        mean, std = zscore if zscore is not None else (0.0, 1.0)
+        n = C.c_int64()
+        check(lib().tb_pair_values(self._h, bp, mp, int(zscore is not None), float(mean), float(std),
+                                   C.byref(n), None, None, None))
+        r = np.empty(n.value, dtype=np.int32)
+        c = np.empty(n.value, dtype=np.int32)
+        v = np.empty(n.value, dtype=np.float64)
+        if n.value:
+            check(lib().tb_pair_values(self._h, bp, mp, int(zscore is not None), float(mean), float(std),
+                                       C.byref(n), ptr(r, C.c_int32), ptr(c, C.c_int32),
+                                       ptr(v, C.c_double)))
+        return r, c, v
+
+    def decay_sums(self, bias, bad=None):
+        """Per section and distance: (normalised sums float64[N], raw sums int64[N]) indexed by
+        first bin of the section + distance, and (cis, total) normalised off-diagonal sums."""
+        m, mp = self._mask(bad)
+        b, bp = self._bias(bias)
+        nrm = np.zeros(self.size, dtype=np.float64)
+        raw = np.zeros(self.size, dtype=np.int64)
+        ct = np.zeros(2, dtype=np.float64)
+        check(lib().tb_decay_sums(self._h, bp, mp, ptr(nrm, C.c_double), ptr(raw, C.c_int64),
+                                  ptr(ct, C.c_double)))
+        return nrm, raw, (float(ct[0]), float(ct[1]))
+
     def diag_sums(self, bad, ndiag):
         m, mp = self._mask(bad)
         out = np.zeros(max(int(ndiag), 0), dtype=np.int64)

@@ -40,6 +40,23 @@ class NumpyStore(object):
     def diag_sums(self, bad, ndiag):                       # tb_diag_sums
         return np.asarray(orc.diagonal_sums(self.m, self._bads(bad), ndiag)[0], dtype=np.int64)
 
+    def pair_stats(self, bias=None, bad=None, center=0.0):  # tb_pair_stats
+        r, c, v = orc.pair_values(self.m, bias, self._bads(bad))
+        if v.size == 0:
+            return 0, float("inf"), 0.0, 0.0
+        logs = np.log10(v.astype(np.float64))
+        return int(v.size), float(v.min()), float(logs.sum()), float(((logs - center) ** 2).sum())
+
+    def pair_values(self, bias=None, bad=None, zscore=None):  # tb_pair_values
+        r, c, v = orc.pair_values(self.m, bias, self._bads(bad))
+        v = v.astype(np.float64)
+        if zscore is not None:
+            v = (np.log10(v) - zscore[0]) / zscore[1]
+        return r.astype(np.int32), c.astype(np.int32), v
+
+    def decay_sums(self, bias, bad=None):                  # tb_decay_sums
+        return orc.decay_sums(self.m, bias, self._bads(bad))
+
     def export_upper(self):                                # tb_store_export_upper
         return (self.m.rows.astype(np.int32), self.m.cols.astype(np.int32), self.m.vals)
 
