@@ -170,6 +170,8 @@ void exchange_setup(tb_store *s) {
   v.rank = s->world == 1 ? 0 : s->rank;
   place(v.rank, px.base);
   v.my_flags = v.flag[v.rank];
+  v.mine[0] = v.s[v.rank][0];
+  v.mine[1] = v.s[v.rank][1];
   px.ready = true;
   if (s->world == 1) return;
   const char *e = getenv("TB_EXCHANGE");

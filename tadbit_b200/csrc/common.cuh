@@ -99,10 +99,11 @@ struct IceState {
 // its own rows into, plus one arrival flag per peer (comm.cu sets this up, k_ice_exchange in
 // kernels.cu uses it).  With one GPU the "peers" are the rank itself and nothing is mapped.
 constexpr int kMaxPeers = 16;
-struct PeerView {                  // passed to the kernel by value
+struct PeerView {                  // passed to the kernel by value; indexed with constants only
   double *s[kMaxPeers][2];         // peer q's buffers (s[rank] = local)
   unsigned long long *flag[kMaxPeers];   // peer q's flag array; this rank writes flag[q][rank]
   unsigned long long *my_flags;    // local flag array, entry q written by peer q
+  double *mine[2];                 // the local buffers again (no dynamic index into s[][])
   int rank, world;
 };
 struct PeerExchange {
@@ -259,6 +260,7 @@ void build_encoded(tb_store *s);     // compact row-sum stream from the CSR
 // rowsum.cu
 void launch_rowsum(tb_store *s, const double *x, const IceState *state);   // K1 over the compact stream
 void launch_rowsum_chunks(tb_store *s, const double *x, const IceState *state);   // dense + per-cell part
+bool sparse_in_dense_tail(const tb_store *s);
 // tiles.cu
 void build_tiles(tb_store *s);       // sparse tiles from the ENC_T chunks (after build_encoded)
 void launch_rowsum_tiles(tb_store *s, const double *x, const IceState *state);

@@ -291,9 +291,22 @@ __device__ __forceinline__ void block_stats(double &sum, double &mn, double &mx,
 __device__ __forceinline__ void fold_blocks(const double *block_red, unsigned int nblocks, double &sum,
                                             double &mn, double &mx, double &dcnt) {
   sum = 0.0; mn = INFINITY; mx = -INFINITY; dcnt = 0.0;
-  for (unsigned int bl = threadIdx.x; bl < nblocks; bl += 32) {
-    const volatile double *br = block_red + 4 * bl;
-    sum += br[0]; mn = fmin(mn, br[1]); mx = fmax(mx, br[2]); dcnt += br[3];
+  // the entries of 8 blocks per lane are requested together (independent loads, one L2 round trip),
+  // then added in block order
+  for (unsigned int b0 = threadIdx.x; b0 < nblocks; b0 += 32 * 8) {
+    double v[8][4];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const unsigned int bl = b0 + 32 * k;
+      const double2 *br = reinterpret_cast<const double2 *>(block_red + 4 * (bl < nblocks ? bl : b0));
+      const double2 a = __ldcg(br), c = __ldcg(br + 1);     // L2: written by other CTAs of this launch
+      v[k][0] = a.x; v[k][1] = a.y; v[k][2] = c.x; v[k][3] = c.y;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (b0 + 32 * k < nblocks) {
+        sum += v[k][0]; mn = fmin(mn, v[k][1]); mx = fmax(mx, v[k][2]); dcnt += v[k][3];
+      }
   }
   for (int o = 16; o; o >>= 1) {
     sum += __shfl_xor_sync(0xffffffffu, sum, o);
@@ -396,8 +409,8 @@ __global__ void k_ice_update(const double *__restrict__ s_full, double *__restri
 //   4. bias update B *= S / meanS, x = 1 / B.
 // The pass number is read from the device state, so the launch arguments never change.
 // The grid must be co-resident: CTAs wait for each other.  It is sized from the occupancy the
-// runtime reports (exchange_grid), three CTAs of 512 threads per SM: the row phase is a chain of
-// dependent loads per row and needs the threads to cover their latency.
+// runtime reports (exchange_grid), two CTAs of 512 threads per SM; the row phase is a chain of
+// dependent loads per row, so every thread works on two rows at a time to keep loads in flight.
 // ---------------------------------------------------------------------------------
 constexpr int kXThreads = 512;
 constexpr unsigned long long kPeerTimeoutNs = 4000000000ull;    // 4 s: a peer that never arrives
@@ -424,7 +437,7 @@ __device__ __forceinline__ unsigned long long now_ns() {
   return t;
 }
 
-__global__ void __launch_bounds__(kXThreads, 3)
+__global__ void __launch_bounds__(kXThreads, 2)
 k_ice_exchange(PeerView pv, const double *__restrict__ pf, const int64_t *__restrict__ row_chunk,
                TileSums ts, int64_t nrows, int64_t rb, int64_t n, double *__restrict__ x,
                double *__restrict__ b, const uint8_t *__restrict__ bad, uint8_t *__restrict__ present,
@@ -438,12 +451,26 @@ k_ice_exchange(PeerView pv, const double *__restrict__ pf, const int64_t *__rest
   const unsigned long long epoch = vs->epoch_base + (unsigned long long)pass + 1ull;
   const int buf = pass & 1;
   if (threadIdx.x == 0) s_fault = 0;
-  // 1. the rows of this rank -> every rank
-  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
-       r += (int64_t)gridDim.x * blockDim.x) {
-    double a = row_total(pf, row_chunk, ts, r);
-    if (pass == 0) a = mark_present(bad, live, rb + r, r, a);
-    for (int q = 0; q < pv.world; ++q) pv.s[q][buf][rb + r] = a;
+  // 1. the rows of this rank -> every rank (two rows per thread and step)
+  {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows; r += 2 * stride) {
+      const int64_t r2 = r + stride;
+      const bool two = r2 < nrows;
+      double a = row_total(pf, row_chunk, ts, r);
+      double a2 = two ? row_total(pf, row_chunk, ts, r2) : 0.0;
+      if (pass == 0) {
+        a = mark_present(bad, live, rb + r, r, a);
+        if (two) a2 = mark_present(bad, live, rb + r2, r2, a2);
+      }
+#pragma unroll
+      for (int q = 0; q < kMaxPeers; ++q)          // constant indices: the parameter stays in the constant bank
+        if (q < pv.world) {
+          double *dst = buf ? pv.s[q][1] : pv.s[q][0];
+          dst[rb + r] = a;
+          if (two) dst[rb + r2] = a2;
+        }
+    }
   }
   __threadfence_system();
   __syncthreads();
@@ -453,7 +480,9 @@ k_ice_exchange(PeerView pv, const double *__restrict__ pf, const int64_t *__rest
     if (t == gridDim.x - 1) {
       state->arrive1 = 0;
       __threadfence_system();
-      for (int q = 0; q < pv.world; ++q) st_release_sys(pv.flag[q] + pv.rank, epoch);
+#pragma unroll
+      for (int q = 0; q < kMaxPeers; ++q)
+        if (q < pv.world) st_release_sys(pv.flag[q] + pv.rank, epoch);
     }
   }
   if (threadIdx.x < pv.world) {
@@ -468,7 +497,7 @@ k_ice_exchange(PeerView pv, const double *__restrict__ pf, const int64_t *__rest
     return;
   }
   // 3. statistics of the pass
-  const double *sfull = pv.s[pv.rank][buf];
+  const double *sfull = buf ? pv.mine[1] : pv.mine[0];
   double sum = 0.0, mn = INFINITY, mx = -INFINITY;
   long long cnt = 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
@@ -859,7 +888,7 @@ int exchange_grid(const tb_store *s) {
   if (!v) {
     TB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_ice_exchange, kXThreads, 0));
     if (v < 1) v = 1;
-    if (v > 3) v = 3;
+    if (v > 2) v = 2;
   }
   return v * s->sm_count;
 }
@@ -1057,7 +1086,7 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
     }
   }
   {   // kernels of this library launched by the call (NCCL's own kernels are not counted)
-    const int k1 = csr_walk ? 1 : (s->t_nunits > 0) + (s->n_groups > 0) + (s->n_sparse > 0);
+    const int k1 = csr_walk ? 1 : (s->t_nunits > 0) + (s->n_groups > 0) + (s->n_sparse > 0 && !sparse_in_dense_tail(s));
     const int k2 = fused ? 1 : 2 + (s->world > 1 && s->nrows ? 1 : 0);   // exchange | (combine) + reduce + update
     s->total_launches = 2 /* init, finalize */ + (live ? 1 : 0) + launched * (k1 + k2);
   }
@@ -1212,7 +1241,7 @@ void ice_batch(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max
   s->exchange_ms = 0;
   s->rowsum_launches = 0;
   {
-    const int k1 = csr_walk ? 1 : (s->t_nunits > 0) + (s->n_groups > 0) + (s->n_sparse > 0);
+    const int k1 = csr_walk ? 1 : (s->t_nunits > 0) + (s->n_groups > 0) + (s->n_sparse > 0 && !sparse_in_dense_tail(s));
     s->total_launches = 3 + (live ? 1 : 0) + launched * (k1 + 2);
   }
 }

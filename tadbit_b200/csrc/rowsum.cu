@@ -144,11 +144,18 @@ __device__ __forceinline__ GroupRec load_rec(const GroupRec *__restrict__ recs, 
   return g;
 }
 
+template <int NT>
+__device__ __forceinline__ void sparse_chunk(const uint8_t *__restrict__ data, const int64_t *__restrict__ off,
+                                             const int4 *__restrict__ desc, int32_t c,
+                                             const double *__restrict__ x, double *__restrict__ partial,
+                                             double *wsum);
+
 __global__ void __launch_bounds__(kDenseWarps * 32, 1)
 k_rowsum_dense(const uint8_t *__restrict__ data, const GroupRec *__restrict__ recs,
                const int32_t *__restrict__ cta_range, const int4 *__restrict__ desc,
                const double *__restrict__ x, double *__restrict__ partial,
-               const IceState *__restrict__ state) {
+               const IceState *__restrict__ state, const int64_t *__restrict__ enc_off,
+               const int32_t *__restrict__ sparse_ids, int64_t n_sparse_tail) {
   if (state && state->stopped) return;
   extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
@@ -274,6 +281,74 @@ k_rowsum_dense(const uint8_t *__restrict__ data, const GroupRec *__restrict__ re
     }
     g = ge;
   }
+  // the few per-cell chunks of the store (values that fit no other encoding), one per CTA that is
+  // done with its panels: no launch of their own (10 us per pass for a single chunk otherwise)
+  if (n_sparse_tail) {
+    __syncthreads();
+    double *wsum = reinterpret_cast<double *>(smem);          // the x panel is no longer needed
+    for (int64_t i = blockIdx.x; i < n_sparse_tail; i += gridDim.x)
+      sparse_chunk<kDenseWarps * 32>(data, enc_off, desc, sparse_ids[i], x, partial, wsum);
+  }
+}
+
+// One per-cell chunk (negative or very large values: there are few) by the NT threads of a CTA:
+// the gathers go through L1/L2, warp sums are added in warp order.
+template <int NT>
+__device__ __forceinline__ void sparse_chunk(const uint8_t *__restrict__ data, const int64_t *__restrict__ off,
+                                             const int4 *__restrict__ desc, int32_t c,
+                                             const double *__restrict__ x, double *__restrict__ partial,
+                                             double *wsum) {
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5, tid = threadIdx.x;
+  const int4 d = desc[c];
+  const uint8_t *p = data + off[c];
+  const int n = d.y;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  if ((d.z & 0xff) == ENC_S16) {
+    const double *xb = x + d.x;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(p);
+    int k = tid;
+    for (; k + 3 * NT < n; k += 4 * NT) {
+      const uint32_t e0 = ldg_stream_u32(w + k), e1 = ldg_stream_u32(w + k + NT);
+      const uint32_t e2 = ldg_stream_u32(w + k + 2 * NT), e3 = ldg_stream_u32(w + k + 3 * NT);
+      const double x0 = __ldg(xb + (e0 & 0xffff)), x1 = __ldg(xb + (e1 & 0xffff));
+      const double x2 = __ldg(xb + (e2 & 0xffff)), x3 = __ldg(xb + (e3 & 0xffff));
+      a0 = fma(u2d(e0 >> 16), x0, a0);
+      a1 = fma(u2d(e1 >> 16), x1, a1);
+      a2 = fma(u2d(e2 >> 16), x2, a2);
+      a3 = fma(u2d(e3 >> 16), x3, a3);
+    }
+    for (; k < n; k += NT) {
+      const uint32_t e0 = ldg_stream_u32(w + k);
+      a0 = fma(u2d(e0 >> 16), __ldg(xb + (e0 & 0xffff)), a0);
+    }
+  } else {                                     // ENC_S32
+    const uint2 *w = reinterpret_cast<const uint2 *>(p);
+    int k = tid;
+    for (; k + 3 * NT < n; k += 4 * NT) {
+      const uint2 e0 = ldg_stream_u64(w + k), e1 = ldg_stream_u64(w + k + NT);
+      const uint2 e2 = ldg_stream_u64(w + k + 2 * NT), e3 = ldg_stream_u64(w + k + 3 * NT);
+      const double x0 = __ldg(x + e0.x), x1 = __ldg(x + e1.x);
+      const double x2 = __ldg(x + e2.x), x3 = __ldg(x + e3.x);
+      a0 = fma(i2d((int32_t)e0.y), x0, a0);
+      a1 = fma(i2d((int32_t)e1.y), x1, a1);
+      a2 = fma(i2d((int32_t)e2.y), x2, a2);
+      a3 = fma(i2d((int32_t)e3.y), x3, a3);
+    }
+    for (; k < n; k += NT) {
+      const uint2 e0 = ldg_stream_u64(w + k);
+      a0 = fma(i2d((int32_t)e0.y), __ldg(x + e0.x), a0);
+    }
+  }
+  const double a = warp_sum((a0 + a1) + (a2 + a3));
+  if (lane == 0) wsum[wic] = a;
+  __syncthreads();
+  if (tid == 0) {
+    double t = wsum[0];
+#pragma unroll
+    for (int q = 1; q < NT / 32; ++q) t += wsum[q];
+    partial[c] = t;
+  }
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(256)
@@ -282,66 +357,17 @@ k_rowsum_sparse(const uint8_t *__restrict__ data, const int64_t *__restrict__ of
                 const double *__restrict__ x, double *__restrict__ partial,
                 const IceState *__restrict__ state) {
   if (state && state->stopped) return;
-  // one CTA per chunk (these chunks are few: cells with negative or very large values): the
-  // gathers of a chunk are spread over 8 warps, warp sums are added in warp order
   __shared__ double wsum[8];
-  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5, tid = threadIdx.x;
-  for (int64_t i = blockIdx.x; i < ns; i += gridDim.x) {
-    const int32_t c = ids[i];
-    const int4 d = desc[c];
-    const uint8_t *p = data + off[c];
-    const int n = d.y;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    if ((d.z & 0xff) == ENC_S16) {
-      const double *xb = x + d.x;
-      const uint32_t *w = reinterpret_cast<const uint32_t *>(p);
-      int k = tid;
-      for (; k + 768 < n; k += 1024) {
-        const uint32_t e0 = ldg_stream_u32(w + k), e1 = ldg_stream_u32(w + k + 256);
-        const uint32_t e2 = ldg_stream_u32(w + k + 512), e3 = ldg_stream_u32(w + k + 768);
-        const double x0 = __ldg(xb + (e0 & 0xffff)), x1 = __ldg(xb + (e1 & 0xffff));
-        const double x2 = __ldg(xb + (e2 & 0xffff)), x3 = __ldg(xb + (e3 & 0xffff));
-        a0 = fma(u2d(e0 >> 16), x0, a0);
-        a1 = fma(u2d(e1 >> 16), x1, a1);
-        a2 = fma(u2d(e2 >> 16), x2, a2);
-        a3 = fma(u2d(e3 >> 16), x3, a3);
-      }
-      for (; k < n; k += 256) {
-        const uint32_t e0 = ldg_stream_u32(w + k);
-        a0 = fma(u2d(e0 >> 16), __ldg(xb + (e0 & 0xffff)), a0);
-      }
-    } else {                                     // ENC_S32
-      const uint2 *w = reinterpret_cast<const uint2 *>(p);
-      int k = tid;
-      for (; k + 768 < n; k += 1024) {
-        const uint2 e0 = ldg_stream_u64(w + k), e1 = ldg_stream_u64(w + k + 256);
-        const uint2 e2 = ldg_stream_u64(w + k + 512), e3 = ldg_stream_u64(w + k + 768);
-        const double x0 = __ldg(x + e0.x), x1 = __ldg(x + e1.x);
-        const double x2 = __ldg(x + e2.x), x3 = __ldg(x + e3.x);
-        a0 = fma(i2d((int32_t)e0.y), x0, a0);
-        a1 = fma(i2d((int32_t)e1.y), x1, a1);
-        a2 = fma(i2d((int32_t)e2.y), x2, a2);
-        a3 = fma(i2d((int32_t)e3.y), x3, a3);
-      }
-      for (; k < n; k += 256) {
-        const uint2 e0 = ldg_stream_u64(w + k);
-        a0 = fma(i2d((int32_t)e0.y), __ldg(x + e0.x), a0);
-      }
-    }
-    const double a = warp_sum((a0 + a1) + (a2 + a3));
-    if (lane == 0) wsum[wic] = a;
-    __syncthreads();
-    if (tid == 0) {
-      double t = wsum[0];
-#pragma unroll
-      for (int q = 1; q < 8; ++q) t += wsum[q];
-      partial[c] = t;
-    }
-    __syncthreads();
-  }
+  for (int64_t i = blockIdx.x; i < ns; i += gridDim.x)
+    sparse_chunk<256>(data, off, desc, ids[i], x, partial, wsum);
 }
 
 }  // namespace
+
+// per-cell chunks ride at the end of the dense kernel when there are only a few of them
+bool sparse_in_dense_tail(const tb_store *s) {
+  return s->n_groups > 0 && s->n_sparse <= 2 * (int64_t)s->n_dense_ctas;
+}
 
 void launch_rowsum(tb_store *s, const double *x, const IceState *state) {
   launch_rowsum_tiles(s, x, state);
@@ -357,9 +383,10 @@ void launch_rowsum_chunks(tb_store *s, const double *x, const IceState *state) {
       attr_set[s->device & 63] = true;
     }
     k_rowsum_dense<<<s->n_dense_ctas, kDenseWarps * 32, kDenseSmem, s->stream>>>(
-        s->enc_data.p, s->groups.p, s->group_range.p, s->enc_desc.p, x, s->partial_f.p, state);
+        s->enc_data.p, s->groups.p, s->group_range.p, s->enc_desc.p, x, s->partial_f.p, state, s->enc_off.p,
+        s->work_ids.p, sparse_in_dense_tail(s) ? s->n_sparse : 0);
   }
-  if (s->n_sparse) {
+  if (s->n_sparse && !sparse_in_dense_tail(s)) {
     const int64_t cap = (int64_t)s->sm_count * 8;
     const int grid = (int)(s->n_sparse < cap ? s->n_sparse : cap);
     k_rowsum_sparse<<<grid, 256, 0, s->stream>>>(s->enc_data.p, s->enc_off.p, s->enc_desc.p,

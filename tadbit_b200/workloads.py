@@ -89,7 +89,7 @@ def rebalance_by_time(blocks, probes, size):
     return balanced_row_blocks(cost, len(blocks))
 
 
-def build_sharded(wl, rank, world, device, gather=None, refine=2):
+def build_sharded(wl, rank, world, device, gather=None, refine=3):
     """Generate this rank's block of the synthetic matrix.  ``gather`` is a callable that
     all-gathers a python object over ranks (host plumbing, e.g. torch.distributed).
 
@@ -112,7 +112,7 @@ def build_sharded(wl, rank, world, device, gather=None, refine=2):
         dense, tiles = store.row_work()
         probes = gather((ms_t, ms_d, dense, tiles))
         times = [p[0] + p[1] for p in probes]
-        if max(times) <= 1.03 * (sum(times) / world):
+        if max(times) <= 1.012 * (sum(times) / world):
             break
         new = rebalance_by_time(blocks, probes, n)
         if new == blocks:
