@@ -399,7 +399,7 @@ def main():
 
     # ---- the filter, once (K4 + the <=100-point host tail) ------------------------------------
     t0 = time.perf_counter()
-    hic.filter_columns(silent=True)
+    hic.filter_columns(silent=True, **wl["filter_kw"])
     filter_ms = (time.perf_counter() - t0) * 1e3
     k4_ms = store.timing()["kernel_ms"]                # the last masked column-sum pass
     mask = bad_mask(n, hic.bads)
@@ -520,7 +520,8 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["description"], "bins": n, "contacts_upper": nnz_upper,
                        "passes_per_step": passes_per_step,
-                       "ice": "iterations=%d max_dev=%g, mask of filter_columns()" % (ITERATIONS, MAX_DEV),
+                       "ice": "iterations=%d max_dev=%g, mask of filter_columns(%s)" % (
+                           ITERATIONS, MAX_DEV, ", ".join("%s=%s" % kv for kv in wl["filter_kw"].items())),
                        "l2": "inputs exceed L2 (store %.1f GB vs 126 MB)" % (info["device_bytes"] / 1e9),
                        "sharding": ("rows, balanced by measured K1 time; per pass one fused kernel stores the "
                                     "row sums into every GPU (%s)" % exchange_kind) if world > 1 else "single GPU",

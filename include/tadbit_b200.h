@@ -284,6 +284,13 @@ int tb_pair_values(tb_store *s, const double *h_bias, const uint8_t *h_bad, int3
  * out_cis_total[0..1] = normalised interactions inside sections / in total, off-diagonal pairs. */
 int tb_decay_sums(tb_store *s, const double *h_bias, const uint8_t *h_bad, double *h_nrm,
                   int64_t *h_raw, double out_cis_total[2]);
+/* N3 (the HiC_data part) -- HiC_data.get_matrix / yield_matrix / write_matrix
+ * (_pytadbit/hic_data.py:578-686, :1514-1582): the dense window rows [row_begin, row_end) x columns
+ * [col_begin, col_end) of the full symmetric matrix, row-major into h_out: the count, or
+ * count / bias[i] / bias[j] when h_bias is given; cells without contacts are 0.  A row-sharded
+ * store fills only the rows it owns. */
+int tb_window(tb_store *s, int64_t row_begin, int64_t row_end, int64_t col_begin, int64_t col_end,
+              const double *h_bias, double *h_out);
 
 #ifdef __cplusplus
 }

@@ -282,6 +282,49 @@ def reference_pair_cases(ns):
     return index
 
 
+def reference_window_cases(ns):
+    """N3 (HiC_data part): get_matrix / yield_matrix / write_matrix of the UNMODIFIED reference
+    (_pytadbit/hic_data.py:578-686, :1514-1582) on a seeded 3-chromosome matrix."""
+    import tempfile
+    rng = np.random.default_rng(606)
+    sizes = [40, 25, 15]
+    n, r, c, v = synth_dense(rng, sizes, a=300.0, trans=0.4, low_frac=0.1, empty_frac=0.05)
+    names = ["chrA", "chrB", "chrC"]
+    hic = build_reference(ns, n, r, c, v, sizes, names)
+    hic.resolution = 10000
+    with contextlib.redirect_stderr(io.StringIO()), contextlib.redirect_stdout(io.StringIO()):
+        hic.filter_columns(silent=True)
+        hic.normalize_hic(iterations=30, max_dev=1e-5, silent=True)
+    rec = OrderedDict(name="window_3chrom", size=n, chromosomes=list(zip(names, sizes)), resolution=10000,
+                      bads=jsonable_bads(hic.bads), bias=[float(hic.bias[i]) for i in range(n)], calls=[])
+    focuses = [None, (5, 30), (3, 20, 41, 70), "chrB", ("chrA", "chrC"), "chrA:50000-250000"]
+    for focus in focuses:
+        for normalized in (False, True):
+            for diagonal in (True, False):
+                m = hic.get_matrix(focus=focus, diagonal=diagonal, normalized=normalized)
+                item = OrderedDict(fn="get_matrix", focus=focus, normalized=normalized, diagonal=diagonal,
+                                   value=[[float(x) for x in row] for row in m])
+                rec["calls"].append(item)
+                if isinstance(focus, str) and ":" in focus:
+                    continue                       # yield_matrix / write_matrix do not parse ranges
+                lines = list(hic.yield_matrix(focus=focus, diagonal=diagonal, normalized=normalized))
+                rec["calls"].append(OrderedDict(fn="yield_matrix", focus=focus, normalized=normalized,
+                                                diagonal=diagonal,
+                                                value=[[float(x) for x in row] for row in lines]))
+    mm = hic.get_matrix(focus=(2, 30), normalized=True, masked=True)
+    rec["masked"] = OrderedDict(focus=(2, 30), mask=np.asarray(mm.mask).astype(int).tolist())
+    with tempfile.TemporaryDirectory() as tmp:
+        for tag, kw in (("raw", dict()), ("norm_focus", dict(focus="chrB", normalized=True, diagonal=False))):
+            fname = os.path.join(tmp, "m.tsv")
+            hic.write_matrix(fname, **kw)
+            rec["write_" + tag] = open(fname).read()
+    np.savez_compressed(os.path.join(OUT, "window_3chrom.npz"), size=n, rows=r.astype(np.int32),
+                        cols=c.astype(np.int32), vals=v)
+    with open(os.path.join(OUT, "window_3chrom.json"), "w") as fh:
+        json.dump(rec, fh)
+    return ["window_3chrom"]
+
+
 class _NowPool(object):
     """Stand-in for multiprocessing.Pool: the reference's tail farms its three helper functions out
     to worker processes; here they run in place (same functions, same arguments)."""
@@ -488,9 +531,11 @@ def main():
     reference_known_answers(ns)
     pair_cases = reference_pair_cases(ns)
     decay_cases = reference_decay_cases(ns)
+    window_cases = reference_window_cases(ns)
 
     with open(os.path.join(OUT, "INDEX.json"), "w") as fh:
-        json.dump(dict(cases=index, pair_cases=pair_cases, decay_cases=decay_cases, numpy=np.__version__,
+        json.dump(dict(cases=index, pair_cases=pair_cases, decay_cases=decay_cases, window_cases=window_cases,
+                       numpy=np.__version__,
                        generator="oracle/gen_golden.py", reference="TADbit v1.1 (unmodified, via oracle/ref_shim.py)"), fh, indent=1)
 
 

@@ -541,6 +541,16 @@ int tb_decay_sums(tb_store *s, const double *h_bias, const uint8_t *h_bad, doubl
   });
 }
 
+int tb_window(tb_store *s, int64_t row_begin, int64_t row_end, int64_t col_begin, int64_t col_end,
+              const double *h_bias, double *h_out) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(s, "null argument");
+    DeviceGuard g(s->device);
+    window(s, row_begin, row_end, col_begin, col_end, h_bias, h_out);
+    return TB_OK;
+  });
+}
+
 int tb_diag_sums(tb_store *s, const uint8_t *h_bad, int64_t ndiag, int64_t *h_sum_d) {
   return guarded([&]() -> int {
     TB_REQUIRE(s, "null argument");

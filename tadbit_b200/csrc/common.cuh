@@ -125,7 +125,10 @@ constexpr int kPanel = 4096;      // column panel of the chunk planner / dense e
 constexpr int kSub = TB_KSUB;     // bytes per row per pipeline stage of k_rowsum_dense
 constexpr int kRows = 4;          // dense chunks (rows) one warp walks together
 constexpr int kXPad = 16384;      // zero tail of the gathered vector (panels / windows read past N)
-constexpr int kTileRows = 2048;   // rows of a sparse tile (two per thread of a k_rowsum_tiles CTA)
+#ifndef TB_TILE_ROWS
+#define TB_TILE_ROWS 4096                 // measured on the genome-wide 5 kb matrix: tile kernel 1.067 ms with
+#endif                                    // 4096 rows per tile (229.8 KB of shared memory), 1.163 ms with 2048
+constexpr int kTileRows = TB_TILE_ROWS;   // rows of a sparse tile (2048 or 4096: per-unit accumulators in shared memory)
 constexpr int kTileCols = 4 * kPanel;  // columns of a sparse tile = x window in shared memory (128 KB)
 constexpr int kTileValBits = 15;  // packed tile cell: (column offset * 4) << 16 | value, value < 2^15
 
@@ -286,6 +289,7 @@ void pair_values(tb_store *s, const double *h_bias, const uint8_t *h_bad, int zs
                  int64_t *n, int32_t *h_row, int32_t *h_col, double *h_val);
 void decay_sums(tb_store *s, const double *h_bias, const uint8_t *h_bad, double *h_nrm, int64_t *h_raw,
                 double out[2]);
+void window(tb_store *s, int64_t r0, int64_t r1, int64_t c0, int64_t c1, const double *h_bias, double *h_out);
 // comm.cu
 void comm_unique_id(uint8_t id[128]);
 void comm_init(tb_store *s, int rank, int world, const uint8_t id[128]);

@@ -212,6 +212,25 @@ struct DecayVisitor {
   }
 };
 
+// N3: a dense window of the (normalised) matrix, rows [r0, r1) x columns [c0, c1)
+struct WindowVisitor {
+  static constexpr int kShared = 0;
+  static constexpr int kThreads = 256;
+  int64_t r0, r1, c0, c1;
+  const double *w;                    // biases, or null for raw counts
+  double *out;                        // [(r1 - r0) * (c1 - c0)], zero-initialised
+  __device__ void begin(uint8_t *) {}
+  __device__ bool block(int64_t i0, int64_t i1, int64_t j0, int64_t j1) {
+    return i0 < r1 && i1 > r0 && j0 < c1 && j1 > c0;
+  }
+  __device__ bool row(int64_t i) { return i >= r0 && i < r1; }
+  __device__ void cell(int64_t i, int64_t j, int32_t v) {
+    if (j < c0 || j >= c1) return;
+    out[(i - r0) * (c1 - c0) + (j - c0)] = w ? (double)v / w[i] / w[j] : (double)v;
+  }
+  __device__ void end(uint8_t *) {}
+};
+
 struct Weights {
   DevBuf<double> w;
   DevBuf<uint8_t> skip;
@@ -408,6 +427,33 @@ void decay_sums(tb_store *s, const double *h_bias, const uint8_t *h_bad, double 
   TB_CUDA(cudaStreamSynchronize(st));
   out[0] = cis;
   out[1] = total;
+}
+
+// Dense window rows [r0, r1) x columns [c0, c1) of the full symmetric matrix: counts, or
+// count / bias[i] / bias[j] when h_bias is given (HiC_data.get_matrix / yield_matrix,
+// _pytadbit/hic_data.py:632-686, :1514-1582).  A row-sharded store fills the rows it owns.
+void window(tb_store *s, int64_t r0, int64_t r1, int64_t c0, int64_t c1, const double *h_bias, double *h_out) {
+  cudaStream_t st = s->stream;
+  const int64_t N = s->nbins;
+  TB_REQUIRE(r0 >= 0 && r0 <= r1 && r1 <= N && c0 >= 0 && c0 <= c1 && c1 <= N && h_out, "window: bad arguments");
+  const int64_t cells = (r1 - r0) * (c1 - c0);
+  if (cells == 0) return;
+  TB_REQUIRE(cells < (1LL << 33), "window: more than 2^33 cells requested");
+  DevBuf<double> out;
+  out.alloc(cells);
+  TB_CUDA(cudaMemsetAsync(out.p, 0, out.bytes(), st));
+  const double *w = nullptr;
+  if (h_bias) {
+    TB_CUDA(cudaMemcpyAsync(s->b.p, h_bias, N * sizeof(double), cudaMemcpyHostToDevice, st));
+    w = s->b.p;
+  }
+  WindowVisitor vis;
+  vis.r0 = r0; vis.r1 = r1; vis.c0 = c0; vis.c1 = c1;
+  vis.w = w;
+  vis.out = out.p;
+  visit_upper(s, vis, true);            // whole rows: the window may lie below the diagonal
+  TB_CUDA(cudaMemcpyAsync(h_out, out.p, out.bytes(), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
 }
 
 }  // namespace tb

@@ -112,18 +112,44 @@ __device__ __forceinline__ double tile_sum(const TileSums &ts, int64_t r) {
   return a;
 }
 
-// row sum of owned row r = its chunk partials in chunk order + its sparse-tile sums
+// row sum of owned row r = its chunk partials in chunk order + its sparse-tile sums.  The two
+// chains of dependent loads (row -> chunks -> partials, row block -> units -> partials) are started
+// together: two round trips to L2 instead of four or five.
 __device__ __forceinline__ double row_total(const double *__restrict__ pf, const int64_t *__restrict__ row_chunk,
                                             const TileSums &ts, int64_t r) {
   int64_t c = row_chunk[r];
   const int64_t c1 = row_chunk[r + 1];
-  double a = 0.0;
-  for (; c + 4 <= c1; c += 4) {
+  int32_t u = 0, u1 = 0;
+  const double *p = nullptr;
+  if (ts.partial) {
+    const int64_t rb = r / kTileRows;
+    u = ts.unit_of_rb[rb];
+    u1 = ts.unit_of_rb[rb + 1];
+    p = ts.partial + (r % kTileRows);
+  }
+  // first batch of both lists at once
+  double v[4], w[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = c + k < c1 ? pf[c + k] : 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) w[k] = u + k < u1 ? p[(int64_t)(u + k) * kTileRows] : 0.0;
+  double a = 0.0, t = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) if (c + k < c1) a += v[k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) if (u + k < u1) t += w[k];
+  for (c += 4; c + 4 <= c1; c += 4) {
     const double v0 = pf[c], v1 = pf[c + 1], v2 = pf[c + 2], v3 = pf[c + 3];
     a += v0; a += v1; a += v2; a += v3;
   }
   for (; c < c1; ++c) a += pf[c];
-  return a + tile_sum(ts, r);
+  for (u += 4; u + 4 <= u1; u += 4) {
+    const double v0 = p[(int64_t)u * kTileRows], v1 = p[(int64_t)(u + 1) * kTileRows];
+    const double v2 = p[(int64_t)(u + 2) * kTileRows], v3 = p[(int64_t)(u + 3) * kTileRows];
+    t += v0; t += v1; t += v2; t += v3;
+  }
+  for (; u < u1; ++u) t += p[(int64_t)u * kTileRows];
+  return a + t;
 }
 
 // Rows kept by copy_matrix (normalize_hic.py:165-177): not bad, and at least one stored cell whose
@@ -442,9 +468,20 @@ k_ice_exchange(PeerView pv, const double *__restrict__ pf, const int64_t *__rest
                TileSums ts, int64_t nrows, int64_t rb, int64_t n, double *__restrict__ x,
                double *__restrict__ b, const uint8_t *__restrict__ bad, uint8_t *__restrict__ present,
                const double *__restrict__ live, int iterations, double max_dev,
-               double *__restrict__ block_red, double *__restrict__ trace, IceState *state) {
+               double *__restrict__ block_red, double *__restrict__ trace, IceState *state,
+               unsigned long long *__restrict__ prof) {
   volatile IceState *vs = state;
   if (vs->stopped) return;
+  // TB_TIMING=1: CTA 0 adds the time it spends in each phase (ns, %globaltimer) to prof[0..5]
+  unsigned long long tprev = 0;
+  auto lap = [&](int k) {
+    if (prof && blockIdx.x == 0 && threadIdx.x == 0) {
+      const unsigned long long t = now_ns();
+      if (k >= 0) prof[k] += t - tprev;
+      tprev = t;
+    }
+  };
+  lap(-1);
   __shared__ double sh[4 * (kXThreads / 32)];
   __shared__ int s_last, s_fault;
   const int pass = vs->passes_done;
@@ -472,14 +509,18 @@ k_ice_exchange(PeerView pv, const double *__restrict__ pf, const int64_t *__rest
         }
     }
   }
-  __threadfence_system();
+  lap(0);
+  if (pv.world > 1) __threadfence_system();      // the stores to the peers are out before the flag is
+  else __threadfence();
   __syncthreads();
+  lap(1);
   // 2. publish once every CTA has stored, then wait for every peer
   if (threadIdx.x == 0) {
     const unsigned int t = atomicAdd(&state->arrive1, 1u);
     if (t == gridDim.x - 1) {
       state->arrive1 = 0;
-      __threadfence_system();
+      if (pv.world > 1) __threadfence_system();
+      else __threadfence();
 #pragma unroll
       for (int q = 0; q < kMaxPeers; ++q)
         if (q < pv.world) st_release_sys(pv.flag[q] + pv.rank, epoch);
@@ -496,6 +537,7 @@ k_ice_exchange(PeerView pv, const double *__restrict__ pf, const int64_t *__rest
     if (threadIdx.x == 0) { vs->fault = 1; vs->stopped = 1; }
     return;
   }
+  lap(2);
   // 3. statistics of the pass
   const double *sfull = buf ? pv.mine[1] : pv.mine[0];
   double sum = 0.0, mn = INFINITY, mx = -INFINITY;
@@ -536,6 +578,7 @@ k_ice_exchange(PeerView pv, const double *__restrict__ pf, const int64_t *__rest
       st_release_gpu(&state->fold_epoch, epoch);
     }
   }
+  lap(3);
   // 4. every CTA waits for the decision, then updates its part of B and x
   if (threadIdx.x == 0) {
     const unsigned long long t0 = now_ns();
@@ -548,6 +591,7 @@ k_ice_exchange(PeerView pv, const double *__restrict__ pf, const int64_t *__rest
     if (threadIdx.x == 0) { vs->fault = 1; vs->stopped = 1; }
     return;
   }
+  lap(4);
   if (vs->passes_done != pass + 1 || vs->all_bad || vs->zero_div) return;
   const double mean = vs->mean_s;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
@@ -561,6 +605,7 @@ k_ice_exchange(PeerView pv, const double *__restrict__ pf, const int64_t *__rest
     b[i] = bi;
     x[i] = (bi != 0.0) ? 1.0 / bi : 0.0;     // B == 0: row frozen by the ZeroDivisionError skip
   }
+  lap(5);
 }
 
 __global__ void k_ice_finalize(const double *__restrict__ b, const uint8_t *__restrict__ present,
@@ -984,6 +1029,11 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
   const double *live = live_counts(s);
   if (!csr_walk) clear_tile_chunk_partials(s);
   double *dst = s->world > 1 ? s->s_part.p : s->s_full.p;      // separate-step path only
+  DevBuf<unsigned long long> prof;
+  if (split && fused) {
+    prof.alloc(8);
+    TB_CUDA(cudaMemsetAsync(prof.p, 0, prof.bytes(), st));
+  }
   // The host only needs to know WHEN the loop stopped: passes queued after the stop are no-ops
   // on the device.  ICE converges geometrically, so the next look is scheduled where the
   // deviation is predicted to cross max_dev (at most 16 passes ahead).
@@ -1000,7 +1050,7 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
     if (fused) {
       k_ice_exchange<<<exchange_grid(s), kXThreads, 0, st>>>(
           s->px.view, s->partial_f.p, s->row_chunk.p, ts, s->nrows, s->row_begin, N, s->x.p, s->b.p,
-          s->bad.p, s->present.p, live, iterations, max_dev, s->block_red.p, s->trace.p, s->state.p);
+          s->bad.p, s->present.p, live, iterations, max_dev, s->block_red.p, s->trace.p, s->state.p, prof.p);
     } else if (s->world > 1) {
       if (s->nrows)
         k_combine_f64<<<grid_1d(s->nrows, 256, s->sm_count), 256, 0, st>>>(
@@ -1100,6 +1150,14 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
       fprintf(stderr, "[tadbit_b200] rank %d: per pass row sum %.1f us, %s %.1f us, whole pass %.1f us (%d passes)\n",
               s->rank, 1e3 * s->rowsum_ms / cnt, fused ? "fused exchange + statistics + update" : "statistics + update",
               1e3 * s->exchange_ms / cnt, 1e3 * s->loop_ms / cnt, cnt);
+    if (prof.p) {
+      unsigned long long h[8];
+      TB_CUDA(cudaMemcpy(h, prof.p, sizeof(h), cudaMemcpyDeviceToHost));
+      fprintf(stderr, "[tadbit_b200] rank %d: k_ice_exchange CTA 0 per pass: row sums + peer stores %.1f us, fence + "
+                      "CTA barrier %.1f us, arrive + publish + wait for peers %.1f us, statistics + arrive %.1f us, "
+                      "fold + wait for decision %.1f us, update %.1f us\n", s->rank, 1e-3 * h[0] / cnt,
+              1e-3 * h[1] / cnt, 1e-3 * h[2] / cnt, 1e-3 * h[3] / cnt, 1e-3 * h[4] / cnt, 1e-3 * h[5] / cnt);
+    }
   }
   return rc;
 }

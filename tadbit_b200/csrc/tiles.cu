@@ -61,13 +61,13 @@ namespace {
 #define TB_FILL_HIST 1      // k_tile_fill counts residues in a shared-memory histogram per warp (match_any +
 #endif                      // one add per group); 0 = 32 ballots per 32 cells (measured on the genome-wide
                             // 5 kb matrix: tile build 103 ms vs 165 ms, same layout)
-constexpr int kSortThreads = kTileRows / 2;                // k_tile_sort
+constexpr int kSortThreads = kTileRows / 2 < 1024 ? kTileRows / 2 : 1024;   // k_tile_sort
 constexpr int kTileWarps = TB_TILE_WARPS;                  // warps of a k_rowsum_tiles CTA
 constexpr int kTileThreads = kTileWarps * 32;
 constexpr int kPieceBlocks = 4;                            // 512-byte blocks per ring stage
 constexpr int kSlices = kTileRows / 32;
 constexpr int kSliceTab = 2 * kSlices + 1;                 // (ones start, general start) per slice + end
-constexpr int kRowBits = 11;                               // kTileRows = 2048
+constexpr int kRowBits = kTileRows == 4096 ? 12 : 11;      // kTileRows = 2048 | 4096
 constexpr int kWinBytes = kTileCols * 8;
 constexpr int kZeroTail = 128;                             // 16 zeros behind the window (ones padding)
 constexpr int kWarpSlices = kSlices / kTileWarps;          // slices of a tile one warp streams

@@ -301,6 +301,169 @@ class HiC_data(object):
             bias = BinVector(values * target)
         self.bias = bias
 
+    # -- dense windows (the HiC_data part) ---------------------------------
+    def _bias_array(self):
+        bias = self.bias
+        if isinstance(bias, BinVector):
+            return bias.to_array()
+        return np.array([bias[i] for i in range(self.__size)], dtype=np.float64)
+
+    def _window(self, r0, r1, c0, c1, normalized):
+        """Rows [r0, r1) x columns [c0, c1) as nested lists: ints, or count / bias[i] / bias[j]
+        (one kernel over the resident cells, ``tb_window``, instead of a dict lookup per cell)."""
+        r0, r1, c0, c1 = max(r0, 0), min(r1, self.__size), max(c0, 0), min(c1, self.__size)
+        if normalized:
+            return self.store.window(r0, r1, c0, c1, self._bias_array()).tolist()
+        return np.rint(self.store.window(r0, r1, c0, c1)).astype(np.int64).tolist()
+
+    def _focus_simple(self, focus):
+        """Window of write_matrix / yield_matrix (hic_data.py:590-610, :1532-1551)."""
+        if focus:
+            if isinstance(focus, tuple) and isinstance(focus[0], int):
+                if len(focus) == 2:
+                    start1, end1 = focus
+                    start2, end2 = focus
+                    start1 -= 1
+                    start2 -= 1
+                else:
+                    start1, end1, start2, end2 = focus
+                    start1 -= 1
+                    start2 -= 1
+            elif isinstance(focus, tuple) and isinstance(focus[0], str):
+                start1, end1 = self.section_pos[focus[0]]
+                start2, end2 = self.section_pos[focus[1]]
+            else:
+                start1, end1 = self.section_pos[focus]
+                start2, end2 = self.section_pos[focus]
+        else:
+            start1 = start2 = 0
+            end1 = end2 = len(self)
+        return start1, end1, start2, end2
+
+    def _focus_coords(self, focus):
+        """hic_data.py:688-738 (chromosome names may carry a 'chr:beg-end' range in base pairs)."""
+        siz = len(self)
+        if focus:
+            if isinstance(focus, tuple) and isinstance(focus[0], int):
+                if len(focus) == 2:
+                    start1, end1 = focus
+                    start2, end2 = focus
+                    start1 -= 1
+                    start2 -= 1
+                else:
+                    start1, end1, start2, end2 = focus
+                    start1 -= 1
+                    start2 -= 1
+            elif isinstance(focus, tuple) and isinstance(focus[0], str):
+                start1, end1 = self.section_pos[focus[0].split(':')[0]]
+                start2, end2 = self.section_pos[focus[1].split(':')[0]]
+                if ':' in focus[0]:
+                    pos = focus[0].split(':')[1]
+                    try:
+                        pos1, pos2 = [int(p) // self.resolution
+                                      for p in pos.split('-')]
+                    except ValueError:
+                        raise Exception('ERROR: should be in format "chr3:10000:20000"')
+                    start1, end1 = start1 + pos1, start1 + pos2
+                if ':' in focus[1]:
+                    pos = focus[0].split(':')[1]
+                    try:
+                        pos1, pos2 = [int(p) // self.resolution
+                                      for p in pos.split('-')]
+                    except ValueError:
+                        raise Exception('ERROR: should be in format "chr3:10000:20000"')
+                    start2, end2 = start1 + pos1, start1 + pos2
+            else:
+                start1, end1 = self.section_pos[focus.split(':')[0]]
+                if ':' in focus:
+                    pos = focus.split(':')[1]
+                    try:
+                        pos1, pos2 = [int(p) // self.resolution
+                                      for p in pos.split('-')]
+                    except ValueError:
+                        raise Exception('ERROR: should be in format "chr3:10000:20000"')
+                    start1, end1 = start1 + pos1, start1 + pos2
+                start2, end2 = start1, end1
+        else:
+            start1 = start2 = 0
+            end1 = end2 = siz
+        return start1, start2, end1, end2
+
+    def get_matrix(self, focus=None, diagonal=True, normalized=False, masked=False):
+        """A window of the matrix as a list of lists (hic_data.py:632-686).
+
+        :param None focus: ``(start, end)`` (1-based, inclusive), a chromosome name, or a tuple of two
+        :param True diagonal: if False the diagonal is replaced by ones, or zeroes if normalized
+        :param False normalized: divide the counts by the biases
+        :param False masked: return a masked array built from the bad columns
+        """
+        if normalized and not self.bias:
+            raise Exception('ERROR: experiment not normalized yet')
+        start1, start2, end1, end2 = self._focus_coords(focus)
+        # matrix[j - start1][i - start2] = self[i, j] / bias[i] / bias[j]: the window is computed with
+        # i as its row (the same order of the two divisions) and transposed
+        matrix = [list(col) for col in zip(*self._window(start2, end2, start1, end1, normalized))]
+        if not matrix:
+            matrix = [[] for _ in range(start1, end1)]
+        if not diagonal and start1 == start2:
+            for i in range(len(matrix)):
+                if normalized:
+                    matrix[i][i] = 0
+                else:
+                    matrix[i][i] = 1 if matrix[i][i] else 0
+        if masked:
+            from numpy import ma, zeros_like
+            bads1 = [b - start1 for b in self.bads if start1 <= b < end1]
+            bads2 = [b - start2 for b in self.bads if start2 <= b < end2]
+            m = zeros_like(matrix)
+            for bad1 in bads1:
+                m[:, bad1] = 1
+                for bad2 in bads2:
+                    m[bad2, :] = 1
+            matrix = ma.masked_array(matrix, m)
+        return matrix
+
+    def yield_matrix(self, focus=None, diagonal=True, normalized=False):
+        """The window line by line; bad rows come out as null rows (hic_data.py:1514-1582)."""
+        if normalized and not self.bias:
+            raise Exception('ERROR: experiment not normalized yet')
+        start1, end1, start2, end2 = self._focus_simple(focus)
+        step = max(1, (1 << 24) // max(end1 - start1, 1))           # 128 MB of doubles per slab
+        for lo in range(start2, end2, step):
+            hi = min(lo + step, end2)
+            rows = self._window(lo, hi, start1, end1, normalized)
+            for i, line in zip(range(lo, hi), rows):
+                if i in self.bads:
+                    yield [0.0 if normalized else 0 for _ in range(start1, end1)]
+                    continue
+                if not (diagonal or start1 != start2) and start1 <= i < end1:
+                    line[i - start1] = 0.0 if normalized else 0
+                yield line
+
+    def write_matrix(self, fname, focus=None, diagonal=True, normalized=False):
+        """hic_data.py:578-630."""
+        start1, end1, start2, end2 = self._focus_simple(focus)
+        out = open(fname, 'w')
+        out.write('# MASKED %s\n' % (','.join([str(k - start1)
+                                               for k in list(self.bads.keys())
+                                               if start1 <= k <= end1])))
+        rownam = ['%s\t%d-%d' % (k[0],
+                                 k[1] * self.resolution + 1,
+                                 (k[1] + 1) * self.resolution)
+                  for k in sorted(self.sections,
+                                  key=lambda x: self.sections[x])
+                  if start2 <= self.sections[k] < end2]
+        if rownam:
+            for line in self.yield_matrix(focus=focus, diagonal=diagonal,
+                                          normalized=normalized):
+                out.write(rownam.pop(0) + '\t' +
+                          '\t'.join([str(i) for i in line]) + '\n')
+        else:
+            for line in self.yield_matrix(focus=focus, diagonal=diagonal,
+                                          normalized=normalized):
+                out.write('\t'.join([str(i) for i in line]) + '\n')
+        out.close()
+
     def save_biases(self, fnam, protocol=None):
         """Pickle biases, decay and bad columns in the reference's format
         (hic_data.py:415-429): plain dicts, readable by TADbit's loaders."""

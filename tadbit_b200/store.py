@@ -318,6 +318,15 @@ class ContactStore(object):
                                        ptr(v, C.c_double)))
         return r, c, v
 
+    def window(self, r0, r1, c0, c1, bias=None):
+        """Dense float64 window rows [r0, r1) x columns [c0, c1) of the full symmetric matrix: counts,
+        or count / bias[i] / bias[j]."""
+        b, bp = self._bias(bias)
+        out = np.zeros((max(r1 - r0, 0), max(c1 - c0, 0)), dtype=np.float64)
+        if out.size:
+            check(lib().tb_window(self._h, int(r0), int(r1), int(c0), int(c1), bp, ptr(out, C.c_double)))
+        return out
+
     def decay_sums(self, bias, bad=None):
         """Per section and distance: (normalised sums float64[N], raw sums int64[N]) indexed by
         first bin of the section + distance, and (cis, total) normalised off-diagonal sums."""

@@ -54,6 +54,13 @@ class NumpyStore(object):
             v = (np.log10(v) - zscore[0]) / zscore[1]
         return r.astype(np.int32), c.astype(np.int32), v
 
+    def window(self, r0, r1, c0, c1, bias=None):           # tb_window
+        full = self.m.full_csr(dtype=np.float64)[r0:r1, c0:c1].toarray()
+        if bias is not None:
+            b = np.asarray(bias, dtype=np.float64)
+            full = full / b[r0:r1, None] / b[None, c0:c1]
+        return full
+
     def decay_sums(self, bias, bad=None):                  # tb_decay_sums
         return orc.decay_sums(self.m, bias, self._bads(bad))
 
