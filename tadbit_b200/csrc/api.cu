@@ -148,7 +148,7 @@ using namespace tb;
 
 extern "C" {
 
-int tb_version(void) { return 200; }
+int tb_version(void) { return 200 + (TB_CHECK ? 1000 : 0); }     /* +1000: the checked build */
 
 const char *tb_last_error(void) { return g_error; }
 

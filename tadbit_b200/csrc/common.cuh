@@ -116,6 +116,34 @@ struct PeerExchange {
   PeerView view = {};
 };
 
+// -DTB_CHECK=1: a debug build with bounds assertions on every descriptor / ring / gather index of
+// the hot kernels (compute-sanitizer is not available on the GPU pool).  A failed assertion prints
+// its source line and traps, which the host sees as a CUDA error.  tools/kernel_coverage.py runs
+// under this build in the GPU tests (tadbit_b200/variants/check.so, built by __graft_entry__.build()).
+#ifndef TB_CHECK
+#define TB_CHECK 0
+#endif
+#if TB_CHECK
+#include <stdio.h>
+#define TB_DCHECK(cond)                                                                        \
+  do {                                                                                         \
+    if (!(cond)) {                                                                             \
+      printf("TB_CHECK failed %s:%d: %s (block %d thread %d)\n", __FILE__, __LINE__, #cond,    \
+             (int)blockIdx.x, (int)threadIdx.x);                                               \
+      __trap();                                                                                \
+    }                                                                                          \
+  } while (0)
+#else
+#define TB_DCHECK(cond) do { } while (0)
+#endif
+struct CheckLimits {               // sizes the assertions compare against (one copy per translation unit)
+  long long nbins, nrows, nchunks, enc_bytes, n_groups;
+  long long t_cell_words, t_ntiles, t_nunits, t_ndesc, t_nlist;
+};
+#if TB_CHECK
+static __constant__ CheckLimits c_lim;
+#endif
+
 constexpr int kWarp = 32;
 constexpr int kChunk = 4096;      // max stored cells one warp reduces before writing a partial
 constexpr int kPanel = 4096;      // column panel of the chunk planner / dense encodings
@@ -247,6 +275,18 @@ struct tb_store {
 };
 
 namespace tb {
+#if TB_CHECK
+inline void set_check_limits(const tb_store *s) {   // before a checked launch, in that kernel's translation unit
+  CheckLimits h;
+  h.nbins = s->nbins; h.nrows = s->nrows; h.nchunks = s->nchunks; h.enc_bytes = s->enc_bytes;
+  h.n_groups = s->n_groups;
+  h.t_cell_words = (long long)s->t_cells.n; h.t_ntiles = s->t_nrb * s->t_nwin; h.t_nunits = s->t_nunits;
+  h.t_ndesc = (long long)s->t_desc.n; h.t_nlist = (long long)s->t_list.n;
+  cudaMemcpyToSymbolAsync(c_lim, &h, sizeof(h), 0, cudaMemcpyHostToDevice, s->stream);
+}
+#else
+inline void set_check_limits(const tb_store *) {}
+#endif
 // build.cu
 void build_from_coo(tb_store *s, int64_t nnz, const int32_t *row, const int32_t *col,
                     const int32_t *val, int mem);

@@ -119,6 +119,7 @@ __device__ __forceinline__ double row_total(const double *__restrict__ pf, const
                                             const TileSums &ts, int64_t r) {
   int64_t c = row_chunk[r];
   const int64_t c1 = row_chunk[r + 1];
+  TB_DCHECK(c >= 0 && c <= c1 && c1 <= c_lim.nchunks && r < c_lim.nrows);
   int32_t u = 0, u1 = 0;
   const double *p = nullptr;
   if (ts.partial) {
@@ -126,6 +127,7 @@ __device__ __forceinline__ double row_total(const double *__restrict__ pf, const
     u = ts.unit_of_rb[rb];
     u1 = ts.unit_of_rb[rb + 1];
     p = ts.partial + (r % kTileRows);
+    TB_DCHECK(u >= 0 && u <= u1 && u1 <= c_lim.t_nunits);
   }
   // first batch of both lists at once
   double v[4], w[4];
@@ -910,6 +912,7 @@ void masked_row_sums(tb_store *s, long long *dst) {
   cudaStream_t st = s->stream;
   const int64_t N = s->nbins;
   if (!s->nrows) return;
+  set_check_limits(s);
   const int rgrid = grid_1d(s->nrows, 256, s->sm_count);
   if (s->positive && !use_csr_rowsum(s)) {
     // K1 with x = the good mask: every term and every partial sum is an integer below 2^53
@@ -1010,6 +1013,7 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
   if (s->trace.n < (size_t)npass_max * 4) s->trace.alloc((size_t)npass_max * 4);
   if (!s->px.ready) exchange_setup(s);
   const bool fused = use_fused_exchange(s);
+  set_check_limits(s);
   upload_bad(s, h_bad);
   const int vg = grid_1d(N, 256, s->sm_count);
   int rg = grid_1d(N, kRedThreads, s->sm_count, 4);
@@ -1166,6 +1170,7 @@ void norm_sum(tb_store *s, const double *h_bias, const uint8_t *h_bad, double *o
   cudaStream_t st = s->stream;
   const int64_t N = s->nbins;
   TB_REQUIRE(out, "norm_sum: null output");
+  set_check_limits(s);
   upload_bad(s, h_bad);
   if (!h_bias) {        // raw sum: exact integers
     masked_row_sums(s, s->i_full.p);
@@ -1243,6 +1248,7 @@ void ice_batch(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max
   const int64_t N = s->nbins;
   TB_REQUIRE(iterations >= 0, "ice_batch: iterations must be >= 0");
   TB_REQUIRE(s->world == 1, "ice_batch: batches are not sharded (one replica per GPU)");
+  set_check_limits(s);
   const int nseg = (int)s->chrom_offsets.size() - 1;
   const int npass_max = iterations + 1;
   DevBuf<SegState> seg;

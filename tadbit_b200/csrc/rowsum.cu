@@ -202,6 +202,11 @@ k_rowsum_dense(const uint8_t *__restrict__ data, const GroupRec *__restrict__ re
       mbar_expect_tx(bar, (uint32_t)(nvalid * kSub));
 #pragma unroll
       for (int r = 0; r < kRows; ++r)
+        if (poff[r] != 0xffffffffu) {
+          TB_DCHECK(((long long)poff[r] << 4) + ((long long)psub + 1) * kSub <= c_lim.enc_bytes);
+        }
+#pragma unroll
+      for (int r = 0; r < kRows; ++r)
         if (poff[r] != 0xffffffffu)
           bulk_g2s(ring_u32 + (stage * kRows + r) * kSub,
                    data + ((int64_t)poff[r] << 4) + (int64_t)psub * kSub, kSub, bar);
@@ -245,6 +250,7 @@ k_rowsum_dense(const uint8_t *__restrict__ data, const GroupRec *__restrict__ re
               data + ((int64_t)cg.off16[r] << 4) + (int64_t)cg.nsub * kSub);
           for (int k = lane; k < novf[r]; k += 32) {
             const int2 e = __ldg(cells + k);
+            TB_DCHECK(e.x >= cg.c0 && e.x - cg.c0 < kPanel);
             lo[r] = fma(i2d(e.y), xs[e.x - cg.c0], lo[r]);
           }
         }
@@ -252,6 +258,7 @@ k_rowsum_dense(const uint8_t *__restrict__ data, const GroupRec *__restrict__ re
 #pragma unroll
       for (int r = 0; r < kRows; ++r) {
         const double a = warp_sum(lo[r] + hi[r]);
+        TB_DCHECK(cg.id[r] < c_lim.nchunks);
         if (lane == 0 && cg.id[r] >= 0) partial[cg.id[r]] = a;
         lo[r] = hi[r] = 0.0;
       }
@@ -263,6 +270,7 @@ k_rowsum_dense(const uint8_t *__restrict__ data, const GroupRec *__restrict__ re
   for (int64_t g = g0; g < g1;) {            // panel segments of the range
     const int4 head = __ldg(reinterpret_cast<const int4 *>(recs + g) + 2);   // c0, nsub, enc, seg_end
     const int64_t ge = head.w < g1 ? head.w : g1;
+    TB_DCHECK(g1 <= c_lim.n_groups && head.x >= 0 && (long long)head.x + kPanel <= c_lim.nbins + kXPad);
     __syncthreads();                         // every warp is done with the previous panel
     if (threadIdx.x == 0) {
       mbar_expect_tx(xbar, kPanelBytes);
@@ -299,9 +307,11 @@ __device__ __forceinline__ void sparse_chunk(const uint8_t *__restrict__ data, c
                                              const double *__restrict__ x, double *__restrict__ partial,
                                              double *wsum) {
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5, tid = threadIdx.x;
+  TB_DCHECK(c >= 0 && c < c_lim.nchunks);
   const int4 d = desc[c];
   const uint8_t *p = data + off[c];
   const int n = d.y;
+  TB_DCHECK(off[c] + (long long)n * 4 <= c_lim.enc_bytes);
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   if ((d.z & 0xff) == ENC_S16) {
     const double *xb = x + d.x;
@@ -375,6 +385,7 @@ void launch_rowsum(tb_store *s, const double *x, const IceState *state) {
 }
 
 void launch_rowsum_chunks(tb_store *s, const double *x, const IceState *state) {
+  set_check_limits(s);
   if (s->n_groups) {
     static bool attr_set[64] = {false};          // per device: the attribute is per context
     if (!attr_set[s->device & 63]) {

@@ -489,9 +489,11 @@ k_tile_desc(const int4 *__restrict__ unit, const int32_t *__restrict__ list,
 
 // ---- the pass kernel --------------------------------------------------------------------------
 __device__ __forceinline__ double cell_term(uint32_t c, const uint8_t *xw) {
+  TB_DCHECK((c >> 15) + 8u <= (uint32_t)kWinBytes && ((c >> 15) & 7u) == 0u);
   return u2d(c & 0xffffu) * *reinterpret_cast<const double *>(xw + (c >> 15));
 }
 __device__ __forceinline__ double x_at(uint32_t byte_off, const uint8_t *xw) {
+  TB_DCHECK(byte_off + 8u <= (uint32_t)(kWinBytes + kZeroTail));
   return *reinterpret_cast<const double *>(xw + byte_off);
 }
 
@@ -585,16 +587,21 @@ k_rowsum_tiles(const uint32_t *__restrict__ cells, const uint2 *__restrict__ des
     const unsigned int ui = *s_next;
     if (ui >= nunits) break;
     const int u = order[ui];
+    TB_DCHECK(u >= 0 && u < c_lim.t_nunits);
     const int4 un = unit[u];
+    TB_DCHECK(un.y >= 0 && un.y <= un.z && un.z <= c_lim.t_nlist);
     const int i0 = un.y, n = un.z - un.y;
 #pragma unroll
     for (int e = t; e < kTileRows; e += kTileThreads) acc[e] = 0.0;
     const int64_t dbeg = desc_off[(int64_t)u * kTileWarps + wic];
     const int nd = (int)(desc_off[(int64_t)u * kTileWarps + wic + 1] - dbeg);
     const uint2 *dp = desc + dbeg;
+    TB_DCHECK(nd >= 1 && dbeg >= 0 && dbeg + nd <= c_lim.t_ndesc);
     // start the copy of piece `e` into `stage`; fetch the rows of its slice if it ends one
     auto issue = [&](int stage, const uint2 &e, uint32_t &row) {
       const uint32_t nb = (e.y >> 26) & 15u;
+      TB_DCHECK(nb <= (uint32_t)kPieceBlocks && ((long long)e.x + nb) * 128 <= c_lim.t_cell_words);
+      TB_DCHECK((long long)(e.y & kDescGroupMask) < c_lim.t_ntiles * kSlices);
       if (nb && lane == 0) {
         mbar_expect_tx(rbar + 8 * stage, nb * 512u);
         bulk_g2s(ring_u32 + stage * kPieceBytes, cells + (size_t)e.x * 128, nb * 512u, rbar + 8 * stage);
@@ -610,7 +617,9 @@ k_rowsum_tiles(const uint32_t *__restrict__ cells, const uint2 *__restrict__ des
     for (int j = 0; j < n; ++j) {
       __syncthreads();                       // the window of the previous tile is consumed
       if (t == 0) {                          // 128 KB window, four 32 KB bulk copies
+        TB_DCHECK(list[i0 + j] >= 0 && list[i0 + j] < c_lim.t_ntiles);
         const double *src = x + (list[i0 + j] % nwin) * kTileCols;
+        TB_DCHECK((list[i0 + j] % nwin) * (long long)kTileCols + kTileCols <= c_lim.nbins + kXPad);
         mbar_expect_tx(wbar, kWinBytes);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -635,6 +644,7 @@ k_rowsum_tiles(const uint32_t *__restrict__ cells, const uint2 *__restrict__ des
         }
         __syncwarp();                        // every lane has read this stage
         if (meta & kDescEndSlice) {          // a row belongs to one slice: no other warp adds to it
+          TB_DCHECK(row < (uint32_t)kTileRows);
           acc[row] += a0 + a1;
           a0 = a1 = 0.0;
         }
@@ -844,6 +854,7 @@ void launch_rowsum_tiles(tb_store *s, const double *x, const IceState *state) {
   const int grid = (int)(s->t_nunits < s->sm_count ? s->t_nunits : s->sm_count);
   const int cur = s->t_launches & 1;
   ++s->t_launches;
+  set_check_limits(s);
   k_rowsum_tiles<<<grid, kTileThreads, kTileSmem, s->stream>>>(
       s->t_cells.p, s->t_desc.p, s->t_desc_off.p, s->t_perm.p, s->t_list.p,
       reinterpret_cast<const int4 *>(s->t_unit.p), s->t_order.p, (unsigned int)s->t_nunits, s->t_nwin, x,

@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(1024) k_visit_chunks(VisitSrc src, V vis) {
           else v = (int32_t)u[e];
           if (v == 0) continue;
           const int64_t j = (int64_t)c0 + dense_slot(wi * per + e);
+          TB_DCHECK(j < src.nbins && gi < src.nbins);
           if (j >= g) vis.cell(gi, j, v);
         }
       }
@@ -168,6 +169,7 @@ __global__ void __launch_bounds__(1024) k_visit_tiles(VisitSrc src, V vis) {
     const int64_t g = src.full_rows ? -1 : gi;
     const bool mine = gi < src.nbins && vis.row(gi);    // (rows of a partial last tile hold no cells)
     const uint4 *base = reinterpret_cast<const uint4 *>(src.t_cells + src.t_off[tile] * 128);
+    TB_DCHECK(o1 <= o2 && o2 <= o3 && (src.t_off[tile] + o3) * 128 <= c_lim.t_cell_words);
     for (uint32_t blk = o1; blk < o2; ++blk) {          // ones: 8 column offsets per lane and block
       if (!mine) break;
       const uint4 q = base[(size_t)blk * 32 + lane];
@@ -177,6 +179,7 @@ __global__ void __launch_bounds__(1024) k_visit_tiles(VisitSrc src, V vis) {
         const uint32_t off = (u[e >> 1] >> (16 * (e & 1))) & 0xffffu;
         if (off >= (uint32_t)kTileCols) continue;       // padding points behind the window
         const int64_t j = wlo + off;
+        TB_DCHECK(j < src.nbins && gi < src.nbins);
         if (j >= g) vis.cell(gi, j, 1);
       }
     }
@@ -189,6 +192,7 @@ __global__ void __launch_bounds__(1024) k_visit_tiles(VisitSrc src, V vis) {
         const int32_t v = (int32_t)(u[e] & 0xffffu);
         if (v == 0) continue;                           // padding
         const int64_t j = wlo + (u[e] >> 18);
+        TB_DCHECK(j < src.nbins && gi < src.nbins);
         if (j >= g) vis.cell(gi, j, v);
       }
     }
@@ -238,6 +242,7 @@ template <typename V>
 void visit_upper(const tb_store *s, const V &vis, bool full_rows = false) {
   VisitSrc src = visit_src(s);
   src.full_rows = full_rows;
+  set_check_limits(s);
   if (s->nchunks == 0) return;
   if (s->csr_resident) {
     k_visit_csr<V><<<visit_grid<V>(s, k_visit_csr<V>, s->nchunks), V::kThreads, V::kShared, s->stream>>>(src, vis);

@@ -29,6 +29,20 @@ def test_kernel_coverage_script():
 
 
 @pytest.mark.gpu
+def test_kernel_coverage_under_the_checked_build():
+    """-DTB_CHECK=1: every descriptor, ring, gather and decode index of the hot kernels is asserted
+    on the device (compute-sanitizer is not available on the GPU pool); a violation traps."""
+    chk = os.path.join(ROOT, "tadbit_b200", "variants", "check.so")
+    if not os.path.exists(chk):
+        pytest.skip("variants/check.so not built (python -c 'import __graft_entry__ as g; g.build()')")
+    lines = _run({"TADBIT_B200_LIB": chk})
+    assert all("'T': 0" not in l for l in lines)
+    # the assertions are live: the library reports it
+    import ctypes
+    assert ctypes.CDLL(chk).tb_version() == 200 + 1000
+
+
+@pytest.mark.gpu
 def test_kernel_coverage_without_tiles():
     """TB_TILES=0 (A/B switch): sparse cells stay per-cell chunks, large cells of dense chunks
     stay in their overflow lists -- the list walk at the end of a dense group gets real work."""
