@@ -152,7 +152,8 @@ void exchange_setup(tb_store *s) {
   PeerExchange &px = s->px;
   TB_REQUIRE(s->world <= kMaxPeers, "at most %d GPUs per group", kMaxPeers);
   px.stride = (((size_t)s->nbins + 63) / 64) * 64;
-  const size_t flag_off = 2 * px.stride * sizeof(double);
+  // an entry is 16 bytes: two tagged words of the LL protocol (the flag protocol uses 8 of them)
+  const size_t flag_off = 2 * px.stride * 2 * sizeof(double);
   const size_t bytes = flag_off + kMaxPeers * sizeof(unsigned long long);
   TB_CUDA(cudaMalloc(&px.base, bytes));
   TB_CUDA(cudaMemset(px.base, 0, bytes));
@@ -163,7 +164,7 @@ void exchange_setup(tb_store *s) {
   v.world = 1;                                   // until the peers are mapped
   auto place = [&](int q, void *base) {
     v.s[q][0] = reinterpret_cast<double *>(base);
-    v.s[q][1] = reinterpret_cast<double *>(base) + px.stride;
+    v.s[q][1] = reinterpret_cast<double *>(base) + 2 * px.stride;
     v.flag[q] = reinterpret_cast<unsigned long long *>(reinterpret_cast<uint8_t *>(base) + flag_off);
   };
   // one GPU: the only "peer" is the rank itself, slot 0

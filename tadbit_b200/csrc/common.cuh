@@ -306,7 +306,7 @@ void launch_rowsum_chunks(tb_store *s, const double *x, const IceState *state); 
 bool sparse_in_dense_tail(const tb_store *s);
 // tiles.cu
 void build_tiles(tb_store *s);       // sparse tiles from the ENC_T chunks (after build_encoded)
-void launch_rowsum_tiles(tb_store *s, const double *x, const IceState *state);
+void launch_rowsum_tiles(tb_store *s, const double *x, const IceState *state, unsigned long long *prof = nullptr);
 // synth.cu
 void build_synthetic(tb_store *s, const tb_synth_params *p);
 void synthetic_row_counts(int64_t nbins, int32_t n_chrom, const int64_t *chrom_offsets,

@@ -459,12 +459,28 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long
 __device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v) {
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// LL exchange: a row sum travels as two 8-byte words, each = (pass tag << 32) | half of the double.
+// An aligned 8-byte store is single-copy atomic, so a reader that finds the tag of the current
+// pass in both words has the value: no fence, no flag, no barrier between the GPUs.
+__device__ __forceinline__ void st_ll(unsigned long long *p, double v, unsigned long long tag) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long w0 = tag | (bits & 0xffffffffull), w1 = tag | (bits >> 32);
+  asm volatile("st.relaxed.sys.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ bool ld_ll(const unsigned long long *p, unsigned long long tag, double &v) {
+  unsigned long long w0, w1;
+  asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+  v = __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
+  return (w0 & 0xffffffff00000000ull) == tag && (w1 & 0xffffffff00000000ull) == tag;
+}
+
 __device__ __forceinline__ unsigned long long now_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
 
+template <bool LL>
 __global__ void __launch_bounds__(kXThreads, 2)
 k_ice_exchange(PeerView pv, const double *__restrict__ pf, const int64_t *__restrict__ row_chunk,
                TileSums ts, int64_t nrows, int64_t rb, int64_t n, double *__restrict__ x,
@@ -489,6 +505,7 @@ k_ice_exchange(PeerView pv, const double *__restrict__ pf, const int64_t *__rest
   const int pass = vs->passes_done;
   const unsigned long long epoch = vs->epoch_base + (unsigned long long)pass + 1ull;
   const int buf = pass & 1;
+  const unsigned long long tag = (epoch & 0xffffffffull) << 32;
   if (threadIdx.x == 0) s_fault = 0;
   // 1. the rows of this rank -> every rank (two rows per thread and step)
   {
@@ -506,18 +523,27 @@ k_ice_exchange(PeerView pv, const double *__restrict__ pf, const int64_t *__rest
       for (int q = 0; q < kMaxPeers; ++q)          // constant indices: the parameter stays in the constant bank
         if (q < pv.world) {
           double *dst = buf ? pv.s[q][1] : pv.s[q][0];
-          dst[rb + r] = a;
-          if (two) dst[rb + r2] = a2;
+          if (LL) {
+            unsigned long long *d = reinterpret_cast<unsigned long long *>(dst);
+            st_ll(d + 2 * (rb + r), a, tag);
+            if (two) st_ll(d + 2 * (rb + r2), a2, tag);
+          } else {
+            dst[rb + r] = a;
+            if (two) dst[rb + r2] = a2;
+          }
         }
     }
   }
   lap(0);
-  if (pv.world > 1) __threadfence_system();      // the stores to the peers are out before the flag is
-  else __threadfence();
+  // CTA barrier, then ONE fence per CTA (as a cooperative-groups grid sync does): the barrier orders the
+  // stores of the CTA's threads before thread 0's fence, whose cumulativity carries them to system
+  // scope before the arrival is counted and the flag published
   __syncthreads();
   lap(1);
-  // 2. publish once every CTA has stored, then wait for every peer
-  if (threadIdx.x == 0) {
+  // 2. (flag protocol only) publish once every CTA has stored, then wait for every peer
+  if (!LL && threadIdx.x == 0) {
+    if (pv.world > 1) __threadfence_system();
+    else __threadfence();
     const unsigned int t = atomicAdd(&state->arrive1, 1u);
     if (t == gridDim.x - 1) {
       state->arrive1 = 0;
@@ -528,25 +554,40 @@ k_ice_exchange(PeerView pv, const double *__restrict__ pf, const int64_t *__rest
         if (q < pv.world) st_release_sys(pv.flag[q] + pv.rank, epoch);
     }
   }
-  if (threadIdx.x < pv.world) {
+  if (!LL && threadIdx.x < pv.world) {
     const unsigned long long t0 = now_ns();
     while (ld_acquire_sys(pv.my_flags + threadIdx.x) < epoch) {
       if (now_ns() - t0 > kPeerTimeoutNs) { s_fault = 1; break; }
     }
   }
-  __syncthreads();
-  if (s_fault) {                       // give up: the host reports it, nothing is updated
-    if (threadIdx.x == 0) { vs->fault = 1; vs->stopped = 1; }
-    return;
+  if (!LL) {
+    __syncthreads();
+    if (s_fault) {                     // give up: the host reports it, nothing is updated
+      if (threadIdx.x == 0) { vs->fault = 1; vs->stopped = 1; }
+      return;
+    }
   }
   lap(2);
-  // 3. statistics of the pass
+  // 3. statistics of the pass (LL: every thread waits for the words of its own entries)
   const double *sfull = buf ? pv.mine[1] : pv.mine[0];
+  const unsigned long long *sll = reinterpret_cast<const unsigned long long *>(sfull);
   double sum = 0.0, mn = INFINITY, mx = -INFINITY;
   long long cnt = 0;
+  bool late = false;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const double si = __ldcg(sfull + i);
+    double si;
+    if (LL) {
+      if (!ld_ll(sll + 2 * i, tag, si)) {
+        const unsigned long long t0 = now_ns();
+        unsigned int spins = 0;
+        while (!ld_ll(sll + 2 * i, tag, si))
+          if ((++spins & 1023u) == 0u && now_ns() - t0 > kPeerTimeoutNs) { late = true; break; }
+      }
+      if (late) break;
+    } else {
+      si = __ldcg(sfull + i);
+    }
     bool p;
     if (pass == 0) present[i] = p = !isnan(si);
     else p = present[i];
@@ -556,6 +597,14 @@ k_ice_exchange(PeerView pv, const double *__restrict__ pf, const int64_t *__rest
       mn = fmin(mn, S);
       mx = fmax(mx, S);
       ++cnt;
+    }
+  }
+  if (LL) {
+    if (late) s_fault = 1;
+    __syncthreads();
+    if (s_fault) {                     // a peer never delivered: the host reports it, nothing is updated
+      if (threadIdx.x == 0) { vs->fault = 1; vs->stopped = 1; }
+      return;
     }
   }
   block_stats(sum, mn, mx, cnt, sh, kXThreads / 32);
@@ -602,7 +651,10 @@ k_ice_exchange(PeerView pv, const double *__restrict__ pf, const int64_t *__rest
       x[i] = 0.0;
       continue;
     }
-    const double S = x[i] * __ldcg(sfull + i);
+    double si;
+    if (LL) ld_ll(sll + 2 * i, tag, si);
+    else si = __ldcg(sfull + i);
+    const double S = x[i] * si;
     const double bi = b[i] * (S / mean);
     b[i] = bi;
     x[i] = (bi != 0.0) ? 1.0 / bi : 0.0;     // B == 0: row frozen by the ZeroDivisionError skip
@@ -929,12 +981,26 @@ void masked_row_sums(tb_store *s, long long *dst) {
   }
 }
 
+// TB_EXCHANGE=flags: data stores + one flag per peer behind a system-scope fence (the first fused
+// protocol); default: LL words that carry their own pass tag
+bool exchange_ll() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("TB_EXCHANGE");
+    v = (e && !strcmp(e, "flags")) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 // CTAs of k_ice_exchange that are resident at the same time on this device
 int exchange_grid(const tb_store *s) {
   static int per_sm[64] = {0};
   int &v = per_sm[s->device & 63];
   if (!v) {
-    TB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_ice_exchange, kXThreads, 0));
+    TB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_ice_exchange<true>, kXThreads, 0));
+    int v2 = v;
+    TB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v2, k_ice_exchange<false>, kXThreads, 0));
+    if (v2 < v) v = v2;
     if (v < 1) v = 1;
     if (v > 2) v = 2;
   }
@@ -1052,7 +1118,7 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
     rowsum_once(s, s->x.p, s->state.p);
     TB_CUDA(cudaEventRecord(ev(p, 1), st));
     if (fused) {
-      k_ice_exchange<<<exchange_grid(s), kXThreads, 0, st>>>(
+      (exchange_ll() ? k_ice_exchange<true> : k_ice_exchange<false>)<<<exchange_grid(s), kXThreads, 0, st>>>(
           s->px.view, s->partial_f.p, s->row_chunk.p, ts, s->nrows, s->row_begin, N, s->x.p, s->b.p,
           s->bad.p, s->present.p, live, iterations, max_dev, s->block_red.p, s->trace.p, s->state.p, prof.p);
     } else if (s->world > 1) {
@@ -1373,6 +1439,32 @@ void probe_rowsum(tb_store *s, int32_t reps, double ms[3]) {
   ms[1] = tiles / reps;
   ms[2] = rest / reps;
   ms[0] = ms[1] + ms[2];
+  const char *tenv = getenv("TB_TIMING");
+  if (tenv && tenv[0] == '1' && s->t_nunits) {     // when do the CTAs of the tile kernel start and finish?
+    const int grid = (int)(s->t_nunits < s->sm_count ? s->t_nunits : s->sm_count);
+    DevBuf<unsigned long long> prof;
+    prof.alloc(4 * (size_t)grid);
+    launch_rowsum_tiles(s, s->x.p, nullptr, prof.p);
+    std::vector<unsigned long long> h(4 * (size_t)grid);
+    TB_CUDA(cudaMemcpyAsync(h.data(), prof.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    unsigned long long t0 = ~0ull, t1 = 0, umin = ~0ull, umax = 0, utot = 0, ttot = 0;
+    double end_sum = 0.0, end_min = 1e30;
+    for (int b = 0; b < grid; ++b) t0 = h[4 * b] < t0 ? h[4 * b] : t0;
+    for (int b = 0; b < grid; ++b) {
+      const double end = (double)(h[4 * b + 1] - t0);
+      end_sum += end;
+      end_min = end < end_min ? end : end_min;
+      t1 = h[4 * b + 1] > t1 ? h[4 * b + 1] : t1;
+      umin = h[4 * b + 2] < umin ? h[4 * b + 2] : umin;
+      umax = h[4 * b + 2] > umax ? h[4 * b + 2] : umax;
+      utot += h[4 * b + 2];
+      ttot += h[4 * b + 3];
+    }
+    fprintf(stderr, "[tadbit_b200] k_rowsum_tiles: %d CTAs, %llu units (%llu..%llu per CTA), %llu tile visits; "
+                    "CTAs finish %.1f us (first) / %.1f us (mean) / %.1f us (last) after the first one starts\n",
+            grid, utot, umin, umax, ttot, 1e-3 * end_min, 1e-3 * end_sum / grid, 1e-3 * (double)(t1 - t0));
+  }
 }
 
 }  // namespace tb

@@ -42,6 +42,7 @@
 // sums, added per row in unit order by the combine step, so results do not depend on which CTA
 // ran which unit: deterministic, no atomics on the data path.
 #include "common.cuh"
+#include <stdio.h>
 #include <stdlib.h>
 #include <algorithm>
 #include <numeric>
@@ -558,7 +559,8 @@ k_rowsum_tiles(const uint32_t *__restrict__ cells, const uint2 *__restrict__ des
                const int32_t *__restrict__ list, const int4 *__restrict__ unit,
                const int32_t *__restrict__ order, unsigned int nunits, int64_t nwin,
                const double *__restrict__ x, double *__restrict__ partial,
-               unsigned int *__restrict__ counter, int cur, const IceState *__restrict__ state) {
+               unsigned int *__restrict__ counter, int cur, const IceState *__restrict__ state,
+               unsigned long long *__restrict__ prof) {
   // the next launch fetches from the other counter
   if (blockIdx.x == 0 && threadIdx.x == 0) counter[cur ^ 1] = 0u;
   if (state && state->stopped) return;
@@ -581,11 +583,19 @@ k_rowsum_tiles(const uint32_t *__restrict__ cells, const uint2 *__restrict__ des
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   uint32_t wparity = 0, rparity = 0;                    // rparity bit q = parity of ring stage q
+  // TB_TIMING probe (tb_probe_rowsum): per CTA first / last timestamp, units and tiles it processed
+  unsigned long long p_units = 0, p_tiles = 0;
+  if (prof && t == 0) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    prof[4 * blockIdx.x] = now;
+  }
   for (;;) {
     if (t == 0) *s_next = atomicAdd(&counter[cur], 1u);
     __syncthreads();
     const unsigned int ui = *s_next;
     if (ui >= nunits) break;
+    ++p_units;
     const int u = order[ui];
     TB_DCHECK(u >= 0 && u < c_lim.t_nunits);
     const int4 un = unit[u];
@@ -614,6 +624,7 @@ k_rowsum_tiles(const uint32_t *__restrict__ cells, const uint2 *__restrict__ des
     if (nd > 1) { e1 = dp[1]; issue(1, e1, row1); }
     uint2 pf = nd > 2 ? dp[2] : make_uint2(0u, 0u);     // descriptor two ahead of the consumer
     int ci = 0, stage = 0;
+    p_tiles += n;
     for (int j = 0; j < n; ++j) {
       __syncthreads();                       // the window of the previous tile is consumed
       if (t == 0) {                          // 128 KB window, four 32 KB bulk copies
@@ -670,6 +681,13 @@ k_rowsum_tiles(const uint32_t *__restrict__ cells, const uint2 *__restrict__ des
 #pragma unroll
     for (int e = t; e < kTileRows; e += kTileThreads) partial[(int64_t)u * kTileRows + e] = acc[e];
     __syncthreads();                          // acc is re-zeroed, s_next rewritten for the next unit
+  }
+  if (prof && t == 0) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    prof[4 * blockIdx.x + 1] = now;
+    prof[4 * blockIdx.x + 2] = p_units;
+    prof[4 * blockIdx.x + 3] = p_tiles;
   }
 }
 
@@ -764,6 +782,13 @@ void build_tiles(tb_store *s) {
                                  std::min(3.0 * (double)kTileFixedCost, total_cost / s->sm_count)) + 1.0;
   std::vector<int32_t> list, units, unit_of_rb(nrb + 1, 0);
   std::vector<double> cost;
+  // Units are fetched most expensive first; the work of the last row blocks is cut finer so that the
+  // CTAs finish together (TB_TILE_TAIL="share,divisor": the last `share` of the cost in units of
+  // target / divisor)
+  double tail_share = 0.0, tail_div = 1.0, seen_cost = 0.0;
+  if (const char *e = getenv("TB_TILE_TAIL")) sscanf(e, "%lf,%lf", &tail_share, &tail_div);
+  if (tail_div < 1.0) tail_div = 1.0;
+  const double target_coarse = target;
   for (int64_t rb = 0; rb < nrb; ++rb) {
     unit_of_rb[rb] = (int32_t)(units.size() / 4);
     double run = 0;
@@ -779,6 +804,8 @@ void build_tiles(tb_store *s) {
     for (int64_t w = 0; w < nwin; ++w) {
       if (!h_size[rb * nwin + w]) continue;
       const double sz = h_eff[rb * nwin + w];
+      const double target = seen_cost >= (1.0 - tail_share) * total_cost ? target_coarse / tail_div : target_coarse;
+      seen_cost += sz + (double)kTileFixedCost;
       if (sz > 1.5 * target) {
         flush();
         int parts = (int)(sz / target + 0.999);
@@ -844,7 +871,7 @@ void build_tiles(tb_store *s) {
   TB_CUDA(cudaStreamSynchronize(st));
 }
 
-void launch_rowsum_tiles(tb_store *s, const double *x, const IceState *state) {
+void launch_rowsum_tiles(tb_store *s, const double *x, const IceState *state, unsigned long long *prof) {
   if (s->t_nunits == 0) return;
   static bool attr_set[64] = {false};            // per device: the attribute is per context
   if (!attr_set[s->device & 63]) {
@@ -858,7 +885,7 @@ void launch_rowsum_tiles(tb_store *s, const double *x, const IceState *state) {
   k_rowsum_tiles<<<grid, kTileThreads, kTileSmem, s->stream>>>(
       s->t_cells.p, s->t_desc.p, s->t_desc_off.p, s->t_perm.p, s->t_list.p,
       reinterpret_cast<const int4 *>(s->t_unit.p), s->t_order.p, (unsigned int)s->t_nunits, s->t_nwin, x,
-      s->t_partial.p, s->t_counter.p, cur, state);
+      s->t_partial.p, s->t_counter.p, cur, state, prof);
 }
 
 }  // namespace tb
