@@ -92,7 +92,7 @@ def rebalance_by_time(blocks, probes, size):
     return balanced_row_blocks(cost, len(blocks))
 
 
-def build_sharded(wl, rank, world, device, gather=None, refine=3):
+def build_sharded(wl, rank, world, device, gather=None, refine=4):
     """Generate this rank's block of the synthetic matrix.  ``gather`` is a callable that
     all-gathers a python object over ranks (host plumbing, e.g. torch.distributed).
 
@@ -111,11 +111,11 @@ def build_sharded(wl, rank, world, device, gather=None, refine=3):
     store = ContactStore.synthetic(n, wl["params"], chromosomes=wl["chromosomes"],
                                    row_block=blocks[rank], device=device)
     for _ in range(refine):
-        total, ms_t, ms_d = store.probe_rowsum(4)                    # shard alone, timing only
+        total, ms_t, ms_d = store.probe_rowsum(8)                    # shard alone, timing only
         dense, tiles = store.row_work()
         probes = gather((ms_t, ms_d, dense, tiles))
         times = [p[0] + p[1] for p in probes]
-        if max(times) <= 1.012 * (sum(times) / world):
+        if max(times) <= 1.006 * (sum(times) / world):
             break
         new = rebalance_by_time(blocks, probes, n)
         if new == blocks:
