@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-compartments", action="store_true")
     ap.add_argument("--parity-workload", default="c3s")
     ap.add_argument("--cpu-bins", type=int, default=32768,
                     help="bins of the leading sub-matrix used for the CPU baseline sample")
@@ -514,6 +515,35 @@ def main():
                          "frac_algorithmic": gbs(k5_alg, k5_ms) / peak,
                          "frac": gbs(lay["stream_bytes"], k5_ms) / peak,
                          "what": "cell visitor over the compact stream, int64 histogram"}}
+
+    # ---- N4 (compartments) on the largest chromosome, once: obs/exp scatter, fp64 X X^T on the
+    # tensor pipe (DMMA), Lanczos eigen-solver.  A dense contraction: its roofline is flop, not bytes.
+    if world == 1 and not args.no_compartments:
+        try:
+            sec = max(wl["chromosomes"], key=lambda c: wl["chromosomes"][c])
+            beg, end = hic.section_pos[sec]
+            exp_arr = np.array([hic.expected.get(d, 1.0) or 1.0 for d in range(end - beg)])
+            t0 = time.perf_counter()
+            n_good = store.corr_build(beg, end, hic.bias.to_array(), bad_mask(n, hic.bads), exp_arr, stage=1)
+            evals, _, einfo = store.corr_eig(3)
+            cmp_wall = (time.perf_counter() - t0) * 1e3
+            ct = store.corr_timing()
+            ld = -(-n_good // 16) * 16
+            ntile = -(-n_good // 128)
+            flop = ntile * (ntile + 1) / 2 * 128 * 128 * ld * 2.0
+            pipeline_rec["n4_compartments"] = {
+                "section": sec, "good_bins": n_good, "wall_ms": cmp_wall,
+                "obs_exp_visitor_ms": ct["visit_ms"], "center_ms": ct["center_ms"],
+                "syrk": {"kernel": "k_syrk_dmma", "ms": ct["gemm_ms"], "flop": flop,
+                         "tflops": flop / (ct["gemm_ms"] * 1e-3) / 1e12 if ct["gemm_ms"] else None,
+                         "peak_tflops_nominal_fp64": 40.0,
+                         "frac": flop / (ct["gemm_ms"] * 1e-3) / 1e12 / 40.0 if ct["gemm_ms"] else None,
+                         "bound": "fp64 tensor pipe (mma.sync m8n8k4 f64; tcgen05 has no fp64 kind)"},
+                "scale_ms": ct["scale_ms"],
+                "eigen": {"ms": ct["eig_ms"], "lanczos_vectors": einfo["steps"], "restarts": einfo["restarts"],
+                          "eigenvalues": [float(x) for x in evals]}}
+        except Exception as exc:                           # never lose the headline over the extra
+            pipeline_rec["n4_compartments"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,

@@ -292,6 +292,43 @@ int tb_decay_sums(tb_store *s, const double *h_bias, const uint8_t *h_bad, doubl
 int tb_window(tb_store *s, int64_t row_begin, int64_t row_end, int64_t col_begin, int64_t col_end,
               const double *h_bias, double *h_out);
 
+/* ---- N4: compartments --------------------------------------------------------- */
+/* The numeric core of HiC_data.find_compartments (_pytadbit/hic_data.py:845-937), per section
+ * (chromosome) [bin_begin, bin_end) of the genome, over the bins of the section that are not bad
+ * (n of them, in genomic order):
+ *   stage 0  the observed / expected matrix the reference builds as nested lists (:851-871):
+ *            m[a][b] = float(count(i, j)) / h_expected[j - i] / h_bias[i] / h_bias[j] for i <= j,
+ *            mirrored (the same order of divisions: the values equal the reference's bit for bit);
+ *   stage 1  numpy.corrcoef of its rows (:873) with the reference's NaN -> 0 (:881): rows centred,
+ *            X X^T / (n - 1) as fp64 tensor-core tiles (DMMA), c_ij / sd_i / sd_j, clipped to [-1, 1].
+ * h_bias[nbins], h_bad[nbins] or NULL, h_expected[bin_end - bin_begin] (expected count per distance;
+ * a zero entry is the caller's to refuse: the reference raises ZeroDivisionError).  *n_good = n.
+ * The matrix stays resident in the store (one at a time) for tb_corr_get / tb_corr_eig.  On a
+ * row-sharded store every rank ends with the whole matrix (one all-reduce of n x n doubles). */
+int tb_corr_build(tb_store *s, int64_t bin_begin, int64_t bin_end, const double *h_bias,
+                  const uint8_t *h_bad, const double *h_expected, int32_t stage, int64_t *n_good);
+/* The resident matrix, row-major n x n doubles, to the host (the reference's savecorr file, :883-913,
+ * and its optional scipy median_filter smoothing, :915-917, stay host work) ... */
+int tb_corr_get(tb_store *s, double *h_out);
+/* ... and a (smoothed) n x n symmetric matrix from the host back into the store. */
+int tb_corr_set(tb_store *s, int64_t n, const double *h_in);
+/* Replaces scipy.sparse.linalg.eigsh(matrix, k=max_ev) (:926-937): the k eigenpairs of largest
+ * magnitude of the resident symmetric matrix by Lanczos iteration with full re-orthogonalisation
+ * (every vector operation a kernel; fixed start vector, so the result is reproducible, which
+ * ARPACK's is too), eigenvalues in descending order = the order the reference reads them in;
+ * k >= n returns all n eigenpairs by descending value (scipy falls back to a dense solver there).
+ * h_evals[k], h_evecs[k * n] (vector v at h_evecs + v * n, unit norm; the sign of an eigenvector
+ * is arbitrary here as it is in ARPACK).  info[0] eigenpairs returned, [1] Lanczos vectors built,
+ * [2] restarts after an invariant subspace, [3] converged.  TB_ERR_STATE if not converged. */
+int tb_corr_eig(tb_store *s, int32_t k, double *h_evals, double *h_evecs, int32_t info[4]);
+/* Device times of the last tb_corr_build / tb_corr_eig in ms: out[0] cell visitor, [1] centring,
+ * [2] X X^T, [3] scaling, [4] eigen-solver; out[5] n, [6] stage resident, [7] 1 if corr_gemm=simple. */
+int tb_corr_timing(const tb_store *s, double out[8]);
+/* Host-only helper of tb_corr_eig, exported for tests: eigen-decomposition of the symmetric
+ * tridiagonal matrix (diag[n], sub[n - 1]) by implicit QL.  diag is overwritten by the
+ * eigenvalues (unordered), vecs[r * n + i] = component r of the eigenvector of diag[i]. */
+int tb_tridiag_eig(int32_t n, double *diag, const double *sub, double *vecs);
+
 #ifdef __cplusplus
 }
 #endif

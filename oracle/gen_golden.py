@@ -20,6 +20,7 @@ import io
 import json
 import os
 import sys
+import warnings
 from collections import OrderedDict
 
 import numpy as np
@@ -450,9 +451,94 @@ def reference_decay_cases(ns):
     return index
 
 
+def reference_compartment_cases(ns):
+    """N4: HiC_data.find_compartments of the UNMODIFIED reference (_pytadbit/hic_data.py:736-1031) on
+    a reference fixture and on seeded matrices with an A/B checkerboard.  The matrices the
+    reference hands to numpy.corrcoef (observed / expected over the good bins) and to scipy's
+    eigsh (the correlation matrix, NaN -> 0) are recorded by wrapping those two names in its
+    module namespace; nothing of the reference is changed."""
+    import pytadbit.hic_data as ref_mod
+    sys.path.insert(0, os.path.join(HERE, "..", "tests"))
+    from _compartment_cases import compartment_case, full_dict, sections_of
+    names = []
+
+    def record(name, hic, prepare, call_kw):
+        print("compartments", name, file=sys.stderr)
+        seen = {"obsexp": [], "corr": []}
+        real_corrcoef, real_eigsh = ref_mod.corrcoef, ref_mod.eigsh
+
+        def spy_corrcoef(m, *a, **k):
+            if len(m) > 1:                    # (a single row ends in the reference's "MT" branch)
+                seen["obsexp"].append(np.array(m, dtype=np.float64))
+            return real_corrcoef(m, *a, **k)
+
+        def spy_eigsh(m, *a, **k):
+            seen["corr"].append(np.array(m, dtype=np.float64))
+            return real_eigsh(m, *a, **k)
+        prepare(hic)
+        ref_mod.corrcoef, ref_mod.eigsh = spy_corrcoef, spy_eigsh
+        try:
+            with warnings.catch_warnings(record=True) as caught:
+                warnings.simplefilter("always")
+                firsts, stats = hic.find_compartments(**call_kw)
+        finally:
+            ref_mod.corrcoef, ref_mod.eigsh = real_corrcoef, real_eigsh
+        r, c, v = upper_store(hic)
+        n = len(hic)
+        arrays = dict(rows=r, cols=c, vals=v, bias=np.array([hic.bias[i] for i in range(n)]))
+        secs = [sec for sec in hic.section_pos if sec in firsts]
+        assert len(secs) == len(seen["obsexp"]) == len(seen["corr"])
+        for k, sec in enumerate(secs):
+            arrays["obsexp_%d" % k] = seen["obsexp"][k]
+            arrays["corr_%d" % k] = seen["corr"][k]
+            arrays["evals_%d" % k] = np.array(firsts[sec][0], dtype=np.float64)
+            arrays["evecs_%d" % k] = np.array(firsts[sec][1], dtype=np.float64)
+        np.savez_compressed(os.path.join(OUT, "compartments_%s.npz" % name), **arrays)
+        rec = OrderedDict(
+            name=name, n=n,
+            chromosomes=[[str(k), int(x)] for k, x in hic.chromosomes.items()] if hic.chromosomes else None,
+            resolution=hic.resolution, call=call_kw, sections=[str(s_) for s_ in secs],
+            bads=jsonable_bads(hic.bads),
+            expected=OrderedDict((str(k), float(x)) for k, x in sorted(hic.expected.items())),
+            compartments=OrderedDict((str(k), x) for k, x in hic.compartments.items()),
+            warnings=sorted(str(w.message) for w in caught if "Chromosome" in str(w.message)))
+        with open(os.path.join(OUT, "compartments_%s.json" % name), "w") as fh:
+            json.dump(rec, fh, indent=1)
+        names.append(name)
+
+    def nothing(hic):
+        pass
+
+    def pipeline(hic):
+        hic.filter_columns(silent=True)
+        hic.normalize_hic(iterations=50, max_dev=1e-6, silent=True)
+        hic.normalize_expected()
+
+    fix = ns.read_matrix(os.path.join(ns.root, "test", "20Kb", "chrT", "chrT_A.tsv"), one=True,
+                         resolution=20000)
+    record("chrT_20Kb_A", fix, nothing, dict(max_ev=3))
+    for name, seed, sizes, prep, kw in (
+            ("synth_4chrom", 11, (120, 90, 3, 1), nothing, dict(max_ev=3)),
+            ("synth_pipeline", 12, (150, 64, 40), pipeline, dict(max_ev=2)),
+            ("synth_300", 13, (300,), pipeline, dict(max_ev=3))):
+        case = compartment_case(seed, sizes=sizes, n_dead=max(3, sum(sizes) // 60))
+        hic = ns.HiC_data(full_dict(case), case["n"], chromosomes=case["chromosomes"],
+                          dict_sec=sections_of(case["chromosomes"]), resolution=10000)
+        record(name, hic, prep, kw)
+    return names
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_shim.load()
+    if "--only-compartments" in sys.argv:
+        names = reference_compartment_cases(ns)
+        path = os.path.join(OUT, "INDEX.json")
+        index = json.load(open(path))
+        index["compartment_cases"] = names
+        with open(path, "w") as fh:
+            json.dump(index, fh, indent=1)
+        return
     index = []
     # 1. the reference's own fixtures
     for reso in ("20Kb", "40Kb", "80Kb"):
@@ -532,9 +618,10 @@ def main():
     pair_cases = reference_pair_cases(ns)
     decay_cases = reference_decay_cases(ns)
     window_cases = reference_window_cases(ns)
+    compartment_cases = reference_compartment_cases(ns)
 
     with open(os.path.join(OUT, "INDEX.json"), "w") as fh:
-        json.dump(dict(cases=index, pair_cases=pair_cases, decay_cases=decay_cases, window_cases=window_cases,
+        json.dump(dict(cases=index, pair_cases=pair_cases, decay_cases=decay_cases, window_cases=window_cases, compartment_cases=compartment_cases,
                        numpy=np.__version__,
                        generator="oracle/gen_golden.py", reference="TADbit v1.1 (unmodified, via oracle/ref_shim.py)"), fh, indent=1)
 

@@ -800,3 +800,55 @@ def rescale_and_decay(m, biases, badcol, factor=1, signal_to_noise=0.05):
                 pass
         decay[crm] = dec
     return b, decay, norm_cisprc
+
+
+# ---------------------------------------------------------------------------------------------
+# N4 -- compartments: observed / expected, correlation, leading eigenpairs
+#        <- _pytadbit/hic_data.py:845-937 (HiC_data.find_compartments)
+# ---------------------------------------------------------------------------------------------
+def obs_exp_matrix(m, beg, end, bias, bads, expected_by_distance):
+    """The nested lists of hic_data.py:851-871 as an array over the good bins of [beg, end):
+    cell (a, b) = float(count) / expected[|j - i|] / bias[i] / bias[j] with i <= j the two bins
+    (the reference computes every cell both ways and keeps the one of its lower triangle, i.e.
+    the smaller bin divides first)."""
+    bad = _bad_mask(m.size, bads)
+    idx = np.array([i for i in range(beg, end) if not bad[i]], dtype=np.int64)
+    n = idx.size
+    if n == 0:
+        return np.zeros((0, 0))
+    full = m.full_csr(dtype=np.float64)[idx][:, idx].toarray()
+    b = np.asarray(bias, dtype=np.float64)
+    e = np.asarray(expected_by_distance, dtype=np.float64)
+    lo = np.minimum(idx[:, None], idx[None, :])
+    hi = np.maximum(idx[:, None], idx[None, :])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return full / e[hi - lo] / b[lo] / b[hi]
+
+
+def correlation_matrix(matrix):
+    """numpy.corrcoef of the rows, NaN -> 0 (hic_data.py:873, :881)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        c = np.corrcoef(matrix)
+    return np.where(np.isnan(c), 0.0, c)
+
+
+def largest_eigenpairs(matrix, k):
+    """What the reference reads out of scipy's eigsh(matrix, k) (hic_data.py:926-941): the k
+    eigenpairs of largest magnitude, taken back to front from ARPACK's ascending algebraic order
+    -> descending eigenvalues; k >= n: every eigenpair (scipy switches to a dense solver).
+    Computed with the dense LAPACK solver; eigenvectors as rows, sign arbitrary."""
+    w, v = np.linalg.eigh(np.asarray(matrix, dtype=np.float64))
+    n = w.size
+    if k >= n:
+        order = np.argsort(-w, kind="stable")
+    else:
+        order = np.argsort(-np.abs(w), kind="stable")[:k]
+        order = order[np.argsort(-w[order], kind="stable")]
+    return w[order], v[:, order].T.copy()
+
+
+def compartment_breaks(vector):
+    """Break points at the sign changes of an eigenvector over the good bins (hic_data.py:942-947)."""
+    v = np.asarray(vector, dtype=np.float64)
+    flips = np.flatnonzero(v[1:] * v[:-1] < 0).tolist() + [len(v) - 1]
+    return [{"start": flips[i - 1] + 1 if i else 0, "end": b} for i, b in enumerate(flips)]

@@ -79,6 +79,12 @@ PROTOTYPES = {
                         _f64p], C.c_int),
     "tb_window": ([_store, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _f64p, _f64p], C.c_int),
     "tb_decay_sums": ([_store, _f64p, _u8p, _f64p, _i64p, _f64p], C.c_int),
+    "tb_corr_build": ([_store, C.c_int64, C.c_int64, _f64p, _u8p, _f64p, C.c_int32, _i64p], C.c_int),
+    "tb_corr_get": ([_store, _f64p], C.c_int),
+    "tb_corr_set": ([_store, C.c_int64, _f64p], C.c_int),
+    "tb_corr_eig": ([_store, C.c_int32, _f64p, _f64p, _i32p], C.c_int),
+    "tb_corr_timing": ([_store, _f64p], C.c_int),
+    "tb_tridiag_eig": ([C.c_int32, _f64p, _f64p, _f64p], C.c_int),
 }
 
 _lib = None

@@ -7,6 +7,7 @@
 #include <new>
 
 #include "common.cuh"
+#include "lanczos.hpp"
 
 namespace tb {
 
@@ -350,6 +351,12 @@ int tb_store_set_option(tb_store *s, const char *name, const char *value) {
     else { set_error("exchange must be 'fused' or 'nccl'"); return TB_ERR_ARG; }
     return TB_OK;
   }
+  if (!strcmp(name, "corr_gemm")) {      // X X^T of tb_corr_build: fp64 tensor tiles, or the plain parity kernel
+    if (!strcmp(value, "dmma")) s->corr_gemm_mode = 0;
+    else if (!strcmp(value, "simple")) s->corr_gemm_mode = 1;
+    else { set_error("corr_gemm must be 'dmma' or 'simple'"); return TB_ERR_ARG; }
+    return TB_OK;
+  }
   set_error("unknown option %s", name);
   return TB_ERR_ARG;
 }
@@ -547,6 +554,64 @@ int tb_window(tb_store *s, int64_t row_begin, int64_t row_end, int64_t col_begin
     TB_REQUIRE(s, "null argument");
     DeviceGuard g(s->device);
     window(s, row_begin, row_end, col_begin, col_end, h_bias, h_out);
+    return TB_OK;
+  });
+}
+
+int tb_corr_build(tb_store *s, int64_t bin_begin, int64_t bin_end, const double *h_bias, const uint8_t *h_bad,
+                  const double *h_expected, int32_t stage, int64_t *n_good) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(s, "null argument");
+    DeviceGuard g(s->device);
+    corr_build(s, bin_begin, bin_end, h_bias, h_bad, h_expected, stage, n_good);
+    return TB_OK;
+  });
+}
+
+int tb_corr_get(tb_store *s, double *h_out) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(s, "null argument");
+    DeviceGuard g(s->device);
+    corr_get(s, h_out);
+    return TB_OK;
+  });
+}
+
+int tb_corr_set(tb_store *s, int64_t n, const double *h_in) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(s, "null argument");
+    DeviceGuard g(s->device);
+    corr_set(s, n, h_in);
+    return TB_OK;
+  });
+}
+
+int tb_corr_eig(tb_store *s, int32_t k, double *h_evals, double *h_evecs, int32_t info[4]) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(s, "null argument");
+    DeviceGuard g(s->device);
+    corr_eig(s, k, h_evals, h_evecs, info);
+    return TB_OK;
+  });
+}
+
+int tb_corr_timing(const tb_store *s, double out[8]) {
+  if (!s || !out) { set_error("null argument"); return TB_ERR_ARG; }
+  for (int k = 0; k < 5; ++k) out[k] = s->corr_ms[k];
+  out[5] = (double)s->dense_n;
+  out[6] = (double)s->dense_stage;
+  out[7] = (double)s->corr_gemm_mode;
+  return TB_OK;
+}
+
+int tb_tridiag_eig(int32_t n, double *diag, const double *sub, double *vecs) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(n >= 1 && diag && vecs && (sub || n == 1), "null argument");
+    std::vector<double> d(diag, diag + n), e(n, 0.0), z;
+    for (int i = 0; i + 1 < n; ++i) e[i] = sub[i];
+    if (!tridiag_eig(n, d, e, z)) { set_error("tridiag_eig: no convergence"); return TB_ERR_STATE; }
+    for (int i = 0; i < n; ++i) diag[i] = d[i];
+    for (size_t i = 0; i < z.size(); ++i) vecs[i] = z[i];
     return TB_OK;
   });
 }

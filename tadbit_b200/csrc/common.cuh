@@ -270,6 +270,12 @@ struct tb_store {
   double last_kernel_ms = 0;              // device time of the last one-pass reduction (K4 / K5)
   int rowsum_launches = 0, total_launches = 0;
   int64_t device_bytes = 0;
+  // N4 (compartments.cu): the dense matrix of one section over its good bins, resident between calls
+  tb::DevBuf<double> dense;               // [dense_rows x dense_ld], zero outside n x n
+  int64_t dense_n = 0, dense_ld = 0, dense_rows = 0;
+  int dense_stage = -1;                   // 0 observed / expected, 1 correlation, 2 uploaded by the host
+  int corr_gemm_mode = 0;                 // 0 DMMA tiles, 1 plain kernel (tb_store_set_option corr_gemm)
+  double corr_ms[5] = {0, 0, 0, 0, 0};    // visitor, centring, X X^T, scaling, eigen-solver
   int rowsum_mode = -1;     // -1 default (compact stream), 0 compact, 1 CSR walk (tb_store_set_option)
   int exchange_mode = -1;   // -1 default (TB_EXCHANGE), 1 fused exchange kernel, 0 separate steps / NCCL
 };
@@ -330,6 +336,12 @@ void pair_values(tb_store *s, const double *h_bias, const uint8_t *h_bad, int zs
 void decay_sums(tb_store *s, const double *h_bias, const uint8_t *h_bad, double *h_nrm, int64_t *h_raw,
                 double out[2]);
 void window(tb_store *s, int64_t r0, int64_t r1, int64_t c0, int64_t c1, const double *h_bias, double *h_out);
+// compartments.cu
+void corr_build(tb_store *s, int64_t beg, int64_t end, const double *h_bias, const uint8_t *h_bad,
+                const double *h_expected, int stage, int64_t *n_good);
+void corr_get(tb_store *s, double *h_out);
+void corr_set(tb_store *s, int64_t n, const double *h_in);
+void corr_eig(tb_store *s, int32_t k, double *h_evals, double *h_evecs, int32_t info[4]);
 // comm.cu
 void comm_unique_id(uint8_t id[128]);
 void comm_init(tb_store *s, int rank, int world, const uint8_t id[128]);

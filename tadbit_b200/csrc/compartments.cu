@@ -1,0 +1,545 @@
+// N4: what HiC_data.find_compartments computes per chromosome before it looks for
+// sign changes (_pytadbit/hic_data.py:845-937):
+//
+//   1. the observed / expected matrix of the chromosome over its good bins,
+//        m[a][b] = float(hic[i, j]) / expected[|j - i|] / bias[i] / bias[j]      (i <= j, mirrored:
+//        the reference fills both triangles and then copies the lower one over the upper one,
+//        :851-871) -- a cell visitor (visit.cuh) over the compact stream, scattering into a dense
+//        n x n matrix of doubles in HBM;
+//   2. numpy.corrcoef of its rows (:873): rows centred, C = X X^T / (n - 1), c_ij / sd_i / sd_j,
+//        clipped to [-1, 1], NaN -> 0 (:881).  X X^T is the one dense contraction of the path
+//        (2 n^3 flop in fp64, n up to 24 896 for chr1 at 10 kb).  It has to stay fp64 (1e-10
+//        parity), for which tcgen05 has no operand kind: the product runs on the fp64 tensor
+//        pipe through mma.sync.m8n8k4.f64 (SASS: DMMA), 128 x 128 tiles of the upper triangle,
+//        operands staged by a 4-deep cp.async ring in bank-padded shared memory, mirrored on
+//        the way out;
+//   3. the max_ev eigenpairs of largest magnitude (:926-937, scipy's eigsh = ARPACK): Lanczos
+//        with full re-orthogonalisation, every vector operation a kernel over HBM-resident
+//        data (lanczos.hpp holds the control flow, compartments.cu the kernels).
+//
+// The matrix stays on the device between the calls (tb_corr_build -> tb_corr_eig); tb_corr_get /
+// tb_corr_set move it for the reference's optional steps that stay on the host (savecorr file,
+// scipy median_filter smoothing).
+#include <math.h>
+
+#include "common.cuh"
+#include "lanczos.hpp"
+#include "visit.cuh"
+
+namespace tb {
+
+namespace {
+
+inline int grid_for(int64_t n, int threads, int sm_count, int per_sm = 8) {
+  int64_t g = (n + threads - 1) / threads, cap = (int64_t)sm_count * per_sm;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1. observed / expected
+// ---------------------------------------------------------------------------------------------
+struct ObsExpVisitor {
+  static constexpr int kShared = 0;
+  static constexpr int kThreads = 256;
+  int64_t lo, hi, ld;                 // section [lo, hi) of the genome
+  const int32_t *pos;                 // [hi - lo] index among the good bins of the section, -1 = bad
+  const double *w;                    // biases [N]
+  const double *expect;               // [hi - lo] expected count at each distance
+  double *out;                        // [n_pad x ld], zero-initialised
+  int64_t pi;
+  __device__ void begin(uint8_t *) {}
+  __device__ bool block(int64_t i0, int64_t i1, int64_t j0, int64_t j1) {
+    return i0 < hi && i1 > lo && j0 < hi && j1 > lo;
+  }
+  __device__ bool row(int64_t i) {
+    if (i < lo || i >= hi) return false;
+    pi = pos[i - lo];
+    return pi >= 0;
+  }
+  __device__ void cell(int64_t i, int64_t j, int32_t v) {
+    if (j >= hi) return;
+    const int64_t pj = pos[j - lo];
+    if (pj < 0) return;
+    // the reference's order of divisions for the cell it keeps (row j, column i of its nested
+    // lists, i <= j): float(v) / expected / bias[i] / bias[j]
+    const double x = (double)v / expect[j - i] / w[i] / w[j];
+    out[pi * ld + pj] = x;
+    out[pj * ld + pi] = x;
+  }
+  __device__ void end(uint8_t *) {}
+};
+
+// ---------------------------------------------------------------------------------------------
+// 2. correlation
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double *sh) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[wid] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int k = 0; k < nw; ++k) t += sh[k];     // every thread adds in the same order
+  return t;
+}
+
+// rows of X minus their mean (numpy.cov: X -= X.mean(axis=1)[:, None]); the zero padding stays zero
+__global__ void __launch_bounds__(256) k_center_rows(double *__restrict__ X, int64_t n, int64_t ld) {
+  __shared__ double sh[8];
+  for (int64_t r = blockIdx.x; r < n; r += gridDim.x) {
+    double *row = X + r * ld;
+    double acc = 0.0;
+    for (int64_t k = threadIdx.x; k < n; k += blockDim.x) acc += row[k];
+    const double mean = block_sum(acc, sh) / (double)n;
+    for (int64_t k = threadIdx.x; k < n; k += blockDim.x) row[k] -= mean;
+  }
+}
+
+constexpr int kBM = 128;              // CTA tile: 128 rows x 128 rows of X
+constexpr int kBK = 16;               // doubles of k per pipeline stage
+constexpr int kStages = 4;
+constexpr int kLdS = kBK + 4;         // shared row pitch in doubles: 40 words, so that the four rows a
+                                      // half-warp reads (8 words each) fall into disjoint banks
+constexpr int kStageDoubles = 2 * kBM * kLdS;
+constexpr int kSyrkShared = kStages * kStageDoubles * 8;   // 163 840 bytes
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// C[i][j] = scale * sum_k X[i][k] X[j][k] for the 128 x 128 tiles with tile row <= tile column;
+// each tile is also written transposed.  X: n_pad x ld, zero beyond n in both directions
+// (n_pad multiple of 128, ld multiple of 16).  8 warps as 2 x 4, warp tile 64 x 32:
+// 8 x 4 DMMA accumulator fragments per warp.
+__global__ void __launch_bounds__(256, 1)
+k_syrk_dmma(const double *__restrict__ X, int64_t ld, int64_t n, int ntile, double scale,
+            double *__restrict__ C, int64_t ldc) {
+  extern __shared__ __align__(16) double sm[];
+  int ti = 0, rem = blockIdx.x;
+  while (rem >= ntile - ti) { rem -= ntile - ti; ++ti; }
+  const int tj = ti + rem;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int g = lane >> 2, tg = lane & 3;
+  const double *gA = X + (int64_t)ti * kBM * ld;
+  const double *gB = X + (int64_t)tj * kBM * ld;
+  const int nk = (int)(ld / kBK);
+
+  auto load_stage = [&](int stage, int kt) {
+    double *sA = sm + (size_t)stage * kStageDoubles;
+    double *sB = sA + kBM * kLdS;
+    const int64_t k0 = (int64_t)kt * kBK;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int chunk = tid + c * 256;          // 128 rows x 8 chunks of 16 bytes
+      const int r = chunk >> 3, kc = (chunk & 7) * 2;
+      cp_async16(sA + r * kLdS + kc, gA + (int64_t)r * ld + k0 + kc);
+      cp_async16(sB + r * kLdS + kc, gB + (int64_t)r * ld + k0 + kc);
+    }
+  };
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < kStages - 1; ++s) {
+    if (s < nk) load_stage(s, s);
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<kStages - 2>();
+    __syncthreads();
+    const int nxt = kt + kStages - 1;
+    if (nxt < nk) load_stage(nxt % kStages, nxt);
+    cp_async_commit();
+    const double *sA = sm + (size_t)(kt % kStages) * kStageDoubles + (wm * 64 + g) * kLdS + tg;
+    const double *sB = sm + (size_t)(kt % kStages) * kStageDoubles + kBM * kLdS + (wn * 32 + g) * kLdS + tg;
+#pragma unroll
+    for (int kk = 0; kk < kBK; kk += 4) {
+      double a[8], b[4];
+#pragma unroll
+      for (int f = 0; f < 8; ++f) a[f] = sA[f * 8 * kLdS + kk];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) b[f] = sB[f * 8 * kLdS + kk];
+#pragma unroll
+      for (int fm = 0; fm < 8; ++fm)
+#pragma unroll
+        for (int fn = 0; fn < 4; ++fn) dmma884(acc[fm][fn][0], acc[fm][fn][1], a[fm], b[fn]);
+    }
+  }
+  cp_async_wait<0>();
+
+  const int64_t row0 = (int64_t)ti * kBM + wm * 64 + g;
+  const int64_t col0 = (int64_t)tj * kBM + wn * 32 + tg * 2;
+#pragma unroll
+  for (int fm = 0; fm < 8; ++fm) {
+    const int64_t r = row0 + fm * 8;
+    if (r >= n) continue;
+#pragma unroll
+    for (int fn = 0; fn < 4; ++fn) {
+      const int64_t c = col0 + fn * 8;
+      const double v0 = acc[fm][fn][0] * scale, v1 = acc[fm][fn][1] * scale;
+      if (c + 1 < n) {
+        *reinterpret_cast<double2 *>(C + r * ldc + c) = make_double2(v0, v1);
+        C[c * ldc + r] = v0;
+        C[(c + 1) * ldc + r] = v1;
+      } else if (c < n) {
+        C[r * ldc + c] = v0;
+        C[c * ldc + r] = v0;
+      }
+    }
+  }
+}
+
+// the same product without tensor instructions: 16 x 16 outputs per CTA, one per thread
+// (option corr_gemm=simple: parity reference of k_syrk_dmma)
+__global__ void __launch_bounds__(256) k_syrk_simple(const double *__restrict__ X, int64_t ld, int64_t n,
+                                                     double scale, double *__restrict__ C, int64_t ldc) {
+  __shared__ double sa[16][17], sb[16][17];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int64_t i0 = (int64_t)blockIdx.y * 16, j0 = (int64_t)blockIdx.x * 16;
+  double acc = 0.0;
+  for (int64_t k0 = 0; k0 < ld; k0 += 16) {
+    sa[ty][tx] = X[(i0 + ty) * ld + k0 + tx];
+    sb[ty][tx] = X[(j0 + ty) * ld + k0 + tx];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc = fma(sa[ty][k], sb[tx][k], acc);
+    __syncthreads();
+  }
+  const int64_t i = i0 + ty, j = j0 + tx;
+  if (i < n && j < n) C[i * ldc + j] = acc * scale;
+}
+
+__global__ void k_diag_sd(const double *__restrict__ C, int64_t n, int64_t ldc, double *__restrict__ sd) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    sd[i] = sqrt(C[i * ldc + i]);
+}
+
+// numpy.corrcoef: c /= stddev[:, None]; c /= stddev[None, :]; clip to [-1, 1]; then the
+// reference's NaN -> 0.  Both triangles get the value of the (min, max) ordering: symmetric bits.
+__global__ void k_corr_finish(double *__restrict__ C, int64_t n, int64_t ldc, const double *__restrict__ sd) {
+  const int64_t total = n * n;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / n, j = e - i * n;
+    const int64_t lo = i < j ? i : j, hi = i < j ? j : i;
+    // C is symmetric bit for bit (both kernels add the same products in the same order for
+    // (i, j) and (j, i)): every element only needs itself.  x / 0 = +-inf is clipped to +-1 as
+    // numpy does, 0 / 0 = NaN becomes the reference's 0.
+    double c = C[i * ldc + j] / sd[lo] / sd[hi];
+    c = isnan(c) ? 0.0 : fmin(fmax(c, -1.0), 1.0);
+    C[i * ldc + j] = c;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3. vector kernels of the Lanczos iteration
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9e3779b97f4a7c15ULL;
+  x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ULL;
+  x = (x ^ (x >> 27)) * 0x94d049bb133111ebULL;
+  return x ^ (x >> 31);
+}
+
+__global__ void k_random_vec(double *__restrict__ w, int64_t n, uint64_t seed) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = splitmix64(seed * 0x100000001b3ULL + (uint64_t)i);
+    w[i] = (double)(r >> 11) * (2.0 / 9007199254740992.0) - 1.0;      // uniform in [-1, 1)
+  }
+}
+
+// w = A v: one warp per row, 16-byte loads (the padding columns of A and the tail of v are zero)
+__global__ void __launch_bounds__(256) k_symv(const double *__restrict__ A, int64_t ld, int64_t n,
+                                              const double *__restrict__ v, double *__restrict__ w) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const double2 *v2 = reinterpret_cast<const double2 *>(v);
+  for (int64_t r = warp; r < n; r += nwarp) {
+    const double2 *row = reinterpret_cast<const double2 *>(A + r * ld);
+    double acc = 0.0;
+    for (int64_t k = lane; k < ld / 2; k += 32) {
+      const double2 a = row[k], x = v2[k];
+      acc = fma(a.x, x.x, acc);
+      acc = fma(a.y, x.y, acc);
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) w[r] = acc;
+  }
+}
+
+// h[k] = V[k] . w, one CTA per k
+__global__ void __launch_bounds__(256) k_dots(const double *__restrict__ V, int64_t ld, int64_t n,
+                                              const double *__restrict__ w, double *__restrict__ h) {
+  __shared__ double sh[8];
+  const double *row = V + (int64_t)blockIdx.x * ld;
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc = fma(row[i], w[i], acc);
+  const double t = block_sum(acc, sh);
+  if (threadIdx.x == 0) h[blockIdx.x] = t;
+}
+
+// w -= sum_k h[k] V[k]
+__global__ void k_subtract(const double *__restrict__ V, int64_t ld, int64_t n, int m,
+                           const double *__restrict__ h, double *__restrict__ w) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int k = 0; k < m; ++k) acc = fma(h[k], V[(int64_t)k * ld + i], acc);
+    w[i] -= acc;
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_norm(const double *__restrict__ w, int64_t n, double *__restrict__ out) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc = fma(w[i], w[i], acc);
+  const double t = block_sum(acc, sh);
+  if (threadIdx.x == 0) out[0] = sqrt(t);
+}
+
+__global__ void k_scale_copy(double *__restrict__ dst, const double *__restrict__ src, double scale, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = src[i] * scale;
+}
+
+// out[i] = sum_j coef[i * m + j] V[j]
+__global__ void k_combine(const double *__restrict__ V, int64_t ld, int64_t n, int m, int k,
+                          const double *__restrict__ coef, double *__restrict__ out) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n * k; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = e / n, i = e - v * n;
+    double acc = 0.0;
+    for (int j = 0; j < m; ++j) acc = fma(coef[v * m + j], V[(int64_t)j * ld + i], acc);
+    out[v * n + i] = acc;
+  }
+}
+
+struct DeviceOps {
+  tb_store *s;
+  const double *A;
+  int64_t n, ld;
+  int m_cap;
+  DevBuf<double> V, w, h, coef, vec;
+  PinnedBuf<double> hh;
+  void init(tb_store *store, int cap) {
+    s = store;
+    A = s->dense.p;
+    n = s->dense_n;
+    ld = s->dense_ld;
+    m_cap = cap;
+    V.alloc((size_t)m_cap * ld);
+    w.alloc(ld);
+    h.alloc(m_cap + 2);
+    hh.alloc(m_cap + 2);
+    TB_CUDA(cudaMemsetAsync(V.p, 0, V.bytes(), s->stream));
+    TB_CUDA(cudaMemsetAsync(w.p, 0, w.bytes(), s->stream));
+  }
+  void random_w(uint64_t seed) {
+    k_random_vec<<<grid_for(n, 256, s->sm_count), 256, 0, s->stream>>>(w.p, n, seed);
+  }
+  void matvec(int slot) {
+    k_symv<<<grid_for(n * 32, 256, s->sm_count), 256, 0, s->stream>>>(A, ld, n, V.p + (int64_t)slot * ld, w.p);
+  }
+  void project(int m, double *out) {
+    if (m <= 0) return;
+    k_dots<<<m, 256, 0, s->stream>>>(V.p, ld, n, w.p, h.p);
+    k_subtract<<<grid_for(n, 128, s->sm_count), 128, 0, s->stream>>>(V.p, ld, n, m, h.p, w.p);
+    TB_CUDA(cudaMemcpyAsync(hh.p, h.p, m * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    TB_CUDA(cudaStreamSynchronize(s->stream));
+    for (int k = 0; k < m; ++k) out[k] = hh.p[k];
+  }
+  double norm_w() {
+    k_norm<<<1, 1024, 0, s->stream>>>(w.p, n, h.p + m_cap + 1);
+    TB_CUDA(cudaMemcpyAsync(hh.p + m_cap + 1, h.p + m_cap + 1, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    TB_CUDA(cudaStreamSynchronize(s->stream));
+    return hh.p[m_cap + 1];
+  }
+  void keep(int slot, double scale) {
+    k_scale_copy<<<grid_for(n, 256, s->sm_count), 256, 0, s->stream>>>(V.p + (int64_t)slot * ld, w.p, scale, n);
+  }
+  void combine(int m, int k, const double *h_coef, double *h_out) {
+    coef.alloc((size_t)k * m);
+    vec.alloc((size_t)k * n);
+    TB_CUDA(cudaMemcpyAsync(coef.p, h_coef, coef.bytes(), cudaMemcpyHostToDevice, s->stream));
+    k_combine<<<grid_for(n * k, 256, s->sm_count), 256, 0, s->stream>>>(V.p, ld, n, m, k, coef.p, vec.p);
+    for (int v = 0; v < k; ++v) {              // unit norm, as ARPACK returns them
+      k_norm<<<1, 1024, 0, s->stream>>>(vec.p + (int64_t)v * n, n, h.p);
+      TB_CUDA(cudaMemcpyAsync(hh.p, h.p, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+      TB_CUDA(cudaStreamSynchronize(s->stream));
+      const double nv = hh.p[0];
+      if (nv > 0.0)
+        k_scale_copy<<<grid_for(n, 256, s->sm_count), 256, 0, s->stream>>>(vec.p + (int64_t)v * n,
+                                                                        vec.p + (int64_t)v * n, 1.0 / nv, n);
+    }
+    TB_CUDA(cudaMemcpyAsync(h_out, vec.p, vec.bytes(), cudaMemcpyDeviceToHost, s->stream));
+    TB_CUDA(cudaStreamSynchronize(s->stream));
+  }
+};
+
+int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
+
+template <int N>
+struct Events {                       // destroyed on every exit path
+  cudaEvent_t e[N];
+  Events() { for (auto &x : e) x = nullptr; for (auto &x : e) TB_CUDA(cudaEventCreate(&x)); }
+  ~Events() { for (auto &x : e) if (x) cudaEventDestroy(x); }
+  cudaEvent_t operator[](int k) const { return e[k]; }
+};
+
+void alloc_dense(tb_store *s, int64_t n) {
+  s->dense_n = n;
+  s->dense_ld = round_up(n > 0 ? n : 1, kBK);
+  s->dense_rows = round_up(n > 0 ? n : 1, kBM);
+  s->dense.alloc((size_t)s->dense_rows * s->dense_ld);
+  TB_CUDA(cudaMemsetAsync(s->dense.p, 0, s->dense.bytes(), s->stream));
+}
+
+}  // namespace
+
+// Builds, for the section [beg, end) of the genome, the observed / expected matrix over its good
+// bins (stage 0) and from it the correlation matrix of its rows (stage 1), resident in the store.
+// h_expected[d], d < end - beg.  *n_good = its order.
+void corr_build(tb_store *s, int64_t beg, int64_t end, const double *h_bias, const uint8_t *h_bad,
+                const double *h_expected, int stage, int64_t *n_good) {
+  cudaStream_t st = s->stream;
+  const int64_t N = s->nbins;
+  TB_REQUIRE(beg >= 0 && beg <= end && end <= N && h_bias && h_expected && n_good, "corr_build: bad arguments");
+  const int64_t len = end - beg;
+  std::vector<int32_t> pos(len > 0 ? len : 1, -1);
+  int64_t n = 0;
+  for (int64_t i = 0; i < len; ++i)
+    if (!(h_bad && h_bad[beg + i])) pos[i] = (int32_t)n++;
+  *n_good = n;
+  for (double &t : s->corr_ms) t = 0.0;
+  s->dense_stage = -1;
+  if (n == 0) {
+    s->dense.release();
+    s->dense_n = 0;
+    return;
+  }
+  TB_REQUIRE(n <= 65536, "corr_build: more than 65536 good bins in one section");
+  Events<5> ev;
+  alloc_dense(s, n);
+  DevBuf<int32_t> d_pos;
+  DevBuf<double> d_exp;
+  d_pos.alloc(len);
+  d_exp.alloc(len);
+  TB_CUDA(cudaMemcpyAsync(d_pos.p, pos.data(), len * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  TB_CUDA(cudaMemcpyAsync(d_exp.p, h_expected, len * sizeof(double), cudaMemcpyHostToDevice, st));
+  TB_CUDA(cudaMemcpyAsync(s->b.p, h_bias, N * sizeof(double), cudaMemcpyHostToDevice, st));
+  TB_CUDA(cudaEventRecord(ev[0], st));
+  ObsExpVisitor vis;
+  vis.lo = beg; vis.hi = end; vis.ld = s->dense_ld;
+  vis.pos = d_pos.p;
+  vis.w = s->b.p;
+  vis.expect = d_exp.p;
+  vis.out = s->dense.p;
+  vis.pi = 0;
+  visit_upper(s, vis);
+  if (s->world > 1)        // a row-sharded store filled the cells of its own rows: the others are zero
+    allreduce_f64(s, s->dense.p, s->dense.p, s->dense.n);
+  TB_CUDA(cudaEventRecord(ev[1], st));
+  s->dense_stage = 0;
+  if (stage >= 1) {
+    DevBuf<double> C, sd;
+    C.alloc(s->dense.n);
+    sd.alloc(n);
+    TB_CUDA(cudaMemsetAsync(C.p, 0, C.bytes(), st));
+    k_center_rows<<<(int)std::min<int64_t>(n, (int64_t)s->sm_count * 8), 256, 0, st>>>(s->dense.p, n, s->dense_ld);
+    TB_CUDA(cudaEventRecord(ev[2], st));
+    // numpy.cov: c = dot(X, X.T); c *= 1 / (n - 1)   (n == 1: 1 / 0 -> the row becomes NaN -> 0)
+    const double scale = 1.0 / (double)(n - 1);
+    if (s->corr_gemm_mode == 1) {
+      dim3 grid((unsigned)((n + 15) / 16), (unsigned)((n + 15) / 16));
+      k_syrk_simple<<<grid, 256, 0, st>>>(s->dense.p, s->dense_ld, n, scale, C.p, s->dense_ld);
+    } else {
+      const int ntile = (int)(s->dense_rows / kBM);
+      TB_CUDA(cudaFuncSetAttribute(k_syrk_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, kSyrkShared));
+      k_syrk_dmma<<<ntile * (ntile + 1) / 2, 256, kSyrkShared, st>>>(s->dense.p, s->dense_ld, n, ntile, scale, C.p,
+                                                                    s->dense_ld);
+    }
+    TB_CUDA(cudaGetLastError());
+    TB_CUDA(cudaEventRecord(ev[3], st));
+    k_diag_sd<<<grid_for(n, 256, s->sm_count), 256, 0, st>>>(C.p, n, s->dense_ld, sd.p);
+    k_corr_finish<<<grid_for(n * n, 256, s->sm_count, 16), 256, 0, st>>>(C.p, n, s->dense_ld, sd.p);
+    TB_CUDA(cudaEventRecord(ev[4], st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    std::swap(s->dense.p, C.p);                 // the store keeps the correlation, X goes away with C
+    std::swap(s->dense.n, C.n);
+    s->dense_stage = 1;
+    float ms = 0.f;
+    TB_CUDA(cudaEventElapsedTime(&ms, ev[1], ev[2])); s->corr_ms[1] = ms;
+    TB_CUDA(cudaEventElapsedTime(&ms, ev[2], ev[3])); s->corr_ms[2] = ms;
+    TB_CUDA(cudaEventElapsedTime(&ms, ev[3], ev[4])); s->corr_ms[3] = ms;
+  }
+  TB_CUDA(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  TB_CUDA(cudaEventElapsedTime(&ms, ev[0], ev[1])); s->corr_ms[0] = ms;
+}
+
+// the resident matrix (n x n, row-major) to the host / from the host
+void corr_get(tb_store *s, double *h_out) {
+  TB_REQUIRE(h_out, "corr_get: null argument");
+  if (s->dense_n == 0) return;
+  TB_REQUIRE(s->dense.p, "corr_get: no matrix resident (call tb_corr_build or tb_corr_set first)");
+  const int64_t n = s->dense_n;
+  TB_CUDA(cudaMemcpy2DAsync(h_out, n * sizeof(double), s->dense.p, s->dense_ld * sizeof(double), n * sizeof(double),
+                            n, cudaMemcpyDeviceToHost, s->stream));
+  TB_CUDA(cudaStreamSynchronize(s->stream));
+}
+
+void corr_set(tb_store *s, int64_t n, const double *h_in) {
+  TB_REQUIRE(n >= 1 && n <= 65536 && h_in, "corr_set: bad arguments");
+  alloc_dense(s, n);
+  TB_CUDA(cudaMemcpy2DAsync(s->dense.p, s->dense_ld * sizeof(double), h_in, n * sizeof(double), n * sizeof(double), n,
+                            cudaMemcpyHostToDevice, s->stream));
+  TB_CUDA(cudaStreamSynchronize(s->stream));
+  s->dense_stage = 2;
+}
+
+// The k eigenpairs of largest magnitude of the resident matrix (k >= n: all of them), eigenvalues
+// descending; h_evecs[v * n + i].  info: [0] eigenpairs returned, [1] Lanczos vectors,
+// [2] restarts, [3] converged.
+void corr_eig(tb_store *s, int32_t k, double *h_evals, double *h_evecs, int32_t info[4]) {
+  TB_REQUIRE(k >= 1 && h_evals && h_evecs && info, "corr_eig: bad arguments");
+  TB_REQUIRE(s->dense.p && s->dense_n > 0, "corr_eig: no matrix resident (call tb_corr_build or tb_corr_set first)");
+  const int64_t n = s->dense_n;
+  const bool all = k >= n;
+  if (all) k = (int32_t)n;
+  Events<2> ev;
+  TB_CUDA(cudaEventRecord(ev[0], s->stream));
+  int cap = (int)std::min<int64_t>(n, all ? n : std::max<int64_t>(20 * (int64_t)k, 600));
+  DeviceOps ops;
+  ops.init(s, cap);
+  LanczosResult r = lanczos_largest(ops, n, k, cap, 1e-13, all, h_evecs);
+  TB_CUDA(cudaEventRecord(ev[1], s->stream));
+  TB_CUDA(cudaStreamSynchronize(s->stream));
+  float ms = 0.f;
+  TB_CUDA(cudaEventElapsedTime(&ms, ev[0], ev[1]));
+  s->corr_ms[4] = ms;
+  info[0] = (int32_t)r.evals.size();
+  info[1] = r.steps;
+  info[2] = r.restarts;
+  info[3] = r.converged ? 1 : 0;
+  for (size_t i = 0; i < r.evals.size(); ++i) h_evals[i] = r.evals[i];
+  if (!r.converged) {
+    set_error("corr_eig: Lanczos did not converge in %d steps (residual %.3g)", r.steps, r.residual);
+    throw Fail{TB_ERR_STATE};
+  }
+}
+
+}  // namespace tb

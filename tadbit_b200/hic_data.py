@@ -6,8 +6,9 @@ matrix-balancing path: same constructor arguments, ``len()``, ``hic[i, j]``,
 ``load_biases``, ``get_hic_data_as_csr`` and the attributes ``bias``, ``bads``,
 ``expected``, ``chromosomes``, ``sections``, ``section_pos``, ``resolution``,
 ``symmetricized``.  The cells live in HBM as a ``ContactStore``; all reductions are
-CUDA kernels behind the C-ABI.  Everything else of the reference class (compartments,
-writers, ...) is out of scope.
+CUDA kernels behind the C-ABI.  Dense windows (``get_matrix`` ...) and ``find_compartments``
+are the consumers of the biases that SURVEY.md 8f ranks next; the rest of the reference class
+(``find_compartments_beta``, cooler export, ...) is out of scope.
 """
 from collections import OrderedDict
 from pickle import HIGHEST_PROTOCOL, dump, load
@@ -463,6 +464,23 @@ class HiC_data(object):
                                           normalized=normalized):
                 out.write('\t'.join([str(i) for i in line]) + '\n')
         out.close()
+
+    # -- compartments -------------------------------------------------------
+    def find_compartments(self, crms=None, savefig=None, savedata=None, savecorr=None, show=False,
+                          suffix='', ev_index=None, rich_in_A=None, format='png', savedir=None,
+                          max_ev=3, show_compartment_labels=False, smoothing_window=0, **kwargs):
+        """A/B compartments per chromosome (hic_data.py:736-1031); see tadbit_b200/compartments.py."""
+        from .compartments import find_compartments
+        return find_compartments(self, crms=crms, savefig=savefig, savedata=savedata,
+                                 savecorr=savecorr, show=show, suffix=suffix, ev_index=ev_index,
+                                 rich_in_A=rich_in_A, format=format, savedir=savedir, max_ev=max_ev,
+                                 show_compartment_labels=show_compartment_labels,
+                                 smoothing_window=smoothing_window, **kwargs)
+
+    def write_compartments(self, savedata, chroms=None, ev_nums=None):
+        """hic_data.py:1486-1511."""
+        from .compartments import write_compartments
+        return write_compartments(self, savedata, chroms=chroms, ev_nums=ev_nums)
 
     def save_biases(self, fnam, protocol=None):
         """Pickle biases, decay and bad columns in the reference's format

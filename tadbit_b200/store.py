@@ -339,6 +339,59 @@ class ContactStore(object):
                                   ptr(ct, C.c_double)))
         return nrm, raw, (float(ct[0]), float(ct[1]))
 
+    # -- N4: compartments (tb_corr_*) ---------------------------------------------------------------
+    def corr_build(self, beg, end, bias, bad, expected, stage=1):
+        """Observed / expected matrix (``stage=0``) or its correlation matrix (``stage=1``) of the
+        section ``[beg, end)`` over its good bins, left resident on the device; ``expected[d]`` for
+        ``d < end - beg``.  Returns the order of the matrix (number of good bins)."""
+        m, mp = self._mask(bad)
+        b, bp = self._bias(bias)
+        e = np.ascontiguousarray(expected, dtype=np.float64)
+        if e.shape != (max(int(end) - int(beg), 0),):
+            raise ValueError("expected must have one entry per distance of the section")
+        n = C.c_int64()
+        check(lib().tb_corr_build(self._h, int(beg), int(end), bp, mp, ptr(e, C.c_double), int(stage),
+                                  C.byref(n)))
+        self._corr_n = n.value
+        return n.value
+
+    def corr_get(self):
+        """The resident matrix as float64[n, n]."""
+        n = getattr(self, "_corr_n", 0)
+        out = np.zeros((n, n), dtype=np.float64)
+        if n:
+            check(lib().tb_corr_get(self._h, ptr(out, C.c_double)))
+        return out
+
+    def corr_set(self, matrix):
+        """Replace the resident matrix by a symmetric float64[n, n] from the host."""
+        a = np.ascontiguousarray(matrix, dtype=np.float64)
+        if a.ndim != 2 or a.shape[0] != a.shape[1] or a.shape[0] < 1:
+            raise ValueError("corr_set needs a square matrix")
+        check(lib().tb_corr_set(self._h, a.shape[0], ptr(a, C.c_double)))
+        self._corr_n = a.shape[0]
+
+    def corr_eig(self, k):
+        """The ``k`` eigenpairs of largest magnitude of the resident matrix (``k >= n``: all of
+        them): (eigenvalues descending float64[k'], eigenvectors float64[k', n], info dict)."""
+        n = getattr(self, "_corr_n", 0)
+        kk = max(min(int(k), n), 1)
+        evals = np.zeros(kk, dtype=np.float64)
+        evecs = np.zeros((kk, max(n, 1)), dtype=np.float64)
+        info = np.zeros(4, dtype=np.int32)
+        check(lib().tb_corr_eig(self._h, int(k), ptr(evals, C.c_double), ptr(evecs, C.c_double),
+                                ptr(info, C.c_int32)))
+        got = int(info[0])
+        return evals[:got], evecs[:got, :n], dict(steps=int(info[1]), restarts=int(info[2]),
+                                                  converged=bool(info[3]))
+
+    def corr_timing(self):
+        """Device ms of the last corr_build / corr_eig: cell visitor, centring, X X^T, scaling, eigen-solver."""
+        out = np.zeros(8, dtype=np.float64)
+        check(lib().tb_corr_timing(self._h, ptr(out, C.c_double)))
+        return dict(visit_ms=out[0], center_ms=out[1], gemm_ms=out[2], scale_ms=out[3], eig_ms=out[4],
+                    n=int(out[5]), stage=int(out[6]), gemm="simple" if out[7] else "dmma")
+
     def diag_sums(self, bad, ndiag):
         m, mp = self._mask(bad)
         out = np.zeros(max(int(ndiag), 0), dtype=np.int64)

@@ -61,6 +61,24 @@ class NumpyStore(object):
             full = full / b[r0:r1, None] / b[None, c0:c1]
         return full
 
+    def corr_build(self, beg, end, bias, bad, expected, stage=1):   # tb_corr_build
+        mat = orc.obs_exp_matrix(self.m, beg, end, bias, self._bads(bad), expected)
+        self._dense = orc.correlation_matrix(mat) if stage >= 1 and mat.shape[0] else mat
+        return self._dense.shape[0]
+
+    def corr_get(self):                                    # tb_corr_get
+        return np.array(self._dense, dtype=np.float64)
+
+    def corr_set(self, matrix):                            # tb_corr_set
+        self._dense = np.array(matrix, dtype=np.float64)
+
+    def corr_eig(self, k):                                 # tb_corr_eig
+        w, v = orc.largest_eigenpairs(self._dense, k)
+        return w, v, dict(steps=0, restarts=0, converged=True)
+
+    def corr_timing(self):                                 # tb_corr_timing
+        return {}
+
     def decay_sums(self, bias, bad=None):                  # tb_decay_sums
         return orc.decay_sums(self.m, bias, self._bads(bad))
 
