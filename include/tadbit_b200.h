@@ -140,7 +140,12 @@ int tb_store_info(const tb_store *s, int64_t *nbins, int64_t *row_begin, int64_t
  *   "exchange" = "fused" (default) or "nccl": per ICE pass either ONE kernel that stores the owned
  *     row sums into every GPU's buffer (peer-mapped memory), waits on flags and does the
  *     statistics and the bias update, or combine -> ncclAllReduce -> statistics -> update as
- *     separate launches.  All ranks of a group must choose the same. */
+ *     separate launches.  All ranks of a group must choose the same.
+ *   "k1_streams" = "2" (default) or "1": the dense kernel of a row-sum evaluation on a second
+ *     stream next to the tile kernel, or the two kernels back to back on the store's stream
+ *     (same bits either way; 0.5 % faster on a whole genome-wide matrix, 4.4 % on a 1/8 shard).
+ *   "corr_gemm" = "dmma" (default) or "simple": X X^T of tb_corr_build as fp64 tensor-core tiles
+ *     or as a plain kernel (parity reference of the former). */
 int tb_store_set_option(tb_store *s, const char *name, const char *value);
 
 /* Layout of the compact row-sum stream (tadbit_b200/csrc/encode.cu, tiles.cu):
@@ -232,6 +237,10 @@ int tb_ice_batch(tb_store *s, const uint8_t *h_bad, int32_t iterations, double m
  * HOST).  The host combines both to re-cut row blocks so that every GPU takes the same time per
  * pass (tadbit_b200/workloads.py:build_sharded). */
 int tb_probe_rowsum(tb_store *s, int32_t reps, double ms[3]);
+/* Mean device ms of one K1 evaluation issued as the ICE loop issues it: ms[0] with its two kernels
+ * back to back on one stream, ms[1] with the dense kernel on a second stream next to the tile
+ * kernel (tb_store_set_option "k1_streams" = "1" | "2").  Timing only, also on an unconnected shard. */
+int tb_probe_k1(tb_store *s, int32_t reps, double ms[2]);
 int tb_row_work(tb_store *s, int64_t *h_dense_bytes, int64_t *h_tile_cells);
 
 /* timing of the last tb_ice call, measured with CUDA events on the store's stream:

@@ -68,6 +68,7 @@ PROTOTYPES = {
     "tb_ice_batch": ([_store, _u8p, C.c_int32, C.c_double, _f64p, _f64p, C.POINTER(C.c_int32)],
                      C.c_int),
     "tb_probe_rowsum": ([_store, C.c_int32, _f64p], C.c_int),
+    "tb_probe_k1": ([_store, C.c_int32, _f64p], C.c_int),
     "tb_row_work": ([_store, _i64p, _i64p], C.c_int),
     "tb_ice_last_timing": ([_store, _f64p, _f64p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
                            C.c_int),

@@ -310,6 +310,12 @@ int tb_store_destroy(tb_store *s) {
     comm_destroy(s);
   } catch (...) {
   }
+  if (s->stream2) {
+    cudaStreamSynchronize(s->stream2);
+    cudaStreamDestroy(s->stream2);
+  }
+  if (s->k1_fork) cudaEventDestroy(s->k1_fork);
+  if (s->k1_join) cudaEventDestroy(s->k1_join);
   if (s->stream) {
     cudaStreamSynchronize(s->stream);
     cudaStreamDestroy(s->stream);
@@ -349,6 +355,12 @@ int tb_store_set_option(tb_store *s, const char *name, const char *value) {
     if (!strcmp(value, "nccl")) s->exchange_mode = 0;
     else if (!strcmp(value, "fused")) s->exchange_mode = 1;
     else { set_error("exchange must be 'fused' or 'nccl'"); return TB_ERR_ARG; }
+    return TB_OK;
+  }
+  if (!strcmp(name, "k1_streams")) {     // K1's two kernels back to back (1) or on two streams (2)
+    if (!strcmp(value, "1")) s->k1_streams_mode = 1;
+    else if (!strcmp(value, "2")) s->k1_streams_mode = 2;
+    else { set_error("k1_streams must be '1' or '2'"); return TB_ERR_ARG; }
     return TB_OK;
   }
   if (!strcmp(name, "corr_gemm")) {      // X X^T of tb_corr_build: fp64 tensor tiles, or the plain parity kernel
@@ -473,6 +485,15 @@ int tb_probe_rowsum(tb_store *s, int32_t reps, double ms[3]) {
     TB_REQUIRE(s, "null argument");
     DeviceGuard g(s->device);
     probe_rowsum(s, reps, ms);
+    return TB_OK;
+  });
+}
+
+int tb_probe_k1(tb_store *s, int32_t reps, double ms[2]) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(s, "null argument");
+    DeviceGuard g(s->device);
+    probe_k1(s, reps, ms);
     return TB_OK;
   });
 }

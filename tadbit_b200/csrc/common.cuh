@@ -191,6 +191,9 @@ struct tb_comm {
 struct tb_store {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;         // K1: the dense kernel runs here next to the tile kernel (rowsum.cu)
+  cudaEvent_t k1_fork = nullptr, k1_join = nullptr;
+  int k1_streams_mode = -1;               // -1 default (TB_K1_STREAMS, else 2), 1 serial, 2 two streams
   int sm_count = 148;
   int64_t nbins = 0, row_begin = 0, row_end = 0, nrows = 0;
   int64_t nnz_full = 0;     // stored full-matrix cells with row in the block
@@ -325,6 +328,7 @@ int ice(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, d
         double *h_trace, int32_t *n_passes);
 void norm_sum(tb_store *s, const double *h_bias, const uint8_t *h_bad, double *out);
 void probe_rowsum(tb_store *s, int32_t reps, double ms[3]);
+void probe_k1(tb_store *s, int32_t reps, double ms[2]);
 void row_work(tb_store *s, int64_t *h_dense, int64_t *h_tile);
 void ice_batch(tb_store *s, const uint8_t *h_bad, int32_t iterations, double max_dev, double *h_bias,
                double *h_trace, int32_t *n_passes);

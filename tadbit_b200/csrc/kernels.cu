@@ -731,11 +731,15 @@ struct DiagVisitor {
   const int64_t *chrom_end;       // [sections] one past the last bin of each section
   int64_t ndiag;
   unsigned long long *hist;
-  unsigned long long *sh;
+  // shared histogram as two 32-bit halves per distance: a 64-bit atomic add on shared memory is a
+  // compare-and-swap loop (ncu, first version: 6 wavefronts per add), a 32-bit one is native; the
+  // carry out of the low half (rare) and the sign extension of a negative count go to the high half
+  unsigned int *lo, *hi;
   int64_t jend;                   // per thread: cells of the current row count up to this column
   __device__ void begin(uint8_t *smem) {
-    sh = reinterpret_cast<unsigned long long *>(smem);
-    for (int k = threadIdx.x; k < kDiagShared; k += blockDim.x) sh[k] = 0ull;
+    lo = reinterpret_cast<unsigned int *>(smem);
+    hi = lo + kDiagShared;
+    for (int k = threadIdx.x; k < 2 * kDiagShared; k += blockDim.x) lo[k] = 0u;
   }
   // rows [i0, i1) reach at most to the end of the section of row i1 - 1
   __device__ bool block(int64_t i0, int64_t i1, int64_t j0, int64_t j1) {
@@ -750,13 +754,20 @@ struct DiagVisitor {
   __device__ void cell(int64_t i, int64_t j, int32_t v) {
     if (j >= jend) return;
     const int64_t d = j - i;
-    const unsigned long long u = (unsigned long long)(long long)v;
-    if (d < kDiagShared) atomicAdd(&sh[d], u);
-    else atomicAdd(&hist[d], u);
+    if (d < kDiagShared) {
+      const unsigned int add = (unsigned int)v;
+      const unsigned int old = atomicAdd(&lo[d], add);
+      const unsigned int up = (v < 0 ? 0xffffffffu : 0u) + ((unsigned int)(old + add) < old ? 1u : 0u);
+      if (up) atomicAdd(&hi[d], up);
+    } else {
+      atomicAdd(&hist[d], (unsigned long long)(long long)v);
+    }
   }
   __device__ void end(uint8_t *smem) {
-    for (int k = threadIdx.x; k < kDiagShared && k < ndiag; k += blockDim.x)
-      if (sh[k]) atomicAdd(&hist[k], sh[k]);
+    for (int k = threadIdx.x; k < kDiagShared && k < ndiag; k += blockDim.x) {
+      const unsigned long long t = ((unsigned long long)hi[k] << 32) + lo[k];
+      if (t) atomicAdd(&hist[k], t);
+    }
   }
   int64_t ndiag_rows;             // number of bins (rows of a partial last tile lie beyond it)
 };
@@ -1292,7 +1303,7 @@ void diag_sums(tb_store *s, const uint8_t *h_bad, int64_t ndiag, int64_t *h_sum_
   vis.jend = 0;
   vis.ndiag = ndiag;
   vis.hist = hist.p;
-  vis.sh = nullptr;
+  vis.lo = vis.hi = nullptr;
   visit_upper(s, vis);
   TB_CUDA(cudaEventRecord(e1, st));
   unsigned long long *src = hist.p;
@@ -1465,6 +1476,31 @@ void probe_rowsum(tb_store *s, int32_t reps, double ms[3]) {
                     "CTAs finish %.1f us (first) / %.1f us (mean) / %.1f us (last) after the first one starts\n",
             grid, utot, umin, umax, ttot, 1e-3 * end_min, 1e-3 * end_sum / grid, 1e-3 * (double)(t1 - t0));
   }
+}
+
+// Mean device time of one K1 evaluation as the ICE loop issues it: ms[0] with its two kernels
+// back to back on one stream, ms[1] with the dense kernel on a second stream next to the tile
+// kernel (rowsum.cu:launch_rowsum; option k1_streams).  Also on an unconnected shard.
+void probe_k1(tb_store *s, int32_t reps, double ms[2]) {
+  cudaStream_t st = s->stream;
+  TB_REQUIRE(reps > 0 && ms, "probe_k1: bad arguments");
+  TB_CUDA(cudaMemsetAsync(s->bad.p, 0, s->nbins, st));
+  k_ice_init<<<grid_1d(s->nbins, 256, s->sm_count), 256, 0, st>>>(s->bad.p, s->nbins, s->x.p, s->b.p,
+                                                                  s->state.p, s->px.epoch);
+  const int keep = s->k1_streams_mode;
+  cudaEvent_t e0 = ice_event(s, 0), e1 = ice_event(s, 1);
+  for (int mode = 1; mode <= 2; ++mode) {
+    s->k1_streams_mode = mode;
+    launch_rowsum(s, s->x.p, nullptr);               // warm-up (creates the second stream)
+    TB_CUDA(cudaEventRecord(e0, st));
+    for (int r = 0; r < reps; ++r) launch_rowsum(s, s->x.p, nullptr);
+    TB_CUDA(cudaEventRecord(e1, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    float f = 0.f;
+    TB_CUDA(cudaEventElapsedTime(&f, e0, e1));
+    ms[mode - 1] = f / reps;
+  }
+  s->k1_streams_mode = keep;
 }
 
 }  // namespace tb

@@ -23,6 +23,8 @@
 // Integer -> double by exponent splice (one DADD) instead of I2F.F64.
 #include <type_traits>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace tb {
@@ -379,9 +381,54 @@ bool sparse_in_dense_tail(const tb_store *s) {
   return s->n_groups > 0 && s->n_sparse <= 2 * (int64_t)s->n_dense_ctas;
 }
 
+// One K1 evaluation = the dense kernel (static panel ranges per CTA) and the tile kernel (work
+// units fetched from a counter), both one CTA per SM with all of its shared memory.  Back to back
+// on one stream each pays its own tail: the second kernel cannot start before the slowest CTA of
+// the first has left.  They are independent (own partials, same x), so the dense kernel goes to
+// a second stream first and the tile kernel follows on the main stream: its CTAs start on an SM
+// as soon as the dense CTA there retires, and the dynamic unit fetch absorbs the spread
+// (option k1_streams = 1 | 2, environment TB_K1_STREAMS; default 2).  Same bits either way.
+// Measured on the genome-wide 5 kb matrix (tb_probe_k1): whole matrix 2.067 -> 2.055 ms per pass
+// (0.5 %), a 1/2 shard 1.044 -> 1.029 ms (1.4 %), a 1/8 shard 0.309 -> 0.296 ms (4.4 %): the
+// shorter the kernels, the larger the share of their tails.
+static bool two_streams(const tb_store *s) {
+  if (s->k1_streams_mode >= 0) return s->k1_streams_mode == 2;
+  static int env = -1;
+  if (env < 0) {
+    const char *e = getenv("TB_K1_STREAMS");
+    env = (e && e[0] == '1') ? 1 : 2;
+  }
+  return env == 2;
+}
+
 void launch_rowsum(tb_store *s, const double *x, const IceState *state) {
+  if (!two_streams(s) || !s->n_groups || !s->t_nunits) {
+    launch_rowsum_tiles(s, x, state);
+    launch_rowsum_chunks(s, x, state);
+    return;
+  }
+  if (!s->stream2) {
+    // highest priority: of two kernels that become runnable together its CTAs are placed first
+    int prio_low = 0, prio_high = 0;
+    TB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+    TB_CUDA(cudaStreamCreateWithPriority(&s->stream2, cudaStreamNonBlocking, prio_high));
+    TB_CUDA(cudaEventCreateWithFlags(&s->k1_fork, cudaEventDisableTiming));
+    TB_CUDA(cudaEventCreateWithFlags(&s->k1_join, cudaEventDisableTiming));
+  }
+  cudaStream_t main_stream = s->stream;
+  TB_CUDA(cudaEventRecord(s->k1_fork, main_stream));
+  TB_CUDA(cudaStreamWaitEvent(s->stream2, s->k1_fork, 0));
+  s->stream = s->stream2;                     // the launch helpers use the store's stream
+  try {
+    launch_rowsum_chunks(s, x, state);
+  } catch (...) {
+    s->stream = main_stream;
+    throw;
+  }
+  s->stream = main_stream;
+  TB_CUDA(cudaEventRecord(s->k1_join, s->stream2));
   launch_rowsum_tiles(s, x, state);
-  launch_rowsum_chunks(s, x, state);
+  TB_CUDA(cudaStreamWaitEvent(main_stream, s->k1_join, 0));
 }
 
 void launch_rowsum_chunks(tb_store *s, const double *x, const IceState *state) {

@@ -243,6 +243,13 @@ class ContactStore(object):
         check(lib().tb_probe_rowsum(self._h, int(reps), ptr(ms, C.c_double)))
         return tuple(ms.tolist())
 
+    def probe_k1(self, reps=8):
+        """Mean device ms of one K1 evaluation as the ICE loop issues it: (kernels back to back,
+        dense kernel on a second stream next to the tile kernel)."""
+        ms = np.zeros(2, dtype=np.float64)
+        check(lib().tb_probe_k1(self._h, int(reps), ptr(ms, C.c_double)))
+        return tuple(ms.tolist())
+
     def row_work(self):
         """Per owned row: payload bytes of its dense chunks, cells in sparse tiles."""
         i = self.info()

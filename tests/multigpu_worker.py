@@ -52,6 +52,22 @@ def main():
     nccl_bias, nccl_passes = hic.bias.to_array().copy(), len(hic.last_trace)
     store.set_option("exchange", "fused")
     hic.normalize_hic(iterations=100, max_dev=1e-5, silent=True)
+    # K1 with its two kernels back to back instead of on two streams: the same bits
+    store.set_option("k1_streams", "1")
+    hic.normalize_hic(iterations=100, max_dev=1e-5, silent=True)
+    serial_bias = hic.bias.to_array().copy()
+    store.set_option("k1_streams", "2")
+    # N4: observed / expected and correlation matrix of the first chromosome from the row-sharded
+    # store (every rank ends with the whole matrix), leading eigenpairs
+    sec = list(wl["chromosomes"])[0]
+    c_beg, c_end = hic.section_pos[sec]
+    c_mask = bad_mask(wl["size"], hic.bads)
+    c_exp = np.array([hic.expected[d] or 1.0 for d in range(c_end - c_beg)])
+    store.corr_build(c_beg, c_end, hic.bias.to_array(), c_mask, c_exp, stage=0)
+    cmp_oe = store.corr_get()
+    store.corr_build(c_beg, c_end, hic.bias.to_array(), c_mask, c_exp, stage=1)
+    cmp_corr = store.corr_get()
+    cmp_vals, cmp_vecs, _ = store.corr_eig(3)
     # pre-partitioned input: this rank's rows exported in CSR form and a second store built from them
     ptr, cc, vv = store.export_csr("full_rows")
     again = tadbit_b200.ContactStore.from_csr(wl["size"], ptr, cc, vv, form="full_rows",
@@ -62,7 +78,8 @@ def main():
     result = dict(bads=hic.bads, bias=hic.bias.to_array(), raw_bias=raw_bias, expected=hic.expected, nnz=nnz,
                   rsum=rsum, raw=raw, passes=len(hic.last_trace), block=block,
                   nnz_upper=store.info()["nnz_upper"], exchange=exchange, nccl_bias=nccl_bias,
-                  nccl_passes=nccl_passes, same_rows=bool(same_rows))
+                  nccl_passes=nccl_passes, same_rows=bool(same_rows), serial_bias=serial_bias,
+                  cmp_oe=cmp_oe, cmp_corr=cmp_corr, cmp_vals=cmp_vals, cmp_vecs=cmp_vecs)
     allres = gather(result)
     ok = True
     if rank == 0:
@@ -80,6 +97,11 @@ def main():
         ref.normalize_hic(iterations=100, max_dev=1e-5, silent=True)
         ref.normalize_expected()
         n1, s1 = one.row_stats()
+        one.corr_build(c_beg, c_end, hic.bias.to_array(), c_mask, c_exp, stage=0)
+        one_oe = one.corr_get()
+        one.corr_build(c_beg, c_end, hic.bias.to_array(), c_mask, c_exp, stage=1)
+        one_corr = one.corr_get()
+        one_vals, one_vecs, _ = one.corr_eig(3)
         checks = {
             "blocks cover rows": [b["block"] for b in allres][0][0] == 0 and
                                  allres[-1]["block"][1] == wl["size"],
@@ -100,6 +122,11 @@ def main():
             "nccl path ranks identical": all(np.array_equal(b["nccl_bias"], allres[0]["nccl_bias"])
                                              for b in allres),
             "rows round trip (CSR form)": all(b["same_rows"] for b in allres),
+            "K1 one stream = two streams": all(np.array_equal(b["serial_bias"], b["bias"]) for b in allres),
+            "obs/exp = one GPU (bits)": all(np.array_equal(b["cmp_oe"], one_oe) for b in allres),
+            "correlation = one GPU (bits)": all(np.array_equal(b["cmp_corr"], one_corr) for b in allres),
+            "eigenpairs = one GPU (bits)": all(np.array_equal(b["cmp_vals"], one_vals) and
+                                               np.array_equal(b["cmp_vecs"], one_vecs) for b in allres),
         }
         print("exchange in use:", [b["exchange"] for b in allres])
         for k, v in checks.items():
