@@ -328,8 +328,9 @@ int tb_corr_set(tb_store *s, int64_t n, const double *h_in);
  * k >= n returns all n eigenpairs by descending value (scipy falls back to a dense solver there).
  * h_evals[k], h_evecs[k * n] (vector v at h_evecs + v * n, unit norm; the sign of an eigenvector
  * is arbitrary here as it is in ARPACK).  info[0] eigenpairs returned, [1] Lanczos vectors built,
- * [2] restarts after an invariant subspace, [3] converged.  TB_ERR_STATE if not converged. */
-int tb_corr_eig(tb_store *s, int32_t k, double *h_evals, double *h_evecs, int32_t info[4]);
+ * [2] restarts after an invariant subspace, [3] converged, [4] host round trips (the steps between
+ * two convergence tests are queued without one), [5..7] reserved.  TB_ERR_STATE if not converged. */
+int tb_corr_eig(tb_store *s, int32_t k, double *h_evals, double *h_evecs, int32_t info[8]);
 /* Device times of the last tb_corr_build / tb_corr_eig in ms: out[0] cell visitor, [1] centring,
  * [2] X X^T, [3] scaling, [4] eigen-solver; out[5] n, [6] stage resident, [7] 1 if corr_gemm=simple. */
 int tb_corr_timing(const tb_store *s, double out[8]);

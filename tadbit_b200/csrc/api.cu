@@ -607,7 +607,7 @@ int tb_corr_set(tb_store *s, int64_t n, const double *h_in) {
   });
 }
 
-int tb_corr_eig(tb_store *s, int32_t k, double *h_evals, double *h_evecs, int32_t info[4]) {
+int tb_corr_eig(tb_store *s, int32_t k, double *h_evals, double *h_evecs, int32_t info[8]) {
   return guarded([&]() -> int {
     TB_REQUIRE(s, "null argument");
     DeviceGuard g(s->device);

@@ -345,7 +345,7 @@ void corr_build(tb_store *s, int64_t beg, int64_t end, const double *h_bias, con
                 const double *h_expected, int stage, int64_t *n_good);
 void corr_get(tb_store *s, double *h_out);
 void corr_set(tb_store *s, int64_t n, const double *h_in);
-void corr_eig(tb_store *s, int32_t k, double *h_evals, double *h_evecs, int32_t info[4]);
+void corr_eig(tb_store *s, int32_t k, double *h_evals, double *h_evecs, int32_t info[8]);
 // comm.cu
 void comm_unique_id(uint8_t id[128]);
 void comm_init(tb_store *s, int rank, int world, const uint8_t id[128]);

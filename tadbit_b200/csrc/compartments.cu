@@ -316,6 +316,31 @@ __global__ void __launch_bounds__(1024) k_norm(const double *__restrict__ w, int
   if (threadIdx.x == 0) out[0] = sqrt(t);
 }
 
+// end of a Lanczos step, one CTA: beta = ||w||, alpha = the two Gram-Schmidt coefficients on the
+// current vector, and 1 / beta for the kernel that stores the next vector -- all without the host
+__global__ void __launch_bounds__(1024) k_step_scalars(const double *__restrict__ w, int64_t n,
+                                                       const double *__restrict__ h1, const double *__restrict__ h2,
+                                                       double *__restrict__ alpha, double *__restrict__ beta,
+                                                       double *__restrict__ inv) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc = fma(w[i], w[i], acc);
+  const double t = block_sum(acc, sh);
+  if (threadIdx.x == 0) {
+    const double b = sqrt(t);
+    *beta = b;
+    *alpha = *h1 + *h2;
+    *inv = b > 0.0 ? 1.0 / b : 0.0;
+  }
+}
+
+__global__ void k_scale_copy_dev(double *__restrict__ dst, const double *__restrict__ src,
+                                 const double *__restrict__ scale, int64_t n) {
+  const double f = *scale;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = src[i] * f;
+}
+
 __global__ void k_scale_copy(double *__restrict__ dst, const double *__restrict__ src, double scale, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] = src[i] * scale;
@@ -337,7 +362,7 @@ struct DeviceOps {
   const double *A;
   int64_t n, ld;
   int m_cap;
-  DevBuf<double> V, w, h, coef, vec;
+  DevBuf<double> V, w, h, h2, ab, coef, vec;   // ab: alpha[m_cap], beta[m_cap], 1 / beta, scratch norm
   PinnedBuf<double> hh;
   void init(tb_store *store, int cap) {
     s = store;
@@ -348,32 +373,51 @@ struct DeviceOps {
     V.alloc((size_t)m_cap * ld);
     w.alloc(ld);
     h.alloc(m_cap + 2);
-    hh.alloc(m_cap + 2);
+    h2.alloc(m_cap + 2);
+    ab.alloc(2 * (size_t)m_cap + 2);
+    hh.alloc(2 * (size_t)m_cap + 2);
     TB_CUDA(cudaMemsetAsync(V.p, 0, V.bytes(), s->stream));
     TB_CUDA(cudaMemsetAsync(w.p, 0, w.bytes(), s->stream));
   }
+  double *inv_d() { return ab.p + 2 * (size_t)m_cap; }
+  double *norm_d() { return ab.p + 2 * (size_t)m_cap + 1; }
   void random_w(uint64_t seed) {
     k_random_vec<<<grid_for(n, 256, s->sm_count), 256, 0, s->stream>>>(w.p, n, seed);
   }
   void matvec(int slot) {
     k_symv<<<grid_for(n * 32, 256, s->sm_count), 256, 0, s->stream>>>(A, ld, n, V.p + (int64_t)slot * ld, w.p);
   }
-  void project(int m, double *out) {
+  void project_into(int m, double *coeff) {
     if (m <= 0) return;
-    k_dots<<<m, 256, 0, s->stream>>>(V.p, ld, n, w.p, h.p);
-    k_subtract<<<grid_for(n, 128, s->sm_count), 128, 0, s->stream>>>(V.p, ld, n, m, h.p, w.p);
-    TB_CUDA(cudaMemcpyAsync(hh.p, h.p, m * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    TB_CUDA(cudaStreamSynchronize(s->stream));
-    for (int k = 0; k < m; ++k) out[k] = hh.p[k];
+    k_dots<<<m, 256, 0, s->stream>>>(V.p, ld, n, w.p, coeff);
+    k_subtract<<<grid_for(n, 128, s->sm_count), 128, 0, s->stream>>>(V.p, ld, n, m, coeff, w.p);
   }
+  void project(int m) { project_into(m, h.p); }
   double norm_w() {
-    k_norm<<<1, 1024, 0, s->stream>>>(w.p, n, h.p + m_cap + 1);
-    TB_CUDA(cudaMemcpyAsync(hh.p + m_cap + 1, h.p + m_cap + 1, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    k_norm<<<1, 1024, 0, s->stream>>>(w.p, n, norm_d());
+    TB_CUDA(cudaMemcpyAsync(hh.p, norm_d(), sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     TB_CUDA(cudaStreamSynchronize(s->stream));
-    return hh.p[m_cap + 1];
+    return hh.p[0];
   }
   void keep(int slot, double scale) {
     k_scale_copy<<<grid_for(n, 256, s->sm_count), 256, 0, s->stream>>>(V.p + (int64_t)slot * ld, w.p, scale, n);
+  }
+  void step(int j, bool store_next) {        // seven launches, no round trip
+    matvec(j);
+    project_into(j + 1, h.p);
+    project_into(j + 1, h2.p);               // second Gram-Schmidt pass ("twice is enough")
+    k_step_scalars<<<1, 1024, 0, s->stream>>>(w.p, n, h.p + j, h2.p + j, ab.p + j, ab.p + m_cap + j, inv_d());
+    if (store_next)
+      k_scale_copy_dev<<<grid_for(n, 256, s->sm_count), 256, 0, s->stream>>>(V.p + (int64_t)(j + 1) * ld, w.p,
+                                                                            inv_d(), n);
+  }
+  void read_ab(int j0, int j1, double *a, double *b) {
+    const size_t cnt = (size_t)(j1 - j0);
+    TB_CUDA(cudaMemcpyAsync(hh.p, ab.p + j0, cnt * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    TB_CUDA(cudaMemcpyAsync(hh.p + m_cap, ab.p + m_cap + j0, cnt * sizeof(double), cudaMemcpyDeviceToHost,
+                            s->stream));
+    TB_CUDA(cudaStreamSynchronize(s->stream));
+    for (size_t q = 0; q < cnt; ++q) { a[q] = hh.p[q]; b[q] = hh.p[m_cap + q]; }
   }
   void combine(int m, int k, const double *h_coef, double *h_out) {
     coef.alloc((size_t)k * m);
@@ -381,8 +425,8 @@ struct DeviceOps {
     TB_CUDA(cudaMemcpyAsync(coef.p, h_coef, coef.bytes(), cudaMemcpyHostToDevice, s->stream));
     k_combine<<<grid_for(n * k, 256, s->sm_count), 256, 0, s->stream>>>(V.p, ld, n, m, k, coef.p, vec.p);
     for (int v = 0; v < k; ++v) {              // unit norm, as ARPACK returns them
-      k_norm<<<1, 1024, 0, s->stream>>>(vec.p + (int64_t)v * n, n, h.p);
-      TB_CUDA(cudaMemcpyAsync(hh.p, h.p, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+      k_norm<<<1, 1024, 0, s->stream>>>(vec.p + (int64_t)v * n, n, norm_d());
+      TB_CUDA(cudaMemcpyAsync(hh.p, norm_d(), sizeof(double), cudaMemcpyDeviceToHost, s->stream));
       TB_CUDA(cudaStreamSynchronize(s->stream));
       const double nv = hh.p[0];
       if (nv > 0.0)
@@ -536,8 +580,9 @@ void corr_set(tb_store *s, int64_t n, const double *h_in) {
 
 // The k eigenpairs of largest magnitude of the resident matrix (k >= n: all of them), eigenvalues
 // descending; h_evecs[v * n + i].  info: [0] eigenpairs returned, [1] Lanczos vectors,
-// [2] restarts, [3] converged.
-void corr_eig(tb_store *s, int32_t k, double *h_evals, double *h_evecs, int32_t info[4]) {
+// [2] restarts, [3] converged, [4] host round trips (bursts of steps), [5..7] 0.
+void corr_eig(tb_store *s, int32_t k, double *h_evals, double *h_evecs, int32_t info[8]) {
+  for (int q = 0; q < 8; ++q) info[q] = 0;
   TB_REQUIRE(k >= 1 && h_evals && h_evecs && info, "corr_eig: bad arguments");
   TB_REQUIRE(s->dense.p && s->dense_n > 0, "corr_eig: no matrix resident (call tb_corr_build or tb_corr_set first)");
   const int64_t n = s->dense_n;
@@ -557,6 +602,7 @@ void corr_eig(tb_store *s, int32_t k, double *h_evals, double *h_evecs, int32_t 
   info[0] = (int32_t)r.evals.size();
   info[1] = r.steps;
   info[2] = r.restarts;
+  info[4] = r.round_trips;
   info[3] = r.converged ? 1 : 0;
   for (size_t i = 0; i < r.evals.size(); ++i) h_evals[i] = r.evals[i];
   if (!r.converged) {

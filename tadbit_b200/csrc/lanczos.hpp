@@ -10,12 +10,23 @@
 // break-down, restart, selection and ordering are tested without a GPU).
 //
 //   Ops:  void   random_w(uint64_t seed);            w = reproducible pseudo-random vector
-//         void   matvec(int slot);                   w = A * V[slot]
-//         void   project(int m, double *h);          h[k] = V[k] . w (k < m);  w -= sum_k h[k] V[k]
-//         double norm_w();                           ||w||
+//         void   project(int m);                     w -= sum_k (V[k] . w) V[k], k < m
+//         double norm_w();                           ||w||                              (synchronises)
 //         void   keep(int slot, double scale);       V[slot] = scale * w
+//         void   step(int j, bool store_next);       one Lanczos step WITHOUT a round trip to the host:
+//                                                    w = A V[j]; project(j + 1) twice; alpha[j] = the
+//                                                    two coefficients on V[j]; beta[j] = ||w||;
+//                                                    V[j + 1] = w / beta[j] if store_next
+//         void   read_ab(int j0, int j1, double *alpha, double *beta);
+//                                                    alpha[j], beta[j] of steps j0 <= j < j1   (synchronises)
 //         void   combine(int m, int k, const double *coef, double *out);
 //                                                    out[i] = normalised sum_j coef[i * m + j] V[j]   (host, k x n)
+//
+// The steps between two convergence tests are queued back to back and their scalars read in one go:
+// on a chromosome of a thousand bins a step is a few microseconds of kernels, and three round
+// trips per step (the first version) were 90 % of the solver's time.  A break-down inside such a
+// burst shows as a vanishing beta when the scalars arrive; the steps queued after it worked on
+// garbage and are dropped.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -87,6 +98,7 @@ struct LanczosResult {
   std::vector<double> evals;      // the selected eigenvalues, descending (algebraic)
   int steps = 0;                  // Lanczos vectors built
   int restarts = 0;               // invariant subspaces met (new start vector each time)
+  int round_trips = 0;            // bursts of steps = reads of the scalars
   bool converged = false;
   double residual = 0.0;          // largest residual estimate of the selected pairs, relative to max |theta|
 };
@@ -100,76 +112,77 @@ LanczosResult lanczos_largest(Ops &ops, int64_t n, int k, int m_cap, double tol,
   LanczosResult res;
   if (m_cap > n) m_cap = (int)n;
   if (k > m_cap) k = m_cap;
-  std::vector<double> alpha, beta;           // T: alpha[j] on the diagonal, beta[j] couples j and j + 1
-  std::vector<double> h((size_t)m_cap + 2), h2((size_t)m_cap + 2);
-  std::vector<double> d, e, z;
-  uint64_t seed = 0x7ad0b17b200ULL;
+  // T: alpha[j] on the diagonal; resid[j] = ||w|| after step j couples j and j + 1 unless the
+  // iteration was restarted there (cut[j])
+  std::vector<double> alpha, resid, d, e, z, a, b;
+  std::vector<char> cut;
+  const uint64_t seed = 0x7ad0b17b200ULL;
 
   ops.random_w(seed);
-  double nrm = ops.norm_w();
-  ops.keep(0, 1.0 / nrm);
-  double anorm = 0.0;                        // running estimate of ||A|| (largest |alpha| + |beta|)
+  ops.keep(0, 1.0 / ops.norm_w());
+  double anorm = 0.0;                        // running estimate of ||A||
   int next_check = (int)std::min<int64_t>(n, std::max(2 * k + 1, 8));
-  int m = 0;
-  bool exhausted = false;
-  for (int j = 0; j < m_cap; ++j) {
-    ops.matvec(j);
-    ops.project(j + 1, h.data());
-    ops.project(j + 1, h2.data());           // second Gram-Schmidt pass ("twice is enough")
-    const double a = h[j] + h2[j];
-    const double b = ops.norm_w();
-    alpha.push_back(a);
-    m = j + 1;
-    anorm = std::max(anorm, fabs(a) + b + (j ? beta[j - 1] : 0.0));
-    const bool breakdown = b <= 1e-13 * std::max(anorm, 1e-300);
-    const bool last = m == m_cap;
-    if (breakdown || last || m >= next_check) {
-      d = alpha;
-      e.assign(beta.begin(), beta.end());
-      e.resize(m, 0.0);
-      if (!tridiag_eig(m, d, e, z)) break;
-      // residual estimate of a Ritz pair: |b| * |last component of its eigenvector of T|
-      std::vector<int> idx(m);
-      for (int i = 0; i < m; ++i) idx[i] = i;
-      if (all_by_value) std::sort(idx.begin(), idx.end(), [&](int p, int q) { return d[p] > d[q]; });
-      else std::sort(idx.begin(), idx.end(), [&](int p, int q) { return fabs(d[p]) > fabs(d[q]); });
-      double tmax = 0.0;
-      for (int i = 0; i < m; ++i) tmax = std::max(tmax, fabs(d[i]));
-      double worst = 0.0;
-      const int kk = std::min(k, m);
-      for (int i = 0; i < kk; ++i)
-        worst = std::max(worst, (breakdown ? 0.0 : b) * fabs(z[(size_t)(m - 1) * m + idx[i]]));
-      res.residual = tmax > 0.0 ? worst / tmax : 0.0;
-      const bool ok = m >= k && worst <= tol * std::max(tmax, 1e-300);
-      if ((ok && !(breakdown && m < n && all_by_value)) || m == n || last) {
-        res.converged = ok || m == n;
-        break;
-      }
-      next_check = m + std::max(2, m / 6);
+  int m = 0;                                 // accepted steps = size of T
+  bool solved = false;
+  while (m < m_cap) {
+    const int stop = std::min(std::max(next_check, m + 1), m_cap);
+    for (int j = m; j < stop; ++j) ops.step(j, j + 1 < m_cap);
+    a.resize(stop - m);
+    b.resize(stop - m);
+    ops.read_ab(m, stop, a.data(), b.data());
+    ++res.round_trips;
+    bool breakdown = false;
+    for (int j = m; j < stop && !breakdown; ++j) {
+      alpha.push_back(a[j - m]);
+      resid.push_back(b[j - m]);
+      cut.push_back(0);
+      anorm = std::max(anorm, fabs(alpha[j]) + resid[j] + ((j && !cut[j - 1]) ? resid[j - 1] : 0.0));
+      breakdown = !(resid[j] > 1e-13 * std::max(anorm, 1e-300));      // also catches NaN
     }
+    m = (int)alpha.size();
+    const bool last = m == m_cap;
+    d = alpha;
+    e.assign(m, 0.0);
+    for (int j = 0; j + 1 < m; ++j) e[j] = cut[j] ? 0.0 : resid[j];
+    solved = tridiag_eig(m, d, e, z);
+    if (!solved) break;
+    // residual estimate of a Ritz pair: ||w|| * |last component of its eigenvector of T|
+    std::vector<int> idx(m);
+    for (int i = 0; i < m; ++i) idx[i] = i;
+    if (all_by_value) std::sort(idx.begin(), idx.end(), [&](int p, int q) { return d[p] > d[q]; });
+    else std::sort(idx.begin(), idx.end(), [&](int p, int q) { return fabs(d[p]) > fabs(d[q]); });
+    double tmax = 0.0, worst = 0.0;
+    for (int i = 0; i < m; ++i) tmax = std::max(tmax, fabs(d[i]));
+    const int kk = std::min(k, m);
+    for (int i = 0; i < kk; ++i)
+      worst = std::max(worst, (breakdown ? 0.0 : resid[m - 1]) * fabs(z[(size_t)(m - 1) * m + idx[i]]));
+    res.residual = tmax > 0.0 ? worst / tmax : 0.0;
+    const bool ok = m >= k && worst <= tol * std::max(tmax, 1e-300);
+    if (ok || m == n || last) {
+      res.converged = ok || m == n;
+      break;
+    }
+    next_check = m + std::max(2, m / 6);
     if (breakdown) {
       // the Krylov space is invariant: carry on from a fresh vector orthogonal to it
       ++res.restarts;
       ops.random_w(seed + (uint64_t)res.restarts);
-      ops.project(m, h.data());
-      ops.project(m, h2.data());
+      ops.project(m);
+      ops.project(m);
       const double nb = ops.norm_w();
-      if (!(nb > 1e-8)) { exhausted = true; break; }
+      if (!(nb > 1e-8)) {                      // nothing left outside the space: T is exact
+        res.converged = true;
+        break;
+      }
       ops.keep(m, 1.0 / nb);
-      beta.push_back(0.0);
-    } else {
-      ops.keep(m, 1.0 / b);
-      beta.push_back(b);
+      cut[m - 1] = 1;
     }
   }
   res.steps = m;
-  if (exhausted) {                           // nothing left outside the space: T is exact
-    d = alpha;
-    e.assign(beta.begin(), beta.end());
-    e.resize(m, 0.0);
-    res.converged = tridiag_eig(m, d, e, z);
+  if (!solved || m == 0) {
+    res.converged = false;
+    return res;
   }
-  if (d.size() != (size_t)m || m == 0) return res;
   // selection: largest magnitude (or all), then descending algebraic order
   std::vector<int> idx(m);
   for (int i = 0; i < m; ++i) idx[i] = i;

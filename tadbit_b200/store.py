@@ -385,12 +385,12 @@ class ContactStore(object):
         kk = max(min(int(k), n), 1)
         evals = np.zeros(kk, dtype=np.float64)
         evecs = np.zeros((kk, max(n, 1)), dtype=np.float64)
-        info = np.zeros(4, dtype=np.int32)
+        info = np.zeros(8, dtype=np.int32)
         check(lib().tb_corr_eig(self._h, int(k), ptr(evals, C.c_double), ptr(evecs, C.c_double),
                                 ptr(info, C.c_int32)))
         got = int(info[0])
         return evals[:got], evecs[:got, :n], dict(steps=int(info[1]), restarts=int(info[2]),
-                                                  converged=bool(info[3]))
+                                                  converged=bool(info[3]), round_trips=int(info[4]))
 
     def corr_timing(self):
         """Device ms of the last corr_build / corr_eig: cell visitor, centring, X X^T, scaling, eigen-solver."""

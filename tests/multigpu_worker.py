@@ -59,14 +59,17 @@ def main():
     store.set_option("k1_streams", "2")
     # N4: observed / expected and correlation matrix of the first chromosome from the row-sharded
     # store (every rank ends with the whole matrix), leading eigenpairs
+    import hashlib
     sec = list(wl["chromosomes"])[0]
     c_beg, c_end = hic.section_pos[sec]
+    c_end = min(c_end, c_beg + 3000)              # a 3000-bin stretch is enough (n x n doubles per rank)
+    digest = lambda arr: hashlib.sha1(np.ascontiguousarray(arr).tobytes()).hexdigest()   # noqa: E731
     c_mask = bad_mask(wl["size"], hic.bads)
     c_exp = np.array([hic.expected[d] or 1.0 for d in range(c_end - c_beg)])
     store.corr_build(c_beg, c_end, hic.bias.to_array(), c_mask, c_exp, stage=0)
-    cmp_oe = store.corr_get()
+    cmp_oe = digest(store.corr_get())
     store.corr_build(c_beg, c_end, hic.bias.to_array(), c_mask, c_exp, stage=1)
-    cmp_corr = store.corr_get()
+    cmp_corr = digest(store.corr_get())
     cmp_vals, cmp_vecs, _ = store.corr_eig(3)
     # pre-partitioned input: this rank's rows exported in CSR form and a second store built from them
     ptr, cc, vv = store.export_csr("full_rows")
@@ -98,9 +101,9 @@ def main():
         ref.normalize_expected()
         n1, s1 = one.row_stats()
         one.corr_build(c_beg, c_end, hic.bias.to_array(), c_mask, c_exp, stage=0)
-        one_oe = one.corr_get()
+        one_oe = digest(one.corr_get())
         one.corr_build(c_beg, c_end, hic.bias.to_array(), c_mask, c_exp, stage=1)
-        one_corr = one.corr_get()
+        one_corr = digest(one.corr_get())
         one_vals, one_vecs, _ = one.corr_eig(3)
         checks = {
             "blocks cover rows": [b["block"] for b in allres][0][0] == 0 and
@@ -123,8 +126,8 @@ def main():
                                              for b in allres),
             "rows round trip (CSR form)": all(b["same_rows"] for b in allres),
             "K1 one stream = two streams": all(np.array_equal(b["serial_bias"], b["bias"]) for b in allres),
-            "obs/exp = one GPU (bits)": all(np.array_equal(b["cmp_oe"], one_oe) for b in allres),
-            "correlation = one GPU (bits)": all(np.array_equal(b["cmp_corr"], one_corr) for b in allres),
+            "obs/exp = one GPU (bits)": all(b["cmp_oe"] == one_oe for b in allres),
+            "correlation = one GPU (bits)": all(b["cmp_corr"] == one_corr for b in allres),
             "eigenpairs = one GPU (bits)": all(np.array_equal(b["cmp_vals"], one_vals) and
                                                np.array_equal(b["cmp_vecs"], one_vecs) for b in allres),
         }

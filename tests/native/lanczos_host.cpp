@@ -36,7 +36,10 @@ struct HostOps {
       w[r] = acc;
     }
   }
-  void project(int m, double *h) {
+  std::vector<double> al, be;
+  void project(int m) { project_h(m, nullptr); }
+  double project_h(int m, double *last) {
+    std::vector<double> h(m);
     for (int k = 0; k < m; ++k) {
       double acc = 0.0;
       for (int64_t i = 0; i < n; ++i) acc += V[(size_t)k * n + i] * w[i];
@@ -44,6 +47,22 @@ struct HostOps {
     }
     for (int k = 0; k < m; ++k)
       for (int64_t i = 0; i < n; ++i) w[i] -= h[k] * V[(size_t)k * n + i];
+    if (last) *last = h[m - 1];
+    return 0.0;
+  }
+  void step(int j, bool store_next) {
+    matvec(j);
+    double h1 = 0.0, h2 = 0.0;
+    project_h(j + 1, &h1);
+    project_h(j + 1, &h2);
+    if ((int)al.size() <= j) { al.resize(j + 1); be.resize(j + 1); }
+    al[j] = h1 + h2;
+    be[j] = norm_w();
+    const double inv = be[j] > 0.0 ? 1.0 / be[j] : 0.0;
+    if (store_next) keep(j + 1, inv);
+  }
+  void read_ab(int j0, int j1, double *a, double *b) {
+    for (int j = j0; j < j1; ++j) { a[j - j0] = al[j]; b[j - j0] = be[j]; }
   }
   double norm_w() {
     double acc = 0.0;
@@ -87,5 +106,6 @@ extern "C" int lanczos_host(int64_t n, const double *A, int k, int m_cap, double
   info[1] = r.steps;
   info[2] = r.restarts;
   info[3] = r.converged ? 1 : 0;
+  info[4] = r.round_trips;
   return 0;
 }

@@ -35,7 +35,7 @@ def run(lib, a, k, m_cap=0, tol=1e-13):
     kk = min(k, n)
     evals = np.zeros(kk)
     evecs = np.zeros((kk, n))
-    info = np.zeros(4, dtype=np.int32)
+    info = np.zeros(5, dtype=np.int32)
     lib.lanczos_host(n, a.ctypes.data, k, m_cap, tol, evals.ctypes.data, evecs.ctypes.data,
                      info.ctypes.data)
     return evals[:info[0]], evecs[:info[0]], info
