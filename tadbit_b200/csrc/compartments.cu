@@ -590,7 +590,7 @@ void corr_eig(tb_store *s, int32_t k, double *h_evals, double *h_evecs, int32_t 
   if (all) k = (int32_t)n;
   Events<2> ev;
   TB_CUDA(cudaEventRecord(ev[0], s->stream));
-  int cap = (int)std::min<int64_t>(n, all ? n : std::max<int64_t>(20 * (int64_t)k, 600));
+  int cap = (int)std::min<int64_t>(n, all ? n : std::max<int64_t>(20 * (int64_t)k, 1000));
   DeviceOps ops;
   ops.init(s, cap);
   LanczosResult r = lanczos_largest(ops, n, k, cap, 1e-13, all, h_evecs);

@@ -465,6 +465,44 @@ class HiC_data(object):
                 out.write('\t'.join([str(i) for i in line]) + '\n')
         out.close()
 
+    def write_coord_table(self, fname, focus=None, diagonal=True,
+                          normalized=False, format='BED'):
+        """Coordinate table of the non-zero cells of a window, 'BED' or 'long-range' format
+        (hic_data.py:451-540), streamed from ``yield_matrix``.  As in the reference the values of a
+        row are consumed from its first column on while the partner names start after the row's own
+        bin (its iterator over the line is not advanced to the diagonal)."""
+        start1, end1, start2, end2 = self._focus_simple(focus)
+        if format not in ('long-range', 'BED'):
+            open(fname, 'w').close()                       # the reference has opened the file by then
+            raise Exception('ERROR: format "%s" not found\n' % format)
+        names = sorted(self.sections, key=lambda x: self.sections[x])
+        inside = [k for k in names if start2 <= self.sections[k] < end2]
+        span = [(k[0], k[1] * self.resolution, (k[1] + 1) * self.resolution) for k in inside]
+        colnam = ['%s:%d-%d' % t for t in span]
+        if format == 'long-range':
+            rownam = colnam
+            missing = 'ERROR: HiC data object should have genomic coordinates'
+            pair_string = '%s\t%s\t%f\n' if normalized else '%s\t%s\t%d\n'
+        else:
+            rownam = ['%s\t%d\t%d' % t for t in span]
+            missing = 'ERROR: Hi-C data object should have genomic coordinates'
+            pair_string = '%s\t%s,%f\t%d\t.\n' if normalized else '%s\t%s,%d\t%d\t.\n'
+        with open(fname, 'w') as out:
+            if not rownam:
+                raise Exception(missing)
+            iter_rows = self.yield_matrix(focus=focus, diagonal=diagonal, normalized=normalized)
+            count = 1
+            for nrow, row in enumerate(rownam, 1):
+                line = next(iter_rows)
+                for col, val in zip(colnam[nrow:], line):
+                    if not val:
+                        continue
+                    if format == 'long-range':
+                        out.write(pair_string % (row, col, val))
+                    else:
+                        out.write(pair_string % (row, col, val, count))
+                        count += 1
+
     # -- compartments (SURVEY.md 8f, N4) -------------------------------------------------------
     def find_compartments(self, crms=None, savefig=None, savedata=None, savecorr=None, show=False,
                           suffix='', ev_index=None, rich_in_A=None, format='png', savedir=None,

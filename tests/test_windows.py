@@ -104,3 +104,40 @@ def test_windows_through_the_kernel(tmp_path):
             k = (a >= r0) & (a < r1) & (b >= c0) & (b < c1)
             want[a[k] - r0, b[k] - c0] = v[k]
         assert np.array_equal(store.window(r0, r1, c0, c1), want)
+
+
+def test_coord_tables_against_the_live_reference(tmp_path):
+    """write_coord_table (hic_data.py:451-540) in both formats, raw and normalised, next to the
+    unmodified reference on the same matrix (skipped where the reference tree is absent)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    import tadbit_b200
+    from tadbit_b200.vectors import BinVector
+    ns = ref_shim.load()
+    rec, z, chroms = _load()
+    n = rec["size"]
+    dico = {}
+    for a, b, v in zip(z["rows"].tolist(), z["cols"].tolist(), z["vals"].tolist()):
+        dico[a * n + b] = v
+        dico[b * n + a] = v
+    ref = ns.HiC_data(dico, n, chromosomes=chroms, dict_sec=_sections(chroms), resolution=rec["resolution"])
+    store = NumpyStore(n, z["rows"], z["cols"], z["vals"], chromosomes=chroms)
+    ours = tadbit_b200.HiC_data.from_store(store, chromosomes=chroms, dict_sec=_sections(chroms),
+                                           resolution=rec["resolution"])
+    bads = dict((int(k), v) for k, v in rec["bads"].items())
+    ref.bads, ours.bads = dict(bads), dict(bads)
+    ref.bias = dict(enumerate(rec["bias"]))
+    ours.bias = BinVector(np.array(rec["bias"]))
+    for fmt in ("BED", "long-range"):
+        for kw in (dict(), dict(normalized=True), dict(focus="chrB", diagonal=False),
+                   dict(focus=(3, 40), normalized=True)):
+            fr, fo = str(tmp_path / "r.txt"), str(tmp_path / "o.txt")
+            ref.write_coord_table(fr, format=fmt, **kw)
+            ours.write_coord_table(fo, format=fmt, **kw)
+            assert open(fo).read() == open(fr).read(), (fmt, kw)
+    for hic in (ref, ours):
+        with pytest.raises(Exception, match="not found"):
+            hic.write_coord_table(str(tmp_path / "x.txt"), format="wig")
