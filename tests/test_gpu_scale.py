@@ -186,6 +186,70 @@ def test_full_size_c2_against_oracle():
         store.close()
 
 
+def test_full_size_c2_compartments_against_numpy_and_arpack():
+    """N4 at BASELINE configs[1] size: chr1 @10 kb, ~24 300 good bins.  Observed / expected rows
+    against the exported cells (same divisions: bit for bit), rows of the correlation matrix against
+    numpy on the host, and the eigenpairs against the reference's own call, scipy's
+    eigsh(matrix, k=3) (ARPACK), on the correlation matrix the device produced."""
+    from scipy.sparse.linalg import eigsh
+    from tadbit_b200._capi import bad_mask
+    wl, store, hic = _full_size_case("c2")
+    if _host_gb() < 48:
+        store.close()
+        pytest.skip("needs ~48 GB of free host memory")
+    try:
+        n = wl["size"]
+        hic.filter_columns(silent=True)
+        hic.normalize_hic(iterations=100, max_dev=1e-5, silent=True)
+        hic.normalize_expected()
+        bias = hic.bias.to_array()
+        mask = bad_mask(n, hic.bads)
+        exp_arr = np.array([hic.expected[d] or 1.0 for d in range(n)])
+        good = np.flatnonzero(mask == 0)
+        pos = np.full(n, -1, dtype=np.int64)
+        pos[good] = np.arange(good.size)
+        ng = store.corr_build(0, n, bias, mask, exp_arr, stage=0)
+        assert ng == good.size and ng > 24000
+        oe = store.corr_get()
+        assert np.array_equal(oe, oe.T)
+        r, c, v = store.export_upper()
+        rng = np.random.default_rng(5)
+        for i in rng.choice(good, size=12, replace=False).tolist():
+            want = np.zeros(ng)
+            for a, b in ((r, c), (c, r)):                  # row i of the full symmetric matrix
+                k = np.flatnonzero(a == i)
+                j = b[k].astype(np.int64)
+                keep = mask[j] == 0
+                j, vv = j[keep], v[k][keep].astype(np.float64)
+                lo, hi = np.minimum(i, j), np.maximum(i, j)
+                want[pos[j]] = vv / exp_arr[hi - lo] / bias[lo] / bias[hi]
+            assert np.array_equal(oe[pos[i]], want), i
+        store.corr_build(0, n, bias, mask, exp_arr, stage=1)
+        corr = store.corr_get()
+        assert np.array_equal(corr, corr.T) and np.abs(corr).max() <= 1.0
+        rows = np.sort(rng.choice(ng, size=256, replace=False))
+        oe -= oe.mean(axis=1, keepdims=True)              # numpy.cov, in place
+        sd = np.sqrt(np.einsum("ij,ij->i", oe, oe) / (ng - 1))
+        cov = oe[rows] @ oe.T / (ng - 1)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            want = np.clip(cov / sd[rows, None] / sd[None, :], -1, 1)
+        want = np.where(np.isnan(want), 0.0, want)
+        np.testing.assert_allclose(corr[rows], want, rtol=0, atol=1e-12)
+        del oe, cov, want
+        vals, vecs, info = store.corr_eig(3)
+        assert info["converged"]
+        w, z = eigsh(corr, k=3)                            # hic_data.py:926-930
+        np.testing.assert_allclose(vals, w[::-1], rtol=1e-10)
+        for i in range(3):
+            ref = z[:, -(i + 1)]
+            assert min(np.abs(vecs[i] - ref).max(), np.abs(vecs[i] + ref).max()) < 1e-8, i
+        t = store.corr_timing()
+        print("c2 compartments: n %d, X X^T %.1f ms, eigen %.1f ms, %d Lanczos vectors" % (
+            ng, t["gemm_ms"], t["eig_ms"], info["steps"]))
+    finally:
+        store.close()
+
+
 def test_full_size_c3_against_oracle():
     """BASELINE configs[2], the bench workload: genome-wide 5 kb, 1.97e9 stored contacts."""
     wl, store, hic = _full_size_case("c3")
