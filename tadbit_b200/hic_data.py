@@ -317,78 +317,56 @@ class HiC_data(object):
             return self.store.window(r0, r1, c0, c1, self._bias_array()).tolist()
         return np.rint(self.store.window(r0, r1, c0, c1)).astype(np.int64).tolist()
 
+    @staticmethod
+    def _numeric_focus(focus):
+        """(start, end) or (start1, end1, start2, end2), 1-based inclusive -> 0-based half-open."""
+        if len(focus) == 2:
+            return focus[0] - 1, focus[1], focus[0] - 1, focus[1]
+        beg1, end1, beg2, end2 = focus
+        return beg1 - 1, end1, beg2 - 1, end2
+
     def _focus_simple(self, focus):
-        """Window of write_matrix / yield_matrix (hic_data.py:590-610, :1532-1551)."""
-        if focus:
-            if isinstance(focus, tuple) and isinstance(focus[0], int):
-                if len(focus) == 2:
-                    start1, end1 = focus
-                    start2, end2 = focus
-                    start1 -= 1
-                    start2 -= 1
-                else:
-                    start1, end1, start2, end2 = focus
-                    start1 -= 1
-                    start2 -= 1
-            elif isinstance(focus, tuple) and isinstance(focus[0], str):
-                start1, end1 = self.section_pos[focus[0]]
-                start2, end2 = self.section_pos[focus[1]]
-            else:
-                start1, end1 = self.section_pos[focus]
-                start2, end2 = self.section_pos[focus]
-        else:
-            start1 = start2 = 0
-            end1 = end2 = len(self)
-        return start1, end1, start2, end2
+        """Window of write_matrix / yield_matrix / write_coord_table (hic_data.py:590-610, :1532-1551)
+        as (start1, end1, start2, end2): bin numbers, one chromosome name, or a pair of names."""
+        if not focus:
+            return 0, len(self), 0, len(self)
+        if isinstance(focus, tuple) and isinstance(focus[0], int):
+            return self._numeric_focus(focus)
+        first, second = focus if isinstance(focus, tuple) else (focus, focus)
+        return self.section_pos[first] + self.section_pos[second]
+
+    def _bp_range(self, spec):
+        """'chr3:10000-20000' -> bin offsets inside the chromosome (base pairs // resolution)."""
+        try:
+            beg, end = [int(p) // self.resolution for p in spec.split(':')[1].split('-')]
+        except ValueError:
+            raise Exception('ERROR: should be in format "chr3:10000:20000"')
+        return beg, end
 
     def _focus_coords(self, focus):
-        """hic_data.py:688-738 (chromosome names may carry a 'chr:beg-end' range in base pairs)."""
-        siz = len(self)
-        if focus:
-            if isinstance(focus, tuple) and isinstance(focus[0], int):
-                if len(focus) == 2:
-                    start1, end1 = focus
-                    start2, end2 = focus
-                    start1 -= 1
-                    start2 -= 1
-                else:
-                    start1, end1, start2, end2 = focus
-                    start1 -= 1
-                    start2 -= 1
-            elif isinstance(focus, tuple) and isinstance(focus[0], str):
-                start1, end1 = self.section_pos[focus[0].split(':')[0]]
-                start2, end2 = self.section_pos[focus[1].split(':')[0]]
-                if ':' in focus[0]:
-                    pos = focus[0].split(':')[1]
-                    try:
-                        pos1, pos2 = [int(p) // self.resolution
-                                      for p in pos.split('-')]
-                    except ValueError:
-                        raise Exception('ERROR: should be in format "chr3:10000:20000"')
-                    start1, end1 = start1 + pos1, start1 + pos2
-                if ':' in focus[1]:
-                    pos = focus[0].split(':')[1]
-                    try:
-                        pos1, pos2 = [int(p) // self.resolution
-                                      for p in pos.split('-')]
-                    except ValueError:
-                        raise Exception('ERROR: should be in format "chr3:10000:20000"')
-                    start2, end2 = start1 + pos1, start1 + pos2
-            else:
-                start1, end1 = self.section_pos[focus.split(':')[0]]
-                if ':' in focus:
-                    pos = focus.split(':')[1]
-                    try:
-                        pos1, pos2 = [int(p) // self.resolution
-                                      for p in pos.split('-')]
-                    except ValueError:
-                        raise Exception('ERROR: should be in format "chr3:10000:20000"')
-                    start1, end1 = start1 + pos1, start1 + pos2
-                start2, end2 = start1, end1
-        else:
-            start1 = start2 = 0
-            end1 = end2 = siz
-        return start1, start2, end1, end2
+        """Window of get_matrix (hic_data.py:688-738) as (start1, start2, end1, end2); chromosome
+        names may carry a range in base pairs.  As in the reference the range of the SECOND name of
+        a pair is read from the first name and offset from the first window."""
+        if not focus:
+            return 0, 0, len(self), len(self)
+        if isinstance(focus, tuple) and isinstance(focus[0], int):
+            beg1, end1, beg2, end2 = self._numeric_focus(focus)
+            return beg1, beg2, end1, end2
+        if isinstance(focus, tuple):
+            beg1, end1 = self.section_pos[focus[0].split(':')[0]]
+            beg2, end2 = self.section_pos[focus[1].split(':')[0]]
+            if ':' in focus[0]:
+                lo, hi = self._bp_range(focus[0])
+                beg1, end1 = beg1 + lo, beg1 + hi
+            if ':' in focus[1]:
+                lo, hi = self._bp_range(focus[0])
+                beg2, end2 = beg1 + lo, beg1 + hi
+            return beg1, beg2, end1, end2
+        beg1, end1 = self.section_pos[focus.split(':')[0]]
+        if ':' in focus:
+            lo, hi = self._bp_range(focus)
+            beg1, end1 = beg1 + lo, beg1 + hi
+        return beg1, beg1, end1, end1
 
     def get_matrix(self, focus=None, diagonal=True, normalized=False, masked=False):
         """A window of the matrix as a list of lists (hic_data.py:632-686).

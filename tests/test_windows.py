@@ -141,3 +141,38 @@ def test_coord_tables_against_the_live_reference(tmp_path):
     for hic in (ref, ours):
         with pytest.raises(Exception, match="not found"):
             hic.write_coord_table(str(tmp_path / "x.txt"), format="wig")
+
+
+def test_focus_forms_against_the_live_reference():
+    """Every focus form of get_matrix (hic_data.py:688-738), ranges in base pairs included, and the
+    reference's quirk for a pair of ranged names, next to the unmodified reference."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    import tadbit_b200
+    ns = ref_shim.load()
+    rec, z, chroms = _load()
+    n, reso = rec["size"], rec["resolution"]
+    dico = {}
+    for a, b, v in zip(z["rows"].tolist(), z["cols"].tolist(), z["vals"].tolist()):
+        dico[a * n + b] = v
+        dico[b * n + a] = v
+    ref = ns.HiC_data(dico, n, chromosomes=chroms, dict_sec=_sections(chroms), resolution=reso)
+    store = NumpyStore(n, z["rows"], z["cols"], z["vals"], chromosomes=chroms)
+    ours = tadbit_b200.HiC_data.from_store(store, chromosomes=chroms, dict_sec=_sections(chroms),
+                                           resolution=reso)
+    names = list(chroms)
+    a, b = names[0], names[1]
+    rng = "%d-%d" % (2 * reso, 9 * reso)
+    forms = [None, (3, 17), (2, 9, 20, 31), a, (a, b), "%s:%s" % (a, rng), ("%s:%s" % (a, rng), b),
+             ("%s:%s" % (a, rng), "%s:%s" % (b, rng))]
+    for focus in forms:
+        assert ours._focus_coords(focus) == ref._focus_coords(focus), focus
+        assert ours.get_matrix(focus=focus) == ref.get_matrix(focus=focus), focus
+    for hic in (ref, ours):
+        with pytest.raises(Exception, match="should be in format"):
+            hic.get_matrix(focus="%s:12" % a)
+        with pytest.raises(IndexError):
+            hic.get_matrix(focus=(a, "%s:%s" % (b, rng)))      # range of the 2nd name read from the 1st
