@@ -6,7 +6,8 @@ every result; export round trips, CSR-form constructors, batch vs loop).
 
 Covers: synthetic generator, COO build (sorted fast path and general sort), chunk plan,
 every stream encoding (dense D8/D16/D32 with overflow cells, S16/S32, sparse tiles),
-both row-sum modes, filter statistics, ICE, batch ICE, normalised sum, diagonal sums, export.
+both row-sum modes, filter statistics, ICE, batch ICE, normalised sum, diagonal sums, export,
+the compartment kernels (observed / expected visitor, both X X^T kernels, eigen-solver).
 Results are cross-checked between the two row-sum modes (no oracle: nothing here imports
 ``oracle/``)."""
 import os
@@ -36,6 +37,39 @@ def keep_csr(make):
             os.environ["TB_KEEP_CSR"] = old
 
 
+def compartments_check(hic, hic2, chroms):
+    """N4 on the first chromosome: the observed / expected visitor over the compact stream against
+    the one over the kept CSR (same bits), X X^T as tensor-core tiles against the plain kernel,
+    eigenpairs by their residuals."""
+    from tadbit_b200._capi import bad_mask
+    n = len(hic)
+    beg, end = hic.section_pos[list(chroms)[0]]
+    mask = bad_mask(n, hic.bads)
+    bias = hic.bias.to_array()
+    exp_arr = np.array([hic.expected.get(d, 1.0) or 1.0 for d in range(end - beg)])
+    mats = []
+    for h in (hic, hic2):
+        h.store.corr_build(beg, end, bias, mask, exp_arr, stage=0)
+        mats.append(h.store.corr_get())
+    assert np.array_equal(mats[0], mats[1], equal_nan=True) and np.array_equal(mats[0], mats[0].T, equal_nan=True)
+    if not np.all(np.isfinite(mats[0])) or mats[0].shape[0] < 8:
+        return
+    corr = {}
+    for gemm in ("dmma", "simple"):
+        hic.store.set_option("corr_gemm", gemm)
+        hic.store.corr_build(beg, end, bias, mask, exp_arr, stage=1)
+        corr[gemm] = hic.store.corr_get()
+    hic.store.set_option("corr_gemm", "dmma")
+    assert np.array_equal(corr["dmma"], corr["dmma"].T) and np.abs(corr["dmma"]).max() <= 1.0
+    assert np.allclose(corr["dmma"], corr["simple"], rtol=0, atol=1e-12)
+    vals, vecs, info = hic.store.corr_eig(3)
+    assert info["converged"] and len(vals) == 3
+    scale = max(abs(vals[0]), 1.0)
+    for lam, v in zip(vals, vecs):
+        assert np.linalg.norm(corr["dmma"] @ v - lam * v) <= 1e-10 * scale
+        assert abs(np.linalg.norm(v) - 1.0) < 1e-12
+
+
 def run_path(make, chroms, tag):
     """The pipeline on the store `make()` builds (CSR released when every value is positive: every
     kernel decodes the compact stream) and on its twin that kept the CSR; the two must agree --
@@ -57,6 +91,7 @@ def run_path(make, chroms, tag):
     for x, y in zip(store.export_csr("full_rows"), twin.export_csr("full_rows")):
         assert np.array_equal(x, y)
     assert hic.sum() == hic2.sum()
+    compartments_check(hic, hic2, chroms)
     twin.set_option("rowsum", "csr")
     hic2.normalize_hic(iterations=20, max_dev=1e-5, silent=True)
     twin.set_option("rowsum", "compact")
