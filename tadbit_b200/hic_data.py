@@ -271,6 +271,41 @@ class HiC_data(object):
             return self.store.norm_sum(arr, mask)
         return int(self.store.norm_sum(None, mask))
 
+    def cis_trans_ratio(self, normalized=False, exclude=None, diagonal=True, equals=None):
+        """Interactions inside chromosomes over all interactions between good bins
+        (hic_data.py:252-316).  One pass of the per-chromosome distance sums (``tb_decay_sums``): the
+        cells of a chromosome at distance d > 0 count twice (both triangles), the diagonal once.
+
+        :param False normalized: use count / bias[i] / bias[j]
+        :param None exclude: chromosomes to leave out
+        :param True diagonal: include the diagonal in the cis count
+        :param None equals: merging chromosomes by a user function is not supported here
+        """
+        from ._capi import bad_mask
+        if normalized and not self.bias:
+            raise Exception('ERROR: experiment not normalized yet')
+        if not self.chromosomes:
+            return float('nan')
+        if equals is not None:
+            raise NotImplementedError('cis_trans_ratio: merging chromosomes with `equals` is not '
+                                      'available on the GPU-resident store')
+        bads = set(self.bads.keys())
+        for c in (exclude or []):
+            bads.update(range(*self.section_pos[c]))
+        mask = bad_mask(self.__size, bads)
+        weights = self._bias_array() if normalized else np.ones(self.__size)
+        nrm, raw, _ = self.store.decay_sums(weights, mask)
+        intra = 0.0 if normalized else 0
+        for beg, end in self.section_pos.values():
+            per_distance = nrm[beg:end] if normalized else raw[beg:end]
+            if end > beg:
+                inside = 2 * per_distance[1:].sum() + (per_distance[0] if diagonal else 0)
+                intra += float(inside) if normalized else int(inside)
+        try:
+            return float(intra) / self.sum(bias=self.bias if normalized else None, bads=bads)
+        except ZeroDivisionError:
+            return 0.
+
     def normalize_expected(self, **kwargs):
         self.expected = expected(self, bads=self.bads, **kwargs)
 

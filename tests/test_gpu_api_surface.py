@@ -97,3 +97,30 @@ def test_float_matrices_are_refused_not_silently_truncated():
         tadbit_b200.HiC_data({0: 1.5, 1: 2.0, 2: 2.0, 3: 1.0}, 2)
     hic = tadbit_b200.HiC_data({0: 1.0, 1: 2.0, 2: 2.0, 3: 4.0}, 2)     # integral floats are counts
     assert hic[0, 1] == 2 and hic.sum() == 9
+
+
+def test_cis_trans_ratio_through_the_kernels():
+    """HiC_data.cis_trans_ratio (hic_data.py:252-316) from tb_decay_sums / tb_norm_sum against the same
+    host code around the oracle (tests/test_host_vs_reference.py pins that to the live reference)."""
+    import tadbit_b200
+    from _numpy_store import NumpyStore
+    case = load("synth_3chrom")
+    gpu = tadbit_b200.HiC_data.from_coo(case.size, case.rows, case.cols, case.vals, chromosomes=case.chromosomes)
+    cpu = tadbit_b200.HiC_data.from_store(NumpyStore(case.size, case.rows, case.cols, case.vals,
+                                                      chromosomes=case.chromosomes),
+                                          chromosomes=case.chromosomes)
+    first = list(case.chromosomes)[0]
+    for hic in (gpu, cpu):
+        hic.filter_columns(silent=True)
+    assert gpu.bads == cpu.bads
+    for kw in (dict(), dict(diagonal=False), dict(exclude=[first])):
+        assert gpu.cis_trans_ratio(**kw) == cpu.cis_trans_ratio(**kw), kw
+    for hic in (gpu, cpu):
+        hic.normalize_hic(iterations=20, max_dev=1e-5, silent=True)
+    for kw in (dict(normalized=True), dict(normalized=True, diagonal=False, exclude=[first])):
+        a, b = gpu.cis_trans_ratio(**kw), cpu.cis_trans_ratio(**kw)
+        assert abs(a - b) <= 1e-12 * abs(b), (kw, a, b)
+    plain = tadbit_b200.HiC_data.from_coo(case.size, case.rows, case.cols, case.vals)
+    assert np.isnan(plain.cis_trans_ratio())                  # no chromosomes: NaN, as the reference
+    with pytest.raises(NotImplementedError):
+        gpu.cis_trans_ratio(equals=lambda x, y: x[:3] == y[:3])

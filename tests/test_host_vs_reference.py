@@ -290,3 +290,35 @@ def test_failing_normalisation_prints_and_raises_like_the_reference(kind):
         outs.append((buf.getvalue(), str(exc.value)))
     assert outs[0] == outs[1]
     assert ("computing biases" in outs[0][0]) == (kind == "all_zero")
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_cis_trans_ratio_against_the_reference(seed):
+    """HiC_data.cis_trans_ratio (hic_data.py:252-316): raw (exact integers -> the same float),
+    normalised, without the diagonal, with an excluded chromosome."""
+    ns = ref_shim.load()
+    k = _random_case(21000 + seed)
+    if not k["sizes"]:
+        k["sizes"], k["names"] = [k["n"]], ["chrX"]
+    ref = _reference(ns, k)
+    ours = _product(k)
+    for hic in (ref, ours):
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            hic.filter_columns(silent=True, perc_zero=k["perc_zero"], by_mean=k["by_mean"])
+    assert ours.bads == ref.bads
+    assert ours.cis_trans_ratio() == ref.cis_trans_ratio()
+    assert ours.cis_trans_ratio(diagonal=False) == ref.cis_trans_ratio(diagonal=False)
+    if len(k["names"]) > 1:
+        assert ours.cis_trans_ratio(exclude=[k["names"][0]]) == ref.cis_trans_ratio(exclude=[k["names"][0]])
+    for hic in (ref, ours):
+        with pytest.raises(Exception, match="not normalized"):
+            hic.cis_trans_ratio(normalized=True)
+    try:
+        for hic in (ref, ours):
+            with contextlib.redirect_stdout(io.StringIO()):
+                hic.normalize_hic(iterations=10, max_dev=1e-4, silent=True)
+    except ZeroDivisionError:
+        return
+    for kw in (dict(normalized=True), dict(normalized=True, diagonal=False)):
+        a, b = ours.cis_trans_ratio(**kw), ref.cis_trans_ratio(**kw)
+        assert abs(a - b) <= 1e-12 * abs(b), (kw, a, b)
