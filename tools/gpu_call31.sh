@@ -1,5 +1,5 @@
 #!/bin/bash
-# tile kernel with a scheduler warp (TB_TILE_PREFETCH=1, default) vs the build without it: parity subset, K1 on C3 and on a 1/8 shard
+# tile kernel with a scheduler warp (an experimental -DTB_TILE_PREFETCH build that was measured here and then removed from the tree) vs the build without it: parity subset, K1 on C3 and on a 1/8 shard
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 O=gpurun_out
