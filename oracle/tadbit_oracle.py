@@ -10,6 +10,10 @@ behaviour of the reference (citations are ``path:line`` under the reference root
 * ``matrix_sum``            <- _pytadbit/hic_data.py:350-375
 * ``filter_columns``        <- _pytadbit/hic_data.py:318-348
 * ``normalize_hic``         <- _pytadbit/hic_data.py:380-413
+* ``pair_values`` / ``pair_zscores`` / ``decay_sums`` / ``rescale_and_decay`` (N1, N2)
+                            <- _pytadbit/experiment.py:737-799, tools/tadbit_normalize.py:963-1159
+* ``obs_exp_matrix`` / ``correlation_matrix`` / ``largest_eigenpairs`` / ``compartment_breaks`` (N4)
+                            <- _pytadbit/hic_data.py:845-947 (find_compartments)
 
 Parity is PINNED: ``oracle/gen_golden.py`` runs the unmodified reference (through
 ``oracle/ref_shim.py``) on the reference's own 12 chrT fixtures and on seeded
