@@ -177,6 +177,46 @@ def reference_rate(wl, nbins=1500):
         return {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
 
 
+def reference_compartments(wl, nbins=1000):
+    """N4 beside the GPU numbers: the UNMODIFIED reference's HiC_data.find_compartments (nested Python
+    lists, numpy.corrcoef, scipy eigsh) on the leading nbins x nbins block of the model as one
+    chromosome, single-threaded Python apart from numpy's BLAS.  None when the reference is absent."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import ref_shim
+        if not ref_shim.available():
+            return None
+        import contextlib
+        import io
+        import warnings
+        from collections import OrderedDict
+        orc = _oracle()
+        r, c, v = orc.synthetic_block(nbins, wl["params"], wl["chromosomes"])
+        with contextlib.redirect_stderr(io.StringIO()), contextlib.redirect_stdout(io.StringIO()), \
+                warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ns = ref_shim.load()
+            dico = {}
+            for a, b, x in zip(r.tolist(), c.tolist(), v.tolist()):
+                dico[a * nbins + b] = x
+                dico[b * nbins + a] = x
+            chroms = OrderedDict([("chr1", nbins)])
+            hic = ns.HiC_data(dico, nbins, chromosomes=chroms,
+                              dict_sec=dict((("chr1", p), p) for p in range(nbins)), resolution=10000)
+            hic.filter_columns(silent=True, by_mean=False)
+            hic.normalize_hic(iterations=10, max_dev=1e-4, silent=True)
+            hic.normalize_expected()
+            t0 = time.perf_counter()
+            hic.find_compartments()
+            dt = time.perf_counter() - t0
+        n = nbins - len(hic.bads)
+        return {"seconds": dt, "good_bins": n, "us_per_cell": dt / max(n * n, 1) * 1e6, "kind": "reference",
+                "sample": "unmodified pytadbit HiC_data.find_compartments on one chromosome of %d bins "
+                          "(leading block of the %s model)" % (nbins, wl["name"])}
+    except Exception as exc:                                      # noqa: BLE001
+        return {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
+
+
 def run_reference(args, rank, world):
     """CPU arm.  The reference's ICE is pure Python over a dict (1.6-2.0e6 contacts*it/s) and cannot
     hold the benchmarked matrix, so the line's value is the oracle port (C + OpenMP, all host
@@ -200,6 +240,7 @@ def run_reference(args, rank, world):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["description"], "sample": cb["sample"], "same_config": False},
             "cpu_baseline": cb, "reference_python": reference_rate(wl),
+            "reference_python_compartments": reference_compartments(wl),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
