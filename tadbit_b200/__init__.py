@@ -7,7 +7,7 @@ There is no CPU fallback.
 """
 from ._capi import B200Error, SynthParams, device_count
 from .batch import batch_store, ice_batch, normalize_hic_batch
-from .decay import rescale_and_decay
+from .decay import column_biases, rescale_and_decay
 from .experiment import Experiment
 from .hic_data import HiC_data, from_reference
 from .hic_filtering import filter_by_mean, filter_by_zero_count
@@ -18,4 +18,4 @@ from .vectors import BinVector
 __version__ = "0.1.0"
 __all__ = ["HiC_data", "from_reference", "ContactStore", "CommGroup", "SynthParams", "BinVector",
            "iterative", "expected", "filter_by_mean", "filter_by_zero_count",
-           "device_count", "B200Error", "normalize_hic_batch", "batch_store", "ice_batch", "Experiment", "rescale_and_decay"]
+           "device_count", "B200Error", "normalize_hic_batch", "batch_store", "ice_batch", "Experiment", "rescale_and_decay", "column_biases"]

@@ -102,6 +102,34 @@ def pool_decay(nrm, raw, ndiag, min_n):
     return dec
 
 
+def column_biases(hic_data, badcol, normalization='Vanilla'):
+    """The biases ``tadbit normalize`` starts from (tadbit_normalize.py:897-925), before
+    :func:`rescale_and_decay` rescales them: per bin the total number of interactions of its row
+    (``cisprc[k][1]`` of the CLI, here ``tb_row_stats``; 1.0 for a bin without any), NaN on bad
+    columns, then
+
+    * ``'Vanilla'``: total / mean * sqrt(mean) (mean over the columns that are not NaN),
+    * ``'SQRT'``: the same on the square roots of the totals,
+    * ``'ICE'``: ``normalize_hic(iterations=100, max_dev=0.000001)`` with ``badcol`` as mask.
+
+    Returns ``{bin: bias}`` (``'ICE'``: the ``bias`` mapping of the object, as the CLI copies it)."""
+    size = len(hic_data)
+    if normalization == 'ICE':
+        hic_data.bads = badcol
+        hic_data.normalize_hic(iterations=100, max_dev=0.000001)
+        return hic_data.bias
+    if normalization not in ('Vanilla', 'SQRT'):
+        raise NotImplementedError('ERROR: method %s not implemented' % normalization)
+    _, totals = hic_data.store.row_stats()
+    biases = np.where(totals > 0, totals.astype(np.float64), 1.0)
+    biases[bad_mask(size, badcol) != 0] = np.nan
+    if normalization == 'SQRT':
+        biases = biases ** 0.5
+    mean_col = np.nanmean(biases)
+    biases = biases / mean_col * mean_col ** 0.5
+    return dict((k, v) for k, v in enumerate(biases.tolist()))
+
+
 def rescale_and_decay(hic_data, biases, badcol, factor=1, normalize_only=False,
                       signal_to_noise=0.05):
     """-> ``(biases, decay, badcol, norm_cisprc)`` as the tail of the reference's ``read_bam``
@@ -141,4 +169,4 @@ def rescale_and_decay(hic_data, biases, badcol, factor=1, normalize_only=False,
     return biases, decay, badcol, norm_cisprc
 
 
-__all__ = ["rescale_and_decay", "diagonal_cell_counts", "pool_decay"]
+__all__ = ["rescale_and_decay", "column_biases", "diagonal_cell_counts", "pool_decay"]

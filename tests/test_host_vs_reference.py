@@ -322,3 +322,51 @@ def test_cis_trans_ratio_against_the_reference(seed):
     for kw in (dict(normalized=True), dict(normalized=True, diagonal=False)):
         a, b = ours.cis_trans_ratio(**kw), ref.cis_trans_ratio(**kw)
         assert abs(a - b) <= 1e-12 * abs(b), (kw, a, b)
+
+
+def _reference_cli_biases():
+    """Lines of _pytadbit/tools/tadbit_normalize.py from 'Rescaling sum of interactions per bins' to
+    the end of the SQRT branch, compiled UNMODIFIED as a function of the variables they read (the
+    module itself needs pysam / matplotlib).  The ICE branch (reads a BAM) is cut off."""
+    src = open(os.path.join(ref_shim.REFERENCE_ROOT, "_pytadbit", "tools", "tadbit_normalize.py")).read().splitlines()
+    first = next(i for i, l in enumerate(src) if "Rescaling sum of interactions per bins" in l)
+    ice0 = next(i for i, l in enumerate(src) if l.strip() == "if normalization == 'ICE':")
+    van0 = next(i for i, l in enumerate(src) if l.strip() == "elif normalization == 'Vanilla':")
+    one0 = next(i for i, l in enumerate(src) if l.strip() == "elif normalization == 'oneD':")
+    body = src[first:ice0] + [src[van0].replace("elif", "if", 1)] + src[van0 + 1:one0]
+    code = "def _biases(bins, badcol, cisprc, normalization):\n" + "\n".join(body) + "\n    return biases\n"
+    space = dict(printime=lambda msg: None, nanmean=np.nanmean)
+    exec(compile(code, "tadbit_normalize.py[%d:%d]" % (first + 1, one0), "exec"), space)
+    return space["_biases"]
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_cli_column_biases_against_the_reference_lines(seed):
+    """tadbit_b200.column_biases ('Vanilla', 'SQRT') next to the reference CLI's own lines
+    (tools/tadbit_normalize.py:896-925) fed with the same per-bin totals."""
+    import tadbit_b200
+    k = _random_case(31000 + seed)
+    ours = _product(k)
+    n = k["n"]
+    _, totals = ours.store.row_stats()
+    cisprc = dict((i, [0, int(t), 0, 0]) for i, t in enumerate(totals.tolist()) if t > 0)
+    rng = np.random.default_rng(seed)
+    badcol = dict((int(b), True) for b in rng.choice(n, size=max(1, n // 12), replace=False))
+    ref_fn = _reference_cli_biases()
+    for method in ("Vanilla", "SQRT"):
+        want = ref_fn(list(range(n)), dict(badcol), dict(cisprc), method)
+        got = tadbit_b200.column_biases(ours, dict(badcol), method)
+        assert sorted(got) == sorted(want) == list(range(n))
+        a = np.array([got[i] for i in range(n)])
+        b = np.array([want[i] for i in range(n)])
+        assert np.array_equal(np.isnan(a), np.isnan(b)) and set(np.flatnonzero(np.isnan(b)).tolist()) == set(badcol)
+        np.testing.assert_allclose(a[~np.isnan(a)], b[~np.isnan(b)], rtol=1e-14, atol=0)
+    with pytest.raises(NotImplementedError):
+        tadbit_b200.column_biases(ours, badcol, "oneD")
+    # 'ICE': the object's own normalize_hic(100, 1e-6) with badcol as the mask
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            bias = tadbit_b200.column_biases(ours, dict(badcol), "ICE")
+    except ZeroDivisionError:
+        return
+    assert ours.bads == badcol and bias is ours.bias and len(bias) == n
