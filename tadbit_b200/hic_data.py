@@ -478,6 +478,15 @@ class HiC_data(object):
                 out.write('\t'.join([str(i) for i in line]) + '\n')
         out.close()
 
+    def get_as_tuple(self):
+        """Every cell of the matrix, row after row, as one tuple of ints (hic_data.py:446-449)."""
+        out = []
+        step = max(1, (1 << 24) // max(self.__size, 1))
+        for lo in range(0, self.__size, step):
+            for line in self._window(lo, min(lo + step, self.__size), 0, self.__size, False):
+                out.extend(line)
+        return tuple(out)
+
     def write_coord_table(self, fname, focus=None, diagonal=True,
                           normalized=False, format='BED'):
         """Coordinate table of the non-zero cells of a window, 'BED' or 'long-range' format

@@ -171,6 +171,7 @@ def test_focus_forms_against_the_live_reference():
     for focus in forms:
         assert ours._focus_coords(focus) == ref._focus_coords(focus), focus
         assert ours.get_matrix(focus=focus) == ref.get_matrix(focus=focus), focus
+    assert ours.get_as_tuple() == ref.get_as_tuple()
     for hic in (ref, ours):
         with pytest.raises(Exception, match="should be in format"):
             hic.get_matrix(focus="%s:12" % a)
