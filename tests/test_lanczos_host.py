@@ -158,3 +158,28 @@ def test_tridiagonal_solver_exported_by_the_library():
         np.testing.assert_allclose(dd[order], np.linalg.eigvalsh(t), atol=1e-12 * max(1, np.abs(t).max()))
         np.testing.assert_allclose(t @ vecs, vecs * dd[None, :], atol=1e-11)
         np.testing.assert_allclose(vecs.T @ vecs, np.eye(n), atol=1e-11)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_spectra_with_clusters_and_signs(host_lib, seed):
+    """Matrices with a prescribed spectrum: a few leading eigenvalues (some negative, some only
+    1e-3 apart) over a bulk; the pairs returned must be the ones of largest magnitude, in
+    descending algebraic order, each with a small residual."""
+    rng = np.random.default_rng(900 + seed)
+    n = int(rng.integers(40, 260))
+    k = int(rng.integers(1, 6))
+    lead = rng.uniform(3.0, 9.0, size=6) * rng.choice([-1.0, 1.0], size=6, p=[0.3, 0.7])
+    if seed % 3 == 0:
+        lead[1] = lead[0] * (1 - 1e-3)                    # a tight pair at the top
+    bulk = rng.uniform(-1.0, 1.0, size=n - 6)
+    w = np.concatenate([lead, bulk])
+    q, _ = np.linalg.qr(rng.normal(size=(n, n)))
+    a = (q * w) @ q.T
+    a = (a + a.T) / 2
+    evals, evecs, info = run(host_lib, a, k)
+    assert info[3] == 1 and info[0] == k
+    want = np.sort(w[np.argsort(-np.abs(w))[:k]])[::-1]
+    np.testing.assert_allclose(evals, want, rtol=0, atol=1e-10)
+    for lam, v in zip(evals, evecs):
+        assert np.linalg.norm(a @ v - lam * v) < 1e-9
+    assert info[4] <= info[1]                             # fewer host round trips than Lanczos steps
