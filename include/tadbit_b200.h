@@ -301,6 +301,22 @@ int tb_decay_sums(tb_store *s, const double *h_bias, const uint8_t *h_bad, doubl
 int tb_window(tb_store *s, int64_t row_begin, int64_t row_end, int64_t col_begin, int64_t col_end,
               const double *h_bias, double *h_out);
 
+/* N3 (the extraction side) -- get_matrix / write_matrix of the BAM parser
+ * (_pytadbit/parsers/hic_bam_parser.py:755-872, :892-1242) with the store in the place of the BAM
+ * file: the stored cells of the full symmetric matrix inside rows [row_begin, row_end) x columns
+ * [col_begin, col_end), row-major; cells of a bin flagged in h_bad (NULL = none) are dropped, as
+ * `if i not in bads1 and j not in bads2` does (:860, :1205).  half != 0 keeps the cells whose offset
+ * inside the row range is <= their offset inside the column range (_read_half_bam_frag, :447-458,
+ * which write_matrix reads with).  Per cell: h_row / h_col global bin indices, h_raw the count,
+ * h_nrm = count / bias[i] / bias[j] (transform_value_norm, :828; h_bias[nbins] or NULL), h_dec =
+ * h_nrm / h_decay[first bin of the section + |i - j|] for a cell inside one section, NaN between
+ * sections (transform_value_decay, :830-833; h_decay[nbins] in the layout tb_decay_sums uses, or
+ * NULL).  Call with NULL arrays to learn *n.  A row-sharded store returns the cells of its rows. */
+int tb_region_cells(tb_store *s, int64_t row_begin, int64_t row_end, int64_t col_begin, int64_t col_end,
+                    const uint8_t *h_bad, const double *h_bias, const double *h_decay, int32_t half,
+                    int64_t *n, int32_t *h_row, int32_t *h_col, int32_t *h_raw, double *h_nrm,
+                    double *h_dec);
+
 /* ---- N4: compartments --------------------------------------------------------- */
 /* The numeric core of HiC_data.find_compartments (_pytadbit/hic_data.py:845-937), per section
  * (chromosome) [bin_begin, bin_end) of the genome, over the bins of the section that are not bad

@@ -12,6 +12,8 @@ behaviour of the reference (citations are ``path:line`` under the reference root
 * ``normalize_hic``         <- _pytadbit/hic_data.py:380-413
 * ``pair_values`` / ``pair_zscores`` / ``decay_sums`` / ``rescale_and_decay`` (N1, N2)
                             <- _pytadbit/experiment.py:737-799, tools/tadbit_normalize.py:963-1159
+* ``region_cells`` (N3, extraction side)
+                            <- _pytadbit/parsers/hic_bam_parser.py:755-872, :892-1242
 * ``obs_exp_matrix`` / ``correlation_matrix`` / ``largest_eigenpairs`` / ``compartment_breaks`` (N4)
                             <- _pytadbit/hic_data.py:845-947 (find_compartments)
 
@@ -693,6 +695,45 @@ def pair_zscores(m, bias=None, bads=None):
     logs = np.log10(v.astype(np.float64))
     mean_v, std_v = np.mean(logs), np.std(logs)
     return r, c, (logs - mean_v) / std_v, (v.size, float(v.min()), float(mean_v), float(std_v))
+
+
+# --------------------------------------------------------------------------
+# N3 (extraction side): get_matrix / write_matrix of the BAM parser with the matrix in the place of
+# the BAM file (_pytadbit/parsers/hic_bam_parser.py:755-872, :892-1242)
+# --------------------------------------------------------------------------
+def region_cells(m, r0, r1, c0, c1, bads=None, bias=None, decay=None, half=False):
+    """The stored cells (both triangles) inside rows [r0, r1) x columns [c0, c1), row-major, between
+    bins that are not bad (`if i not in bads1 and j not in bads2`, :860, :1205):
+    (rows, cols, raw, nrm | None, dec | None) with global bin indices,
+    nrm = v / bias[i] / bias[j] (transform_value_norm, :828) and
+    dec = nrm / decay[crm][|i - j|] (transform_value_decay, :830-833; ``decay`` = {crm: {dist: x}});
+    NaN where the cell lies between two chromosomes or the distance has no entry.
+    ``half``: what _read_half_bam_frag keeps (:447-458), offset in rows <= offset in columns."""
+    bad = _bad_mask(m.size, bads)
+    od = m.rows != m.cols
+    rr = np.concatenate([m.rows, m.cols[od]])
+    cc = np.concatenate([m.cols, m.rows[od]])
+    vv = np.concatenate([m.vals, m.vals[od]])
+    keep = (rr >= r0) & (rr < r1) & (cc >= c0) & (cc < c1) & ~bad[rr] & ~bad[cc] & (vv != 0)
+    if half:
+        keep &= (rr - r0) <= (cc - c0)
+    rr, cc, vv = rr[keep], cc[keep], vv[keep]
+    order = np.lexsort((cc, rr))
+    rr, cc, vv = rr[order], cc[order], vv[order]
+    nrm = dec = None
+    if bias is not None:
+        b = np.asarray(bias, dtype=np.float64)
+        nrm = vv.astype(np.float64) / b[rr] / b[cc]
+    if decay is not None:
+        dec = np.full(rr.size, np.nan)
+        for crm, (beg, end) in m.section_pos.items():
+            inside = (rr >= beg) & (rr < end) & (cc >= beg) & (cc < end)
+            table = decay.get(crm, {})
+            for k in np.flatnonzero(inside):
+                d = abs(int(rr[k]) - int(cc[k]))
+                if d in table:
+                    dec[k] = nrm[k] / table[d]
+    return rr, cc, vv, nrm, dec
 
 
 # --------------------------------------------------------------------------

@@ -9,6 +9,7 @@ from ._capi import B200Error, SynthParams, device_count
 from .batch import batch_store, ice_batch, normalize_hic_batch
 from .decay import column_biases, rescale_and_decay
 from .experiment import Experiment
+from . import extraction
 from .hic_data import HiC_data, from_reference
 from .hic_filtering import filter_by_mean, filter_by_zero_count
 from .normalize_hic import expected, iterative
@@ -18,4 +19,4 @@ from .vectors import BinVector
 __version__ = "0.1.0"
 __all__ = ["HiC_data", "from_reference", "ContactStore", "CommGroup", "SynthParams", "BinVector",
            "iterative", "expected", "filter_by_mean", "filter_by_zero_count",
-           "device_count", "B200Error", "normalize_hic_batch", "batch_store", "ice_batch", "Experiment", "rescale_and_decay", "column_biases"]
+           "device_count", "B200Error", "normalize_hic_batch", "batch_store", "ice_batch", "Experiment", "rescale_and_decay", "column_biases", "extraction"]

@@ -79,6 +79,8 @@ PROTOTYPES = {
     "tb_pair_values": ([_store, _f64p, _u8p, C.c_int32, C.c_double, C.c_double, _i64p, _i32p, _i32p,
                         _f64p], C.c_int),
     "tb_window": ([_store, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _f64p, _f64p], C.c_int),
+    "tb_region_cells": ([_store, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _u8p, _f64p, _f64p, C.c_int32,
+                         _i64p, _i32p, _i32p, _i32p, _f64p, _f64p], C.c_int),
     "tb_decay_sums": ([_store, _f64p, _u8p, _f64p, _i64p, _f64p], C.c_int),
     "tb_corr_build": ([_store, C.c_int64, C.c_int64, _f64p, _u8p, _f64p, C.c_int32, _i64p], C.c_int),
     "tb_corr_get": ([_store, _f64p], C.c_int),

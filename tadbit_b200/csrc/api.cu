@@ -579,6 +579,18 @@ int tb_window(tb_store *s, int64_t row_begin, int64_t row_end, int64_t col_begin
   });
 }
 
+int tb_region_cells(tb_store *s, int64_t row_begin, int64_t row_end, int64_t col_begin, int64_t col_end,
+                    const uint8_t *h_bad, const double *h_bias, const double *h_decay, int32_t half, int64_t *n,
+                    int32_t *h_row, int32_t *h_col, int32_t *h_raw, double *h_nrm, double *h_dec) {
+  return guarded([&]() -> int {
+    TB_REQUIRE(s && n, "null argument");
+    DeviceGuard g(s->device);
+    region_cells(s, row_begin, row_end, col_begin, col_end, h_bad, h_bias, h_decay, half, n, h_row, h_col,
+                 h_raw, h_nrm, h_dec);
+    return TB_OK;
+  });
+}
+
 int tb_corr_build(tb_store *s, int64_t bin_begin, int64_t bin_end, const double *h_bias, const uint8_t *h_bad,
                   const double *h_expected, int32_t stage, int64_t *n_good) {
   return guarded([&]() -> int {

@@ -231,6 +231,75 @@ struct WindowVisitor {
   __device__ void end(uint8_t *) {}
 };
 
+// N3 (extraction side): the stored cells inside rows [r0, r1) x columns [c0, c1) of the full
+// symmetric matrix between bins that are not bad (get_matrix / write_matrix of
+// _pytadbit/parsers/hic_bam_parser.py:755-872, :892-1242: `if i not in bads1 and j not in bads2`).
+// half: only the cells whose position inside the row range is not behind their position inside
+// the column range (what _read_half_bam_frag keeps, :447-458: `if pos1 > pos2: continue` on the
+// region-local indices).
+struct RegionVisitorBase {
+  static constexpr int kShared = 0;
+  static constexpr int kThreads = 256;
+  int64_t r0, r1, c0, c1, rb;
+  bool half;
+  const uint8_t *skip;
+  __device__ void begin(uint8_t *) {}
+  __device__ bool block(int64_t i0, int64_t i1, int64_t j0, int64_t j1) {
+    return i0 < r1 && i1 > r0 && j0 < c1 && j1 > c0;
+  }
+  __device__ bool row(int64_t i) { return i >= r0 && i < r1 && !skip[i]; }
+  __device__ bool wanted(int64_t i, int64_t j, int32_t v) const {
+    if (j < c0 || j >= c1 || v == 0 || skip[j]) return false;
+    return !half || (i - r0) <= (j - c0);
+  }
+  __device__ void end(uint8_t *) {}
+};
+
+struct RegionCountVisitor : RegionVisitorBase {
+  unsigned long long *cnt;            // [nrows]
+  __device__ void cell(int64_t i, int64_t j, int32_t v) {
+    if (wanted(i, j, v)) atomicAdd(&cnt[i - rb], 1ull);
+  }
+};
+
+struct RegionPlaceVisitor : RegionVisitorBase {
+  const int64_t *off;
+  unsigned long long *cursor;
+  uint64_t *key;
+  int32_t *raw;
+  __device__ void cell(int64_t i, int64_t j, int32_t v) {
+    if (!wanted(i, j, v)) return;
+    const int64_t r = i - rb;
+    const int64_t pos = off[r] + (int64_t)atomicAdd(&cursor[r], 1ull);
+    key[pos] = ((uint64_t)r << 32) | (uint32_t)j;
+    raw[pos] = v;
+  }
+};
+
+// sorted keys -> (row, column) and the transformed values: transform_value_norm / _decay of
+// hic_bam_parser.py:828-833 (v / bias1[a] / bias2[b] / decay[c][|a - b|], the same order of
+// divisions; between two sections there is no decay: NaN)
+__global__ void k_unpack_region(const uint64_t *__restrict__ key, const int32_t *__restrict__ raw, int64_t n,
+                                int64_t rb, const double *__restrict__ bias, const double *__restrict__ decay,
+                                const int32_t *__restrict__ chrom_of, const int64_t *__restrict__ chrom_beg,
+                                int32_t *__restrict__ orow, int32_t *__restrict__ ocol,
+                                double *__restrict__ onrm, double *__restrict__ odec) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t e = key[k];
+    const int64_t i = rb + (int64_t)(e >> 32), j = (int64_t)(e & 0xffffffffu);
+    orow[k] = (int32_t)i;
+    ocol[k] = (int32_t)j;
+    if (!bias) continue;
+    const double x = (double)raw[k] / bias[i] / bias[j];
+    onrm[k] = x;
+    if (!decay) continue;
+    const int32_t c = chrom_of[i];
+    const int64_t d = i < j ? j - i : i - j;
+    odec[k] = chrom_of[j] == c ? x / decay[chrom_beg[c] + d] : nan("");
+  }
+}
+
 struct Weights {
   DevBuf<double> w;
   DevBuf<uint8_t> skip;
@@ -453,6 +522,96 @@ void window(tb_store *s, int64_t r0, int64_t r1, int64_t c0, int64_t c1, const d
   vis.out = out.p;
   visit_upper(s, vis, true);            // whole rows: the window may lie below the diagonal
   TB_CUDA(cudaMemcpyAsync(h_out, out.p, out.bytes(), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+}
+
+// The stored cells of rows [r0, r1) x columns [c0, c1) of the full symmetric matrix, row-major, bad bins
+// dropped: global (row, column), count, count / bias_i / bias_j (h_bias given) and that over
+// h_decay[first bin of the section + |i - j|] (h_decay given; NaN between sections).  Call with null
+// arrays to get *n.  A row-sharded store returns the cells of its own rows.
+void region_cells(tb_store *s, int64_t r0, int64_t r1, int64_t c0, int64_t c1, const uint8_t *h_bad,
+                  const double *h_bias, const double *h_decay, int half, int64_t *n, int32_t *h_row,
+                  int32_t *h_col, int32_t *h_raw, double *h_nrm, double *h_dec) {
+  cudaStream_t st = s->stream;
+  const int64_t N = s->nbins, nrows = s->nrows;
+  TB_REQUIRE(r0 >= 0 && r0 <= r1 && r1 <= N && c0 >= 0 && c0 <= c1 && c1 <= N && n, "region_cells: bad arguments");
+  TB_REQUIRE(!h_decay || h_bias, "region_cells: the decay needs the biases");
+  *n = 0;
+  if (r0 == r1 || c0 == c1 || nrows == 0) return;
+  if (h_bad) TB_CUDA(cudaMemcpyAsync(s->bad.p, h_bad, N, cudaMemcpyHostToDevice, st));
+  else TB_CUDA(cudaMemsetAsync(s->bad.p, 0, N, st));
+  DevBuf<unsigned long long> cnt;
+  DevBuf<int64_t> off;
+  cnt.alloc(nrows + 1);
+  off.alloc(nrows + 1);
+  TB_CUDA(cudaMemsetAsync(cnt.p, 0, cnt.bytes(), st));
+  RegionCountVisitor cv;
+  cv.r0 = r0; cv.r1 = r1; cv.c0 = c0; cv.c1 = c1; cv.rb = s->row_begin;
+  cv.half = half != 0;
+  cv.skip = s->bad.p;
+  cv.cnt = cnt.p;
+  visit_upper(s, cv, true);             // whole rows: the region may lie below the diagonal
+  {
+    size_t tmp_bytes = 0;
+    TB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, reinterpret_cast<const int64_t *>(cnt.p), off.p,
+                                          nrows + 1, st));
+    DevBuf<uint8_t> tmp;
+    tmp.alloc(tmp_bytes ? tmp_bytes : 1);
+    TB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, reinterpret_cast<const int64_t *>(cnt.p), off.p,
+                                          nrows + 1, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+  }
+  int64_t m = 0;
+  TB_CUDA(cudaMemcpy(&m, off.p + nrows, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  *n = m;
+  if (!h_row || m == 0) return;
+  TB_REQUIRE(h_col && h_raw && (!h_bias || h_nrm) && (!h_decay || h_dec), "region_cells: null output buffer");
+  DevBuf<uint64_t> key_in, key_out;
+  DevBuf<int32_t> raw_in, raw_out, orow, ocol;
+  DevBuf<double> bias, decay, onrm, odec;
+  DevBuf<int64_t> beg;
+  key_in.alloc(m); key_out.alloc(m); raw_in.alloc(m); raw_out.alloc(m); orow.alloc(m); ocol.alloc(m);
+  TB_CUDA(cudaMemsetAsync(cnt.p, 0, cnt.bytes(), st));
+  RegionPlaceVisitor pv;
+  pv.r0 = r0; pv.r1 = r1; pv.c0 = c0; pv.c1 = c1; pv.rb = s->row_begin;
+  pv.half = half != 0;
+  pv.skip = s->bad.p;
+  pv.off = off.p;
+  pv.cursor = cnt.p;
+  pv.key = key_in.p;
+  pv.raw = raw_in.p;
+  visit_upper(s, pv, true);
+  int row_bits = 1;
+  while (((int64_t)1 << row_bits) < nrows) ++row_bits;
+  size_t tmp_bytes = 0;
+  TB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_in.p, key_out.p, raw_in.p, raw_out.p, m, 0,
+                                          32 + row_bits, st));
+  DevBuf<uint8_t> tmp;
+  tmp.alloc(tmp_bytes ? tmp_bytes : 1);
+  TB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key_in.p, key_out.p, raw_in.p, raw_out.p, m, 0,
+                                          32 + row_bits, st));
+  if (h_bias) {
+    bias.alloc(N);
+    onrm.alloc(m);
+    TB_CUDA(cudaMemcpyAsync(bias.p, h_bias, N * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  if (h_decay) {
+    decay.alloc(N);
+    odec.alloc(m);
+    const size_t nsec = s->chrom_offsets.size() - 1;
+    beg.alloc(nsec);
+    TB_CUDA(cudaMemcpyAsync(decay.p, h_decay, N * sizeof(double), cudaMemcpyHostToDevice, st));
+    TB_CUDA(cudaMemcpyAsync(beg.p, s->chrom_offsets.data(), nsec * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  }
+  k_unpack_region<<<grid_1d(m, 256, s->sm_count), 256, 0, st>>>(key_out.p, raw_out.p, m, s->row_begin, bias.p,
+                                                               decay.p, s->chrom_of.p, beg.p, orow.p, ocol.p,
+                                                               onrm.p, odec.p);
+  TB_CUDA(cudaGetLastError());
+  TB_CUDA(cudaMemcpyAsync(h_row, orow.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaMemcpyAsync(h_col, ocol.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaMemcpyAsync(h_raw, raw_out.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (h_bias) TB_CUDA(cudaMemcpyAsync(h_nrm, onrm.p, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (h_decay) TB_CUDA(cudaMemcpyAsync(h_dec, odec.p, m * sizeof(double), cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaStreamSynchronize(st));
 }
 

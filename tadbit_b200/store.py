@@ -334,6 +334,32 @@ class ContactStore(object):
             check(lib().tb_window(self._h, int(r0), int(r1), int(c0), int(c1), bp, ptr(out, C.c_double)))
         return out
 
+    def region_cells(self, r0, r1, c0, c1, bad=None, bias=None, decay=None, half=False):
+        """The stored cells inside rows [r0, r1) x columns [c0, c1) of the full symmetric matrix between
+        good bins, row-major: (rows, cols, raw int32, normalised float64 | None, over-decay float64 |
+        None).  ``decay``: float64[N] indexed by first bin of the section + distance (the layout of
+        ``decay_sums``); cells between two sections get NaN.  ``half`` keeps the cells whose offset in
+        the row range is <= their offset in the column range."""
+        m, mp = self._mask(bad)
+        b, bp = self._bias(bias)
+        d, dp = self._bias(decay)
+        if d is not None and b is None:
+            raise ValueError("the decay needs the biases")
+        n = C.c_int64()
+        args = (self._h, int(r0), int(r1), int(c0), int(c1), mp, bp, dp, int(bool(half)), C.byref(n))
+        check(lib().tb_region_cells(*(args + (None, None, None, None, None))))
+        r = np.empty(n.value, dtype=np.int32)
+        c = np.empty(n.value, dtype=np.int32)
+        v = np.empty(n.value, dtype=np.int32)
+        nrm = np.empty(n.value, dtype=np.float64) if b is not None else None
+        dec = np.empty(n.value, dtype=np.float64) if d is not None else None
+        if n.value:
+            check(lib().tb_region_cells(*(args + (
+                ptr(r, C.c_int32), ptr(c, C.c_int32), ptr(v, C.c_int32),
+                ptr(nrm, C.c_double) if nrm is not None else None,
+                ptr(dec, C.c_double) if dec is not None else None))))
+        return r, c, v, nrm, dec
+
     def decay_sums(self, bias, bad=None):
         """Per section and distance: (normalised sums float64[N], raw sums int64[N]) indexed by
         first bin of the section + distance, and (cis, total) normalised off-diagonal sums."""

@@ -79,6 +79,14 @@ class NumpyStore(object):
     def corr_timing(self):                                 # tb_corr_timing
         return {}
 
+    def region_cells(self, r0, r1, c0, c1, bad=None, bias=None, decay=None, half=False):  # tb_region_cells
+        table = None
+        if decay is not None:
+            table = dict((crm, dict((d, float(decay[beg + d])) for d in range(end - beg)))
+                         for crm, (beg, end) in self.m.section_pos.items())
+        r, c, v, nrm, dec = orc.region_cells(self.m, r0, r1, c0, c1, self._bads(bad), bias, table, half)
+        return r.astype(np.int32), c.astype(np.int32), v.astype(np.int32), nrm, dec
+
     def decay_sums(self, bias, bad=None):                  # tb_decay_sums
         return orc.decay_sums(self.m, bias, self._bads(bad))
 

@@ -7,6 +7,7 @@ every result; export round trips, CSR-form constructors, batch vs loop).
 Covers: synthetic generator, COO build (sorted fast path and general sort), chunk plan,
 every stream encoding (dense D8/D16/D32 with overflow cells, S16/S32, sparse tiles),
 both row-sum modes, filter statistics, ICE, batch ICE, normalised sum, diagonal sums, export,
+region extraction (tb_region_cells against tb_window),
 the compartment kernels (observed / expected visitor, both X X^T kernels, eigen-solver).
 Results are cross-checked between the two row-sum modes (no oracle: nothing here imports
 ``oracle/``)."""
@@ -70,6 +71,33 @@ def compartments_check(hic, hic2, chroms):
         assert abs(np.linalg.norm(v) - 1.0) < 1e-12
 
 
+def region_cells_check(hic, hic2):
+    """N3, extraction side: tb_region_cells over the compact stream against the one over the kept
+    CSR (same cells, same bits), against the dense window of tb_window, half vs full."""
+    from tadbit_b200._capi import bad_mask
+    n = len(hic)
+    mask = bad_mask(n, hic.bads)
+    bias = hic.bias.to_array()
+    decay = 1.0 + np.arange(n, dtype=np.float64) % 97
+    for (r0, r1, c0, c1) in ((0, n, 0, n), (n // 3, n // 2, 0, n // 4), (10, 700, 300, 1200), (n - 300, n, n - 300, n)):
+        for half in (False, True):
+            a = hic.store.region_cells(r0, r1, c0, c1, bad=mask, bias=bias, decay=decay, half=half)
+            b = hic2.store.region_cells(r0, r1, c0, c1, bad=mask, bias=bias, decay=decay, half=half)
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y, equal_nan=True)
+            key = a[0].astype(np.int64) * n + a[1]
+            assert np.all(np.diff(key) > 0) and not mask[a[0]].any() and not mask[a[1]].any()
+            if half:
+                assert np.all(a[0] - r0 <= a[1] - c0)
+        if (r1 - r0) * (c1 - c0) <= 1 << 22:
+            dense = hic.store.window(r0, r1, c0, c1, bias=bias)
+            keep = ~mask[r0:r1, None].astype(bool) & ~mask[None, c0:c1].astype(bool)
+            rr, cc, _, nrm, _ = hic.store.region_cells(r0, r1, c0, c1, bad=mask, bias=bias)
+            got = np.zeros_like(dense)
+            got[rr - r0, cc - c0] = nrm
+            assert np.array_equal(got, np.where(keep, dense, 0.0))
+
+
 def run_path(make, chroms, tag):
     """The pipeline on the store `make()` builds (CSR released when every value is positive: every
     kernel decodes the compact stream) and on its twin that kept the CSR; the two must agree --
@@ -91,6 +119,7 @@ def run_path(make, chroms, tag):
     for x, y in zip(store.export_csr("full_rows"), twin.export_csr("full_rows")):
         assert np.array_equal(x, y)
     assert hic.sum() == hic2.sum()
+    region_cells_check(hic, hic2)
     compartments_check(hic, hic2, chroms)
     twin.set_option("rowsum", "csr")
     hic2.normalize_hic(iterations=20, max_dev=1e-5, silent=True)
