@@ -317,6 +317,15 @@ int tb_region_cells(tb_store *s, int64_t row_begin, int64_t row_end, int64_t col
                     int64_t *n, int32_t *h_row, int32_t *h_col, int32_t *h_raw, double *h_nrm,
                     double *h_dec);
 
+/* Host-only helper of the same path (no GPU involved): appends n cell lines of an .abc file,
+ * "a<TAB>b<TAB><TAB>value<NL>" -- what the write_raw / write_bias / write_expc closures of
+ * write_matrix print per cell (_pytadbit/parsers/hic_bam_parser.py:1101-1125,
+ * '{}\t{}\n'.format('{}\t{}\t'.format(a, b), value)).  value = h_int[k] when h_int is given, else
+ * h_val[k] written as Python's repr(float) writes it (shortest digits that read back as the same
+ * double; fixed notation for 1e-4 <= |x| < 1e16, d.ddde+XX outside; nan, inf, -inf). */
+int tb_write_abc_lines(const char *path, int64_t n, const int32_t *h_a, const int32_t *h_b,
+                       const int32_t *h_int, const double *h_val);
+
 /* ---- N4: compartments --------------------------------------------------------- */
 /* The numeric core of HiC_data.find_compartments (_pytadbit/hic_data.py:845-937), per section
  * (chromosome) [bin_begin, bin_end) of the genome, over the bins of the section that are not bad

@@ -340,6 +340,8 @@ void pair_values(tb_store *s, const double *h_bias, const uint8_t *h_bad, int zs
 void decay_sums(tb_store *s, const double *h_bias, const uint8_t *h_bad, double *h_nrm, int64_t *h_raw,
                 double out[2]);
 void window(tb_store *s, int64_t r0, int64_t r1, int64_t c0, int64_t c1, const double *h_bias, double *h_out);
+void write_abc_lines(const char *path, int64_t n, const int32_t *a, const int32_t *b, const int32_t *ival,
+                     const double *fval);
 void region_cells(tb_store *s, int64_t r0, int64_t r1, int64_t c0, int64_t c1, const uint8_t *h_bad,
                   const double *h_bias, const double *h_decay, int half, int64_t *n, int32_t *h_row,
                   int32_t *h_col, int32_t *h_raw, double *h_nrm, double *h_dec);

@@ -255,6 +255,24 @@ def get_matrix(hic_data, resolution, biases=None,
     return dico
 
 
+def _write_lines(path, a, b, values):
+    """``a <tab> b <tab> <tab> value`` per cell, appended to ``path`` by tb_write_abc_lines (integers
+    as they are, floats as ``repr`` writes them)."""
+    import ctypes as C
+    from . import _capi
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    b = np.ascontiguousarray(b, dtype=np.int32)
+    ints = vals = None
+    if values.dtype.kind in 'iu':
+        values = np.ascontiguousarray(values, dtype=np.int32)
+        ints = _capi.ptr(values, C.c_int32)
+    else:
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        vals = _capi.ptr(values, C.c_double)
+    _capi.check(_capi.lib().tb_write_abc_lines(os.fsencode(path), a.size, _capi.ptr(a, C.c_int32),
+                                               _capi.ptr(b, C.c_int32), ints, vals))
+
+
 def write_matrix(hic_data, resolution, biases, outdir,
                  filter_exclude=(1, 2, 3, 4, 6, 7, 8, 9, 10),
                  normalizations=('decay',),
@@ -357,34 +375,37 @@ def write_matrix(hic_data, resolution, biases, outdir,
     if 'raw&decay' in normalizations:
         fnames['RAW&DEC'] = files['DEC'][0]
 
-    a, b = cells.a.tolist(), cells.b.tolist()
-    if row_names:
-        if a:                                                # section_pos2 stays empty without region2
-            missing = [k for k in range(len(a)) if a[k] not in section_pos1 or b[k] not in section_pos2]
-            if missing:
-                k = missing[0]
-                raise KeyError(a[k] if a[k] not in section_pos1 else b[k])
-        names = ['{}\t{}\t{}\t{}\t'.format(*(section_pos1[i] + section_pos2[j])) for i, j in zip(a, b)]
-    else:
-        names = ['%d\t%d\t' % (i, j) for i, j in zip(a, b)]
-    raw = cells.raw.tolist()
+    # per file the value columns its writers print, in the reference's writer order
     if 'raw' in normalizations:
-        files['RAW'][1].append(['%s\t%d\n' % (n, v) for n, v in zip(names, raw)])
+        files['RAW'][1].append(cells.raw)
     if want_norm:
-        files['NRM'][1].append(['%s\t%r\n' % (n, v) for n, v in zip(names, cells.nrm.tolist())])
+        files['NRM'][1].append(cells.nrm)
     if want_decay:
         if len(regions) in [1, 2]:                           # write_expc / write_expc_2reg: no guard
             cells.check_decay()
-            files['DEC'][1].append(['%s\t%r\n' % (n, v) for n, v in zip(names, cells.dec.tolist())])
-        else:                                                # write_expc_err: 'nan' where there is no decay
-            files['DEC'][1].append(['%s\t%r\n' % (n, v) for n, v in zip(names, cells.dec.tolist())])
+        files['DEC'][1].append(cells.dec)                    # write_expc_err: 'nan' where there is no decay
     if 'raw&decay' in normalizations:
         # the reference's format string has two fields for three values: the raw count is written
-        files['DEC'][1].append(['%s\t%d\n' % (n, v) for n, v in zip(names, raw)])
+        files['DEC'][1].append(cells.raw)
+    names = None
+    if row_names:
+        a, b = cells.a.tolist(), cells.b.tolist()
+        for i, j in zip(a, b):                               # section_pos2 stays empty without region2
+            if i not in section_pos1:
+                raise KeyError(i)
+            if j not in section_pos2:
+                raise KeyError(j)
+        names = ['{}\t{}\t{}\t{}\t'.format(*(section_pos1[i] + section_pos2[j])) for i, j in zip(a, b)]
     for path, columns in files.values():
+        if names is None and len(columns) == 1:              # the usual case: formatted by the library
+            _write_lines(path, cells.a, cells.b, columns[0])
+            continue
+        if names is None:
+            names = ['%d\t%d\t' % (i, j) for i, j in zip(cells.a.tolist(), cells.b.tolist())]
+        text = [['%s\t%r\n' % (n, v) for n, v in zip(names, col.tolist())] for col in columns]
         with open(path, 'a') as out:
-            if len(columns) == 1:
-                out.write(''.join(columns[0]))
+            if len(text) == 1:
+                out.write(''.join(text[0]))
             else:                                            # decay and raw&decay share a file, cell by cell
-                out.write(''.join(''.join(lines) for lines in zip(*columns)))
+                out.write(''.join(''.join(lines) for lines in zip(*text)))
     return fnames
