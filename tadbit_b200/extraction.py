@@ -81,6 +81,18 @@ def get_biases_region(biases, bin_coords, check_resolution=None):
     return bias1, bias2, decay, bads1, bads2
 
 
+def cooler_weights_region(biases, bin_coords):
+    """The row and column weights write_matrix(cooler=True, normalizations=('norm',)) hands to the
+    cooler writer (hic_bam_parser.py:1228-1232): ``1 / bias`` where the bias is a positive number,
+    else 0, bins counted from the start of each region."""
+    bias1, bias2, _, _, _ = get_biases_region(biases, bin_coords)
+
+    def weights(bias):
+        return [1. / bias[b] if not bias[b] != bias[b] and bias[b] > 0 else 0 for b in range(len(bias))]
+
+    return weights(bias1), weights(bias2)
+
+
 class _Region(object):
     """What read_bam (hic_bam_parser.py:496-686) derives from the region arguments."""
 

@@ -454,6 +454,35 @@ class HiC_data(object):
                     line[i - start1] = 0.0 if normalized else 0
                 yield line
 
+    def cooler_weights(self):
+        """The ``weight`` column of the bins table that ``write_cooler(normalized=True)`` stores
+        (_pytadbit/hic_data.py:572-574): ``1 / bias`` for a good bin with a positive bias, else 0
+        (cooler multiplies by the weights where TADbit divides by the biases)."""
+        bias = self._bias_array()
+        good = np.ones(len(self), dtype=bool)
+        if self.bads:
+            good[[int(k) for k in self.bads]] = False
+        with np.errstate(divide='ignore', invalid='ignore'):
+            return np.where(good & (bias > 0), 1. / bias, 0.)
+
+    def write_cooler(self, fname, normalized=False):
+        """
+        writes the hic_data to a cooler file (_pytadbit/hic_data.py:543-576).  The HDF5 container
+        needs h5py, as in the reference (same message without it); writing it is not part of this
+        package: the values it would hold are ``items()`` (upper triangle) and
+        :meth:`cooler_weights`.
+
+        :param False normalized: get normalized data
+        """
+        try:
+            import h5py  # noqa: F401
+        except ImportError:
+            raise Exception('ERROR: cooler output is not available. Probably ' +
+                            'you need to install h5py\n')
+        if normalized and not self.bias:
+            raise Exception('ERROR: data not normalized yet')
+        raise NotImplementedError('cooler container output')
+
     def write_matrix(self, fname, focus=None, diagonal=True, normalized=False):
         """hic_data.py:578-630."""
         start1, end1, start2, end2 = self._focus_simple(focus)

@@ -207,6 +207,9 @@ def test_biases_pickle_path_and_default_lengths(tmp_path):
     assert head == ["# CRM chrB\t240000", "# chrB resolution:10000", "# MASKED "]
     assert [nicer(x) for x in (0, 999, 1000, 25000, 1000000, 2500000, 3000000000)] == \
         ["0 b", "999 b", "1 kb", "25 kb", "1 Mb", "2500 kb", "3 Gb"]
+    from tadbit_b200.extraction import cooler_weights_region
+    odd = dict(biases={0: 2.0, 1: float("nan"), 2: 0.0, 3: -1.0, 4: 0.5, 5: 4.0}, badcol={}, resolution=1)
+    assert cooler_weights_region(odd, (0, 4, 2, 6)) == ([0.5, 0, 0, 0], [0, 0, 2.0, 0.25])   # :1228-1231
     with pytest.raises(ValueError):
         get_matrix(hic, 5000)
     with pytest.raises(NotImplementedError):

@@ -177,3 +177,24 @@ def test_focus_forms_against_the_live_reference():
             hic.get_matrix(focus="%s:12" % a)
         with pytest.raises(IndexError):
             hic.get_matrix(focus=(a, "%s:%s" % (b, rng)))      # range of the 2nd name read from the 1st
+
+
+def test_cooler_weights_and_the_missing_h5py_message():
+    """write_cooler's weight column (_pytadbit/hic_data.py:572-574: 1 / bias on good bins with a
+    positive bias, else 0) and the reference's error when h5py is absent (:549-551)."""
+    import tadbit_b200
+    from tadbit_b200.vectors import BinVector
+    rec, z, chroms = _load()
+    store = NumpyStore(rec["size"], z["rows"], z["cols"], z["vals"], chromosomes=chroms)
+    hic = tadbit_b200.HiC_data.from_store(store, chromosomes=chroms, resolution=rec["resolution"])
+    hic.bads = dict((int(k), v) for k, v in rec["bads"].items())
+    bias = np.array(rec["bias"])
+    bias[3], bias[4] = 0.0, -1.0
+    hic.bias = BinVector(bias)
+    want = [1. / hic.bias[i] if i not in hic.bads and hic.bias[i] > 0 else 0. for i in range(len(hic))]
+    assert hic.cooler_weights().tolist() == want and want[3] == 0. and want[4] == 0.
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(Exception, match="cooler output is not available"):
+            hic.write_cooler("x.mcool", normalized=True)
