@@ -226,7 +226,7 @@ def get_matrix(hic_data, resolution, biases=None,
                region1=None, start1=None, end1=None,
                region2=None, start2=None, end2=None, dico=None, clean=False,
                return_headers=False, tmpdir='.', normalization='raw', ncpus=8,
-               nchunks=100, verbose=False, max_size=None, chr_order=None):
+               nchunks=100, verbose=False, max_size=None, chr_order=None, as_arrays=False):
     """
     The matrix at the intersection of two regions as a dictionary, with the wanted normalisation
     applied (hic_bam_parser.py:755-872).
@@ -242,6 +242,8 @@ def get_matrix(hic_data, resolution, biases=None,
        returning a dictionary
     :param False return_headers: also return bads1, bads2, regions, name, bin_coords
     :param None max_size: largest number of cells accepted
+    :param False as_arrays: (not in the reference) return ``(bin1, bin2, values)`` arrays, row-major,
+       instead of building the dictionary -- which costs more than extracting the cells
 
     :returns: dictionary ``{(bin1, bin2): value}``, bins counted from the start of each region
     """
@@ -260,7 +262,10 @@ def get_matrix(hic_data, resolution, biases=None,
             dico[i, j] = v
         return None
     values = {'raw': cells.raw, 'norm': cells.nrm, 'decay': cells.dec}[normalization]
-    dico = dict(zip(zip(a, b), values.tolist()))
+    if as_arrays:
+        dico = (cells.a, cells.b, values)
+    else:
+        dico = dict(zip(zip(a, b), values.tolist()))
     if return_headers:
         name = _generate_name(reg.regions, (start1, start2), (end1, end2), resolution, chr_order)
         return dico, cells.bads1, cells.bads2, reg.regions, name, reg.bin_coords

@@ -120,6 +120,11 @@ def _check_get(rec, z, make_store):
         np.testing.assert_allclose([g[2] for g in got], [w[2] for w in want], rtol=1e-15, atol=0)
         if item["normalization"] == "raw":
             assert all(isinstance(g[2], int) for g in got)
+    arr = get_matrix(hics["fake.bam"], rec["resolution"], biases=_biases(rec, "full"), normalization="norm",
+                     region1="chrB", as_arrays=True)
+    dic = get_matrix(hics["fake.bam"], rec["resolution"], biases=_biases(rec, "full"), normalization="norm",
+                     region1="chrB")
+    assert dict(zip(zip(arr[0].tolist(), arr[1].tolist()), arr[2].tolist())) == dic
     # a dict-like to fill instead of a dictionary to return
     filled = {}
     assert get_matrix(hics["fake.bam"], rec["resolution"], region1="chrB", dico=filled) is None

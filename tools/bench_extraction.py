@@ -96,6 +96,11 @@ def main():
                                   end1=(w1 - beg) * reso, normalization="decay")
         out["runs"].append({"what": "get_matrix decay, %d-bin window (dictionary)" % (w1 - w0),
                             "s": time.perf_counter() - t0, "cells": len(d)})
+        t0 = time.perf_counter()
+        arr = extraction.get_matrix(hic, reso, biases=biases, region1=first, start1=(w0 - beg) * reso,
+                                    end1=(w1 - beg) * reso, normalization="decay", as_arrays=True)
+        out["runs"].append({"what": "get_matrix decay, %d-bin window (arrays)" % (w1 - w0),
+                            "s": time.perf_counter() - t0, "cells": int(arr[0].size)})
     print(json.dumps(out))
 
 
