@@ -332,6 +332,48 @@ def parity_block(args, rank, local, world, gather, dist):
     return out
 
 
+def extraction_leg(hic, store, wl, window=2000):
+    """N3, extraction side, once: the cells of a `window`-bin square on the diagonal of the largest
+    chromosome (tb_region_cells with the norm and decay transforms) and the three .abc files of
+    extraction.write_matrix for it (wall clock of the API calls)."""
+    import tempfile
+    from tadbit_b200 import extraction
+    from tadbit_b200._capi import bad_mask
+    n = len(hic)
+    reso = hic.resolution
+    sec = max(wl["chromosomes"], key=lambda c: wl["chromosomes"][c])
+    beg, end = hic.section_pos[sec]
+    w0 = beg + (end - beg) // 3
+    w1 = min(w0 + window, end)
+    bias = hic.bias.to_array()
+    decay = np.ones(n)
+    table = {}
+    for crm, (b0, b1) in hic.section_pos.items():
+        vals = [hic.expected.get(d, 1.0) or 1.0 for d in range(b1 - b0)]
+        decay[b0:b1] = vals
+        table[crm] = dict(enumerate(vals))
+    t0 = time.perf_counter()
+    cells = store.region_cells(w0, w1, w0, w1, bad=bad_mask(n, hic.bads), bias=bias, decay=decay)
+    t_cells = time.perf_counter() - t0
+    biases = dict(biases=hic.bias.to_dict(), badcol=dict((int(k), v) for k, v in hic.bads.items()),
+                  decay=table, resolution=reso)
+    with tempfile.TemporaryDirectory() as tmp:
+        t0 = time.perf_counter()
+        fnames = extraction.write_matrix(hic, reso, biases, tmp, normalizations=("raw", "norm", "decay"),
+                                         region1=sec, start1=(w0 - beg) * reso, end1=(w1 - beg) * reso,
+                                         verbose=False)
+        t_write = time.perf_counter() - t0
+        nbytes = sum(os.path.getsize(f) for f in fnames.values())
+        nlines = sum(1 for _ in open(fnames["RAW"]))
+    return {"section": sec, "window_bins": w1 - w0, "cells_full": int(cells[0].size),
+            "region_cells_ms": t_cells * 1e3, "cells_per_s": cells[0].size / t_cells if t_cells else None,
+            "write_matrix_ms": t_write * 1e3, "files": len(fnames), "lines_per_file": nlines, "bytes": nbytes,
+            "what": "tb_region_cells (count, scan, place, radix sort, v / b_i / b_j / decay on the device) and "
+                    "the raw_ / nrm_ / dec_ .abc files of the window (half matrix), lines formatted by "
+                    "tb_write_abc_lines; the unmodified reference spends 3.96 us per cell on the same three "
+                    "files after its BAM file is read (profiles/r02_n3_reference_cost_per_cell.json)"}
+
+
 def e2e_leg(args, wl, store, rank, local, world, dist, mask):
     """Same metric through the public API with HOST buffers, every rank at once: pinned CSR-form
     cells (N = 1: the upper triangle of the matrix, 8 B per cell; N > 1: the rows each rank owns,
@@ -585,6 +627,12 @@ def main():
                           "eigenvalues": [float(x) for x in evals]}}
         except Exception as exc:                           # never lose the headline over the extra
             pipeline_rec["n4_compartments"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
+    if world == 1 and not args.no_compartments:
+        try:
+            pipeline_rec["n3_extraction"] = extraction_leg(hic, store, wl)
+        except Exception as exc:                           # never lose the headline over the extra
+            pipeline_rec["n3_extraction"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,

@@ -279,3 +279,21 @@ def test_region_cells_against_the_oracle_on_a_larger_matrix(keep_csr):
     got = store.region_cells(0, n, 0, n)
     assert got[3] is None and got[4] is None and got[2].sum() == 2 * v.sum() - v[r == c].sum()
     store.close()
+
+
+def test_bench_extraction_leg_on_the_store_double():
+    """bench.py's N3 leg (pipeline.n3_extraction of the JSON line) driven on the CPU."""
+    import os as _os
+    import sys as _sys
+    import tadbit_b200
+    _sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+    import bench
+    rec, z = _load()
+    hic = _hic(rec, z, "fake.bam", _numpy_store)
+    hic.filter_columns(silent=True)
+    hic.normalize_hic(iterations=10, max_dev=1e-4, silent=True)
+    hic.normalize_expected()
+    wl = dict(chromosomes=_chroms(rec, "fake.bam"))
+    out = bench.extraction_leg(hic, hic.store, wl, window=12)
+    assert out["section"] == "chrA" and out["window_bins"] == 12 and out["files"] == 3
+    assert out["cells_full"] > 0 and out["lines_per_file"] > 3 and out["bytes"] > 0
