@@ -22,6 +22,11 @@ Differences, all in what a BAM file is and a matrix is not:
   ``# CRM`` header lines) defaults to ``(bins - 1) * resolution``;
 * a file that the reference leaves half written when it raises in the middle holds only its header
   here.
+* a row range that runs past the end of ``region1``'s chromosome holds nothing there.  (The
+  reference agrees unless ``region2`` is also given: its list of row bins is then built over both
+  regions with ``region1``'s offsets, hic_bam_parser.py:604-616, and reads of ``region2``'s
+  chromosome that fall into the overrun come back as extra rows numbered after the range -- an
+  accident that is not reproduced.)
 """
 import os
 from collections import OrderedDict
@@ -96,7 +101,8 @@ def cooler_weights_region(biases, bin_coords):
 class _Region(object):
     """What read_bam (hic_bam_parser.py:496-686) derives from the region arguments."""
 
-    def __init__(self, hic, resolution, region1, start1, end1, region2, start2, end2, max_size, chr_order):
+    def __init__(self, hic, resolution, region1, start1, end1, region2, start2, end2, max_size, chr_order,
+                 nchunks=100):
         if hic.chromosomes:
             self.sections = OrderedDict((c, int(n)) for c, n in hic.chromosomes.items())
         else:
@@ -128,6 +134,12 @@ class _Region(object):
             end_bin1 = section_pos[region1][0] + end1 // resolution
         else:
             end_bin1 = section_pos[region1][1] if region1 else total
+        # the reference cuts [start_bin1, end_bin1) into chunks and looks their first bins up in the
+        # list of all bins: an empty range, or one that runs past the end of the genome, dies there
+        span = end_bin1 - start_bin1
+        step = span // (min(span, nchunks) + 1) + 1
+        if span <= 0 or start_bin1 + (span - 1) // step * step >= total:
+            raise IndexError('list index out of range')
         for crm in self.regions:                              # the reference indexes both before it checks
             section_pos[crm]
         if region2:
@@ -154,7 +166,7 @@ class _Region(object):
 class _Cells(object):
     """The cells of a region and the vectors the transforms need."""
 
-    def __init__(self, hic, reg, biases, want_norm, want_decay, half):
+    def __init__(self, hic, reg, biases, want_norm, want_decay, half, touch_bias=False):
         size = len(hic)
         start_bin1, _, start_bin2, _ = reg.bin_coords
         self.bads1 = self.bads2 = {}
@@ -168,7 +180,7 @@ class _Cells(object):
                 if bads:
                     idx = np.fromiter(bads.keys(), dtype=np.int64, count=len(bads)) + beg
                     bad[idx[idx < size]] = 1
-            if want_norm or want_decay:
+            if want_norm or want_decay or touch_bias:
                 bias = np.full(size, np.nan)
                 have = np.zeros(size, dtype=bool)
                 for table, beg in ((self.bias1, start_bin1), (self.bias2, start_bin2)):
@@ -189,7 +201,8 @@ class _Cells(object):
                         ok = (d >= 0) & (d < end - beg)
                         decay[beg + d[ok]], self.have_decay[beg + d[ok]] = val[ok], True
         self.rows, self.cols, self.raw, self.nrm, self.dec = hic.store.region_cells(
-            reg.rows[0], reg.rows[1], reg.cols[0], reg.cols[1], bad=bad, bias=bias, decay=decay, half=half)
+            reg.rows[0], reg.rows[1], reg.cols[0], reg.cols[1], bad=bad,
+            bias=bias if (want_norm or want_decay) else None, decay=decay, half=half)
         # region-local indices, as the reference's bins_dict1 / bins_dict2 give them
         self.a = self.rows.astype(np.int64) - start_bin1
         self.b = self.cols.astype(np.int64) - start_bin2
@@ -247,7 +260,8 @@ def get_matrix(hic_data, resolution, biases=None,
 
     :returns: dictionary ``{(bin1, bin2): value}``, bins counted from the start of each region
     """
-    reg = _Region(hic_data, resolution, region1, start1, end1, region2, start2, end2, max_size, chr_order)
+    reg = _Region(hic_data, resolution, region1, start1, end1, region2, start2, end2, max_size, chr_order,
+                  nchunks)
     if not biases and normalization != 'raw':
         raise Exception('ERROR: should provide path to file with biases (pickle).')
     if normalization not in ('raw', 'norm', 'decay'):
@@ -325,7 +339,8 @@ def write_matrix(hic_data, resolution, biases, outdir,
         normalizations = tuple([normalizations])
     if append_to_tar:
         raise NotImplementedError('append_to_tar')
-    reg = _Region(hic_data, resolution, region1, start1, end1, region2, start2, end2, None, chr_order)
+    reg = _Region(hic_data, resolution, region1, start1, end1, region2, start2, end2, None, chr_order,
+                  nchunks)
     regions = reg.regions
     start_bin1, end_bin1, start_bin2, end_bin2 = reg.bin_coords
     if lengths is None:
@@ -351,7 +366,10 @@ def write_matrix(hic_data, resolution, biases, outdir,
         raise Exception('ERROR: should provide path to file with biases (pickle).')
     want_norm = 'norm' in normalizations
     want_decay = 'decay' in normalizations
-    cells = _Cells(hic_data, reg, biases, want_norm and not cooler, want_decay and not cooler, half=half_matrix)
+    # the raw&decay writer evaluates v / bias1[a] / bias2[b] for every cell before it prints the raw
+    # count: a bin without a bias is a KeyError there too
+    cells = _Cells(hic_data, reg, biases, want_norm and not cooler, want_decay and not cooler, half=half_matrix,
+                   touch_bias='raw&decay' in normalizations and not cooler)
     bads1, bads2 = cells.bads1, cells.bads2
 
     name = _generate_name(regions, (start1, start2), (end1, end2), resolution, chr_order)
