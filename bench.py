@@ -138,7 +138,7 @@ def cpu_baseline(wl, nbins, threads=None):
     # pass loop in C + OpenMP (oracle/ice_port.c); only the loop is timed, the CSR build is not
     bias, trace, cores, dt = orc.iterative_fast(m, {}, ITERATIONS, MAX_DEV, threads)
     return {"value": r.size * len(trace) / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "same_config": False,
+            "same_config": False, "seconds": dt,
             "sample": "leading %d x %d block of the %s model (%d contacts, %d passes, %.2f s "
                       "in the pass loop)" % (nbins, nbins, wl["name"], r.size, len(trace), dt)}
 
@@ -234,9 +234,10 @@ def run_reference(args, rank, world):
     cb = vals[-1]
     value = float(np.mean([v["value"] for v in vals[1:]])) if len(vals) > 1 else cb["value"]
     cb = dict(cb, value=value)
+    step_ms = float(np.mean([v["seconds"] for v in (vals[1:] if len(vals) > 1 else vals)])) * 1e3
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["description"], "sample": cb["sample"], "same_config": False},
             "cpu_baseline": cb, "reference_python": reference_rate(wl),
