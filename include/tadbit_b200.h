@@ -326,6 +326,13 @@ int tb_region_cells(tb_store *s, int64_t row_begin, int64_t row_end, int64_t col
 int tb_write_abc_lines(const char *path, int64_t n, const int32_t *h_a, const int32_t *h_b,
                        const int32_t *h_int, const double *h_val);
 
+/* Host-only, the same for N1: appends n lines "a<sep>b<sep>value<tail>" of
+ * Experiment.write_interaction_pairs (_pytadbit/experiment.py:1171-1186: '%s\t%s\t%s\n' for tsv,
+ * '%s,%s,%s\n' and '%s,%s,%s,\n' for json); value = h_int[k] when h_int is given, else h_val[k] as
+ * Python prints a float.  sep and tail: at most 8 bytes each. */
+int tb_write_pair_lines(const char *path, int64_t n, const int64_t *h_a, const int64_t *h_b,
+                        const int64_t *h_int, const double *h_val, const char *sep, const char *tail);
+
 /* ---- N4: compartments --------------------------------------------------------- */
 /* The numeric core of HiC_data.find_compartments (_pytadbit/hic_data.py:845-937), per section
  * (chromosome) [bin_begin, bin_end) of the genome, over the bins of the section that are not bad

@@ -599,6 +599,14 @@ int tb_write_abc_lines(const char *path, int64_t n, const int32_t *h_a, const in
   });
 }
 
+int tb_write_pair_lines(const char *path, int64_t n, const int64_t *h_a, const int64_t *h_b, const int64_t *h_int,
+                        const double *h_val, const char *sep, const char *tail) {
+  return guarded([&]() -> int {
+    write_pair_lines(path, n, h_a, h_b, h_int, h_val, sep, tail);
+    return TB_OK;
+  });
+}
+
 int tb_corr_build(tb_store *s, int64_t bin_begin, int64_t bin_end, const double *h_bias, const uint8_t *h_bad,
                   const double *h_expected, int32_t stage, int64_t *n_good) {
   return guarded([&]() -> int {

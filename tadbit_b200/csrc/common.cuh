@@ -342,6 +342,8 @@ void decay_sums(tb_store *s, const double *h_bias, const uint8_t *h_bad, double 
 void window(tb_store *s, int64_t r0, int64_t r1, int64_t c0, int64_t c1, const double *h_bias, double *h_out);
 void write_abc_lines(const char *path, int64_t n, const int32_t *a, const int32_t *b, const int32_t *ival,
                      const double *fval);
+void write_pair_lines(const char *path, int64_t n, const int64_t *a, const int64_t *b, const int64_t *ival,
+                      const double *fval, const char *sep, const char *tail);
 void region_cells(tb_store *s, int64_t r0, int64_t r1, int64_t c0, int64_t c1, const uint8_t *h_bad,
                   const double *h_bias, const double *h_decay, int half, int64_t *n, int32_t *h_row,
                   int32_t *h_col, int32_t *h_raw, double *h_nrm, double *h_dec);

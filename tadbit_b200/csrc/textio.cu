@@ -103,4 +103,35 @@ void write_abc_lines(const char *path, int64_t n, const int32_t *a, const int32_
   TB_REQUIRE(ok, "write_abc_lines: write to %s failed", path);
 }
 
+// Lines "a<sep>b<sep>value<tail>" of Experiment.write_interaction_pairs
+// (_pytadbit/experiment.py:1171-1186: '%s\t%s\t%s\n' for tsv, '%s,%s,%s\n' / '%s,%s,%s,\n' for
+// json), appended to `path`; value = ival[k] or fval[k] as Python's '%s' prints a float (= repr).
+void write_pair_lines(const char *path, int64_t n, const int64_t *a, const int64_t *b, const int64_t *ival,
+                      const double *fval, const char *sep, const char *tail) {
+  TB_REQUIRE(path && sep && tail && n >= 0 && (n == 0 || (a && b && (ival || fval))),
+             "write_pair_lines: bad arguments");
+  const size_t ls = strlen(sep), lt = strlen(tail);
+  TB_REQUIRE(ls <= 8 && lt <= 8, "write_pair_lines: separator or line end longer than 8 bytes");
+  FILE *f = fopen(path, "ab");
+  TB_REQUIRE(f, "write_pair_lines: cannot open %s", path);
+  constexpr int64_t kBatch = 1 << 15;
+  std::vector<char> buf((size_t)kBatch * 128);
+  bool ok = true;
+  for (int64_t k0 = 0; k0 < n && ok; k0 += kBatch) {
+    const int64_t k1 = k0 + kBatch < n ? k0 + kBatch : n;
+    char *p = buf.data();
+    for (int64_t k = k0; k < k1; ++k) {
+      p = put_int(p, a[k]);
+      memcpy(p, sep, ls); p += ls;
+      p = put_int(p, b[k]);
+      memcpy(p, sep, ls); p += ls;
+      p = ival ? put_int(p, ival[k]) : put_repr(p, fval[k]);
+      memcpy(p, tail, lt); p += lt;
+    }
+    ok = fwrite(buf.data(), 1, (size_t)(p - buf.data()), f) == (size_t)(p - buf.data());
+  }
+  ok = (fclose(f) == 0) && ok;
+  TB_REQUIRE(ok, "write_pair_lines: write to %s failed", path);
+}
+
 }  // namespace tb

@@ -15,7 +15,7 @@ import numpy as np
 
 from ._capi import bad_mask
 from .hic_data import HiC_data
-from .vectors import BinVector
+from .vectors import BinVector, PairTable
 
 
 class NormalizedMatrix(object):
@@ -136,9 +136,7 @@ class Experiment(object):
         else:
             rows, cols, vals = self._dense_pairs(good, normalized, zscored)
         self._pairs = (rows, cols, vals)
-        zsc = self._zscores
-        for i, j, v in zip(rows.tolist(), cols.tolist(), vals.tolist()):
-            zsc.setdefault(str(i), {})[str(j)] = v
+        self._zscores = PairTable(rows, cols, vals)     # {str(i): {str(j): value}} over the arrays
 
     def _dense_pairs(self, good, normalized, zscored):
         """All pairs i < j between good columns, zeros included (``remove_zeros=False`` or raw
@@ -191,6 +189,22 @@ class Experiment(object):
         else:
             start, end = 0, self.size
         sep = '\t' if format == 'tsv' else ','
+        pairs = self._sparse_pairs(normalized, zscored, diagonal, cutoff, uniq, remove_zeros, start, end)
+        if pairs is not None and format in ('tsv', 'json'):
+            rows, cols, vals = pairs
+            if true_position:
+                a, b = self.resolution * (rows + 1), self.resolution * (cols + 1)
+                tail = ',\n' if format == 'json' else '\n'
+            else:
+                a, b, tail = rows + 1 - start, cols + 1 - start, '\n'
+            if isinstance(fname, str):
+                out.close()
+                _write_pair_lines(fname, a, b, vals, sep, tail)
+                out = open(fname, 'a')
+            else:
+                out.write(''.join('%s%s%s%s%s%s' % (x, sep, y, sep, v, tail)
+                                  for x, y, v in zip(a.tolist(), b.tolist(), vals.tolist())))
+            start = end                                   # nothing left for the loop below
         for i in range(start, end):
             if i in self._zeros:
                 continue
@@ -225,6 +239,53 @@ class Experiment(object):
         if format == 'json':
             out.write(']}\n')
         out.close()
+
+
+    def _sparse_pairs(self, normalized, zscored, diagonal, cutoff, uniq, remove_zeros, start, end):
+        """The pairs the double loop of write_interaction_pairs would print, as arrays, when they
+        can be had without walking N^2 pairs: z-scores kept as a PairTable (only stored pairs pass
+        the loop's KeyError guard), or values without their zeros.  None otherwise."""
+        if zscored:
+            table = self._zscores
+            if not isinstance(table, PairTable):
+                return None
+            rows, cols, vals = table.rows, table.cols, table.vals
+            with np.errstate(invalid='ignore'):
+                keep = ~(vals < cutoff) & (vals != -99)
+        elif remove_zeros and uniq and not diagonal:
+            store = self.hic_data[0].store
+            bias = self._bias_array() if normalized else None
+            rows, cols, vals = store.pair_values(bias, bad_mask(self.size, self._zeros), zscore=None)
+            rows, cols = rows.astype(np.int64), cols.astype(np.int64)
+            if not normalized:
+                vals = vals.astype(np.int64)
+            keep = np.ones(rows.size, dtype=bool)
+        else:
+            return None
+        zero = bad_mask(self.size, self._zeros).astype(bool)
+        keep &= (rows >= start) & (rows < end) & (cols >= start) & (cols < end) & ~zero[rows] & ~zero[cols]
+        if remove_zeros:
+            keep &= vals != 0
+        return rows[keep], cols[keep], vals[keep]
+
+
+def _write_pair_lines(path, a, b, vals, sep, tail):
+    """``a <sep> b <sep> value <tail>`` per pair, appended to ``path`` by tb_write_pair_lines."""
+    import ctypes as C
+    import os
+    from . import _capi
+    a = np.ascontiguousarray(a, dtype=np.int64)
+    b = np.ascontiguousarray(b, dtype=np.int64)
+    ints = flts = None
+    if vals.dtype.kind in 'iu':
+        vals = np.ascontiguousarray(vals, dtype=np.int64)
+        ints = _capi.ptr(vals, C.c_int64)
+    else:
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        flts = _capi.ptr(vals, C.c_double)
+    _capi.check(_capi.lib().tb_write_pair_lines(os.fsencode(path), a.size, _capi.ptr(a, C.c_int64),
+                                                _capi.ptr(b, C.c_int64), ints, flts, sep.encode(),
+                                                tail.encode()))
 
 
 __all__ = ["Experiment", "NormalizedMatrix"]
