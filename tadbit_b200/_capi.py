@@ -156,7 +156,10 @@ def bad_mask(size, bads):
     """bads dict (or None) -> uint8[N] mask."""
     mask = np.zeros(size, dtype=np.uint8)
     if bads:
-        idx = np.fromiter((int(k) for k in bads), dtype=np.int64, count=len(bads))
+        try:                                               # integer keys: no Python-level loop
+            idx = np.fromiter(bads, dtype=np.int64, count=len(bads))
+        except (TypeError, ValueError):
+            idx = np.fromiter((int(k) for k in bads), dtype=np.int64, count=len(bads))
         idx = idx[(idx >= 0) & (idx < size)]
         mask[idx] = 1
     return mask

@@ -48,7 +48,7 @@ def filter_by_zero_count(matrx, perc_zero, min_count=None, silent=True):
             min_count *= 2
         min_val = size - min_count
         flagged = sums < min_count                             # :205
-    bads = dict((int(i), True) for i in np.flatnonzero(flagged))
+    bads = dict.fromkeys(np.flatnonzero(flagged).tolist(), True)
     if bads and not silent:
         if min_count is None:
             stderr.write(('\nWARNING: removing columns having more than %s '
@@ -148,8 +148,8 @@ def filter_by_mean(matrx, draw_hist=False, silent=False, bads=None, savefig=None
                              ' SKIPPING...\n')
             return bads
         totals = matrx.store.col_sums_masked(None)             # all rows, :141-145
-        for i in np.flatnonzero(totals < root):
-            bads[int(i)] = int(totals[i])
+        low = np.flatnonzero(totals < root)
+        bads.update(zip(low.tolist(), totals[low].tolist()))
         if bads and not silent:
             try:
                 message = ('\nWARNING: removing columns having less than %s '
