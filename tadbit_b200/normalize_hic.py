@@ -67,11 +67,25 @@ def expected(hic_data, bads=None, signal_to_noise=0.05, inter_chrom=False, **kwa
         size = max(hic_data.chromosomes.values())
     bad = bad_mask(len(hic_data), bads)
     ndiag = size
-    sums = hic_data.store.diag_sums(bad, ndiag).tolist()              # K5 (device), exact ints
+    sum_d = np.asarray(hic_data.store.diag_sums(bad, ndiag))         # K5 (device), exact ints
     sections = hic_data.section_pos or {None: (0, len(hic_data))}   # normalize_hic.py:279-283
-    cells = diagonal_cell_counts(sections, len(hic_data), bad, ndiag).tolist()
+    cell_d = diagonal_cell_counts(sections, len(hic_data), bad, ndiag)
+    sums, cells = sum_d.tolist(), cell_d.tolist()
     expc = {}
     dist = 0
+    # The short distances are not pooled: a diagonal that holds more than min_n reads (or no cell at
+    # all) is a group of its own, and the loop below gives it float(sum) / cells (or 0.).  That
+    # leading run is done at once (the sums are < 2^53: the division is the same); the loop takes
+    # over at the first distance that needs pooling.
+    alone = (cell_d == 0) | (sum_d > min_n)
+    lead = int(np.argmin(alone)) if not alone.all() else ndiag
+    lead = min(lead, size)
+    if lead and abs(sum_d[:lead]).max() < 2 ** 53:
+        with np.errstate(divide='ignore', invalid='ignore'):
+            vals = np.where(cell_d[:lead] == 0, 0., sum_d[:lead] / np.maximum(cell_d[:lead], 1)).tolist()
+        expc = dict(zip(range(lead), vals))
+        expc[lead] = vals[-1]                           # the key each group writes past its end
+        dist = lead
     while dist < size:                                  # normalize_hic.py:262-267
         total, ncell, stop = 0, 0, dist
         while True:                                     # _meandiag recursion, unrolled
