@@ -333,6 +333,22 @@ int tb_write_abc_lines(const char *path, int64_t n, const int32_t *h_a, const in
 int tb_write_pair_lines(const char *path, int64_t n, const int64_t *h_a, const int64_t *h_b,
                         const int64_t *h_int, const double *h_val, const char *sep, const char *tail);
 
+/* Host-only tails of K5 and N2 (no GPU involved): the sequential pooling walks over the per-distance
+ * sums.  tb_pool_expected -- the loop of `expected` around `_meandiag`
+ * (_pytadbit/utils/normalize_hic.py:262-291): h_sum_d / h_cells_d [ndiag] = reads and visited cells
+ * per distance (tb_diag_sums and the closed-form counts), consecutive distances pooled until they
+ * hold more than min_n reads; h_out[size + 2] receives the value of key d at h_out[d], *nkeys the
+ * number of keys (0 .. *nkeys - 1, the trailing key of the reference included).
+ * tb_pool_decay -- the pooling of one chromosome in `tadbit normalize`
+ * (_pytadbit/tools/tadbit_normalize.py:1077-1106): h_nrm / h_raw [size] from tb_decay_sums, h_ndiag
+ * [size] the cells per distance that touch no bad column; h_out[size] the decay per distance,
+ * h_state[size] = 0 no key, 1 a key the walk started with, 2 a key the walk added (the reference's
+ * dictionary lists the former first); *empty = 1 when the reference ends with an empty dictionary. */
+int tb_pool_expected(int64_t size, int64_t ndiag, const int64_t *h_sum_d, const int64_t *h_cells_d,
+                     double min_n, double *h_out, int64_t *nkeys);
+int tb_pool_decay(int64_t size, const double *h_nrm, const int64_t *h_raw, const int64_t *h_ndiag,
+                  double min_n, double *h_out, uint8_t *h_state, int32_t *empty);
+
 /* ---- N4: compartments --------------------------------------------------------- */
 /* The numeric core of HiC_data.find_compartments (_pytadbit/hic_data.py:845-937), per section
  * (chromosome) [bin_begin, bin_end) of the genome, over the bins of the section that are not bad

@@ -83,6 +83,8 @@ PROTOTYPES = {
                          _i64p, _i32p, _i32p, _i32p, _f64p, _f64p], C.c_int),
     "tb_write_abc_lines": ([C.c_char_p, C.c_int64, _i32p, _i32p, _i32p, _f64p], C.c_int),
     "tb_write_pair_lines": ([C.c_char_p, C.c_int64, _i64p, _i64p, _i64p, _f64p, C.c_char_p, C.c_char_p], C.c_int),
+    "tb_pool_expected": ([C.c_int64, C.c_int64, _i64p, _i64p, C.c_double, _f64p, _i64p], C.c_int),
+    "tb_pool_decay": ([C.c_int64, _f64p, _i64p, _i64p, C.c_double, _f64p, _u8p, _i32p], C.c_int),
     "tb_decay_sums": ([_store, _f64p, _u8p, _f64p, _i64p, _f64p], C.c_int),
     "tb_corr_build": ([_store, C.c_int64, C.c_int64, _f64p, _u8p, _f64p, C.c_int32, _i64p], C.c_int),
     "tb_corr_get": ([_store, _f64p], C.c_int),

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtadbit_b200.so")
-SOURCES = ["api.cu", "build.cu", "encode.cu", "rowsum.cu", "tiles.cu", "kernels.cu", "extras.cu", "compartments.cu", "synth.cu", "comm.cu", "textio.cu"]
+SOURCES = ["api.cu", "build.cu", "encode.cu", "rowsum.cu", "tiles.cu", "kernels.cu", "extras.cu", "compartments.cu", "synth.cu", "comm.cu", "textio.cu", "pooling.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr"]
 

@@ -607,6 +607,22 @@ int tb_write_pair_lines(const char *path, int64_t n, const int64_t *h_a, const i
   });
 }
 
+int tb_pool_expected(int64_t size, int64_t ndiag, const int64_t *h_sum_d, const int64_t *h_cells_d, double min_n,
+                     double *h_out, int64_t *nkeys) {
+  return guarded([&]() -> int {
+    pool_expected(size, ndiag, h_sum_d, h_cells_d, min_n, h_out, nkeys);
+    return TB_OK;
+  });
+}
+
+int tb_pool_decay(int64_t size, const double *h_nrm, const int64_t *h_raw, const int64_t *h_ndiag, double min_n,
+                  double *h_out, uint8_t *h_state, int32_t *empty) {
+  return guarded([&]() -> int {
+    pool_decay(size, h_nrm, h_raw, h_ndiag, min_n, h_out, h_state, empty);
+    return TB_OK;
+  });
+}
+
 int tb_corr_build(tb_store *s, int64_t bin_begin, int64_t bin_end, const double *h_bias, const uint8_t *h_bad,
                   const double *h_expected, int32_t stage, int64_t *n_good) {
   return guarded([&]() -> int {

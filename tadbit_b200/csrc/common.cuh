@@ -344,6 +344,10 @@ void write_abc_lines(const char *path, int64_t n, const int32_t *a, const int32_
                      const double *fval);
 void write_pair_lines(const char *path, int64_t n, const int64_t *a, const int64_t *b, const int64_t *ival,
                       const double *fval, const char *sep, const char *tail);
+void pool_expected(int64_t size, int64_t ndiag, const int64_t *sums, const int64_t *cells, double min_n,
+                   double *out_val, int64_t *nkeys);
+void pool_decay(int64_t size, const double *nrm, const int64_t *raw, const int64_t *ndiag, double min_n,
+                double *out_val, uint8_t *out_state, int32_t *empty);
 void region_cells(tb_store *s, int64_t r0, int64_t r1, int64_t c0, int64_t c1, const uint8_t *h_bad,
                   const double *h_bias, const double *h_decay, int half, int64_t *n, int32_t *h_row,
                   int32_t *h_col, int32_t *h_raw, double *h_nrm, double *h_dec);

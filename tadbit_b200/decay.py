@@ -17,9 +17,11 @@ its inclusive ``beg_chr <= b <= end_chr`` test.
 """
 from collections import OrderedDict
 
+import ctypes as C
+
 import numpy as np
 
-from ._capi import bad_mask
+from ._capi import bad_mask, check, lib, ptr
 
 
 def diagonal_cell_counts(section_pos, badcol):
@@ -27,7 +29,10 @@ def diagonal_cell_counts(section_pos, badcol):
     distance: |A u B| = |A| + |B| - |A n B| with A = bad columns left of ``end - dist``, B = bad
     columns at or right of ``beg + dist`` shifted by ``dist``, and A n B = pairs of bad columns
     ``dist`` apart, i.e. the autocorrelation of the bad-column indicator of the chromosome."""
-    bads = np.array(sorted(int(b) for b in badcol), dtype=np.int64)
+    try:
+        bads = np.sort(np.fromiter(badcol, dtype=np.int64, count=len(badcol)))
+    except (TypeError, ValueError):
+        bads = np.array(sorted(int(b) for b in badcol), dtype=np.int64)
     out = OrderedDict()
     for crm, (beg, end) in section_pos.items():
         size = end - beg
@@ -55,10 +60,12 @@ def diagonal_cell_counts(section_pos, badcol):
     return out
 
 
-def pool_decay(nrm, raw, ndiag, min_n):
+def _pool_decay_loop(nrm, raw, ndiag, min_n):
     """The pooling loop of one chromosome (tadbit_normalize.py:1077-1106) over the per-distance
     normalised sums ``nrm``, raw sums ``raw`` (both indexed by distance, 0 where the reference's
-    dict has no key) and cell counts ``ndiag``.  Returns the ``{distance: value}`` dict."""
+    dict has no key) and cell counts ``ndiag``, distance by distance as the reference walks them:
+    kept for inputs the group-wise form below does not take (negative or non-integer sums) and as
+    what the tests compare it with."""
     size = len(ndiag)
     has = (np.asarray(raw) != 0)
     nrm_l, raw_l, nd_l = [float(v) for v in nrm], [int(v) for v in raw], [int(v) for v in ndiag]
@@ -102,6 +109,34 @@ def pool_decay(nrm, raw, ndiag, min_n):
     return dec
 
 
+def pool_decay(nrm, raw, ndiag, min_n):
+    """The pooling loop of one chromosome (tadbit_normalize.py:1077-1106) over the per-distance
+    normalised sums ``nrm``, raw sums ``raw`` (both indexed by distance, 0 where the reference's
+    dict has no key) and cell counts ``ndiag``.  Returns the ``{distance: value}`` dict.
+
+    The walk itself runs in the library (``tb_pool_decay``, host C++: same additions in the same
+    order, same divisions); the dictionary is put together here in the reference's key order -- the
+    distances that hold reads first, then the ones the pooling added."""
+    raw_a = np.asarray(raw)
+    if raw_a.dtype.kind not in 'iu' or (raw_a.size and np.abs(raw_a).max() >= 2 ** 53):
+        return _pool_decay_loop(nrm, raw, ndiag, min_n)            # never the case for counts
+    size = len(ndiag)
+    raw_a = np.ascontiguousarray(raw_a, dtype=np.int64)
+    nrm_a = np.ascontiguousarray(nrm, dtype=np.float64)
+    nd_a = np.ascontiguousarray(ndiag, dtype=np.int64)
+    out = np.empty(size, dtype=np.float64)
+    state = np.empty(size, dtype=np.uint8)
+    empty = C.c_int32()
+    check(lib().tb_pool_decay(size, ptr(nrm_a, C.c_double), ptr(raw_a, C.c_int64), ptr(nd_a, C.c_int64),
+                              float(min_n), ptr(out, C.c_double), ptr(state, C.c_uint8), C.byref(empty)))
+    if empty.value:
+        return {}
+    began, added = np.flatnonzero(state == 1), np.flatnonzero(state == 2)
+    dec = dict(zip(began.tolist(), out[began].tolist()))
+    dec.update(zip(added.tolist(), out[added].tolist()))
+    return dec
+
+
 def column_biases(hic_data, badcol, normalization='Vanilla'):
     """The biases ``tadbit normalize`` starts from (tadbit_normalize.py:897-925), before
     :func:`rescale_and_decay` rescales them: per bin the total number of interactions of its row
@@ -127,7 +162,7 @@ def column_biases(hic_data, badcol, normalization='Vanilla'):
         biases = biases ** 0.5
     mean_col = np.nanmean(biases)
     biases = biases / mean_col * mean_col ** 0.5
-    return dict((k, v) for k, v in enumerate(biases.tolist()))
+    return dict(enumerate(biases.tolist()))
 
 
 def rescale_and_decay(hic_data, biases, badcol, factor=1, normalize_only=False,
@@ -146,7 +181,7 @@ def rescale_and_decay(hic_data, biases, badcol, factor=1, normalize_only=False,
     if hasattr(biases, 'to_array'):
         b = biases.to_array().astype(np.float64)
     elif isinstance(biases, dict):
-        b = np.array([biases[k] for k in range(size)], dtype=np.float64)
+        b = np.fromiter(map(biases.__getitem__, range(size)), dtype=np.float64, count=size)
     else:
         b = np.asarray(biases, dtype=np.float64)
     nan = np.isnan(b)
@@ -154,7 +189,7 @@ def rescale_and_decay(hic_data, biases, badcol, factor=1, normalize_only=False,
     sumnrm = store.norm_sum(np.where(nan, 1.0, b), nan.astype(np.uint8))
     target = (sumnrm / float(size * size * factor)) ** 0.5
     b = b * target
-    biases = dict((k, v) for k, v in enumerate(b.tolist()))
+    biases = dict(enumerate(b.tolist()))
     sections = hic_data.chromosomes or OrderedDict([(None, size)])
     section_pos = hic_data.section_pos or {None: (0, size)}
     mask = bad_mask(size, badcol)

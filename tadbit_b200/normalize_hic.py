@@ -3,9 +3,11 @@
 Drop-in for ``pytadbit.utils.normalize_hic.iterative`` / ``expected``
 (reference: _pytadbit/utils/normalize_hic.py:180-231 and :234-291).
 """
+import ctypes as C
+
 import numpy as np
 
-from ._capi import bad_mask
+from ._capi import bad_mask, check, lib, ptr
 from .vectors import BinVector
 
 TRACE_FORMAT = '   %15.3f %15.3f %15.3f %4s %9.5f'          # normalize_hic.py:220
@@ -67,25 +69,23 @@ def expected(hic_data, bads=None, signal_to_noise=0.05, inter_chrom=False, **kwa
         size = max(hic_data.chromosomes.values())
     bad = bad_mask(len(hic_data), bads)
     ndiag = size
-    sum_d = np.asarray(hic_data.store.diag_sums(bad, ndiag))         # K5 (device), exact ints
+    sum_d = np.ascontiguousarray(hic_data.store.diag_sums(bad, ndiag), dtype=np.int64)   # K5 (device)
     sections = hic_data.section_pos or {None: (0, len(hic_data))}   # normalize_hic.py:279-283
-    cell_d = diagonal_cell_counts(sections, len(hic_data), bad, ndiag)
-    sums, cells = sum_d.tolist(), cell_d.tolist()
+    cell_d = np.ascontiguousarray(diagonal_cell_counts(sections, len(hic_data), bad, ndiag), dtype=np.int64)
+    if sum_d.size and np.abs(sum_d).max() >= 2 ** 53:              # float(total) would round
+        return _pool_expected_loop(sum_d.tolist(), cell_d.tolist(), size, ndiag, min_n)
+    vals = np.empty(size + 2, dtype=np.float64)
+    nkeys = C.c_int64()
+    check(lib().tb_pool_expected(size, ndiag, ptr(sum_d, C.c_int64), ptr(cell_d, C.c_int64), float(min_n),
+                                 ptr(vals, C.c_double), C.byref(nkeys)))
+    return dict(zip(range(nkeys.value), vals[:nkeys.value].tolist()))
+
+
+def _pool_expected_loop(sums, cells, size, ndiag, min_n):
+    """The pooling of ``expected`` distance by distance in Python (normalize_hic.py:262-291): what
+    tb_pool_expected does, kept for sums beyond 2^53 and as what the tests compare it with."""
     expc = {}
     dist = 0
-    # The short distances are not pooled: a diagonal that holds more than min_n reads (or no cell at
-    # all) is a group of its own, and the loop below gives it float(sum) / cells (or 0.).  That
-    # leading run is done at once (the sums are < 2^53: the division is the same); the loop takes
-    # over at the first distance that needs pooling.
-    alone = (cell_d == 0) | (sum_d > min_n)
-    lead = int(np.argmin(alone)) if not alone.all() else ndiag
-    lead = min(lead, size)
-    if lead and abs(sum_d[:lead]).max() < 2 ** 53:
-        with np.errstate(divide='ignore', invalid='ignore'):
-            vals = np.where(cell_d[:lead] == 0, 0., sum_d[:lead] / np.maximum(cell_d[:lead], 1)).tolist()
-        expc = dict(zip(range(lead), vals))
-        expc[lead] = vals[-1]                           # the key each group writes past its end
-        dist = lead
     while dist < size:                                  # normalize_hic.py:262-267
         total, ncell, stop = 0, 0, dist
         while True:                                     # _meandiag recursion, unrolled

@@ -149,3 +149,54 @@ def test_closed_form_cell_counts_equal_the_literal_loop():
         got = diagonal_cell_counts(pos, badcol)
         for crm in pos:
             assert [int(v) for v in got[crm]] == [want[crm][k] for k in range(len(got[crm]))], (sizes, sorted(badcol))
+
+
+def test_native_decay_pooling_equals_the_python_loop():
+    """decay.pool_decay runs the walk in the library (tb_pool_decay, host C++); _pool_decay_loop is
+    the reference's walk in Python, distance by distance.  Same dictionaries -- keys, their order,
+    and the bits of the values -- on random chromosomes, incl. empty diagonals, diagonals without a
+    good cell, thresholds an integer sum can hit exactly, negative counts."""
+    from tadbit_b200 import decay as d
+    rng = np.random.default_rng(2)
+    for it in range(3000):
+        size = int(rng.integers(0, 60)) if it % 50 else int(rng.integers(2000, 6000))
+        scale = rng.choice([0, 1, 20, 300, 500, 5000, 1e5])
+        raw = (scale * rng.random(size) * (np.arange(size) + 1.0) ** -rng.choice([0, 0.5, 1.5])).astype(np.int64)
+        if rng.random() < 0.4:
+            raw[rng.random(size) < 0.4] = 0
+        if rng.random() < 0.05 and size:
+            raw[rng.integers(0, size)] *= -1
+        nrm = np.where(raw != 0, rng.random(size) * raw * rng.lognormal(0, 1, size), 0.0)
+        if rng.random() < 0.1:
+            nrm = rng.random(size)
+        nd = np.maximum(size - np.arange(size) - rng.integers(0, 5, size), 0)
+        if rng.random() < 0.2 and size:
+            nd[rng.random(size) < 0.3] = 0
+        min_n = float(rng.choice([0.05, 0.1, 0.5, 0.02, 0.25])) ** -2.
+        got, want = d.pool_decay(nrm, raw, nd, min_n), d._pool_decay_loop(nrm, raw, nd, min_n)
+        assert list(got.items()) == list(want.items()), (it, size, min_n)
+
+
+def test_native_expected_pooling_equals_the_python_loop():
+    """tb_pool_expected against the Python restatement of the loop around _meandiag
+    (normalize_hic.py:262-291): same keys in the same order, same bits."""
+    import ctypes as C
+    from tadbit_b200 import _capi, normalize_hic as nh
+    rng = np.random.default_rng(8)
+    for it in range(3000):
+        size = int(rng.integers(0, 70)) if it % 60 else int(rng.integers(3000, 9000))
+        ndiag = size if rng.random() < 0.8 else int(rng.integers(0, size + 1))
+        scale = rng.choice([0, 1, 50, 500, 5000, 1e7])
+        sums = (scale * rng.random(ndiag) * (np.arange(ndiag) + 1.0) ** -rng.choice([0, 1, 2])).astype(np.int64)
+        cells = np.maximum(ndiag - np.arange(ndiag) - rng.integers(0, 4, ndiag), 0).astype(np.int64)
+        if rng.random() < 0.3 and ndiag:
+            cells[rng.random(ndiag) < 0.3] = 0
+        min_n = float(rng.choice([0.05, 0.1, 0.5, 0.25])) ** -2.
+        vals = np.empty(size + 2, dtype=np.float64)
+        nkeys = C.c_int64()
+        _capi.check(_capi.lib().tb_pool_expected(size, ndiag, _capi.ptr(sums, C.c_int64),
+                                                 _capi.ptr(cells, C.c_int64), min_n,
+                                                 _capi.ptr(vals, C.c_double), C.byref(nkeys)))
+        got = dict(zip(range(nkeys.value), vals[:nkeys.value].tolist()))
+        want = nh._pool_expected_loop(sums.tolist(), cells.tolist(), size, ndiag, min_n)
+        assert list(got.items()) == list(want.items()), (it, size, ndiag, min_n)
