@@ -84,7 +84,10 @@ def _swapped_r2(poly, counts, edges):
     # the reference calls get_r2(p, x, y): X = counts, Y = bin edges (hic_filtering.py:19-22,94)
     centre = np.mean(edges)
     total = sum([(edges[k] - centre) ** 2 for k in range(len(edges))])
-    resid = sum([(edges[k] - poly(counts[k])) ** 2 for k in range(len(edges))])
+    # Horner's rule is elementwise: evaluating all bins at once gives the values of 100 separate
+    # calls; the squares are still added left to right as the reference's sum([...]) adds them
+    fitted = poly(np.asarray(counts))
+    resid = sum([(edges[k] - fitted[k]) ** 2 for k in range(len(edges))])
     return 1 - resid / total
 
 
