@@ -130,6 +130,8 @@ class HiC_data(object):
         self._init_common(store.size, chromosomes, dict_sec, resolution, masked, symmetricized)
         self.store = store
         self._keys = self._vals = None
+        if hasattr(type(store), 'from_coo'):               # cells set later rebuild a store of this kind
+            self._new_store = type(store).from_coo
         return self
 
     def _init_common(self, size, chromosomes, dict_sec, resolution, masked, symmetricized):
@@ -145,6 +147,10 @@ class HiC_data(object):
         self.symmetricized = symmetricized
         self.compartments = {}
         self.last_trace = None
+        self._pending = {}                                     # cells set since the store was built
+        self._store = None
+        self._device = 0
+        self._new_store = ContactStore.from_coo
         if self.chromosomes:                                   # hic_data.py:70-75
             total = 0
             for crm in self.chromosomes:
@@ -174,14 +180,59 @@ class HiC_data(object):
         self._keys = keys[order]
         self._vals = vals[order].astype(np.int64)
         chrom = self.chromosomes if self.chromosomes else None
+        self._device = device
         self.store = ContactStore.from_coo(self.__size, rows[order], cols[order],
                                            self._vals, chromosomes=chrom, device=device)
+
+    # -- the resident store; cells set through ``hic[i, j] = v`` are folded in before it is used -----
+    @property
+    def store(self):
+        if self._pending:
+            self._rebuild()
+        return self._store
+
+    @store.setter
+    def store(self, value):
+        self._store = value
+
+    def _rebuild(self):
+        """Fold the pending cells into the host copy of the upper triangle and build the store anew
+        (a store is immutable: its compact stream is laid out once)."""
+        if self._keys is None:
+            r, c, v = self._store.export_upper()
+            self._keys = r.astype(np.int64) * self.__size + c
+            self._vals = v.astype(np.int64)
+        pend_k = np.fromiter(self._pending.keys(), dtype=np.int64, count=len(self._pending))
+        pend_v = np.fromiter(self._pending.values(), dtype=np.int64, count=len(self._pending))
+        self._pending = {}
+        order = np.argsort(pend_k)
+        pend_k, pend_v = pend_k[order], pend_v[order]
+        pos = np.searchsorted(self._keys, pend_k)
+        found = (pos < self._keys.size) & (self._keys[np.minimum(pos, max(self._keys.size - 1, 0))] == pend_k) \
+            if self._keys.size else np.zeros(pend_k.size, dtype=bool)
+        vals = self._vals.copy()
+        vals[pos[found]] = pend_v[found]
+        keys = np.concatenate([self._keys, pend_k[~found]])
+        vals = np.concatenate([vals, pend_v[~found]])
+        order = np.argsort(keys, kind="stable")
+        self._keys, self._vals = keys[order], vals[order]
+        rows, cols = np.divmod(self._keys, self.__size)
+        old = self._store
+        chrom = self.chromosomes if self.chromosomes else None
+        kw = dict(chromosomes=chrom)
+        if self._new_store is ContactStore.from_coo:
+            kw["device"] = self._device
+        self._store = self._new_store(self.__size, rows, cols, self._vals, **kw)
+        if old is not None and hasattr(old, "close"):
+            old.close()
 
     # -- dict-like surface --------------------------------------------------------------
     def __len__(self):
         return self.__size
 
     def _host_cells(self):
+        if self._pending:
+            self._rebuild()
         if self._keys is None:
             r, c, v = self.store.export_upper()
             self._keys = r.astype(np.int64) * self.__size + c
@@ -192,8 +243,12 @@ class HiC_data(object):
         row, col = divmod(int(pos), self.__size)
         if row > col:
             row, col = col, row
-        keys, vals = self._host_cells()
         k = row * self.__size + col
+        if k in self._pending:
+            return self._pending[k]
+        if self._keys is None:
+            self._host_cells()
+        keys, vals = self._keys, self._vals
         p = int(np.searchsorted(keys, k))
         if p < keys.size and keys[p] == k:
             return int(vals[p])
@@ -212,8 +267,31 @@ class HiC_data(object):
             return self.get(row_col, 0)
 
     def __setitem__(self, row_col, val):
-        raise NotImplementedError('the GPU-resident contact store is immutable; build a new '
-                                  'HiC_data to change cells')
+        """``hic[row, col] = count`` (hic_data.py:146-164).  The matrix stays symmetric: the cell and
+        its mirror are one stored value (the reference's dictionary would take them one by one; its
+        parsers always set both).  Cells set this way are kept aside and folded into a new resident
+        store the next time the matrix is used, so set many, then compute."""
+        try:
+            row, col = row_col
+            pos = row * self.__size + col
+            if pos > self._size2:
+                print(row, col, pos)
+                raise IndexError('ERROR: row or column larger than %s' % self.__size)
+        except TypeError:
+            if row_col > self._size2:
+                raise IndexError('ERROR: position %d larger than %s^2' % (row_col, self.__size))
+            row, col = divmod(int(row_col), self.__size)
+        if val != int(val):
+            raise NotImplementedError('tadbit_b200 balances raw integer counts; normalised (float) '
+                                      'matrices are outside the accelerated path')
+        if abs(int(val)) > _INT32_MAX:
+            raise OverflowError('cell count does not fit int32')
+        row, col = int(row), int(col)
+        if not (0 <= row < self.__size and 0 <= col < self.__size):
+            raise IndexError('ERROR: row or column larger than %s' % self.__size)
+        if row > col:
+            row, col = col, row
+        self._pending[row * self.__size + col] = int(val)
 
     def items(self):
         """(key, value) over BOTH triangles, as the reference's dict holds them."""

@@ -15,6 +15,10 @@ class NumpyStore(object):
         self.m = orc.OracleMatrix(size, rows, cols, vals, chromosomes=chromosomes,
                                   symmetricized=symmetricized)
 
+    @classmethod
+    def from_coo(cls, size, rows, cols, vals, chromosomes=None):   # ContactStore.from_coo
+        return cls(size, rows, cols, vals, chromosomes=chromosomes)
+
     @staticmethod
     def _bads(mask):
         if mask is None:

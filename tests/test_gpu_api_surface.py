@@ -45,8 +45,26 @@ def test_reference_style_constructor_matches_from_coo():
     assert dict(hic.items()) == full
     csr = hic.get_hic_data_as_csr()
     assert csr.shape == (n, n) and csr.sum() == sum(full.values())
+    # cells can be set (hic_data.py:146-164); the matrix stays symmetric and the resident store is
+    # rebuilt the next time it is used
+    old = hic[0, 1]
+    hic[0, 1] = old + 3
+    hic[n - 1, 2] = 7
+    assert hic[0, 1] == old + 3 and hic[1, 0] == old + 3 and hic[2, n - 1] == 7
+    changed = dict(full)
+    for key in (1, n):
+        changed[key] = old + 3
+    for key in ((n - 1) * n + 2, 2 * n + n - 1):
+        changed[key] = 7
+    assert dict(hic.items()) == changed
+    hic.bads = {}
+    assert hic.sum() == sum(changed.values())              # K3 over the rebuilt store
+    stored, sums = hic.store.row_stats()
+    assert int(sums[0]) == sum(v for k, v in changed.items() if k // n == 0)
     with pytest.raises(NotImplementedError):
-        hic[0, 1] = 3
+        hic[0, 1] = 3.5
+    with pytest.raises(IndexError):
+        hic[n, n + 5] = 1
 
 
 def test_from_reference_like_object_and_bias_pickle(tmp_path):

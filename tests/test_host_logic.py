@@ -184,3 +184,52 @@ def test_rebalance_by_time_equalises_estimated_time():
     probes[1] = (0.0, probes[1][1], probes[1][2], np.zeros_like(probes[1][3]))
     again = rebalance_by_time(blocks, probes, n)
     assert again[0][0] == 0 and again[-1][1] == n
+
+
+def test_cells_can_be_set_and_the_store_is_rebuilt():
+    """HiC_data.__setitem__ (reference: _pytadbit/hic_data.py:146-164): symmetric assignment, pending
+    cells visible to item access at once and folded into a new store on the next use -- the host
+    logic of tests/test_gpu_api_surface.py, here over the store double."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import numpy as np
+    import pytest
+    import tadbit_b200
+    from _numpy_store import NumpyStore
+    rng = np.random.default_rng(3)
+    n = 40
+    i, j = np.triu_indices(n)
+    keep = rng.random(i.size) < 0.4
+    r, c, v = i[keep], j[keep], rng.integers(1, 50, int(keep.sum()))
+    full = {}
+    for a, b, x in zip(r.tolist(), c.tolist(), v.tolist()):
+        full[a * n + b] = x
+        full[b * n + a] = x
+    hic = tadbit_b200.HiC_data.from_store(NumpyStore(n, r, c, v), dict_sec={})
+    first_store = hic.store
+    old = hic[0, 1]
+    hic[0, 1] = old + 3
+    hic[n - 1, 2] = 7                                        # given below the diagonal
+    hic[5 * n + 5] = 0                                       # flat position; an explicit zero is a stored cell
+    assert hic[0, 1] == old + 3 and hic[1, 0] == old + 3 and hic[2, n - 1] == 7 and hic[5, 5] == 0
+    changed = dict(full)
+    changed[1] = changed[n] = old + 3
+    changed[(n - 1) * n + 2] = changed[2 * n + n - 1] = 7
+    changed[5 * n + 5] = 0
+    assert dict(hic.items()) == changed
+    assert hic.store is not first_store and hic.store is hic.store           # rebuilt once
+    assert hic.sum() == sum(changed.values())
+    stored, sums = hic.store.row_stats()
+    assert int(sums[0]) == sum(x for k, x in changed.items() if k // n == 0)
+    assert int(stored[5]) == sum(1 for k in changed if k // n == 5)
+    hic[0, 1] = old                                          # and back: same matrix as at the start
+    hic[n - 1, 2] = full.get((n - 1) * n + 2, 0)
+    got = dict((k, x) for k, x in hic.items() if x != 0 or k in full)
+    assert dict((k, x) for k, x in got.items() if x) == dict((k, x) for k, x in full.items() if x)
+    with pytest.raises(NotImplementedError):
+        hic[0, 1] = 3.5
+    with pytest.raises(IndexError):
+        hic[n, n + 5] = 1
+    with pytest.raises(OverflowError):
+        hic[0, 0] = 2 ** 31
