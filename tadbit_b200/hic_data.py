@@ -220,7 +220,7 @@ class HiC_data(object):
         old = self._store
         chrom = self.chromosomes if self.chromosomes else None
         kw = dict(chromosomes=chrom)
-        if self._new_store is ContactStore.from_coo:
+        if self._new_store == ContactStore.from_coo:
             kw["device"] = self._device
         self._store = self._new_store(self.__size, rows, cols, self._vals, **kw)
         if old is not None and hasattr(old, "close"):
