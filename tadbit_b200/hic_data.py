@@ -357,16 +357,15 @@ class HiC_data(object):
         :param False normalized: use count / bias[i] / bias[j]
         :param None exclude: chromosomes to leave out
         :param True diagonal: include the diagonal in the cis count
-        :param None equals: merging chromosomes by a user function is not supported here
+        :param None equals: function of two chromosome names that says whether they count as one
+           (e.g. ``lambda x, y: x[:4] == y[:4]`` for chr2L / chr2R; consecutive chromosomes only, as
+           in the reference).  Costs one pass of the normalised sum per group of chromosomes.
         """
         from ._capi import bad_mask
         if normalized and not self.bias:
             raise Exception('ERROR: experiment not normalized yet')
         if not self.chromosomes:
             return float('nan')
-        if equals is not None:
-            raise NotImplementedError('cis_trans_ratio: merging chromosomes with `equals` is not '
-                                      'available on the GPU-resident store')
         bads = set(self.bads.keys())
         for c in (exclude or []):
             bads.update(range(*self.section_pos[c]))
@@ -374,11 +373,34 @@ class HiC_data(object):
         weights = self._bias_array() if normalized else np.ones(self.__size)
         nrm, raw, _ = self.store.decay_sums(weights, mask)
         intra = 0.0 if normalized else 0
-        for beg, end in self.section_pos.values():
-            per_distance = nrm[beg:end] if normalized else raw[beg:end]
-            if end > beg:
-                inside = 2 * per_distance[1:].sum() + (per_distance[0] if diagonal else 0)
-                intra += float(inside) if normalized else int(inside)
+        if equals is None:
+            for beg, end in self.section_pos.values():
+                per_distance = nrm[beg:end] if normalized else raw[beg:end]
+                if end > beg:
+                    inside = 2 * per_distance[1:].sum() + (per_distance[0] if diagonal else 0)
+                    intra += float(inside) if normalized else int(inside)
+        else:
+            # chromosomes merged with their successor (hic_data.py:281-290): a group of consecutive
+            # chromosomes is one square block of the matrix; its sum is the normalised sum with
+            # everything outside the block masked (K3), minus its diagonal when that is left out
+            to_skip, c_prev = set(), ''
+            for c in self.chromosomes:
+                if equals(c, c_prev):
+                    to_skip.add(c_prev)
+                c_prev = c
+            ends = sorted(self.section_pos[c][1] for c in self.section_pos if c not in to_skip)
+            diag = dict((beg, (nrm if normalized else raw)[beg]) for beg, end in self.section_pos.values()
+                        if end > beg)
+            beg = 0
+            for end in ends:
+                block = mask.copy()
+                block[:beg] = 1
+                block[end:] = 1
+                inside = self.store.norm_sum(weights if normalized else None, block)
+                if not diagonal:
+                    inside -= sum(v for b, v in diag.items() if beg <= b < end)
+                intra += float(inside) if normalized else int(round(inside))
+                beg = end
         try:
             return float(intra) / self.sum(bias=self.bias if normalized else None, bads=bads)
         except ZeroDivisionError:

@@ -140,5 +140,11 @@ def test_cis_trans_ratio_through_the_kernels():
         assert abs(a - b) <= 1e-12 * abs(b), (kw, a, b)
     plain = tadbit_b200.HiC_data.from_coo(case.size, case.rows, case.cols, case.vals)
     assert np.isnan(plain.cis_trans_ratio())                  # no chromosomes: NaN, as the reference
-    with pytest.raises(NotImplementedError):
-        gpu.cis_trans_ratio(equals=lambda x, y: x[:3] == y[:3])
+    # chromosomes merged with their successor (one K3 pass per group of chromosomes)
+    names = list(case.chromosomes)
+    merged = lambda x, y: {x, y} == set(names[:2])                        # noqa: E731
+    for kw in (dict(equals=merged), dict(equals=merged, diagonal=False)):
+        assert gpu.cis_trans_ratio(**kw) == cpu.cis_trans_ratio(**kw), kw
+    a, b = gpu.cis_trans_ratio(normalized=True, equals=merged), cpu.cis_trans_ratio(normalized=True, equals=merged)
+    assert abs(a - b) <= 1e-12 * abs(b)
+    assert gpu.cis_trans_ratio(equals=lambda x, y: True) == 1.0              # everything one group

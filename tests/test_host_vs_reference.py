@@ -310,6 +310,11 @@ def test_cis_trans_ratio_against_the_reference(seed):
     assert ours.cis_trans_ratio(diagonal=False) == ref.cis_trans_ratio(diagonal=False)
     if len(k["names"]) > 1:
         assert ours.cis_trans_ratio(exclude=[k["names"][0]]) == ref.cis_trans_ratio(exclude=[k["names"][0]])
+    # chromosomes merged with their successor: pairs (c0, c1), (c2, c3) by name; all into one
+    for equals in (lambda x, y: x[1:].isdigit() and y[1:].isdigit() and int(x[1:]) // 2 == int(y[1:]) // 2,
+                   lambda x, y: bool(y)):
+        for kw in (dict(), dict(diagonal=False)):
+            assert ours.cis_trans_ratio(equals=equals, **kw) == ref.cis_trans_ratio(equals=equals, **kw)
     for hic in (ref, ours):
         with pytest.raises(Exception, match="not normalized"):
             hic.cis_trans_ratio(normalized=True)
@@ -319,7 +324,9 @@ def test_cis_trans_ratio_against_the_reference(seed):
                 hic.normalize_hic(iterations=10, max_dev=1e-4, silent=True)
     except ZeroDivisionError:
         return
-    for kw in (dict(normalized=True), dict(normalized=True, diagonal=False)):
+    pairs = lambda x, y: x[1:].isdigit() and y[1:].isdigit() and int(x[1:]) // 2 == int(y[1:]) // 2   # noqa: E731
+    for kw in (dict(normalized=True), dict(normalized=True, diagonal=False),
+               dict(normalized=True, equals=pairs), dict(normalized=True, diagonal=False, equals=pairs)):
         a, b = ours.cis_trans_ratio(**kw), ref.cis_trans_ratio(**kw)
         assert abs(a - b) <= 1e-12 * abs(b), (kw, a, b)
 
