@@ -48,9 +48,16 @@ class Experiment(object):
     :param None hic_data: a :class:`tadbit_b200.HiC_data`
     """
 
-    def __init__(self, name, resolution, hic_data=None, **kw_descr):
+    def __init__(self, name, resolution, hic_data=None, conditions=None, identifier=None,
+                 cell_type=None, enzyme=None, exp_type='Hi-C', **kw_descr):
         self.name = name
         self.resolution = resolution
+        self.identifier = identifier
+        self.cell_type = cell_type
+        self.enzyme = enzyme
+        self.exp_type = exp_type
+        self.crm = None                                      # the chromosome object it belongs to (.name)
+        self.conditions = sorted(conditions) if conditions else []
         self.description = kw_descr
         self.hic_data = None
         self.size = None
@@ -184,6 +191,33 @@ class Experiment(object):
             out.write('elt1\telt2\t%s\n' % ('zscore' if zscored else
                                             'normalized hi-c' if normalized
                                             else 'raw hi-c'))
+        elif header and format == 'json':                    # experiment.py:1118-1144, the same text
+            out.write('''
+{
+    "metadata": {
+                        "formatVersion" : 3,
+                        %s
+                        "species" : "%s",
+                        "cellType" : "%s",
+                        "experimentType" : "%s",
+                        "identifier" : "%s",
+                        "resolution" : %s,
+                        "chromosome" : "%s",
+                        "start" : %s,
+                        "end" : %s
+                },
+    "interactions": [
+                ''' % ('\n'.join(['"%s": "%s",' % (k, self.description[k])
+                                  for k in self.description]),
+                       self.description.get('species', ''),
+                       self.cell_type,
+                       self.exp_type,
+                       self.identifier,
+                       self.resolution,
+                       self.crm.name,
+                       focus[0] * self.resolution if focus else 1,
+                       (focus[1] * self.resolution if focus else
+                        self.resolution * self.size)))
         if focus:
             start, end = focus[0], focus[1] + 1
         else:
