@@ -275,6 +275,59 @@ class Experiment(object):
         out.close()
 
 
+    # -- the dense matrix ----------------------------------------------------------------------
+    def _dense(self, start, end, normalized):
+        store = self.hic_data[0].store
+        if normalized:
+            return store.window(start, end, start, end, self._bias_array()).tolist()
+        return np.rint(store.window(start, end, start, end)).astype(np.int64).tolist()
+
+    def get_hic_matrix(self, focus=None, diagonal=True, normalized=False):
+        """
+        Return the Hi-C matrix (experiment.py:1192-1226) -- a dense window from ``tb_window``.
+
+        :param None focus: a tuple (start, end), both inclusive, bins counted from 1
+        :param True diagonal: False replaces the values in the diagonal by one (zero where empty)
+        :param False normalized: normalized data instead of raw Hi-C
+
+        :returns: list of lists
+        """
+        if normalized and not self.norm:
+            raise Exception('ERROR: experiment not normalized yet')
+        if focus:
+            start, end = focus
+            start -= 1
+        else:
+            start, end = 0, self.size
+        mtrx = self._dense(start, end, normalized)
+        if not diagonal:
+            for i in range(start, end):                       # absolute indices, as in the reference
+                mtrx[i][i] = 1 if mtrx[i][i] else 0
+        return mtrx
+
+    def print_hic_matrix(self, print_it=True, normalized=False, zeros=False):
+        """
+        Return the Hi-C matrix as string (experiment.py:1229-1255)
+
+        :param True print_it: Otherwise, returns the string
+        :param False normalized: normalized data, instead of raw Hi-C
+        :param False zeros: write 'nan' in the filtered columns
+        """
+        siz = self.size
+        if normalized and not self.norm:
+            raise TypeError("'NoneType' object is not subscriptable")     # self.norm[0] of the reference
+        rows = self._dense(0, siz, normalized)
+        if zeros:
+            zero = [i in self._zeros for i in range(siz)]
+            out = '\n'.join(['\t'.join(['nan' if (zero[i] or zero[j]) else str(rows[j][i])
+                                        for i in range(siz)]) for j in range(siz)])
+        else:
+            out = '\n'.join(['\t'.join([str(x) for x in row]) for row in rows])
+        if print_it:
+            print(out)
+        else:
+            return out + '\n'
+
     def _sparse_pairs(self, normalized, zscored, diagonal, cutoff, uniq, remove_zeros, start, end):
         """The pairs the double loop of write_interaction_pairs would print, as arrays, when they
         can be had without walking N^2 pairs: z-scores kept as a PairTable (only stored pairs pass

@@ -101,6 +101,45 @@ def test_written_pairs_against_the_live_reference(seed, tmp_path):
     assert out.getvalue() == open(str(tmp_path / "p.tsv")).read()
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_dense_matrix_against_the_live_reference(seed):
+    """Experiment.get_hic_matrix / print_hic_matrix (experiment.py:1192-1255) over tb_window."""
+    rng, n, r, c, v = _matrix(100 + seed)
+    ref, new = _reference_experiment(n, r, c, v), _ours(n, r, c, v)
+    with contextlib.redirect_stderr(io.StringIO()), contextlib.redirect_stdout(io.StringIO()), \
+            np.errstate(all="ignore"):
+        for exp in (ref, new):
+            with pytest.raises(Exception, match="not normalized"):
+                exp.get_hic_matrix(normalized=True)
+            exp.filter_columns(silent=True)
+            exp.normalize_hic(silent=True, iterations=8, max_dev=1e-3)
+    hi = int(rng.integers(5, n))
+    for kw in (dict(), dict(diagonal=False), dict(focus=(1, hi)), dict(focus=(1, hi), diagonal=False),
+               dict(focus=(3, hi)), dict(normalized=True), dict(normalized=True, focus=(2, hi)),
+               dict(normalized=True, diagonal=False)):
+        a, b = ref.get_hic_matrix(**kw), new.get_hic_matrix(**kw)
+        assert len(a) == len(b) and all(len(x) == len(y) for x, y in zip(a, b)), kw
+        if kw.get("normalized"):
+            np.testing.assert_allclose(np.array(b, dtype=float), np.array(a, dtype=float), rtol=1e-9, atol=0)
+        else:
+            assert a == b and all(isinstance(x, int) for x in b[0]), kw
+    for kw in (dict(focus=(4, hi), diagonal=False),):               # absolute indices into a window
+        outcome = []
+        for exp in (ref, new):
+            try:
+                outcome.append(exp.get_hic_matrix(**kw))
+            except IndexError as e:
+                outcome.append(str(e))
+        assert outcome[0] == outcome[1]
+    for kw in (dict(), dict(zeros=True)):
+        assert ref.print_hic_matrix(print_it=False, **kw) == new.print_hic_matrix(print_it=False, **kw)
+    ta = ref.print_hic_matrix(print_it=False, normalized=True, zeros=True).split()
+    tb = new.print_hic_matrix(print_it=False, normalized=True, zeros=True).split()
+    assert len(ta) == len(tb)
+    for x, y in zip(ta, tb):
+        assert x == y or abs(float(x) - float(y)) <= 1e-9 * abs(float(x))
+
+
 def test_pair_table_is_the_dictionary_of_dictionaries():
     from tadbit_b200.vectors import PairTable
     rows = np.array([0, 0, 2, 2, 2, 7])
