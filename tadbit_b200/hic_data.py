@@ -148,6 +148,7 @@ class HiC_data(object):
         self.compartments = {}
         self.last_trace = None
         self._pending = {}                                     # cells set since the store was built
+        self._stale = False                                    # chromosomes changed since then
         self._store = None
         self._device = 0
         self._new_store = ContactStore.from_coo
@@ -187,7 +188,7 @@ class HiC_data(object):
     # -- the resident store; cells set through ``hic[i, j] = v`` are folded in before it is used -----
     @property
     def store(self):
-        if self._pending:
+        if self._pending or self._stale:
             self._rebuild()
         return self._store
 
@@ -198,10 +199,16 @@ class HiC_data(object):
     def _rebuild(self):
         """Fold the pending cells into the host copy of the upper triangle and build the store anew
         (a store is immutable: its compact stream is laid out once)."""
+        if hasattr(self._store, "info"):
+            block = self._store.info()
+            if (block["row_begin"], block["row_end"]) != (0, self.__size):
+                raise NotImplementedError('the cells / chromosomes of a row-sharded matrix cannot be '
+                                          'changed: build the shards from the new data')
         if self._keys is None:
             r, c, v = self._store.export_upper()
             self._keys = r.astype(np.int64) * self.__size + c
             self._vals = v.astype(np.int64)
+        self._stale = False
         pend_k = np.fromiter(self._pending.keys(), dtype=np.int64, count=len(self._pending))
         pend_v = np.fromiter(self._pending.values(), dtype=np.int64, count=len(self._pending))
         self._pending = {}
@@ -231,7 +238,7 @@ class HiC_data(object):
         return self.__size
 
     def _host_cells(self):
-        if self._pending:
+        if self._pending or self._stale:
             self._rebuild()
         if self._keys is None:
             r, c, v = self.store.export_upper()
@@ -322,6 +329,43 @@ class HiC_data(object):
         cols = np.concatenate([j, i[od]])
         data = np.concatenate([vals, vals[od]]).astype(float)
         return csr_matrix((data, (rows, cols)), shape=(self.__size, self.__size))
+
+    def add_sections(self, lengths, chr_names=None, binned=False):
+        """
+        Add genomic coordinates to the object from a list of chromosome lengths; order matters
+        (hic_data.py:216-250).  The per-chromosome reductions (expected, decay, compartments) follow
+        the new chromosomes: the resident store is laid out again on the next use.
+
+        :param lengths: list of chromosome lengths
+        :param None chr_names: list of corresponding chromosome names
+        :param False binned: if True, lengths will not be divided by resolution
+        """
+        from warnings import warn
+        genome_seq = OrderedDict()
+        size = 0
+        resolution = 1 if binned else self.resolution
+        for crm, length in enumerate(lengths):
+            cnam = 'chr' + str(crm) if not chr_names else chr_names[crm]
+            genome_seq[cnam] = int(length) // resolution + 1
+            size += genome_seq[cnam]
+        if size != self.__size:
+            warn('WARNING: different sizes (%d, now:%d), ' % (self.__size, size)
+                 + 'should adjust the resolution')
+            # the reference goes on with a matrix whose size no longer matches its cells
+            raise ValueError('chromosomes of %d bins in all do not fit a matrix of %d bins'
+                             % (size, self.__size))
+        sections = [(crm, i) for crm in genome_seq for i in range(genome_seq[crm])]
+        self.chromosomes = genome_seq
+        self.sections = dict([(j, i) for i, j in enumerate(sections)])
+        # The nameless whole-matrix section of an object built without chromosomes goes: the
+        # reference keeps it next to the new chromosomes, and its `expected` then walks every
+        # diagonal once per entry (cells inside a chromosome are counted twice).
+        self.section_pos.pop(None, None)
+        total = 0
+        for crm in self.chromosomes:
+            self.section_pos[crm] = (total, total + self.chromosomes[crm])
+            total += self.chromosomes[crm]
+        self._stale = True
 
     # -- the accelerated path -------------------------------------------------------------
     def filter_columns(self, draw_hist=False, savefig=None, perc_zero=99,

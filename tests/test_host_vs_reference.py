@@ -377,3 +377,37 @@ def test_cli_column_biases_against_the_reference_lines(seed):
     except ZeroDivisionError:
         return
     assert ours.bads == badcol and bias is ours.bias and len(bias) == n
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_add_sections_against_the_reference(seed):
+    """HiC_data.add_sections (hic_data.py:216-250) on a matrix built without chromosomes: the
+    per-chromosome reductions follow the new chromosomes (expected, cis / trans ratio)."""
+    ns = ref_shim.load()
+    k = _random_case(31000 + seed)
+    rng = np.random.RandomState(seed)
+    n = k["n"]
+    k["sizes"], k["names"] = None, None
+    cuts = sorted(set(rng.randint(1, n, rng.randint(1, 4)).tolist()))
+    sizes = np.diff([0] + cuts + [n]).tolist()
+    names = ["c%d" % i for i in range(len(sizes))] if seed % 2 else None
+    ref, ours = _reference(ns, k), _product(k)
+    if seed % 3 == 0:                                   # objects that never had sections
+        ref.sections, ref.section_pos = None, {}
+        ours.sections, ours.section_pos = None, {}
+    for hic in (ref, ours):
+        hic.add_sections([s - 1 for s in sizes], chr_names=names, binned=True)    # bins = length // 1 + 1
+    assert ours.chromosomes == ref.chromosomes and ours.sections == ref.sections
+    # the reference keeps the nameless section of an object built without chromosomes (and then
+    # counts the cells inside chromosomes twice in `expected`); the product drops it
+    assert (None in ref.section_pos) == (seed % 3 != 0) and None not in ours.section_pos
+    ref.section_pos.pop(None, None)
+    assert ours.section_pos == ref.section_pos
+    for hic in (ref, ours):
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            hic.filter_columns(silent=True, perc_zero=k["perc_zero"], by_mean=k["by_mean"])
+            hic.normalize_expected()
+    assert ours.bads == ref.bads and ours.expected == ref.expected
+    assert ours.cis_trans_ratio() == ref.cis_trans_ratio()
+    with pytest.warns(UserWarning, match="different sizes"), pytest.raises(ValueError):
+        ours.add_sections([n + 5], binned=True)
