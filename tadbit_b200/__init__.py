@@ -14,9 +14,9 @@ from .hic_data import HiC_data, from_reference
 from .hic_filtering import filter_by_mean, filter_by_zero_count
 from .normalize_hic import expected, iterative
 from .store import CommGroup, ContactStore
-from .vectors import BinVector
+from .vectors import BinVector, PairTable
 
 __version__ = "0.1.0"
-__all__ = ["HiC_data", "from_reference", "ContactStore", "CommGroup", "SynthParams", "BinVector",
+__all__ = ["HiC_data", "from_reference", "ContactStore", "CommGroup", "SynthParams", "BinVector", "PairTable",
            "iterative", "expected", "filter_by_mean", "filter_by_zero_count",
            "device_count", "B200Error", "normalize_hic_batch", "batch_store", "ice_batch", "Experiment", "rescale_and_decay", "column_biases", "extraction"]
