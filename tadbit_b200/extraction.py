@@ -194,6 +194,8 @@ class _Cells(object):
                 decay = np.full(size, np.nan)
                 self.have_decay = np.zeros(size, dtype=bool)
                 for crm, (beg, end) in reg.section_pos.items():
+                    if end <= reg.rows[0] or beg >= reg.rows[1]:   # no row of the region in it
+                        continue
                     table = self.decay_table.get(crm, {})
                     if table:
                         d = np.fromiter(table.keys(), dtype=np.int64, count=len(table))
